@@ -1,0 +1,199 @@
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/<case>.npz.  Nothing is written into /root/reference.
+
+What is recorded per case: the reference's state_dict, the batch, every dropout
+mask in call order (mapped to the names oracle.Rand uses), the CPU attack noise
+(layers.py:917), and the reference's outputs: forward pair, losses, the
+per-parameter .grad after the two routed backward passes of trainer.py:672-686,
+full-sort scores / top-k / hit flags, predict scores.
+"""
+import os
+import sys
+import types
+import logging
+
+os.environ.setdefault('PYTHONDONTWRITEBYTECODE', '1')
+sys.dont_write_bytecode = True
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def import_reference():
+    for n in ('colorlog', 'colorama', 'thop'):
+        sys.modules[n] = types.ModuleType(n)
+    sys.modules['colorlog'].ColoredFormatter = lambda fmt, datefmt, log_colors=None: logging.Formatter(
+        fmt.replace('%(log_color)s', ''), datefmt)
+    sys.modules['colorama'].init = lambda **k: None
+    sys.modules['thop'].profile = None
+    if not hasattr(np, 'float'):
+        np.float = float
+    sys.path.insert(0, '/root/reference')
+    from recbole.model.sequential_recommender.acsasrec import ACSASRec
+    from recbole.data.interaction import Interaction
+    torch.autograd.set_detect_anomaly(False)      # sine.py:25 switches it on at import; arithmetic unaffected
+    return ACSASRec, Interaction
+
+
+class FakeDataset:
+    def __init__(self, n):
+        self.n = n
+
+    def num(self, field):
+        return self.n
+
+
+class Recorder:
+    """Replaces nn.Dropout.forward and torch.randn while the reference runs."""
+
+    def __init__(self, seed):
+        self.g = torch.Generator().manual_seed(seed)
+        self.masks, self.noises = [], []
+
+    def __enter__(self):
+        rec = self
+        self._fwd = torch.nn.Dropout.forward
+        self._randn = torch.randn
+
+        def fwd(mod, x):
+            if not mod.training or mod.p <= 0:
+                return x
+            keep = (torch.rand(x.shape, generator=rec.g) >= mod.p)
+            rec.masks.append(keep)
+            return x * keep.to(x.dtype) / (1.0 - mod.p)
+
+        def randn(*shape, **kw):
+            n = rec._randn(*shape, generator=rec.g)
+            rec.noises.append(n)
+            return n
+        torch.nn.Dropout.forward = fwd
+        torch.randn = randn
+        return self
+
+    def __exit__(self, *a):
+        torch.nn.Dropout.forward = self._fwd
+        torch.randn = self._randn
+
+
+def base_config(**kw):
+    from oracle.acsr_oracle import default_cfg
+    c = default_cfg(**kw)
+    c.update(USER_ID_FIELD='user_id', ITEM_ID_FIELD='item_id', LIST_SUFFIX='_list',
+             ITEM_LIST_LENGTH_FIELD='item_length', NEG_PREFIX='neg_', device='cpu')
+    return c
+
+
+def make_case(name, V, B, seed, train, k=50, **cfgkw):
+    from oracle.acsr_oracle import synth_batch
+    ACSASRec, Interaction = import_reference()
+    cfg = base_config(**cfgkw)
+    L = cfg['MAX_ITEM_LIST_LENGTH']
+    torch.manual_seed(seed)
+    model = ACSASRec(cfg, FakeDataset(V))
+    # make biases / LN non-trivial so the test exercises them (the init zeroes them)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('.bias'):
+                p.add_(torch.randn(p.shape, generator=g) * 0.02)
+            if 'LayerNorm.weight' in n:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    seq, ln, pos = synth_batch(B, L, V, seed=seed + 2)
+    ln[0] = L                                   # one full-length row
+    seq[0] = torch.randint(1, V, (L,), generator=g)
+    ln[1] = 1                                   # one minimal row
+    seq[1, 1:] = 0
+    inter = Interaction({'item_id_list': seq, 'item_length': ln, 'item_id': pos})
+    out = {'V': V, 'B': B, 'k': min(k, V - 1), 'train': int(train), 'seed': seed,
+           'item_id_list': seq.numpy(), 'item_length': ln.numpy(), 'item_id': pos.numpy()}
+    for kk, vv in cfgkw.items():
+        out['cfg.' + kk] = np.array(vv)
+    for n, p in model.state_dict().items():
+        out['param.' + n] = p.detach().numpy().copy()
+    model.train(train)
+    N = cfg['n_layers']
+    with Recorder(seed + 3) as rec:
+        if train:
+            l_att, l_cal = model.calculate_loss(inter)
+        else:
+            att, cal, Ms = model.forward(seq, ln)
+    # map recorded randomness to names
+    if train and (cfg['hidden_dropout_prob'] > 0 or cfg['attn_dropout_prob'] > 0):
+        assert cfg['hidden_dropout_prob'] > 0 and cfg['attn_dropout_prob'] > 0
+        assert len(rec.masks) == 1 + 7 * N, len(rec.masks)
+        out['rand.emb'] = rec.masks[0].numpy().astype(np.uint8)
+        for l in range(N):
+            for j, key in enumerate(('D1', 'D2', 'D3', 'D4', 'D5', 'D6', 'D7')):
+                out['rand.%d.%s' % (l, key)] = rec.masks[1 + 7 * l + j].numpy().astype(np.uint8)
+    assert len(rec.noises) == N
+    for l in range(N):
+        out['rand.%d.noise' % l] = rec.noises[l].numpy()
+    if train:
+        out['loss_att'] = l_att.detach().numpy()
+        out['loss_cal'] = l_cal.detach().numpy()
+        # trainer.py:672-686
+        def is_attack(n):
+            return 'attack_key_transform' in n or 'attack_query_transform' in n
+        for n, p in model.named_parameters():
+            p.requires_grad = not is_attack(n)
+        l_cal.backward(retain_graph=True)
+        for n, p in model.named_parameters():
+            p.requires_grad = is_attack(n)
+        l_att.backward()
+        for n, p in model.named_parameters():
+            p.requires_grad = True
+            gr = p.grad if p.grad is not None else torch.zeros_like(p)
+            out['grad.' + n] = gr.detach().numpy().copy()
+    else:
+        out['out_att'] = att.detach().numpy()
+        out['out_cal'] = cal.detach().numpy()
+        for l, M in enumerate(Ms):
+            out['pen_sq.%d' % l] = torch.sum((1 - M) ** 2).detach().numpy()
+        with Recorder(seed + 3):                  # same noise again
+            _, scores = model.full_sort_predict(inter)
+        scores = scores.detach().clone()
+        out['scores'] = scores.numpy().copy()
+        scores[:, 0] = -np.inf                    # trainer.py:942
+        _, idx = torch.topk(scores, out['k'], dim=-1)
+        out['topk_idx'] = idx.numpy()
+        pm = torch.zeros_like(scores, dtype=torch.int)
+        pm[torch.arange(B), pos] = 1              # collector.py:148-152
+        out['rec_topk'] = torch.cat((torch.gather(pm, 1, idx), pm.sum(1, keepdim=True)), 1).numpy()
+        with Recorder(seed + 3):
+            a_s, c_s = model.predict(inter)
+        out['predict_att'] = a_s.detach().numpy()
+        out['predict_cal'] = c_s.detach().numpy()
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **out)
+    print(name, os.path.getsize(path) // 1024, 'KB')
+
+
+CASES = [
+    # name, V, B, seed, train, cfg overrides
+    ('c1_eval', 301, 4, 11, False, {}),
+    ('c1_train', 301, 4, 12, True, {}),
+    ('c1_train_p0', 301, 4, 13, True, dict(hidden_dropout_prob=0.0, attn_dropout_prob=0.0)),
+    ('beauty_train', 257, 3, 14, True, dict(n_layers=3, n_heads=4, inner_size=128)),
+    ('beauty_eval', 257, 3, 15, False, dict(n_layers=3, n_heads=4, inner_size=128)),
+    ('pos_tw_train', 131, 3, 16, True, dict(n_layers=1, use_position_embedding=True,
+                                           trainable_mask_loss_weight=True)),
+    ('noorder_train', 131, 3, 17, True, dict(n_layers=1, use_order=False)),
+    ('nodist_train', 131, 3, 18, True, dict(n_layers=1, use_distance=False)),
+    ('fixed_onelevel_train', 131, 3, 19, True, dict(n_layers=2, combine_option='fixed', two_level=False,
+                                                   rich_calibrated_combine='fixed')),
+    ('relu_h8_eval', 131, 3, 20, False, dict(n_layers=1, n_heads=8, hidden_size=128, inner_size=64,
+                                             hidden_act='relu')),
+]
+
+if __name__ == '__main__':
+    only = set(sys.argv[1:])
+    for name, V, B, seed, train, kw in CASES:
+        if only and name not in only:
+            continue
+        make_case(name, V, B, seed, train, **kw)
