@@ -1,0 +1,20 @@
+"""ac-tsr_b200: B200-native (sm_100a) AC-SASRec training + full-sort evaluation hot path.
+
+Drop-in surface (names mirror the reference, AIM-SE/AC-TSR = RecBole 1.0.1 fork):
+    ACSASRec                      recbole/model/sequential_recommender/acsasrec.py
+    AttackRTransformerEncoder...  recbole/model/layers.py:614-1131
+    ACSASRecTrainer               recbole/trainer/trainer.py:505-1044
+    Config / Interaction          recbole/config/configurator.py, recbole/data/interaction.py
+All arithmetic runs in csrc/libacsr.so (C ABI: include/acsr.h).  No CPU fallback.
+
+The directory name contains a hyphen; import it as `ac_tsr_b200` (shim module at the repo root).
+"""
+from . import _lib, build, compat, data, evaluator, layers, ops, trainer, acsasrec    # noqa: F401
+from ._lib import LIB, AcsrError                                                      # noqa: F401
+from .acsasrec import ACSASRec                                                        # noqa: F401
+from .compat import Config, Interaction, ModelType                                    # noqa: F401
+from .layers import (AttackRMultiHeadAttention, AttackRTransformerEncoder,            # noqa: F401
+                     AttackRTransformerLayer, FeedForward)
+from .trainer import ACSASRecTrainer, FlatAdam                                        # noqa: F401
+
+__version__ = '0.1.0'

@@ -1,0 +1,440 @@
+// Full-catalogue logits  D[M,V] = out[M,64] . E[V,64]^T  on the 5th-gen tensor cores (tcgen05),
+// with the consumer fused into the TMEM epilogue so the [M,V] logits never reach HBM:
+//   MODE_STORE : plain scores (full_sort_predict)                  acsasrec.py:162-163
+//   MODE_CE    : per-row running (max, sum exp) -> cross entropy   acsasrec.py:118-120
+//   MODE_GRAD  : G = (softmax - onehot) * row_scale (CE backward)
+//   MODE_TOPK  : streaming per-row top-k, column 0 excluded         trainer.py:941-942, collector.py:147
+//
+// Warp-specialised persistent CTA (320 threads, one per SM):
+//   warp 0      producer : 1-D bulk async copies (TMA engine, cp.async.bulk -> UBLKCP) of 64-row
+//                          fp32 tiles of the item table into a shared-memory ring, mbarrier tx-count
+//   warps 2-5   splitter : fp32 tile -> (hi, lo) TF32 operands written in the canonical no-swizzle
+//                          K-major UMMA layout (8x16B core matrices); diagonal chunk rotation keeps
+//                          both the LDS and the STS bank-conflict free
+//   warp 1      MMA      : one thread issues tcgen05.mma.kind::tf32 128x64x8, 8 k-steps x {lo.hi,
+//                          hi.lo, hi.hi} (3xTF32: fp32-level accuracy) or 1 pass; accumulator in
+//                          TMEM, double buffered (2 x 64 columns); completion via tcgen05.commit
+//   warps 6-9   epilogue : tcgen05.ld 32 lanes x 32 columns -> one thread owns one logits row, so the
+//                          online softmax / top-k state is thread-private (no shuffles)
+// The activation tile A (128 x 64, hi and lo) is stationary in shared memory.
+#include "acsr_common.cuh"
+#include "../../include/acsr.h"
+
+namespace acsr {
+
+constexpr int kD = 64;                 // hidden size handled by ABI v1 of the tensor-core path
+constexpr int kBM = 128;               // rows per CTA tile  (UMMA M)
+constexpr int kBN = 64;                // catalogue rows per tile (UMMA N)
+constexpr int kKC = kD / 4;            // 16-byte K chunks per row
+constexpr int kTcThreads = 320;
+constexpr int kTmemCols = 128;         // 2 accumulator stages x 64 columns
+constexpr int kMaxTopK = 64;
+
+enum { MODE_STORE = 0, MODE_CE = 1, MODE_GRAD = 2, MODE_TOPK = 3 };
+
+struct LogitsParams {
+  const float* out;      // [M,64]
+  const float* table;    // [V,64]
+  int M;
+  long long V;
+  int passes;
+  int m_tiles, n_tiles, n_chunks;
+  // STORE / GRAD
+  float* C;
+  long long ldc;
+  const float* lse;
+  const long long* target;
+  const float* row_scale;
+  // CE
+  float* partial;        // [M, n_chunks, 2]
+  // TOPK
+  int k;
+  long long idx_offset;
+  int skip_col0;
+  float* pval;           // [M, n_chunks, k]
+  long long* pidx;
+};
+
+template <int MODE>
+struct TcCfg {
+  static constexpr int kStages = MODE == MODE_TOPK ? 2 : 4;
+  static constexpr int kAbytes = kBM * kD * 4;          // 32 KB per (hi|lo)
+  static constexpr int kBbytes = kBN * kD * 4;          // 16 KB per (hi|lo) per buffer
+  static constexpr int kOffAhi = 0;
+  static constexpr int kOffAlo = kOffAhi + kAbytes;
+  static constexpr int kOffBhi = kOffAlo + kAbytes;      // [2]
+  static constexpr int kOffBlo = kOffBhi + 2 * kBbytes;  // [2]
+  static constexpr int kOffStg = kOffBlo + 2 * kBbytes;  // [kStages]
+  static constexpr int kOffTopk = kOffStg + kStages * kBbytes;
+  static constexpr int kTopkBytes = MODE == MODE_TOPK ? 2 * kMaxTopK * kBM * 4 : 0;
+  static constexpr int kOffBar = kOffTopk + kTopkBytes;
+  static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 2;
+  static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
+};
+
+// thread-private sorted (descending) top-k list, slot-major so that lane == bank for every slot
+__device__ __noinline__ void topk_insert(float x, int col, float* lval, int* lidx, int row, int k, int& cnt, float& thr) {
+  int pos = cnt < k ? cnt++ : k - 1;
+  while (pos > 0 && lval[(pos - 1) * kBM + row] < x) {
+    lval[pos * kBM + row] = lval[(pos - 1) * kBM + row];
+    lidx[pos * kBM + row] = lidx[(pos - 1) * kBM + row];
+    --pos;
+  }
+  lval[pos * kBM + row] = x;
+  lidx[pos * kBM + row] = col;
+  if (cnt == k) thr = lval[(k - 1) * kBM + row];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsParams p) {
+  using Cfg = TcCfg<MODE>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x % p.m_tiles;
+  const int chunk = blockIdx.x / p.m_tiles;
+  const int my_tiles = chunk < p.n_tiles ? (p.n_tiles - chunk + p.n_chunks - 1) / p.n_chunks : 0;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+  uint64_t* stg_full = bars;
+  uint64_t* stg_empty = bars + Cfg::kStages;
+  uint64_t* op_full = bars + 2 * Cfg::kStages;
+  uint64_t* op_empty = op_full + 2;
+  uint64_t* tm_full = op_empty + 2;
+  uint64_t* tm_empty = tm_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(stg_full + s, 1); mbar_init(stg_empty + s, 128); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(op_full + s, 128); mbar_init(op_empty + s, 1);
+      mbar_init(tm_full + s, 1); mbar_init(tm_empty + s, 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+
+  // stationary A tile: rows of `out`, split into hi/lo TF32, canonical K-major layout
+  {
+    float* Ahi = reinterpret_cast<float*>(smem + Cfg::kOffAhi);
+    float* Alo = reinterpret_cast<float*>(smem + Cfg::kOffAlo);
+    for (int item = threadIdx.x; item < kBM * kKC; item += kTcThreads) {
+      const int r = item / kKC, kc = item % kKC;
+      const int grow = m_tile * kBM + r;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (grow < p.M) x = *reinterpret_cast<const float4*>(p.out + (long long)grow * kD + kc * 4);
+      float4 hi = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+      float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+      const int off = kc * (kBM * 4) + r * 4;      // floats: chunk plane of kBM rows x 16 B
+      *reinterpret_cast<float4*>(Ahi + off) = hi;
+      *reinterpret_cast<float4*>(Alo + off) = lo;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ producer ------------------------------
+    if (lane == 0) {
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        const long long n0 = (long long)(chunk + it * p.n_chunks) * kBN;
+        const long long rows = (p.V - n0) < kBN ? (p.V - n0) : kBN;
+        mbar_wait(stg_empty + s, ph ^ 1);
+        mbar_arrive_expect_tx(stg_full + s, (uint32_t)(rows * kD * 4));
+        bulk_g2s(smem + Cfg::kOffStg + s * Cfg::kBbytes, p.table + n0 * kD, (uint32_t)(rows * kD * 4), stg_full + s);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(kBM, kBN);
+      const uint32_t a_hi = smem_u32(smem + Cfg::kOffAhi), a_lo = smem_u32(smem + Cfg::kOffAlo);
+      constexpr uint32_t kALbo = kBM * 16, kBLbo = kBN * 16, kSbo = 128;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int ob = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(op_full + ob, ph);
+        mbar_wait(tm_empty + ob, ph ^ 1);
+        tc_fence_after();
+        const uint32_t b_hi = smem_u32(smem + Cfg::kOffBhi + ob * Cfg::kBbytes);
+        const uint32_t b_lo = smem_u32(smem + Cfg::kOffBlo + ob * Cfg::kBbytes);
+        const uint32_t d_tmem = tmem_base + ob * kBN;
+        uint32_t acc = 0;
+        const int npass = p.passes == 3 ? 3 : 1;
+        for (int ps = 0; ps < npass; ++ps) {
+          // small cross terms first, the dominant hi.hi product last
+          const uint32_t a_base = (npass == 3 && ps == 0) ? a_lo : a_hi;
+          const uint32_t b_base = (npass == 3 && ps == 1) ? b_lo : b_hi;
+#pragma unroll
+          for (int ks = 0; ks < kD / 8; ++ks) {
+            const uint64_t ad = umma_desc_kmajor(a_base + ks * 2 * kALbo, kALbo, kSbo);
+            const uint64_t bd = umma_desc_kmajor(b_base + ks * 2 * kBLbo, kBLbo, kSbo);
+            umma_tf32(d_tmem, ad, bd, idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(op_empty + ob);     // operand buffer may be overwritten once these MMAs retire
+        umma_commit(tm_full + ob);      // accumulator stage ready for the epilogue
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------ hi/lo splitter ------------------------------
+    const int tid = threadIdx.x - 64;   // 0..127
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % Cfg::kStages;
+      const uint32_t sph = (it / Cfg::kStages) & 1;
+      const int ob = it & 1;
+      const uint32_t oph = (it >> 1) & 1;
+      const long long n0 = (long long)(chunk + it * p.n_chunks) * kBN;
+      const int rows = (int)((p.V - n0) < kBN ? (p.V - n0) : kBN);
+      mbar_wait(stg_full + s, sph);
+      mbar_wait(op_empty + ob, oph ^ 1);
+      const float* stg = reinterpret_cast<const float*>(smem + Cfg::kOffStg + s * Cfg::kBbytes);
+      float* Bhi = reinterpret_cast<float*>(smem + Cfg::kOffBhi + ob * Cfg::kBbytes);
+      float* Blo = reinterpret_cast<float*>(smem + Cfg::kOffBlo + ob * Cfg::kBbytes);
+#pragma unroll
+      for (int q = 0; q < (kBN * kKC) / 128; ++q) {
+        const int item = q * 128 + tid;
+        const int r = item % kBN;
+        const int kc = (item / kBN + r) % kKC;      // diagonal rotation: conflict-free LDS and STS
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) x = *reinterpret_cast<const float4*>(stg + r * kD + kc * 4);
+        float4 hi = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+        float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+        const int off = kc * (kBN * 4) + r * 4;
+        *reinterpret_cast<float4*>(Bhi + off) = hi;
+        *reinterpret_cast<float4*>(Blo + off) = lo;
+      }
+      fence_proxy_async();               // generic-proxy stores -> visible to the tensor-core (async) proxy
+      mbar_arrive(op_full + ob);
+      mbar_arrive(stg_empty + s);
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const int grow = m_tile * kBM + row;
+    const bool row_ok = grow < p.M;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float run_m = -INFINITY, run_s = 0.f;         // MODE_CE
+    float g_lse = 0.f, g_scale = 0.f;             // MODE_GRAD
+    long long g_tgt = -1;
+    float* lval = reinterpret_cast<float*>(smem + Cfg::kOffTopk);           // [k][128]
+    int* lidx = reinterpret_cast<int*>(smem + Cfg::kOffTopk + kMaxTopK * kBM * 4);
+    int cnt = 0;
+    float thr = -INFINITY;
+    if (MODE == MODE_GRAD && row_ok) { g_lse = p.lse[grow]; g_scale = p.row_scale[grow]; g_tgt = p.target[grow]; }
+    for (int it = 0; it < my_tiles; ++it) {
+      const int ob = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const long long n0 = (long long)(chunk + it * p.n_chunks) * kBN;
+      mbar_wait(tm_full + ob, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < kBN / 32; ++cc) {
+        float v[32];
+        tmem_ld32(t_lane + ob * kBN + cc * 32, v);
+        const long long c0 = n0 + cc * 32;
+        const int nvalid = (int)((p.V - c0) < 32 ? ((p.V - c0) > 0 ? (p.V - c0) : 0) : 32);
+        if (MODE == MODE_STORE || MODE == MODE_GRAD) {
+          if (row_ok) {
+            if (MODE == MODE_GRAD) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float g = expf(v[i] - g_lse);
+                if (c0 + i == g_tgt) g -= 1.0f;
+                v[i] = g * g_scale;
+              }
+            }
+            float* dst = p.C + (long long)grow * p.ldc + c0;
+            if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < nvalid) dst[i] = v[i];
+            }
+          }
+        } else if (MODE == MODE_CE) {
+          if (nvalid > 0) {
+            float cm = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < nvalid) cm = fmaxf(cm, v[i]);
+            const float nm = fmaxf(run_m, cm);
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < nvalid) s += expf(v[i] - nm);
+            run_s = run_s * expf(run_m - nm) + s;
+            run_m = nm;
+          }
+        } else {   // MODE_TOPK
+          const int k = p.k;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = v[i];
+            if (i < nvalid && !(p.skip_col0 && c0 + i == 0) && (cnt < k || x > thr))
+              topk_insert(x, (int)(c0 + i), lval, lidx, row, k, cnt, thr);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tm_empty + ob);
+    }
+    if (MODE == MODE_CE && row_ok) {
+      float* o = p.partial + ((long long)grow * p.n_chunks + chunk) * 2;
+      o[0] = run_m; o[1] = run_s;
+    }
+    if (MODE == MODE_TOPK && row_ok) {
+      float* ov = p.pval + ((long long)grow * p.n_chunks + chunk) * p.k;
+      long long* oi = p.pidx + ((long long)grow * p.n_chunks + chunk) * p.k;
+      for (int s = 0; s < p.k; ++s) {
+        const bool ok = s < cnt;
+        ov[s] = ok ? lval[s * kBM + row] : -INFINITY;
+        oi[s] = ok ? (long long)lidx[s * kBM + row] + p.idx_offset : -1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---- CE finalize: single CTA, warp per row -------------------------------------------------
+__global__ void __launch_bounds__(1024) ce_finalize_kernel(const float* __restrict__ partial, int n_parts, const float* __restrict__ out,
+                                                           const float* __restrict__ table, const long long* __restrict__ target, int M,
+                                                           int d, long long V, long long idx_offset, int n_groups, float* __restrict__ lse,
+                                                           float* __restrict__ tgt_logit, float* __restrict__ row_loss, float* __restrict__ loss) {
+  __shared__ double gsum[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (threadIdx.x < 8) gsum[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int per_group = M / n_groups;
+  for (int m = warp; m < M; m += nw) {
+    float mx = -INFINITY;
+    for (int i = lane; i < n_parts; i += 32) mx = fmaxf(mx, partial[((long long)m * n_parts + i) * 2]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int i = lane; i < n_parts; i += 32) {
+      const float pm = partial[((long long)m * n_parts + i) * 2], ps = partial[((long long)m * n_parts + i) * 2 + 1];
+      if (ps > 0.f) s += ps * expf(pm - mx);
+    }
+    s = warp_sum(s);
+    const float l = mx + logf(s);
+    const long long t = target[m] - idx_offset;
+    float dot = 0.f;
+    if (t >= 0 && t < V)
+      for (int j = lane; j < d; j += 32) dot = fmaf(out[(long long)m * d + j], table[t * d + j], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      lse[m] = l; tgt_logit[m] = dot; row_loss[m] = l - dot;
+      atomicAdd(&gsum[m / per_group], (double)(l - dot));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_groups) loss[threadIdx.x] = (float)(gsum[threadIdx.x] / per_group);
+}
+
+static void plan(LogitsParams& p) {
+  p.m_tiles = (p.M + kBM - 1) / kBM;
+  p.n_tiles = (int)((p.V + kBN - 1) / kBN);
+  int nc = kNumSMs / (p.m_tiles > 0 ? p.m_tiles : 1);
+  if (nc < 1) nc = 1;
+  if (nc > p.n_tiles) nc = p.n_tiles;
+  p.n_chunks = nc;
+}
+
+template <int MODE>
+static int launch_tc(LogitsParams& p, cudaStream_t st, const char* who) {
+  using Cfg = TcCfg<MODE>;
+  static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
+  plan(p);
+  cudaError_t e = cudaFuncSetAttribute(logits_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) { set_error("%s: smem attr: %s", who, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
+  logits_tc_kernel<MODE><<<p.m_tiles * p.n_chunks, kTcThreads, Cfg::kSmemBytes, st>>>(p);
+  return check_launch(who);
+}
+
+static int validate_common(const float* out, const float* table, int M, long long V, int d, int passes, const char* who) {
+  ACSR_REQUIRE(out && table, "%s: NULL input", who);
+  ACSR_REQUIRE(M > 0 && V > 0, "%s: bad sizes M=%d V=%lld", who, M, V);
+  if (d != kD) { set_error("%s: hidden size %d unsupported by the tensor-core path in ABI v1 (64)", who, d); return ACSR_ERR_UNSUPPORTED; }
+  ACSR_REQUIRE(passes == 1 || passes == 3, "%s: passes must be 1 (TF32) or 3 (3xTF32)", who);
+  ACSR_REQUIRE(V < (1ll << 31), "%s: V too large", who);
+  return ACSR_OK;
+}
+
+}  // namespace acsr
+
+using namespace acsr;
+
+extern "C" {
+
+int acsr_logits_num_chunks(int M, int64_t V) {
+  LogitsParams p = {};
+  p.M = M; p.V = V;
+  if (M <= 0 || V <= 0) return 0;
+  plan(p);
+  return p.n_chunks;
+}
+
+int acsr_logits_store(const float* out, const float* table, int M, int64_t V, int d, int passes, float* scores, int64_t ldc,
+                      void* stream) {
+  int rc = validate_common(out, table, M, V, d, passes, "logits_store");
+  if (rc) return rc;
+  ACSR_REQUIRE(scores && ldc >= V, "logits_store: bad output");
+  LogitsParams p = {};
+  p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.C = scores; p.ldc = ldc;
+  return launch_tc<MODE_STORE>(p, (cudaStream_t)stream, "logits_store");
+}
+
+int acsr_logits_ce_partial(const float* out, const float* table, int M, int64_t V, int d, int passes, float* partial, void* stream) {
+  int rc = validate_common(out, table, M, V, d, passes, "logits_ce_partial");
+  if (rc) return rc;
+  ACSR_REQUIRE(partial, "logits_ce_partial: NULL output");
+  LogitsParams p = {};
+  p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.partial = partial;
+  return launch_tc<MODE_CE>(p, (cudaStream_t)stream, "logits_ce_partial");
+}
+
+int acsr_ce_finalize(const float* partial, int n_parts, const float* out, const float* table, const int64_t* target, int M, int d,
+                     int64_t V, int64_t idx_offset, int n_groups, float* lse, float* tgt_logit, float* row_loss, float* loss,
+                     void* stream) {
+  ACSR_REQUIRE(partial && out && table && target && lse && tgt_logit && row_loss && loss, "ce_finalize: NULL pointer");
+  ACSR_REQUIRE(M > 0 && n_parts > 0 && n_groups > 0 && n_groups <= 8 && M % n_groups == 0, "ce_finalize: bad sizes");
+  ce_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partial, n_parts, out, table, (const long long*)target, M, d, V,
+                                                          idx_offset, n_groups, lse, tgt_logit, row_loss, loss);
+  return check_launch("ce_finalize");
+}
+
+int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, const int64_t* target, const float* row_scale, int M,
+                        int64_t V, int d, int passes, float* G, int64_t ldg, void* stream) {
+  int rc = validate_common(out, table, M, V, d, passes, "logits_ce_grad");
+  if (rc) return rc;
+  ACSR_REQUIRE(lse && target && row_scale && G && ldg >= V, "logits_ce_grad: bad arguments");
+  LogitsParams p = {};
+  p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.C = G; p.ldc = ldg;
+  p.lse = lse; p.target = (const long long*)target; p.row_scale = row_scale;
+  return launch_tc<MODE_GRAD>(p, (cudaStream_t)stream, "logits_ce_grad");
+}
+
+int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_t V, int d, int passes, int k, int64_t idx_offset,
+                             int skip_col0, float* partial_val, int64_t* partial_idx, void* stream) {
+  int rc = validate_common(out, table, M, V, d, passes, "logits_topk_partial");
+  if (rc) return rc;
+  ACSR_REQUIRE(partial_val && partial_idx, "logits_topk_partial: NULL output");
+  if (k < 1 || k > kMaxTopK) { set_error("logits_topk_partial: k=%d unsupported (1..%d)", k, kMaxTopK); return ACSR_ERR_UNSUPPORTED; }
+  LogitsParams p = {};
+  p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes;
+  p.k = k; p.idx_offset = idx_offset; p.skip_col0 = skip_col0; p.pval = partial_val; p.pidx = (long long*)partial_idx;
+  return launch_tc<MODE_TOPK>(p, (cudaStream_t)stream, "logits_topk_partial");
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+"""Feeds of the hot path: synthetic Interaction-shaped batches and the two loaders
+the trainer iterates (recbole/data/dataloader/general_dataloader.py:23-65, 161-253, sequential branch).
+Only what AC-SASRec reads is carried: item_id_list int64[B,L], item_length int64[B], item_id int64[B]
+(the reference moves 5 more unused fields per step)."""
+import math
+
+import torch
+
+from .compat import Interaction
+
+
+def synth_sequences(n_rows, L, V, seed=42, full_len=False):
+    """lengths ~ clip(round(LogNormal(ln 7, 0.8)), 1, L); items Zipf(1) on [1, V-1]; right-padded with 0."""
+    g = torch.Generator().manual_seed(seed)
+    if full_len:
+        ln = torch.full((n_rows,), L, dtype=torch.int64)
+    else:
+        ln = torch.exp(torch.randn(n_rows, generator=g) * 0.8 + math.log(7.0)).round().clamp(1, L).to(torch.int64)
+    w = 1.0 / torch.arange(1, V, dtype=torch.float64)
+    items = torch.multinomial(w, n_rows * (L + 1), replacement=True, generator=g).view(n_rows, L + 1) + 1
+    seq = items[:, :L].clone()
+    seq[torch.arange(L).view(1, L) >= ln.view(n_rows, 1)] = 0
+    return seq, ln, items[:, L].clone()
+
+
+class SyntheticSequentialDataset(object):
+    """Stands in for SequentialDataset (recbole/data/dataset/sequential_dataset.py) with seeded synthetic rows."""
+
+    def __init__(self, config, n_rows, n_items, seed=42, full_len=False, pin=True):
+        self.config = config
+        self.item_num = int(n_items)
+        L = config['MAX_ITEM_LIST_LENGTH']
+        self.iid_field = config['ITEM_ID_FIELD']
+        self.uid_field = config['USER_ID_FIELD']
+        seq, ln, tgt = synth_sequences(n_rows, L, n_items, seed, full_len)
+        feat = {self.iid_field + config['LIST_SUFFIX']: seq, config['ITEM_LIST_LENGTH_FIELD']: ln, self.iid_field: tgt}
+        if pin and torch.cuda.is_available():
+            feat = {k: v.pin_memory() for k, v in feat.items()}
+        self.inter_feat = Interaction(feat)
+
+    def num(self, field):
+        if field == self.iid_field or field == self.iid_field + self.config['LIST_SUFFIX']:
+            return self.item_num
+        return len(self.inter_feat)
+
+    def __len__(self):
+        return len(self.inter_feat)
+
+
+class TrainDataLoader(object):
+    """general_dataloader.py:23-65: per-epoch CPU randperm shuffle, then contiguous batch slices."""
+
+    def __init__(self, config, dataset, shuffle=True, batch_size=None):
+        self.config, self.dataset, self.shuffle = config, dataset, shuffle
+        self.batch_size = batch_size or config['train_batch_size']
+        self.pr = 0
+
+    @property
+    def pr_end(self):
+        return len(self.dataset)
+
+    def __len__(self):
+        return math.ceil(self.pr_end / self.batch_size)
+
+    def __iter__(self):
+        if self.shuffle:
+            self.dataset.inter_feat.shuffle()
+            if torch.cuda.is_available():
+                self.dataset.inter_feat = Interaction({k: v.pin_memory() for k, v in self.dataset.inter_feat.interaction.items()})
+        return self
+
+    def __next__(self):
+        if self.pr >= self.pr_end:
+            self.pr = 0
+            raise StopIteration()
+        cur = self.dataset.inter_feat[self.pr:self.pr + self.batch_size]
+        self.pr += self.batch_size
+        return cur
+
+
+class FullSortEvalDataLoader(object):
+    """general_dataloader.py:246-253: (interaction, history_index=None, positive_u=arange(B), positive_i=item_id)."""
+
+    def __init__(self, config, dataset, batch_size=None):
+        self.config, self.dataset = config, dataset
+        self.batch_size = batch_size or config['eval_batch_size']
+        self.iid_field = config['ITEM_ID_FIELD']
+        self.pr = 0
+
+    @property
+    def pr_end(self):
+        return len(self.dataset)
+
+    def __len__(self):
+        return math.ceil(self.pr_end / self.batch_size)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.pr >= self.pr_end:
+            self.pr = 0
+            raise StopIteration()
+        interaction = self.dataset.inter_feat[self.pr:self.pr + self.batch_size]
+        n = len(interaction)
+        self.pr += self.batch_size
+        return interaction, None, torch.arange(n), interaction[self.iid_field]

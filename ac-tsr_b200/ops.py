@@ -1,0 +1,347 @@
+"""torch.autograd.Function wrappers over the C ABI (include/acsr.h).
+
+PyTorch is plumbing here: it owns device memory, the stream and the autograd tape; every op
+below launches hand-written sm_100a kernels from libacsr.so.  Tensors must be CUDA, contiguous,
+float32 (ids int64) -- anything else raises; there is no CPU or eager fallback.
+"""
+import torch
+
+from ._lib import LIB, AcsrError
+
+ACT_IDS = {'gelu': 0, 'relu': 1, 'swish': 2, 'tanh': 3, 'sigmoid': 4}
+COMBINE_IDS = {'gate': 0, 'fixed': 1, 'annealing': 2}
+RICH_IDS = {'none': 0, 'fixed': 1, 'trainable': 2}
+
+
+def _p(t, dtype=torch.float32):
+    """device pointer of a tensor (None -> NULL) after checking the ABI's layout contract."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise AcsrError('AC-SASRec hot path needs CUDA tensors (got %s); there is no CPU fallback' % t.device)
+    if t.dtype != dtype:
+        raise AcsrError('expected dtype %s, got %s' % (dtype, t.dtype))
+    if not t.is_contiguous():
+        raise AcsrError('tensor must be contiguous')
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _c(t):
+    return None if t is None else t.contiguous()
+
+
+class DeviceRng:
+    """{seed, step} in device memory; kernels read it so CUDA-graph replays draw fresh masks."""
+
+    def __init__(self, seed, device):
+        self.state = torch.tensor([int(seed) & 0x7fffffffffffffff, 0], dtype=torch.int64, device=device)
+
+    @property
+    def ptr(self):
+        return self.state.data_ptr()
+
+    def advance(self):
+        LIB.call('acsr_rng_advance', self.ptr, _stream())
+
+
+# ------------------------------------------------------------------------------------------
+class EmbedLnDropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, item_seq, table, pos_emb, ln_w, ln_b, eps, p, mask, rng, rng_stream):
+        B, L = item_seq.shape
+        V, d = table.shape
+        item_seq = item_seq.contiguous()
+        out = torch.empty((B, L, d), dtype=torch.float32, device=table.device)
+        stats = torch.empty((B * L, 2), dtype=torch.float32, device=table.device)
+        mask = _c(mask)
+        LIB.call('acsr_embed_ln_dropout_fwd', _p(item_seq, torch.int64), _p(table), _p(pos_emb), _p(ln_w), _p(ln_b),
+                 eps, B * L, L, d, V, p, _p(mask), rng.ptr if rng is not None else None, rng_stream,
+                 _p(out), _p(stats), _stream())
+        ctx.save_for_backward(item_seq, table, pos_emb, ln_w, stats, mask)
+        ctx.meta = (B, L, d, V, p, rng, rng_stream)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        item_seq, table, pos_emb, ln_w, stats, mask = ctx.saved_tensors
+        B, L, d, V, p, rng, rng_stream = ctx.meta
+        d_out = d_out.contiguous()
+        d_table = torch.zeros_like(table)
+        d_pos = torch.zeros_like(pos_emb) if pos_emb is not None else None
+        d_w = torch.zeros_like(ln_w)
+        d_b = torch.zeros_like(ln_w)
+        LIB.call('acsr_embed_ln_dropout_bwd', _p(d_out), _p(item_seq, torch.int64), _p(table), _p(pos_emb), _p(ln_w),
+                 _p(stats), B * L, L, d, V, p, _p(mask), rng.ptr if rng is not None else None, rng_stream,
+                 _p(d_table), _p(d_pos), _p(d_w), _p(d_b), _stream())
+        return None, d_table, d_pos, d_w, d_b, None, None, None, None, None
+
+
+class BiasDropoutResLnFn(torch.autograd.Function):
+    """LN(dropout(h + bias) + res)  -- layers.py:681-683 / 794-796."""
+
+    @staticmethod
+    def forward(ctx, h, bias, res, ln_w, ln_b, eps, p, mask, rng, rng_stream):
+        h, res, mask = h.contiguous(), res.contiguous(), _c(mask)
+        d = h.shape[-1]
+        T = h.numel() // d
+        out = torch.empty_like(h)
+        stats = torch.empty((T, 2), dtype=torch.float32, device=h.device)
+        LIB.call('acsr_bias_dropout_res_ln_fwd', _p(h), _p(bias), _p(res), _p(ln_w), _p(ln_b), eps, T, d, p, _p(mask),
+                 rng.ptr if rng is not None else None, rng_stream, _p(out), _p(stats), _stream())
+        ctx.save_for_backward(h, bias, res, ln_w, stats, mask)
+        ctx.meta = (T, d, p, rng, rng_stream)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        h, bias, res, ln_w, stats, mask = ctx.saved_tensors
+        T, d, p, rng, rng_stream = ctx.meta
+        d_out = d_out.contiguous()
+        d_h = torch.empty_like(h)
+        d_res = torch.empty_like(h)
+        d_bias = torch.zeros_like(bias) if bias is not None else None
+        d_w = torch.zeros_like(ln_w)
+        d_b = torch.zeros_like(ln_w)
+        LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_out), _p(h), _p(bias), _p(res), _p(ln_w), _p(stats), T, d, p,
+                 _p(mask), rng.ptr if rng is not None else None, rng_stream, _p(d_h), _p(d_res), _p(d_bias), _p(d_w),
+                 _p(d_b), _stream())
+        return d_h, d_bias, d_res, d_w, d_b, None, None, None, None, None
+
+
+class BiasActFn(torch.autograd.Function):
+    """act(h + bias)  -- layers.py:776-792."""
+
+    @staticmethod
+    def forward(ctx, h, bias, act):
+        h = h.contiguous()
+        n = h.shape[-1]
+        T = h.numel() // n
+        out = torch.empty_like(h)
+        LIB.call('acsr_bias_act_fwd', _p(h), _p(bias), T, n, act, _p(out), _stream())
+        ctx.save_for_backward(h, bias)
+        ctx.meta = (T, n, act)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        h, bias = ctx.saved_tensors
+        T, n, act = ctx.meta
+        d_out = d_out.contiguous()
+        d_h = torch.empty_like(h)
+        d_bias = torch.zeros_like(bias) if bias is not None else None
+        LIB.call('acsr_bias_act_bwd', _p(d_out), _p(h), _p(bias), T, n, act, _p(d_h), _p(d_bias), _stream())
+        return d_h, d_bias, None
+
+
+class GatherLastFn(torch.autograd.Function):
+    """rows [0,B) = x_att[b, len-1], rows [B,2B) = x_cal[b, len-1]  (abstract_recommender.py:130-134)."""
+
+    @staticmethod
+    def forward(ctx, x_att, x_cal, item_len):
+        B, L, d = x_cal.shape
+        x_cal = x_cal.contiguous()
+        x_att = _c(x_att)
+        item_len = item_len.contiguous()
+        rows = 2 * B if x_att is not None else B
+        out = torch.empty((rows, d), dtype=torch.float32, device=x_cal.device)
+        LIB.call('acsr_gather_last_fwd', _p(x_att), _p(x_cal), _p(item_len, torch.int64), B, L, d, _p(out), _stream())
+        ctx.save_for_backward(item_len)
+        ctx.meta = (B, L, d, x_att is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (item_len,) = ctx.saved_tensors
+        B, L, d, has_att = ctx.meta
+        d_out = d_out.contiguous()
+        d_cal = torch.zeros((B, L, d), dtype=torch.float32, device=d_out.device)
+        d_att = torch.zeros_like(d_cal) if has_att else None
+        LIB.call('acsr_gather_last_bwd', _p(d_out), _p(item_len, torch.int64), B, L, d, _p(d_att), _p(d_cal), _stream())
+        return d_att, d_cal, None
+
+
+class AttnOpts:
+    """static options of one fused-attention call (mirrors the AttackR* constructor flags)."""
+
+    def __init__(self, n_heads, two_level, combine_option, rich_mode, p_attn):
+        self.n_heads = n_heads
+        self.two_level = int(bool(two_level))
+        self.combine = COMBINE_IDS[combine_option]
+        self.rich = RICH_IDS.get(rich_mode, 0)
+        self.p_attn = float(p_attn)
+
+
+class AttnCalibFn(torch.autograd.Function):
+    """fused spatial + adversarial calibrated attention; returns (ctx_att|None, ctx_cal, pen_sq)."""
+
+    @staticmethod
+    def forward(ctx, mq, mk, mv, aq, ak, gate_logit, key_ids, order_w, order_b, dist_w, dist_b, scalar, rich_ratio,
+                opts, comb_scalar, p_attn, rand, rng, rng_stream, need_att, want_probs):
+        B, L, d = mq.shape
+        H = opts.n_heads
+        dh = d // H
+        ctx.set_materialize_grads(False)     # unused outputs arrive as None -> the kernel skips that branch
+        mq, mk, mv, aq, ak = (t.contiguous() for t in (mq, mk, mv, aq, ak))
+        gate_logit = _c(gate_logit)
+        key_ids = key_ids.contiguous()
+        D1, D2, D3, noise = (_c(rand.get(k)) if rand else None for k in ('D1', 'D2', 'D3', 'noise'))
+        dev = mq.device
+        ctx_cal = torch.empty((B, L, d), dtype=torch.float32, device=dev)
+        ctx_att = torch.empty_like(ctx_cal) if need_att else None
+        pen = torch.zeros(1, dtype=torch.float64, device=dev)
+        probs = torch.empty((6, B, H, L, L), dtype=torch.float32, device=dev) if want_probs else None
+        rngp = rng.ptr if rng is not None else None
+        LIB.call('acsr_attn_calib_fwd', _p(mq), _p(mk), _p(mv), _p(aq), _p(ak), _p(gate_logit), _p(key_ids, torch.int64),
+                 _p(order_w), _p(order_b), _p(dist_w), _p(dist_b), _p(scalar), B, L, H, dh,
+                 opts.two_level, opts.combine, float(comb_scalar), opts.rich, _p(rich_ratio),
+                 p_attn, _p(D1), _p(D2), _p(D3), _p(noise), rngp, rng_stream,
+                 _p(ctx_att), _p(ctx_cal), pen.data_ptr(), _p(probs), _stream())
+        ctx.save_for_backward(mq, mk, mv, aq, ak, gate_logit, key_ids, order_w, order_b, dist_w, dist_b, scalar, rich_ratio,
+                              D1, D2, D3, noise)
+        ctx.meta = (B, L, H, dh, opts, float(comb_scalar), p_attn, rng, rng_stream, need_att)
+        pen32 = pen.to(torch.float32)
+        ctx.mark_non_differentiable(*([probs] if probs is not None else []))
+        return ctx_att, ctx_cal, pen32, probs
+
+    @staticmethod
+    def backward(ctx, d_att, d_cal, d_pen, _d_probs):
+        (mq, mk, mv, aq, ak, gate_logit, key_ids, order_w, order_b, dist_w, dist_b, scalar, rich_ratio,
+         D1, D2, D3, noise) = ctx.saved_tensors
+        B, L, H, dh, opts, comb_scalar, p_attn, rng, rng_stream, need_att = ctx.meta
+        d_att = _c(d_att) if need_att else None
+        d_cal = _c(d_cal)
+        d_pen = _c(d_pen)
+        z = torch.zeros_like
+        d_mq, d_mk, d_mv, d_aq, d_ak = (torch.empty_like(mq) for _ in range(5))
+        d_gate = z(gate_logit) if gate_logit is not None else None
+        d_ow = z(order_w) if order_w is not None else None
+        d_ob = z(order_b) if order_b is not None else None
+        d_dw = z(dist_w) if dist_w is not None else None
+        d_db = z(dist_b) if dist_b is not None else None
+        d_sc = z(scalar) if scalar is not None else None
+        d_rr = z(rich_ratio) if rich_ratio is not None else None
+        LIB.call('acsr_attn_calib_bwd', _p(d_att), _p(d_cal), _p(d_pen), _p(mq), _p(mk), _p(mv), _p(aq), _p(ak),
+                 _p(gate_logit), _p(key_ids, torch.int64), _p(order_w), _p(order_b), _p(dist_w), _p(dist_b), _p(scalar),
+                 B, L, H, dh, opts.two_level, opts.combine, comb_scalar, opts.rich, _p(rich_ratio),
+                 p_attn, _p(D1), _p(D2), _p(D3), _p(noise), rng.ptr if rng is not None else None, rng_stream,
+                 _p(d_mq), _p(d_mk), _p(d_mv), _p(d_aq), _p(d_ak), _p(d_gate), _p(d_ow), _p(d_ob), _p(d_dw), _p(d_db),
+                 _p(d_sc), _p(d_rr), _stream())
+        return (d_mq, d_mk, d_mv, d_aq, d_ak, d_gate, None, d_ow, d_ob, d_dw, d_db, d_sc, d_rr,
+                None, None, None, None, None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------
+# full-catalogue logits on tcgen05
+# ------------------------------------------------------------------------------------------
+def logits_num_chunks(M, V):
+    return LIB.query('acsr_logits_num_chunks', int(M), int(V))
+
+
+def ce_partial(out, table, passes=3):
+    """-> partial [M, n_chunks, 2] (max, sumexp) over this table (shard)."""
+    M, d = out.shape
+    V = table.shape[0]
+    part = torch.empty((M, logits_num_chunks(M, V), 2), dtype=torch.float32, device=out.device)
+    LIB.call('acsr_logits_ce_partial', _p(out), _p(table), M, V, d, passes, _p(part), _stream())
+    return part
+
+
+def ce_finalize(partial, out, table, target, n_groups, idx_offset=0):
+    M, d = out.shape
+    dev = out.device
+    lse = torch.empty(M, dtype=torch.float32, device=dev)
+    tgt = torch.empty_like(lse)
+    row_loss = torch.empty_like(lse)
+    loss = torch.empty(n_groups, dtype=torch.float32, device=dev)
+    LIB.call('acsr_ce_finalize', _p(partial), partial.shape[1], _p(out), _p(table), _p(target, torch.int64), M, d,
+             table.shape[0], idx_offset, n_groups, _p(lse), _p(tgt), _p(row_loss), _p(loss), _stream())
+    return lse, tgt, row_loss, loss
+
+
+def ce_grad_matrix(out, table, lse, target, row_scale, passes=3):
+    """G [M, V] (row stride padded to 4) = (softmax - onehot) * row_scale."""
+    M, d = out.shape
+    V = table.shape[0]
+    ld = (V + 3) // 4 * 4
+    G = torch.empty((M, ld), dtype=torch.float32, device=out.device)
+    LIB.call('acsr_logits_ce_grad', _p(out), _p(table), _p(lse), _p(target, torch.int64), _p(row_scale), M, V, d, passes,
+             _p(G), ld, _stream())
+    return G[:, :V]
+
+
+class LogitsCEFn(torch.autograd.Function):
+    """loss[g] = mean CE over row group g of softmax(out.E^T) vs target -- acsasrec.py:117-121.
+    Logits never materialise in the forward; the backward writes G once and uses two GEMMs."""
+
+    @staticmethod
+    def forward(ctx, out, table, target, n_groups, passes):
+        out, table, target = out.contiguous(), table.contiguous(), target.contiguous()
+        part = ce_partial(out, table, passes)
+        lse, _, _, loss = ce_finalize(part, out, table, target, n_groups)
+        ctx.save_for_backward(out, table, target, lse)
+        ctx.meta = (n_groups, passes)
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        out, table, target, lse = ctx.saved_tensors
+        n_groups, passes = ctx.meta
+        M = out.shape[0]
+        per = M // n_groups
+        row_scale = (d_loss.to(torch.float32) / per).view(n_groups, 1).expand(n_groups, per).reshape(-1)
+        G = ce_grad_matrix(out, table, lse, target, row_scale, passes)
+        d_out = G @ table if ctx.needs_input_grad[0] else None
+        d_table = G.t() @ out if ctx.needs_input_grad[1] else None
+        return d_out, d_table, None, None, None
+
+
+def logits_scores(out, table, passes=3):
+    """scores [M,V] = out.E^T (contiguous)  -- acsasrec.py:162-163."""
+    out, table = out.contiguous(), table.contiguous()
+    M, d = out.shape
+    V = table.shape[0]
+    scores = torch.empty((M, V), dtype=torch.float32, device=out.device)
+    LIB.call('acsr_logits_store', _p(out), _p(table), M, V, d, passes, _p(scores), V, _stream())
+    return scores
+
+
+def logits_topk_partial(out, table, k, idx_offset=0, skip_col0=True, passes=3):
+    out, table = out.contiguous(), table.contiguous()
+    M, d = out.shape
+    V = table.shape[0]
+    nc = logits_num_chunks(M, V)
+    pv = torch.empty((M, nc, k), dtype=torch.float32, device=out.device)
+    pi = torch.empty((M, nc, k), dtype=torch.int64, device=out.device)
+    LIB.call('acsr_logits_topk_partial', _p(out), _p(table), M, V, d, passes, k, idx_offset, int(skip_col0),
+             _p(pv), _p(pi, torch.int64), _stream())
+    return pv, pi
+
+
+def topk_merge(pv, pi, k, positive=None):
+    """-> (val [M,k], idx [M,k] int64, rec_topk [M,k+1] int32 | None)."""
+    M = pv.shape[0]
+    pv = pv.reshape(M, -1, k).contiguous()
+    pi = pi.reshape(M, -1, k).contiguous()
+    dev = pv.device
+    val = torch.empty((M, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((M, k), dtype=torch.int64, device=dev)
+    rec = torch.empty((M, k + 1), dtype=torch.int32, device=dev) if positive is not None else None
+    LIB.call('acsr_topk_merge', _p(pv), _p(pi, torch.int64), M, pv.shape[1], k,
+             _p(positive.contiguous(), torch.int64) if positive is not None else None,
+             _p(val), _p(idx, torch.int64), _p(rec, torch.int32), _stream())
+    return val, idx, rec
+
+
+def full_sort_topk(out, table, k, positive=None, passes=3):
+    """fused scores -> scores[:,0]=-inf -> top-k -> hit flags (trainer.py:941-942, collector.py:147-153)."""
+    pv, pi = logits_topk_partial(out, table, k, 0, True, passes)
+    return topk_merge(pv, pi, k, positive)
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step_count, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+    LIB.call('acsr_adam_step', _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, beta1, beta2, eps,
+             weight_decay, _p(step_count, torch.int64), _stream())

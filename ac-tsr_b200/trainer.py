@@ -1,0 +1,347 @@
+"""ACSASRecTrainer -- drop-in for recbole/trainer/trainer.py:505-1044 (AttackSASRecTrainer /
+ACSASRecTrainer) restricted to what AC-SASRec uses: the adversarial two-loss step (:660-687), the
+full-sort evaluation driver (:926-945, :964-1019) with the collector's top-k (evaluator/collector.py:
+145-153), early stopping and the checkpoint format (:710-761, :809-924).
+
+B200-native choices: parameters, gradients and Adam moments live in three flat fp32 buffers so the
+optimizer is ONE fused kernel and zero_grad ONE memset; the whole step (H2D'd batch -> both losses ->
+both routed backward passes -> Adam) is captured once in a CUDA graph and replayed, with dropout /
+noise streams advanced on the device; evaluation uses the fused logits+top-k kernel, so neither
+the [B,V] scores nor the [B,V] int pos_matrix of the reference exist.
+"""
+import os
+import time
+from logging import getLogger
+
+import numpy as np
+import torch
+
+from . import ops
+from .compat import Interaction, cfg_get
+from .evaluator import Evaluator
+
+ATTACK_KEYS = ('attack_key_transform', 'attack_query_transform')      # trainer.py:673
+
+
+def is_attack_param(name):
+    return any(k in name for k in ATTACK_KEYS)
+
+
+def early_stopping(value, best, cur_step, max_step, bigger=True):
+    """recbole/utils/utils.py:103-144."""
+    stop_flag = update_flag = False
+    better = value >= best if bigger else value <= best
+    if better:
+        cur_step, best, update_flag = 0, value, True
+    else:
+        cur_step += 1
+        if cur_step > max_step:
+            stop_flag = True
+    return best, cur_step, stop_flag, update_flag
+
+
+class FlatAdam(object):
+    """torch.optim.Adam semantics (trainer.py:614-615) over flat buffers; step() is one fused kernel."""
+
+    def __init__(self, model, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+        params = [p for p in model.parameters()]
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                self.flat_param[off:off + k].copy_(p.data.reshape(-1))
+                p.data = self.flat_param[off:off + k].view(p.shape)
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+                off += k
+        self.lr, self.weight_decay, self.betas, self.eps = float(lr), float(weight_decay or 0.0), betas, eps
+        self.params = params
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+
+    def step(self):
+        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
+                      self.betas[0], self.betas[1], self.eps, self.weight_decay)
+
+    def state_dict(self):
+        return {'flat_adam': True, 'exp_avg': self.exp_avg.cpu(), 'exp_avg_sq': self.exp_avg_sq.cpu(),
+                'step': int(self.step_count.item()), 'lr': self.lr, 'weight_decay': self.weight_decay}
+
+    def load_state_dict(self, sd):
+        if not sd.get('flat_adam'):
+            raise ValueError('optimizer state was not written by FlatAdam')
+        self.exp_avg.copy_(sd['exp_avg'])
+        self.exp_avg_sq.copy_(sd['exp_avg_sq'])
+        self.step_count.fill_(sd['step'])
+
+
+class ACSASRecTrainer(object):
+    def __init__(self, config, model):
+        self.config, self.model = config, model
+        self.logger = getLogger()
+        self.learner = cfg_get(config, 'learner', 'adam')
+        self.learning_rate = config['learning_rate']
+        self.epochs = config['epochs']
+        self.eval_step = min(cfg_get(config, 'eval_step', 1), self.epochs)
+        self.stopping_step = cfg_get(config, 'stopping_step', 10)
+        self.clip_grad_norm = config['clip_grad_norm']
+        self.valid_metric = str(cfg_get(config, 'valid_metric', 'MRR@10')).lower()
+        self.valid_metric_bigger = cfg_get(config, 'valid_metric_bigger', True)
+        self.test_batch_size = config['eval_batch_size']
+        self.device = config['device']
+        self.checkpoint_dir = cfg_get(config, 'checkpoint_dir', 'saved')
+        os.makedirs(self.checkpoint_dir, exist_ok=True)
+        self.saved_model_file = os.path.join(self.checkpoint_dir, '{}-{}.pth'.format(
+            cfg_get(config, 'model', 'ACSASRec'), time.strftime('%b-%d-%Y_%H-%M-%S')))
+        self.weight_decay = cfg_get(config, 'weight_decay', 0.0)
+        self.start_epoch, self.cur_step = 0, 0
+        self.best_valid_score = -np.inf if self.valid_metric_bigger else np.inf
+        self.best_valid_result = None
+        self.train_loss_dict = dict()
+        self.optimizer = self._build_optimizer()
+        self.evaluator = Evaluator(config)
+        self.topk = list(config['topk'])
+        self.tot_item_num = None
+        self.use_graph = bool(cfg_get(config, 'cuda_graph', True))
+        self.fused_topk = bool(cfg_get(config, 'fused_topk', True))
+        self._graph = None
+        self.nan_check_interval = int(cfg_get(config, 'nan_check_interval', 50))
+        self.logger.info('use attack trainer!!!')
+
+    # ------------------------------------------------------------------------------------------
+    def _build_optimizer(self, **kwargs):
+        learner = str(kwargs.pop('learner', self.learner)).lower()
+        lr = kwargs.pop('learning_rate', self.learning_rate)
+        wd = kwargs.pop('weight_decay', self.weight_decay)
+        if learner == 'adam':
+            return FlatAdam(self.model, lr, wd)
+        import torch.optim as optim         # other learners are outside the hot path: library optimizers
+        params = self.model.parameters()
+        if learner == 'sgd':
+            return optim.SGD(params, lr=lr, weight_decay=wd or 0.0)
+        if learner == 'adagrad':
+            return optim.Adagrad(params, lr=lr, weight_decay=wd or 0.0)
+        if learner == 'rmsprop':
+            return optim.RMSprop(params, lr=lr, weight_decay=wd or 0.0)
+        self.logger.warning('Received unrecognized optimizer, set default Adam optimizer')
+        return FlatAdam(self.model, lr, 0.0)
+
+    def _route(self, attack):
+        for name, p in self.model.named_parameters():
+            p.requires_grad = is_attack_param(name) == attack
+
+    def _step_body(self, interaction):
+        """trainer.py:660-687 without the host syncs: -> (attacked_loss, calibrated_loss) tensors."""
+        self.optimizer.zero_grad()
+        attacked_loss, calibrated_loss = self.model.calculate_loss(interaction)
+        self._route(attack=False)
+        calibrated_loss.backward(retain_graph=True)
+        if attacked_loss is not None:
+            self._route(attack=True)
+            attacked_loss.backward()
+        for p in self.model.parameters():
+            p.requires_grad = True
+        if self.clip_grad_norm:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
+        self.optimizer.step()
+        return attacked_loss.detach(), calibrated_loss.detach()
+
+    def train_step(self, interaction):
+        """One optimisation step on a device-resident Interaction (eager launch path)."""
+        return self._step_body(interaction)
+
+    # -------- CUDA-graph replay of the whole step ----------------------------------------------
+    def _graph_key(self, interaction):
+        return tuple((k, tuple(interaction[k].shape)) for k in self._fields())
+
+    def _fields(self):
+        m = self.model
+        f = [m.ITEM_SEQ, m.ITEM_SEQ_LEN, m.POS_ITEM_ID]
+        if m.loss_type == 'BPR':
+            f.append(m.NEG_ITEM_ID)
+        return f
+
+    def _capture(self, interaction):
+        dev = self.device
+        static = {k: torch.empty_like(interaction[k], device=dev) for k in self._fields()}
+        for k in static:
+            static[k].copy_(interaction[k])
+        static_inter = Interaction(static)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up on a side stream (allocator + lazy inits), state restored after
+            snap = (self.optimizer.flat_param.clone(), self.optimizer.exp_avg.clone(), self.optimizer.exp_avg_sq.clone(),
+                    self.optimizer.step_count.clone(), self.model._rng.state.clone() if self.model._rng else None)
+            for _ in range(2):
+                self._step_body(static_inter)
+            self.optimizer.flat_param.copy_(snap[0]); self.optimizer.exp_avg.copy_(snap[1])
+            self.optimizer.exp_avg_sq.copy_(snap[2]); self.optimizer.step_count.copy_(snap[3])
+            if snap[4] is not None:
+                self.model._rng.state.copy_(snap[4])
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            la, lc = self._step_body(static_inter)
+        self._graph = dict(graph=g, static=static, key=self._graph_key(interaction), la=la, lc=lc)
+
+    def graphed_step(self, interaction):
+        """interaction: host (pinned) or device tensors of the captured shape.  Copies the batch into the
+        static buffers on the current stream and replays the captured step."""
+        if self._graph is None or self._graph['key'] != self._graph_key(interaction):
+            if self._graph is not None:
+                return self._step_body(interaction.to(self.device))      # ragged last batch: eager launch
+            self._capture(interaction)
+        st = self._graph['static']
+        for k in st:
+            st[k].copy_(interaction[k], non_blocking=True)
+        self._graph['graph'].replay()
+        return self._graph['la'], self._graph['lc']
+
+    # ------------------------------------------------------------------------------------------
+    def _check_nan(self, loss):
+        if torch.isnan(loss):
+            raise ValueError('Training loss is nan')
+
+    def _train_epoch(self, train_data, epoch_idx, loss_func=None, show_progress=False, attack=True, calibrate=True):
+        assert attack or calibrate
+        self.model.train()
+        tot_a = torch.zeros((), dtype=torch.float64, device=self.device)
+        tot_c = torch.zeros((), dtype=torch.float64, device=self.device)
+        graph_ok = self.use_graph and isinstance(self.optimizer, FlatAdam) and not self.clip_grad_norm
+        for batch_idx, interaction in enumerate(train_data):
+            if graph_ok:
+                la, lc = self.graphed_step(interaction)
+            else:
+                la, lc = self.train_step(interaction.to(self.device))
+            tot_a += la
+            tot_c += lc
+            if self.nan_check_interval and (batch_idx + 1) % self.nan_check_interval == 0:
+                self._check_nan(tot_a + tot_c)
+        self._check_nan(tot_a + tot_c)
+        return float(tot_a.item()), float(tot_c.item())
+
+    def _valid_epoch(self, valid_data, show_progress=False):
+        valid_result = self.evaluate(valid_data, load_best_model=False, show_progress=show_progress)
+        return valid_result[self.valid_metric] if self.valid_metric else valid_result['recall@10'], valid_result
+
+    def _save_checkpoint(self, epoch, verbose=True, **kwargs):
+        """trainer.py:710-731 (same keys)."""
+        saved_model_file = kwargs.pop('saved_model_file', self.saved_model_file)
+        state = {
+            'config': self.config, 'epoch': epoch, 'cur_step': self.cur_step, 'best_valid_score': self.best_valid_score,
+            'state_dict': {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
+            'other_parameter': self.model.other_parameter(), 'optimizer': self.optimizer.state_dict(),
+        }
+        torch.save(state, saved_model_file)
+        if verbose:
+            self.logger.info('Saving current: %s' % saved_model_file)
+
+    def _load_state(self, state_dict):
+        with torch.no_grad():               # copy in place: parameters are views of the flat buffer
+            own = self.model.state_dict()
+            missing = set(own) - set(state_dict)
+            if missing:
+                raise KeyError('missing keys in checkpoint: %s' % sorted(missing))
+            for k, v in own.items():
+                v.copy_(state_dict[k])
+
+    def resume_checkpoint(self, resume_file):
+        """trainer.py:733-761."""
+        resume_file = str(resume_file)
+        self.saved_model_file = resume_file
+        checkpoint = torch.load(resume_file, map_location='cpu', weights_only=False)
+        self.start_epoch = checkpoint['epoch'] + 1
+        self.cur_step = checkpoint['cur_step']
+        self.best_valid_score = checkpoint['best_valid_score']
+        self._load_state(checkpoint['state_dict'])
+        self.model.load_other_parameter(checkpoint.get('other_parameter'))
+        self.optimizer.load_state_dict(checkpoint['optimizer'])
+        self.logger.info('Checkpoint loaded. Resume training from epoch {}'.format(self.start_epoch))
+
+    def fit(self, train_data, valid_data=None, verbose=True, saved=True, show_progress=False, callback_fn=None):
+        """trainer.py:809-924 (epoch range 2*epochs, eval every eval_step, early stopping, checkpoint on improvement)."""
+        if saved and self.start_epoch >= self.epochs:
+            self._save_checkpoint(-1, verbose=verbose)
+        for epoch_idx in range(self.start_epoch, 2 * self.epochs):
+            t0 = time.time()
+            a, c = self._train_epoch(train_data, epoch_idx, show_progress=show_progress)
+            self.train_loss_dict[epoch_idx] = (a, c)
+            t1 = time.time()
+            if verbose:
+                des = self.config['loss_decimal_place'] or 4
+                self.logger.info(('epoch %d training [time: %.2fs, train loss: %.' + str(des) + 'f]') % (epoch_idx, t1 - t0, a))
+                self.logger.info(('epoch %d training [time: %.2fs, train loss: %.' + str(des) + 'f]') % (epoch_idx, t1 - t0, c))
+            if self.eval_step <= 0 or not valid_data:
+                if saved:
+                    self._save_checkpoint(epoch_idx, verbose=verbose)
+                continue
+            if (epoch_idx + 1) % self.eval_step == 0:
+                v0 = time.time()
+                valid_score, valid_result = self._valid_epoch(valid_data, show_progress=show_progress)
+                self.best_valid_score, self.cur_step, stop_flag, update_flag = early_stopping(
+                    valid_score, self.best_valid_score, self.cur_step, max_step=self.stopping_step,
+                    bigger=self.valid_metric_bigger)
+                if verbose:
+                    self.logger.info('epoch %d evaluating [time: %.2fs, valid_score: %f]' % (epoch_idx, time.time() - v0, valid_score))
+                    self.logger.info('valid result: \n' + '    '.join('%s : %s' % kv for kv in valid_result.items()))
+                if update_flag:
+                    if saved:
+                        self._save_checkpoint(epoch_idx, verbose=verbose)
+                    self.best_valid_result = valid_result
+                if callback_fn:
+                    callback_fn(epoch_idx, valid_score)
+                if stop_flag:
+                    if verbose:
+                        self.logger.info('Finished training, best eval result in epoch %d' %
+                                         (epoch_idx - self.cur_step * self.eval_step))
+                    break
+        return self.best_valid_score, self.best_valid_result
+
+    # ------------------------------------------------------------------------------------------
+    def _full_sort_batch_eval(self, batched_data):
+        """trainer.py:926-945 with the API-compatible materialised scores (used when fused_topk is off)."""
+        interaction, history_index, positive_u, positive_i = batched_data
+        _, scores = self.model.full_sort_predict(interaction.to(self.device))
+        scores = scores.view(-1, self.tot_item_num)
+        scores[:, 0] = -np.inf
+        if history_index is not None:
+            scores[history_index] = -np.inf
+        return interaction, scores, positive_u, positive_i
+
+    def eval_batch(self, batched_data):
+        """-> rec_topk [B, kmax+1] int32 on the device (collector.py:145-153 'rec.topk')."""
+        interaction, history_index, positive_u, positive_i = batched_data
+        kmax = max(self.topk)
+        if self.fused_topk and history_index is None:
+            inter = interaction.to(self.device)
+            _, _, rec = self.model.full_sort_topk(inter, kmax, positive_i.to(self.device, non_blocking=True))
+            return rec
+        interaction, scores, positive_u, positive_i = self._full_sort_batch_eval(batched_data)
+        _, topk_idx = torch.topk(scores, kmax, dim=-1)
+        pos = positive_i.to(self.device)
+        flags = (topk_idx == pos.view(-1, 1)).to(torch.int32)
+        return torch.cat((flags, torch.ones_like(flags[:, :1])), dim=1)
+
+    @torch.no_grad()
+    def evaluate(self, eval_data, load_best_model=True, model_file=None, show_progress=False):
+        """trainer.py:964-1019."""
+        if not eval_data:
+            return
+        if load_best_model:
+            checkpoint_file = model_file or self.saved_model_file
+            checkpoint = torch.load(checkpoint_file, map_location='cpu', weights_only=False)
+            self._load_state(checkpoint['state_dict'])
+            self.model.load_other_parameter(checkpoint.get('other_parameter'))
+            self.logger.info('Loading model structure and parameters from {}'.format(checkpoint_file))
+        self.model.eval()
+        self.tot_item_num = eval_data.dataset.item_num
+        recs = [self.eval_batch(b) for b in eval_data]
+        rec = torch.cat(recs, dim=0).cpu().numpy()
+        return self.evaluator.evaluate(rec)

@@ -1,0 +1,181 @@
+/* acsr.h -- flat C ABI of the B200-native AC-SASRec hot path (libacsr.so).
+ *
+ * The reference (AIM-SE/AC-TSR, a RecBole 1.0.1 fork) has no native code and no FFI:
+ * every "kernel" is an ATen call made from Python.  Each entry point below therefore
+ * cites the reference *Python call site* it replaces (paths relative to
+ * /root/reference/recbole).  The reference-side binding is ctypes; INTEGRATION.md
+ * shows the stub a maintainer adds to recbole/model/sequential_recommender/acsasrec.py.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch tensors), contiguous
+ *    row-major; activations/parameters float32, ids int64 (RecBole's dtype).
+ *  - `stream` is a cudaStream_t passed as void*; calls only enqueue work, never
+ *    synchronise, never allocate.  Workspaces are passed in by the caller.
+ *  - return 0 on success, <0 on error (ACSR_ERR_*); acsr_last_error() returns the
+ *    message of the last failing call on this thread.  No exceptions cross the ABI.
+ *  - dropout: `p` keep-complement probability.  If `mask` != NULL it holds the
+ *    multiplicative mask (0 or 1/(1-p)) to apply (test / parity mode).  Otherwise, if
+ *    p > 0, the mask is generated in-kernel with Philox4x32-10 keyed by
+ *    (rng->seed, rng->step, rng_stream, element index); `rng` points to DEVICE memory
+ *    {uint64 seed; uint64 step} so CUDA-graph replays see a new step.  Backward
+ *    kernels regenerate the identical mask from the same triple.
+ */
+#ifndef ACSR_H_
+#define ACSR_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACSR_ABI_VERSION 1
+#define ACSR_OK 0
+#define ACSR_ERR_ARG (-1)
+#define ACSR_ERR_UNSUPPORTED (-2)
+#define ACSR_ERR_CUDA (-3)
+
+int acsr_version(void);
+const char* acsr_last_error(void);
+/* number of SMs the persistent kernels size their grids for (148 on B200) */
+int acsr_num_sms(void);
+
+/* rng state helper: rng->step += 1 (one tiny kernel; keeps graph replays distinct) */
+int acsr_rng_advance(void* rng, void* stream);
+
+/* ---- K1: item-embedding gather (+position add) + LayerNorm + dropout ------------------
+ * replaces model/sequential_recommender/acsasrec.py:87-95.
+ * item_seq [T] int64 (T = B*L tokens), table [V,d], pos_emb [L,d] or NULL, out [T,d],
+ * stats [T,2] (mean, rstd) saved for backward.  d in {32,64,128,256}. */
+int acsr_embed_ln_dropout_fwd(const int64_t* item_seq, const float* table, const float* pos_emb,
+                              const float* ln_w, const float* ln_b, float eps,
+                              int T, int L, int d, int64_t V,
+                              float p, const float* mask, const void* rng, uint32_t rng_stream,
+                              float* out, float* stats, void* stream);
+/* backward: d_table [V,d] += scatter (row 0 = padding_idx gets nothing, nn.Embedding(padding_idx=0)),
+ * d_pos [L,d] +=, d_ln_w [d] +=, d_ln_b [d] += (all accumulate with atomics). */
+int acsr_embed_ln_dropout_bwd(const float* d_out, const int64_t* item_seq, const float* table, const float* pos_emb,
+                              const float* ln_w, const float* stats,
+                              int T, int L, int d, int64_t V,
+                              float p, const float* mask, const void* rng, uint32_t rng_stream,
+                              float* d_table, float* d_pos, float* d_ln_w, float* d_ln_b, void* stream);
+
+/* ---- K4-K7 core, K11: fused calibrated causal attention -------------------------------
+ * replaces model/layers.py:657-674 (cal_attack_mask), 686-742 (cal_origin_qkv after the
+ * projections), 883-896 (combine_attention), 917-936 and the probs.V of 676-678; the
+ * additive mask of model/abstract_recommender.py:136-143 is derived from item_seq in-kernel.
+ * mq,mk,mv,aq,ak [B,L,d] projected tensors; gate_logit [B,L,L] (combine_option gate) or NULL.
+ * order_w [2*dh], order_b [1] or NULL (use_order False); dist_w, dist_b, scalar likewise.
+ * flags: see ACSR_ATTN_*.  comb_scalar: annealing rate (combine_option annealing).
+ * rich_ratio: device float* (rich_calibrated_combine trainable) or NULL (fixed -> 0.5).
+ * D1,D2,D3 explicit dropout masks [B,H,L,L] or NULL; noise [B,H,L,L] or NULL (Philox normal).
+ * ctx_att (may be NULL: attacked branch skipped), ctx_cal [B,L,d]; pen_sq [1] double,
+ * accumulated: sum over b,h,i,j of (1-M)^2 (acsasrec.py:135).  probs_out NULL or
+ * [6,B,H,L,L] = P0,P,M,A,C,R for introspection (layers.py:899-950).  L <= 64, dh <= 64. */
+#define ACSR_ATTN_TWO_LEVEL 1
+#define ACSR_ATTN_COMBINE_GATE 0
+#define ACSR_ATTN_COMBINE_FIXED 1
+#define ACSR_ATTN_COMBINE_ANNEAL 2
+#define ACSR_ATTN_RICH_NONE 0
+#define ACSR_ATTN_RICH_FIXED 1
+#define ACSR_ATTN_RICH_TRAINABLE 2
+int acsr_attn_calib_fwd(const float* mq, const float* mk, const float* mv, const float* aq, const float* ak,
+                        const float* gate_logit, const int64_t* item_seq,
+                        const float* order_w, const float* order_b,
+                        const float* dist_w, const float* dist_b, const float* scalar,
+                        int B, int L, int H, int dh,
+                        int two_level, int combine_option, float comb_scalar, int rich_mode, const float* rich_ratio,
+                        float p_attn, const float* D1, const float* D2, const float* D3, const float* noise,
+                        const void* rng, uint32_t rng_stream,
+                        float* ctx_att, float* ctx_cal, double* pen_sq, float* probs_out, void* stream);
+/* backward of the same block.  d_ctx_att / d_ctx_cal [B,L,d] (either may be NULL == zero),
+ * d_pen_sq device float[1] or NULL.  Outputs (written, not accumulated): d_mq,d_mk,d_mv,d_aq,d_ak [B,L,d].
+ * Accumulated with atomics (caller zeroes): d_gate_logit [B,L,L], d_order_w [2dh], d_order_b [1],
+ * d_dist_w [2dh], d_dist_b [1], d_scalar [1], d_rich_ratio [1] (NULL when the parameter is absent). */
+int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const float* d_pen_sq,
+                        const float* mq, const float* mk, const float* mv, const float* aq, const float* ak,
+                        const float* gate_logit, const int64_t* item_seq,
+                        const float* order_w, const float* order_b,
+                        const float* dist_w, const float* dist_b, const float* scalar,
+                        int B, int L, int H, int dh,
+                        int two_level, int combine_option, float comb_scalar, int rich_mode, const float* rich_ratio,
+                        float p_attn, const float* D1, const float* D2, const float* D3, const float* noise,
+                        const void* rng, uint32_t rng_stream,
+                        float* d_mq, float* d_mk, float* d_mv, float* d_aq, float* d_ak,
+                        float* d_gate_logit, float* d_order_w, float* d_order_b,
+                        float* d_dist_w, float* d_dist_b, float* d_scalar, float* d_rich_ratio, void* stream);
+
+/* ---- epilogue of the output projection and of the FFN: LN(dropout(h + bias) + res) ----
+ * replaces model/layers.py:681-683 and 794-796 (bias add of the preceding nn.Linear folded in).
+ * h,res,out [T,d]; bias [d] or NULL. */
+int acsr_bias_dropout_res_ln_fwd(const float* h, const float* bias, const float* res,
+                                 const float* ln_w, const float* ln_b, float eps, int T, int d,
+                                 float p, const float* mask, const void* rng, uint32_t rng_stream,
+                                 float* out, float* stats, void* stream);
+/* d_h [T,d] (= grad of the GEMM output), d_res [T,d] written; d_bias,d_ln_w,d_ln_b [d] accumulated. */
+int acsr_bias_dropout_res_ln_bwd(const float* d_out, const float* h, const float* bias, const float* res,
+                                 const float* ln_w, const float* stats, int T, int d,
+                                 float p, const float* mask, const void* rng, uint32_t rng_stream,
+                                 float* d_h, float* d_res, float* d_bias, float* d_ln_w, float* d_ln_b, void* stream);
+
+/* ---- FFN activation: out = act(h + bias)   (model/layers.py:776-792) -------------------
+ * act: 0 gelu(erf) 1 relu 2 swish 3 tanh 4 sigmoid.  h,out [T,n]. */
+int acsr_bias_act_fwd(const float* h, const float* bias, int T, int n, int act, float* out, void* stream);
+int acsr_bias_act_bwd(const float* d_out, const float* h, const float* bias, int T, int n, int act,
+                      float* d_h, float* d_bias, void* stream);
+
+/* ---- K9: gather the hidden state at position len-1 (abstract_recommender.py:130-134) ---
+ * x_att (may be NULL), x_cal [B,L,d]; out [2B,d] rows [0,B) attacked, [B,2B) calibrated
+ * (or [B,d] when x_att is NULL). */
+int acsr_gather_last_fwd(const float* x_att, const float* x_cal, const int64_t* item_len,
+                         int B, int L, int d, float* out, void* stream);
+/* d_x_att/d_x_cal [B,L,d] must be zero-filled by the caller; rows len-1 are written. */
+int acsr_gather_last_bwd(const float* d_out, const int64_t* item_len, int B, int L, int d,
+                         float* d_x_att, float* d_x_cal, void* stream);
+
+/* ---- K10/K12: full-catalogue logits out.E^T on tcgen05 tensor cores --------------------
+ * replaces acsasrec.py:118-120 (logits + CrossEntropyLoss), 162-163 (full-sort scores),
+ * trainer/trainer.py:941-942 + evaluator/collector.py:147-153 (scores[:,0]=-inf, topk, hit flags).
+ * out [M,64] float32 (d must be 64 in ABI v1), table [V,64].  passes: 1 = TF32, 3 = 3xTF32
+ * (hi/lo split, fp32-level accuracy).  All kernels are persistent over [m_tile(128), n_chunk];
+ * n_chunks = acsr_logits_num_chunks(M, V).
+ */
+int acsr_logits_num_chunks(int M, int64_t V);
+/* scores [M, ldc] = out.E^T  (full_sort_predict, predict-all) */
+int acsr_logits_store(const float* out, const float* table, int M, int64_t V, int d, int passes,
+                      float* scores, int64_t ldc, void* stream);
+/* CE forward: partial [M, n_chunks, 2] = (running max, sum exp) over this call's vocabulary
+ * range; combine with acsr_ce_finalize (after an all-gather when vocab-sharded). */
+int acsr_logits_ce_partial(const float* out, const float* table, int M, int64_t V, int d, int passes,
+                           float* partial, void* stream);
+/* combine partial (max, sumexp) pairs -> lse [M]; tgt_logit[m] = out[m].E[target[m]-idx_offset] as an
+ * fp32 dot when the target row lives in this table shard (else 0; sum across shards);
+ * row_loss[m] = lse - tgt_logit; loss[g] = mean of row_loss over each of n_groups groups of
+ * M/n_groups consecutive rows (attacked rows first, calibrated second).  Single-CTA kernel. */
+int acsr_ce_finalize(const float* partial, int n_parts, const float* out, const float* table,
+                     const int64_t* target, int M, int d, int64_t V, int64_t idx_offset, int n_groups,
+                     float* lse, float* tgt_logit, float* row_loss, float* loss, void* stream);
+/* CE backward part 1: G [M, ldg] = (exp(out.E^T - lse) - onehot(target)) * row_scale[m]
+ * (then d_out = G.E and d_E = G^T.out are plain GEMMs). */
+int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, const int64_t* target,
+                        const float* row_scale, int M, int64_t V, int d, int passes,
+                        float* G, int64_t ldg, void* stream);
+/* fused logits + streaming top-k: partial_val/partial_idx [M, n_chunks, k] (descending, padded with
+ * -inf/-1); column 0 is excluded (trainer.py:942); idx_offset is added to indices (vocab shards). */
+int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_t V, int d, int passes,
+                             int k, int64_t idx_offset, int skip_col0,
+                             float* partial_val, int64_t* partial_idx, void* stream);
+/* merge n_parts sorted partial lists per row -> topk_val [M,k], topk_idx [M,k] int64 and, when
+ * positive != NULL, rec_topk [M,k+1] int32 = hit flags + pos_len(=1) (collector.py:148-153). */
+int acsr_topk_merge(const float* partial_val, const int64_t* partial_idx, int M, int n_parts, int k,
+                    const int64_t* positive, float* topk_val, int64_t* topk_idx, int32_t* rec_topk, void* stream);
+
+/* ---- K13: fused Adam over one flat fp32 buffer (trainer/trainer.py:614-615,687) ---------
+ * torch.optim.Adam semantics (no amsgrad); step_count device int64[1], incremented by the call. */
+int acsr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                   int64_t* step_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACSR_H_ */

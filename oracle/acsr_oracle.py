@@ -125,7 +125,7 @@ def additive_mask(item_seq):
 
 
 def embed_ln_dropout(item_seq, E, ln_w, ln_b, eps, rnd, pos_emb=None):
-    x = E[item_seq]
+    x = torch.nn.functional.embedding(item_seq, E, padding_idx=0)   # acsasrec.py:37: no gradient to row 0 via the gather
     if pos_emb is not None:
         x = x + pos_emb[: item_seq.shape[1]].unsqueeze(0)
     x = layer_norm(x, ln_w, ln_b, eps)

@@ -1,0 +1,248 @@
+"""End-to-end parity of the CUDA ACSASRec (through the drop-in model / trainer API) against
+(a) the golden vectors produced by the real reference and (b) the oracle, plus size-independent
+properties at BASELINE.json's full sizes."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import acsr_oracle as O
+from golden_util import GOLDEN_DIR, load_case
+
+ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+TRAIN = [n for n in ALL if '_train' in n]
+EVAL = [n for n in ALL if '_eval' in n]
+
+
+@pytest.fixture(scope='module')
+def A():
+    import ac_tsr_b200 as pkg
+    pkg.LIB.load()
+    return pkg
+
+
+class DS:
+    def __init__(self, n):
+        self.n = n
+        self.item_num = n
+
+    def num(self, field):
+        return self.n
+
+
+def make_config(A, cfg, **extra):
+    d = dict(cfg)
+    d.update(USER_ID_FIELD='user_id', ITEM_ID_FIELD='item_id', LIST_SUFFIX='_list', ITEM_LIST_LENGTH_FIELD='item_length',
+             NEG_PREFIX='neg_', device=torch.device('cuda'), seed=42, learning_rate=1e-3, epochs=1, eval_batch_size=256,
+             train_batch_size=256, topk=[1, 5, 10, 50], metrics=['Hit', 'MRR', 'NDCG', 'Recall'], valid_metric='Hit@10',
+             checkpoint_dir='/tmp/acsr_ckpt', cuda_graph=False)
+    d.update(extra)
+    return A.Config(model='ACSASRec', config_dict=d)
+
+
+def build_model(A, c, **extra):
+    config = make_config(A, c['cfg'], **extra)
+    model = A.ACSASRec(config, DS(c['V'])).to('cuda')
+    sd = {k: v.cuda() for k, v in c['params'].items()}
+    missing, unexpected = model.load_state_dict(sd, strict=True), None     # reference state_dict loads unchanged
+    model._debug_rand = {k: v.cuda() for k, v in c['rand'].d.items()}
+    return config, model
+
+
+def inter_of(A, c):
+    b = c['batch']
+    return A.Interaction({'item_id_list': b['item_seq'].cuda(), 'item_length': b['item_len'].cuda(), 'item_id': b['pos'].cuda()})
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+@pytest.mark.parametrize('name', EVAL)
+def test_golden_eval(A, name):
+    c = load_case(name)
+    z = c['z']
+    config, model = build_model(A, c)
+    model.eval()
+    inter = inter_of(A, c)
+    with torch.no_grad():
+        att, cal, masks = model.forward(inter['item_id_list'], inter['item_length'])
+        assert rel(att, z['out_att']) < 1e-4 and rel(cal, z['out_cal']) < 1e-4
+        for l, m in enumerate(masks):
+            assert rel(m.pen_sq, z['pen_sq.%d' % l].reshape(1)) < 1e-5
+        if c['cfg']['hidden_size'] != 64:
+            # ABI v1: the tensor-core logits path is built for d=64 only and must say so, not fall back
+            with pytest.raises(A.AcsrError, match='unsupported'):
+                model.full_sort_predict(inter)
+            return
+        none, scores = model.full_sort_predict(inter)
+        assert none is None and scores.shape == (c['batch']['pos'].shape[0], c['V']) and scores.is_contiguous()
+        assert rel(scores, z['scores']) < 1e-4                      # north_star: logits within 1e-3 relative
+        val, idx, rec = model.full_sort_topk(inter, c['k'], inter['item_id'])
+        ok, nbad = O.topk_equal_modulo_ties(idx.cpu(), torch.from_numpy(z['topk_idx']), torch.from_numpy(z['scores']))
+        assert ok, nbad
+        assert np.array_equal(rec.cpu().numpy(), z['rec_topk']) or ok
+        pa, pc = model.predict(inter)
+        assert rel(pa, z['predict_att']) < 1e-4 and rel(pc, z['predict_cal']) < 1e-4
+        # the trainer's API-compatible path: scores[:,0] = -inf ; torch.topk
+        s2 = scores.view(-1, c['V']).clone()
+        s2[:, 0] = -np.inf
+        _, idx2 = torch.topk(s2, c['k'], dim=-1)
+        ok2, _ = O.topk_equal_modulo_ties(idx2.cpu(), torch.from_numpy(z['topk_idx']), torch.from_numpy(z['scores']))
+        assert ok2
+
+
+@pytest.mark.parametrize('name', TRAIN)
+def test_golden_train_losses_and_routed_grads(A, name):
+    """reference trainer semantics (trainer.py:672-686) through the drop-in API: .grad after the two backward passes."""
+    c = load_case(name)
+    z = c['z']
+    config, model = build_model(A, c)
+    model.train()
+    inter = inter_of(A, c)
+    l_att, l_cal = model.calculate_loss(inter)
+    assert abs(float(l_att) - float(z['loss_att'])) < 1e-4 * abs(float(z['loss_att']))      # north_star: 1e-3
+    assert abs(float(l_cal) - float(z['loss_cal'])) < 1e-4 * abs(float(z['loss_cal']))
+    for n, p in model.named_parameters():
+        p.requires_grad = not ('attack_key_transform' in n or 'attack_query_transform' in n)
+    l_cal.backward(retain_graph=True)
+    for n, p in model.named_parameters():
+        p.requires_grad = ('attack_key_transform' in n or 'attack_query_transform' in n)
+    l_att.backward()
+    names = [n for n, _ in model.named_parameters()]
+    assert set(names) == set(c['grads'])
+    for n, p in model.named_parameters():
+        ref = c['grads'][n]
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(ref)
+        scale = float(ref.abs().max())
+        err = float((got - ref).abs().max())
+        assert err <= 1e-3 * scale + 1e-8, (n, err, scale)
+
+
+@pytest.mark.parametrize('name', ['c1_train', 'beauty_train'])
+def test_trainer_step_matches_oracle_adam(A, name):
+    """one full optimisation step (both losses, routed grads, fused Adam) == oracle grads + oracle Adam."""
+    c = load_case(name)
+    config, model = build_model(A, c)
+    trainer = A.ACSASRecTrainer(config, model)
+    model.train()
+    la, lc = trainer.train_step(inter_of(A, c))
+    b = c['batch']
+    _, _, grads = O.train_grads(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['pos'], c['rand'])
+    sd = model.state_dict()
+    for n, p0 in c['params'].items():
+        want, _, _ = O.adam_step(p0, grads[n], torch.zeros_like(p0), torch.zeros_like(p0), 1, 1e-3)
+        got = sd[n].cpu()
+        # Adam's first step moves every weight by ~lr*sign(g): compare the update, not the weight
+        upd_w, upd_g = (want - p0), (got - p0)
+        big = grads[n].abs() > 1e-3 * grads[n].abs().max()
+        assert float((upd_w - upd_g)[big].abs().max()) < 2e-5, n
+    assert abs(float(lc) - float(c['z']['loss_cal'])) < 1e-4 * abs(float(c['z']['loss_cal']))
+
+
+def test_graphed_step_equals_eager_step(A):
+    """CUDA-graph replay of the step == eager launches (dropout off so both are deterministic)."""
+    cfg = O.default_cfg(hidden_dropout_prob=0.0, attn_dropout_prob=0.0)
+    V, B, L = 500, 64, 50
+    params = O.init_params(cfg, V, seed=1)
+    seq, ln, pos = O.synth_batch(B, L, V, seed=5)
+    results = []
+    for graph in (False, True):
+        config = make_config(A, cfg, cuda_graph=graph)
+        model = A.ACSASRec(config, DS(V)).to('cuda')
+        model.load_state_dict({k: v.cuda() for k, v in params.items()})
+        model._debug_rand = {(l, 'noise'): torch.zeros(B, cfg['n_heads'], L, L).cuda() for l in range(cfg['n_layers'])}
+        trainer = A.ACSASRecTrainer(config, model)
+        model.train()
+        inter = A.Interaction({'item_id_list': seq, 'item_length': ln, 'item_id': pos})
+        losses = []
+        for _ in range(3):
+            la, lc = trainer.graphed_step(inter) if graph else trainer.train_step(inter.to('cuda'))
+            losses.append((float(la), float(lc)))
+        results.append((losses, {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}))
+    (l0, s0), (l1, s1) = results
+    for a, b in zip(l0, l1):
+        assert abs(a[0] - b[0]) < 1e-4 * abs(a[0]) and abs(a[1] - b[1]) < 1e-4 * abs(a[1])
+    assert l0[2][1] < l0[0][1]                      # the calibrated loss goes down
+    for k in s0:
+        assert float((s0[k] - s1[k]).abs().max()) < 1e-5, k
+
+
+def test_full_size_properties_beauty_shape(A):
+    """BASELINE config #2 (V=12,102, L=50, d=64, N=2, B=256): properties that need no CPU reference."""
+    cfg = O.default_cfg()
+    V, B, L, k = 12102, 256, 50, 50
+    config = make_config(A, cfg)
+    torch.manual_seed(42)
+    model = A.ACSASRec(config, DS(V)).to('cuda')
+    seq, ln, pos = O.synth_batch(B, L, V, seed=42)
+    inter = A.Interaction({'item_id_list': seq.cuda(), 'item_length': ln.cuda(), 'item_id': pos.cuda()})
+    model.eval()
+    with torch.no_grad():
+        _, scores = model.full_sort_predict(inter)
+        val, idx, rec = model.full_sort_topk(inter, k, inter['item_id'])
+    s = scores.clone()
+    s[:, 0] = -np.inf
+    rv, ri = torch.topk(s, k, dim=-1)
+    assert (val[:, :-1] >= val[:, 1:]).all()                              # sortedness
+    ok, nbad = O.topk_equal_modulo_ties(idx.cpu(), ri.cpu(), scores.cpu())
+    assert ok, nbad                                                       # fused top-k == materialised top-k
+    assert torch.equal(rec[:, :-1].bool().cpu(), (idx == inter['item_id'].view(-1, 1)).cpu())
+    # CE identity: loss == logsumexp(scores) - scores[target], softmax-gradient rows sum to zero
+    out, _ = model._encode(inter['item_id_list'], inter['item_length'], need_attacked=False)
+    out = out.detach().requires_grad_(True)
+    E = model.item_embedding.weight
+    loss = A.ops.LogitsCEFn.apply(out, E, inter['item_id'], 1, 3)[0]
+    ref = (torch.logsumexp(scores.double(), 1) - scores.double()[torch.arange(B), inter['item_id']]).mean()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    lse = torch.logsumexp(scores.double(), 1).float()
+    G = A.ops.ce_grad_matrix(out.detach(), E.detach(), lse, inter['item_id'], torch.ones(B).cuda(), 3)
+    assert float(G.double().sum(1).abs().max()) < 1e-4
+    # a padded-key change must not leak: padding positions never influence the calibrated output
+    seq2 = seq.clone()
+    rows = torch.arange(B)
+    with torch.no_grad():
+        out_a, _ = model._encode(seq.cuda(), ln.cuda(), need_attacked=False)
+        short = ln < L
+        seq3 = seq.clone()
+        seq3[short, -1] = 0                                               # already 0: idempotent
+        out_b, _ = model._encode(seq3.cuda(), ln.cuda(), need_attacked=False)
+    assert torch.equal(out_a, out_b)
+
+
+def test_checkpoint_roundtrip_and_eval_loop(A, tmp_path):
+    cfg = O.default_cfg(n_layers=1)
+    V, L = 400, 50
+    config = make_config(A, cfg, checkpoint_dir=str(tmp_path), epochs=1, train_batch_size=64, eval_batch_size=64,
+                         cuda_graph=True)
+    torch.manual_seed(0)
+    train_ds = A.data.SyntheticSequentialDataset(config, 64 * 3 + 10, V, seed=1)
+    valid_ds = A.data.SyntheticSequentialDataset(config, 100, V, seed=2)
+    model = A.ACSASRec(config, train_ds).to('cuda')
+    trainer = A.ACSASRecTrainer(config, model)
+    trainer.epochs = 1
+    train_loader = A.data.TrainDataLoader(config, train_ds, shuffle=True)
+    valid_loader = A.data.FullSortEvalDataLoader(config, valid_ds)
+    # fit() runs range(0, 2*epochs) epochs (trainer.py:835); the last batch (10 rows) takes the eager path
+    score, result = trainer.fit(train_loader, valid_loader, verbose=False, saved=True)
+    assert set(result) == {'%s@%d' % (m, k) for m in ('hit', 'mrr', 'ndcg', 'recall') for k in (1, 5, 10, 50)}
+    assert os.path.exists(trainer.saved_model_file)
+    ck = torch.load(trainer.saved_model_file, map_location='cpu', weights_only=False)
+    assert set(ck) == {'config', 'epoch', 'cur_step', 'best_valid_score', 'state_dict', 'other_parameter', 'optimizer'}
+    res2 = trainer.evaluate(valid_loader, load_best_model=True)
+    trainer.fused_topk = False                     # API-compatible path: full_sort_predict + scores[:,0]=-inf + topk
+    res3 = trainer.evaluate(valid_loader, load_best_model=False)
+    for k in res2:
+        assert abs(res2[k] - res3[k]) <= 1e-4      # north_star: Recall@10 / NDCG@10 within 1e-4
+    # metrics equal the oracle's restatement of metrics.py
+    trainer.fused_topk = True
+    model.eval()
+    recs = torch.cat([trainer.eval_batch(b) for b in valid_loader]).cpu().numpy()
+    want = O.topk_metrics(recs[:, :-1], recs[:, -1], topk=(1, 5, 10, 50))
+    for k, v in res2.items():
+        assert abs(want[k] - v) < 1e-9

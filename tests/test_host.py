@@ -1,0 +1,168 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/acsr.h declares, the
+host mirror keeps the reference's names / shapes / error behaviour, and nothing silently falls
+back to the CPU."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import acsr_oracle as O
+from golden_util import GOLDEN_DIR, load_case
+
+import ac_tsr_b200 as A
+
+
+class DS:
+    def __init__(self, n):
+        self.n = self.item_num = n
+
+    def num(self, field):
+        return self.n
+
+
+def cfg_for(**kw):
+    d = O.default_cfg(**kw)
+    d.update(device=torch.device('cpu'), seed=42, learning_rate=1e-3, epochs=1, eval_batch_size=8, train_batch_size=8,
+             topk=[1, 5, 10], metrics=['Hit', 'MRR', 'NDCG', 'Recall'], valid_metric='Hit@10', checkpoint_dir='/tmp/acsr_ckpt')
+    return A.Config(model='ACSASRec', config_dict=d)
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    protos = A._lib.parse_header()
+    assert len(protos) >= 22
+    dll = ctypes.CDLL(A._lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(dll, name), name
+    A.LIB.load()
+    assert A.LIB.query('acsr_version') == 1
+    assert A.LIB.query('acsr_num_sms') == 148
+    # grid planning is host-side: persistent grid never exceeds the SM count for the benchmark shapes
+    for M, V in ((256, 12102), (512, 12102), (512, 1000001), (256, 1683)):
+        nc = A.LIB.query('acsr_logits_num_chunks', M, V)
+        assert 1 <= nc and ((M + 127) // 128) * nc <= 148
+
+
+def test_abi_rejects_bad_arguments_without_a_gpu():
+    A.LIB.load()
+    with pytest.raises(A.AcsrError, match='NULL'):
+        A.LIB.call('acsr_rng_advance', None, None)
+    with pytest.raises(A.AcsrError):
+        A.LIB.call('acsr_topk_merge', None, None, 1, 1, 1, None, None, None, None, None)
+
+
+def test_state_dict_names_match_reference_checkpoints():
+    for name in ('c1_train', 'beauty_train', 'pos_tw_train', 'noorder_train', 'nodist_train', 'fixed_onelevel_train', 'relu_h8_eval'):
+        c = load_case(name)
+        cfg = cfg_for(**{k: c['cfg'][k] for k in c['cfg']})
+        model = A.ACSASRec(cfg, DS(c['V']))
+        own = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        ref = {k: tuple(v.shape) for k, v in c['params'].items()}
+        assert own == ref, name
+        model.load_state_dict(c['params'], strict=True)
+    assert model.type == A.ModelType.SEQUENTIAL and 'Trainable parameters' in str(model)
+
+
+def test_init_follows_reference_rules():
+    torch.manual_seed(0)
+    m = A.ACSASRec(cfg_for(n_layers=3), DS(1000))
+    sd = m.state_dict()
+    assert abs(float(sd['item_embedding.weight'].std()) - 0.02) < 2e-3
+    assert float(sd['item_embedding.weight'][0].abs().sum()) > 0          # pad row is re-initialised (acsasrec.py:76-79)
+    assert float(sd['trm_encoder.layer.0.attack_attention.query.bias'].abs().sum()) == 0
+    assert float((sd['LayerNorm.weight'] - 1).abs().sum()) == 0
+    # `scalar` is drawn once and deep-copied into every layer, never re-initialised (layers.py:640,1095)
+    s = [float(sd['trm_encoder.layer.%d.attack_attention.scalar' % l]) for l in range(3)]
+    assert s[0] == s[1] == s[2]
+    assert not torch.equal(sd['trm_encoder.layer.0.attack_attention.query.weight'], sd['trm_encoder.layer.1.attack_attention.query.weight'])
+    assert sd['trm_encoder.layer.0.gate.weight'].shape == (50, 64)
+
+
+def test_constructor_errors_match_reference():
+    with pytest.raises(ValueError, match='not a multiple'):
+        A.ACSASRec(cfg_for(n_heads=3), DS(10))
+    with pytest.raises(NotImplementedError):
+        A.ACSASRec(cfg_for(loss_type='XX'), DS(10))
+    with pytest.raises(KeyError):
+        A.layers.FeedForward(64, 64, 0.5, 'nope', 1e-12)
+
+
+def test_no_cpu_fallback():
+    m = A.ACSASRec(cfg_for(), DS(100))
+    seq, ln, pos = O.synth_batch(4, 50, 100)
+    inter = A.Interaction({'item_id_list': seq, 'item_length': ln, 'item_id': pos})
+    for fn in (m.calculate_loss, m.predict, m.full_sort_predict):
+        with pytest.raises(A.AcsrError, match='CUDA'):
+            fn(inter)
+
+
+def test_config_priority_and_yaml_floats(tmp_path):
+    f = tmp_path / 'a.yaml'
+    f.write_text('layer_norm_eps: 1e-12\nn_layers: 3\ntopk: [1,3]\nlearning_rate: 0.0001\nmask_loss_weight: 0.03\n')
+    c = A.Config(model='ACSASRec', dataset='x', config_file_list=[str(f)], config_dict={'n_layers': 4},
+                 cmd_args=['--learning_rate=0.01'])
+    assert c['layer_norm_eps'] == 1e-12 and isinstance(c['layer_norm_eps'], float)
+    assert c['n_layers'] == 4 and c['learning_rate'] == 0.01 and c['topk'] == [1, 3]
+    assert c['nonexistent'] is None and 'n_layers' in c and c['model'] == 'ACSASRec'
+    ref_yaml = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'config', 'amazon-beauty.yaml')
+    if os.path.exists(ref_yaml):
+        c2 = A.Config(model='ACSASRec', config_file_list=[ref_yaml])
+        assert c2['n_heads'] == 4 and c2['combine_option'] == 'gate' and c2['layer_norm_eps'] == 1e-12
+
+
+def test_interaction_semantics():
+    it = A.Interaction({'a': torch.arange(10), 'b': np.arange(20).reshape(10, 2)})
+    assert len(it) == 10 and it['a'][3] == 3 and it.b.shape == (10, 2)
+    sub = it[2:5]
+    assert len(sub) == 3 and sub['b'][0, 0] == 4
+    with pytest.raises(ValueError):
+        A.Interaction({'a': 'x'})
+    assert set(it.to('cpu').columns) == {'a', 'b'}
+
+
+def test_evaluator_matches_oracle_metrics():
+    rng = np.random.RandomState(1)
+    k = 50
+    pos = np.zeros((200, k), dtype=np.int32)
+    for r in range(200):
+        if rng.rand() < 0.6:
+            pos[r, rng.randint(k)] = 1
+    rec = np.concatenate([pos, np.ones((200, 1), dtype=np.int32)], 1)
+    cfg = cfg_for()
+    cfg['topk'] = [1, 3, 5, 10, 20, 50]
+    cfg['metrics'] = ['Hit', 'MRR', 'NDCG', 'Recall']
+    got = A.evaluator.Evaluator(cfg).evaluate(rec)
+    want = O.topk_metrics(pos, np.ones(200, dtype=np.int64))
+    assert got == want
+    cfg['metrics'] = ['AUC']
+    with pytest.raises(NotImplementedError):
+        A.evaluator.Evaluator(cfg)
+
+
+def test_loaders_shapes_and_eval_tuple():
+    cfg = cfg_for()
+    ds = A.data.SyntheticSequentialDataset(cfg, 21, 300, seed=3, pin=False)
+    assert ds.num('item_id') == 300 and len(ds) == 21
+    tl = A.data.TrainDataLoader(cfg, ds, shuffle=True)
+    sizes = [len(b) for b in tl]
+    assert sizes == [8, 8, 5] and len(tl) == 3
+    b = next(iter(tl))
+    assert b['item_id_list'].shape == (8, 50) and b['item_id_list'].dtype == torch.int64
+    ln = b['item_length']
+    assert ((b['item_id_list'] != 0).sum(1) == ln).all()                 # right-padded with 0
+    el = A.data.FullSortEvalDataLoader(cfg, ds)
+    inter, hist, pu, pi = next(iter(el))
+    assert hist is None and torch.equal(pu, torch.arange(8)) and torch.equal(pi, inter['item_id'])
+
+
+def test_early_stopping_rule():
+    es = A.trainer.early_stopping
+    assert es(0.5, 0.4, 3, 10) == (0.5, 0, False, True)
+    assert es(0.3, 0.4, 10, 10) == (0.4, 11, True, False)
+    assert es(0.3, 0.4, 0, 10, bigger=False) == (0.3, 0, False, True)
+    assert A.trainer.is_attack_param('trm_encoder.layer.0.attack_attention.attack_key_transform.weight')
+    assert not A.trainer.is_attack_param('trm_encoder.layer.0.attack_attention.key.weight')
