@@ -48,6 +48,7 @@ class _Lib:
     def __init__(self):
         self._dll = None
         self.protos = parse_header()
+        self.timer = None            # KernelTimer while bench.py measures per-kernel device time
 
     def load(self):
         if self._dll is not None:
@@ -68,6 +69,8 @@ class _Lib:
 
     def call(self, name, *args):
         dll = self.load()
+        if self.timer is not None:
+            return self.timer.timed_call(self, dll, name, args)
         rc = getattr(dll, name)(*args)
         if rc != 0:
             msg = dll.acsr_last_error()
@@ -75,6 +78,37 @@ class _Lib:
 
     def query(self, name, *args):
         return getattr(self.load(), name)(*args)
+
+
+class KernelTimer:
+    """Brackets every C-ABI launch with CUDA events on the launching (current torch) stream.
+    Used by bench.py for the per-kernel share / roofline numbers; never active in the timed step."""
+
+    def __init__(self):
+        self.events = []             # (name, start, stop)
+        self.launches = 0
+
+    def timed_call(self, lib, dll, name, args):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(dll, name)(*args)
+        e1.record()
+        if rc != 0:
+            msg = dll.acsr_last_error()
+            raise AcsrError('%s failed (%d): %s' % (name, rc, msg.decode() if msg else ''))
+        self.events.append((name, e0, e1))
+        self.launches += 1
+
+    def summary(self):
+        """-> {name: (n_calls, total_ms)} after a device synchronize."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.events:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + e0.elapsed_time(e1))
+        return out
 
 
 LIB = _Lib()

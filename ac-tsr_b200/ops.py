@@ -292,7 +292,7 @@ class LogitsCEFn(torch.autograd.Function):
         n_groups, passes = ctx.meta
         M = out.shape[0]
         per = M // n_groups
-        row_scale = (d_loss.to(torch.float32) / per).view(n_groups, 1).expand(n_groups, per).reshape(-1)
+        row_scale = (d_loss.to(torch.float32) / per).view(n_groups, 1).expand(n_groups, per).reshape(-1).contiguous()
         G = ce_grad_matrix(out, table, lse, target, row_scale, passes)
         d_out = G @ table if ctx.needs_input_grad[0] else None
         d_table = G.t() @ out if ctx.needs_input_grad[1] else None

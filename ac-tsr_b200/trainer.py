@@ -46,8 +46,9 @@ class FlatAdam(object):
     def __init__(self, model, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
         params = [p for p in model.parameters()]
         dev = params[0].device
-        n = sum(p.numel() for p in params)
-        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        align = 64                      # floats: every parameter starts on a 256-byte boundary (float4 / bulk-copy loads)
+        n = sum((p.numel() + align - 1) // align * align for p in params)
+        self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -59,7 +60,7 @@ class FlatAdam(object):
                 self.flat_param[off:off + k].copy_(p.data.reshape(-1))
                 p.data = self.flat_param[off:off + k].view(p.shape)
                 p.grad = self.flat_grad[off:off + k].view(p.shape)
-                off += k
+                off += (k + align - 1) // align * align
         self.lr, self.weight_decay, self.betas, self.eps = float(lr), float(weight_decay or 0.0), betas, eps
         self.params = params
 
@@ -112,6 +113,7 @@ class ACSASRecTrainer(object):
         self.use_graph = bool(cfg_get(config, 'cuda_graph', True))
         self.fused_topk = bool(cfg_get(config, 'fused_topk', True))
         self._graph = None
+        self.dp_world = 1
         self.nan_check_interval = int(cfg_get(config, 'nan_check_interval', 50))
         self.logger.info('use attack trainer!!!')
 
@@ -148,10 +150,22 @@ class ACSASRecTrainer(object):
             attacked_loss.backward()
         for p in self.model.parameters():
             p.requires_grad = True
+        if self.dp_world > 1:               # batch data-parallel: average the flat gradient over ranks (NCCL / NVLink)
+            import torch.distributed as dist
+            dist.all_reduce(self.optimizer.flat_grad)
+            self.optimizer.flat_grad.mul_(1.0 / self.dp_world)
         if self.clip_grad_norm:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
         self.optimizer.step()
         return attacked_loss.detach(), calibrated_loss.detach()
+
+    def enable_data_parallel(self):
+        """One process per GPU, replicated parameters: broadcast rank 0's weights, then all-reduce gradients every step."""
+        import torch.distributed as dist
+        if not isinstance(self.optimizer, FlatAdam):
+            raise ValueError('data-parallel training needs the flat Adam optimizer')
+        self.dp_world = dist.get_world_size()
+        dist.broadcast(self.optimizer.flat_param, src=0)
 
     def train_step(self, interaction):
         """One optimisation step on a device-resident Interaction (eager launch path)."""

@@ -1,0 +1,416 @@
+"""bench.py -- AC-SASRec training seq/s (+ full-sort eval users/s) on B200, BASELINE.json config #2:
+synthetic Amazon-Beauty shape (22,363 users, 12,101 items + pad -> V=12,102, L=50, d=64, 2 layers,
+2 heads, inner 256, B=256, top-k 50).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (oracle port of the reference)
+
+A "step" is one pass of the training hot path over one batch of 256 sequences: both losses, both
+routed backward passes, Adam (trainer.py:660-687).  `value` times it with the batch already resident
+in HBM; `e2e` times the trainer's public step with the batch in pinned host memory (H2D inside the
+timed region) and the two losses read back every step.  Each timed step is bracketed by CUDA events
+on the launching stream; L2 is flushed (256 MiB write) between timed steps, outside the brackets.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+WORKLOAD = dict(name='C2 synthetic Amazon-Beauty shape', users=22363, V=12102, L=50, d=64, n_layers=2, n_heads=2,
+                inner=256, B=256, topk=50)
+
+
+def model_cfg():
+    return dict(n_layers=WORKLOAD['n_layers'], n_heads=WORKLOAD['n_heads'], hidden_size=WORKLOAD['d'],
+                inner_size=WORKLOAD['inner'], hidden_dropout_prob=0.5, attn_dropout_prob=0.5, hidden_act='gelu',
+                layer_norm_eps=1e-12, initializer_range=0.02, loss_type='CE', combine_option='gate',
+                rich_calibrated_combine='none', two_level=True, use_position_embedding=False, use_order=True,
+                use_distance=True, trainable_mask_loss_weight=False, mask_loss_weight=0.03, MAX_ITEM_LIST_LENGTH=WORKLOAD['L'])
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """polls SM clock + throttle reasons of one GPU while the timed regions run (NVML)."""
+    REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown', 0x2: 'applications_clocks_setting'}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {'sm_mhz': (s[len(s) // 2] if s else None), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+def timed_steps(fn, n, flush):
+    """run fn() n times, each bracketed by CUDA events on the current stream; flush L2 in between.  -> total ms"""
+    evs = []
+    for _ in range(n):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs)
+
+
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(name, per_step_calls, cfg, B, V):
+    """ALGORITHMIC HBM bytes of all launches of one kernel in one training step."""
+    L, d, N, I = cfg['MAX_ITEM_LIST_LENGTH'], cfg['hidden_size'], cfg['n_layers'], cfg['inner_size']
+    T = B * L
+    if name == 'acsr_attn_calib_fwd':       # 5 inputs + gate logits + ids, n_out contexts; attacked only on the last layer
+        return sum(B * ((5 + (2 if l == N - 1 else 1)) * L * d * 4 + L * L * 4 + 8 * L) for l in range(N))
+    if name == 'acsr_attn_calib_bwd':       # 2 passes x N layers: 5 inputs + gate + ids + n_cot cotangents in, 5 grads + dgate out
+        tot = 0
+        for l in range(N):
+            for n_cot in ((1, 1) if l < N - 1 else (1, 1)):
+                tot += B * ((5 + n_cot + 5) * L * d * 4 + 2 * L * L * 4 + 8 * L)
+        return tot
+    if name == 'acsr_bias_dropout_res_ln_fwd':
+        return per_step_calls * T * d * 4 * 3
+    if name == 'acsr_bias_dropout_res_ln_bwd':
+        return per_step_calls * T * d * 4 * 5
+    if name == 'acsr_bias_act_fwd':
+        return per_step_calls * T * I * 4 * 2
+    if name == 'acsr_bias_act_bwd':
+        return per_step_calls * T * I * 4 * 3
+    if name == 'acsr_embed_ln_dropout_fwd':
+        return T * (8 + 4 * d + 4 * d)
+    if name == 'acsr_embed_ln_dropout_bwd':
+        return per_step_calls * T * (8 + 4 * d + 4 * d + 8 * d)
+    if name == 'acsr_logits_ce_partial':
+        return V * d * 4 + 2 * B * d * 4
+    if name == 'acsr_logits_ce_grad':
+        return per_step_calls * (V * d * 4 + 2 * B * d * 4 + 2 * B * V * 4)
+    if name == 'acsr_adam_step':
+        return None                                # filled by caller (28 B / parameter)
+    return None
+
+
+def build(dev, rank, world, cuda_graph=True):
+    import ac_tsr_b200 as A
+    cfg = model_cfg()
+    d = dict(cfg)
+    d.update(USER_ID_FIELD='user_id', ITEM_ID_FIELD='item_id', LIST_SUFFIX='_list', ITEM_LIST_LENGTH_FIELD='item_length',
+             NEG_PREFIX='neg_', device=dev, seed=42, learning_rate=1e-4, epochs=1, train_batch_size=WORKLOAD['B'],
+             eval_batch_size=WORKLOAD['B'], topk=[1, 3, 5, 10, 20, 50], metrics=['Hit', 'MRR', 'NDCG'], valid_metric='Hit@10',
+             checkpoint_dir='/tmp/acsr_bench_ckpt', cuda_graph=cuda_graph, logits_passes=3)
+    config = A.Config(model='ACSASRec', config_dict=d)
+
+    class DS:
+        item_num = WORKLOAD['V']
+
+        def num(self, f):
+            return WORKLOAD['V']
+    torch.manual_seed(42)
+    model = A.ACSASRec(config, DS()).to(dev)
+    trainer = A.ACSASRecTrainer(config, model)
+    return A, cfg, config, model, trainer
+
+
+def run_ours(args):
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    A, cfg, config, model, trainer = build(dev, rank, world, cuda_graph=(world == 1))
+    if world > 1:
+        trainer.enable_data_parallel()
+    B, L, V, K, W = WORKLOAD['B'], WORKLOAD['L'], WORKLOAD['V'], args.steps, args.warmup
+    nb = 8                                                             # distinct synthetic batches cycled through
+    seq, ln, tgt = A.data.synth_sequences(nb * B, L, V, seed=42 + rank)
+    host = [A.Interaction({'item_id_list': seq[i * B:(i + 1) * B].pin_memory(), 'item_length': ln[i * B:(i + 1) * B].pin_memory(),
+                           'item_id': tgt[i * B:(i + 1) * B].pin_memory()}) for i in range(nb)]
+    devb = [h.to(dev) for h in host]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    model.train()
+    step = trainer.graphed_step if world == 1 else trainer.train_step
+    it = [0]
+
+    def dev_step():
+        step(devb[it[0] % nb])
+        it[0] += 1
+    loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        b = host[it[0] % nb]
+        la, lc = step(b if world == 1 else b.to(dev))
+        loss_pin[0:1].copy_(la.reshape(1), non_blocking=True)
+        loss_pin[1:2].copy_(lc.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()                      # the loss is read on the host every step
+        it[0] += 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(W, 3)):
+        dev_step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ms_dev = timed_steps(dev_step, K, flush)
+    barrier()
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    ms_e2e = timed_steps(e2e_step, K, flush)
+    barrier()
+    # ---- full-sort eval (fused logits + top-k), same batch size ----
+    model.eval()
+    kmax = WORKLOAD['topk']
+    rec_pin = torch.empty((B, kmax + 1), dtype=torch.int32).pin_memory()
+
+    def eval_dev():
+        b = devb[it[0] % nb]
+        with torch.no_grad():
+            model.full_sort_topk(b, kmax, b['item_id'])
+        it[0] += 1
+
+    def eval_e2e():
+        b = host[it[0] % nb]
+        with torch.no_grad():
+            rec = trainer.eval_batch((b, None, None, b['item_id']))
+        rec_pin.copy_(rec, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        it[0] += 1
+    for _ in range(3):
+        eval_dev()
+    barrier()
+    ms_eval = timed_steps(eval_dev, K, flush)
+    for _ in range(3):
+        eval_e2e()
+    barrier()
+    ms_eval_e2e = timed_steps(eval_e2e, K, flush)
+    barrier()
+    clocks = sampler.stop()
+
+    # ---- per-kernel device time: eager (non-graph) steps with every C-ABI launch bracketed by events ----
+    model.train()
+    kt_steps = min(K, 20)
+    timer = A._lib.KernelTimer()
+    A.LIB.timer = timer
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(kt_steps):
+        trainer.train_step(devb[i % nb])
+    t1.record()
+    ksum = timer.summary()
+    A.LIB.timer = None
+    eager_ms = t0.elapsed_time(t1) / kt_steps
+    launches_per_step = timer.launches / kt_steps + 1                   # adam_step enqueues two kernels
+    n_param = trainer.optimizer.flat_param.numel()
+    kernels = {}
+    total_k = sum(t for _, t in ksum.values())
+    for name, (n, t) in sorted(ksum.items(), key=lambda x: -x[1][1]):
+        per_step_calls = n / kt_steps
+        ab = algorithmic_bytes(name, per_step_calls, cfg, B, V)
+        if name == 'acsr_adam_step':
+            ab = 28 * n_param
+        ms = t / kt_steps
+        kernels[name] = {'calls_per_step': per_step_calls, 'ms_per_step': round(ms, 5), 'share': round(t / total_k, 4),
+                         'algo_bytes_per_step': ab, 'gbs': (round(ab / ms / 1e6, 1) if ab else None)}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak, peak_src = (peaks.get('hbm_gbs'), 'measured (MEASURED_PEAKS.json hbm_gbs)') if peaks.get('hbm_gbs') else (6650.0, 'fallback 6.65 TB/s')
+    top = next(iter(kernels))
+    topk_ = kernels[top]
+    calls = max(1.0, topk_['calls_per_step'])
+    roof = {'kernel': top, 'bound': 'hbm', 'achieved': topk_['gbs'], 'peak': peak, 'unit': 'GB/s',
+            'frac': (round(topk_['gbs'] / peak, 4) if topk_['gbs'] else None), 'traffic': None, 'peak_source': peak_src,
+            'avg_launch_us': round(topk_['ms_per_step'] / calls * 1e3, 2),
+            'algo_bytes_per_launch': (int(topk_['algo_bytes_per_step'] / calls) if topk_['algo_bytes_per_step'] else None),
+            'share_of_kernel_time': topk_['share']}
+
+    # max over ranks
+    t = torch.tensor([ms_dev, ms_e2e, ms_eval, ms_eval_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e, ms_eval, ms_eval_e2e = [float(x) for x in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(cfg, B, L, V, budget_s=20.0)
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in host[0].columns)
+    line = {
+        'metric': 'AC-SASRec train seq/s', 'value': round(world * B * K / (ms_dev / 1e3), 1), 'unit': 'seq/s',
+        'n_gpus': world, 'steps': K, 'warmup': max(W, 3), 'ms_per_step': round(ms_dev / K, 4), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': '%s: V=%d, users=%d, L=%d, d=%d, layers=%d, heads=%d, inner=%d, train/eval batch %d per GPU, top-%d; '
+                               'lengths LogNormal(ln7,0.8), items Zipf(1); L2 flushed (256 MiB write) between timed steps'
+                               % (WORKLOAD['name'], V, WORKLOAD['users'], L, WORKLOAD['d'], WORKLOAD['n_layers'], WORKLOAD['n_heads'],
+                                  WORKLOAD['inner'], B, kmax),
+                   'parallelism': 'dp%d (batch-parallel, replicated item table, NCCL all-reduce of the flat gradient)' % world if world > 1 else 'single GPU',
+                   'launch': 'CUDA graph replay of the whole step' if world == 1 else 'eager launches + NCCL',
+                   'logits': '3xTF32 tcgen05 (fp32-level accuracy)'},
+        'e2e': {'value': round(world * B * K / (ms_e2e / 1e3), 1), 'unit': 'seq/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8},
+        'gpu_launches': int(round(launches_per_step * K)),
+        'clocks': clocks,
+        'eval': {'metric': 'AC-SASRec full-sort eval users/s', 'value': round(world * B * K / (ms_eval / 1e3), 1), 'unit': 'users/s',
+                 'ms_per_batch': round(ms_eval / K, 4),
+                 'e2e': {'value': round(world * B * K / (ms_eval_e2e / 1e3), 1), 'unit': 'users/s', 'h2d_bytes_per_step': h2d,
+                         'd2h_bytes_per_step': B * (kmax + 1) * 4}},
+        'roofline': roof,
+        'kernels': kernels,
+        'eager_ms_per_step': round(eager_ms, 4),
+    }
+    if cpu is not None:
+        line['cpu_baseline'] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_step_fn(cfg, B, L, V, seed=42):
+    """one reference-semantics training step on the CPU (oracle port): losses, two routed backward passes, Adam."""
+    from oracle import acsr_oracle as O
+    params = O.init_params(cfg, V, seed=seed)
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in params.items()}
+    seq, ln, pos = O.synth_batch(B, L, V, seed=seed)
+    cnt = [0]
+
+    def step():
+        cnt[0] += 1
+        rnd = O.draw_rand(cfg, B, L, seed=cnt[0], train=True)
+        la, lc, grads = O.train_grads(params, cfg, seq, ln, pos, rnd)
+        for k in params:
+            params[k], m, v = O.adam_step(params[k], grads[k], state[k][0], state[k][1], cnt[0], 1e-4)
+            state[k] = (m, v)
+        return float(la), float(lc)
+    return step
+
+
+def cpu_baseline(cfg, B, L, V, budget_s=20.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = oracle_step_fn(cfg, B, L, V)
+    step()                                       # warm-up
+    t0 = time.time()
+    n = 0
+    while True:
+        step()
+        n += 1
+        if time.time() - t0 > budget_s or n >= 10:
+            break
+    dt = time.time() - t0
+    return {'value': round(B * n / dt, 2), 'unit': 'seq/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d training steps of B=%d (oracle/acsr_oracle.py: CPU restatement of the reference step, all host threads)' % (n, B)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    cfg = model_cfg()
+    B, L, V, K, W = WORKLOAD['B'], WORKLOAD['L'], WORKLOAD['V'], args.steps, args.warmup
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = oracle_step_fn(cfg, B, L, V)
+    t0 = time.time()
+    step()
+    t1 = time.time() - t0
+    Bs = B
+    budget = 150.0
+    if (K + W) * t1 > budget:                    # bounded sample: shrink the per-step batch so the run ends in minutes
+        Bs = max(8, int(B * budget / ((K + W) * t1)))
+        step = oracle_step_fn(cfg, Bs, L, V)
+    for _ in range(W):
+        step()
+    t0 = time.time()
+    for _ in range(K):
+        step()
+    dt = time.time() - t0
+    val = round(Bs * K / dt, 2)
+    cb = {'value': val, 'unit': 'seq/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+          'sample': '%d steps of B=%d of the C2 workload (oracle port of the reference CPU path; /root/reference is Python and '
+                    'cannot travel to the GPU box)' % (K, Bs)}
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'AC-SASRec train seq/s', 'value': val, 'unit': 'seq/s', 'n_gpus': int(args.gpus), 'steps': K,
+        'warmup': W, 'ms_per_step': round(dt / K * 1e3, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': '%s: V=%d, L=%d, d=%d, layers=%d, heads=%d, inner=%d, batch %d (CPU sample batch %d)'
+                               % (WORKLOAD['name'], V, L, WORKLOAD['d'], WORKLOAD['n_layers'], WORKLOAD['n_heads'], WORKLOAD['inner'], B, Bs)},
+        'cpu_baseline': cb, 'e2e': {'value': val, 'unit': 'seq/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()
