@@ -2,16 +2,19 @@
 //
 // One CTA owns one (sequence b, head h): the five projected [L,dh] tiles are staged in shared
 // memory once, each warp then owns query rows i = warp, warp+8, ... and its lanes own key
-// columns j = lane, lane+32, so the four chained softmaxes (spatially-calibrated P, attack mask
-// M, attacked A, calibrated C / combined R) are warp-shuffle reductions and none of the
-// [B,H,L,L] intermediates of the reference (layers.py:686-742, 657-674, 917-925) ever reaches
-// HBM.  The additive mask (abstract_recommender.py:136-143) is derived from item_seq, the
-// spatial-calibrator affine over cat(q_i,k_j) is evaluated in its rank-1 form, dropout masks and
-// the attack noise come from Philox (or from explicit tensors in parity mode), and the penalty
-// sum (1-M)^2 (acsasrec.py:135) is reduced in the same pass.
+// columns j = lane, lane+32, so the chained softmaxes (spatially-calibrated P, attack mask M,
+// attacked A, calibrated C, combined R) are warp-shuffle reductions and none of the [B,H,L,L]
+// intermediates of the reference (layers.py:686-742, 657-674, 917-925) ever reaches HBM.
+// The additive mask (abstract_recommender.py:136-143) is derived from item_seq, the spatial-
+// calibrator affine over cat(q_i,k_j) is evaluated in its rank-1 form, dropout masks and the attack
+// noise come from Philox (or from explicit tensors in parity mode), and the penalty sum (1-M)^2
+// (acsasrec.py:135) is reduced in the same pass.
+// Causal structure is exploited exactly: a 32-column group that lies entirely above the diagonal
+// is skipped (its probabilities are exactly 0 in the reference as well: exp(-10000-max) underflows),
+// and all probs.V / gradient contractions run over j <= i only.
 // The backward recomputes the row's probabilities from the same tiles (and the same Philox
-// counters), keeps dS, dS', R, A as [L,L] shared-memory matrices and finishes the column-side
-// gradients (dK, dK', dV) in a second, column-parallel phase.
+// counters), keeps dS, dS', R, A as lower-triangular shared-memory matrices and finishes the
+// column-side gradients (dK, dK', dV) in a second, column-parallel phase.
 #include "acsr_common.cuh"
 #include "../../include/acsr.h"
 
@@ -62,26 +65,33 @@ struct RowP {
   float Psoft[JPL], P[JPL], P0soft[JPL], P0[JPL], Msoft[JPL], M[JPL];
   float D1[JPL], D2[JPL], D3[JPL], nz[JPL];
   float O[JPL], A[JPL], expm[JPL], C[JPL], g[JPL], F[JPL], R[JPL], Rf[JPL];
-  bool inb[JPL];
+  bool inb[JPL];      // column exists (j < L)
+  bool act[JPL];      // column group intersects the causal triangle of this row (warp-uniform)
 };
 
 struct AttnSmem {
-  float *Q, *K, *V, *Q2, *K2;       // [L][dh+1]
+  float *Q, *K, *V, *Q2, *K2;                        // [L][dh+1]
   float *rowO, *rowD, *colO, *colD, *logd, *keyok;   // [L]
 };
 
+// fast-math forms (ex2/lg2/rcp approx, ~2 ulp): far inside the 1e-3 parity budget, ~10x fewer instructions
+__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+__device__ __forceinline__ float flog(float x) { return __logf(x); }
+__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
 template <int JPL>
-__device__ __forceinline__ void softmax_row(const float* z, const bool* inb, float* y) {
+__device__ __forceinline__ void softmax_row(const float* z, const bool* inb, const bool* act, float* y) {
   float m = -INFINITY;
 #pragma unroll
-  for (int jj = 0; jj < JPL; ++jj) if (inb[jj]) m = fmaxf(m, z[jj]);
+  for (int jj = 0; jj < JPL; ++jj) if (act[jj] && inb[jj]) m = fmaxf(m, z[jj]);
   m = warp_max(m);
   float s = 0.f;
 #pragma unroll
-  for (int jj = 0; jj < JPL; ++jj) { y[jj] = inb[jj] ? expf(z[jj] - m) : 0.f; s += y[jj]; }
+  for (int jj = 0; jj < JPL; ++jj) { y[jj] = (act[jj] && inb[jj]) ? fexp(z[jj] - m) : 0.f; s += y[jj]; }
   s = warp_sum(s);
+  const float inv = 1.0f / s;
 #pragma unroll
-  for (int jj = 0; jj < JPL; ++jj) y[jj] = y[jj] / s;
+  for (int jj = 0; jj < JPL; ++jj) y[jj] *= inv;
 }
 
 // Y .* (dY - sum(Y .* dY))
@@ -137,29 +147,34 @@ __device__ __forceinline__ void row_forward(const AttnParams& p, const AttnSmem&
                                             bool need_att, RowP<JPL>& r) {
   constexpr int dhp = DH + 1;
   const int L = p.L;
-  const float sq = sqrtf((float)DH);
+  const float inv_sq = 1.0f / sqrtf((float)DH);
   int jr[JPL];
 #pragma unroll
   for (int jj = 0; jj < JPL; ++jj) {
     int j = lane + 32 * jj;
     r.inb[jj] = j < L;
+    r.act[jj] = (32 * jj) <= i;
     jr[jj] = j < L ? j : L - 1;
     r.S[jj] = 0.f; r.S2[jj] = 0.f;
   }
   const float* qi = sm.Q + i * dhp;
   const float* q2i = sm.Q2 + i * dhp;
-#pragma unroll 8
-  for (int c = 0; c < DH; ++c) {
-    const float qc = qi[c], q2c = q2i[c];
 #pragma unroll
-    for (int jj = 0; jj < JPL; ++jj) {
-      r.S[jj] = fmaf(qc, sm.K[jr[jj] * dhp + c], r.S[jj]);
-      r.S2[jj] = fmaf(q2c, sm.K2[jr[jj] * dhp + c], r.S2[jj]);
+  for (int jj = 0; jj < JPL; ++jj) {
+    if (!r.act[jj]) continue;
+    const float* kj = sm.K + jr[jj] * dhp;
+    const float* k2j = sm.K2 + jr[jj] * dhp;
+    float s = 0.f, s2 = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < DH; ++c) {
+      s = fmaf(qi[c], kj[c], s);
+      s2 = fmaf(q2i[c], k2j[c], s2);
     }
+    r.S[jj] = s; r.S2[jj] = s2;
   }
   const float ob = p.ob ? p.ob[0] : 0.f, db = p.db ? p.db[0] : 0.f;
   const float sc = p.scalar ? p.scalar[0] : 0.f;
-  const float sc2 = sc * sc;
+  const float sc2h = sc * sc * 0.5f;
   const float rowO = sm.rowO[i], rowD = sm.rowD[i];
   float zP[JPL], z0[JPL], zM[JPL];
 #pragma unroll
@@ -167,83 +182,92 @@ __device__ __forceinline__ void row_forward(const AttnParams& p, const AttnSmem&
     const int j = jr[jj];
     const bool valid = r.inb[jj] && (j <= i) && (sm.keyok[j] != 0.f);
     r.msk[jj] = valid ? 0.f : kMaskNeg;
-    float eo = 0.f, ed = 0.f;
     r.sig[jj] = 0.f; r.delta[jj] = 0.f;
+    zP[jj] = z0[jj] = zM[jj] = kMaskNeg;
+    if (!r.act[jj]) continue;
+    float eo = 0.f, ed = 0.f;
     if (p.ow) {
-      const float sg = sigmoidf_(rowO + sm.colO[j] + ob);
+      const float sg = fsigmoid(rowO + sm.colO[j] + ob);
       r.sig[jj] = sg;
-      eo = (j > i) ? logf(sg + kOrderEps) : logf((1.0f - sg) + kOrderEps);
+      eo = (j > i) ? flog(sg + kOrderEps) : flog((1.0f - sg) + kOrderEps);
     }
     if (p.dw) {
       const int dist = i > j ? i - j : j - i;
       const float dl = sm.logd[dist] - (rowD + sm.colD[j] + db);
       r.delta[jj] = dl;
-      ed = -(dl * dl) * sc2 / 2.0f;
+      ed = -(dl * dl) * sc2h;
     }
-    zP[jj] = (r.S[jj] + eo + ed) / sq + r.msk[jj];
-    z0[jj] = r.S[jj] / sq + r.msk[jj];
-    zM[jj] = r.S2[jj] / sq + r.msk[jj];
+    zP[jj] = (r.S[jj] + eo + ed) * inv_sq + r.msk[jj];
+    z0[jj] = r.S[jj] * inv_sq + r.msk[jj];
+    zM[jj] = r.S2[jj] * inv_sq + r.msk[jj];
   }
-  softmax_row<JPL>(zP, r.inb, r.Psoft);
-  softmax_row<JPL>(zM, r.inb, r.Msoft);
+  softmax_row<JPL>(zP, r.inb, r.act, r.Psoft);
+  softmax_row<JPL>(zM, r.inb, r.act, r.Msoft);
   const bool need_p0 = !p.two_level || p.probs != nullptr;
-  if (need_p0) softmax_row<JPL>(z0, r.inb, r.P0soft);
+  if (need_p0) softmax_row<JPL>(z0, r.inb, r.act, r.P0soft);
   // randomness
   const float inv_keep = p.p > 0.f ? 1.0f / (1.0f - p.p) : 1.0f;
+  const bool philox_drop = p.p > 0.f && p.D1 == nullptr;
+  const bool philox_noise = need_att && p.noise == nullptr && p.rng != nullptr;
 #pragma unroll
   for (int jj = 0; jj < JPL; ++jj) {
-    const long long e = (((long long)b * p.H + h) * L + i) * L + jr[jj];
     r.D1[jj] = r.D2[jj] = r.D3[jj] = 1.0f;
     r.nz[jj] = 0.f;
-    const bool philox_drop = p.p > 0.f && p.D1 == nullptr;
-    const bool philox_noise = need_att && p.noise == nullptr && p.rng != nullptr;
-    if (philox_drop || philox_noise) {
-      const uint4 w = philox4x32(p.rng->seed, p.rng->step, p.stream, (unsigned long long)e);
-      if (philox_drop) { r.D1[jj] = drop_mult(w.x, p.p, inv_keep); r.D3[jj] = drop_mult(w.y, p.p, inv_keep); }
-      if (philox_noise) r.nz[jj] = box_muller(w.z, w.w);
-      if (philox_drop && need_p0) {
-        const uint4 w2 = philox4x32(p.rng->seed, p.rng->step, p.stream + 1u, (unsigned long long)e);
-        r.D2[jj] = drop_mult(w2.x, p.p, inv_keep);
+    if (r.act[jj]) {
+      const long long e = (((long long)b * p.H + h) * L + i) * L + jr[jj];
+      if (philox_drop || philox_noise) {
+        const uint4 w = philox4x32(p.rng->seed, p.rng->step, p.stream, (unsigned long long)e);
+        if (philox_drop) { r.D1[jj] = drop_mult(w.x, p.p, inv_keep); r.D3[jj] = drop_mult(w.y, p.p, inv_keep); }
+        if (philox_noise) {
+          const float u1 = u32_to_unit(w.z), u2 = u32_to_unit(w.w);
+          r.nz[jj] = sqrtf(-2.0f * flog(u1)) * __cosf(6.283185307179586f * u2);
+        }
+        if (philox_drop && need_p0) {
+          const uint4 w2 = philox4x32(p.rng->seed, p.rng->step, p.stream + 1u, (unsigned long long)e);
+          r.D2[jj] = drop_mult(w2.x, p.p, inv_keep);
+        }
       }
+      if (p.D1) r.D1[jj] = p.D1[e];
+      if (p.D2) r.D2[jj] = p.D2[e];
+      if (p.D3) r.D3[jj] = p.D3[e];
+      if (p.noise) r.nz[jj] = p.noise[e];
     }
-    if (p.D1) r.D1[jj] = p.D1[e];
-    if (p.D2) r.D2[jj] = p.D2[e];
-    if (p.D3) r.D3[jj] = p.D3[e];
-    if (p.noise) r.nz[jj] = p.noise[e];
     r.P[jj] = r.Psoft[jj] * r.D1[jj];
     r.P0[jj] = need_p0 ? r.P0soft[jj] * r.D2[jj] : 0.f;
     r.M[jj] = r.Msoft[jj] * r.D3[jj];
     r.O[jj] = p.two_level ? r.P[jj] : r.P0[jj];
-    r.expm[jj] = expf(1.0f - r.M[jj]);
+    r.expm[jj] = r.act[jj] ? fexp(1.0f - r.M[jj]) : 0.f;
   }
   float z[JPL];
   if (need_att) {
 #pragma unroll
     for (int jj = 0; jj < JPL; ++jj) z[jj] = r.O[jj] * r.M[jj] + r.nz[jj] * (1.0f - r.M[jj]) + r.msk[jj];
-    softmax_row<JPL>(z, r.inb, r.A);
+    softmax_row<JPL>(z, r.inb, r.act, r.A);
   } else {
 #pragma unroll
     for (int jj = 0; jj < JPL; ++jj) r.A[jj] = 0.f;
   }
 #pragma unroll
   for (int jj = 0; jj < JPL; ++jj) z[jj] = r.O[jj] * r.expm[jj] + r.msk[jj];
-  softmax_row<JPL>(z, r.inb, r.C);
+  softmax_row<JPL>(z, r.inb, r.act, r.C);
   if (p.combine == ACSR_ATTN_COMBINE_FIXED) {
+    // layers.py:885: softmax(origin + 0.5*calibrated) has NO mask: columns above the diagonal hold exp(0)
+    bool all[JPL];
 #pragma unroll
-    for (int jj = 0; jj < JPL; ++jj) { z[jj] = r.O[jj] + 0.5f * r.C[jj]; r.g[jj] = 0.f; }
-    softmax_row<JPL>(z, r.inb, r.F);
+    for (int jj = 0; jj < JPL; ++jj) { z[jj] = r.O[jj] + 0.5f * r.C[jj]; r.g[jj] = 0.f; all[jj] = true; }
+    softmax_row<JPL>(z, r.inb, all, r.F);
 #pragma unroll
     for (int jj = 0; jj < JPL; ++jj) z[jj] = r.F[jj] + r.msk[jj];
   } else {
 #pragma unroll
     for (int jj = 0; jj < JPL; ++jj) {
       float g = p.comb_scalar;
-      if (p.combine == ACSR_ATTN_COMBINE_GATE) g = sigmoidf_(p.gate[((long long)b * L + i) * L + jr[jj]]);
+      if (p.combine == ACSR_ATTN_COMBINE_GATE && r.act[jj]) g = fsigmoid(p.gate[((long long)b * L + i) * L + jr[jj]]);
       r.g[jj] = g; r.F[jj] = 0.f;
       z[jj] = g * r.O[jj] + (1.0f - g) * r.C[jj] + r.msk[jj];
     }
   }
-  softmax_row<JPL>(z, r.inb, r.R);
+  softmax_row<JPL>(z, r.inb, r.act, r.R);
   float rr = 1.0f;
   if (!p.two_level) rr = (p.rich == ACSR_ATTN_RICH_TRAINABLE) ? p.rich_ratio[0] : 0.5f;
 #pragma unroll
@@ -271,7 +295,7 @@ __device__ __forceinline__ AttnSmem carve_common(float*& ptr, int L, int dh) {
 // forward
 // ------------------------------------------------------------------------------------------
 template <int DH, int JPL>
-__global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_fwd_kernel(const AttnParams p) {
   extern __shared__ float smem_f[];
   constexpr int dhp = DH + 1;
   using CM = CMap<DH>;
@@ -287,7 +311,10 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
   const bool need_att = p.ctx_att != nullptr;
   float pen = 0.f;
   RowP<JPL> r;
-  for (int i = warp; i < L; i += kAttnWarps) {
+  // rows are dealt so that every warp gets a similar amount of causal work (long and short rows alternate)
+  for (int rnd = 0; rnd * kAttnWarps < L; ++rnd) {
+    const int i = rnd * kAttnWarps + ((rnd & 1) ? (kAttnWarps - 1 - warp) : warp);   // snake order: balanced causal work
+    if (i >= L) continue;
     row_forward<DH, JPL>(p, sm, b, h, i, lane, need_att, r);
     float* bufR = rowbuf + (warp * 2 + 0) * L;
     float* bufA = rowbuf + (warp * 2 + 1) * L;
@@ -295,7 +322,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
     for (int jj = 0; jj < JPL; ++jj) {
       const int j = lane + 32 * jj;
       if (r.inb[jj]) {
-        const float om = 1.0f - r.M[jj];
+        const float om = 1.0f - r.M[jj];         // columns above the diagonal: M == 0 -> contributes 1
         pen += om * om;
         bufR[j] = r.Rf[jj];
         bufA[j] = r.A[jj];
@@ -308,11 +335,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
       }
     }
     __syncwarp();
-    // ctx[i][c] = sum_j prob[j] * V[j][c]
+    // ctx[i][c] = sum_{j<=i} prob[j] * V[j][c]
     float accR[CM::CPL], accA[CM::CPL];
 #pragma unroll
     for (int k = 0; k < CM::CPL; ++k) accR[k] = accA[k] = 0.f;
-    for (int j = CM::grp(lane); j < L; j += CM::G) {
+    for (int j = CM::grp(lane); j <= i; j += CM::G) {
       const float pr = bufR[j], pa = bufA[j];
 #pragma unroll
       for (int k = 0; k < CM::CPL; ++k) {
@@ -346,29 +373,31 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
+
 template <int DH, int JPL>
-__global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_kernel(const AttnParams p) {
   extern __shared__ float smem_f[];
   constexpr int dhp = DH + 1;
   using CM = CMap<DH>;
   const int L = p.L;
+  const int ntri = L * (L + 1) / 2;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* ptr = smem_f;
   AttnSmem sm = carve_common(ptr, L, DH);
   float* sDC = ptr; ptr += L * dhp;       // d_ctx_cal head slice
   float* sDA = ptr; ptr += L * dhp;       // d_ctx_att head slice
-  float* matS = ptr; ptr += L * L;        // dS   [i][j]
-  float* matS2 = ptr; ptr += L * L;       // dS'  [i][j]
-  float* matR = ptr; ptr += L * L;        // R_final
-  float* matA = ptr; ptr += L * L;        // A
+  float* matS = ptr; ptr += ntri;         // dS   (lower triangle, packed)
+  float* matS2 = ptr; ptr += ntri;        // dS'
+  float* matR = ptr; ptr += ntri;         // R_final
+  float* matA = ptr; ptr += ntri;         // A
   float* colDU = ptr; ptr += L;
   float* colDT = ptr; ptr += L;
   float* red = ptr; ptr += kAttnWarps * 8;   // scalar partials per warp
   const bool has_att = p.d_ctx_att != nullptr;
   const bool has_cal = p.d_ctx_cal != nullptr;
 
-  // stage cotangent tiles
   for (int e = threadIdx.x; e < L * DH; e += blockDim.x) {
     const int rr = e / DH, c = e % DH;
     const long long o = ((long long)b * L + rr) * p.d + h * DH + c;
@@ -378,42 +407,45 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnParams
   for (int j = threadIdx.x; j < L; j += blockDim.x) { colDU[j] = 0.f; colDT[j] = 0.f; }
   stage_common<DH>(p, sm, b, h);     // ends with __syncthreads()
 
-  const float sq = sqrtf((float)DH);
+  const float inv_sq = 1.0f / sqrtf((float)DH);
   const float dpen = p.d_pen ? p.d_pen[0] : 0.f;
   const float sc = p.scalar ? p.scalar[0] : 0.f;
   const float sc2 = sc * sc;
   float rr = 1.0f;
   if (!p.two_level) rr = (p.rich == ACSR_ATTN_RICH_TRAINABLE) ? p.rich_ratio[0] : 0.5f;
 
-  // per-lane (lane = channel) accumulators of the spatial-calibrator weight gradients, q halves
   float accOq[CM::CPL], accDq[CM::CPL];
 #pragma unroll
   for (int k = 0; k < CM::CPL; ++k) accOq[k] = accDq[k] = 0.f;
   float s_ob = 0.f, s_db = 0.f, s_scalar = 0.f, s_ratio = 0.f;
 
   RowP<JPL> r;
-  for (int i = warp; i < L; i += kAttnWarps) {
+  for (int rnd = 0; rnd * kAttnWarps < L; ++rnd) {
+    const int i = rnd * kAttnWarps + ((rnd & 1) ? (kAttnWarps - 1 - warp) : warp);   // snake order: balanced causal work
+    if (i >= L) continue;
     row_forward<DH, JPL>(p, sm, b, h, i, lane, has_att, r);
     int jr[JPL];
 #pragma unroll
     for (int jj = 0; jj < JPL; ++jj) jr[jj] = (lane + 32 * jj) < L ? lane + 32 * jj : L - 1;
-    // dRf_j = dctx_cal_i . v_j ; dA_j = dctx_att_i . v_j
+    // dRf_j = dctx_cal_i . v_j ; dA_j = dctx_att_i . v_j   (only column groups that touch the triangle)
     float dRf[JPL], dA[JPL];
 #pragma unroll
-    for (int jj = 0; jj < JPL; ++jj) dRf[jj] = dA[jj] = 0.f;
-    for (int c = 0; c < DH; ++c) {
-      const float gc = sDC[i * dhp + c], ga = sDA[i * dhp + c];
-#pragma unroll
-      for (int jj = 0; jj < JPL; ++jj) {
-        const float v = sm.V[jr[jj] * dhp + c];
-        dRf[jj] = fmaf(gc, v, dRf[jj]);
-        dA[jj] = fmaf(ga, v, dA[jj]);
+    for (int jj = 0; jj < JPL; ++jj) {
+      dRf[jj] = dA[jj] = 0.f;
+      if (!r.act[jj]) continue;
+      const float* vj = sm.V + jr[jj] * dhp;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < DH; ++c) {
+        const float v = vj[c];
+        a0 = fmaf(sDC[i * dhp + c], v, a0);
+        a1 = fmaf(sDA[i * dhp + c], v, a1);
       }
+      if (r.inb[jj]) { dRf[jj] = a0; dA[jj] = a1; }
     }
     float dO[JPL], dP[JPL], dM[JPL], dR[JPL], dC[JPL], tmp[JPL], dcm[JPL];
 #pragma unroll
     for (int jj = 0; jj < JPL; ++jj) {
-      if (!r.inb[jj]) { dRf[jj] = 0.f; dA[jj] = 0.f; }
       dO[jj] = 0.f; dP[jj] = 0.f; dM[jj] = 0.f;
       if (p.two_level) dR[jj] = dRf[jj];
       else {
@@ -433,7 +465,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnParams
         const float g = r.g[jj];
         dO[jj] += dcm[jj] * g;
         dC[jj] = dcm[jj] * (1.0f - g);
-        if (p.combine == ACSR_ATTN_COMBINE_GATE && r.inb[jj]) {
+        if (p.combine == ACSR_ATTN_COMBINE_GATE && r.inb[jj] && r.act[jj]) {
           const float dgl = dcm[jj] * (r.O[jj] - r.C[jj]) * g * (1.0f - g);
           if (dgl != 0.f) atomicAdd(p.d_gate + ((long long)b * L + i) * L + jr[jj], dgl);
         }
@@ -456,31 +488,30 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnParams
     float dP0[JPL];
 #pragma unroll
     for (int jj = 0; jj < JPL; ++jj) {
-      if (r.inb[jj]) dM[jj] += dpen * (-2.0f) * (1.0f - r.M[jj]);
+      if (r.inb[jj] && r.act[jj]) dM[jj] += dpen * (-2.0f) * (1.0f - r.M[jj]);
       dM[jj] *= r.D3[jj];
       if (p.two_level) { dP[jj] += dO[jj]; dP0[jj] = 0.f; }
       else dP0[jj] = dO[jj] * r.D2[jj];
       dP[jj] *= r.D1[jj];
     }
-    float dS2[JPL], dz[JPL];
+    float dS2[JPL], dz[JPL], dS[JPL];
     softmax_bwd_row<JPL>(r.Msoft, dM, dS2);
     softmax_bwd_row<JPL>(r.Psoft, dP, dz);
-    float dS[JPL];
     float row_du = 0.f, row_dt = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < JPL; ++jj) { dS2[jj] /= sq; dz[jj] /= sq; dS[jj] = dz[jj]; }
+    for (int jj = 0; jj < JPL; ++jj) { dS2[jj] *= inv_sq; dz[jj] *= inv_sq; dS[jj] = dz[jj]; }
     if (!p.two_level) {
       softmax_bwd_row<JPL>(r.P0soft, dP0, tmp);
 #pragma unroll
-      for (int jj = 0; jj < JPL; ++jj) dS[jj] += tmp[jj] / sq;
+      for (int jj = 0; jj < JPL; ++jj) dS[jj] += tmp[jj] * inv_sq;
     }
 #pragma unroll
     for (int jj = 0; jj < JPL; ++jj) {
       const int j = lane + 32 * jj;
-      if (!r.inb[jj]) continue;
+      if (!r.inb[jj] || j > i) continue;             // everything above the diagonal is exactly zero
       if (p.ow) {
         const float sg = r.sig[jj];
-        const float de = (j > i) ? sg * (1.0f - sg) / (sg + kOrderEps) : -sg * (1.0f - sg) / ((1.0f - sg) + kOrderEps);
+        const float de = -sg * (1.0f - sg) / ((1.0f - sg) + kOrderEps);     // j <= i branch of layers.py:719
         const float du = dz[jj] * de;
         row_du += du;
         if (du != 0.f) atomicAdd(colDU + j, du);
@@ -492,22 +523,24 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnParams
         if (dt != 0.f) atomicAdd(colDT + j, dt);
         s_scalar += dz[jj] * (-(dl * dl) * sc);
       }
-      matS[i * L + j] = dS[jj];
-      matS2[i * L + j] = dS2[jj];
-      matR[i * L + j] = r.Rf[jj];
-      matA[i * L + j] = r.A[jj];
+      const int t = tri(i, j);
+      matS[t] = dS[jj];
+      matS2[t] = dS2[jj];
+      matR[t] = r.Rf[jj];
+      matA[t] = r.A[jj];
     }
     row_du = warp_sum(row_du);
     row_dt = warp_sum(row_dt);
-    s_ob += row_du;            // every lane holds the full row sum: divide by 32 at the end
+    s_ob += row_du;            // identical on every lane; lane 0 publishes it
     s_db += row_dt;
     __syncwarp();
-    // row-side gradients: dq_i, dq'_i  (lane = channel)
+    // row-side gradients: dq_i, dq'_i  (lane = channel, j <= i)
     float aq_[CM::CPL], aq2_[CM::CPL];
 #pragma unroll
     for (int k = 0; k < CM::CPL; ++k) aq_[k] = aq2_[k] = 0.f;
-    for (int j = CM::grp(lane); j < L; j += CM::G) {
-      const float s1 = matS[i * L + j], s2 = matS2[i * L + j];
+    const int tb = tri(i, 0);
+    for (int j = CM::grp(lane); j <= i; j += CM::G) {
+      const float s1 = matS[tb + j], s2 = matS2[tb + j];
 #pragma unroll
       for (int k = 0; k < CM::CPL; ++k) {
         const int c = CM::c(lane, k);
@@ -530,7 +563,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnParams
     }
   }
   __syncthreads();
-  // column-side gradients: dk_j, dk'_j, dv_j  (warp per column, lane = channel)
+  // column-side gradients: dk_j, dk'_j, dv_j  (warp per column, lane = channel, rows i >= j)
   float accOk[CM::CPL], accDk[CM::CPL];
 #pragma unroll
   for (int k = 0; k < CM::CPL; ++k) accOk[k] = accDk[k] = 0.f;
@@ -538,8 +571,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnParams
     float ak_[CM::CPL], ak2_[CM::CPL], av_[CM::CPL];
 #pragma unroll
     for (int k = 0; k < CM::CPL; ++k) ak_[k] = ak2_[k] = av_[k] = 0.f;
-    for (int i = CM::grp(lane); i < L; i += CM::G) {
-      const float s1 = matS[i * L + j], s2 = matS2[i * L + j], pr = matR[i * L + j], pa = matA[i * L + j];
+    for (int i = j + CM::grp(lane); i < L; i += CM::G) {
+      const int t = tri(i, j);
+      const float s1 = matS[t], s2 = matS2[t], pr = matR[t], pa = matA[t];
 #pragma unroll
       for (int k = 0; k < CM::CPL; ++k) {
         const int c = CM::c(lane, k);
@@ -593,23 +627,31 @@ static size_t fwd_smem_bytes(int L, int dh) {
   return f * sizeof(float) + kAttnWarps * sizeof(double);
 }
 static size_t bwd_smem_bytes(int L, int dh) {
-  size_t f = (size_t)7 * L * (dh + 1) + 6 * L + (size_t)4 * L * L + 2 * L + kAttnWarps * 8;
+  size_t f = (size_t)7 * L * (dh + 1) + 6 * L + (size_t)4 * (L * (L + 1) / 2) + 2 * L + kAttnWarps * 8;
   return f * sizeof(float);
+}
+
+template <typename K>
+static int prep_kernel(K kernel, size_t smem, const char* who) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e != cudaSuccess) { set_error("%s: smem %zu: %s", who, smem, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
+  return ACSR_OK;
 }
 
 template <int DH, int JPL>
 static int launch_fwd(const AttnParams& p, cudaStream_t st) {
   size_t smem = fwd_smem_bytes(p.L, DH);
-  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<DH, JPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("attn_calib_fwd: smem %zu: %s", smem, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
+  int rc = prep_kernel(attn_fwd_kernel<DH, JPL>, smem, "attn_calib_fwd");
+  if (rc) return rc;
   attn_fwd_kernel<DH, JPL><<<p.B * p.H, kAttnThreads, smem, st>>>(p);
   return check_launch("attn_calib_fwd");
 }
 template <int DH, int JPL>
 static int launch_bwd(const AttnParams& p, cudaStream_t st) {
   size_t smem = bwd_smem_bytes(p.L, DH);
-  cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<DH, JPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("attn_calib_bwd: smem %zu: %s", smem, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
+  int rc = prep_kernel(attn_bwd_kernel<DH, JPL>, smem, "attn_calib_bwd");
+  if (rc) return rc;
   attn_bwd_kernel<DH, JPL><<<p.B * p.H, kAttnThreads, smem, st>>>(p);
   return check_launch("attn_calib_bwd");
 }

@@ -2,7 +2,7 @@
 // with the consumer fused into the TMEM epilogue so the [M,V] logits never reach HBM:
 //   MODE_STORE : plain scores (full_sort_predict)                  acsasrec.py:162-163
 //   MODE_CE    : per-row running (max, sum exp) -> cross entropy   acsasrec.py:118-120
-//   MODE_GRAD  : G = (softmax - onehot) * row_scale (CE backward)
+//   MODE_GRAD  : Gt[V,M] = ((softmax - onehot) * row_scale)^T (CE backward)
 //   MODE_TOPK  : streaming per-row top-k, column 0 excluded         trainer.py:941-942, collector.py:147
 //
 // Warp-specialised persistent CTA (320 threads, one per SM):
@@ -72,17 +72,28 @@ struct TcCfg {
   static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
 };
 
-// thread-private sorted (descending) top-k list, slot-major so that lane == bank for every slot
-__device__ __noinline__ void topk_insert(float x, int col, float* lval, int* lidx, int row, int k, int& cnt, float& thr) {
-  int pos = cnt < k ? cnt++ : k - 1;
-  while (pos > 0 && lval[(pos - 1) * kBM + row] < x) {
-    lval[pos * kBM + row] = lval[(pos - 1) * kBM + row];
-    lidx[pos * kBM + row] = lidx[(pos - 1) * kBM + row];
-    --pos;
+// Thread-private top-k candidate set kept UNSORTED with a cached minimum (slot-major in shared memory so
+// lane == bank for every slot).  A new score replaces the current minimum and the k slots are rescanned
+// with independent loads -- no dependent shift chain as in a sorted insert; acsr_topk_merge sorts at the end.
+__device__ __noinline__ void topk_insert(float x, int col, float* lval, int* lidx, int row, int k, int& cnt, float& thr,
+                                         int& minpos) {
+  if (cnt < k) {
+    lval[cnt * kBM + row] = x;
+    lidx[cnt * kBM + row] = col;
+    if (++cnt < k) return;
+  } else {
+    lval[minpos * kBM + row] = x;
+    lidx[minpos * kBM + row] = col;
   }
-  lval[pos * kBM + row] = x;
-  lidx[pos * kBM + row] = col;
-  if (cnt == k) thr = lval[(k - 1) * kBM + row];
+  float m = lval[row];
+  int mp = 0;
+#pragma unroll 8
+  for (int s = 1; s < k; ++s) {
+    const float v = lval[s * kBM + row];
+    if (v < m) { m = v; mp = s; }
+  }
+  thr = m;
+  minpos = mp;
 }
 
 template <int MODE>
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
     long long g_tgt = -1;
     float* lval = reinterpret_cast<float*>(smem + Cfg::kOffTopk);           // [k][128]
     int* lidx = reinterpret_cast<int*>(smem + Cfg::kOffTopk + kMaxTopK * kBM * 4);
-    int cnt = 0;
+    int cnt = 0, minpos = 0;
     float thr = -INFINITY;
     if (MODE == MODE_GRAD && row_ok) { g_lse = p.lse[grow]; g_scale = p.row_scale[grow]; g_tgt = p.target[grow]; }
     for (int it = 0; it < my_tiles; ++it) {
@@ -240,16 +251,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
         tmem_ld32(t_lane + ob * kBN + cc * 32, v);
         const long long c0 = n0 + cc * 32;
         const int nvalid = (int)((p.V - c0) < 32 ? ((p.V - c0) > 0 ? (p.V - c0) : 0) : 32);
-        if (MODE == MODE_STORE || MODE == MODE_GRAD) {
+        if (MODE == MODE_GRAD) {
+          // transposed store Gt[v][m]: a warp's 32 rows are 32 consecutive floats -> coalesced 128-byte lines
           if (row_ok) {
-            if (MODE == MODE_GRAD) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float g = expf(v[i] - g_lse);
+            for (int i = 0; i < 32; ++i) {
+              if (i < nvalid) {
+                float g = __expf(v[i] - g_lse);
                 if (c0 + i == g_tgt) g -= 1.0f;
-                v[i] = g * g_scale;
+                p.C[(c0 + i) * p.ldc + grow] = g * g_scale;
               }
             }
+          }
+        } else if (MODE == MODE_STORE) {
+          if (row_ok) {
             float* dst = p.C + (long long)grow * p.ldc + c0;
             if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -267,8 +282,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
             const float nm = fmaxf(run_m, cm);
             float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (i < nvalid) s += expf(v[i] - nm);
-            run_s = run_s * expf(run_m - nm) + s;
+            for (int i = 0; i < 32; ++i) if (i < nvalid) s += __expf(v[i] - nm);
+            run_s = run_s * __expf(run_m - nm) + s;
             run_m = nm;
           }
         } else {   // MODE_TOPK
@@ -277,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
           for (int i = 0; i < 32; ++i) {
             const float x = v[i];
             if (i < nvalid && !(p.skip_col0 && c0 + i == 0) && (cnt < k || x > thr))
-              topk_insert(x, (int)(c0 + i), lval, lidx, row, k, cnt, thr);
+              topk_insert(x, (int)(c0 + i), lval, lidx, row, k, cnt, thr, minpos);
           }
           __syncwarp();
         }
@@ -418,7 +433,7 @@ int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, 
                         int64_t V, int d, int passes, float* G, int64_t ldg, void* stream) {
   int rc = validate_common(out, table, M, V, d, passes, "logits_ce_grad");
   if (rc) return rc;
-  ACSR_REQUIRE(lse && target && row_scale && G && ldg >= V, "logits_ce_grad: bad arguments");
+  ACSR_REQUIRE(lse && target && row_scale && G && ldg >= M, "logits_ce_grad: bad arguments");
   LogitsParams p = {};
   p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.C = G; p.ldc = ldg;
   p.lse = lse; p.target = (const long long*)target; p.row_scale = row_scale;

@@ -71,9 +71,9 @@ class FeedForward(nn.Module):
     def forward(self, input_tensor, rt=None, mask_key=None, rng_stream=0):
         rt = rt or default_runtime(input_tensor.device)
         p = self.dropout.p if self.training else 0.0
-        z = F.linear(input_tensor, self.dense_1.weight)
+        z = ops.linear(input_tensor, self.dense_1.weight)
         z = ops.BiasActFn.apply(z, self.dense_1.bias, ops.ACT_IDS[self.hidden_act])
-        z = F.linear(z, self.dense_2.weight)
+        z = ops.linear(z, self.dense_2.weight)
         return ops.BiasDropoutResLnFn.apply(z, self.dense_2.bias, input_tensor, self.LayerNorm.weight, self.LayerNorm.bias,
                                             self.LayerNorm.eps, p, rt.mask(mask_key) if p > 0 else None, rt.rng, rng_stream)
 
@@ -112,7 +112,7 @@ class AttackRMultiHeadAttention(nn.Module):
         """layers.py:676-684 after probs.V: dense -> dropout -> LN(. + input)."""
         rt = rt or default_runtime(input_tensor.device)
         p = self.out_dropout.p if self.training else 0.0
-        h = F.linear(context_layer, self.dense.weight)
+        h = ops.linear(context_layer, self.dense.weight)
         return ops.BiasDropoutResLnFn.apply(h, self.dense.bias, input_tensor, self.LayerNorm.weight, self.LayerNorm.bias,
                                             self.LayerNorm.eps, p, rt.mask(mask_key) if p > 0 else None, rt.rng, rng_stream)
 
@@ -159,16 +159,16 @@ class AttackRTransformerLayer(nn.Module):
         x = hidden_states
         B, L, d = x.shape
         key_ids = key_ids_from_mask(attention_mask)
-        mq = F.linear(x, aa.query.weight, aa.query.bias)
-        mk = F.linear(x, aa.key.weight, aa.key.bias)
-        mv = F.linear(x, aa.value.weight, aa.value.bias)
-        aq = F.linear(mq, aa.attack_query_transform.weight, aa.attack_query_transform.bias)
-        ak = F.linear(mk, aa.attack_key_transform.weight, aa.attack_key_transform.bias)
+        mq = ops.linear(x, aa.query.weight, aa.query.bias)
+        mk = ops.linear(x, aa.key.weight, aa.key.bias)
+        mv = ops.linear(x, aa.value.weight, aa.value.bias)
+        aq = ops.linear(mq, aa.attack_query_transform.weight, aa.attack_query_transform.bias)
+        ak = ops.linear(mk, aa.attack_key_transform.weight, aa.attack_key_transform.bias)
         gate_logit, comb_scalar = None, 0.0
         if self.combine_option == 'gate':
             if self.gate.out_features != L:
                 raise ValueError('gate width %d != sequence length %d (layers.py:878/887)' % (self.gate.out_features, L))
-            gate_logit = F.linear(mq, self.gate.weight, self.gate.bias)
+            gate_logit = ops.linear(mq, self.gate.weight, self.gate.bias)
         elif self.combine_option == 'annealing':
             comb_scalar = math.exp(-self.anneal_step / 100000)      # layers.py:889-891
             self.anneal_step += 1

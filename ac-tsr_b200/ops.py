@@ -262,20 +262,63 @@ def ce_finalize(partial, out, table, target, n_groups, idx_offset=0):
     return lse, tgt, row_loss, loss
 
 
-def ce_grad_matrix(out, table, lse, target, row_scale, passes=3):
-    """G [M, V] (row stride padded to 4) = (softmax - onehot) * row_scale."""
+def ce_grad_matrix_t(out, table, lse, target, row_scale, passes=3):
+    """Gt [V, M] = ((softmax - onehot) * row_scale)^T  (transposed so the epilogue's stores coalesce)."""
     M, d = out.shape
     V = table.shape[0]
-    ld = (V + 3) // 4 * 4
-    G = torch.empty((M, ld), dtype=torch.float32, device=out.device)
+    Gt = torch.empty((V, M), dtype=torch.float32, device=out.device)
     LIB.call('acsr_logits_ce_grad', _p(out), _p(table), _p(lse), _p(target, torch.int64), _p(row_scale), M, V, d, passes,
-             _p(G), ld, _stream())
-    return G[:, :V]
+             _p(Gt), M, _stream())
+    return Gt
+
+
+def linear_wgrad(dY, X, dW=None, db=None, want_bias=True):
+    """dW [N,K] += dY^T.X and db [N] += colsum(dY) with the token axis split over the GPU (acsr_linear_wgrad)."""
+    N, K = dY.shape[-1], X.shape[-1]
+    dY2, X2 = dY.reshape(-1, N), X.reshape(-1, K)
+    if not dY2.is_contiguous():
+        dY2 = dY2.contiguous()
+    if not X2.is_contiguous():
+        X2 = X2.contiguous()
+    if dW is None:
+        dW = torch.zeros((N, K), dtype=torch.float32, device=dY.device)
+    if db is None and want_bias:
+        db = torch.zeros(N, dtype=torch.float32, device=dY.device)
+    LIB.call('acsr_linear_wgrad', _p(dY2), _p(X2), dY2.shape[0], N, K, _p(dW), _p(db), _stream())
+    return dW, db
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x.W^T (+ b).  Forward and dX are library GEMMs; dW/db use the token-split kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        x2 = x.reshape(-1, x.shape[-1])
+        y = torch.addmm(bias, x2, weight.t()) if bias is not None else x2 @ weight.t()
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (dy.reshape(-1, dy.shape[-1]) @ weight).view_as(x)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dW, db = linear_wgrad(dy, x, want_bias=ctx.has_bias)
+        return dx, dW, db
+
+
+def linear(x, weight, bias=None):
+    return LinearFn.apply(x, weight, bias)
 
 
 class LogitsCEFn(torch.autograd.Function):
     """loss[g] = mean CE over row group g of softmax(out.E^T) vs target -- acsasrec.py:117-121.
-    Logits never materialise in the forward; the backward writes G once and uses two GEMMs."""
+    Logits never materialise in the forward; the backward writes Gt once, then d_E = Gt.out (library
+    GEMM) and d_out = Gt^T.E (token-split kernel, reduction over the catalogue)."""
 
     @staticmethod
     def forward(ctx, out, table, target, n_groups, passes):
@@ -293,9 +336,9 @@ class LogitsCEFn(torch.autograd.Function):
         M = out.shape[0]
         per = M // n_groups
         row_scale = (d_loss.to(torch.float32) / per).view(n_groups, 1).expand(n_groups, per).reshape(-1).contiguous()
-        G = ce_grad_matrix(out, table, lse, target, row_scale, passes)
-        d_out = G @ table if ctx.needs_input_grad[0] else None
-        d_table = G.t() @ out if ctx.needs_input_grad[1] else None
+        Gt = ce_grad_matrix_t(out, table, lse, target, row_scale, passes)
+        d_out = linear_wgrad(Gt, table, want_bias=False)[0] if ctx.needs_input_grad[0] else None
+        d_table = Gt @ out if ctx.needs_input_grad[1] else None
         return d_out, d_table, None, None, None
 
 

@@ -327,6 +327,27 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_profile(args):
+    """Same kernels as the timed step, launched eagerly so ncu lists them one by one (never a bench value)."""
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    import __graft_entry__ as ge
+    ge.build()
+    A, cfg, config, model, trainer = build(dev, 0, 1, cuda_graph=False)
+    B, L, V = WORKLOAD['B'], WORKLOAD['L'], WORKLOAD['V']
+    seq, ln, tgt = A.data.synth_sequences(B, L, V, seed=42)
+    b = A.Interaction({'item_id_list': seq, 'item_length': ln, 'item_id': tgt}).to(dev)
+    model.train()
+    for _ in range(args.warmup + args.steps):
+        trainer.train_step(b)
+    model.eval()
+    with torch.no_grad():
+        for _ in range(args.steps):
+            model.full_sort_topk(b, WORKLOAD['topk'], b['item_id'])
+    torch.cuda.synchronize()
+    print('profile run done')
+
+
 # ------------------------------------------------------------------------------------------------
 def oracle_step_fn(cfg, B, L, V, seed=42):
     """one reference-semantics training step on the CPU (oracle port): losses, two routed backward passes, Adam."""
@@ -405,7 +426,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', action='store_true',
+                    help='launch-list mode for ncu: W+K eager training steps and K eval batches, nothing else')
     args = ap.parse_args()
+    if args.profile:
+        return run_profile(args)
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -154,20 +154,25 @@ int acsr_logits_ce_partial(const float* out, const float* table, int M, int64_t 
 int acsr_ce_finalize(const float* partial, int n_parts, const float* out, const float* table,
                      const int64_t* target, int M, int d, int64_t V, int64_t idx_offset, int n_groups,
                      float* lse, float* tgt_logit, float* row_loss, float* loss, void* stream);
-/* CE backward part 1: G [M, ldg] = (exp(out.E^T - lse) - onehot(target)) * row_scale[m]
- * (then d_out = G.E and d_E = G^T.out are plain GEMMs). */
+/* CE backward part 1: Gt [V, ldg] (ldg >= M) = transpose of (exp(out.E^T - lse) - onehot(target)) * row_scale[m];
+ * then d_E = Gt.out is a plain GEMM and d_out = Gt^T.E goes through acsr_linear_wgrad (reduction over V). */
 int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, const int64_t* target,
                         const float* row_scale, int M, int64_t V, int d, int passes,
-                        float* G, int64_t ldg, void* stream);
-/* fused logits + streaming top-k: partial_val/partial_idx [M, n_chunks, k] (descending, padded with
- * -inf/-1); column 0 is excluded (trainer.py:942); idx_offset is added to indices (vocab shards). */
+                        float* Gt, int64_t ldg, void* stream);
+/* fused logits + streaming top-k: partial_val/partial_idx [M, n_chunks, k] (each chunk's k best, UNSORTED,
+ * padded with -inf/-1); column 0 is excluded (trainer.py:942); idx_offset is added to indices (vocab shards). */
 int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_t V, int d, int passes,
                              int k, int64_t idx_offset, int skip_col0,
                              float* partial_val, int64_t* partial_idx, void* stream);
-/* merge n_parts sorted partial lists per row -> topk_val [M,k], topk_idx [M,k] int64 and, when
+/* merge n_parts partial lists per row (any order) -> topk_val [M,k], topk_idx [M,k] int64 and, when
  * positive != NULL, rec_topk [M,k+1] int32 = hit flags + pos_len(=1) (collector.py:148-153). */
 int acsr_topk_merge(const float* partial_val, const int64_t* partial_idx, int M, int n_parts, int k,
                     const int64_t* positive, float* topk_val, int64_t* topk_idx, int32_t* rec_topk, void* stream);
+
+/* ---- weight / bias gradient of a token-parallel linear layer (backward of the nn.Linear calls in
+ * layers.py:658-659, 687-689, 680, 791-794, 887):  dW[N,K] += dY[T,N]^T . X[T,K],  db[N] += sum_t dY[t,:]
+ * (db may be NULL).  Accumulates with atomics: the caller zeroes or passes its gradient buffer. */
+int acsr_linear_wgrad(const float* dY, const float* X, int T, int N, int K, float* dW, float* db, void* stream);
 
 /* ---- K13: fused Adam over one flat fp32 buffer (trainer/trainer.py:614-615,687) ---------
  * torch.optim.Adam semantics (no amsgrad); step_count device int64[1], incremented by the call. */

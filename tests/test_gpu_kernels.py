@@ -390,3 +390,25 @@ def test_unsupported_shapes_fail_loudly(A):
         A.ops.logits_scores(torch.randn(4, 64), torch.randn(10, 64), 3)                       # CPU tensors
     with pytest.raises(A.AcsrError):
         A.ops.BiasActFn.apply(torch.randn(4, 6).cuda(), None, 0)                              # n % 4
+
+
+@pytest.mark.parametrize('T,N,K', [(12800, 64, 64), (12800, 50, 64), (12800, 256, 64), (12800, 64, 256), (777, 128, 128),
+                                   (12102, 512, 64), (5, 64, 64), (3000, 1024, 256)])
+def test_linear_wgrad_and_linear_fn(A, T, N, K):
+    g = torch.Generator().manual_seed(T + N + K)
+    dY, X = torch.randn(T, N, generator=g), torch.randn(T, K, generator=g)
+    dW, db = A.ops.linear_wgrad(dY.cuda(), X.cuda())
+    close(dW, dY.double().t() @ X.double(), 2e-5, 'dW')
+    close(db, dY.double().sum(0), 2e-5, 'db')
+    # accumulate semantics: a second call adds on top
+    dW2, db2 = A.ops.linear_wgrad(dY.cuda(), X.cuda(), dW.clone(), db.clone())
+    close(dW2, 2 * (dY.double().t() @ X.double()), 2e-5, 'dW accumulate')
+    if T <= 1000:
+        W, b = torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+        xo, Wo, bo = X.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        (torch.nn.functional.linear(xo, Wo, bo) * dY).sum().backward()
+        xc, Wc, bc = X.clone().cuda().requires_grad_(True), W.clone().cuda().requires_grad_(True), b.clone().cuda().requires_grad_(True)
+        y = A.ops.linear(xc.view(1, T, K), Wc, bc)
+        assert y.shape == (1, T, N)
+        (y * dY.cuda().view(1, T, N)).sum().backward()
+        close(xc.grad, xo.grad, 2e-5, 'dx'); close(Wc.grad, Wo.grad, 2e-5, 'dW'); close(bc.grad, bo.grad, 2e-5, 'db')

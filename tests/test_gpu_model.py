@@ -201,8 +201,8 @@ def test_full_size_properties_beauty_shape(A):
     ref = (torch.logsumexp(scores.double(), 1) - scores.double()[torch.arange(B), inter['item_id']]).mean()
     assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
     lse = torch.logsumexp(scores.double(), 1).float()
-    G = A.ops.ce_grad_matrix(out.detach(), E.detach(), lse, inter['item_id'], torch.ones(B).cuda(), 3)
-    assert float(G.double().sum(1).abs().max()) < 1e-4
+    Gt = A.ops.ce_grad_matrix_t(out.detach(), E.detach(), lse, inter['item_id'], torch.ones(B).cuda(), 3)
+    assert float(Gt.double().sum(0).abs().max()) < 1e-4
     # a padded-key change must not leak: padding positions never influence the calibrated output
     seq2 = seq.clone()
     rows = torch.arange(B)
