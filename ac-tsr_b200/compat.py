@@ -122,7 +122,7 @@ _DEFAULTS = dict(
     rm_dup_inter=None, val_interval=None, filter_inter_by_user_or_item=True, user_inter_num_interval=None,
     item_inter_num_interval=None, neg_sampling=None, benchmark_filename=None, seq_len=None,
     # B200 build additions (ignored by the reference)
-    logits_passes=3, cuda_graph=True, fused_topk=True,
+    logits_passes=3, cuda_graph=True, fused_topk=True, fused_step=True,
 )
 
 _yaml_loader = yaml.FullLoader

@@ -743,8 +743,7 @@ int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const fl
   if (rc) return rc;
   ACSR_REQUIRE(d_mq && d_mk && d_mv && d_aq && d_ak, "attn_calib_bwd: NULL output");
   ACSR_REQUIRE(combine_option != ACSR_ATTN_COMBINE_GATE || d_gate_logit != nullptr, "attn_calib_bwd: d_gate_logit is NULL");
-  ACSR_REQUIRE((order_w == nullptr) || (d_order_w && d_order_b), "attn_calib_bwd: d_order_* is NULL");
-  ACSR_REQUIRE((dist_w == nullptr) || (d_dist_w && d_dist_b && d_scalar), "attn_calib_bwd: d_dist_* is NULL");
+  // d_order_*, d_dist_*, d_scalar, d_rich_ratio may be NULL: that cotangent stream does not own those parameters
   ATTN_DISPATCH(launch_bwd, p, (cudaStream_t)stream);
   return ACSR_ERR_UNSUPPORTED;
 }

@@ -1,83 +1,119 @@
 // Weight / bias gradient of a token-parallel linear layer:  dW[N,K] += dY[T,N]^T . X[T,K],  db[N] += sum_t dY.
 // T (tokens) is the long axis (12,800 per step) and the output is tiny (64x64 ... 256x64), the
-// shape library GEMMs handle worst (one split-K CTA per output tile).  Here the token axis is split
-// over the whole GPU: every CTA stages 16-token slabs of dY and X in shared memory, accumulates a
-// register tile per thread in exact fp32 FMAs and finishes with one atomic add per output element,
-// so the gradient lands directly in the caller's (flat) gradient buffer.
-// Also used for d_out = G.E of the CE backward (reduction over the catalogue axis).
+// shape library GEMMs handle worst (one split-K CTA per output tile, ~40 us each on B200).
+// Decomposition: the output is cut into small (8R x 8R) tiles and the token axis into `splits`
+// ranges so that ~4 CTAs per SM are busy while the number of atomics (N*K*splits) stays small.
+// Inside a CTA four 64-thread groups take every fourth token of a 64-token shared-memory slab,
+// each thread accumulates an R x R register tile in exact fp32 FMAs, the four partial tiles are
+// summed through shared memory and one atomic per output element lands the result directly in the
+// caller's (flat) gradient buffer.  Also used for d_out = G.E of the CE backward (reduction over V).
 #include "acsr_common.cuh"
 #include "../../include/acsr.h"
 
 namespace acsr {
 
 constexpr int kWgThreads = 256;
-constexpr int kWgTT = 16;          // tokens per shared-memory slab
+constexpr int kWgSlab = 64;        // tokens per shared-memory slab
 
-template <int TN, int TK>
+template <int R>
 __global__ void __launch_bounds__(kWgThreads)
 linear_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int T, int N, int K, int tok_per_cta,
                     int tiles_k, float* __restrict__ dW, float* __restrict__ db) {
-  constexpr int TILE_N = 16 * TN, TILE_K = 16 * TK;
-  __shared__ __align__(16) float sY[kWgTT][TILE_N];
-  __shared__ __align__(16) float sX[kWgTT][TILE_K];
+  constexpr int TILE = 8 * R;
+  __shared__ __align__(16) float sY[kWgSlab][TILE];
+  __shared__ __align__(16) float sX[kWgSlab][TILE];
+  __shared__ float sRed[3][64][R * R + R];
   const int tile_n = blockIdx.y / tiles_k, tile_k = blockIdx.y % tiles_k;
-  const int n0 = tile_n * TILE_N, k0 = tile_k * TILE_K;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // tx -> k sub-tile, ty -> n sub-tile
+  const int n0 = tile_n * TILE, k0 = tile_k * TILE;
+  const int grp = threadIdx.x >> 6, u = threadIdx.x & 63;
+  const int ty = u >> 3, tx = u & 7;                 // ty -> n sub-tile, tx -> k sub-tile
   const int t_begin = blockIdx.x * tok_per_cta;
   const int t_end = min(T, t_begin + tok_per_cta);
-  float acc[TN][TK];
-  float accb[TN];
+  const bool vecY = (N % 4 == 0) && (n0 + TILE <= N), vecX = (K % 4 == 0) && (k0 + TILE <= K);
+  float acc[R][R], accb[R];
 #pragma unroll
-  for (int a = 0; a < TN; ++a) {
+  for (int a = 0; a < R; ++a) {
     accb[a] = 0.f;
 #pragma unroll
-    for (int c = 0; c < TK; ++c) acc[a][c] = 0.f;
+    for (int c = 0; c < R; ++c) acc[a][c] = 0.f;
   }
-  for (int t0 = t_begin; t0 < t_end; t0 += kWgTT) {
-    // stage (zero-fill outside the matrix so the inner loop is branch-free)
-    for (int e = threadIdx.x; e < kWgTT * TILE_N; e += kWgThreads) {
-      const int tt = e / TILE_N, n = e % TILE_N;
-      const int t = t0 + tt;
-      sY[tt][n] = (t < t_end && n0 + n < N) ? dY[(long long)t * N + n0 + n] : 0.f;
+  // software pipeline: the next 64-token slab is fetched into registers while the current one is consumed
+  constexpr int NV = kWgSlab * TILE / 4 / kWgThreads;      // float4 per thread per matrix per slab
+  float4 ry[NV], rx[NV];
+  auto fetch = [&](int t0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = threadIdx.x + i * kWgThreads;
+      const int tt = e / (TILE / 4), q = e % (TILE / 4), t = t0 + tt;
+      ry[i] = rx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < t_end) {
+        const float* py = dY + (long long)t * N + n0 + 4 * q;
+        const float* px = X + (long long)t * K + k0 + 4 * q;
+        if (vecY) ry[i] = *reinterpret_cast<const float4*>(py);
+        else {
+          if (n0 + 4 * q + 0 < N) ry[i].x = py[0];
+          if (n0 + 4 * q + 1 < N) ry[i].y = py[1];
+          if (n0 + 4 * q + 2 < N) ry[i].z = py[2];
+          if (n0 + 4 * q + 3 < N) ry[i].w = py[3];
+        }
+        if (vecX) rx[i] = *reinterpret_cast<const float4*>(px);
+        else {
+          if (k0 + 4 * q + 0 < K) rx[i].x = px[0];
+          if (k0 + 4 * q + 1 < K) rx[i].y = px[1];
+          if (k0 + 4 * q + 2 < K) rx[i].z = px[2];
+          if (k0 + 4 * q + 3 < K) rx[i].w = px[3];
+        }
+      }
     }
-    for (int e = threadIdx.x; e < kWgTT * TILE_K; e += kWgThreads) {
-      const int tt = e / TILE_K, k = e % TILE_K;
-      const int t = t0 + tt;
-      sX[tt][k] = (t < t_end && k0 + k < K) ? X[(long long)t * K + k0 + k] : 0.f;
+  };
+  if (t_begin < t_end) fetch(t_begin);
+  for (int t0 = t_begin; t0 < t_end; t0 += kWgSlab) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = threadIdx.x + i * kWgThreads;
+      const int tt = e / (TILE / 4), q = e % (TILE / 4);
+      *reinterpret_cast<float4*>(&sY[tt][4 * q]) = ry[i];
+      *reinterpret_cast<float4*>(&sX[tt][4 * q]) = rx[i];
     }
     __syncthreads();
+    if (t0 + kWgSlab < t_end) fetch(t0 + kWgSlab);
+#pragma unroll 4
+    for (int tt = grp; tt < kWgSlab; tt += 4) {
+      float y[R], x[R];
 #pragma unroll
-    for (int tt = 0; tt < kWgTT; ++tt) {
-      float y[TN], x[TK];
+      for (int a = 0; a < R; ++a) { y[a] = sY[tt][ty * R + a]; x[a] = sX[tt][tx * R + a]; }
 #pragma unroll
-      for (int a = 0; a < TN; a += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(&sY[tt][ty * TN + a]);
-        y[a] = v.x; y[a + 1] = v.y; y[a + 2] = v.z; y[a + 3] = v.w;
-      }
-#pragma unroll
-      for (int c = 0; c < TK; c += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(&sX[tt][tx * TK + c]);
-        x[c] = v.x; x[c + 1] = v.y; x[c + 2] = v.z; x[c + 3] = v.w;
-      }
-#pragma unroll
-      for (int a = 0; a < TN; ++a) {
+      for (int a = 0; a < R; ++a) {
         accb[a] += y[a];
 #pragma unroll
-        for (int c = 0; c < TK; ++c) acc[a][c] = fmaf(y[a], x[c], acc[a][c]);
+        for (int c = 0; c < R; ++c) acc[a][c] = fmaf(y[a], x[c], acc[a][c]);
       }
     }
     __syncthreads();
   }
+  // sum the four token groups, then one atomic per output element
+  if (grp > 0) {
 #pragma unroll
-  for (int a = 0; a < TN; ++a) {
-    const int n = n0 + ty * TN + a;
-    if (n >= N) continue;
+    for (int a = 0; a < R; ++a) {
+      sRed[grp - 1][u][R * R + a] = accb[a];
 #pragma unroll
-    for (int c = 0; c < TK; ++c) {
-      const int k = k0 + tx * TK + c;
-      if (k < K) atomicAdd(dW + (long long)n * K + k, acc[a][c]);
+      for (int c = 0; c < R; ++c) sRed[grp - 1][u][a * R + c] = acc[a][c];
     }
-    if (db != nullptr && tx == 0 && tile_k == 0) atomicAdd(db + n, accb[a]);
+  }
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      const int n = n0 + ty * R + a;
+      float bsum = accb[a] + sRed[0][u][R * R + a] + sRed[1][u][R * R + a] + sRed[2][u][R * R + a];
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        const int k = k0 + tx * R + c;
+        const float v = acc[a][c] + sRed[0][u][a * R + c] + sRed[1][u][a * R + c] + sRed[2][u][a * R + c];
+        if (n < N && k < K) atomicAdd(dW + (long long)n * K + k, v);
+      }
+      if (db != nullptr && tx == 0 && tile_k == 0 && n < N) atomicAdd(db + n, bsum);
+    }
   }
 }
 
@@ -89,19 +125,17 @@ extern "C" int acsr_linear_wgrad(const float* dY, const float* X, int T, int N, 
   ACSR_REQUIRE(dY && X && dW, "linear_wgrad: NULL pointer");
   ACSR_REQUIRE(T >= 0 && N > 0 && K > 0, "linear_wgrad: bad sizes");
   if (T == 0) return ACSR_OK;
-  const bool big = (long long)N * K > 4096;
-  const int tile = big ? 128 : 64;
+  const bool big = (long long)N * K > 8192;
+  const int tile = big ? 32 : 16;
   const int tiles_n = (N + tile - 1) / tile, tiles_k = (K + tile - 1) / tile;
-  // split the token axis so that ~2 CTAs per SM are busy, at least 64 tokens each
-  int splits = (2 * kNumSMs) / (tiles_n * tiles_k);
+  int splits = (4 * kNumSMs) / (tiles_n * tiles_k);
   if (splits < 1) splits = 1;
   int tok = (T + splits - 1) / splits;
-  if (tok < 64) tok = 64;
-  tok = (tok + kWgTT - 1) / kWgTT * kWgTT;
+  tok = (tok + kWgSlab - 1) / kWgSlab * kWgSlab;
   dim3 grid((T + tok - 1) / tok, tiles_n * tiles_k);
   if (big)
-    linear_wgrad_kernel<8, 8><<<grid, kWgThreads, 0, (cudaStream_t)stream>>>(dY, X, T, N, K, tok, tiles_k, dW, db);
+    linear_wgrad_kernel<4><<<grid, kWgThreads, 0, (cudaStream_t)stream>>>(dY, X, T, N, K, tok, tiles_k, dW, db);
   else
-    linear_wgrad_kernel<4, 4><<<grid, kWgThreads, 0, (cudaStream_t)stream>>>(dY, X, T, N, K, tok, tiles_k, dW, db);
+    linear_wgrad_kernel<2><<<grid, kWgThreads, 0, (cudaStream_t)stream>>>(dY, X, T, N, K, tok, tiles_k, dW, db);
   return check_launch("linear_wgrad");
 }

@@ -206,7 +206,7 @@ embed_ln_bwd_kernel(const float* __restrict__ d_out, const int64_t* __restrict__
 template <int D>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 bdrl_fwd_kernel(const float* __restrict__ h, const float* __restrict__ bias, const float* __restrict__ res,
-                const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int T,
+                const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int T, int res_rows,
                 float p, const float* __restrict__ mask, const RngState* rng, uint32_t stream,
                 float* __restrict__ out, float* __restrict__ stats) {
   using RV = RowVec<D>;
@@ -222,7 +222,7 @@ bdrl_fwd_kernel(const float* __restrict__ h, const float* __restrict__ bias, con
   for (long long t = (long long)blockIdx.x * kWarpsPerBlock + warp; t < T; t += (long long)gridDim.x * kWarpsPerBlock) {
     float x[RV::VPT], r[RV::VPT], m[RV::VPT];
     RV::load(h + t * D, lane, x);
-    RV::load(res + t * D, lane, r);
+    RV::load(res + (t % res_rows) * D, lane, r);
     RV::dropmask(p, mask, rng, stream, t, lane, m);
 #pragma unroll
     for (int i = 0; i < RV::VPT; ++i) x[i] = (x[i] + bi[i]) * m[i] + r[i];
@@ -239,6 +239,7 @@ template <int D>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 bdrl_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ h, const float* __restrict__ bias,
                 const float* __restrict__ res, const float* __restrict__ ln_w, const float* __restrict__ stats, int T,
+                int act_rows, int res_rows, int param_rows,
                 float p, const float* __restrict__ mask, const RngState* rng, uint32_t stream,
                 float* __restrict__ d_h, float* __restrict__ d_res, float* __restrict__ d_bias,
                 float* __restrict__ d_ln_w, float* __restrict__ d_ln_b) {
@@ -257,17 +258,20 @@ bdrl_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ h, co
   for (int i = 0; i < RV::VPT; ++i) acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
   for (long long t = (long long)blockIdx.x * kWarpsPerBlock + warp; t < T; t += (long long)gridDim.x * kWarpsPerBlock) {
     float x[RV::VPT], r[RV::VPT], m[RV::VPT], g[RV::VPT];
-    RV::load(h + t * D, lane, x);
-    RV::load(res + t * D, lane, r);
+    // saved forward tensors repeat with period act_rows (both cotangent streams of a shared activation)
+    const long long ta = t % act_rows;
+    const float keep = t < param_rows ? 1.0f : 0.0f;       // only these rows feed the parameter gradients
+    RV::load(h + ta * D, lane, x);
+    RV::load(res + (t % res_rows) * D, lane, r);
     RV::load(d_out + t * D, lane, g);
-    RV::dropmask(p, mask, rng, stream, t, lane, m);
-    const float mean = stats[2 * t], rstd = stats[2 * t + 1];
+    RV::dropmask(p, mask, rng, stream, ta, lane, m);
+    const float mean = stats[2 * ta], rstd = stats[2 * ta + 1];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < RV::VPT; ++i) {
       x[i] = ((x[i] + bi[i]) * m[i] + r[i] - mean) * rstd;   // xhat
-      acc[0][i] += g[i] * x[i];
-      acc[1][i] += g[i];
+      acc[0][i] += keep * g[i] * x[i];
+      acc[1][i] += keep * g[i];
       g[i] *= w[i];
       s1 += g[i];
       s2 += g[i] * x[i];
@@ -278,7 +282,7 @@ bdrl_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ h, co
     for (int i = 0; i < RV::VPT; ++i) {
       g[i] = rstd * (g[i] - s1 - x[i] * s2);   // grad wrt (dropout(h+bias) + res)
       r[i] = g[i] * m[i];                      // grad wrt h (and bias)
-      acc[2][i] += r[i];
+      acc[2][i] += keep * r[i];
     }
     RV::store(d_res + t * D, lane, g);
     RV::store(d_h + t * D, lane, r);
@@ -307,7 +311,7 @@ bias_act_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ bia
 
 __global__ void __launch_bounds__(kActTX * kActTY)
 bias_act_bwd_kernel(const float4* __restrict__ d_out, const float4* __restrict__ h, const float4* __restrict__ bias,
-                    int T, int ncv, int act, float4* __restrict__ d_h, float* __restrict__ d_bias) {
+                    int T, int ncv, int act, int act_rows, int param_rows, float4* __restrict__ d_h, float* __restrict__ d_bias) {
   __shared__ float4 red[kActTY][kActTX];
   for (int cv0 = 0; cv0 < ncv; cv0 += kActTX) {      // uniform trip count across the block (syncthreads inside)
     const int cv = cv0 + threadIdx.x;
@@ -315,12 +319,12 @@ bias_act_bwd_kernel(const float4* __restrict__ d_out, const float4* __restrict__
     if (cv < ncv) {
       const float4 b = bias != nullptr ? bias[cv] : make_float4(0.f, 0.f, 0.f, 0.f);
       for (long long t = (long long)blockIdx.x * kActTY + threadIdx.y; t < T; t += (long long)gridDim.x * kActTY) {
-        float4 x = h[t * ncv + cv];
+        float4 x = h[(t % act_rows) * ncv + cv];
         float4 g = d_out[t * ncv + cv];
         g.x *= act_bwd(act, x.x + b.x); g.y *= act_bwd(act, x.y + b.y);
         g.z *= act_bwd(act, x.z + b.z); g.w *= act_bwd(act, x.w + b.w);
         d_h[t * ncv + cv] = g;
-        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        if (t < param_rows) { acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w; }
       }
     }
     red[threadIdx.y][threadIdx.x] = acc;
@@ -430,26 +434,28 @@ int acsr_embed_ln_dropout_bwd(const float* d_out, const int64_t* item_seq, const
 }
 
 int acsr_bias_dropout_res_ln_fwd(const float* h, const float* bias, const float* res, const float* ln_w, const float* ln_b,
-                                 float eps, int T, int d, float p, const float* mask, const void* rng, uint32_t rng_stream,
-                                 float* out, float* stats, void* stream) {
+                                 float eps, int T, int d, int res_rows, float p, const float* mask, const void* rng,
+                                 uint32_t rng_stream, float* out, float* stats, void* stream) {
   ACSR_REQUIRE(h && res && ln_w && ln_b && out && stats, "bias_dropout_res_ln_fwd: NULL pointer");
+  ACSR_REQUIRE(res_rows > 0 && res_rows <= T || T == 0, "bias_dropout_res_ln_fwd: res_rows=%d", res_rows);
   ACSR_REQUIRE(p >= 0.f && p < 1.f, "bias_dropout_res_ln_fwd: dropout p=%f", p);
   ACSR_REQUIRE(!(p > 0.f && mask == nullptr && rng == nullptr), "bias_dropout_res_ln_fwd: p>0 needs mask or rng");
   if (T == 0) return ACSR_OK;
   DISPATCH_D(d, (bdrl_fwd_kernel<D_><<<row_grid(T), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-                    h, bias, res, ln_w, ln_b, eps, T, p, mask, (const RngState*)rng, rng_stream, out, stats)));
+                    h, bias, res, ln_w, ln_b, eps, T, res_rows, p, mask, (const RngState*)rng, rng_stream, out, stats)));
   return check_launch("bias_dropout_res_ln_fwd");
 }
 
 int acsr_bias_dropout_res_ln_bwd(const float* d_out, const float* h, const float* bias, const float* res, const float* ln_w,
-                                 const float* stats, int T, int d, float p, const float* mask, const void* rng,
-                                 uint32_t rng_stream, float* d_h, float* d_res, float* d_bias, float* d_ln_w, float* d_ln_b,
-                                 void* stream) {
+                                 const float* stats, int T, int d, int act_rows, int res_rows, int param_rows, float p,
+                                 const float* mask, const void* rng, uint32_t rng_stream, float* d_h, float* d_res,
+                                 float* d_bias, float* d_ln_w, float* d_ln_b, void* stream) {
   ACSR_REQUIRE(d_out && h && res && ln_w && stats && d_h && d_res, "bias_dropout_res_ln_bwd: NULL pointer");
+  ACSR_REQUIRE(T == 0 || (act_rows > 0 && res_rows > 0 && param_rows >= 0), "bias_dropout_res_ln_bwd: bad row periods");
   if (T == 0) return ACSR_OK;
   DISPATCH_D(d, (bdrl_bwd_kernel<D_><<<row_grid(T), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-                    d_out, h, bias, res, ln_w, stats, T, p, mask, (const RngState*)rng, rng_stream, d_h, d_res, d_bias, d_ln_w,
-                    d_ln_b)));
+                    d_out, h, bias, res, ln_w, stats, T, act_rows, res_rows, param_rows, p, mask, (const RngState*)rng,
+                    rng_stream, d_h, d_res, d_bias, d_ln_w, d_ln_b)));
   return check_launch("bias_dropout_res_ln_bwd");
 }
 
@@ -465,16 +471,17 @@ int acsr_bias_act_fwd(const float* h, const float* bias, int T, int n, int act, 
   return check_launch("bias_act_fwd");
 }
 
-int acsr_bias_act_bwd(const float* d_out, const float* h, const float* bias, int T, int n, int act, float* d_h, float* d_bias,
-                      void* stream) {
+int acsr_bias_act_bwd(const float* d_out, const float* h, const float* bias, int T, int n, int act, int act_rows,
+                      int param_rows, float* d_h, float* d_bias, void* stream) {
   ACSR_REQUIRE(d_out && h && d_h, "bias_act_bwd: NULL pointer");
   ACSR_REQUIRE(n % 4 == 0 && n > 0 && n <= kActTX * 4 * kActMaxK, "bias_act_bwd: n=%d must be a multiple of 4, <= 2048", n);
   ACSR_REQUIRE(act >= 0 && act <= 4, "bias_act_bwd: unknown activation %d", act);
+  ACSR_REQUIRE(T == 0 || (act_rows > 0 && param_rows >= 0), "bias_act_bwd: bad row periods");
   if (T == 0) return ACSR_OK;
   long long need = (T + kActTY - 1) / kActTY, cap = kNumSMs * 4;
   dim3 blk(kActTX, kActTY);
   bias_act_bwd_kernel<<<(int)(need < cap ? need : cap), blk, 0, (cudaStream_t)stream>>>(
-      (const float4*)d_out, (const float4*)h, (const float4*)bias, T, n / 4, act, (float4*)d_h, d_bias);
+      (const float4*)d_out, (const float4*)h, (const float4*)bias, T, n / 4, act, act_rows, param_rows, (float4*)d_h, d_bias);
   return check_launch("bias_act_bwd");
 }
 

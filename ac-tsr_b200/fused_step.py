@@ -1,0 +1,255 @@
+"""Explicit (autograd-free) AC-SASRec training step.
+
+The reference trainer runs two backward traversals with requires_grad toggling (trainer.py:672-686):
+attack_{query,key}_transform receive d(attacked_loss), every other parameter d(calibrated_loss).
+Backward is linear in the cotangent, so here BOTH cotangent streams travel together as the two halves
+of every gradient buffer ([stream 0 = calibrated loss ; stream 1 = attacked loss], 2T rows), each
+kernel / GEMM is launched once for both, and every weight gradient reads the half that owns it and
+accumulates straight into the flat gradient buffer (no autograd tape, no temporaries, no adds).
+
+Dead work the reference performs is skipped without changing any result: the attacked branch of
+non-final layers, the attacked branch's weight gradients, the attacked stream below the first layer.
+
+All buffers are allocated once per batch size, so the step is CUDA-graph capturable as is.
+"""
+import math
+
+import torch
+
+from . import ops
+from ._lib import LIB
+from .ops import _p, _stream
+
+
+def _w(lin):
+    return lin.weight, lin.bias
+
+
+class FusedTrainStep(object):
+    def __init__(self, model, optimizer):
+        if model.loss_type != 'CE':
+            raise NotImplementedError('fused step covers loss_type CE (the shipped configs); BPR takes the autograd path')
+        self.m, self.opt = model, optimizer
+        self.buf = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _buffers(self, B, L, dev):
+        key = (B, L)
+        if key in self.buf:
+            return self.buf[key]
+        m = self.m
+        d, I, N, V = m.hidden_size, m.inner_size, m.n_layers, m.n_items
+        T = B * L
+
+        def f(*s):
+            return torch.empty(s, dtype=torch.float32, device=dev)
+        b = dict(T=T, x0=f(T, d), st_e=f(T, 2), pen=torch.zeros(N, dtype=torch.float64, device=dev), layers=[])
+        for l in range(N):
+            R = 2 * T if l == N - 1 else T
+            b['layers'].append(dict(mq=f(T, d), mk=f(T, d), mv=f(T, d), aq=f(T, d), ak=f(T, d), gl=f(T, L), ctx=f(R, d),
+                                    hz=f(R, d), st_a=f(R, 2), h=f(R, d), z1=f(R, I), a1=f(R, I), z2=f(R, d), st_f=f(R, 2),
+                                    out=f(R, d)))
+        nc = ops.logits_num_chunks(2 * B, V)
+        b.update(out2=f(2 * B, d), partial=f(2 * B, nc, 2), lse=f(2 * B), tgt=f(2 * B), row_loss=f(2 * B), loss=f(2),
+                 Gt=f(V, 2 * B), d_out2=f(2 * B, d), target2=torch.empty(2 * B, dtype=torch.int64, device=dev),
+                 row_scale=torch.cat((torch.full((B,), 1.0 / B), torch.full((B,), -1.0 / B))).to(dev))
+        for n, w in (('d_out', d), ('d_z2', d), ('d_a1', I), ('d_z1', I), ('d_h', d), ('d_hz', d), ('d_x', d), ('d_ctx', d),
+                     ('d_mq', d), ('d_mk', d), ('d_mv', d), ('d_aq', d), ('d_ak', d), ('d_gl', L)):
+            b[n] = f(2 * T, w)
+        self.buf[key] = b
+        return b
+
+    # ------------------------------------------------------------------------------------------
+    def __call__(self, interaction):
+        """-> (final_attacked_loss, calibrated_loss) detached 0-d tensors; parameters are updated in place."""
+        m, opt = self.m, self.opt
+        seq = interaction[m.ITEM_SEQ].contiguous()
+        ln = interaction[m.ITEM_SEQ_LEN].contiguous()
+        pos_items = interaction[m.POS_ITEM_ID]
+        B, L = seq.shape
+        dev = seq.device
+        b = self._buffers(B, L, dev)
+        T, d, I, N, V, H = b['T'], m.hidden_size, m.inner_size, m.n_layers, m.n_items, m.n_heads
+        dh = d // H
+        rt = m._runtime(dev)
+        rng, rand = rt.rng, rt.rand
+        rngp = rng.ptr
+        st = _stream()
+        training = m.training
+        p_h = m.dropout.p if training else 0.0
+        rng.advance()
+
+        def mask(key):
+            return None if (rand is None or p_h == 0.0) else rand.get(key)
+
+        def mask2(l, k_cal, k_att, last):
+            if rand is None or p_h == 0.0:
+                return None
+            a = rand.get((l, k_cal))
+            return torch.cat((a.reshape(T, d), rand.get((l, k_att)).reshape(T, d))) if last else a
+
+        E = m.item_embedding.weight
+        posw = m.position_embedding.weight if m.use_position_embedding else None
+        eps = m.LayerNorm.eps
+        # ---------------- forward ----------------
+        me = mask('emb')
+        LIB.call('acsr_embed_ln_dropout_fwd', _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight), _p(m.LayerNorm.bias),
+                 eps, T, L, d, V, p_h, _p(me), rngp, 1, _p(b['x0']), _p(b['st_e']), st)
+        b['pen'].zero_()
+        x = b['x0']
+        xs = []
+        act_id = ops.ACT_IDS[m.hidden_act]
+        for l, layer in enumerate(m.trm_encoder.layer):
+            last = l == N - 1
+            R = 2 * T if last else T
+            lb = b['layers'][l]
+            aa, ff = layer.attack_attention, layer.feed_forward
+            base = 16 * (l + 1)
+            xs.append(x)
+            torch.addmm(aa.query.bias, x, aa.query.weight.t(), out=lb['mq'])
+            torch.addmm(aa.key.bias, x, aa.key.weight.t(), out=lb['mk'])
+            torch.addmm(aa.value.bias, x, aa.value.weight.t(), out=lb['mv'])
+            torch.addmm(aa.attack_query_transform.bias, lb['mq'], aa.attack_query_transform.weight.t(), out=lb['aq'])
+            torch.addmm(aa.attack_key_transform.bias, lb['mk'], aa.attack_key_transform.weight.t(), out=lb['ak'])
+            gate = layer.combine_option == 'gate'
+            comb_scalar = 0.0
+            if gate:
+                if layer.gate.out_features != L:
+                    raise ValueError('gate width %d != sequence length %d' % (layer.gate.out_features, L))
+                torch.addmm(layer.gate.bias, lb['mq'], layer.gate.weight.t(), out=lb['gl'])
+            elif layer.combine_option == 'annealing':
+                comb_scalar = math.exp(-layer.anneal_step / 100000)
+                layer.anneal_step += 1
+            p_attn = aa.attn_dropout.p if training else 0.0
+            lb['attn_args'] = self._attn_args(layer, lb, seq, B, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base)
+            ctx_cal, ctx_att = lb['ctx'][:T], (lb['ctx'][T:] if last else None)
+            LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal), b['pen'][l:].data_ptr(), None, st)
+            torch.mm(lb['ctx'], aa.dense.weight.t(), out=lb['hz'])
+            lb['m_a'] = mask2(l, 'D5', 'D4', last)
+            LIB.call('acsr_bias_dropout_res_ln_fwd', _p(lb['hz']), _p(aa.dense.bias), _p(x), _p(aa.LayerNorm.weight),
+                     _p(aa.LayerNorm.bias), aa.LayerNorm.eps, R, d, T, p_h, _p(lb['m_a']), rngp, base + 3, _p(lb['h']),
+                     _p(lb['st_a']), st)
+            torch.mm(lb['h'], ff.dense_1.weight.t(), out=lb['z1'])
+            LIB.call('acsr_bias_act_fwd', _p(lb['z1']), _p(ff.dense_1.bias), R, I, act_id, _p(lb['a1']), st)
+            torch.mm(lb['a1'], ff.dense_2.weight.t(), out=lb['z2'])
+            lb['m_f'] = mask2(l, 'D7', 'D6', last)
+            LIB.call('acsr_bias_dropout_res_ln_fwd', _p(lb['z2']), _p(ff.dense_2.bias), _p(lb['h']), _p(ff.LayerNorm.weight),
+                     _p(ff.LayerNorm.bias), ff.LayerNorm.eps, R, d, R, p_h, _p(lb['m_f']), rngp, base + 5, _p(lb['out']),
+                     _p(lb['st_f']), st)
+            x = lb['out'][:T]
+        last_out = b['layers'][N - 1]['out']
+        # rows [0,B) calibrated, [B,2B) attacked  (the kernel's first pointer fills the first B rows)
+        LIB.call('acsr_gather_last_fwd', _p(last_out[:T]), _p(last_out[T:]), _p(ln, torch.int64), B, L, d, _p(b['out2']), st)
+        torch.cat((pos_items, pos_items), out=b['target2'])
+        passes = m.logits_passes
+        LIB.call('acsr_logits_ce_partial', _p(b['out2']), _p(E), 2 * B, V, d, passes, _p(b['partial']), st)
+        LIB.call('acsr_ce_finalize', _p(b['partial']), b['partial'].shape[1], _p(b['out2']), _p(E), _p(b['target2'], torch.int64),
+                 2 * B, d, V, 0, 2, _p(b['lse']), _p(b['tgt']), _p(b['row_loss']), _p(b['loss']), st)
+        pen32 = b['pen'].to(torch.float32)
+        pen_norm = torch.sqrt(pen32)
+        w = m.mask_loss_weight.detach()[0] if m.trainable_mask_loss_weight else float(m.mask_loss_weight)
+        loss_cal = b['loss'][0]
+        loss_att = -b['loss'][1] + pen_norm.mean() * w
+        if not training:
+            return loss_att, loss_cal
+        # ---------------- backward ----------------
+        dpen = (w / (2.0 * N)) / pen_norm                     # d loss_att / d pen_sq_l
+        opt.zero_grad()
+        LIB.call('acsr_logits_ce_grad', _p(b['out2']), _p(E), _p(b['lse']), _p(b['target2'], torch.int64), _p(b['row_scale']),
+                 2 * B, V, d, passes, _p(b['Gt']), 2 * B, st)
+        b['d_out2'].zero_()
+        LIB.call('acsr_linear_wgrad', _p(b['Gt']), _p(E), V, 2 * B, d, _p(b['d_out2']), None, st)
+        E.grad.addmm_(b['Gt'][:, :B], b['out2'][:B])           # only the calibrated rows train the item table
+        d_out, d_x = b['d_out'], b['d_x']
+        d_out.zero_()
+        LIB.call('acsr_gather_last_bwd', _p(b['d_out2']), _p(ln, torch.int64), B, L, d, _p(d_out[:T]), _p(d_out[T:]), st)
+        T2 = 2 * T
+        for l in reversed(range(N)):
+            last = l == N - 1
+            P = T2 if last else T                               # period of the saved forward tensors
+            lb = b['layers'][l]
+            layer = m.trm_encoder.layer[l]
+            aa, ff = layer.attack_attention, layer.feed_forward
+            base = 16 * (l + 1)
+            x = xs[l]
+            gate = layer.combine_option == 'gate'
+            # FFN
+            LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_out), _p(lb['z2']), _p(ff.dense_2.bias), _p(lb['h']),
+                     _p(ff.LayerNorm.weight), _p(lb['st_f']), T2, d, P, P, T, p_h, _p(lb['m_f']), rngp, base + 5,
+                     _p(b['d_z2']), _p(b['d_h']), _p(ff.dense_2.bias.grad), _p(ff.LayerNorm.weight.grad),
+                     _p(ff.LayerNorm.bias.grad), st)
+            LIB.call('acsr_linear_wgrad', _p(b['d_z2']), _p(lb['a1']), T, d, I, _p(ff.dense_2.weight.grad), None, st)
+            torch.mm(b['d_z2'], ff.dense_2.weight, out=b['d_a1'])
+            LIB.call('acsr_bias_act_bwd', _p(b['d_a1']), _p(lb['z1']), _p(ff.dense_1.bias), T2, I, act_id, P, T, _p(b['d_z1']),
+                     _p(ff.dense_1.bias.grad), st)
+            LIB.call('acsr_linear_wgrad', _p(b['d_z1']), _p(lb['h']), T, I, d, _p(ff.dense_1.weight.grad), None, st)
+            b['d_h'].addmm_(b['d_z1'], ff.dense_1.weight)
+            # attention output projection
+            LIB.call('acsr_bias_dropout_res_ln_bwd', _p(b['d_h']), _p(lb['hz']), _p(aa.dense.bias), _p(x),
+                     _p(aa.LayerNorm.weight), _p(lb['st_a']), T2, d, P, T, T, p_h, _p(lb['m_a']), rngp, base + 3,
+                     _p(b['d_hz']), _p(d_x), _p(aa.dense.bias.grad), _p(aa.LayerNorm.weight.grad), _p(aa.LayerNorm.bias.grad), st)
+            LIB.call('acsr_linear_wgrad', _p(b['d_hz']), _p(lb['ctx']), T, d, d, _p(aa.dense.weight.grad), None, st)
+            torch.mm(b['d_hz'], aa.dense.weight, out=b['d_ctx'])
+            # fused attention backward, one launch per cotangent stream
+            if gate:
+                b['d_gl'].zero_()
+            g = lambda t: None if t is None else t.grad     # noqa: E731
+            ow, ob_ = (aa.order_affine.weight, aa.order_affine.bias) if aa.use_order else (None, None)
+            dw, db_, sc = (aa.distance_affine.weight, aa.distance_affine.bias, aa.scalar) if aa.use_distance else (None, None, None)
+            rr = getattr(layer, 'rich_calibrated_combine_ratio', None) if not layer.two_level else None
+            dc = b['d_ctx']
+            for s in (0, 1):
+                rows = slice(0, T) if s == 0 else slice(T, T2)
+                if last:
+                    d_att, d_cal = (None, dc[rows]) if s == 0 else (dc[rows], None)
+                else:
+                    d_att, d_cal = None, dc[rows]
+                d_pen = dpen[l:l + 1] if s == 1 else None
+                own = s == 0                                 # stream 0 owns the non-attack parameters
+                LIB.call('acsr_attn_calib_bwd', _p(d_att), _p(d_cal), _p(d_pen), *lb['attn_args'],
+                         _p(b['d_mq'][rows]), _p(b['d_mk'][rows]), _p(b['d_mv'][rows]), _p(b['d_aq'][rows]), _p(b['d_ak'][rows]),
+                         _p(b['d_gl'][rows]) if gate else None,
+                         _p(g(ow)) if own else None, _p(g(ob_)) if own else None, _p(g(dw)) if own else None,
+                         _p(g(db_)) if own else None, _p(g(sc)) if own else None, _p(g(rr)) if own else None, st)
+            # projections: input gradients for both streams, weight gradients from the owning stream
+            aqt, akt = aa.attack_query_transform, aa.attack_key_transform
+            b['d_mq'].addmm_(b['d_aq'], aqt.weight)
+            b['d_mk'].addmm_(b['d_ak'], akt.weight)
+            LIB.call('acsr_linear_wgrad', _p(b['d_aq'][T:]), _p(lb['mq']), T, d, d, _p(aqt.weight.grad), _p(aqt.bias.grad), st)
+            LIB.call('acsr_linear_wgrad', _p(b['d_ak'][T:]), _p(lb['mk']), T, d, d, _p(akt.weight.grad), _p(akt.bias.grad), st)
+            if gate:
+                b['d_mq'].addmm_(b['d_gl'], layer.gate.weight)
+                LIB.call('acsr_linear_wgrad', _p(b['d_gl']), _p(lb['mq']), T, L, d, _p(layer.gate.weight.grad),
+                         _p(layer.gate.bias.grad), st)
+            for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
+                LIB.call('acsr_linear_wgrad', _p(b[dk]), _p(x), T, d, d, _p(lin.weight.grad), _p(lin.bias.grad), st)
+            if l > 0:
+                for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
+                    d_x.addmm_(b[dk], lin.weight)
+                d_out, d_x = d_x, d_out                       # this layer's input gradient is the next one's output gradient
+            else:
+                for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
+                    d_x[:T].addmm_(b[dk][:T], lin.weight)     # below the first layer only the calibrated stream trains anything
+        LIB.call('acsr_embed_ln_dropout_bwd', _p(d_x[:T]), _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight),
+                 _p(b['st_e']), T, L, d, V, p_h, _p(me), rngp, 1, _p(E.grad), _p(posw.grad if posw is not None else None),
+                 _p(m.LayerNorm.weight.grad), _p(m.LayerNorm.bias.grad), st)
+        return loss_att, loss_cal
+
+    @staticmethod
+    def _attn_args(layer, lb, seq, B, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base):
+        """positional arguments shared by acsr_attn_calib_fwd / _bwd between the cotangents and the outputs."""
+        aa = layer.attack_attention
+        r = (lambda k: None) if (rand is None) else (lambda k: rand.get((l, k)))
+        drop = p_attn > 0.0
+        D1, D2, D3 = (r('D1'), r('D2'), r('D3')) if drop else (None, None, None)
+        lb['_keep'] = (D1, D2, D3, r('noise'))              # keep explicit tensors alive until the backward ran
+        two_level = int(bool(layer.two_level))
+        rich = ops.RICH_IDS.get(layer.rich_calibrated_combine, 0) if not layer.two_level else 0
+        rr = getattr(layer, 'rich_calibrated_combine_ratio', None) if not layer.two_level else None
+        return (_p(lb['mq']), _p(lb['mk']), _p(lb['mv']), _p(lb['aq']), _p(lb['ak']),
+                _p(lb['gl']) if layer.combine_option == 'gate' else None, _p(seq, torch.int64),
+                _p(aa.order_affine.weight) if aa.use_order else None, _p(aa.order_affine.bias) if aa.use_order else None,
+                _p(aa.distance_affine.weight) if aa.use_distance else None, _p(aa.distance_affine.bias) if aa.use_distance else None,
+                _p(aa.scalar) if aa.use_distance else None,
+                B, L, H, dh, two_level, ops.COMBINE_IDS[layer.combine_option], float(comb_scalar), rich, _p(rr),
+                float(p_attn), _p(D1), _p(D2), _p(D3), _p(lb['_keep'][3]), rngp, base)

@@ -90,7 +90,7 @@ class BiasDropoutResLnFn(torch.autograd.Function):
         T = h.numel() // d
         out = torch.empty_like(h)
         stats = torch.empty((T, 2), dtype=torch.float32, device=h.device)
-        LIB.call('acsr_bias_dropout_res_ln_fwd', _p(h), _p(bias), _p(res), _p(ln_w), _p(ln_b), eps, T, d, p, _p(mask),
+        LIB.call('acsr_bias_dropout_res_ln_fwd', _p(h), _p(bias), _p(res), _p(ln_w), _p(ln_b), eps, T, d, T, p, _p(mask),
                  rng.ptr if rng is not None else None, rng_stream, _p(out), _p(stats), _stream())
         ctx.save_for_backward(h, bias, res, ln_w, stats, mask)
         ctx.meta = (T, d, p, rng, rng_stream)
@@ -106,7 +106,7 @@ class BiasDropoutResLnFn(torch.autograd.Function):
         d_bias = torch.zeros_like(bias) if bias is not None else None
         d_w = torch.zeros_like(ln_w)
         d_b = torch.zeros_like(ln_w)
-        LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_out), _p(h), _p(bias), _p(res), _p(ln_w), _p(stats), T, d, p,
+        LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_out), _p(h), _p(bias), _p(res), _p(ln_w), _p(stats), T, d, T, T, T, p,
                  _p(mask), rng.ptr if rng is not None else None, rng_stream, _p(d_h), _p(d_res), _p(d_bias), _p(d_w),
                  _p(d_b), _stream())
         return d_h, d_bias, d_res, d_w, d_b, None, None, None, None, None
@@ -133,7 +133,7 @@ class BiasActFn(torch.autograd.Function):
         d_out = d_out.contiguous()
         d_h = torch.empty_like(h)
         d_bias = torch.zeros_like(bias) if bias is not None else None
-        LIB.call('acsr_bias_act_bwd', _p(d_out), _p(h), _p(bias), T, n, act, _p(d_h), _p(d_bias), _stream())
+        LIB.call('acsr_bias_act_bwd', _p(d_out), _p(h), _p(bias), T, n, act, T, T, _p(d_h), _p(d_bias), _stream())
         return d_h, d_bias, None
 
 

@@ -114,6 +114,11 @@ class ACSASRecTrainer(object):
         self.fused_topk = bool(cfg_get(config, 'fused_topk', True))
         self._graph = None
         self.dp_world = 1
+        self.fused = None
+        if (bool(cfg_get(config, 'fused_step', True)) and isinstance(self.optimizer, FlatAdam)
+                and getattr(model, 'loss_type', None) == 'CE' and not self.clip_grad_norm):
+            from .fused_step import FusedTrainStep
+            self.fused = FusedTrainStep(model, self.optimizer)
         self.nan_check_interval = int(cfg_get(config, 'nan_check_interval', 50))
         self.logger.info('use attack trainer!!!')
 
@@ -141,6 +146,14 @@ class ACSASRecTrainer(object):
 
     def _step_body(self, interaction):
         """trainer.py:660-687 without the host syncs: -> (attacked_loss, calibrated_loss) tensors."""
+        if self.fused is not None:
+            attacked_loss, calibrated_loss = self.fused(interaction)      # both cotangent streams in one pass
+            if self.dp_world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self.optimizer.flat_grad)
+                self.optimizer.flat_grad.mul_(1.0 / self.dp_world)
+            self.optimizer.step()
+            return attacked_loss.detach(), calibrated_loss.detach()
         self.optimizer.zero_grad()
         attacked_loss, calibrated_loss = self.model.calculate_loss(interaction)
         self._route(attack=False)

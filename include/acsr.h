@@ -90,7 +90,8 @@ int acsr_attn_calib_fwd(const float* mq, const float* mk, const float* mv, const
 /* backward of the same block.  d_ctx_att / d_ctx_cal [B,L,d] (either may be NULL == zero),
  * d_pen_sq device float[1] or NULL.  Outputs (written, not accumulated): d_mq,d_mk,d_mv,d_aq,d_ak [B,L,d].
  * Accumulated with atomics (caller zeroes): d_gate_logit [B,L,L], d_order_w [2dh], d_order_b [1],
- * d_dist_w [2dh], d_dist_b [1], d_scalar [1], d_rich_ratio [1] (NULL when the parameter is absent). */
+ * d_dist_w [2dh], d_dist_b [1], d_scalar [1], d_rich_ratio [1] (NULL when the parameter is absent or when this
+ * cotangent stream does not own it: the attacked-loss stream only trains the attack transforms, trainer.py:672-686). */
 int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const float* d_pen_sq,
                         const float* mq, const float* mk, const float* mv, const float* aq, const float* ak,
                         const float* gate_logit, const int64_t* item_seq,
@@ -106,22 +107,27 @@ int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const fl
 
 /* ---- epilogue of the output projection and of the FFN: LN(dropout(h + bias) + res) ----
  * replaces model/layers.py:681-683 and 794-796 (bias add of the preceding nn.Linear folded in).
- * h,res,out [T,d]; bias [d] or NULL. */
+ * h,out [T,d]; bias [d] or NULL; res [res_rows,d] is read with period res_rows (res_rows == T for a plain call;
+ * res_rows == T/2 when the attacked and calibrated branches are stacked and share the layer input). */
 int acsr_bias_dropout_res_ln_fwd(const float* h, const float* bias, const float* res,
-                                 const float* ln_w, const float* ln_b, float eps, int T, int d,
+                                 const float* ln_w, const float* ln_b, float eps, int T, int d, int res_rows,
                                  float p, const float* mask, const void* rng, uint32_t rng_stream,
                                  float* out, float* stats, void* stream);
-/* d_h [T,d] (= grad of the GEMM output), d_res [T,d] written; d_bias,d_ln_w,d_ln_b [d] accumulated. */
+/* backward over T cotangent rows.  The saved forward tensors h/stats/mask repeat with period act_rows and res with
+ * period res_rows (two stacked cotangent streams of one shared activation: act_rows = T/2); only rows
+ * [0,param_rows) feed d_bias,d_ln_w,d_ln_b [d] (accumulated).  d_h (= grad of the GEMM output), d_res [T,d] written. */
 int acsr_bias_dropout_res_ln_bwd(const float* d_out, const float* h, const float* bias, const float* res,
                                  const float* ln_w, const float* stats, int T, int d,
+                                 int act_rows, int res_rows, int param_rows,
                                  float p, const float* mask, const void* rng, uint32_t rng_stream,
                                  float* d_h, float* d_res, float* d_bias, float* d_ln_w, float* d_ln_b, void* stream);
 
 /* ---- FFN activation: out = act(h + bias)   (model/layers.py:776-792) -------------------
- * act: 0 gelu(erf) 1 relu 2 swish 3 tanh 4 sigmoid.  h,out [T,n]. */
+ * act: 0 gelu(erf) 1 relu 2 swish 3 tanh 4 sigmoid.  h,out [T,n].  Backward: h repeats with period act_rows,
+ * rows [0,param_rows) feed d_bias. */
 int acsr_bias_act_fwd(const float* h, const float* bias, int T, int n, int act, float* out, void* stream);
 int acsr_bias_act_bwd(const float* d_out, const float* h, const float* bias, int T, int n, int act,
-                      float* d_h, float* d_bias, void* stream);
+                      int act_rows, int param_rows, float* d_h, float* d_bias, void* stream);
 
 /* ---- K9: gather the hidden state at position len-1 (abstract_recommender.py:130-134) ---
  * x_att (may be NULL), x_cal [B,L,d]; out [2B,d] rows [0,B) attacked, [B,2B) calibrated
