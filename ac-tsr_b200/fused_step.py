@@ -60,8 +60,9 @@ class FusedTrainStep(object):
         return b
 
     # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
     def __call__(self, interaction):
-        """-> (final_attacked_loss, calibrated_loss) detached 0-d tensors; parameters are updated in place."""
+        """-> (final_attacked_loss, calibrated_loss) detached 0-d tensors; gradients land in the flat grad buffer."""
         m, opt = self.m, self.opt
         seq = interaction[m.ITEM_SEQ].contiguous()
         ln = interaction[m.ITEM_SEQ_LEN].contiguous()
