@@ -86,6 +86,16 @@ class ACSASRec(SequentialRecommender):
         if isinstance(module, nn.Linear) and module.bias is not None:
             module.bias.data.zero_()
 
+    def flat_groups(self):
+        """parameters the fused step views as stacked tensors (one batched GEMM for Q/K/V and for the attack pair)."""
+        out = []
+        for layer in self.trm_encoder.layer:
+            aa = layer.attack_attention
+            out += [[aa.query.weight, aa.key.weight, aa.value.weight], [aa.query.bias, aa.key.bias, aa.value.bias],
+                    [aa.attack_query_transform.weight, aa.attack_key_transform.weight],
+                    [aa.attack_query_transform.bias, aa.attack_key_transform.bias]]
+        return out
+
     # ------------------------------------------------------------------------------------------
     def _runtime(self, device, attacked_last_only=True):
         if self._rng is None or self._rng.state.device != device:

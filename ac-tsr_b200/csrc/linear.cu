@@ -18,8 +18,12 @@ constexpr int kWgSlab = 64;        // tokens per shared-memory slab
 template <int R>
 __global__ void __launch_bounds__(kWgThreads)
 linear_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int T, int N, int K, int tok_per_cta,
-                    int tiles_k, float* __restrict__ dW, float* __restrict__ db) {
+                    int tiles_k, float* __restrict__ dW, float* __restrict__ db, long long strY, long long strX, long long strW,
+                    long long strB) {
   constexpr int TILE = 8 * R;
+  // batched launch: blockIdx.z selects one independent (dY, X, dW, db) problem
+  dY += blockIdx.z * strY; X += blockIdx.z * strX; dW += blockIdx.z * strW;
+  if (db != nullptr) db += blockIdx.z * strB;
   __shared__ __align__(16) float sY[kWgSlab][TILE];
   __shared__ __align__(16) float sX[kWgSlab][TILE];
   __shared__ float sRed[3][64][R * R + R];
@@ -121,21 +125,32 @@ linear_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, i
 
 using namespace acsr;
 
-extern "C" int acsr_linear_wgrad(const float* dY, const float* X, int T, int N, int K, float* dW, float* db, void* stream) {
-  ACSR_REQUIRE(dY && X && dW, "linear_wgrad: NULL pointer");
-  ACSR_REQUIRE(T >= 0 && N > 0 && K > 0, "linear_wgrad: bad sizes");
+static int launch_wgrad(const float* dY, const float* X, int T, int N, int K, float* dW, float* db, int batch, long long sY,
+                        long long sX, long long sW, long long sB, cudaStream_t stream, const char* who) {
+  ACSR_REQUIRE(dY && X && dW, "%s: NULL pointer", who);
+  ACSR_REQUIRE(T >= 0 && N > 0 && K > 0 && batch > 0 && batch < 65536, "%s: bad sizes", who);
   if (T == 0) return ACSR_OK;
   const bool big = (long long)N * K > 8192;
   const int tile = big ? 32 : 16;
   const int tiles_n = (N + tile - 1) / tile, tiles_k = (K + tile - 1) / tile;
-  int splits = (4 * kNumSMs) / (tiles_n * tiles_k);
+  int splits = (4 * kNumSMs) / (tiles_n * tiles_k * batch);
   if (splits < 1) splits = 1;
   int tok = (T + splits - 1) / splits;
   tok = (tok + kWgSlab - 1) / kWgSlab * kWgSlab;
-  dim3 grid((T + tok - 1) / tok, tiles_n * tiles_k);
+  dim3 grid((T + tok - 1) / tok, tiles_n * tiles_k, batch);
   if (big)
-    linear_wgrad_kernel<4><<<grid, kWgThreads, 0, (cudaStream_t)stream>>>(dY, X, T, N, K, tok, tiles_k, dW, db);
+    linear_wgrad_kernel<4><<<grid, kWgThreads, 0, stream>>>(dY, X, T, N, K, tok, tiles_k, dW, db, sY, sX, sW, sB);
   else
-    linear_wgrad_kernel<2><<<grid, kWgThreads, 0, (cudaStream_t)stream>>>(dY, X, T, N, K, tok, tiles_k, dW, db);
-  return check_launch("linear_wgrad");
+    linear_wgrad_kernel<2><<<grid, kWgThreads, 0, stream>>>(dY, X, T, N, K, tok, tiles_k, dW, db, sY, sX, sW, sB);
+  return check_launch(who);
+}
+
+extern "C" int acsr_linear_wgrad(const float* dY, const float* X, int T, int N, int K, float* dW, float* db, void* stream) {
+  return launch_wgrad(dY, X, T, N, K, dW, db, 1, 0, 0, 0, 0, (cudaStream_t)stream, "linear_wgrad");
+}
+
+extern "C" int acsr_linear_wgrad_batched(const float* dY, const float* X, int T, int N, int K, float* dW, float* db, int batch,
+                                         int64_t stride_dy, int64_t stride_x, int64_t stride_dw, int64_t stride_db, void* stream) {
+  return launch_wgrad(dY, X, T, N, K, dW, db, batch, stride_dy, stride_x, stride_dw, stride_db, (cudaStream_t)stream,
+                      "linear_wgrad_batched");
 }

@@ -46,7 +46,8 @@ class FusedTrainStep(object):
         b = dict(T=T, x0=f(T, d), st_e=f(T, 2), pen=torch.zeros(N, dtype=torch.float64, device=dev), layers=[])
         for l in range(N):
             R = 2 * T if l == N - 1 else T
-            b['layers'].append(dict(mq=f(T, d), mk=f(T, d), mv=f(T, d), aq=f(T, d), ak=f(T, d), gl=f(T, L), ctx=f(R, d),
+            qkv, aqk = f(3, T, d), f(2, T, d)
+            b['layers'].append(dict(qkv=qkv, aqk=aqk, mq=qkv[0], mk=qkv[1], mv=qkv[2], aq=aqk[0], ak=aqk[1], gl=f(T, L), ctx=f(R, d),
                                     hz=f(R, d), st_a=f(R, 2), h=f(R, d), z1=f(R, I), a1=f(R, I), z2=f(R, d), st_f=f(R, 2),
                                     out=f(R, d)))
         nc = ops.logits_num_chunks(2 * B, V)
@@ -54,8 +55,11 @@ class FusedTrainStep(object):
                  Gt=f(V, 2 * B), d_out2=f(2 * B, d), target2=torch.empty(2 * B, dtype=torch.int64, device=dev),
                  row_scale=torch.cat((torch.full((B,), 1.0 / B), torch.full((B,), -1.0 / B))).to(dev))
         for n, w in (('d_out', d), ('d_z2', d), ('d_a1', I), ('d_z1', I), ('d_h', d), ('d_hz', d), ('d_x', d), ('d_ctx', d),
-                     ('d_mq', d), ('d_mk', d), ('d_mv', d), ('d_aq', d), ('d_ak', d), ('d_gl', L)):
+                     ('d_gl', L)):
             b[n] = f(2 * T, w)
+        b['d_qkv'], b['d_aqk'] = f(3, 2 * T, d), f(2, 2 * T, d)
+        b['d_mq'], b['d_mk'], b['d_mv'] = b['d_qkv'][0], b['d_qkv'][1], b['d_qkv'][2]
+        b['d_aq'], b['d_ak'] = b['d_aqk'][0], b['d_aqk'][1]
         self.buf[key] = b
         return b
 
@@ -107,11 +111,16 @@ class FusedTrainStep(object):
             aa, ff = layer.attack_attention, layer.feed_forward
             base = 16 * (l + 1)
             xs.append(x)
-            torch.addmm(aa.query.bias, x, aa.query.weight.t(), out=lb['mq'])
-            torch.addmm(aa.key.bias, x, aa.key.weight.t(), out=lb['mk'])
-            torch.addmm(aa.value.bias, x, aa.value.weight.t(), out=lb['mv'])
-            torch.addmm(aa.attack_query_transform.bias, lb['mq'], aa.attack_query_transform.weight.t(), out=lb['aq'])
-            torch.addmm(aa.attack_key_transform.bias, lb['mk'], aa.attack_key_transform.weight.t(), out=lb['ak'])
+            st3 = self._stacked(l)
+            if st3 is not None:                               # Q/K/V and the attack pair as two batched GEMMs
+                torch.baddbmm(st3['bqkv'], x.unsqueeze(0).expand(3, T, d), st3['Wqkv'].transpose(1, 2), out=lb['qkv'])
+                torch.baddbmm(st3['baqk'], lb['qkv'][:2], st3['Waqk'].transpose(1, 2), out=lb['aqk'])
+            else:
+                torch.addmm(aa.query.bias, x, aa.query.weight.t(), out=lb['mq'])
+                torch.addmm(aa.key.bias, x, aa.key.weight.t(), out=lb['mk'])
+                torch.addmm(aa.value.bias, x, aa.value.weight.t(), out=lb['mv'])
+                torch.addmm(aa.attack_query_transform.bias, lb['mq'], aa.attack_query_transform.weight.t(), out=lb['aq'])
+                torch.addmm(aa.attack_key_transform.bias, lb['mk'], aa.attack_key_transform.weight.t(), out=lb['ak'])
             gate = layer.combine_option == 'gate'
             comb_scalar = 0.0
             if gate:
@@ -214,16 +223,27 @@ class FusedTrainStep(object):
                          _p(g(db_)) if own else None, _p(g(sc)) if own else None, _p(g(rr)) if own else None, st)
             # projections: input gradients for both streams, weight gradients from the owning stream
             aqt, akt = aa.attack_query_transform, aa.attack_key_transform
-            b['d_mq'].addmm_(b['d_aq'], aqt.weight)
-            b['d_mk'].addmm_(b['d_ak'], akt.weight)
-            LIB.call('acsr_linear_wgrad', _p(b['d_aq'][T:]), _p(lb['mq']), T, d, d, _p(aqt.weight.grad), _p(aqt.bias.grad), st)
-            LIB.call('acsr_linear_wgrad', _p(b['d_ak'][T:]), _p(lb['mk']), T, d, d, _p(akt.weight.grad), _p(akt.bias.grad), st)
+            st3 = self._stacked(l)
+            if st3 is not None:
+                b['d_qkv'][:2].baddbmm_(b['d_aqk'], st3['Waqk'])
+                # attack transforms are trained by the attacked-loss stream (rows [T,2T))
+                LIB.call('acsr_linear_wgrad_batched', _p(b['d_aqk'][0, T:]), _p(lb['qkv'][0]), T, d, d, _p(st3['gWaqk']),
+                         _p(st3['gbaqk']), 2, T2 * d, T * d, d * d, d, st)
+            else:
+                b['d_mq'].addmm_(b['d_aq'], aqt.weight)
+                b['d_mk'].addmm_(b['d_ak'], akt.weight)
+                LIB.call('acsr_linear_wgrad', _p(b['d_aq'][T:]), _p(lb['mq']), T, d, d, _p(aqt.weight.grad), _p(aqt.bias.grad), st)
+                LIB.call('acsr_linear_wgrad', _p(b['d_ak'][T:]), _p(lb['mk']), T, d, d, _p(akt.weight.grad), _p(akt.bias.grad), st)
             if gate:
                 b['d_mq'].addmm_(b['d_gl'], layer.gate.weight)
                 LIB.call('acsr_linear_wgrad', _p(b['d_gl']), _p(lb['mq']), T, L, d, _p(layer.gate.weight.grad),
                          _p(layer.gate.bias.grad), st)
-            for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
-                LIB.call('acsr_linear_wgrad', _p(b[dk]), _p(x), T, d, d, _p(lin.weight.grad), _p(lin.bias.grad), st)
+            if st3 is not None:
+                LIB.call('acsr_linear_wgrad_batched', _p(b['d_qkv'][0]), _p(x), T, d, d, _p(st3['gWqkv']), _p(st3['gbqkv']), 3,
+                         T2 * d, 0, d * d, d, st)
+            else:
+                for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
+                    LIB.call('acsr_linear_wgrad', _p(b[dk]), _p(x), T, d, d, _p(lin.weight.grad), _p(lin.bias.grad), st)
             if l > 0:
                 for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
                     d_x.addmm_(b[dk], lin.weight)
@@ -235,6 +255,30 @@ class FusedTrainStep(object):
                  _p(b['st_e']), T, L, d, V, p_h, _p(me), rngp, 1, _p(E.grad), _p(posw.grad if posw is not None else None),
                  _p(m.LayerNorm.weight.grad), _p(m.LayerNorm.bias.grad), st)
         return loss_att, loss_cal
+
+    def _stacked(self, l):
+        """stacked views [3,d,d]/[2,d,d] of the Q/K/V and attack-pair parameters (adjacent in FlatAdam's layout)."""
+        if not hasattr(self, '_st'):
+            self._st = {}
+        if l not in self._st:
+            aa = self.m.trm_encoder.layer[l].attack_attention
+            opt = self.opt
+            if not hasattr(opt, 'stacked'):
+                self._st[l] = None
+            else:
+                qkv_w, qkv_b = [aa.query.weight, aa.key.weight, aa.value.weight], [aa.query.bias, aa.key.bias, aa.value.bias]
+                aqk_w = [aa.attack_query_transform.weight, aa.attack_key_transform.weight]
+                aqk_b = [aa.attack_query_transform.bias, aa.attack_key_transform.bias]
+                v = dict(Wqkv=opt.stacked(qkv_w), bqkv=opt.stacked(qkv_b), Waqk=opt.stacked(aqk_w), baqk=opt.stacked(aqk_b),
+                         gWqkv=opt.stacked(qkv_w, True), gbqkv=opt.stacked(qkv_b, True), gWaqk=opt.stacked(aqk_w, True),
+                         gbaqk=opt.stacked(aqk_b, True))
+                if any(t is None for t in v.values()):
+                    self._st[l] = None
+                else:
+                    v['bqkv'] = v['bqkv'].unsqueeze(1)
+                    v['baqk'] = v['baqk'].unsqueeze(1)
+                    self._st[l] = v
+        return self._st[l]
 
     @staticmethod
     def _attn_args(layer, lb, seq, B, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base):

@@ -46,23 +46,53 @@ class FlatAdam(object):
     def __init__(self, model, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
         params = [p for p in model.parameters()]
         dev = params[0].device
-        align = 64                      # floats: every parameter starts on a 256-byte boundary (float4 / bulk-copy loads)
-        n = sum((p.numel() + align - 1) // align * align for p in params)
+        align = 64                      # floats: every group starts on a 256-byte boundary (float4 / bulk-copy loads)
+        # groups of parameters that must be adjacent (no padding) so they can be viewed as one stacked tensor
+        groups, seen = [], set()
+        for g in (model.flat_groups() if hasattr(model, 'flat_groups') else []):
+            groups.append(list(g))
+            seen.update(id(p) for p in g)
+        layout = []
+        gi = {id(g[0]): g for g in groups}
+        for p in params:
+            if id(p) in gi:
+                layout.append(gi[id(p)])
+            elif id(p) not in seen:
+                layout.append([p])
+        n = sum((sum(p.numel() for p in g) + align - 1) // align * align for g in layout)
         self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.offsets = {}
         off = 0
         with torch.no_grad():
-            for p in params:
-                k = p.numel()
-                self.flat_param[off:off + k].copy_(p.data.reshape(-1))
-                p.data = self.flat_param[off:off + k].view(p.shape)
-                p.grad = self.flat_grad[off:off + k].view(p.shape)
-                off += (k + align - 1) // align * align
+            for g in layout:
+                start = off
+                for p in g:
+                    k = p.numel()
+                    if k % 4:
+                        off = (off + 3) // 4 * 4
+                    self.flat_param[off:off + k].copy_(p.data.reshape(-1))
+                    p.data = self.flat_param[off:off + k].view(p.shape)
+                    p.grad = self.flat_grad[off:off + k].view(p.shape)
+                    self.offsets[id(p)] = off
+                    off += k
+                off = start + (off - start + align - 1) // align * align
+        assert off <= n + align * len(layout)
         self.lr, self.weight_decay, self.betas, self.eps = float(lr), float(weight_decay or 0.0), betas, eps
         self.params = params
+
+    def stacked(self, plist, grad=False):
+        """view of adjacent, equally shaped parameters (or their grads) as one [len, *shape] tensor; None if not adjacent."""
+        k = plist[0].numel()
+        off0 = self.offsets[id(plist[0])]
+        for i, p in enumerate(plist):
+            if p.shape != plist[0].shape or self.offsets[id(p)] != off0 + i * k:
+                return None
+        src = self.flat_grad if grad else self.flat_param
+        return src[off0:off0 + len(plist) * k].view(len(plist), *plist[0].shape)
 
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()
@@ -113,6 +143,7 @@ class ACSASRecTrainer(object):
         self.use_graph = bool(cfg_get(config, 'cuda_graph', True))
         self.fused_topk = bool(cfg_get(config, 'fused_topk', True))
         self._graph = None
+        self._eval_graphs = {}
         self.dp_world = 1
         self.fused = None
         if (bool(cfg_get(config, 'fused_step', True)) and isinstance(self.optimizer, FlatAdam)
@@ -347,6 +378,8 @@ class ACSASRecTrainer(object):
         interaction, history_index, positive_u, positive_i = batched_data
         kmax = max(self.topk)
         if self.fused_topk and history_index is None:
+            if self.use_graph and not self.model.training:
+                return self._graphed_eval(interaction, positive_i, kmax)
             inter = interaction.to(self.device)
             _, _, rec = self.model.full_sort_topk(inter, kmax, positive_i.to(self.device, non_blocking=True))
             return rec
@@ -355,6 +388,39 @@ class ACSASRecTrainer(object):
         pos = positive_i.to(self.device)
         flags = (topk_idx == pos.view(-1, 1)).to(torch.int32)
         return torch.cat((flags, torch.ones_like(flags[:, :1])), dim=1)
+
+    @torch.no_grad()
+    def _graphed_eval(self, interaction, positive_i, kmax):
+        """forward + fused logits/top-k + hit flags of one eval batch as a CUDA-graph replay (one graph per batch shape).
+        The batch (host or device) is copied into static buffers; the returned rec tensor is a fresh copy."""
+        m = self.model
+        fields = [m.ITEM_SEQ, m.ITEM_SEQ_LEN]
+        key = tuple(tuple(interaction[k].shape) for k in fields) + (kmax,)
+        g = self._eval_graphs.get(key)
+        if g is None:
+            dev = self.device
+            static = {k: torch.empty_like(interaction[k], device=dev) for k in fields}
+            for k in fields:
+                static[k].copy_(interaction[k])
+            pos = torch.empty_like(positive_i, device=dev)
+            pos.copy_(positive_i)
+            inter = Interaction(static)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    m.full_sort_topk(inter, kmax, pos)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                _, _, rec = m.full_sort_topk(inter, kmax, pos)
+            g = dict(graph=graph, static=static, pos=pos, rec=rec)
+            self._eval_graphs[key] = g
+        for k in fields:
+            g['static'][k].copy_(interaction[k], non_blocking=True)
+        g['pos'].copy_(positive_i, non_blocking=True)
+        g['graph'].replay()
+        return g['rec'].clone()
 
     @torch.no_grad()
     def evaluate(self, eval_data, load_best_model=True, model_file=None, show_progress=False):

@@ -170,7 +170,8 @@ def run_ours(args):
         ge.build()
     if world > 1:
         dist.barrier()
-    A, cfg, config, model, trainer = build(dev, rank, world, cuda_graph=(world == 1))
+    use_graph = world == 1 or bool(args.dp_graph)
+    A, cfg, config, model, trainer = build(dev, rank, world, cuda_graph=use_graph)
     if world > 1:
         trainer.enable_data_parallel()
     B, L, V, K, W = WORKLOAD['B'], WORKLOAD['L'], WORKLOAD['V'], args.steps, args.warmup
@@ -181,7 +182,7 @@ def run_ours(args):
     devb = [h.to(dev) for h in host]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     model.train()
-    step = trainer.graphed_step if world == 1 else trainer.train_step
+    step = trainer.graphed_step if use_graph else trainer.train_step
     it = [0]
 
     def dev_step():
@@ -191,7 +192,7 @@ def run_ours(args):
 
     def e2e_step():
         b = host[it[0] % nb]
-        la, lc = step(b if world == 1 else b.to(dev))
+        la, lc = step(b if use_graph else b.to(dev))
         loss_pin[0:1].copy_(la.reshape(1), non_blocking=True)
         loss_pin[1:2].copy_(lc.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()                      # the loss is read on the host every step
@@ -223,7 +224,7 @@ def run_ours(args):
     def eval_dev():
         b = devb[it[0] % nb]
         with torch.no_grad():
-            model.full_sort_topk(b, kmax, b['item_id'])
+            trainer.eval_batch((b, None, None, b['item_id']))
         it[0] += 1
 
     def eval_e2e():
@@ -290,9 +291,24 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e, ms_eval, ms_eval_e2e = [float(x) for x in t.tolist()]
-    if rank != 0:
-        if world > 1:
+    def shutdown():
+        """release the captured graph (it pins NCCL resources) before tearing the process group down; never hang at exit"""
+        if world == 1:
+            return
+        import gc
+        trainer._graph = None
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        try:
+            dist.barrier()
             dist.destroy_process_group()
+        except Exception:
+            pass
+        os._exit(0)
+    if rank != 0:
+        shutdown()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -307,7 +323,7 @@ def run_ours(args):
                                % (WORKLOAD['name'], V, WORKLOAD['users'], L, WORKLOAD['d'], WORKLOAD['n_layers'], WORKLOAD['n_heads'],
                                   WORKLOAD['inner'], B, kmax),
                    'parallelism': 'dp%d (batch-parallel, replicated item table, NCCL all-reduce of the flat gradient)' % world if world > 1 else 'single GPU',
-                   'launch': 'CUDA graph replay of the whole step' if world == 1 else 'eager launches + NCCL',
+                   'launch': ('CUDA graph replay of the whole step' + (' (NCCL all-reduce captured)' if world > 1 else '')) if use_graph else 'eager launches + NCCL',
                    'logits': '3xTF32 tcgen05 (fp32-level accuracy)'},
         'e2e': {'value': round(world * B * K / (ms_e2e / 1e3), 1), 'unit': 'seq/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8},
         'gpu_launches': int(round(launches_per_step * K)),
@@ -323,8 +339,7 @@ def run_ours(args):
     if cpu is not None:
         line['cpu_baseline'] = cpu
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def run_profile(args):
@@ -426,6 +441,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dp-graph', type=int, default=1, help='capture the NCCL all-reduce inside the CUDA graph at N>1 (0 = eager launches)')
     ap.add_argument('--profile', action='store_true',
                     help='launch-list mode for ncu: W+K eager training steps and K eval batches, nothing else')
     args = ap.parse_args()

@@ -179,6 +179,10 @@ int acsr_topk_merge(const float* partial_val, const int64_t* partial_idx, int M,
  * layers.py:658-659, 687-689, 680, 791-794, 887):  dW[N,K] += dY[T,N]^T . X[T,K],  db[N] += sum_t dY[t,:]
  * (db may be NULL).  Accumulates with atomics: the caller zeroes or passes its gradient buffer. */
 int acsr_linear_wgrad(const float* dY, const float* X, int T, int N, int K, float* dW, float* db, void* stream);
+/* `batch` independent problems in one launch; problem z uses dY + z*stride_dy, X + z*stride_x (0 = shared input),
+ * dW + z*stride_dw, db + z*stride_db (strides in floats).  Used for the stacked Q/K/V and attack-Q/K projections. */
+int acsr_linear_wgrad_batched(const float* dY, const float* X, int T, int N, int K, float* dW, float* db, int batch,
+                              int64_t stride_dy, int64_t stride_x, int64_t stride_dw, int64_t stride_db, void* stream);
 
 /* ---- K13: fused Adam over one flat fp32 buffer (trainer/trainer.py:614-615,687) ---------
  * torch.optim.Adam semantics (no amsgrad); step_count device int64[1], incremented by the call. */

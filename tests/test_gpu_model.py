@@ -299,3 +299,36 @@ def test_fused_step_equals_autograd_step_full_batch(A):
     for n in g0:
         scale = float(g0[n].abs().max())
         assert float((g0[n] - g1[n]).abs().max()) <= 2e-4 * scale + 1e-9, n
+
+
+def test_full_size_properties_million_item_catalogue(A):
+    """BASELINE config #4 shape on one GPU (V=1,000,001, B=256): fused CE and fused top-k against the
+    materialised scores of the same device GEMM (size-independent identities, no CPU reference needed)."""
+    V, B, k = 1000001, 256, 50
+    g = torch.Generator().manual_seed(4)
+    out = (torch.randn(2 * B, 64, generator=g) * 0.7).cuda()
+    E = (torch.randn(V, 64, generator=g) * 0.05).cuda()
+    tgt = torch.randint(1, V, (2 * B,), generator=g).cuda()
+    scores = A.ops.logits_scores(out, E, 3)                                 # [512, 1e6] fp32 = 2 GB
+    chk = (out[:8].double() @ E[:4096].double().t())
+    assert float((scores[:8, :4096].double() - chk).abs().max()) < 2e-6 * float(chk.abs().max())
+    loss = A.ops.LogitsCEFn.apply(out, E, tgt, 2, 3)
+    ref = torch.logsumexp(scores.double(), 1) - scores.double()[torch.arange(2 * B), tgt]
+    want = torch.stack([ref[:B].mean(), ref[B:].mean()])
+    assert float((loss.double() - want).abs().max()) < 1e-5 * float(want.abs().max())
+    val, idx, rec = A.ops.full_sort_topk(out[:B], E, k, tgt[:B], 3)
+    s = scores[:B].clone()
+    s[:, 0] = -np.inf
+    rv, ri = torch.topk(s, k, dim=-1)
+    ok, nbad = O.topk_equal_modulo_ties(idx.cpu(), ri.cpu(), scores[:B].cpu())
+    assert ok, nbad
+    assert (val[:, :-1] >= val[:, 1:]).all()
+    assert torch.equal(rec[:, :-1].bool(), idx == tgt[:B].view(-1, 1))
+    del scores, s
+    # gradient identity: rows of (softmax - onehot) sum to zero, d_out = G.E
+    lse = torch.logsumexp(A.ops.logits_scores(out[:64], E, 3).double(), 1).float()
+    Gt = A.ops.ce_grad_matrix_t(out[:64].contiguous(), E, lse, tgt[:64].contiguous(), torch.ones(64).cuda(), 3)
+    assert float(Gt.double().sum(0).abs().max()) < 1e-4
+    d_out, _ = A.ops.linear_wgrad(Gt, E, want_bias=False)
+    want_d = (Gt.double().t() @ E.double())
+    assert float((d_out.double() - want_d).abs().max()) < 1e-4 * float(want_d.abs().max())
