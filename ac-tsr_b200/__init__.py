@@ -9,7 +9,7 @@ All arithmetic runs in csrc/libacsr.so (C ABI: include/acsr.h).  No CPU fallback
 
 The directory name contains a hyphen; import it as `ac_tsr_b200` (shim module at the repo root).
 """
-from . import _lib, build, compat, data, evaluator, layers, ops, trainer, acsasrec, fused_step    # noqa: F401
+from . import _lib, build, compat, data, evaluator, layers, ops, trainer, acsasrec, fused_step, dist    # noqa: F401
 from ._lib import LIB, AcsrError                                                      # noqa: F401
 from .acsasrec import ACSASRec                                                        # noqa: F401
 from .compat import Config, Interaction, ModelType                                    # noqa: F401

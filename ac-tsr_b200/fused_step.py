@@ -31,6 +31,7 @@ class FusedTrainStep(object):
             raise NotImplementedError('fused step covers loss_type CE (the shipped configs); BPR takes the autograd path')
         self.m, self.opt = model, optimizer
         self.buf = {}
+        self.vp = None            # dist.VocabParallel when the logits are sharded over ranks
 
     # ------------------------------------------------------------------------------------------
     def _buffers(self, B, L, dev):
@@ -152,9 +153,15 @@ class FusedTrainStep(object):
         LIB.call('acsr_gather_last_fwd', _p(last_out[:T]), _p(last_out[T:]), _p(ln, torch.int64), B, L, d, _p(b['out2']), st)
         torch.cat((pos_items, pos_items), out=b['target2'])
         passes = m.logits_passes
-        LIB.call('acsr_logits_ce_partial', _p(b['out2']), _p(E), 2 * B, V, d, passes, _p(b['partial']), st)
-        LIB.call('acsr_ce_finalize', _p(b['partial']), b['partial'].shape[1], _p(b['out2']), _p(E), _p(b['target2'], torch.int64),
-                 2 * B, d, V, 0, 2, _p(b['lse']), _p(b['tgt']), _p(b['row_loss']), _p(b['loss']), st)
+        vst = None
+        if self.vp is not None:       # all-gather out -> shard-local partial CE -> all-gather (max, sum-exp) -> combine
+            loss2, vst = self.vp.ce_forward(b['out2'], E, b['target2'], 2)
+            b['loss'].copy_(loss2)
+        else:
+            LIB.call('acsr_logits_ce_partial', _p(b['out2']), _p(E), 2 * B, V, d, passes, _p(b['partial']), st)
+            LIB.call('acsr_ce_finalize', _p(b['partial']), b['partial'].shape[1], _p(b['out2']), _p(E),
+                     _p(b['target2'], torch.int64), 2 * B, d, V, 0, 2, _p(b['lse']), _p(b['tgt']), _p(b['row_loss']),
+                     _p(b['loss']), st)
         pen32 = b['pen'].to(torch.float32)
         pen_norm = torch.sqrt(pen32)
         w = m.mask_loss_weight.detach()[0] if m.trainable_mask_loss_weight else float(m.mask_loss_weight)
@@ -165,11 +172,14 @@ class FusedTrainStep(object):
         # ---------------- backward ----------------
         dpen = (w / (2.0 * N)) / pen_norm                     # d loss_att / d pen_sq_l
         opt.zero_grad()
-        LIB.call('acsr_logits_ce_grad', _p(b['out2']), _p(E), _p(b['lse']), _p(b['target2'], torch.int64), _p(b['row_scale']),
-                 2 * B, V, d, passes, _p(b['Gt']), 2 * B, st)
-        b['d_out2'].zero_()
-        LIB.call('acsr_linear_wgrad', _p(b['Gt']), _p(E), V, 2 * B, d, _p(b['d_out2']), None, st)
-        E.grad.addmm_(b['Gt'][:, :B], b['out2'][:B])           # only the calibrated rows train the item table
+        if self.vp is not None:       # shard-local G^T, reduce-scatter of d_out, dE into the owner's rows
+            b['d_out2'].copy_(self.vp.ce_backward(vst, E, b['row_scale'], E.grad, table_half=0, n_groups=2))
+        else:
+            LIB.call('acsr_logits_ce_grad', _p(b['out2']), _p(E), _p(b['lse']), _p(b['target2'], torch.int64),
+                     _p(b['row_scale']), 2 * B, V, d, passes, _p(b['Gt']), 2 * B, st)
+            b['d_out2'].zero_()
+            LIB.call('acsr_linear_wgrad', _p(b['Gt']), _p(E), V, 2 * B, d, _p(b['d_out2']), None, st)
+            E.grad.addmm_(b['Gt'][:, :B], b['out2'][:B])       # only the calibrated rows train the item table
         d_out, d_x = b['d_out'], b['d_x']
         d_out.zero_()
         LIB.call('acsr_gather_last_bwd', _p(b['d_out2']), _p(ln, torch.int64), B, L, d, _p(d_out[:T]), _p(d_out[T:]), st)

@@ -203,13 +203,22 @@ class ACSASRecTrainer(object):
         self.optimizer.step()
         return attacked_loss.detach(), calibrated_loss.detach()
 
-    def enable_data_parallel(self):
-        """One process per GPU, replicated parameters: broadcast rank 0's weights, then all-reduce gradients every step."""
+    def enable_data_parallel(self, vocab_parallel=False):
+        """One process per GPU, replicated parameters: broadcast rank 0's weights, then all-reduce gradients every step.
+        vocab_parallel=True additionally splits the full-catalogue logits/CE (and top-k) by item rows across ranks
+        (dist.VocabParallel: all-gather of `out`, all-gather of per-row (max, sum-exp), reduce-scatter of d_out)."""
         import torch.distributed as dist
         if not isinstance(self.optimizer, FlatAdam):
             raise ValueError('data-parallel training needs the flat Adam optimizer')
         self.dp_world = dist.get_world_size()
         dist.broadcast(self.optimizer.flat_param, src=0)
+        self.vp = None
+        if vocab_parallel:
+            if self.fused is None:
+                raise ValueError('vocab-parallel logits need the fused step (loss_type CE)')
+            from .dist import VocabParallel, CudaCompute
+            self.vp = VocabParallel(self.model.n_items, compute=CudaCompute(self.model.logits_passes))
+            self.fused.vp = self.vp
 
     def train_step(self, interaction):
         """One optimisation step on a device-resident Interaction (eager launch path)."""
