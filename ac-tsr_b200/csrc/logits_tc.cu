@@ -30,7 +30,7 @@ constexpr int kTcThreads = 320;
 constexpr int kTmemCols = 128;         // 2 accumulator stages x 64 columns
 constexpr int kMaxTopK = 64;
 
-enum { MODE_STORE = 0, MODE_CE = 1, MODE_GRAD = 2, MODE_TOPK = 3 };
+enum { MODE_STORE = 0, MODE_CE = 1, MODE_GRAD = 2, MODE_TOPK = 3, MODE_LINEAR = 4 };
 
 struct LogitsParams {
   const float* out;      // [M,64]
@@ -53,6 +53,11 @@ struct LogitsParams {
   int skip_col0;
   float* pval;           // [M, n_chunks, k]
   long long* pidx;
+  // LINEAR: stationary operand element (r,k) = out[r*out_sn + k*out_sk]; Y[v*ldc + r] (+)= D[r][v] + bias[r]
+  long long out_sn, out_sk;
+  const float* bias;
+  int accumulate;
+  long long b_out, b_table, b_bias, b_C;   // per-problem strides of a batched launch (blockIdx.y)
 };
 
 template <int MODE>
@@ -103,6 +108,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x % p.m_tiles;
   const int chunk = blockIdx.x / p.m_tiles;
+  const float* out_p = p.out + (MODE == MODE_LINEAR ? blockIdx.y * p.b_out : 0);
+  const float* table_p = p.table + (MODE == MODE_LINEAR ? blockIdx.y * p.b_table : 0);
+  float* C_p = p.C + (MODE == MODE_LINEAR ? blockIdx.y * p.b_C : 0);
   const int my_tiles = chunk < p.n_tiles ? (p.n_tiles - chunk + p.n_chunks - 1) / p.n_chunks : 0;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
@@ -132,7 +140,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
       const int r = item / kKC, kc = item % kKC;
       const int grow = m_tile * kBM + r;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (grow < p.M) x = *reinterpret_cast<const float4*>(p.out + (long long)grow * kD + kc * 4);
+      if (grow < p.M) {
+        if (MODE != MODE_LINEAR) x = *reinterpret_cast<const float4*>(out_p + (long long)grow * kD + kc * 4);
+        else if (p.out_sk == 1 && (p.out_sn & 3) == 0) x = *reinterpret_cast<const float4*>(out_p + grow * p.out_sn + kc * 4);
+        else {                         // transposed / strided weight (input-gradient GEMMs)
+          const float* w = out_p + grow * p.out_sn + (long long)(kc * 4) * p.out_sk;
+          x = make_float4(w[0], w[p.out_sk], w[2 * p.out_sk], w[3 * p.out_sk]);
+        }
+      }
       float4 hi = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
       float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
       const int off = kc * (kBM * 4) + r * 4;      // floats: chunk plane of kBM rows x 16 B
@@ -156,7 +171,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
         const long long rows = (p.V - n0) < kBN ? (p.V - n0) : kBN;
         mbar_wait(stg_empty + s, ph ^ 1);
         mbar_arrive_expect_tx(stg_full + s, (uint32_t)(rows * kD * 4));
-        bulk_g2s(smem + Cfg::kOffStg + s * Cfg::kBbytes, p.table + n0 * kD, (uint32_t)(rows * kD * 4), stg_full + s);
+        bulk_g2s(smem + Cfg::kOffStg + s * Cfg::kBbytes, table_p + n0 * kD, (uint32_t)(rows * kD * 4), stg_full + s);
       }
     }
   } else if (warp == 1) {
@@ -239,6 +254,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
     int cnt = 0, minpos = 0;
     float thr = -INFINITY;
     if (MODE == MODE_GRAD && row_ok) { g_lse = p.lse[grow]; g_scale = p.row_scale[grow]; g_tgt = p.target[grow]; }
+    float lin_bias = 0.f;
+    if (MODE == MODE_LINEAR && row_ok && p.bias != nullptr) lin_bias = p.bias[blockIdx.y * p.b_bias + grow];
     for (int it = 0; it < my_tiles; ++it) {
       const int ob = it & 1;
       const uint32_t ph = (it >> 1) & 1;
@@ -251,7 +268,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
         tmem_ld32(t_lane + ob * kBN + cc * 32, v);
         const long long c0 = n0 + cc * 32;
         const int nvalid = (int)((p.V - c0) < 32 ? ((p.V - c0) > 0 ? (p.V - c0) : 0) : 32);
-        if (MODE == MODE_GRAD) {
+        if (MODE == MODE_LINEAR) {
+          // Y[token][feature]: a warp's 32 features are 32 consecutive floats of one token row -> coalesced
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < nvalid) {
+                float* dst = C_p + (c0 + i) * p.ldc + grow;
+                float y = v[i] + lin_bias;
+                if (p.accumulate) y += *dst;
+                *dst = y;
+              }
+            }
+          }
+        } else if (MODE == MODE_GRAD) {
           // transposed store Gt[v][m]: a warp's 32 rows are 32 consecutive floats -> coalesced 128-byte lines
           if (row_ok) {
 #pragma unroll
@@ -259,13 +289,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
               if (i < nvalid) {
                 float g = __expf(v[i] - g_lse);
                 if (c0 + i == g_tgt) g -= 1.0f;
-                p.C[(c0 + i) * p.ldc + grow] = g * g_scale;
+                C_p[(c0 + i) * p.ldc + grow] = g * g_scale;
               }
             }
           }
         } else if (MODE == MODE_STORE) {
           if (row_ok) {
-            float* dst = p.C + (long long)grow * p.ldc + c0;
+            float* dst = C_p + (long long)grow * p.ldc + c0;
             if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -357,23 +387,23 @@ __global__ void __launch_bounds__(1024) ce_finalize_kernel(const float* __restri
   if (threadIdx.x < n_groups) loss[threadIdx.x] = (float)(gsum[threadIdx.x] / per_group);
 }
 
-static void plan(LogitsParams& p) {
+static void plan(LogitsParams& p, int batch = 1) {
   p.m_tiles = (p.M + kBM - 1) / kBM;
   p.n_tiles = (int)((p.V + kBN - 1) / kBN);
-  int nc = kNumSMs / (p.m_tiles > 0 ? p.m_tiles : 1);
+  int nc = kNumSMs / ((p.m_tiles > 0 ? p.m_tiles : 1) * batch);
   if (nc < 1) nc = 1;
   if (nc > p.n_tiles) nc = p.n_tiles;
   p.n_chunks = nc;
 }
 
 template <int MODE>
-static int launch_tc(LogitsParams& p, cudaStream_t st, const char* who) {
+static int launch_tc(LogitsParams& p, cudaStream_t st, const char* who, int batch = 1) {
   using Cfg = TcCfg<MODE>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
-  plan(p);
+  plan(p, batch);
   cudaError_t e = cudaFuncSetAttribute(logits_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) { set_error("%s: smem attr: %s", who, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
-  logits_tc_kernel<MODE><<<p.m_tiles * p.n_chunks, kTcThreads, Cfg::kSmemBytes, st>>>(p);
+  logits_tc_kernel<MODE><<<dim3(p.m_tiles * p.n_chunks, batch), kTcThreads, Cfg::kSmemBytes, st>>>(p);
   return check_launch(who);
 }
 
@@ -438,6 +468,21 @@ int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, 
   p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.C = G; p.ldc = ldg;
   p.lse = lse; p.target = (const long long*)target; p.row_scale = row_scale;
   return launch_tc<MODE_GRAD>(p, (cudaStream_t)stream, "logits_ce_grad");
+}
+
+int acsr_linear_tc(const float* X, int64_t rows, int K, const float* W, int N, int64_t w_stride_n, int64_t w_stride_k,
+                   const float* bias, int accumulate, float* Y, int64_t ldy, int batch, int64_t stride_x, int64_t stride_w,
+                   int64_t stride_bias, int64_t stride_y, int passes, void* stream) {
+  ACSR_REQUIRE(X && W && Y, "linear_tc: NULL pointer");
+  ACSR_REQUIRE(rows >= 0 && N > 0 && batch > 0 && batch < 65536 && ldy >= N, "linear_tc: bad sizes");
+  if (K != kD) { set_error("linear_tc: K=%d unsupported by the tensor-core path in ABI v1 (64)", K); return ACSR_ERR_UNSUPPORTED; }
+  ACSR_REQUIRE(passes == 1 || passes == 3, "linear_tc: passes must be 1 or 3");
+  if (rows == 0) return ACSR_OK;
+  LogitsParams p = {};
+  p.out = W; p.table = X; p.M = N; p.V = rows; p.passes = passes; p.C = Y; p.ldc = ldy;
+  p.out_sn = w_stride_n; p.out_sk = w_stride_k; p.bias = bias; p.accumulate = accumulate;
+  p.b_out = stride_w; p.b_table = stride_x; p.b_bias = stride_bias; p.b_C = stride_y;
+  return launch_tc<MODE_LINEAR>(p, (cudaStream_t)stream, "linear_tc", batch);
 }
 
 int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_t V, int d, int passes, int k, int64_t idx_offset,

@@ -32,6 +32,8 @@ class FusedTrainStep(object):
         self.m, self.opt = model, optimizer
         self.buf = {}
         self.vp = None            # dist.VocabParallel when the logits are sharded over ranks
+        # encoder GEMMs with K == 64 run on the tcgen05 linear kernel (3xTF32); other shapes stay library GEMMs
+        self.tc = bool(getattr(model, 'tc_linear', True)) and model.hidden_size == 64
 
     # ------------------------------------------------------------------------------------------
     def _buffers(self, B, L, dev):
@@ -113,7 +115,11 @@ class FusedTrainStep(object):
             base = 16 * (l + 1)
             xs.append(x)
             st3 = self._stacked(l)
-            if st3 is not None:                               # Q/K/V and the attack pair as two batched GEMMs
+            if st3 is not None and self.tc:                   # stacked Q/K/V and attack pair: two batched tcgen05 launches
+                ops.linear_tc(x, T, st3['Wqkv'], d, d, 1, st3['bqkv'], lb['qkv'], d, batch=3, sx=0, sw=d * d, sb=d, sy=T * d)
+                ops.linear_tc(lb['qkv'], T, st3['Waqk'], d, d, 1, st3['baqk'], lb['aqk'], d, batch=2, sx=T * d, sw=d * d, sb=d,
+                              sy=T * d)
+            elif st3 is not None:                             # Q/K/V and the attack pair as two batched GEMMs
                 torch.baddbmm(st3['bqkv'], x.unsqueeze(0).expand(3, T, d), st3['Wqkv'].transpose(1, 2), out=lb['qkv'])
                 torch.baddbmm(st3['baqk'], lb['qkv'][:2], st3['Waqk'].transpose(1, 2), out=lb['aqk'])
             else:
@@ -127,7 +133,10 @@ class FusedTrainStep(object):
             if gate:
                 if layer.gate.out_features != L:
                     raise ValueError('gate width %d != sequence length %d' % (layer.gate.out_features, L))
-                torch.addmm(layer.gate.bias, lb['mq'], layer.gate.weight.t(), out=lb['gl'])
+                if self.tc:
+                    ops.linear_tc(lb['mq'], T, layer.gate.weight, L, d, 1, layer.gate.bias, lb['gl'], L)
+                else:
+                    torch.addmm(layer.gate.bias, lb['mq'], layer.gate.weight.t(), out=lb['gl'])
             elif layer.combine_option == 'annealing':
                 comb_scalar = math.exp(-layer.anneal_step / 100000)
                 layer.anneal_step += 1
@@ -135,12 +144,18 @@ class FusedTrainStep(object):
             lb['attn_args'] = self._attn_args(layer, lb, seq, B, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base)
             ctx_cal, ctx_att = lb['ctx'][:T], (lb['ctx'][T:] if last else None)
             LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal), b['pen'][l:].data_ptr(), None, st)
-            torch.mm(lb['ctx'], aa.dense.weight.t(), out=lb['hz'])
+            if self.tc:
+                ops.linear_tc(lb['ctx'], R, aa.dense.weight, d, d, 1, None, lb['hz'], d)
+            else:
+                torch.mm(lb['ctx'], aa.dense.weight.t(), out=lb['hz'])
             lb['m_a'] = mask2(l, 'D5', 'D4', last)
             LIB.call('acsr_bias_dropout_res_ln_fwd', _p(lb['hz']), _p(aa.dense.bias), _p(x), _p(aa.LayerNorm.weight),
                      _p(aa.LayerNorm.bias), aa.LayerNorm.eps, R, d, T, p_h, _p(lb['m_a']), rngp, base + 3, _p(lb['h']),
                      _p(lb['st_a']), st)
-            torch.mm(lb['h'], ff.dense_1.weight.t(), out=lb['z1'])
+            if self.tc:
+                ops.linear_tc(lb['h'], R, ff.dense_1.weight, I, d, 1, None, lb['z1'], I)
+            else:
+                torch.mm(lb['h'], ff.dense_1.weight.t(), out=lb['z1'])
             LIB.call('acsr_bias_act_fwd', _p(lb['z1']), _p(ff.dense_1.bias), R, I, act_id, _p(lb['a1']), st)
             torch.mm(lb['a1'], ff.dense_2.weight.t(), out=lb['z2'])
             lb['m_f'] = mask2(l, 'D7', 'D6', last)
@@ -199,7 +214,10 @@ class FusedTrainStep(object):
                      _p(b['d_z2']), _p(b['d_h']), _p(ff.dense_2.bias.grad), _p(ff.LayerNorm.weight.grad),
                      _p(ff.LayerNorm.bias.grad), st)
             LIB.call('acsr_linear_wgrad', _p(b['d_z2']), _p(lb['a1']), T, d, I, _p(ff.dense_2.weight.grad), None, st)
-            torch.mm(b['d_z2'], ff.dense_2.weight, out=b['d_a1'])
+            if self.tc:                                      # d_a1 = d_z2.W2 : Wt[i][c] = W2[c*I + i]
+                ops.linear_tc(b['d_z2'], T2, ff.dense_2.weight, I, 1, I, None, b['d_a1'], I)
+            else:
+                torch.mm(b['d_z2'], ff.dense_2.weight, out=b['d_a1'])
             LIB.call('acsr_bias_act_bwd', _p(b['d_a1']), _p(lb['z1']), _p(ff.dense_1.bias), T2, I, act_id, P, T, _p(b['d_z1']),
                      _p(ff.dense_1.bias.grad), st)
             LIB.call('acsr_linear_wgrad', _p(b['d_z1']), _p(lb['h']), T, I, d, _p(ff.dense_1.weight.grad), None, st)
@@ -209,7 +227,10 @@ class FusedTrainStep(object):
                      _p(aa.LayerNorm.weight), _p(lb['st_a']), T2, d, P, T, T, p_h, _p(lb['m_a']), rngp, base + 3,
                      _p(b['d_hz']), _p(d_x), _p(aa.dense.bias.grad), _p(aa.LayerNorm.weight.grad), _p(aa.LayerNorm.bias.grad), st)
             LIB.call('acsr_linear_wgrad', _p(b['d_hz']), _p(lb['ctx']), T, d, d, _p(aa.dense.weight.grad), None, st)
-            torch.mm(b['d_hz'], aa.dense.weight, out=b['d_ctx'])
+            if self.tc:
+                ops.linear_tc(b['d_hz'], T2, aa.dense.weight, d, 1, d, None, b['d_ctx'], d)
+            else:
+                torch.mm(b['d_hz'], aa.dense.weight, out=b['d_ctx'])
             # fused attention backward, one launch per cotangent stream
             if gate:
                 b['d_gl'].zero_()
@@ -235,7 +256,11 @@ class FusedTrainStep(object):
             aqt, akt = aa.attack_query_transform, aa.attack_key_transform
             st3 = self._stacked(l)
             if st3 is not None:
-                b['d_qkv'][:2].baddbmm_(b['d_aqk'], st3['Waqk'])
+                if self.tc:
+                    ops.linear_tc(b['d_aqk'], T2, st3['Waqk'], d, 1, d, None, b['d_qkv'], d, accumulate=True, batch=2,
+                                  sx=T2 * d, sw=d * d, sb=0, sy=T2 * d)
+                else:
+                    b['d_qkv'][:2].baddbmm_(b['d_aqk'], st3['Waqk'])
                 # attack transforms are trained by the attacked-loss stream (rows [T,2T))
                 LIB.call('acsr_linear_wgrad_batched', _p(b['d_aqk'][0, T:]), _p(lb['qkv'][0]), T, d, d, _p(st3['gWaqk']),
                          _p(st3['gbaqk']), 2, T2 * d, T * d, d * d, d, st)
@@ -256,11 +281,17 @@ class FusedTrainStep(object):
                     LIB.call('acsr_linear_wgrad', _p(b[dk]), _p(x), T, d, d, _p(lin.weight.grad), _p(lin.bias.grad), st)
             if l > 0:
                 for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
-                    d_x.addmm_(b[dk], lin.weight)
+                    if self.tc:
+                        ops.linear_tc(b[dk], T2, lin.weight, d, 1, d, None, d_x, d, accumulate=True)
+                    else:
+                        d_x.addmm_(b[dk], lin.weight)
                 d_out, d_x = d_x, d_out                       # this layer's input gradient is the next one's output gradient
             else:
                 for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
-                    d_x[:T].addmm_(b[dk][:T], lin.weight)     # below the first layer only the calibrated stream trains anything
+                    if self.tc:                               # below the first layer only the calibrated stream trains anything
+                        ops.linear_tc(b[dk], T, lin.weight, d, 1, d, None, d_x, d, accumulate=True)
+                    else:
+                        d_x[:T].addmm_(b[dk][:T], lin.weight)
         LIB.call('acsr_embed_ln_dropout_bwd', _p(d_x[:T]), _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight),
                  _p(b['st_e']), T, L, d, V, p_h, _p(me), rngp, 1, _p(E.grad), _p(posw.grad if posw is not None else None),
                  _p(m.LayerNorm.weight.grad), _p(m.LayerNorm.bias.grad), st)

@@ -288,6 +288,12 @@ def linear_wgrad(dY, X, dW=None, db=None, want_bias=True):
     return dW, db
 
 
+def linear_tc(X, rows, W, N, w_sn, w_sk, bias, Y, ldy, accumulate=False, batch=1, sx=0, sw=0, sb=0, sy=0, passes=3):
+    """Y[rows,N] (+)= X[rows,64].Wt^T + bias on tcgen05 (acsr_linear_tc); pointers may be views, strides in floats."""
+    LIB.call('acsr_linear_tc', _p(X), int(rows), 64, _p(W), int(N), int(w_sn), int(w_sk), _p(bias), int(bool(accumulate)),
+             _p(Y), int(ldy), int(batch), int(sx), int(sw), int(sb), int(sy), passes, _stream())
+
+
 class LinearFn(torch.autograd.Function):
     """y = x.W^T (+ b).  Forward and dX are library GEMMs; dW/db use the token-split kernel."""
 

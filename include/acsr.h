@@ -175,6 +175,15 @@ int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_
 int acsr_topk_merge(const float* partial_val, const int64_t* partial_idx, int M, int n_parts, int k,
                     const int64_t* positive, float* topk_val, int64_t* topk_idx, int32_t* rec_topk, void* stream);
 
+/* ---- token-parallel linear layer on tcgen05 (3xTF32):  Y[rows, N] (+)= X[rows, K] . Wt^T + bias,  K == 64 (ABI v1).
+ * replaces the forward nn.Linear calls at layers.py:658-659, 680, 687-689, 791 and their input-gradient GEMMs.
+ * The stationary operand is addressed as Wt[n][k] = W[n*w_stride_n + k*w_stride_k]: (K,1) for y = x.W^T with W [N,K]
+ * row-major, (1,ldw) for dx = dy.W.  accumulate != 0 adds into Y.  `batch` independent problems per launch with
+ * float strides stride_x/w/bias/y (stacked Q/K/V).  X rows must be contiguous (row pitch K). */
+int acsr_linear_tc(const float* X, int64_t rows, int K, const float* W, int N, int64_t w_stride_n, int64_t w_stride_k,
+                   const float* bias, int accumulate, float* Y, int64_t ldy, int batch, int64_t stride_x, int64_t stride_w,
+                   int64_t stride_bias, int64_t stride_y, int passes, void* stream);
+
 /* ---- weight / bias gradient of a token-parallel linear layer (backward of the nn.Linear calls in
  * layers.py:658-659, 687-689, 680, 791-794, 887):  dW[N,K] += dY[T,N]^T . X[T,K],  db[N] += sum_t dY[t,:]
  * (db may be NULL).  Accumulates with atomics: the caller zeroes or passes its gradient buffer. */

@@ -412,3 +412,30 @@ def test_linear_wgrad_and_linear_fn(A, T, N, K):
         assert y.shape == (1, T, N)
         (y * dY.cuda().view(1, T, N)).sum().backward()
         close(xc.grad, xo.grad, 2e-5, 'dx'); close(Wc.grad, Wo.grad, 2e-5, 'dW'); close(bc.grad, bo.grad, 2e-5, 'db')
+
+
+@pytest.mark.parametrize('rows,N,transposed,bias,acc,batch', [
+    (12800, 64, False, True, False, 1), (12800, 256, False, False, False, 1), (12800, 50, False, True, False, 1),
+    (25600, 256, True, False, False, 1), (25600, 64, True, False, True, 1), (12800, 64, False, True, False, 3),
+    (25600, 64, True, False, True, 2), (77, 64, False, True, False, 1), (1, 130, False, False, True, 1)])
+def test_linear_tc(A, rows, N, transposed, bias, acc, batch):
+    """tcgen05 linear (3xTF32): Y (+)= X.Wt^T + b against fp64, forward and input-gradient addressing, batched."""
+    g = torch.Generator().manual_seed(rows + N + batch)
+    X = torch.randn(batch, rows, 64, generator=g)
+    W = torch.randn(batch, 64, N, generator=g) * 0.2 if transposed else torch.randn(batch, N, 64, generator=g) * 0.2
+    b = torch.randn(batch, N, generator=g) if bias else None
+    Y0 = torch.randn(batch, rows, N, generator=g)
+    Wt = W.transpose(1, 2) if transposed else W                     # [batch, N, 64]
+    ref = X.double() @ Wt.double().transpose(1, 2)
+    if bias:
+        ref = ref + b.double().unsqueeze(1)
+    if acc:
+        ref = ref + Y0.double()
+    Xc, Wc, Yc = X.cuda(), W.cuda(), Y0.clone().cuda()
+    bc = b.cuda() if bias else None
+    sn, sk = (1, N) if transposed else (64, 1)
+    A.ops.linear_tc(Xc, rows, Wc, N, sn, sk, bc, Yc, N, accumulate=acc, batch=batch, sx=rows * 64, sw=64 * N,
+                    sb=N if bias else 0, sy=rows * N)
+    close(Yc, ref, 3e-6, 'linear_tc')
+    with pytest.raises(A.AcsrError, match='unsupported'):
+        A.LIB.call('acsr_linear_tc', Xc.data_ptr(), rows, 128, Wc.data_ptr(), N, 128, 1, None, 0, Yc.data_ptr(), N, 1, 0, 0, 0, 0, 3, None)
