@@ -33,7 +33,11 @@ class FusedTrainStep(object):
         self.buf = {}
         self.vp = None            # dist.VocabParallel when the logits are sharded over ranks
         # encoder GEMMs with K == 64 run on the tcgen05 linear kernel (3xTF32); other shapes stay library GEMMs
-        self.tc = bool(getattr(model, 'tc_linear', True)) and model.hidden_size == 64
+        self.tc = bool(getattr(model, 'tc_linear', False)) and model.hidden_size == 64
+        # weight-gradient reductions have no consumer before Adam: they run on a second stream (a parallel branch of
+        # the captured graph) and overlap the dependent chain of input-gradient kernels
+        self.overlap_wgrad = bool(getattr(model, 'overlap_wgrad', True))
+        self._side = None
 
     # ------------------------------------------------------------------------------------------
     def _buffers(self, B, L, dev):
@@ -57,12 +61,16 @@ class FusedTrainStep(object):
         b.update(out2=f(2 * B, d), partial=f(2 * B, nc, 2), lse=f(2 * B), tgt=f(2 * B), row_loss=f(2 * B), loss=f(2),
                  Gt=f(V, 2 * B), d_out2=f(2 * B, d), target2=torch.empty(2 * B, dtype=torch.int64, device=dev),
                  row_scale=torch.cat((torch.full((B,), 1.0 / B), torch.full((B,), -1.0 / B))).to(dev))
-        for n, w in (('d_out', d), ('d_z2', d), ('d_a1', I), ('d_z1', I), ('d_h', d), ('d_hz', d), ('d_x', d), ('d_ctx', d),
-                     ('d_gl', L)):
+        for n, w in (('d_out', d), ('d_a1', I), ('d_h', d), ('d_x', d), ('d_ctx', d)):
             b[n] = f(2 * T, w)
-        b['d_qkv'], b['d_aqk'] = f(3, 2 * T, d), f(2, 2 * T, d)
-        b['d_mq'], b['d_mk'], b['d_mv'] = b['d_qkv'][0], b['d_qkv'][1], b['d_qkv'][2]
-        b['d_aq'], b['d_ak'] = b['d_aqk'][0], b['d_aqk'][1]
+        # buffers read by the weight-gradient kernels are per layer: the side stream may still be reading layer l's
+        # while the main stream already writes layer l-1's
+        for lb in b['layers']:
+            for n, w in (('d_z2', d), ('d_z1', I), ('d_hz', d), ('d_gl', L)):
+                lb[n] = f(2 * T, w)
+            lb['d_qkv'], lb['d_aqk'] = f(3, 2 * T, d), f(2, 2 * T, d)
+            lb['d_mq'], lb['d_mk'], lb['d_mv'] = lb['d_qkv'][0], lb['d_qkv'][1], lb['d_qkv'][2]
+            lb['d_aq'], lb['d_ak'] = lb['d_aqk'][0], lb['d_aqk'][1]
         self.buf[key] = b
         return b
 
@@ -186,6 +194,17 @@ class FusedTrainStep(object):
             return loss_att, loss_cal
         # ---------------- backward ----------------
         dpen = (w / (2.0 * N)) / pen_norm                     # d loss_att / d pen_sq_l
+        main = torch.cuda.current_stream()
+        if self.overlap_wgrad and self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side if self.overlap_wgrad else None
+
+        def fork():
+            """-> stream handle for a weight-gradient launch: the side stream, ordered after everything enqueued so far"""
+            if side is None:
+                return st
+            side.wait_stream(main)
+            return side.cuda_stream
         opt.zero_grad()
         if self.vp is not None:       # shard-local G^T, reduce-scatter of d_out, dE into the owner's rows
             b['d_out2'].copy_(self.vp.ce_backward(vst, E, b['row_scale'], E.grad, table_half=0, n_groups=2))
@@ -194,7 +213,12 @@ class FusedTrainStep(object):
                      _p(b['row_scale']), 2 * B, V, d, passes, _p(b['Gt']), 2 * B, st)
             b['d_out2'].zero_()
             LIB.call('acsr_linear_wgrad', _p(b['Gt']), _p(E), V, 2 * B, d, _p(b['d_out2']), None, st)
-            E.grad.addmm_(b['Gt'][:, :B], b['out2'][:B])       # only the calibrated rows train the item table
+            if side is not None:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    E.grad.addmm_(b['Gt'][:, :B], b['out2'][:B])
+            else:
+                E.grad.addmm_(b['Gt'][:, :B], b['out2'][:B])       # only the calibrated rows train the item table
         d_out, d_x = b['d_out'], b['d_x']
         d_out.zero_()
         LIB.call('acsr_gather_last_bwd', _p(b['d_out2']), _p(ln, torch.int64), B, L, d, _p(d_out[:T]), _p(d_out[T:]), st)
@@ -211,29 +235,32 @@ class FusedTrainStep(object):
             # FFN
             LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_out), _p(lb['z2']), _p(ff.dense_2.bias), _p(lb['h']),
                      _p(ff.LayerNorm.weight), _p(lb['st_f']), T2, d, P, P, T, p_h, _p(lb['m_f']), rngp, base + 5,
-                     _p(b['d_z2']), _p(b['d_h']), _p(ff.dense_2.bias.grad), _p(ff.LayerNorm.weight.grad),
+                     _p(lb['d_z2']), _p(b['d_h']), _p(ff.dense_2.bias.grad), _p(ff.LayerNorm.weight.grad),
                      _p(ff.LayerNorm.bias.grad), st)
-            LIB.call('acsr_linear_wgrad', _p(b['d_z2']), _p(lb['a1']), T, d, I, _p(ff.dense_2.weight.grad), None, st)
+            sst = fork()
+            LIB.call('acsr_linear_wgrad', _p(lb['d_z2']), _p(lb['a1']), T, d, I, _p(ff.dense_2.weight.grad), None, sst)
             if self.tc:                                      # d_a1 = d_z2.W2 : Wt[i][c] = W2[c*I + i]
-                ops.linear_tc(b['d_z2'], T2, ff.dense_2.weight, I, 1, I, None, b['d_a1'], I)
+                ops.linear_tc(lb['d_z2'], T2, ff.dense_2.weight, I, 1, I, None, b['d_a1'], I)
             else:
-                torch.mm(b['d_z2'], ff.dense_2.weight, out=b['d_a1'])
-            LIB.call('acsr_bias_act_bwd', _p(b['d_a1']), _p(lb['z1']), _p(ff.dense_1.bias), T2, I, act_id, P, T, _p(b['d_z1']),
+                torch.mm(lb['d_z2'], ff.dense_2.weight, out=b['d_a1'])
+            LIB.call('acsr_bias_act_bwd', _p(b['d_a1']), _p(lb['z1']), _p(ff.dense_1.bias), T2, I, act_id, P, T, _p(lb['d_z1']),
                      _p(ff.dense_1.bias.grad), st)
-            LIB.call('acsr_linear_wgrad', _p(b['d_z1']), _p(lb['h']), T, I, d, _p(ff.dense_1.weight.grad), None, st)
-            b['d_h'].addmm_(b['d_z1'], ff.dense_1.weight)
+            sst = fork()
+            LIB.call('acsr_linear_wgrad', _p(lb['d_z1']), _p(lb['h']), T, I, d, _p(ff.dense_1.weight.grad), None, sst)
+            b['d_h'].addmm_(lb['d_z1'], ff.dense_1.weight)
             # attention output projection
             LIB.call('acsr_bias_dropout_res_ln_bwd', _p(b['d_h']), _p(lb['hz']), _p(aa.dense.bias), _p(x),
                      _p(aa.LayerNorm.weight), _p(lb['st_a']), T2, d, P, T, T, p_h, _p(lb['m_a']), rngp, base + 3,
-                     _p(b['d_hz']), _p(d_x), _p(aa.dense.bias.grad), _p(aa.LayerNorm.weight.grad), _p(aa.LayerNorm.bias.grad), st)
-            LIB.call('acsr_linear_wgrad', _p(b['d_hz']), _p(lb['ctx']), T, d, d, _p(aa.dense.weight.grad), None, st)
+                     _p(lb['d_hz']), _p(d_x), _p(aa.dense.bias.grad), _p(aa.LayerNorm.weight.grad), _p(aa.LayerNorm.bias.grad), st)
+            sst = fork()
+            LIB.call('acsr_linear_wgrad', _p(lb['d_hz']), _p(lb['ctx']), T, d, d, _p(aa.dense.weight.grad), None, sst)
             if self.tc:
-                ops.linear_tc(b['d_hz'], T2, aa.dense.weight, d, 1, d, None, b['d_ctx'], d)
+                ops.linear_tc(lb['d_hz'], T2, aa.dense.weight, d, 1, d, None, b['d_ctx'], d)
             else:
-                torch.mm(b['d_hz'], aa.dense.weight, out=b['d_ctx'])
+                torch.mm(lb['d_hz'], aa.dense.weight, out=b['d_ctx'])
             # fused attention backward, one launch per cotangent stream
             if gate:
-                b['d_gl'].zero_()
+                lb['d_gl'].zero_()
             g = lambda t: None if t is None else t.grad     # noqa: E731
             ow, ob_ = (aa.order_affine.weight, aa.order_affine.bias) if aa.use_order else (None, None)
             dw, db_, sc = (aa.distance_affine.weight, aa.distance_affine.bias, aa.scalar) if aa.use_distance else (None, None, None)
@@ -248,8 +275,8 @@ class FusedTrainStep(object):
                 d_pen = dpen[l:l + 1] if s == 1 else None
                 own = s == 0                                 # stream 0 owns the non-attack parameters
                 LIB.call('acsr_attn_calib_bwd', _p(d_att), _p(d_cal), _p(d_pen), *lb['attn_args'],
-                         _p(b['d_mq'][rows]), _p(b['d_mk'][rows]), _p(b['d_mv'][rows]), _p(b['d_aq'][rows]), _p(b['d_ak'][rows]),
-                         _p(b['d_gl'][rows]) if gate else None,
+                         _p(lb['d_mq'][rows]), _p(lb['d_mk'][rows]), _p(lb['d_mv'][rows]), _p(lb['d_aq'][rows]), _p(lb['d_ak'][rows]),
+                         _p(lb['d_gl'][rows]) if gate else None,
                          _p(g(ow)) if own else None, _p(g(ob_)) if own else None, _p(g(dw)) if own else None,
                          _p(g(db_)) if own else None, _p(g(sc)) if own else None, _p(g(rr)) if own else None, st)
             # projections: input gradients for both streams, weight gradients from the owning stream
@@ -257,41 +284,49 @@ class FusedTrainStep(object):
             st3 = self._stacked(l)
             if st3 is not None:
                 if self.tc:
-                    ops.linear_tc(b['d_aqk'], T2, st3['Waqk'], d, 1, d, None, b['d_qkv'], d, accumulate=True, batch=2,
+                    ops.linear_tc(lb['d_aqk'], T2, st3['Waqk'], d, 1, d, None, lb['d_qkv'], d, accumulate=True, batch=2,
                                   sx=T2 * d, sw=d * d, sb=0, sy=T2 * d)
                 else:
-                    b['d_qkv'][:2].baddbmm_(b['d_aqk'], st3['Waqk'])
+                    lb['d_qkv'][:2].baddbmm_(lb['d_aqk'], st3['Waqk'])
                 # attack transforms are trained by the attacked-loss stream (rows [T,2T))
-                LIB.call('acsr_linear_wgrad_batched', _p(b['d_aqk'][0, T:]), _p(lb['qkv'][0]), T, d, d, _p(st3['gWaqk']),
-                         _p(st3['gbaqk']), 2, T2 * d, T * d, d * d, d, st)
+                sst = fork()
+                LIB.call('acsr_linear_wgrad_batched', _p(lb['d_aqk'][0, T:]), _p(lb['qkv'][0]), T, d, d, _p(st3['gWaqk']),
+                         _p(st3['gbaqk']), 2, T2 * d, T * d, d * d, d, sst)
             else:
-                b['d_mq'].addmm_(b['d_aq'], aqt.weight)
-                b['d_mk'].addmm_(b['d_ak'], akt.weight)
-                LIB.call('acsr_linear_wgrad', _p(b['d_aq'][T:]), _p(lb['mq']), T, d, d, _p(aqt.weight.grad), _p(aqt.bias.grad), st)
-                LIB.call('acsr_linear_wgrad', _p(b['d_ak'][T:]), _p(lb['mk']), T, d, d, _p(akt.weight.grad), _p(akt.bias.grad), st)
+                lb['d_mq'].addmm_(lb['d_aq'], aqt.weight)
+                lb['d_mk'].addmm_(lb['d_ak'], akt.weight)
+                sst = fork()
+                LIB.call('acsr_linear_wgrad', _p(lb['d_aq'][T:]), _p(lb['mq']), T, d, d, _p(aqt.weight.grad), _p(aqt.bias.grad), sst)
+                sst = fork()
+                LIB.call('acsr_linear_wgrad', _p(lb['d_ak'][T:]), _p(lb['mk']), T, d, d, _p(akt.weight.grad), _p(akt.bias.grad), sst)
             if gate:
-                b['d_mq'].addmm_(b['d_gl'], layer.gate.weight)
-                LIB.call('acsr_linear_wgrad', _p(b['d_gl']), _p(lb['mq']), T, L, d, _p(layer.gate.weight.grad),
-                         _p(layer.gate.bias.grad), st)
+                lb['d_mq'].addmm_(lb['d_gl'], layer.gate.weight)
+                sst = fork()
+                LIB.call('acsr_linear_wgrad', _p(lb['d_gl']), _p(lb['mq']), T, L, d, _p(layer.gate.weight.grad),
+                         _p(layer.gate.bias.grad), sst)
             if st3 is not None:
-                LIB.call('acsr_linear_wgrad_batched', _p(b['d_qkv'][0]), _p(x), T, d, d, _p(st3['gWqkv']), _p(st3['gbqkv']), 3,
-                         T2 * d, 0, d * d, d, st)
+                sst = fork()
+                LIB.call('acsr_linear_wgrad_batched', _p(lb['d_qkv'][0]), _p(x), T, d, d, _p(st3['gWqkv']), _p(st3['gbqkv']), 3,
+                         T2 * d, 0, d * d, d, sst)
             else:
                 for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
-                    LIB.call('acsr_linear_wgrad', _p(b[dk]), _p(x), T, d, d, _p(lin.weight.grad), _p(lin.bias.grad), st)
+                    sst = fork()
+                    LIB.call('acsr_linear_wgrad', _p(lb[dk]), _p(x), T, d, d, _p(lin.weight.grad), _p(lin.bias.grad), sst)
             if l > 0:
                 for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
                     if self.tc:
-                        ops.linear_tc(b[dk], T2, lin.weight, d, 1, d, None, d_x, d, accumulate=True)
+                        ops.linear_tc(lb[dk], T2, lin.weight, d, 1, d, None, d_x, d, accumulate=True)
                     else:
-                        d_x.addmm_(b[dk], lin.weight)
+                        d_x.addmm_(lb[dk], lin.weight)
                 d_out, d_x = d_x, d_out                       # this layer's input gradient is the next one's output gradient
             else:
                 for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
                     if self.tc:                               # below the first layer only the calibrated stream trains anything
-                        ops.linear_tc(b[dk], T, lin.weight, d, 1, d, None, d_x, d, accumulate=True)
+                        ops.linear_tc(lb[dk], T, lin.weight, d, 1, d, None, d_x, d, accumulate=True)
                     else:
-                        d_x[:T].addmm_(b[dk][:T], lin.weight)
+                        d_x[:T].addmm_(lb[dk][:T], lin.weight)
+        if side is not None:
+            main.wait_stream(side)                            # join: every weight gradient landed (dE is shared with K1 bwd)
         LIB.call('acsr_embed_ln_dropout_bwd', _p(d_x[:T]), _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight),
                  _p(b['st_e']), T, L, d, V, p_h, _p(me), rngp, 1, _p(E.grad), _p(posw.grad if posw is not None else None),
                  _p(m.LayerNorm.weight.grad), _p(m.LayerNorm.bias.grad), st)

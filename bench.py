@@ -250,6 +250,8 @@ def run_ours(args):
     kt_steps = min(K, 20)
     timer = A._lib.KernelTimer()
     A.LIB.timer = timer
+    if trainer.fused is not None:
+        trainer.fused.overlap_wgrad = False       # per-kernel events are recorded on the launching (main) stream
     torch.cuda.synchronize()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -258,6 +260,8 @@ def run_ours(args):
     t1.record()
     ksum = timer.summary()
     A.LIB.timer = None
+    if trainer.fused is not None:
+        trainer.fused.overlap_wgrad = True
     eager_ms = t0.elapsed_time(t1) / kt_steps
     launches_per_step = timer.launches / kt_steps + 1                   # adam_step enqueues two kernels
     n_param = trainer.optimizer.flat_param.numel()
