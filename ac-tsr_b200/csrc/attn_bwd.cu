@@ -1,0 +1,545 @@
+// Fused calibrated causal attention, backward (see attn_common.cuh for the design).
+//
+// The backward recomputes a row's probabilities once (same tiles, same Philox counters) and then
+// runs the (linear) backward chain for up to TWO cotangent streams -- the reference's two backward()
+// traversals, trainer.py:672-684 -- finishing the row-side gradients (dQ, dQ') from per-group row
+// buffers.  dS, dS' (per stream) and R, A are kept TRANSPOSED in shared memory, packed lower
+// triangular, and the column-side gradients (dK, dK', dV) are finished in a second, column-parallel
+// phase with float4 broadcast reads.  A row whose cotangents are exactly zero (most rows of the
+// calibrated-loss stream: only position len-1 feeds the loss) skips the chain.
+#include "attn_common.cuh"
+
+namespace acsr {
+
+template <int NS>
+struct BwdSmem {
+  float *sT0, *sT1;                  // cotangent tiles [LP][dh+4]
+  float *matST[NS], *matS2T[NS];     // dS^T, dS'^T  [j][i] packed lower triangular
+  float *matRT, *matAT;              // R_final^T, A^T
+  float *rowbuf;                     // per warp: dS / dS' rows of every stream, per row group
+  float *colDU, *colDT;              // [NS][LP]
+  float *pacc;                       // [4*dh] CTA partials of d_ow / d_dw
+  float *red;                        // [warps][4]
+};
+
+struct BwdAcc {                      // lane partials of the scalar parameter gradients (stream 0)
+  float s_ob, s_db, s_scalar, s_ratio;
+};
+
+struct BwdFlags {
+  bool has_t0, has_t1, t1_att, has_att, gate;
+  float sc2;
+};
+
+// one row group iteration: recompute row i, run the chain of every stream, finish dq_i, dq'_i
+template <int DH, int G, int NJ, int NS>
+__device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem& sm, const BwdSmem<NS>& bs, const RowConst& kc,
+                                             const BwdFlags& f, const float* dpen, int b, int h, int i, bool rowok, int bound,
+                                             int grp, int sub, int rstride, float* wbuf, BwdAcc& acc, float* accOq,
+                                             float* accDq) {
+  constexpr int dhp = DH + 4;
+  using CM = CMap<DH, G>;
+  const int L = p.L, LP = (L + 3) & ~3;
+  RowF<NJ> r;
+  row_forward<DH, G, NJ>(p, sm, kc, b, h, i, bound, sub, f.has_att, r);
+  const unsigned act = r.act;
+  // cotangent dots with the value rows: d0_j = t0_i . v_j ; d1_j = t1_i . v_j
+  float d0[NJ], d1[NJ];
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) d0[jj] = d1[jj] = 0.f;
+  if (f.has_t0 || f.has_t1) {
+    const float4* a0 = reinterpret_cast<const float4*>(bs.sT0 + i * dhp);
+    const float4* a1 = reinterpret_cast<const float4*>(bs.sT1 + i * dhp);
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int jcl = ((act >> jj) & 1u) ? sub + G * jj : 0;
+      const float4* vj = reinterpret_cast<const float4*>(sm.V + jcl * dhp);
+      float x0 = 0.f, x1 = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < DH / 4; ++c4) {
+        const float4 v = vj[c4];
+        if (f.has_t0) x0 = dot4(a0[c4], v, x0);
+        if (f.has_t1) x1 = dot4(a1[c4], v, x1);
+      }
+      if ((act >> jj) & 1u) { d0[jj] = x0; d1[jj] = x1; }
+    }
+  }
+  // forward quantities shared by the streams
+  float Pj[NJ], Mj[NJ], Oj[NJ], expm[NJ];
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const bool a = (act >> jj) & 1u;
+    Pj[jj] = r.Psoft[jj] * r.D1[jj];
+    Mj[jj] = r.Msoft[jj] * r.D3[jj];
+    Oj[jj] = p.two_level ? Pj[jj] : r.P0soft[jj] * r.D2[jj];
+    expm[jj] = a ? fexp(1.0f - Mj[jj]) : 0.f;
+    if (a && rowok) {
+      const int j = sub + G * jj;
+      const int t = tri_off(j, LP) - (j & ~3) + i;
+      bs.matRT[t] = p.two_level ? r.R[jj] : (kc.rr * r.R[jj] + (1.0f - kc.rr) * Pj[jj]);
+      bs.matAT[t] = r.A[jj];
+    }
+  }
+  float* gbuf = wbuf + grp * 2 * NS * rstride;     // [s][2][rstride]
+  bool live[NS];
+  float row_du[NS], row_dt[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    float* bufS = gbuf + (2 * s + 0) * rstride;
+    float* bufS2 = gbuf + (2 * s + 1) * rstride;
+    row_du[s] = row_dt[s] = 0.f;
+    // which cotangents feed this stream
+    const float* dRf = (NS == 1 || s == 0) ? d0 : d1;
+    const float* dA = d1;
+    bool useR = (NS == 1 || s == 0) ? f.has_t0 : (f.has_t1 && !f.t1_att);
+    bool useA = (NS == 1) ? f.has_t1 : (s == 1 && f.has_t1 && f.t1_att);
+    bool nzR = false, nzA = false;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) { nzR |= dRf[jj] != 0.f; nzA |= dA[jj] != 0.f; }
+    useR = useR && __any_sync(kFull, nzR && rowok);       // exact-zero cotangent rows skip the chain (warp-uniform)
+    useA = useA && __any_sync(kFull, nzA && rowok);
+    const float dp = dpen[s];
+    live[s] = useR || useA || dp != 0.f;
+    if (!live[s]) continue;
+    const bool owner = s == 0;
+    float dO[NJ], dP[NJ], dM[NJ], tmp[NJ];
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) { dO[jj] = 0.f; dP[jj] = 0.f; dM[jj] = 0.f; }
+    if (useR) {
+      float dR[NJ], dcm[NJ], dC[NJ];
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) {
+        if (p.two_level) dR[jj] = dRf[jj];
+        else {
+          dR[jj] = dRf[jj] * kc.rr;
+          dP[jj] = dRf[jj] * (1.0f - kc.rr);
+          if (owner && rowok) acc.s_ratio += dRf[jj] * (r.R[jj] - Pj[jj]);
+        }
+      }
+      softmax_bwd_row<G, NJ>(r.R, dR, dcm);            // grad wrt (comb + mask)
+      if (p.combine == ACSR_ATTN_COMBINE_FIXED) {
+        softmax_bwd_row<G, NJ>(r.F, dcm, tmp);          // grad wrt (O + 0.5 C); columns outside the range carry no cotangent
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) { dO[jj] += tmp[jj]; dC[jj] = 0.5f * tmp[jj]; }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+          const float g = r.g[jj];
+          dO[jj] += dcm[jj] * g;
+          dC[jj] = dcm[jj] * (1.0f - g);
+          if (f.gate && ((act >> jj) & 1u) && rowok) {
+            const float dgl = dcm[jj] * (Oj[jj] - r.C[jj]) * g * (1.0f - g);
+            if (dgl != 0.f) atomicAdd(p.d_gate + s * p.s1_ll + ((long long)b * L + i) * L + sub + G * jj, dgl);
+          }
+        }
+      }
+      softmax_bwd_row<G, NJ>(r.C, dC, tmp);             // grad wrt (O*expm + mask)
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) {
+        dO[jj] += tmp[jj] * expm[jj];
+        dM[jj] -= tmp[jj] * Oj[jj] * expm[jj];
+      }
+    }
+    if (useA) {
+      softmax_bwd_row<G, NJ>(r.A, dA, tmp);             // grad wrt (O*M + n(1-M) + mask)
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) {
+        dO[jj] += tmp[jj] * Mj[jj];
+        dM[jj] += tmp[jj] * (Oj[jj] - r.nz[jj]);
+      }
+    }
+    float dS2[NJ], dS[NJ], dz[NJ];
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      if ((act >> jj) & 1u) dM[jj] += dp * (-2.0f) * (1.0f - Mj[jj]);
+      dM[jj] *= r.D3[jj];
+    }
+    softmax_bwd_row<G, NJ>(r.Msoft, dM, dS2);
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) { dS2[jj] *= kc.inv_sq; dz[jj] = 0.f; dS[jj] = 0.f; }
+    if (useR || useA) {
+      float dP0[NJ];
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) {
+        if (p.two_level) { dP[jj] += dO[jj]; dP0[jj] = 0.f; }
+        else dP0[jj] = dO[jj] * r.D2[jj];
+        dP[jj] *= r.D1[jj];
+      }
+      softmax_bwd_row<G, NJ>(r.Psoft, dP, dz);
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) { dz[jj] *= kc.inv_sq; dS[jj] = dz[jj]; }
+      if (!p.two_level) {
+        softmax_bwd_row<G, NJ>(r.P0soft, dP0, tmp);
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) dS[jj] += tmp[jj] * kc.inv_sq;
+      }
+    }
+    float rdu = 0.f, rdt = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = sub + G * jj;
+      const bool a = ((act >> jj) & 1u) && rowok;       // columns outside the range are exactly zero
+      if (j < rstride) { bufS[j] = a ? dS[jj] : 0.f; bufS2[j] = a ? dS2[jj] : 0.f; }
+      if (!a) continue;
+      if (p.ow) {
+        const float sg = r.sig[jj];
+        const float de = -sg * (1.0f - sg) * frcp((1.0f - sg) + kOrderEps);     // j <= i branch of layers.py:719
+        const float du = dz[jj] * de;
+        rdu += du;
+        if (du != 0.f) atomicAdd(bs.colDU + s * LP + j, du);
+      }
+      if (p.dw) {
+        const float dl = r.delta[jj];
+        const float dt = dz[jj] * dl * f.sc2;
+        rdt += dt;
+        if (dt != 0.f) atomicAdd(bs.colDT + s * LP + j, dt);
+        if (owner) acc.s_scalar += dz[jj] * (-(dl * dl) * kc.sc);
+      }
+      const int t = tri_off(j, LP) - (j & ~3) + i;
+      bs.matST[s][t] = dS[jj];
+      bs.matS2T[s][t] = dS2[jj];
+    }
+    row_du[s] = grp_sum<G>(rdu);
+    row_dt[s] = grp_sum<G>(rdt);
+  }
+  if (sub == 0) { acc.s_ob += row_du[0]; acc.s_db += row_dt[0]; }
+  __syncwarp();
+  // row-side gradients: dq_i, dq'_i of every stream (lane = channel, j < bound; float4 broadcast of the row buffers)
+  float aq_[NS][CM::CPL], aq2_[NS][CM::CPL];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int k = 0; k < CM::CPL; ++k) aq_[s][k] = aq2_[s][k] = 0.f;
+  int lo, hi;
+  CM::slice(sub, 0, (bound + 3) & ~3, lo, hi);
+  const int c0 = CM::c0(sub);
+  bool any_live = false;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) any_live |= live[s];
+  if (any_live) {
+    for (int j = lo; j < hi; j += 4) {
+      float s1v[NS][4], s2v[NS][4];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float4 s1 = *reinterpret_cast<const float4*>(gbuf + (2 * s + 0) * rstride + j);
+        const float4 s2 = *reinterpret_cast<const float4*>(gbuf + (2 * s + 1) * rstride + j);
+        s1v[s][0] = s1.x; s1v[s][1] = s1.y; s1v[s][2] = s1.z; s1v[s][3] = s1.w;
+        s2v[s][0] = s2.x; s2v[s][1] = s2.y; s2v[s][2] = s2.z; s2v[s][3] = s2.w;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float kv[CM::CPL], k2v[CM::CPL];
+        VecLd<CM::CPL>::ld(sm.K + (j + u) * dhp + c0, kv);
+        VecLd<CM::CPL>::ld(sm.K2 + (j + u) * dhp + c0, k2v);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          if (!live[s]) continue;
+#pragma unroll
+          for (int k = 0; k < CM::CPL; ++k) {
+            aq_[s][k] = fmaf(s1v[s][u], kv[k], aq_[s][k]);
+            aq2_[s][k] = fmaf(s2v[s][u], k2v[k], aq2_[s][k]);
+          }
+        }
+      }
+    }
+  }
+  {
+    float qv[CM::CPL];
+    VecLd<CM::CPL>::ld(sm.Q + i * dhp + c0, qv);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      float o1[CM::CPL], o2[CM::CPL];
+#pragma unroll
+      for (int k = 0; k < CM::CPL; ++k) {
+        o1[k] = CM::reduce(aq_[s][k]) + row_du[s] * sm.wo[c0 + k] + row_dt[s] * sm.wd[c0 + k];
+        o2[k] = CM::reduce(aq2_[s][k]);
+      }
+      if (CM::split(sub) == 0 && rowok) {
+        const long long o = s * p.s1_td + ((long long)b * L + i) * p.d + h * DH + c0;
+        VecLd<CM::CPL>::st(p.d_mq + o, o1);
+        VecLd<CM::CPL>::st(p.d_aq + o, o2);
+      }
+    }
+    if (CM::split(sub) == 0 && rowok) {
+#pragma unroll
+      for (int k = 0; k < CM::CPL; ++k) { accOq[k] = fmaf(row_du[0], qv[k], accOq[k]); accDq[k] = fmaf(row_dt[0], qv[k], accDq[k]); }
+    }
+  }
+  __syncwarp();
+}
+
+// row phase + column phase of the (b,h) tile with G-lane groups
+template <int DH, int G, int MAXNJ, int NS>
+__device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm, const BwdSmem<NS>& bs, const RowConst& kc,
+                                         const BwdFlags& f, const float* dpen, int b, int h, int nkey, int rstride, BwdAcc& acc) {
+  constexpr int dhp = DH + 4;
+  constexpr int RPW = 32 / G;
+  using CM = CMap<DH, G>;
+  const int L = p.L, LP = (L + 3) & ~3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / G, sub = lane % G;
+  const int c0 = CM::c0(sub);
+  float* wbuf = bs.rowbuf + warp * rowbuf_floats_per_warp(LP, 2 * NS);
+  float accOq[CM::CPL], accDq[CM::CPL], accOk[CM::CPL], accDk[CM::CPL];
+#pragma unroll
+  for (int k = 0; k < CM::CPL; ++k) accOq[k] = accDq[k] = accOk[k] = accDk[k] = 0.f;
+  for (int t0 = warp * RPW; t0 < L; t0 += kAttnWarps * RPW) {      // heaviest rows first
+    const int iw = L - 1 - t0;
+    const int iraw = iw - grp;
+    const bool rowok = iraw >= 0;
+    const int i = rowok ? iraw : 0;
+    const int bound = min(i + 1, nkey);
+    const int nj = (min(iw + 1, nkey) + G - 1) / G;
+#define ACSR_BWD_ROW(NJV) \
+  bwd_row_iter<DH, G, NJV, NS>(p, sm, bs, kc, f, dpen, b, h, i, rowok, bound, grp, sub, rstride, wbuf, acc, accOq, accDq)
+    if (MAXNJ == 1 || nj == 1) ACSR_BWD_ROW(1);
+    else if (nj == 2) ACSR_BWD_ROW((MAXNJ >= 2 ? 2 : 1));
+    else if (nj == 3) ACSR_BWD_ROW((MAXNJ >= 3 ? 3 : 1));
+    else ACSR_BWD_ROW((MAXNJ >= 4 ? 4 : 1));
+#undef ACSR_BWD_ROW
+  }
+  __syncthreads();
+  // column-side gradients: dk_j, dk'_j, dv_j  (group per column, lane = channel, rows i >= j)
+  for (int t0 = warp * RPW; t0 < nkey; t0 += kAttnWarps * RPW) {    // heaviest columns (small j) first
+    const int jraw = t0 + grp;
+    const bool colok = jraw < nkey;
+    const int j = colok ? jraw : 0;
+    float ak_[NS][CM::CPL], ak2_[NS][CM::CPL], av_[NS][CM::CPL];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int k = 0; k < CM::CPL; ++k) ak_[s][k] = ak2_[s][k] = av_[s][k] = 0.f;
+    int lo, hi;
+    CM::slice(sub, j & ~3, LP, lo, hi);
+    const int off = tri_off(j, LP) - (j & ~3);
+    for (int i = lo; i < hi; i += 4) {
+      float s1v[NS][4], s2v[NS][4];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float4 s1 = *reinterpret_cast<const float4*>(bs.matST[s] + off + i);
+        const float4 s2 = *reinterpret_cast<const float4*>(bs.matS2T[s] + off + i);
+        s1v[s][0] = s1.x; s1v[s][1] = s1.y; s1v[s][2] = s1.z; s1v[s][3] = s1.w;
+        s2v[s][0] = s2.x; s2v[s][1] = s2.y; s2v[s][2] = s2.z; s2v[s][3] = s2.w;
+      }
+      const float4 pr = *reinterpret_cast<const float4*>(bs.matRT + off + i);
+      const float4 pa = *reinterpret_cast<const float4*>(bs.matAT + off + i);
+      const float prv[4] = {pr.x, pr.y, pr.z, pr.w}, pav[4] = {pa.x, pa.y, pa.z, pa.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float qv[CM::CPL], q2v[CM::CPL], t0v[CM::CPL], t1v[CM::CPL];
+        VecLd<CM::CPL>::ld(sm.Q + (i + u) * dhp + c0, qv);
+        VecLd<CM::CPL>::ld(sm.Q2 + (i + u) * dhp + c0, q2v);
+        VecLd<CM::CPL>::ld(bs.sT0 + (i + u) * dhp + c0, t0v);
+        VecLd<CM::CPL>::ld(bs.sT1 + (i + u) * dhp + c0, t1v);
+#pragma unroll
+        for (int k = 0; k < CM::CPL; ++k) {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            ak_[s][k] = fmaf(s1v[s][u], qv[k], ak_[s][k]);
+            ak2_[s][k] = fmaf(s2v[s][u], q2v[k], ak2_[s][k]);
+          }
+          av_[0][k] = fmaf(prv[u], t0v[k], av_[0][k]);
+          av_[NS - 1][k] = fmaf(f.t1_att ? pav[u] : prv[u], t1v[k], av_[NS - 1][k]);
+        }
+      }
+    }
+    float kv[CM::CPL];
+    VecLd<CM::CPL>::ld(sm.K + j * dhp + c0, kv);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float cdu = bs.colDU[s * LP + j], cdt = bs.colDT[s * LP + j];
+      float o1[CM::CPL], o2[CM::CPL], o3[CM::CPL];
+#pragma unroll
+      for (int k = 0; k < CM::CPL; ++k) {
+        o1[k] = CM::reduce(ak_[s][k]) + cdu * sm.wo[DH + c0 + k] + cdt * sm.wd[DH + c0 + k];
+        o2[k] = CM::reduce(ak2_[s][k]);
+        o3[k] = CM::reduce(av_[s][k]);
+      }
+      if (CM::split(sub) == 0 && colok) {
+        const long long o = s * p.s1_td + ((long long)b * L + j) * p.d + h * DH + c0;
+        VecLd<CM::CPL>::st(p.d_mk + o, o1);
+        VecLd<CM::CPL>::st(p.d_ak + o, o2);
+        VecLd<CM::CPL>::st(p.d_mv + o, o3);
+        if (s == 0) {
+#pragma unroll
+          for (int k = 0; k < CM::CPL; ++k) { accOk[k] = fmaf(cdu, kv[k], accOk[k]); accDk[k] = fmaf(cdt, kv[k], accDk[k]); }
+        }
+      }
+    }
+  }
+  // lane partials of d_ow / d_dw -> CTA partials in smem
+  if ((p.d_ow || p.d_dw) && CM::split(sub) == 0) {
+#pragma unroll
+    for (int k = 0; k < CM::CPL; ++k) {
+      const int c = c0 + k;
+      if (accOq[k] != 0.f) atomicAdd(bs.pacc + c, accOq[k]);
+      if (accOk[k] != 0.f) atomicAdd(bs.pacc + DH + c, accOk[k]);
+      if (accDq[k] != 0.f) atomicAdd(bs.pacc + 2 * DH + c, accDq[k]);
+      if (accDk[k] != 0.f) atomicAdd(bs.pacc + 3 * DH + c, accDk[k]);
+    }
+  }
+}
+
+template <int DH, int NS>
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) float smem_f[];
+  constexpr int dhp = DH + 4;
+  const int L = p.L, LP = (L + 3) & ~3;
+  const int TRI = tri_off(L, LP);
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ptr = smem_f;
+  AttnSmem sm = carve_common(ptr, LP, DH);
+  BwdSmem<NS> bs;
+  bs.sT0 = ptr; ptr += LP * dhp;
+  bs.sT1 = ptr; ptr += LP * dhp;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) { bs.matST[s] = ptr; ptr += TRI; bs.matS2T[s] = ptr; ptr += TRI; }
+  bs.matRT = ptr; ptr += TRI;
+  bs.matAT = ptr; ptr += TRI;
+  bs.rowbuf = ptr; ptr += kAttnWarps * rowbuf_floats_per_warp(LP, 2 * NS);
+  bs.colDU = ptr; ptr += NS * LP;
+  bs.colDT = ptr; ptr += NS * LP;
+  bs.pacc = ptr; ptr += 4 * DH;
+  bs.red = ptr; ptr += kAttnWarps * 4;
+  BwdFlags f;
+  f.has_t0 = p.t0 != nullptr; f.has_t1 = p.t1 != nullptr;
+  f.t1_att = NS == 1 ? true : (p.t1_is_att != 0);
+  f.has_att = f.has_t1 && f.t1_att;          // the attacked probabilities A are needed
+  f.gate = p.combine == ACSR_ATTN_COMBINE_GATE;
+
+  stage_tile<DH>(bs.sT0, p.t0, b, h, L, p.d, L, LP);
+  stage_tile<DH>(bs.sT1, p.t1, b, h, L, p.d, L, LP);
+  {
+    const int ntri = (2 * NS + 2) * TRI;       // the packed matrices are contiguous
+    float4* z4 = reinterpret_cast<float4*>(bs.matST[0]);
+    for (int e = threadIdx.x; e < ntri / 4; e += blockDim.x) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int j = threadIdx.x; j < NS * LP; j += blockDim.x) { bs.colDU[j] = 0.f; bs.colDT[j] = 0.f; }
+  for (int j = threadIdx.x; j < 4 * DH; j += blockDim.x) bs.pacc[j] = 0.f;
+  const int nkey = stage_common<DH>(p, sm, b, h, LP);     // waits for all cp.async groups, ends with __syncthreads()
+
+  const RowConst kc = make_consts<DH>(p, f.has_att);
+  f.sc2 = kc.sc * kc.sc;
+  float dpen[NS];
+  dpen[0] = p.d_pen0 ? p.d_pen0[0] : 0.f;
+  if (NS == 2) dpen[NS - 1] = p.d_pen1 ? p.d_pen1[0] : 0.f;
+  BwdAcc acc;
+  acc.s_ob = acc.s_db = acc.s_scalar = acc.s_ratio = 0.f;
+
+  if (nkey <= 8) bwd_body<DH, 8, 1, NS>(p, sm, bs, kc, f, dpen, b, h, nkey, 8, acc);
+  else bwd_body<DH, 16, 4, NS>(p, sm, bs, kc, f, dpen, b, h, nkey, LP, acc);
+
+  // key positions behind the last real item receive no gradient
+  for (int e = threadIdx.x; e < (L - nkey) * (DH / 4); e += blockDim.x) {
+    const int j = nkey + e / (DH / 4), c4 = e % (DH / 4);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const long long o = s * p.s1_td + ((long long)b * L + j) * p.d + h * DH + c4 * 4;
+      *reinterpret_cast<float4*>(p.d_mk + o) = z;
+      *reinterpret_cast<float4*>(p.d_ak + o) = z;
+      *reinterpret_cast<float4*>(p.d_mv + o) = z;
+    }
+  }
+  // parameter gradients (stream 0 owns them): one atomic per address per CTA
+  const float s_ob = warp_sum(acc.s_ob), s_db = warp_sum(acc.s_db);
+  const float s_scalar = warp_sum(acc.s_scalar), s_ratio = warp_sum(acc.s_ratio);
+  if (lane == 0) {
+    bs.red[warp * 4 + 0] = s_ob; bs.red[warp * 4 + 1] = s_db; bs.red[warp * 4 + 2] = s_scalar; bs.red[warp * 4 + 3] = s_ratio;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    for (int w = 0; w < kAttnWarps; ++w) s += bs.red[w * 4 + threadIdx.x];
+    float* dst = threadIdx.x == 0 ? p.d_ob : threadIdx.x == 1 ? p.d_db : threadIdx.x == 2 ? p.d_scalar : p.d_ratio;
+    if (dst != nullptr && s != 0.f) atomicAdd(dst, s);
+  }
+  for (int c = threadIdx.x; c < 4 * DH; c += blockDim.x) {
+    const float v = bs.pacc[c];
+    float* dst = c < 2 * DH ? p.d_ow : p.d_dw;
+    if (dst != nullptr && v != 0.f) atomicAdd(dst + (c < 2 * DH ? c : c - 2 * DH), v);
+  }
+}
+
+static size_t bwd_smem_bytes(int L, int dh, int ns) {
+  const int LP = (L + 3) & ~3;
+  size_t f = common_floats(LP, dh) + (size_t)2 * LP * (dh + 4) + (size_t)(2 * ns + 2) * tri_off(L, LP) +
+             (size_t)kAttnWarps * rowbuf_floats_per_warp(LP, 2 * ns) + 2 * ns * LP + 4 * dh + kAttnWarps * 4;
+  return f * sizeof(float);
+}
+
+template <int DH, int NS>
+static int launch_bwd(const AttnParams& p, cudaStream_t st) {
+  size_t smem = bwd_smem_bytes(p.L, DH, NS);
+  int rc = prep_kernel(attn_bwd_kernel<DH, NS>, smem, "attn_calib_bwd");
+  if (rc) return rc;
+  attn_bwd_kernel<DH, NS><<<p.B * p.H, kAttnThreads, smem, st>>>(p);
+  return check_launch("attn_calib_bwd");
+}
+
+template <int NS>
+static int dispatch_bwd(const AttnParams& p, cudaStream_t st) {
+  switch (p.dh) {
+    case 8: return launch_bwd<8, NS>(p, st);
+    case 16: return launch_bwd<16, NS>(p, st);
+    case 32: return launch_bwd<32, NS>(p, st);
+    case 64: return launch_bwd<64, NS>(p, st);
+  }
+  return ACSR_ERR_UNSUPPORTED;
+}
+
+}  // namespace acsr
+
+using namespace acsr;
+
+extern "C" {
+
+int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const float* d_pen_sq, const float* mq, const float* mk,
+                        const float* mv, const float* aq, const float* ak, const float* gate_logit, const int64_t* item_seq,
+                        const float* order_w, const float* order_b, const float* dist_w, const float* dist_b, const float* scalar,
+                        int B, int L, int H, int dh, int two_level, int combine_option, float comb_scalar, int rich_mode,
+                        const float* rich_ratio, float p_attn, const float* D1, const float* D2, const float* D3,
+                        const float* noise, const void* rng, uint32_t rng_stream, float* d_mq, float* d_mk, float* d_mv,
+                        float* d_aq, float* d_ak, float* d_gate_logit, float* d_order_w, float* d_order_b, float* d_dist_w,
+                        float* d_dist_b, float* d_scalar, float* d_rich_ratio, void* stream) {
+  AttnParams p = {};
+  attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream);
+  p.t0 = d_ctx_cal; p.t1 = d_ctx_att; p.t1_is_att = 1; p.d_pen0 = d_pen_sq;
+  p.d_mq = d_mq; p.d_mk = d_mk; p.d_mv = d_mv; p.d_aq = d_aq; p.d_ak = d_ak; p.d_gate = d_gate_logit;
+  p.d_ow = d_order_w; p.d_ob = d_order_b; p.d_dw = d_dist_w; p.d_db = d_dist_b; p.d_scalar = d_scalar; p.d_ratio = d_rich_ratio;
+  int rc = attn_validate(p, "attn_calib_bwd");
+  if (rc) return rc;
+  ACSR_REQUIRE(d_mq && d_mk && d_mv && d_aq && d_ak, "attn_calib_bwd: NULL output");
+  ACSR_REQUIRE(combine_option != ACSR_ATTN_COMBINE_GATE || d_gate_logit != nullptr, "attn_calib_bwd: d_gate_logit is NULL");
+  // d_order_*, d_dist_*, d_scalar, d_rich_ratio may be NULL: that cotangent stream does not own those parameters
+  return dispatch_bwd<1>(p, (cudaStream_t)stream);
+}
+
+int acsr_attn_calib_bwd2(const float* d_ctx_cal0, const float* d_pen_sq0, const float* d_ctx_att1, const float* d_ctx_cal1,
+                         const float* d_pen_sq1, const float* mq, const float* mk, const float* mv, const float* aq,
+                         const float* ak, const float* gate_logit, const int64_t* item_seq, const float* order_w,
+                         const float* order_b, const float* dist_w, const float* dist_b, const float* scalar, int B, int L, int H,
+                         int dh, int two_level, int combine_option, float comb_scalar, int rich_mode, const float* rich_ratio,
+                         float p_attn, const float* D1, const float* D2, const float* D3, const float* noise, const void* rng,
+                         uint32_t rng_stream, float* d_mq, float* d_mk, float* d_mv, float* d_aq, float* d_ak,
+                         float* d_gate_logit, float* d_order_w, float* d_order_b, float* d_dist_w, float* d_dist_b,
+                         float* d_scalar, float* d_rich_ratio, void* stream) {
+  AttnParams p = {};
+  attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream);
+  ACSR_REQUIRE(!(d_ctx_att1 && d_ctx_cal1), "attn_calib_bwd2: stream 1 takes d_ctx_att or d_ctx_cal, not both");
+  p.t0 = d_ctx_cal0; p.t1 = d_ctx_att1 ? d_ctx_att1 : d_ctx_cal1; p.t1_is_att = d_ctx_att1 != nullptr;
+  p.d_pen0 = d_pen_sq0; p.d_pen1 = d_pen_sq1;
+  p.s1_td = (long long)B * L * H * dh; p.s1_ll = (long long)B * L * L;
+  p.d_mq = d_mq; p.d_mk = d_mk; p.d_mv = d_mv; p.d_aq = d_aq; p.d_ak = d_ak; p.d_gate = d_gate_logit;
+  p.d_ow = d_order_w; p.d_ob = d_order_b; p.d_dw = d_dist_w; p.d_db = d_dist_b; p.d_scalar = d_scalar; p.d_ratio = d_rich_ratio;
+  int rc = attn_validate(p, "attn_calib_bwd2");
+  if (rc) return rc;
+  ACSR_REQUIRE(d_mq && d_mk && d_mv && d_aq && d_ak, "attn_calib_bwd2: NULL output");
+  ACSR_REQUIRE(combine_option != ACSR_ATTN_COMBINE_GATE || d_gate_logit != nullptr, "attn_calib_bwd2: d_gate_logit is NULL");
+  return dispatch_bwd<2>(p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// Fused calibrated causal attention, forward (see attn_common.cuh for the design).
+// Replaces layers.py:657-674, 686-742, 883-896, 917-936 and the probs.V of 676-678.
+#include "attn_common.cuh"
+
+namespace acsr {
+
+struct FwdCtx {
+  float* rowbuf;     // this warp's row buffers
+  float pen;
+};
+
+// one row group iteration: probabilities of row i, penalty, probs.V
+template <int DH, int G, int NJ>
+__device__ __forceinline__ void fwd_row_iter(const AttnParams& p, const AttnSmem& sm, const RowConst& kc, int b, int h, int i,
+                                             bool rowok, int bound, int grp, int sub, bool need_att, int rstride, FwdCtx& cx) {
+  constexpr int dhp = DH + 4;
+  using CM = CMap<DH, G>;
+  const int L = p.L;
+  RowF<NJ> r;
+  row_forward<DH, G, NJ>(p, sm, kc, b, h, i, bound, sub, need_att, r);
+  float* bufR = cx.rowbuf + (grp * 2 + 0) * rstride;
+  float* bufA = cx.rowbuf + (grp * 2 + 1) * rstride;
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const int j = sub + G * jj;
+    const bool a = (r.act >> jj) & 1u;
+    const float Pj = r.Psoft[jj] * r.D1[jj];
+    const float Rf = p.two_level ? r.R[jj] : (kc.rr * r.R[jj] + (1.0f - kc.rr) * Pj);
+    const float Mj = r.Msoft[jj] * r.D3[jj];
+    if (j < rstride) {                            // entries outside the row's range are written as 0
+      bufR[j] = a ? Rf : 0.f;
+      bufA[j] = a ? r.A[jj] : 0.f;
+    }
+    if (a && rowok) { const float om = 1.0f - Mj; cx.pen = fmaf(om, om, cx.pen); }
+    if (p.probs && a && rowok) {
+      const long long e = (((long long)b * p.H + h) * L + i) * L + j;
+      const long long plane = (long long)p.B * p.H * L * L;
+      p.probs[0 * plane + e] = r.P0soft[jj] * r.D2[jj]; p.probs[1 * plane + e] = Pj;
+      p.probs[2 * plane + e] = Mj; p.probs[3 * plane + e] = r.A[jj];
+      p.probs[4 * plane + e] = r.C[jj]; p.probs[5 * plane + e] = Rf;
+    }
+  }
+  if (rowok && sub == 0) cx.pen += (float)(L - bound);      // columns outside the range: M == 0 -> (1-M)^2 == 1
+  __syncwarp();
+  // ctx[i][c] = sum_{j<bound} prob[j] * V[j][c]
+  float accR[CM::CPL], accA[CM::CPL];
+#pragma unroll
+  for (int k = 0; k < CM::CPL; ++k) accR[k] = accA[k] = 0.f;
+  int lo, hi;
+  CM::slice(sub, 0, (bound + 3) & ~3, lo, hi);
+  const int c0 = CM::c0(sub);
+  for (int j = lo; j < hi; j += 4) {
+    const float4 pr = *reinterpret_cast<const float4*>(bufR + j);
+    const float4 pa = *reinterpret_cast<const float4*>(bufA + j);
+    const float prv[4] = {pr.x, pr.y, pr.z, pr.w}, pav[4] = {pa.x, pa.y, pa.z, pa.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[CM::CPL];
+      VecLd<CM::CPL>::ld(sm.V + (j + u) * dhp + c0, v);
+#pragma unroll
+      for (int k = 0; k < CM::CPL; ++k) {
+        accR[k] = fmaf(prv[u], v[k], accR[k]);
+        if (need_att) accA[k] = fmaf(pav[u], v[k], accA[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CM::CPL; ++k) { accR[k] = CM::reduce(accR[k]); accA[k] = CM::reduce(accA[k]); }
+  if (CM::split(sub) == 0 && rowok) {
+    const long long o = ((long long)b * L + i) * p.d + h * DH + c0;
+    VecLd<CM::CPL>::st(p.ctx_cal + o, accR);
+    if (need_att) VecLd<CM::CPL>::st(p.ctx_att + o, accA);
+  }
+  __syncwarp();
+}
+
+// all rows of the (b,h) tile with G-lane row groups; the heaviest rows go first
+template <int DH, int G, int MAXNJ>
+__device__ __forceinline__ void fwd_rows(const AttnParams& p, const AttnSmem& sm, const RowConst& kc, int b, int h, int nkey,
+                                         bool need_att, int rstride, FwdCtx& cx) {
+  constexpr int RPW = 32 / G;
+  const int L = p.L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / G, sub = lane % G;
+  for (int t0 = warp * RPW; t0 < L; t0 += kAttnWarps * RPW) {
+    const int iw = L - 1 - t0;                    // largest row of this warp (>= 0)
+    const int iraw = iw - grp;
+    const bool rowok = iraw >= 0;
+    const int i = rowok ? iraw : 0;
+    const int bound = min(i + 1, nkey);
+    const int nj = (min(iw + 1, nkey) + G - 1) / G;      // warp-uniform number of column groups
+    if (MAXNJ == 1 || nj == 1) fwd_row_iter<DH, G, 1>(p, sm, kc, b, h, i, rowok, bound, grp, sub, need_att, rstride, cx);
+    else if (nj == 2) fwd_row_iter<DH, G, (MAXNJ >= 2 ? 2 : 1)>(p, sm, kc, b, h, i, rowok, bound, grp, sub, need_att, rstride, cx);
+    else if (nj == 3) fwd_row_iter<DH, G, (MAXNJ >= 3 ? 3 : 1)>(p, sm, kc, b, h, i, rowok, bound, grp, sub, need_att, rstride, cx);
+    else fwd_row_iter<DH, G, (MAXNJ >= 4 ? 4 : 1)>(p, sm, kc, b, h, i, rowok, bound, grp, sub, need_att, rstride, cx);
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kAttnThreads, 3) attn_fwd_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int L = p.L, LP = (L + 3) & ~3;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ptr = smem_f;
+  AttnSmem sm = carve_common(ptr, LP, DH);
+  const int rbw = rowbuf_floats_per_warp(LP, 2);
+  FwdCtx cx;
+  cx.rowbuf = ptr + warp * rbw;
+  cx.pen = 0.f;
+  ptr += kAttnWarps * rbw;
+  double* pen_red = reinterpret_cast<double*>(ptr);   // [warps]; ptr offset is a multiple of 4 floats
+  const int nkey = stage_common<DH>(p, sm, b, h, LP);
+  const bool need_att = p.ctx_att != nullptr;
+  const RowConst kc = make_consts<DH>(p, need_att);
+  if (p.probs) {           // introspection output: columns outside a row's range are exactly 0
+    const long long plane = (long long)p.B * p.H * L * L;
+    float* base = p.probs + ((long long)b * p.H + h) * L * L;
+    for (int e = threadIdx.x; e < L * L; e += blockDim.x)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) base[k * plane + e] = 0.f;
+    __syncthreads();
+  }
+  if (nkey <= 8) fwd_rows<DH, 8, 1>(p, sm, kc, b, h, nkey, need_att, 8, cx);
+  else fwd_rows<DH, 16, 4>(p, sm, kc, b, h, nkey, need_att, LP, cx);
+  double pd = warp_sum_d((double)cx.pen);
+  if (lane == 0) pen_red[warp] = pd;
+  __syncthreads();
+  if (threadIdx.x == 0 && p.pen_sq != nullptr) {
+    double s = 0.0;
+    for (int w = 0; w < kAttnWarps; ++w) s += pen_red[w];
+    atomicAdd(p.pen_sq, s);
+  }
+}
+
+static size_t fwd_smem_bytes(int L, int dh) {
+  const int LP = (L + 3) & ~3;
+  size_t f = common_floats(LP, dh) + (size_t)kAttnWarps * rowbuf_floats_per_warp(LP, 2);
+  return f * sizeof(float) + kAttnWarps * sizeof(double);
+}
+
+template <int DH>
+static int launch_fwd(const AttnParams& p, cudaStream_t st) {
+  size_t smem = fwd_smem_bytes(p.L, DH);
+  int rc = prep_kernel(attn_fwd_kernel<DH>, smem, "attn_calib_fwd");
+  if (rc) return rc;
+  attn_fwd_kernel<DH><<<p.B * p.H, kAttnThreads, smem, st>>>(p);
+  return check_launch("attn_calib_fwd");
+}
+
+}  // namespace acsr
+
+using namespace acsr;
+
+extern "C" int acsr_attn_calib_fwd(const float* mq, const float* mk, const float* mv, const float* aq, const float* ak,
+                                   const float* gate_logit, const int64_t* item_seq, const float* order_w, const float* order_b,
+                                   const float* dist_w, const float* dist_b, const float* scalar, int B, int L, int H, int dh,
+                                   int two_level, int combine_option, float comb_scalar, int rich_mode, const float* rich_ratio,
+                                   float p_attn, const float* D1, const float* D2, const float* D3, const float* noise,
+                                   const void* rng, uint32_t rng_stream, float* ctx_att, float* ctx_cal, double* pen_sq,
+                                   float* probs_out, void* stream) {
+  AttnParams p = {};
+  attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream);
+  p.ctx_att = ctx_att; p.ctx_cal = ctx_cal; p.pen_sq = pen_sq; p.probs = probs_out;
+  int rc = attn_validate(p, "attn_calib_fwd");
+  if (rc) return rc;
+  ACSR_REQUIRE(ctx_cal != nullptr, "attn_calib_fwd: ctx_cal is NULL");
+  switch (dh) {
+    case 8: return launch_fwd<8>(p, (cudaStream_t)stream);
+    case 16: return launch_fwd<16>(p, (cudaStream_t)stream);
+    case 32: return launch_fwd<32>(p, (cudaStream_t)stream);
+    case 64: return launch_fwd<64>(p, (cudaStream_t)stream);
+  }
+  return ACSR_ERR_UNSUPPORTED;
+}

@@ -258,7 +258,7 @@ class FusedTrainStep(object):
                 ops.linear_tc(lb['d_hz'], T2, aa.dense.weight, d, 1, d, None, b['d_ctx'], d)
             else:
                 torch.mm(lb['d_hz'], aa.dense.weight, out=b['d_ctx'])
-            # fused attention backward, one launch per cotangent stream
+            # fused attention backward
             if gate:
                 lb['d_gl'].zero_()
             g = lambda t: None if t is None else t.grad     # noqa: E731
@@ -266,19 +266,12 @@ class FusedTrainStep(object):
             dw, db_, sc = (aa.distance_affine.weight, aa.distance_affine.bias, aa.scalar) if aa.use_distance else (None, None, None)
             rr = getattr(layer, 'rich_calibrated_combine_ratio', None) if not layer.two_level else None
             dc = b['d_ctx']
-            for s in (0, 1):
-                rows = slice(0, T) if s == 0 else slice(T, T2)
-                if last:
-                    d_att, d_cal = (None, dc[rows]) if s == 0 else (dc[rows], None)
-                else:
-                    d_att, d_cal = None, dc[rows]
-                d_pen = dpen[l:l + 1] if s == 1 else None
-                own = s == 0                                 # stream 0 owns the non-attack parameters
-                LIB.call('acsr_attn_calib_bwd', _p(d_att), _p(d_cal), _p(d_pen), *lb['attn_args'],
-                         _p(lb['d_mq'][rows]), _p(lb['d_mk'][rows]), _p(lb['d_mv'][rows]), _p(lb['d_aq'][rows]), _p(lb['d_ak'][rows]),
-                         _p(lb['d_gl'][rows]) if gate else None,
-                         _p(g(ow)) if own else None, _p(g(ob_)) if own else None, _p(g(dw)) if own else None,
-                         _p(g(db_)) if own else None, _p(g(sc)) if own else None, _p(g(rr)) if own else None, st)
+            # both cotangent streams in one launch: stream 0 = d(calibrated loss), stream 1 = d(attacked loss) which
+            # enters through the attacked context on the last layer, through the calibrated chain below, plus the penalty
+            d_att1, d_cal1 = (dc[T:], None) if last else (None, dc[T:])
+            LIB.call('acsr_attn_calib_bwd2', _p(dc[:T]), None, _p(d_att1), _p(d_cal1), _p(dpen[l:l + 1]), *lb['attn_args'],
+                     _p(lb['d_mq']), _p(lb['d_mk']), _p(lb['d_mv']), _p(lb['d_aq']), _p(lb['d_ak']),
+                     _p(lb['d_gl']) if gate else None, _p(g(ow)), _p(g(ob_)), _p(g(dw)), _p(g(db_)), _p(g(sc)), _p(g(rr)), st)
             # projections: input gradients for both streams, weight gradients from the owning stream
             aqt, akt = aa.attack_query_transform, aa.attack_key_transform
             st3 = self._stacked(l)

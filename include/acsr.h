@@ -104,6 +104,25 @@ int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const fl
                         float* d_mq, float* d_mk, float* d_mv, float* d_aq, float* d_ak,
                         float* d_gate_logit, float* d_order_w, float* d_order_b,
                         float* d_dist_w, float* d_dist_b, float* d_scalar, float* d_rich_ratio, void* stream);
+/* the same backward for BOTH cotangent streams of the adversarial step in one launch (the reference's two
+ * backward() traversals, trainer/trainer.py:672-684): stream 0 = d(calibrated loss) carries d_ctx_cal0 (+ d_pen_sq0),
+ * stream 1 = d(attacked loss) carries d_ctx_att1 (last layer) OR d_ctx_cal1 (lower layers) and d_pen_sq1; any may be
+ * NULL.  The row probabilities are recomputed once and shared.  Outputs are [2*B*L, .]: stream 1 writes B*L rows below
+ * stream 0 in d_mq..d_ak and in d_gate_logit ([2*B*L, L]).  Parameter gradients (d_order_* .. d_rich_ratio) are taken
+ * from stream 0 only: stream 1 trains nothing but the attack transforms. */
+int acsr_attn_calib_bwd2(const float* d_ctx_cal0, const float* d_pen_sq0,
+                         const float* d_ctx_att1, const float* d_ctx_cal1, const float* d_pen_sq1,
+                         const float* mq, const float* mk, const float* mv, const float* aq, const float* ak,
+                         const float* gate_logit, const int64_t* item_seq,
+                         const float* order_w, const float* order_b,
+                         const float* dist_w, const float* dist_b, const float* scalar,
+                         int B, int L, int H, int dh,
+                         int two_level, int combine_option, float comb_scalar, int rich_mode, const float* rich_ratio,
+                         float p_attn, const float* D1, const float* D2, const float* D3, const float* noise,
+                         const void* rng, uint32_t rng_stream,
+                         float* d_mq, float* d_mk, float* d_mv, float* d_aq, float* d_ak,
+                         float* d_gate_logit, float* d_order_w, float* d_order_b,
+                         float* d_dist_w, float* d_dist_b, float* d_scalar, float* d_rich_ratio, void* stream);
 
 /* ---- epilogue of the output projection and of the FFN: LN(dropout(h + bias) + res) ----
  * replaces model/layers.py:681-683 and 794-796 (bias add of the preceding nn.Linear folded in).

@@ -282,6 +282,72 @@ def test_attn_calib_backward(A, case, which):
         assert float((got.cpu() - ref).abs().max()) <= 5e-4 * scale + 1e-6, (k, got, ref)
 
 
+def _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, cots, dual):
+    """raw C-ABI call of the attention backward.  cots = (cal0, pen0, att1, cal1, pen1) device tensors or None."""
+    H = cfg['n_heads']
+    B, L, d = t['mq'].shape
+    dh = d // H
+    P = A.ops._p
+    c = lambda x: None if x is None else x.clone().cuda().contiguous()
+    tc = {k: c(v) for k, v in t.items()}
+    lpc = {k: c(v) for k, v in lp.items()}
+    rand = {k: c(rnd.get((0, k))) for k in ('D1', 'D2', 'D3', 'noise')}
+    seqc = seq.cuda()
+    two_level = int(bool(cfg['two_level']))
+    comb = A.ops.COMBINE_IDS[cfg['combine_option']]
+    rich = A.ops.RICH_IDS.get(cfg['rich_calibrated_combine'], 0) if not cfg['two_level'] else 0
+    shared = (P(tc['mq']), P(tc['mk']), P(tc['mv']), P(tc['aq']), P(tc['ak']), P(tc['gate']), P(seqc, torch.int64),
+              P(lpc.get('order_affine.weight')), P(lpc.get('order_affine.bias')), P(lpc.get('distance_affine.weight')),
+              P(lpc.get('distance_affine.bias')), P(lpc.get('scalar')), B, L, H, dh, two_level, comb, 0.37, rich,
+              P(lpc.get('rich_calibrated_combine_ratio')), float(p), P(rand['D1']), P(rand['D2']), P(rand['D3']),
+              P(rand['noise']), None, 16)
+    S = 2 if dual else 1
+    out = {k: torch.full((S * B * L, d), float('nan'), device='cuda') for k in ('mq', 'mk', 'mv', 'aq', 'ak')}
+    out['gate'] = torch.zeros(S * B * L, L, device='cuda') if tc['gate'] is not None else None
+    pg = {k: torch.zeros_like(v) for k, v in lpc.items()}
+    outs = (P(out['mq']), P(out['mk']), P(out['mv']), P(out['aq']), P(out['ak']), P(out['gate']),
+            P(pg.get('order_affine.weight')), P(pg.get('order_affine.bias')), P(pg.get('distance_affine.weight')),
+            P(pg.get('distance_affine.bias')), P(pg.get('scalar')), P(pg.get('rich_calibrated_combine_ratio')))
+    cal0, pen0, att1, cal1, pen1 = cots
+    st = A.ops._stream()
+    if dual:
+        A.LIB.call('acsr_attn_calib_bwd2', P(cal0), P(pen0), P(att1), P(cal1), P(pen1), *shared, *outs, st)
+    else:
+        A.LIB.call('acsr_attn_calib_bwd', P(att1), P(cal0), P(pen0), *shared, *outs, st)
+    torch.cuda.synchronize()
+    return out, pg
+
+
+@pytest.mark.parametrize('case', [ATTN_CASES[0], ATTN_CASES[1], ATTN_CASES[5], ATTN_CASES[7], ATTN_CASES[9], ATTN_CASES[4]])
+@pytest.mark.parametrize('last', [True, False])
+def test_attn_calib_backward_two_streams(A, case, last):
+    """acsr_attn_calib_bwd2 == two single-stream launches (stream 0: d_cal; stream 1: d_att|d_cal + d_pen);
+    cotangent rows that are exactly zero (positions behind len-1) take the skip path."""
+    H, dh, L, combine, two_level, rich, uo, ud, p = case
+    cfg, seq, t, lp, rnd, g = _attn_inputs(*case)
+    B, d = t['mq'].shape[0], H * dh
+    g0 = torch.randn(B, L, d, generator=g).cuda()
+    g1 = torch.randn(B, L, d, generator=g).cuda()
+    g0[1:, 7:] = 0.0                                   # most rows of the calibrated-loss stream carry no cotangent
+    if last:
+        g1[:, :L - 1] = 0.0
+    pen = torch.tensor([0.01]).cuda()
+    att1, cal1 = (g1, None) if last else (None, g1)
+    both, pg_both = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (g0, None, att1, cal1, pen), dual=True)
+    s0, pg0 = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (g0, None, None, None, None), dual=False)
+    s1, _ = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (cal1, pen, att1, None, None), dual=False)
+    T = B * L
+    for k in both:
+        if both[k] is None:
+            continue
+        assert not bool(torch.isnan(both[k]).any()), k
+        close(both[k][:T], s0[k], 2e-5, 'stream0 d_' + k)
+        close(both[k][T:], s1[k], 2e-5, 'stream1 d_' + k)
+    for k in pg0:
+        scale = float(pg0[k].abs().max())
+        assert float((pg_both[k] - pg0[k]).abs().max()) <= 1e-4 * scale + 1e-6, k
+
+
 def test_philox_dropout_and_noise_statistics(A):
     """in-kernel RNG: keep rate, inverted scaling, fwd/bwd reuse the same mask, new step -> new mask."""
     d, T, p = 64, 4096, 0.5
