@@ -283,7 +283,7 @@ __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm
   float accOq[CM::CPL], accDq[CM::CPL], accOk[CM::CPL], accDk[CM::CPL];
 #pragma unroll
   for (int k = 0; k < CM::CPL; ++k) accOq[k] = accDq[k] = accOk[k] = accDk[k] = 0.f;
-  for (int t0 = warp * RPW; t0 < L; t0 += kAttnWarps * RPW) {      // heaviest rows first
+  for (int t0 = next_task(sm.misc + 2, RPW); t0 < L; t0 = next_task(sm.misc + 2, RPW)) {      // heaviest rows first
     const int iw = L - 1 - t0;
     const int iraw = iw - grp;
     const bool rowok = iraw >= 0;
@@ -300,7 +300,7 @@ __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm
   }
   __syncthreads();
   // column-side gradients: dk_j, dk'_j, dv_j  (group per column, lane = channel, rows i >= j)
-  for (int t0 = warp * RPW; t0 < nkey; t0 += kAttnWarps * RPW) {    // heaviest columns (small j) first
+  for (int t0 = next_task(sm.misc + 3, RPW); t0 < nkey; t0 = next_task(sm.misc + 3, RPW)) {    // heaviest columns (small j) first
     const int jraw = t0 + grp;
     const bool colok = jraw < nkey;
     const int j = colok ? jraw : 0;

@@ -126,7 +126,8 @@ struct AttnSmem {
   float *Q, *K, *V, *Q2, *K2;                        // [LP][dh+4]
   float *rowO, *rowD, *colO, *colD, *logd, *keyok;   // [LP]
   float *wo, *wd;                                    // [2*dh] spatial-calibrator weights (0 when absent)
-  int* misc;                                         // [4] ballot words of the key-validity scan
+  int* misc;                                         // [8] 0,1: ballot words of the key-validity scan; 2,3: row / column task
+                                                     // counters (dynamic heaviest-first scheduling); 4: warp arrival counter
 };
 
 struct RowConst {      // per-launch scalars hoisted out of the row loop
@@ -183,6 +184,13 @@ __device__ __forceinline__ void softmax_bwd_row(const float* y, const float* dy,
   for (int jj = 0; jj < NJ; ++jj) dz[jj] = y[jj] * (dy[jj] - s);
 }
 
+// next task of a dynamically scheduled loop: tasks are handed out in order (heaviest first), `step` at a time
+__device__ __forceinline__ int next_task(int* counter, int step) {
+  int t = 0;
+  if ((threadIdx.x & 31) == 0) t = atomicAdd(counter, step);
+  return __shfl_sync(kFull, t, 0);
+}
+
 // packed lower-triangular storage of a transposed [j][i] matrix: row j keeps i in [j & ~3, LP)
 __host__ __device__ __forceinline__ int tri_off(int j, int LP) {
   const int a = j >> 2, b = j & 3;
@@ -213,6 +221,7 @@ __device__ __forceinline__ int stage_common(const AttnParams& p, const AttnSmem&
     const bool ok = j < L && p.item_seq[(long long)b * L + j] != 0;
     const unsigned m = __ballot_sync(kFull, ok);
     if ((threadIdx.x & 31) == 0) sm.misc[threadIdx.x >> 5] = (int)m;
+    if (threadIdx.x >= 2 && threadIdx.x < 5) sm.misc[threadIdx.x] = 0;
     if (j < LP) { sm.keyok[j] = ok ? 1.0f : 0.0f; sm.logd[j] = logf((float)j + 1.0f); }
   }
   stage_tile<DH>(sm.Q, p.mq, b, h, L, p.d, L, LP);
@@ -480,10 +489,10 @@ __device__ __forceinline__ AttnSmem carve_common(float*& ptr, int LP, int dh) {
   sm.keyok = ptr; ptr += LP;
   sm.wo = ptr; ptr += 2 * dh;
   sm.wd = ptr; ptr += 2 * dh;
-  sm.misc = reinterpret_cast<int*>(ptr); ptr += 4;
+  sm.misc = reinterpret_cast<int*>(ptr); ptr += 8;
   return sm;
 }
-static inline size_t common_floats(int LP, int dh) { return (size_t)5 * LP * (dh + 4) + 6 * LP + 4 * dh + 4; }
+static inline size_t common_floats(int LP, int dh) { return (size_t)5 * LP * (dh + 4) + 6 * LP + 4 * dh + 8; }
 
 // per-group row buffers: sequences with nkey <= 8 run four 8-lane groups per warp with 8-float rows, all others two
 // 16-lane groups with LP-float rows; the allocation covers both

@@ -80,9 +80,9 @@ __device__ __forceinline__ void fwd_rows(const AttnParams& p, const AttnSmem& sm
                                          bool need_att, int rstride, FwdCtx& cx) {
   constexpr int RPW = 32 / G;
   const int L = p.L;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int grp = lane / G, sub = lane % G;
-  for (int t0 = warp * RPW; t0 < L; t0 += kAttnWarps * RPW) {
+  for (int t0 = next_task(sm.misc + 2, RPW); t0 < L; t0 = next_task(sm.misc + 2, RPW)) {   // heaviest rows first
     const int iw = L - 1 - t0;                    // largest row of this warp (>= 0)
     const int iraw = iw - grp;
     const bool rowok = iraw >= 0;
@@ -97,7 +97,7 @@ __device__ __forceinline__ void fwd_rows(const AttnParams& p, const AttnSmem& sm
 }
 
 template <int DH>
-__global__ void __launch_bounds__(kAttnThreads, 3) attn_fwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 4) attn_fwd_kernel(const AttnParams p) {
   extern __shared__ __align__(16) float smem_f[];
   const int L = p.L, LP = (L + 3) & ~3;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attn_fwd_kernel(const AttnPar
   cx.rowbuf = ptr + warp * rbw;
   cx.pen = 0.f;
   ptr += kAttnWarps * rbw;
-  double* pen_red = reinterpret_cast<double*>(ptr);   // [warps]; ptr offset is a multiple of 4 floats
+  double* pen_red = reinterpret_cast<double*>(ptr);   // CTA penalty sum; ptr offset is a multiple of 4 floats
+  if (threadIdx.x == 0) *pen_red = 0.0;
   const int nkey = stage_common<DH>(p, sm, b, h, LP);
   const bool need_att = p.ctx_att != nullptr;
   const RowConst kc = make_consts<DH>(p, need_att);
@@ -123,13 +124,12 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attn_fwd_kernel(const AttnPar
   }
   if (nkey <= 8) fwd_rows<DH, 8, 1>(p, sm, kc, b, h, nkey, need_att, 8, cx);
   else fwd_rows<DH, 16, 4>(p, sm, kc, b, h, nkey, need_att, LP, cx);
-  double pd = warp_sum_d((double)cx.pen);
-  if (lane == 0) pen_red[warp] = pd;
-  __syncthreads();
-  if (threadIdx.x == 0 && p.pen_sq != nullptr) {
-    double s = 0.0;
-    for (int w = 0; w < kAttnWarps; ++w) s += pen_red[w];
-    atomicAdd(p.pen_sq, s);
+  // CTA penalty sum without a closing barrier: the last warp to arrive publishes it
+  const double pd = warp_sum_d((double)cx.pen);
+  if (lane == 0 && p.pen_sq != nullptr) {
+    atomicAdd(pen_red, pd);
+    __threadfence_block();
+    if (atomicAdd(sm.misc + 4, 1) == kAttnWarps - 1) atomicAdd(p.pen_sq, *reinterpret_cast<volatile double*>(pen_red));
   }
 }
 

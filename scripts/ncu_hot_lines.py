@@ -34,5 +34,5 @@ for r in rows:
 tot = sum(v[0] for v in agg.values())
 tots = sum(v[1] for v in agg.values())
 print('total warp-instructions %d, samples %d' % (tot, tots))
-for (f, ln), (n, s) in sorted(agg.items(), key=lambda x: -x[1][0])[:top]:
+for (f, ln), (n, s) in sorted(agg.items(), key=lambda x: -x[1][int(len(sys.argv) > 3)])[:top]:
     print('%-16s %5d  inst %5.1f%%  samples %5.1f%%  %s' % (f[:16], ln, 100.0 * n / max(tot, 1), 100.0 * s / max(tots, 1), src[(f, ln)].strip()[:100]))
