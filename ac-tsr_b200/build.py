@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libacsr.so')
 STAMP = os.path.join(CSRC, '.libacsr.stamp')
-SOURCES = ['api.cu', 'rowwise.cu', 'attn_fwd.cu', 'attn_bwd.cu', 'logits_tc.cu', 'topk_merge.cu', 'linear.cu']
+SOURCES = ['api.cu', 'rowwise.cu', 'attn_fwd.cu', 'attn_bwd.cu', 'logits_tc.cu', 'topk_merge.cu', 'linear.cu', 'linear_tok.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
 

@@ -294,6 +294,26 @@ def linear_tc(X, rows, W, N, w_sn, w_sk, bias, Y, ldy, accumulate=False, batch=1
              _p(Y), int(ldy), int(batch), int(sx), int(sw), int(sb), int(sy), passes, _stream())
 
 
+def linear_tok(X, rows, K, W, N, Y, ldy, ldx=None, xkb=64, w_sn=None, w_sk=1, wkb=64, bias=None, accumulate=False,
+               batch=1, sx=0, sw=0, sb=0, sy=0, passes=3):
+    """Y[rows,N] (+)= X.W^T + bias on tcgen05 with token rows on the M axis (acsr_linear_tok); strides in floats."""
+    LIB.call('acsr_linear_tok', _p(X), int(K if ldx is None else ldx), int(xkb), int(rows), int(K), _p(W),
+             int(K if w_sn is None else w_sn), int(w_sk), int(wkb), int(N), _p(bias), int(bool(accumulate)), _p(Y), int(ldy),
+             int(batch), int(sx), int(sw), int(sb), int(sy), passes, _stream())
+
+
+def linear_tok_act(X, rows, K, W, N, bias, act, Z, A, passes=3):
+    """Z = X.W^T, A = act(Z + bias)  (acsr_linear_tok_act)."""
+    LIB.call('acsr_linear_tok_act', _p(X), int(K), int(rows), int(K), _p(W), int(N), _p(bias), int(act), _p(Z), _p(A), int(N),
+             passes, _stream())
+
+
+def linear_tok_bdrl(X, rows, K, W, bias, res, res_rows, ln_w, ln_b, eps, p, mask, rngp, rng_stream, HZ, out, stats, passes=3):
+    """HZ = X.W^T ; out = LN(dropout(HZ + bias) + res) ; stats = (mean, rstd)  (acsr_linear_tok_bdrl, width 64)."""
+    LIB.call('acsr_linear_tok_bdrl', _p(X), int(K), int(rows), int(K), _p(W), _p(bias), _p(res), int(res_rows), _p(ln_w), _p(ln_b),
+             float(eps), float(p), _p(mask), rngp, int(rng_stream), _p(HZ), _p(out), _p(stats), passes, _stream())
+
+
 class LinearFn(torch.autograd.Function):
     """y = x.W^T (+ b).  Forward and dX are library GEMMs; dW/db use the token-split kernel."""
 

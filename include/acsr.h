@@ -194,6 +194,30 @@ int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_
 int acsr_topk_merge(const float* partial_val, const int64_t* partial_idx, int M, int n_parts, int k,
                     const int64_t* positive, float* topk_val, int64_t* topk_idx, int32_t* rec_topk, void* stream);
 
+/* ---- encoder GEMMs on tcgen05 with the token rows on the UMMA M axis (3xTF32, fp32-level accuracy) ----
+ * replaces the nn.Linear forward / input-gradient GEMMs of model/layers.py:658-659, 680, 687-689, 791-794, 887.
+ * Y[r, n] (+)= sum_k X(r,k) * W(n,k) + bias[n], r < rows, n < N, k < K <= 256, with strided operands so that
+ * transposed weights (input gradients) and K-concatenated inputs need no copies:
+ *   X(r,k) = X[(k/64)*x_kblock_stride + r*ldx + k%64]
+ *   W(n,k) = W[(k/64)*w_kblock_stride + n*w_stride_n + (k%64)*w_stride_k]
+ * batch > 1 launches independent problems (pointer + b*stride_*).  bias NULL or [N]; accumulate != 0 adds to Y. */
+int acsr_linear_tok(const float* X, int64_t ldx, int64_t x_kblock_stride, int64_t rows, int K,
+                    const float* W, int64_t w_stride_n, int64_t w_stride_k, int64_t w_kblock_stride, int N,
+                    const float* bias, int accumulate, float* Y, int64_t ldy,
+                    int batch, int64_t stride_x, int64_t stride_w, int64_t stride_bias, int64_t stride_y,
+                    int passes, void* stream);
+/* FFN first half fused (model/layers.py:776-792): Z = X.W^T (saved pre-bias for the backward), A = act(Z + bias).
+ * X [rows,K] (row stride ldx), W [N,K] row-major, Z,A [rows,N] (row stride ldy). */
+int acsr_linear_tok_act(const float* X, int64_t ldx, int64_t rows, int K, const float* W, int N, const float* bias, int act,
+                        float* Z, float* A, int64_t ldy, int passes, void* stream);
+/* projection + bias + dropout + residual + LayerNorm fused (model/layers.py:680-683, 793-796), output width 64:
+ * HZ = X.W^T (saved for the backward), out = LN(dropout(HZ + bias) + res[r % res_rows]), stats[r] = (mean, rstd).
+ * Dropout masks use the same Philox counters as acsr_bias_dropout_res_ln_{fwd,bwd}, which stays the backward. */
+int acsr_linear_tok_bdrl(const float* X, int64_t ldx, int64_t rows, int K, const float* W, const float* bias,
+                         const float* res, int64_t res_rows, const float* ln_w, const float* ln_b, float eps,
+                         float p_drop, const float* mask, const void* rng, uint32_t rng_stream,
+                         float* HZ, float* out, float* stats, int passes, void* stream);
+
 /* ---- token-parallel linear layer on tcgen05 (3xTF32):  Y[rows, N] (+)= X[rows, K] . Wt^T + bias,  K == 64 (ABI v1).
  * replaces the forward nn.Linear calls at layers.py:658-659, 680, 687-689, 791 and their input-gradient GEMMs.
  * The stationary operand is addressed as Wt[n][k] = W[n*w_stride_n + k*w_stride_k]: (K,1) for y = x.W^T with W [N,K]

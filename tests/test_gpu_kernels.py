@@ -505,3 +505,114 @@ def test_linear_tc(A, rows, N, transposed, bias, acc, batch):
     close(Yc, ref, 3e-6, 'linear_tc')
     with pytest.raises(A.AcsrError, match='unsupported'):
         A.LIB.call('acsr_linear_tc', Xc.data_ptr(), rows, 128, Wc.data_ptr(), N, 128, 1, None, 0, Yc.data_ptr(), N, 1, 0, 0, 0, 0, 3, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# tcgen05 token-tile GEMMs (acsr_linear_tok*): compared with an fp64 torch reference of the same op
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('rows,K,N', [(12800, 64, 64), (300, 64, 256), (1000, 256, 64), (129, 64, 50), (257, 128, 128), (5, 64, 16)])
+@pytest.mark.parametrize('accumulate', [False, True])
+def test_linear_tok_plain(A, rows, K, N, accumulate):
+    g = torch.Generator().manual_seed(rows + K + N)
+    X = torch.randn(rows, K, generator=g).cuda()
+    W = torch.randn(N, K, generator=g).cuda() * 0.2
+    b = torch.randn(N, generator=g).cuda()
+    Y0 = torch.randn(rows, N, generator=g).cuda()
+    Y = Y0.clone()
+    A.ops.linear_tok(X, rows, K, W, N, Y, N, bias=b, accumulate=accumulate)
+    ref = X.double() @ W.double().t() + b.double() + (Y0.double() if accumulate else 0)
+    close(Y, ref, 3e-6, 'linear_tok')
+
+
+def test_linear_tok_transposed_kconcat_batched(A):
+    g = torch.Generator().manual_seed(5)
+    T2, d, I, L = 700, 64, 256, 50
+    # input gradient through W2 [d, I]: d_a1 = d_z2 . W2  (weight read transposed)
+    dz2 = torch.randn(T2, d, generator=g).cuda()
+    W2 = torch.randn(d, I, generator=g).cuda() * 0.1
+    da1 = torch.empty(T2, I).cuda()
+    A.ops.linear_tok(dz2, T2, d, W2, I, da1, I, w_sn=1, w_sk=I, wkb=64 * I)
+    close(da1, dz2.double() @ W2.double(), 3e-6, 'transposed weight')
+    # K = 256 with a transposed weight, accumulating: d_h += d_z1 . W1   (W1 [I, d])
+    dz1 = torch.randn(T2, I, generator=g).cuda()
+    W1 = torch.randn(I, d, generator=g).cuda() * 0.1
+    dh0 = torch.randn(T2, d, generator=g).cuda()
+    dh = dh0.clone()
+    A.ops.linear_tok(dz1, T2, I, W1, d, dh, d, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
+    close(dh, dh0.double() + dz1.double() @ W1.double(), 3e-6, 'K=256 accumulate')
+    # K-concatenated stacked operands: d_x += sum_b d_qkv[b] . Wqkv[b]
+    dqkv = torch.randn(3, T2, d, generator=g).cuda()
+    Wqkv = torch.randn(3, d, d, generator=g).cuda() * 0.1
+    dx0 = torch.randn(T2, d, generator=g).cuda()
+    dx = dx0.clone()
+    A.ops.linear_tok(dqkv, T2, 3 * d, Wqkv, d, dx, d, ldx=d, xkb=T2 * d, w_sn=1, w_sk=d, wkb=d * d, accumulate=True)
+    ref = dx0.double() + sum(dqkv[i].double() @ Wqkv[i].double() for i in range(3))
+    close(dx, ref, 3e-6, 'K-concat')
+    # rows of a leading sub-range only
+    dx2 = dx0.clone()
+    A.ops.linear_tok(dqkv, 300, 3 * d, Wqkv, d, dx2, d, ldx=d, xkb=T2 * d, w_sn=1, w_sk=d, wkb=d * d, accumulate=True)
+    close(dx2[:300], ref[:300], 3e-6, 'K-concat rows')
+    assert torch.equal(dx2[300:], dx0[300:])
+    # batched with a shared input: Q/K/V projections
+    x = torch.randn(T2, d, generator=g).cuda()
+    bq = torch.randn(3, d, generator=g).cuda()
+    qkv = torch.empty(3, T2, d).cuda()
+    A.ops.linear_tok(x, T2, d, Wqkv, d, qkv, d, bias=bq, batch=3, sx=0, sw=d * d, sb=d, sy=T2 * d)
+    for i in range(3):
+        close(qkv[i], x.double() @ Wqkv[i].double().t() + bq[i].double(), 3e-6, 'batched %d' % i)
+    # unaligned rows (gate: K = L = 50 input gradient, N = 50 forward)
+    Wg = torch.randn(L, d, generator=g).cuda() * 0.1
+    bg = torch.randn(L, generator=g).cuda()
+    gl = torch.empty(T2, L).cuda()
+    A.ops.linear_tok(x, T2, d, Wg, L, gl, L, bias=bg)
+    close(gl, x.double() @ Wg.double().t() + bg.double(), 3e-6, 'N=50')
+    dgl = torch.randn(T2, L, generator=g).cuda()
+    dmq0 = torch.randn(T2, d, generator=g).cuda()
+    dmq = dmq0.clone()
+    A.ops.linear_tok(dgl, T2, L, Wg, d, dmq, d, ldx=L, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
+    close(dmq, dmq0.double() + dgl.double() @ Wg.double(), 3e-6, 'K=50')
+
+
+@pytest.mark.parametrize('act', ['gelu', 'relu', 'swish', 'tanh', 'sigmoid'])
+def test_linear_tok_act(A, act):
+    g = torch.Generator().manual_seed(9)
+    R, d, I = 1500, 64, 256
+    X = torch.randn(R, d, generator=g).cuda()
+    W = torch.randn(I, d, generator=g).cuda() * 0.2
+    b = torch.randn(I, generator=g).cuda()
+    Z, A1 = torch.empty(R, I).cuda(), torch.empty(R, I).cuda()
+    A.ops.linear_tok_act(X, R, d, W, I, b, A.ops.ACT_IDS[act], Z, A1)
+    zr = X.double() @ W.double().t()
+    close(Z, zr, 3e-6, 'Z')
+    close(A1, O.act_fn(act)((zr + b.double()).float().cpu()), 1e-5, 'act')
+
+
+@pytest.mark.parametrize('K,p,explicit', [(64, 0.0, False), (64, 0.5, True), (256, 0.5, True), (64, 0.5, False), (128, 0.3, True)])
+def test_linear_tok_bdrl(A, K, p, explicit):
+    g = torch.Generator().manual_seed(K + int(p * 10))
+    R, Tres, d = 2 * 640, 640, 64
+    X = torch.randn(R, K, generator=g).cuda()
+    W = torch.randn(d, K, generator=g).cuda() * 0.2
+    b = torch.randn(d, generator=g).cuda()
+    res = torch.randn(Tres, d, generator=g).cuda()
+    lw, lb = torch.randn(d, generator=g).cuda(), torch.randn(d, generator=g).cuda()
+    mask = drop((R, d), p, g).cuda() if explicit else None
+    rng = A.ops.DeviceRng(77, torch.device('cuda'))
+    HZ, out, stats = torch.empty(R, d).cuda(), torch.empty(R, d).cuda(), torch.empty(R, 2).cuda()
+    A.ops.linear_tok_bdrl(X, R, K, W, b, res, Tres, lw, lb, 1e-12, p, mask, rng.ptr, 19, HZ, out, stats)
+    hz = X.double() @ W.double().t()
+    close(HZ, hz, 3e-6, 'HZ')
+    # the unfused kernel with the same rng / mask is the reference of the epilogue (same Philox counters)
+    out2, stats2 = torch.empty(R, d).cuda(), torch.empty(R, 2).cuda()
+    A.LIB.call('acsr_bias_dropout_res_ln_fwd', HZ.data_ptr(), b.data_ptr(), res.data_ptr(), lw.data_ptr(), lb.data_ptr(), 1e-12,
+               R, d, Tres, p, mask.data_ptr() if explicit else None, rng.ptr, 19, out2.data_ptr(), stats2.data_ptr(),
+               A.ops._stream())
+    close(out, out2, 2e-5, 'out vs unfused')
+    close(stats, stats2, 2e-5, 'stats vs unfused')
+    if explicit or p == 0.0:
+        m = mask.double() if explicit else 1.0
+        x = (hz + b.double()) * m + res.double().repeat(R // Tres, 1)
+        mean = x.mean(-1, keepdim=True)
+        var = ((x - mean) ** 2).mean(-1, keepdim=True)
+        ref = (x - mean) / torch.sqrt(var + 1e-12) * lw.double() + lb.double()
+        close(out, ref, 2e-5, 'out')
