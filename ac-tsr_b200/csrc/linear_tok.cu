@@ -105,23 +105,36 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
     float* Bhi = reinterpret_cast<float*>(sBhi);
     float* Blo = reinterpret_cast<float*>(sBlo);
     const bool vec_ok = p.w_sk == 1 && (p.w_sn & 3) == 0 && (p.wkb & 3) == 0 && ((reinterpret_cast<uintptr_t>(Wp) & 15) == 0);
-    for (int item = threadIdx.x; item < NB * KC; item += kLtThreads) {
-      const int n = item % NB, kc = item / NB;
-      const int kb = kc / (kLtKB / 4), kcl = kc % (kLtKB / 4);
-      const int k0 = kb * kLtKB + kcl * 4;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + n < p.N && k0 < p.K) {
-        const float* w = Wp + kb * p.wkb + (long long)(n0 + n) * p.w_sn + (long long)(kcl * 4) * p.w_sk;
-        if (vec_ok && k0 + 4 <= p.K) x = __ldg(reinterpret_cast<const float4*>(w));
-        else {
-          x.x = __ldg(w);
-          if (k0 + 1 < p.K) x.y = __ldg(w + p.w_sk);
-          if (k0 + 2 < p.K) x.z = __ldg(w + 2 * p.w_sk);
-          if (k0 + 3 < p.K) x.w = __ldg(w + 3 * p.w_sk);
+    constexpr int kU = 4;                                  // loads in flight per thread
+    for (int item0 = threadIdx.x; item0 < NB * KC; item0 += kLtThreads * kU) {
+      float4 xs[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int item = item0 + u * kLtThreads;
+        xs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item >= NB * KC) continue;
+        const int n = item % NB, kc = item / NB;
+        const int kb = kc / (kLtKB / 4), kcl = kc % (kLtKB / 4);
+        const int k0 = kb * kLtKB + kcl * 4;
+        if (n0 + n < p.N && k0 < p.K) {
+          const float* w = Wp + kb * p.wkb + (long long)(n0 + n) * p.w_sn + (long long)(kcl * 4) * p.w_sk;
+          if (vec_ok && k0 + 4 <= p.K) xs[u] = __ldg(reinterpret_cast<const float4*>(w));
+          else {
+            xs[u].x = __ldg(w);
+            if (k0 + 1 < p.K) xs[u].y = __ldg(w + p.w_sk);
+            if (k0 + 2 < p.K) xs[u].z = __ldg(w + 2 * p.w_sk);
+            if (k0 + 3 < p.K) xs[u].w = __ldg(w + 3 * p.w_sk);
+          }
         }
       }
-      const int off = kc * (NB * 4) + n * 4;               // floats: chunk plane of NB rows x 16 B
-      lt_split_store(Bhi + off, Blo + off, x);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int item = item0 + u * kLtThreads;
+        if (item >= NB * KC) continue;
+        const int n = item % NB, kc = item / NB;
+        const int off = kc * (NB * 4) + n * 4;             // floats: chunk plane of NB rows x 16 B
+        lt_split_store(Bhi + off, Blo + off, xs[u]);
+      }
     }
     for (int i = threadIdx.x; i < 128; i += kLtThreads) sBias[i] = (biasp != nullptr && n0 + i < p.N) ? biasp[n0 + i] : 0.f;
   }

@@ -32,8 +32,10 @@ class FusedTrainStep(object):
         self.m, self.opt = model, optimizer
         self.buf = {}
         self.vp = None            # dist.VocabParallel when the logits are sharded over ranks
-        # encoder GEMMs with K == 64 run on the tcgen05 linear kernel (3xTF32); other shapes stay library GEMMs
-        self.tc = bool(getattr(model, 'tc_linear', False)) and model.hidden_size == 64
+        # d == 64: every encoder GEMM runs on the tcgen05 token-tile kernel (3xTF32) with its epilogue fused;
+        # other widths stay library GEMMs + the row-wise epilogue kernels
+        self.tc = (bool(getattr(model, 'tc_linear', True)) and model.hidden_size == 64 and model.inner_size <= 256
+                   and model.inner_size % 4 == 0)
         # weight-gradient reductions have no consumer before Adam: they run on a second stream (a parallel branch of
         # the captured graph) and overlap the dependent chain of input-gradient kernels
         self.overlap_wgrad = bool(getattr(model, 'overlap_wgrad', True))
@@ -124,9 +126,9 @@ class FusedTrainStep(object):
             xs.append(x)
             st3 = self._stacked(l)
             if st3 is not None and self.tc:                   # stacked Q/K/V and attack pair: two batched tcgen05 launches
-                ops.linear_tc(x, T, st3['Wqkv'], d, d, 1, st3['bqkv'], lb['qkv'], d, batch=3, sx=0, sw=d * d, sb=d, sy=T * d)
-                ops.linear_tc(lb['qkv'], T, st3['Waqk'], d, d, 1, st3['baqk'], lb['aqk'], d, batch=2, sx=T * d, sw=d * d, sb=d,
-                              sy=T * d)
+                ops.linear_tok(x, T, d, st3['Wqkv'], d, lb['qkv'], d, bias=st3['bqkv'], batch=3, sx=0, sw=d * d, sb=d, sy=T * d)
+                ops.linear_tok(lb['qkv'], T, d, st3['Waqk'], d, lb['aqk'], d, bias=st3['baqk'], batch=2, sx=T * d, sw=d * d,
+                               sb=d, sy=T * d)
             elif st3 is not None:                             # Q/K/V and the attack pair as two batched GEMMs
                 torch.baddbmm(st3['bqkv'], x.unsqueeze(0).expand(3, T, d), st3['Wqkv'].transpose(1, 2), out=lb['qkv'])
                 torch.baddbmm(st3['baqk'], lb['qkv'][:2], st3['Waqk'].transpose(1, 2), out=lb['aqk'])
@@ -142,7 +144,7 @@ class FusedTrainStep(object):
                 if layer.gate.out_features != L:
                     raise ValueError('gate width %d != sequence length %d' % (layer.gate.out_features, L))
                 if self.tc:
-                    ops.linear_tc(lb['mq'], T, layer.gate.weight, L, d, 1, layer.gate.bias, lb['gl'], L)
+                    ops.linear_tok(lb['mq'], T, d, layer.gate.weight, L, lb['gl'], L, bias=layer.gate.bias)
                 else:
                     torch.addmm(layer.gate.bias, lb['mq'], layer.gate.weight.t(), out=lb['gl'])
             elif layer.combine_option == 'annealing':
@@ -152,24 +154,31 @@ class FusedTrainStep(object):
             lb['attn_args'] = self._attn_args(layer, lb, seq, B, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base)
             ctx_cal, ctx_att = lb['ctx'][:T], (lb['ctx'][T:] if last else None)
             LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal), b['pen'][l:].data_ptr(), None, st)
+            lb['m_a'] = mask2(l, 'D5', 'D4', last)
+            lb['m_f'] = mask2(l, 'D7', 'D6', last)
             if self.tc:
-                ops.linear_tc(lb['ctx'], R, aa.dense.weight, d, d, 1, None, lb['hz'], d)
+                # out-projection + bias + dropout + residual + LayerNorm in one kernel; FFN: GEMM + bias + activation, then
+                # GEMM + bias + dropout + residual + LayerNorm
+                ops.linear_tok_bdrl(lb['ctx'], R, d, aa.dense.weight, aa.dense.bias, x, T, aa.LayerNorm.weight, aa.LayerNorm.bias,
+                                    aa.LayerNorm.eps, p_h, lb['m_a'], rngp, base + 3, lb['hz'], lb['h'], lb['st_a'])
+                # (the fused bias+activation epilogue, acsr_linear_tok_act, is slower than GEMM + the row-wise kernel at I=256:
+                # four epilogue warps per SM cannot hide the erf latency)
+                ops.linear_tok(lb['h'], R, d, ff.dense_1.weight, I, lb['z1'], I)
+                LIB.call('acsr_bias_act_fwd', _p(lb['z1']), _p(ff.dense_1.bias), R, I, act_id, _p(lb['a1']), st)
+                ops.linear_tok_bdrl(lb['a1'], R, I, ff.dense_2.weight, ff.dense_2.bias, lb['h'], R, ff.LayerNorm.weight,
+                                    ff.LayerNorm.bias, ff.LayerNorm.eps, p_h, lb['m_f'], rngp, base + 5, lb['z2'], lb['out'],
+                                    lb['st_f'])
             else:
                 torch.mm(lb['ctx'], aa.dense.weight.t(), out=lb['hz'])
-            lb['m_a'] = mask2(l, 'D5', 'D4', last)
-            LIB.call('acsr_bias_dropout_res_ln_fwd', _p(lb['hz']), _p(aa.dense.bias), _p(x), _p(aa.LayerNorm.weight),
-                     _p(aa.LayerNorm.bias), aa.LayerNorm.eps, R, d, T, p_h, _p(lb['m_a']), rngp, base + 3, _p(lb['h']),
-                     _p(lb['st_a']), st)
-            if self.tc:
-                ops.linear_tc(lb['h'], R, ff.dense_1.weight, I, d, 1, None, lb['z1'], I)
-            else:
+                LIB.call('acsr_bias_dropout_res_ln_fwd', _p(lb['hz']), _p(aa.dense.bias), _p(x), _p(aa.LayerNorm.weight),
+                         _p(aa.LayerNorm.bias), aa.LayerNorm.eps, R, d, T, p_h, _p(lb['m_a']), rngp, base + 3, _p(lb['h']),
+                         _p(lb['st_a']), st)
                 torch.mm(lb['h'], ff.dense_1.weight.t(), out=lb['z1'])
-            LIB.call('acsr_bias_act_fwd', _p(lb['z1']), _p(ff.dense_1.bias), R, I, act_id, _p(lb['a1']), st)
-            torch.mm(lb['a1'], ff.dense_2.weight.t(), out=lb['z2'])
-            lb['m_f'] = mask2(l, 'D7', 'D6', last)
-            LIB.call('acsr_bias_dropout_res_ln_fwd', _p(lb['z2']), _p(ff.dense_2.bias), _p(lb['h']), _p(ff.LayerNorm.weight),
-                     _p(ff.LayerNorm.bias), ff.LayerNorm.eps, R, d, R, p_h, _p(lb['m_f']), rngp, base + 5, _p(lb['out']),
-                     _p(lb['st_f']), st)
+                LIB.call('acsr_bias_act_fwd', _p(lb['z1']), _p(ff.dense_1.bias), R, I, act_id, _p(lb['a1']), st)
+                torch.mm(lb['a1'], ff.dense_2.weight.t(), out=lb['z2'])
+                LIB.call('acsr_bias_dropout_res_ln_fwd', _p(lb['z2']), _p(ff.dense_2.bias), _p(lb['h']), _p(ff.LayerNorm.weight),
+                         _p(ff.LayerNorm.bias), ff.LayerNorm.eps, R, d, R, p_h, _p(lb['m_f']), rngp, base + 5, _p(lb['out']),
+                         _p(lb['st_f']), st)
             x = lb['out'][:T]
         last_out = b['layers'][N - 1]['out']
         # rows [0,B) calibrated, [B,2B) attacked  (the kernel's first pointer fills the first B rows)
@@ -213,12 +222,14 @@ class FusedTrainStep(object):
                      _p(b['row_scale']), 2 * B, V, d, passes, _p(b['Gt']), 2 * B, st)
             b['d_out2'].zero_()
             LIB.call('acsr_linear_wgrad', _p(b['Gt']), _p(E), V, 2 * B, d, _p(b['d_out2']), None, st)
+            # dE += Gt[:, :B] . out[:B]: only the calibrated rows train the item table
             if side is not None:
                 side.wait_stream(main)
-                with torch.cuda.stream(side):
+            with torch.cuda.stream(side if side is not None else main):
+                if self.tc and B <= 256:
+                    ops.linear_tok(b['Gt'], V, B, b['out2'], d, E.grad, d, ldx=2 * B, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
+                else:
                     E.grad.addmm_(b['Gt'][:, :B], b['out2'][:B])
-            else:
-                E.grad.addmm_(b['Gt'][:, :B], b['out2'][:B])       # only the calibrated rows train the item table
         d_out, d_x = b['d_out'], b['d_x']
         d_out.zero_()
         LIB.call('acsr_gather_last_bwd', _p(b['d_out2']), _p(ln, torch.int64), B, L, d, _p(d_out[:T]), _p(d_out[T:]), st)
@@ -239,15 +250,18 @@ class FusedTrainStep(object):
                      _p(ff.LayerNorm.bias.grad), st)
             sst = fork()
             LIB.call('acsr_linear_wgrad', _p(lb['d_z2']), _p(lb['a1']), T, d, I, _p(ff.dense_2.weight.grad), None, sst)
-            if self.tc:                                      # d_a1 = d_z2.W2 : Wt[i][c] = W2[c*I + i]
-                ops.linear_tc(lb['d_z2'], T2, ff.dense_2.weight, I, 1, I, None, b['d_a1'], I)
+            if self.tc:                                      # d_a1 = d_z2.W2 : the weight is read transposed
+                ops.linear_tok(lb['d_z2'], T2, d, ff.dense_2.weight, I, b['d_a1'], I, w_sn=1, w_sk=I, wkb=64 * I)
             else:
                 torch.mm(lb['d_z2'], ff.dense_2.weight, out=b['d_a1'])
             LIB.call('acsr_bias_act_bwd', _p(b['d_a1']), _p(lb['z1']), _p(ff.dense_1.bias), T2, I, act_id, P, T, _p(lb['d_z1']),
                      _p(ff.dense_1.bias.grad), st)
             sst = fork()
             LIB.call('acsr_linear_wgrad', _p(lb['d_z1']), _p(lb['h']), T, I, d, _p(ff.dense_1.weight.grad), None, sst)
-            b['d_h'].addmm_(lb['d_z1'], ff.dense_1.weight)
+            if self.tc:
+                ops.linear_tok(lb['d_z1'], T2, I, ff.dense_1.weight, d, b['d_h'], d, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
+            else:
+                b['d_h'].addmm_(lb['d_z1'], ff.dense_1.weight)
             # attention output projection
             LIB.call('acsr_bias_dropout_res_ln_bwd', _p(b['d_h']), _p(lb['hz']), _p(aa.dense.bias), _p(x),
                      _p(aa.LayerNorm.weight), _p(lb['st_a']), T2, d, P, T, T, p_h, _p(lb['m_a']), rngp, base + 3,
@@ -255,7 +269,7 @@ class FusedTrainStep(object):
             sst = fork()
             LIB.call('acsr_linear_wgrad', _p(lb['d_hz']), _p(lb['ctx']), T, d, d, _p(aa.dense.weight.grad), None, sst)
             if self.tc:
-                ops.linear_tc(lb['d_hz'], T2, aa.dense.weight, d, 1, d, None, b['d_ctx'], d)
+                ops.linear_tok(lb['d_hz'], T2, d, aa.dense.weight, d, b['d_ctx'], d, w_sn=1, w_sk=d, wkb=64 * d)
             else:
                 torch.mm(lb['d_hz'], aa.dense.weight, out=b['d_ctx'])
             # fused attention backward
@@ -277,8 +291,8 @@ class FusedTrainStep(object):
             st3 = self._stacked(l)
             if st3 is not None:
                 if self.tc:
-                    ops.linear_tc(lb['d_aqk'], T2, st3['Waqk'], d, 1, d, None, lb['d_qkv'], d, accumulate=True, batch=2,
-                                  sx=T2 * d, sw=d * d, sb=0, sy=T2 * d)
+                    ops.linear_tok(lb['d_aqk'], T2, d, st3['Waqk'], d, lb['d_qkv'], d, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True,
+                                   batch=2, sx=T2 * d, sw=d * d, sb=0, sy=T2 * d)
                 else:
                     lb['d_qkv'][:2].baddbmm_(lb['d_aqk'], st3['Waqk'])
                 # attack transforms are trained by the attacked-loss stream (rows [T,2T))
@@ -293,7 +307,11 @@ class FusedTrainStep(object):
                 sst = fork()
                 LIB.call('acsr_linear_wgrad', _p(lb['d_ak'][T:]), _p(lb['mk']), T, d, d, _p(akt.weight.grad), _p(akt.bias.grad), sst)
             if gate:
-                lb['d_mq'].addmm_(lb['d_gl'], layer.gate.weight)
+                if self.tc:
+                    ops.linear_tok(lb['d_gl'], T2, L, layer.gate.weight, d, lb['d_mq'], d, ldx=L, w_sn=1, w_sk=d, wkb=64 * d,
+                                   accumulate=True)
+                else:
+                    lb['d_mq'].addmm_(lb['d_gl'], layer.gate.weight)
                 sst = fork()
                 LIB.call('acsr_linear_wgrad', _p(lb['d_gl']), _p(lb['mq']), T, L, d, _p(layer.gate.weight.grad),
                          _p(layer.gate.bias.grad), sst)
@@ -305,19 +323,15 @@ class FusedTrainStep(object):
                 for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
                     sst = fork()
                     LIB.call('acsr_linear_wgrad', _p(lb[dk]), _p(x), T, d, d, _p(lin.weight.grad), _p(lin.bias.grad), sst)
-            if l > 0:
-                for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
-                    if self.tc:
-                        ops.linear_tc(lb[dk], T2, lin.weight, d, 1, d, None, d_x, d, accumulate=True)
-                    else:
-                        d_x.addmm_(lb[dk], lin.weight)
-                d_out, d_x = d_x, d_out                       # this layer's input gradient is the next one's output gradient
+            rows_x = T2 if l > 0 else T                      # below the first layer only the calibrated stream trains anything
+            if self.tc and st3 is not None:                  # d_x += [d_mq d_mk d_mv] . [Wq; Wk; Wv]: one K = 3d GEMM
+                ops.linear_tok(lb['d_qkv'], rows_x, 3 * d, st3['Wqkv'], d, d_x, d, ldx=d, xkb=T2 * d, w_sn=1, w_sk=d, wkb=d * d,
+                               accumulate=True)
             else:
                 for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
-                    if self.tc:                               # below the first layer only the calibrated stream trains anything
-                        ops.linear_tc(lb[dk], T, lin.weight, d, 1, d, None, d_x, d, accumulate=True)
-                    else:
-                        d_x[:T].addmm_(lb[dk][:T], lin.weight)
+                    d_x[:rows_x].addmm_(lb[dk][:rows_x], lin.weight)
+            if l > 0:
+                d_out, d_x = d_x, d_out                       # this layer's input gradient is the next one's output gradient
         if side is not None:
             main.wait_stream(side)                            # join: every weight gradient landed (dE is shared with K1 bwd)
         LIB.call('acsr_embed_ln_dropout_bwd', _p(d_x[:T]), _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight),
