@@ -72,6 +72,7 @@ class ACSASRec(SequentialRecommender):
 
         # B200 runtime state (not parameters, not in the state_dict)
         self.logits_passes = int(cfg_get(config, 'logits_passes', 3))
+        self.step_branches = int(cfg_get(config, 'step_branches', 1))     # parallel sequence groups of the fused step (measured: no gain at B=256)
         self._seed = int(cfg_get(config, 'seed', 2020))
         self._rng = None
         self._debug_rand = None      # {key: tensor}: explicit dropout masks / noise for parity tests

@@ -10,6 +10,13 @@ accumulates straight into the flat gradient buffer (no autograd tape, no tempora
 Dead work the reference performs is skipped without changing any result: the attacked branch of
 non-final layers, the attacked branch's weight gradients, the attacked stream below the first layer.
 
+At B=256 every kernel of the step is latency-bound (a few hundred CTAs, ~10 us each), so the step is
+laid out as a DAG instead of a chain: the batch is cut into `step_branches` groups of sequences whose
+encoder forward and backward run on parallel CUDA streams (parallel branches of the captured graph;
+sequences only meet in the full-catalogue cross entropy, in the penalty norm and in the gradient
+buffers, which are accumulated with atomics), and inside a branch the weight-gradient reductions,
+which nothing consumes before Adam, run on a second stream next to the input-gradient chain.
+
 All buffers are allocated once per batch size, so the step is CUDA-graph capturable as is.
 """
 import math
@@ -21,8 +28,15 @@ from ._lib import LIB
 from .ops import _p, _stream
 
 
-def _w(lin):
-    return lin.weight, lin.bias
+class _RandSlice(object):
+    """explicit masks / noise of a parity test ({key: full-batch tensor}), restricted to one branch's sequences."""
+
+    def __init__(self, rand, sl):
+        self.rand, self.sl = rand, sl
+
+    def get(self, key):
+        t = self.rand.get(key)
+        return None if t is None else t[self.sl].contiguous()
 
 
 class FusedTrainStep(object):
@@ -36,45 +50,63 @@ class FusedTrainStep(object):
         # other widths stay library GEMMs + the row-wise epilogue kernels
         self.tc = (bool(getattr(model, 'tc_linear', True)) and model.hidden_size == 64 and model.inner_size <= 256
                    and model.inner_size % 4 == 0)
-        # weight-gradient reductions have no consumer before Adam: they run on a second stream (a parallel branch of
-        # the captured graph) and overlap the dependent chain of input-gradient kernels
         self.overlap_wgrad = bool(getattr(model, 'overlap_wgrad', True))
-        self._side = None
+        self.n_branches = int(getattr(model, 'step_branches', 1))
+        self._streams = {}
 
     # ------------------------------------------------------------------------------------------
-    def _buffers(self, B, L, dev):
-        key = (B, L)
+    def _stream_for(self, dev, key):
+        if key not in self._streams:
+            self._streams[key] = torch.cuda.Stream(device=dev)
+        return self._streams[key]
+
+    def _branch_buffers(self, Bs, L, dev, idx):
+        """activations saved for the backward + gradient buffers of one group of Bs sequences."""
+        key = ('branch', Bs, L, idx)
         if key in self.buf:
             return self.buf[key]
         m = self.m
-        d, I, N, V = m.hidden_size, m.inner_size, m.n_layers, m.n_items
-        T = B * L
+        d, I, N = m.hidden_size, m.inner_size, m.n_layers
+        T = Bs * L
 
         def f(*s):
             return torch.empty(s, dtype=torch.float32, device=dev)
-        b = dict(T=T, x0=f(T, d), st_e=f(T, 2), pen=torch.zeros(N, dtype=torch.float64, device=dev), layers=[])
+        b = dict(T=T, x0=f(T, d), st_e=f(T, 2), layers=[])
         for l in range(N):
             R = 2 * T if l == N - 1 else T
             qkv, aqk = f(3, T, d), f(2, T, d)
-            b['layers'].append(dict(qkv=qkv, aqk=aqk, mq=qkv[0], mk=qkv[1], mv=qkv[2], aq=aqk[0], ak=aqk[1], gl=f(T, L), ctx=f(R, d),
-                                    hz=f(R, d), st_a=f(R, 2), h=f(R, d), z1=f(R, I), a1=f(R, I), z2=f(R, d), st_f=f(R, 2),
-                                    out=f(R, d)))
-        nc = ops.logits_num_chunks(2 * B, V)
-        b.update(out2=f(2 * B, d), partial=f(2 * B, nc, 2), lse=f(2 * B), tgt=f(2 * B), row_loss=f(2 * B), loss=f(2),
-                 Gt=f(V, 2 * B), d_out2=f(2 * B, d), target2=torch.empty(2 * B, dtype=torch.int64, device=dev),
-                 row_scale=torch.cat((torch.full((B,), 1.0 / B), torch.full((B,), -1.0 / B))).to(dev))
-        for n, w in (('d_out', d), ('d_a1', I), ('d_h', d), ('d_x', d), ('d_ctx', d)):
-            b[n] = f(2 * T, w)
-        # buffers read by the weight-gradient kernels are per layer: the side stream may still be reading layer l's
-        # while the main stream already writes layer l-1's
-        for lb in b['layers']:
+            lb = dict(qkv=qkv, aqk=aqk, mq=qkv[0], mk=qkv[1], mv=qkv[2], aq=aqk[0], ak=aqk[1], gl=f(T, L), ctx=f(R, d),
+                      hz=f(R, d), st_a=f(R, 2), h=f(R, d), z1=f(R, I), a1=f(R, I), z2=f(R, d), st_f=f(R, 2), out=f(R, d))
+            # buffers read by the weight-gradient kernels are per layer: the side stream may still be reading layer l's
+            # while the branch stream already writes layer l-1's
             for n, w in (('d_z2', d), ('d_z1', I), ('d_hz', d), ('d_gl', L)):
                 lb[n] = f(2 * T, w)
             lb['d_qkv'], lb['d_aqk'] = f(3, 2 * T, d), f(2, 2 * T, d)
             lb['d_mq'], lb['d_mk'], lb['d_mv'] = lb['d_qkv'][0], lb['d_qkv'][1], lb['d_qkv'][2]
             lb['d_aq'], lb['d_ak'] = lb['d_aqk'][0], lb['d_aqk'][1]
+            b['layers'].append(lb)
+        for n, w in (('d_out', d), ('d_a1', I), ('d_h', d), ('d_x', d), ('d_ctx', d)):
+            b[n] = f(2 * T, w)
         self.buf[key] = b
         return b
+
+    def _joint_buffers(self, B, dev):
+        """full-batch buffers of the part where the sequences meet: last-position outputs, cross entropy, penalty."""
+        key = ('joint', B)
+        if key in self.buf:
+            return self.buf[key]
+        m = self.m
+        d, N, V = m.hidden_size, m.n_layers, m.n_items
+
+        def f(*s):
+            return torch.empty(s, dtype=torch.float32, device=dev)
+        nc = ops.logits_num_chunks(2 * B, V)
+        j = dict(pen=torch.zeros(N, dtype=torch.float64, device=dev), out2=f(2 * B, d), partial=f(2 * B, nc, 2), lse=f(2 * B),
+                 tgt=f(2 * B), row_loss=f(2 * B), loss=f(2), Gt=f(V, 2 * B), d_out2=f(2 * B, d),
+                 target2=torch.empty(2 * B, dtype=torch.int64, device=dev),
+                 row_scale=torch.cat((torch.full((B,), 1.0 / B), torch.full((B,), -1.0 / B))).to(dev))
+        self.buf[key] = j
+        return j
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -86,16 +118,94 @@ class FusedTrainStep(object):
         pos_items = interaction[m.POS_ITEM_ID]
         B, L = seq.shape
         dev = seq.device
-        b = self._buffers(B, L, dev)
-        T, d, I, N, V, H = b['T'], m.hidden_size, m.inner_size, m.n_layers, m.n_items, m.n_heads
-        dh = d // H
+        d, N, V = m.hidden_size, m.n_layers, m.n_items
         rt = m._runtime(dev)
         rng, rand = rt.rng, rt.rand
+        training = m.training
+        E = m.item_embedding.weight
+        main = torch.cuda.current_stream()
+        nb = self.n_branches if (self.n_branches > 1 and B % self.n_branches == 0) else 1
+        Bs = B // nb
+        jb = self._joint_buffers(B, dev)
+        branches = []
+        for s in range(nb):
+            sl = slice(s * Bs, (s + 1) * Bs)
+            branches.append(dict(idx=s, sl=sl, seq=seq[sl], ln=ln[sl], buf=self._branch_buffers(Bs, L, dev, s),
+                                 rand=rand if (rand is None or nb == 1) else _RandSlice(rand, sl),
+                                 stream=main if s == 0 else self._stream_for(dev, ('branch', s)),
+                                 side=self._stream_for(dev, ('side', s)) if self.overlap_wgrad else None))
+        rng.advance()
+        jb['pen'].zero_()
+        # ---------------- forward: parallel branches ----------------
+        for br in branches:
+            if br['stream'] is not main:
+                br['stream'].wait_stream(main)
+            with torch.cuda.stream(br['stream']):
+                self._forward_branch(br, jb, B, L, rt, training)
+        for br in branches:
+            if br['stream'] is not main:
+                main.wait_stream(br['stream'])
+        # ---------------- where the sequences meet: full-catalogue cross entropy + penalty norm ----------------
+        st = _stream()
+        torch.cat((pos_items, pos_items), out=jb['target2'])
+        passes = m.logits_passes
+        vst = None
+        if self.vp is not None:       # all-gather out -> shard-local partial CE -> all-gather (max, sum-exp) -> combine
+            loss2, vst = self.vp.ce_forward(jb['out2'], E, jb['target2'], 2)
+            jb['loss'].copy_(loss2)
+        else:
+            LIB.call('acsr_logits_ce_partial', _p(jb['out2']), _p(E), 2 * B, V, d, passes, _p(jb['partial']), st)
+            LIB.call('acsr_ce_finalize', _p(jb['partial']), jb['partial'].shape[1], _p(jb['out2']), _p(E),
+                     _p(jb['target2'], torch.int64), 2 * B, d, V, 0, 2, _p(jb['lse']), _p(jb['tgt']), _p(jb['row_loss']),
+                     _p(jb['loss']), st)
+        pen_norm = torch.sqrt(jb['pen'].to(torch.float32))
+        w = m.mask_loss_weight.detach()[0] if m.trainable_mask_loss_weight else float(m.mask_loss_weight)
+        loss_cal = jb['loss'][0]
+        loss_att = -jb['loss'][1] + pen_norm.mean() * w
+        if not training:
+            return loss_att, loss_cal
+        # ---------------- backward ----------------
+        dpen = (w / (2.0 * N)) / pen_norm                     # d loss_att / d pen_sq_l
+        opt.zero_grad()
+        if self.vp is not None:       # shard-local G^T, reduce-scatter of d_out, dE into the owner's rows
+            jb['d_out2'].copy_(self.vp.ce_backward(vst, E, jb['row_scale'], E.grad, table_half=0, n_groups=2))
+        else:
+            LIB.call('acsr_logits_ce_grad', _p(jb['out2']), _p(E), _p(jb['lse']), _p(jb['target2'], torch.int64),
+                     _p(jb['row_scale']), 2 * B, V, d, passes, _p(jb['Gt']), 2 * B, st)
+            jb['d_out2'].zero_()
+            LIB.call('acsr_linear_wgrad', _p(jb['Gt']), _p(E), V, 2 * B, d, _p(jb['d_out2']), None, st)
+        for br in branches:
+            if br['stream'] is not main:
+                br['stream'].wait_stream(main)
+        if self.vp is None:
+            # dE += Gt[:, :B] . out[:B]: only the calibrated rows train the item table.  It reads and writes dE without
+            # atomics, so every branch's embedding scatter waits for it (dE_done).
+            if self.tc and B <= 256:
+                ops.linear_tok(jb['Gt'], V, B, jb['out2'], d, E.grad, d, ldx=2 * B, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
+            else:
+                E.grad.addmm_(jb['Gt'][:, :B], jb['out2'][:B])
+        dE_done = torch.cuda.Event()
+        dE_done.record(main)
+        for br in branches:
+            with torch.cuda.stream(br['stream']):
+                self._backward_branch(br, jb, B, L, rt, dpen, dE_done)
+        for br in branches:
+            if br['stream'] is not main:
+                main.wait_stream(br['stream'])
+        return loss_att, loss_cal
+
+    # ------------------------------------------------------------------------------------------
+    def _forward_branch(self, br, jb, B, L, rt, training):
+        m = self.m
+        b, seq, ln, s = br['buf'], br['seq'], br['ln'], br['idx']
+        Bs = seq.shape[0]
+        T, d, I, N, V, H = b['T'], m.hidden_size, m.inner_size, m.n_layers, m.n_items, m.n_heads
+        dh = d // H
+        rng, rand = rt.rng, br['rand']
         rngp = rng.ptr
         st = _stream()
-        training = m.training
         p_h = m.dropout.p if training else 0.0
-        rng.advance()
+        soff = 4096 * s                                           # Philox stream ids of this branch
 
         def mask(key):
             return None if (rand is None or p_h == 0.0) else rand.get(key)
@@ -108,22 +218,19 @@ class FusedTrainStep(object):
 
         E = m.item_embedding.weight
         posw = m.position_embedding.weight if m.use_position_embedding else None
-        eps = m.LayerNorm.eps
-        # ---------------- forward ----------------
-        me = mask('emb')
+        b['me'] = mask('emb')
         LIB.call('acsr_embed_ln_dropout_fwd', _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight), _p(m.LayerNorm.bias),
-                 eps, T, L, d, V, p_h, _p(me), rngp, 1, _p(b['x0']), _p(b['st_e']), st)
-        b['pen'].zero_()
+                 m.LayerNorm.eps, T, L, d, V, p_h, _p(b['me']), rngp, soff + 1, _p(b['x0']), _p(b['st_e']), st)
         x = b['x0']
-        xs = []
+        b['xs'] = []
         act_id = ops.ACT_IDS[m.hidden_act]
         for l, layer in enumerate(m.trm_encoder.layer):
             last = l == N - 1
             R = 2 * T if last else T
             lb = b['layers'][l]
             aa, ff = layer.attack_attention, layer.feed_forward
-            base = 16 * (l + 1)
-            xs.append(x)
+            base = soff + 16 * (l + 1)
+            b['xs'].append(x)
             st3 = self._stacked(l)
             if st3 is not None and self.tc:                   # stacked Q/K/V and attack pair: two batched tcgen05 launches
                 ops.linear_tok(x, T, d, st3['Wqkv'], d, lb['qkv'], d, bias=st3['bqkv'], batch=3, sx=0, sw=d * d, sb=d, sy=T * d)
@@ -149,15 +256,16 @@ class FusedTrainStep(object):
                     torch.addmm(layer.gate.bias, lb['mq'], layer.gate.weight.t(), out=lb['gl'])
             elif layer.combine_option == 'annealing':
                 comb_scalar = math.exp(-layer.anneal_step / 100000)
-                layer.anneal_step += 1
+                if s == 0:
+                    layer.anneal_step += 1
             p_attn = aa.attn_dropout.p if training else 0.0
-            lb['attn_args'] = self._attn_args(layer, lb, seq, B, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base)
+            lb['attn_args'] = self._attn_args(layer, lb, seq, Bs, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base)
             ctx_cal, ctx_att = lb['ctx'][:T], (lb['ctx'][T:] if last else None)
-            LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal), b['pen'][l:].data_ptr(), None, st)
+            LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal), jb['pen'][l:].data_ptr(), None, st)
             lb['m_a'] = mask2(l, 'D5', 'D4', last)
             lb['m_f'] = mask2(l, 'D7', 'D6', last)
             if self.tc:
-                # out-projection + bias + dropout + residual + LayerNorm in one kernel; FFN: GEMM + bias + activation, then
+                # out-projection + bias + dropout + residual + LayerNorm in one kernel; FFN: GEMM, bias + activation, then
                 # GEMM + bias + dropout + residual + LayerNorm
                 ops.linear_tok_bdrl(lb['ctx'], R, d, aa.dense.weight, aa.dense.bias, x, T, aa.LayerNorm.weight, aa.LayerNorm.bias,
                                     aa.LayerNorm.eps, p_h, lb['m_a'], rngp, base + 3, lb['hz'], lb['h'], lb['st_a'])
@@ -181,32 +289,26 @@ class FusedTrainStep(object):
                          _p(lb['st_f']), st)
             x = lb['out'][:T]
         last_out = b['layers'][N - 1]['out']
-        # rows [0,B) calibrated, [B,2B) attacked  (the kernel's first pointer fills the first B rows)
-        LIB.call('acsr_gather_last_fwd', _p(last_out[:T]), _p(last_out[T:]), _p(ln, torch.int64), B, L, d, _p(b['out2']), st)
-        torch.cat((pos_items, pos_items), out=b['target2'])
-        passes = m.logits_passes
-        vst = None
-        if self.vp is not None:       # all-gather out -> shard-local partial CE -> all-gather (max, sum-exp) -> combine
-            loss2, vst = self.vp.ce_forward(b['out2'], E, b['target2'], 2)
-            b['loss'].copy_(loss2)
-        else:
-            LIB.call('acsr_logits_ce_partial', _p(b['out2']), _p(E), 2 * B, V, d, passes, _p(b['partial']), st)
-            LIB.call('acsr_ce_finalize', _p(b['partial']), b['partial'].shape[1], _p(b['out2']), _p(E),
-                     _p(b['target2'], torch.int64), 2 * B, d, V, 0, 2, _p(b['lse']), _p(b['tgt']), _p(b['row_loss']),
-                     _p(b['loss']), st)
-        pen32 = b['pen'].to(torch.float32)
-        pen_norm = torch.sqrt(pen32)
-        w = m.mask_loss_weight.detach()[0] if m.trainable_mask_loss_weight else float(m.mask_loss_weight)
-        loss_cal = b['loss'][0]
-        loss_att = -b['loss'][1] + pen_norm.mean() * w
-        if not training:
-            return loss_att, loss_cal
-        # ---------------- backward ----------------
-        dpen = (w / (2.0 * N)) / pen_norm                     # d loss_att / d pen_sq_l
+        # rows [0,B) of out2 calibrated, [B,2B) attacked; this branch owns the rows of its sequences in both halves
+        lo = br['sl'].start
+        LIB.call('acsr_gather_last_fwd', None, _p(last_out[:T]), _p(ln, torch.int64), Bs, L, d, _p(jb['out2'][lo:lo + Bs]), st)
+        LIB.call('acsr_gather_last_fwd', None, _p(last_out[T:]), _p(ln, torch.int64), Bs, L, d, _p(jb['out2'][B + lo:B + lo + Bs]), st)
+
+    # ------------------------------------------------------------------------------------------
+    def _backward_branch(self, br, jb, B, L, rt, dpen, dE_done):
+        m = self.m
+        b, seq, ln, s = br['buf'], br['seq'], br['ln'], br['idx']
+        Bs = seq.shape[0]
+        T, d, I, N, V = b['T'], m.hidden_size, m.inner_size, m.n_layers, m.n_items
+        rngp = rt.rng.ptr
+        st = _stream()
         main = torch.cuda.current_stream()
-        if self.overlap_wgrad and self._side is None:
-            self._side = torch.cuda.Stream(device=dev)
-        side = self._side if self.overlap_wgrad else None
+        side = br['side']
+        p_h = m.dropout.p
+        soff = 4096 * s
+        act_id = ops.ACT_IDS[m.hidden_act]
+        E = m.item_embedding.weight
+        posw = m.position_embedding.weight if m.use_position_embedding else None
 
         def fork():
             """-> stream handle for a weight-gradient launch: the side stream, ordered after everything enqueued so far"""
@@ -214,25 +316,12 @@ class FusedTrainStep(object):
                 return st
             side.wait_stream(main)
             return side.cuda_stream
-        opt.zero_grad()
-        if self.vp is not None:       # shard-local G^T, reduce-scatter of d_out, dE into the owner's rows
-            b['d_out2'].copy_(self.vp.ce_backward(vst, E, b['row_scale'], E.grad, table_half=0, n_groups=2))
-        else:
-            LIB.call('acsr_logits_ce_grad', _p(b['out2']), _p(E), _p(b['lse']), _p(b['target2'], torch.int64),
-                     _p(b['row_scale']), 2 * B, V, d, passes, _p(b['Gt']), 2 * B, st)
-            b['d_out2'].zero_()
-            LIB.call('acsr_linear_wgrad', _p(b['Gt']), _p(E), V, 2 * B, d, _p(b['d_out2']), None, st)
-            # dE += Gt[:, :B] . out[:B]: only the calibrated rows train the item table
-            if side is not None:
-                side.wait_stream(main)
-            with torch.cuda.stream(side if side is not None else main):
-                if self.tc and B <= 256:
-                    ops.linear_tok(b['Gt'], V, B, b['out2'], d, E.grad, d, ldx=2 * B, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
-                else:
-                    E.grad.addmm_(b['Gt'][:, :B], b['out2'][:B])
+
         d_out, d_x = b['d_out'], b['d_x']
         d_out.zero_()
-        LIB.call('acsr_gather_last_bwd', _p(b['d_out2']), _p(ln, torch.int64), B, L, d, _p(d_out[:T]), _p(d_out[T:]), st)
+        lo = br['sl'].start
+        LIB.call('acsr_gather_last_bwd', _p(jb['d_out2'][lo:lo + Bs]), _p(ln, torch.int64), Bs, L, d, None, _p(d_out[:T]), st)
+        LIB.call('acsr_gather_last_bwd', _p(jb['d_out2'][B + lo:B + lo + Bs]), _p(ln, torch.int64), Bs, L, d, None, _p(d_out[T:]), st)
         T2 = 2 * T
         for l in reversed(range(N)):
             last = l == N - 1
@@ -240,8 +329,8 @@ class FusedTrainStep(object):
             lb = b['layers'][l]
             layer = m.trm_encoder.layer[l]
             aa, ff = layer.attack_attention, layer.feed_forward
-            base = 16 * (l + 1)
-            x = xs[l]
+            base = soff + 16 * (l + 1)
+            x = b['xs'][l]
             gate = layer.combine_option == 'gate'
             # FFN
             LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_out), _p(lb['z2']), _p(ff.dense_2.bias), _p(lb['h']),
@@ -332,12 +421,12 @@ class FusedTrainStep(object):
                     d_x[:rows_x].addmm_(lb[dk][:rows_x], lin.weight)
             if l > 0:
                 d_out, d_x = d_x, d_out                       # this layer's input gradient is the next one's output gradient
-        if side is not None:
-            main.wait_stream(side)                            # join: every weight gradient landed (dE is shared with K1 bwd)
+        main.wait_event(dE_done)                              # the dE GEMM is a plain read-modify-write of the table gradient
         LIB.call('acsr_embed_ln_dropout_bwd', _p(d_x[:T]), _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight),
-                 _p(b['st_e']), T, L, d, V, p_h, _p(me), rngp, 1, _p(E.grad), _p(posw.grad if posw is not None else None),
+                 _p(b['st_e']), T, L, d, V, p_h, _p(b['me']), rngp, soff + 1, _p(E.grad), _p(posw.grad if posw is not None else None),
                  _p(m.LayerNorm.weight.grad), _p(m.LayerNorm.bias.grad), st)
-        return loss_att, loss_cal
+        if side is not None:
+            main.wait_stream(side)                            # join: every weight gradient of this branch landed
 
     def _stacked(self, l):
         """stacked views [3,d,d]/[2,d,d] of the Q/K/V and attack-pair parameters (adjacent in FlatAdam's layout)."""

@@ -301,6 +301,32 @@ def test_fused_step_equals_autograd_step_full_batch(A):
         assert float((g0[n] - g1[n]).abs().max()) <= 2e-4 * scale + 1e-9, n
 
 
+@pytest.mark.parametrize('nb', [2, 4])
+def test_fused_step_branches_equal_single_chain(A, nb):
+    """the step cut into nb parallel sequence groups == the single chain (dropout off, injected noise)."""
+    cfg = O.default_cfg(hidden_dropout_prob=0.0, attn_dropout_prob=0.0)
+    V, B, L = 3001, 64, 50
+    params = O.init_params(cfg, V, seed=3)
+    seq, ln, pos = O.synth_batch(B, L, V, seed=6)
+    res = []
+    for branches in (1, nb):
+        config = make_config(A, cfg, fused_step=True)
+        model = A.ACSASRec(config, DS(V)).to('cuda')
+        model.load_state_dict({k: v.cuda() for k, v in params.items()})
+        g = torch.Generator().manual_seed(0)
+        model._debug_rand = {(l, 'noise'): torch.randn(B, cfg['n_heads'], L, L, generator=g).cuda() for l in range(cfg['n_layers'])}
+        trainer = A.ACSASRecTrainer(config, model)
+        trainer.fused.n_branches = branches
+        model.train()
+        inter = A.Interaction({'item_id_list': seq.cuda(), 'item_length': ln.cuda(), 'item_id': pos.cuda()})
+        la, lc = trainer.fused(inter)
+        torch.cuda.synchronize()
+        res.append((float(la), float(lc), trainer.optimizer.flat_grad.detach().cpu().clone()))
+    (a0, c0, g0), (a1, c1, g1) = res
+    assert abs(a0 - a1) < 1e-5 * abs(a0) and abs(c0 - c1) < 1e-5 * abs(c0)
+    assert float((g0 - g1).abs().max()) <= 1e-4 * float(g0.abs().max())
+
+
 def test_full_size_properties_million_item_catalogue(A):
     """BASELINE config #4 shape on one GPU (V=1,000,001, B=256): fused CE and fused top-k against the
     materialised scores of the same device GEMM (size-independent identities, no CPU reference needed)."""
