@@ -108,6 +108,10 @@ class ACSASRec(SequentialRecommender):
         dev = self.item_embedding.weight.device
         if not item_seq.is_cuda:
             raise ops.AcsrError('ACSASRec runs on CUDA only (got %s tensors); there is no CPU fallback' % item_seq.device)
+        fused = getattr(self, '_fused_step', None)
+        if (fused is not None and not self.training and not need_attacked and not torch.is_grad_enabled()
+                and item_seq.dim() == 2):
+            return fused.encode_eval(item_seq, item_seq_len), []      # eval: the fused forward (same kernels as training)
         rt = self._runtime(dev)
         if self.training:
             rt.rng.advance()

@@ -27,6 +27,34 @@ constexpr float kMaskNeg = -10000.0f;   // abstract_recommender.py:142
 constexpr float kOrderEps = 1e-24f;     // layers.py:719
 
 // ------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the step is a few microseconds long, so the
+// launch gap between dependent kernels is a large share of the chain.  Kernels are launched with
+// programmaticStreamSerializationAllowed and start with `pdl_launch_dependents(); ... pdl_wait();`:
+// the next kernel's CTAs are scheduled (and run their data-independent prologue: barrier init, TMEM
+// allocation, WEIGHT staging) while this one still runs; pdl_wait() returns once every kernel it
+// depends on has completed and its writes are visible.  Only parameters, which no kernel but Adam
+// (the last node of the step) writes, may be read before pdl_wait().  Off unless acsr_set_pdl(1) / ACSR_PDL=1:
+// the fused training step turns it on for its own launches (measured +1.5 %; the eval graph is slower with it).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+void pdl_set(int on);
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG.  key = seed, counter = (idx_lo, idx_hi, stream, step).
 // The same (seed, step, stream, idx) reproduces the same bits in forward and backward.
 // ------------------------------------------------------------------------------------
@@ -88,9 +116,27 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 // activation ids shared with the host (layers.py:764-773)
 enum Act { ACT_GELU = 0, ACT_RELU = 1, ACT_SWISH = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
 
+// Normal cdf / pdf for the erf GELU (layers.py:776-785) from ONE exponential: u = exp(-x^2/2) is the pdf (up to
+// 1/sqrt(2 pi)) and also the tail factor of erf(x/sqrt 2) = 1 - poly(t) * u, t = 1/(1 + p |x|/sqrt 2)
+// (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7: fp32 level).
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  float u;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(x * x * -0.72134752044448170368f));   // exp(-x^2/2)
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfa = 1.0f - poly * t * u;            // erf(|x|/sqrt 2)
+  cdf = 0.5f * (1.0f + copysignf(erfa, x));
+  pdf = 0.39894228040143267794f * u;
+}
+
 __device__ __forceinline__ float act_fwd(int act, float x) {
   switch (act) {
-    case ACT_GELU: return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    case ACT_GELU: { float cdf, pdf; gelu_parts(x, cdf, pdf); return x * cdf; }
     case ACT_RELU: return fmaxf(x, 0.0f);
     case ACT_SWISH: return x * sigmoidf_(x);
     case ACT_TANH: return tanhf(x);
@@ -99,11 +145,7 @@ __device__ __forceinline__ float act_fwd(int act, float x) {
 }
 __device__ __forceinline__ float act_bwd(int act, float x) {   // d act / d x
   switch (act) {
-    case ACT_GELU: {
-      float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-      float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-      return cdf + x * pdf;
-    }
+    case ACT_GELU: { float cdf, pdf; gelu_parts(x, cdf, pdf); return cdf + x * pdf; }
     case ACT_RELU: return x > 0.0f ? 1.0f : 0.0f;
     case ACT_SWISH: { float s = sigmoidf_(x); return s + x * s * (1.0f - s); }
     case ACT_TANH: { float t = tanhf(x); return 1.0f - t * t; }

@@ -3,6 +3,7 @@
 #include "../../include/acsr.h"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 namespace acsr {
 static thread_local char g_err[512] = "";
@@ -23,17 +24,30 @@ int check_launch(const char* what) {
   return ACSR_OK;
 }
 
-__global__ void rng_advance_kernel(RngState* s) { s->step += 1ull; }
+static int g_pdl = -1;       // -1: not decided yet (environment), 0 / 1: set
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("ACSR_PDL");
+    g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl == 1;
+}
+void pdl_set(int on) { g_pdl = on ? 1 : 0; }
+
+__global__ void rng_advance_kernel(RngState* s) {
+  pdl_launch_dependents();
+  pdl_wait(); s->step += 1ull; }
 }  // namespace acsr
 
 extern "C" {
 int acsr_version(void) { return ACSR_ABI_VERSION; }
 const char* acsr_last_error(void) { return acsr::g_err; }
 int acsr_num_sms(void) { return acsr::kNumSMs; }
+int acsr_set_pdl(int on) { int was = acsr::pdl_enabled() ? 1 : 0; acsr::pdl_set(on); return was; }
 
 int acsr_rng_advance(void* rng, void* stream) {
   ACSR_REQUIRE(rng != nullptr, "acsr_rng_advance: rng is NULL");
-  acsr::rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((acsr::RngState*)rng);
+  launch_pdl(acsr::rng_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (acsr::RngState*)rng);
   return acsr::check_launch("acsr_rng_advance");
 }
 }

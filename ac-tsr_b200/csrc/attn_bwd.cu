@@ -382,6 +382,8 @@ __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm
 
 template <int DH, int NS>
 __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_kernel(const AttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_f[];
   constexpr int dhp = DH + 4;
   const int L = p.L, LP = (L + 3) & ~3;
@@ -474,7 +476,7 @@ static int launch_bwd(const AttnParams& p, cudaStream_t st) {
   size_t smem = bwd_smem_bytes(p.L, DH, NS);
   int rc = prep_kernel(attn_bwd_kernel<DH, NS>, smem, "attn_calib_bwd");
   if (rc) return rc;
-  attn_bwd_kernel<DH, NS><<<p.B * p.H, kAttnThreads, smem, st>>>(p);
+  launch_pdl(attn_bwd_kernel<DH, NS>, dim3(p.B * p.H), dim3(kAttnThreads), smem, st, p);
   return check_launch("attn_calib_bwd");
 }
 

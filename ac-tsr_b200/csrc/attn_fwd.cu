@@ -98,6 +98,8 @@ __device__ __forceinline__ void fwd_rows(const AttnParams& p, const AttnSmem& sm
 
 template <int DH>
 __global__ void __launch_bounds__(kAttnThreads, 4) attn_fwd_kernel(const AttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_f[];
   const int L = p.L, LP = (L + 3) & ~3;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -144,7 +146,7 @@ static int launch_fwd(const AttnParams& p, cudaStream_t st) {
   size_t smem = fwd_smem_bytes(p.L, DH);
   int rc = prep_kernel(attn_fwd_kernel<DH>, smem, "attn_calib_fwd");
   if (rc) return rc;
-  attn_fwd_kernel<DH><<<p.B * p.H, kAttnThreads, smem, st>>>(p);
+  launch_pdl(attn_fwd_kernel<DH>, dim3(p.B * p.H), dim3(kAttnThreads), smem, st, p);
   return check_launch("attn_calib_fwd");
 }
 

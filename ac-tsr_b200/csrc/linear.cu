@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(kWgThreads)
 linear_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int T, int N, int K, int tok_per_cta,
                     int tiles_k, float* __restrict__ dW, float* __restrict__ db, long long strY, long long strX, long long strW,
                     long long strB) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int TILE = 8 * R;
   // batched launch: blockIdx.z selects one independent (dY, X, dW, db) problem
   dY += blockIdx.z * strY; X += blockIdx.z * strX; dW += blockIdx.z * strW;
@@ -139,9 +141,9 @@ static int launch_wgrad(const float* dY, const float* X, int T, int N, int K, fl
   tok = (tok + kWgSlab - 1) / kWgSlab * kWgSlab;
   dim3 grid((T + tok - 1) / tok, tiles_n * tiles_k, batch);
   if (big)
-    linear_wgrad_kernel<4><<<grid, kWgThreads, 0, stream>>>(dY, X, T, N, K, tok, tiles_k, dW, db, sY, sX, sW, sB);
+    launch_pdl(linear_wgrad_kernel<4>, dim3(grid), dim3(kWgThreads), 0, stream, dY, X, T, N, K, tok, tiles_k, dW, db, sY, sX, sW, sB);
   else
-    linear_wgrad_kernel<2><<<grid, kWgThreads, 0, stream>>>(dY, X, T, N, K, tok, tiles_k, dW, db, sY, sX, sW, sB);
+    launch_pdl(linear_wgrad_kernel<2>, dim3(grid), dim3(kWgThreads), 0, stream, dY, X, T, N, K, tok, tiles_k, dW, db, sY, sX, sW, sB);
   return check_launch(who);
 }
 

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
   uint64_t* tm_empty = bars + 6;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(a_full + s, 128); mbar_init(a_empty + s, 1);
@@ -98,19 +99,37 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<kLtTmemCols>(tmem_slot);
+  pdl_wait();                 // everything above overlaps the tail of the previous kernel
+  const bool is_loader = warp >= 2 && warp < 6;
+  const int lr = threadIdx.x - 64;            // loader: token row of the tile owned by this thread (0..127)
+  const bool x_vec_ok = (p.ldx & 3) == 0 && (p.xkb & 3) == 0 && ((reinterpret_cast<uintptr_t>(Xp) & 15) == 0);
+  // the loader warps put the loads of their first tile in flight while the other warps stage the weights
+  float4 xpre[kLtKB / 4];
+  if (is_loader && (int)blockIdx.x < p.m_tiles) {
+    const long long grow = (long long)blockIdx.x * kLtBM + lr;
+    const int kvalid = min(kLtKB, p.K);
+    const float* xrow = Xp + grow * p.ldx;
+#pragma unroll
+    for (int q = 0; q < kLtKB / 4; ++q) {
+      const int kc = (q + lr) & (kLtKB / 4 - 1);
+      xpre[q] = grow < p.rows ? lt_load4(xrow, kc * 4, kc * 4, kvalid, x_vec_ok) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
 
   // stationary weight block: rows n0 .. n0+NB of W (zero beyond N / K), split into hi/lo, canonical K-major layout
-  {
+  if (!is_loader) {
+    constexpr int kStagers = kLtThreads - 128;
+    const int sid = threadIdx.x < 64 ? threadIdx.x : threadIdx.x - 128;
     const int KC = KBn * (kLtKB / 4);                      // 16-byte chunks along K
     float* Bhi = reinterpret_cast<float*>(sBhi);
     float* Blo = reinterpret_cast<float*>(sBlo);
     const bool vec_ok = p.w_sk == 1 && (p.w_sn & 3) == 0 && (p.wkb & 3) == 0 && ((reinterpret_cast<uintptr_t>(Wp) & 15) == 0);
     constexpr int kU = 4;                                  // loads in flight per thread
-    for (int item0 = threadIdx.x; item0 < NB * KC; item0 += kLtThreads * kU) {
+    for (int item0 = sid; item0 < NB * KC; item0 += kStagers * kU) {
       float4 xs[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const int item = item0 + u * kLtThreads;
+        const int item = item0 + u * kStagers;
         xs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (item >= NB * KC) continue;
         const int n = item % NB, kc = item / NB;
@@ -129,14 +148,14 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const int item = item0 + u * kLtThreads;
+        const int item = item0 + u * kStagers;
         if (item >= NB * KC) continue;
         const int n = item % NB, kc = item / NB;
         const int off = kc * (NB * 4) + n * 4;             // floats: chunk plane of NB rows x 16 B
         lt_split_store(Bhi + off, Blo + off, xs[u]);
       }
     }
-    for (int i = threadIdx.x; i < 128; i += kLtThreads) sBias[i] = (biasp != nullptr && n0 + i < p.N) ? biasp[n0 + i] : 0.f;
+    for (int i = sid; i < 128; i += kStagers) sBias[i] = (biasp != nullptr && n0 + i < p.N) ? biasp[n0 + i] : 0.f;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -183,8 +202,8 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
     }
   } else if (warp >= 2 && warp < 6) {
     // ------------------------------ loader / hi-lo splitter ------------------------------
-    const int r = threadIdx.x - 64;       // token row of the tile owned by this thread (0..127)
-    const bool vec_ok = (p.ldx & 3) == 0 && (p.xkb & 3) == 0 && ((reinterpret_cast<uintptr_t>(Xp) & 15) == 0);
+    const int r = lr;
+    const bool vec_ok = x_vec_ok;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
       const long long grow = (long long)tile * kLtBM + r;
@@ -196,10 +215,15 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
         const float* xrow = Xp + kb * p.xkb + grow * p.ldx;
         // issue the 16 loads of this row first (independent), then wait for the buffer and split
         float4 x[kLtKB / 4];
+        if (it2 == 0) {
 #pragma unroll
-        for (int q = 0; q < kLtKB / 4; ++q) {
-          const int kc = (q + r) & (kLtKB / 4 - 1);          // rotated diagonal: conflict-free STS
-          x[q] = row_ok ? lt_load4(xrow, kc * 4, kc * 4, kvalid, vec_ok) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < kLtKB / 4; ++q) x[q] = xpre[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < kLtKB / 4; ++q) {
+            const int kc = (q + r) & (kLtKB / 4 - 1);          // rotated diagonal
+            x[q] = row_ok ? lt_load4(xrow, kc * 4, kc * 4, kvalid, vec_ok) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         mbar_wait(a_empty + buf, ((it2 / nbuf) & 1) ^ 1);
         float* Ahi = reinterpret_cast<float*>(sA + buf * 2 * kLtABytes);
@@ -371,7 +395,7 @@ static int lt_launch(LinTokParams& p, cudaStream_t st, const char* who) {
   int gx = kNumSMs / (p.n_blocks * p.batch);
   if (gx < 1) gx = 1;
   if (gx > p.m_tiles) gx = p.m_tiles;
-  linear_tok_kernel<EPI><<<dim3(gx, p.n_blocks, p.batch), kLtThreads, smem, st>>>(p);
+  launch_pdl(linear_tok_kernel<EPI>, dim3(gx, p.n_blocks, p.batch), dim3(kLtThreads), smem, st, p);
   return check_launch(who);
 }
 

@@ -103,6 +103,8 @@ __device__ __noinline__ void topk_insert(float x, int col, float* lval, int* lid
 
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   using Cfg = TcCfg<MODE>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -352,39 +354,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
   }
 }
 
-// ---- CE finalize: single CTA, warp per row -------------------------------------------------
-__global__ void __launch_bounds__(1024) ce_finalize_kernel(const float* __restrict__ partial, int n_parts, const float* __restrict__ out,
-                                                           const float* __restrict__ table, const long long* __restrict__ target, int M,
-                                                           int d, long long V, long long idx_offset, int n_groups, float* __restrict__ lse,
-                                                           float* __restrict__ tgt_logit, float* __restrict__ row_loss, float* __restrict__ loss) {
-  __shared__ double gsum[8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  if (threadIdx.x < 8) gsum[threadIdx.x] = 0.0;
-  __syncthreads();
-  const int per_group = M / n_groups;
-  for (int m = warp; m < M; m += nw) {
-    float mx = -INFINITY;
-    for (int i = lane; i < n_parts; i += 32) mx = fmaxf(mx, partial[((long long)m * n_parts + i) * 2]);
-    mx = warp_max(mx);
-    float s = 0.f;
-    for (int i = lane; i < n_parts; i += 32) {
-      const float pm = partial[((long long)m * n_parts + i) * 2], ps = partial[((long long)m * n_parts + i) * 2 + 1];
-      if (ps > 0.f) s += ps * expf(pm - mx);
-    }
-    s = warp_sum(s);
-    const float l = mx + logf(s);
-    const long long t = target[m] - idx_offset;
-    float dot = 0.f;
-    if (t >= 0 && t < V)
-      for (int j = lane; j < d; j += 32) dot = fmaf(out[(long long)m * d + j], table[t * d + j], dot);
-    dot = warp_sum(dot);
-    if (lane == 0) {
-      lse[m] = l; tgt_logit[m] = dot; row_loss[m] = l - dot;
-      atomicAdd(&gsum[m / per_group], (double)(l - dot));
-    }
+// ---- CE finalize: warp per row over the whole GPU, then one small CTA for the group means ---------
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ partial, int n_parts, const float* __restrict__ out,
+                                                      const float* __restrict__ table, const long long* __restrict__ target, int M,
+                                                      int d, long long V, long long idx_offset, float* __restrict__ lse,
+                                                      float* __restrict__ tgt_logit, float* __restrict__ row_loss) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (m >= M) return;
+  float mx = -INFINITY;
+  for (int i = lane; i < n_parts; i += 32) mx = fmaxf(mx, partial[((long long)m * n_parts + i) * 2]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int i = lane; i < n_parts; i += 32) {
+    const float pm = partial[((long long)m * n_parts + i) * 2], ps = partial[((long long)m * n_parts + i) * 2 + 1];
+    if (ps > 0.f) s += ps * expf(pm - mx);
   }
-  __syncthreads();
-  if (threadIdx.x < n_groups) loss[threadIdx.x] = (float)(gsum[threadIdx.x] / per_group);
+  s = warp_sum(s);
+  const float l = mx + logf(s);
+  const long long t = target[m] - idx_offset;
+  float dot = 0.f;
+  if (t >= 0 && t < V)
+    for (int j = lane; j < d; j += 32) dot = fmaf(out[(long long)m * d + j], table[t * d + j], dot);
+  dot = warp_sum(dot);
+  if (lane == 0) { lse[m] = l; tgt_logit[m] = dot; row_loss[m] = l - dot; }
+}
+
+__global__ void __launch_bounds__(256) ce_mean_kernel(const float* __restrict__ row_loss, int M, int n_groups, float* __restrict__ loss) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double red[8];
+  const int per_group = M / n_groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g = 0; g < n_groups; ++g) {          // fixed summation order: deterministic
+    double s = 0.0;
+    for (int i = threadIdx.x; i < per_group; i += blockDim.x) s += (double)row_loss[g * per_group + i];
+    s = warp_sum_d(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+      loss[g] = (float)(t / per_group);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- scalar glue of the adversarial losses (acsasrec.py:129-142): pen_l = sqrt(pen_sq_l);
+// loss_att = -ce_att + w * mean_l pen_l ; d loss_att / d pen_sq_l = w / (2 N pen_l) -------------------
+__global__ void loss_combine_kernel(const double* __restrict__ pen_sq, int n_layers, const float* __restrict__ ce, const float* w_ptr,
+                                    float w_val, float* __restrict__ loss_att, float* __restrict__ d_pen_sq) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x != 0) return;
+  const float w = w_ptr ? w_ptr[0] : w_val;
+  float acc = 0.f;
+  for (int l = 0; l < n_layers; ++l) {
+    const float pn = sqrtf((float)pen_sq[l]);
+    acc += pn;
+    if (d_pen_sq) d_pen_sq[l] = (w / (2.0f * n_layers)) / pn;
+  }
+  loss_att[0] = -ce[0] + (acc / n_layers) * w;
 }
 
 static void plan(LogitsParams& p, int batch = 1) {
@@ -403,7 +436,7 @@ static int launch_tc(LogitsParams& p, cudaStream_t st, const char* who, int batc
   plan(p, batch);
   cudaError_t e = cudaFuncSetAttribute(logits_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) { set_error("%s: smem attr: %s", who, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
-  logits_tc_kernel<MODE><<<dim3(p.m_tiles * p.n_chunks, batch), kTcThreads, Cfg::kSmemBytes, st>>>(p);
+  launch_pdl(logits_tc_kernel<MODE>, dim3(p.m_tiles * p.n_chunks, batch), dim3(kTcThreads), Cfg::kSmemBytes, st, p);
   return check_launch(who);
 }
 
@@ -454,9 +487,18 @@ int acsr_ce_finalize(const float* partial, int n_parts, const float* out, const 
                      void* stream) {
   ACSR_REQUIRE(partial && out && table && target && lse && tgt_logit && row_loss && loss, "ce_finalize: NULL pointer");
   ACSR_REQUIRE(M > 0 && n_parts > 0 && n_groups > 0 && n_groups <= 8 && M % n_groups == 0, "ce_finalize: bad sizes");
-  ce_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partial, n_parts, out, table, (const long long*)target, M, d, V,
-                                                          idx_offset, n_groups, lse, tgt_logit, row_loss, loss);
+  launch_pdl(ce_rows_kernel, dim3((M + 7) / 8), dim3(256), 0, (cudaStream_t)stream, partial, n_parts, out, table,
+             (const long long*)target, M, d, (long long)V, (long long)idx_offset, lse, tgt_logit, row_loss);
+  launch_pdl(ce_mean_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, (const float*)row_loss, M, n_groups, loss);
   return check_launch("ce_finalize");
+}
+
+int acsr_loss_combine(const double* pen_sq, int n_layers, const float* ce_attacked, const float* mask_loss_weight, float mask_loss_weight_value,
+                      float* loss_attacked, float* d_pen_sq, void* stream) {
+  ACSR_REQUIRE(pen_sq && ce_attacked && loss_attacked && n_layers > 0, "loss_combine: bad arguments");
+  launch_pdl(loss_combine_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, pen_sq, n_layers, ce_attacked, mask_loss_weight,
+             mask_loss_weight_value, loss_attacked, d_pen_sq);
+  return check_launch("loss_combine");
 }
 
 int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, const int64_t* target, const float* row_scale, int M,

@@ -116,6 +116,8 @@ embed_ln_fwd_kernel(const int64_t* __restrict__ item_seq, const float* __restric
                     const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int T, int L,
                     float p, const float* __restrict__ mask, const RngState* rng, uint32_t stream,
                     float* __restrict__ out, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   using RV = RowVec<D>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float w[RV::VPT], b[RV::VPT];
@@ -147,6 +149,8 @@ embed_ln_bwd_kernel(const float* __restrict__ d_out, const int64_t* __restrict__
                     const float* __restrict__ pos_emb, const float* __restrict__ ln_w, const float* __restrict__ stats,
                     int T, int L, float p, const float* __restrict__ mask, const RngState* rng, uint32_t stream,
                     float* __restrict__ d_table, float* __restrict__ d_pos, float* __restrict__ d_ln_w, float* __restrict__ d_ln_b) {
+  pdl_launch_dependents();
+  pdl_wait();
   using RV = RowVec<D>;
   __shared__ float red[kWarpsPerBlock * D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -209,6 +213,8 @@ bdrl_fwd_kernel(const float* __restrict__ h, const float* __restrict__ bias, con
                 const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int T, int res_rows,
                 float p, const float* __restrict__ mask, const RngState* rng, uint32_t stream,
                 float* __restrict__ out, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   using RV = RowVec<D>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float w[RV::VPT], b[RV::VPT], bi[RV::VPT];
@@ -243,6 +249,8 @@ bdrl_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ h, co
                 float p, const float* __restrict__ mask, const RngState* rng, uint32_t stream,
                 float* __restrict__ d_h, float* __restrict__ d_res, float* __restrict__ d_bias,
                 float* __restrict__ d_ln_w, float* __restrict__ d_ln_b) {
+  pdl_launch_dependents();
+  pdl_wait();
   using RV = RowVec<D>;
   __shared__ float red[kWarpsPerBlock * D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -298,6 +306,8 @@ constexpr int kActTX = 64, kActTY = 4, kActMaxK = 8;   // n <= 64*4*8 = 2048
 
 __global__ void __launch_bounds__(kActTX * kActTY)
 bias_act_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ bias, int T, int ncv, int act, float4* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int cv = threadIdx.x; cv < ncv; cv += kActTX) {
     const float4 b = bias != nullptr ? bias[cv] : make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long t = (long long)blockIdx.x * kActTY + threadIdx.y; t < T; t += (long long)gridDim.x * kActTY) {
@@ -312,6 +322,8 @@ bias_act_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ bia
 __global__ void __launch_bounds__(kActTX * kActTY)
 bias_act_bwd_kernel(const float4* __restrict__ d_out, const float4* __restrict__ h, const float4* __restrict__ bias,
                     int T, int ncv, int act, int act_rows, int param_rows, float4* __restrict__ d_h, float* __restrict__ d_bias) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float4 red[kActTY][kActTX];
   for (int cv0 = 0; cv0 < ncv; cv0 += kActTX) {      // uniform trip count across the block (syncthreads inside)
     const int cv = cv0 + threadIdx.x;
@@ -348,6 +360,8 @@ bias_act_bwd_kernel(const float4* __restrict__ d_out, const float4* __restrict__
 // ------------------------------------------------------------------------------------------
 __global__ void gather_last_fwd_kernel(const float* __restrict__ x_att, const float* __restrict__ x_cal,
                                        const int64_t* __restrict__ item_len, int B, int L, int d, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;                 // [0, 2B) or [0,B)
   const bool has_att = x_att != nullptr;
   const int b = has_att ? (row % B) : row;
@@ -358,6 +372,8 @@ __global__ void gather_last_fwd_kernel(const float* __restrict__ x_att, const fl
 
 __global__ void gather_last_bwd_kernel(const float* __restrict__ d_out, const int64_t* __restrict__ item_len, int B, int L, int d,
                                        float* __restrict__ d_x_att, float* __restrict__ d_x_cal) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const bool has_att = d_x_att != nullptr;
   const int b = has_att ? (row % B) : row;
@@ -371,6 +387,8 @@ __global__ void gather_last_bwd_kernel(const float* __restrict__ d_out, const in
 // ------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float wd, const long long* __restrict__ step_count) {
+  pdl_launch_dependents();
+  pdl_wait();
   const double step = (double)(step_count[0] + 1);
   const float bc1 = (float)(1.0 - pow((double)b1, step));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, step));
@@ -384,7 +402,9 @@ __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__
     param[i] = pm - step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
   }
 }
-__global__ void step_inc_kernel(long long* step_count) { step_count[0] += 1; }
+__global__ void step_inc_kernel(long long* step_count) {
+  pdl_launch_dependents();
+  pdl_wait(); step_count[0] += 1; }
 
 static int row_grid(long long T) {
   long long need = (T + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -415,7 +435,7 @@ int acsr_embed_ln_dropout_fwd(const int64_t* item_seq, const float* table, const
   ACSR_REQUIRE(p >= 0.f && p < 1.f, "embed_ln_dropout_fwd: dropout p=%f", p);
   ACSR_REQUIRE(!(p > 0.f && mask == nullptr && rng == nullptr), "embed_ln_dropout_fwd: p>0 needs mask or rng");
   if (T == 0) return ACSR_OK;
-  DISPATCH_D(d, (embed_ln_fwd_kernel<D_><<<row_grid(T), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+  DISPATCH_D(d, (launch_pdl(embed_ln_fwd_kernel<D_>, dim3(row_grid(T)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, 
                     item_seq, table, pos_emb, ln_w, ln_b, eps, T, L, p, mask, (const RngState*)rng, rng_stream, out, stats)));
   return check_launch("embed_ln_dropout_fwd");
 }
@@ -427,7 +447,7 @@ int acsr_embed_ln_dropout_bwd(const float* d_out, const int64_t* item_seq, const
   ACSR_REQUIRE(d_out && item_seq && table && ln_w && stats && d_table, "embed_ln_dropout_bwd: NULL pointer");
   ACSR_REQUIRE((pos_emb == nullptr) == (d_pos == nullptr), "embed_ln_dropout_bwd: pos_emb/d_pos mismatch");
   if (T == 0) return ACSR_OK;
-  DISPATCH_D(d, (embed_ln_bwd_kernel<D_><<<row_grid(T), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+  DISPATCH_D(d, (launch_pdl(embed_ln_bwd_kernel<D_>, dim3(row_grid(T)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, 
                     d_out, item_seq, table, pos_emb, ln_w, stats, T, L, p, mask, (const RngState*)rng, rng_stream, d_table,
                     d_pos, d_ln_w, d_ln_b)));
   return check_launch("embed_ln_dropout_bwd");
@@ -441,7 +461,7 @@ int acsr_bias_dropout_res_ln_fwd(const float* h, const float* bias, const float*
   ACSR_REQUIRE(p >= 0.f && p < 1.f, "bias_dropout_res_ln_fwd: dropout p=%f", p);
   ACSR_REQUIRE(!(p > 0.f && mask == nullptr && rng == nullptr), "bias_dropout_res_ln_fwd: p>0 needs mask or rng");
   if (T == 0) return ACSR_OK;
-  DISPATCH_D(d, (bdrl_fwd_kernel<D_><<<row_grid(T), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+  DISPATCH_D(d, (launch_pdl(bdrl_fwd_kernel<D_>, dim3(row_grid(T)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, 
                     h, bias, res, ln_w, ln_b, eps, T, res_rows, p, mask, (const RngState*)rng, rng_stream, out, stats)));
   return check_launch("bias_dropout_res_ln_fwd");
 }
@@ -453,7 +473,7 @@ int acsr_bias_dropout_res_ln_bwd(const float* d_out, const float* h, const float
   ACSR_REQUIRE(d_out && h && res && ln_w && stats && d_h && d_res, "bias_dropout_res_ln_bwd: NULL pointer");
   ACSR_REQUIRE(T == 0 || (act_rows > 0 && res_rows > 0 && param_rows >= 0), "bias_dropout_res_ln_bwd: bad row periods");
   if (T == 0) return ACSR_OK;
-  DISPATCH_D(d, (bdrl_bwd_kernel<D_><<<row_grid(T), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+  DISPATCH_D(d, (launch_pdl(bdrl_bwd_kernel<D_>, dim3(row_grid(T)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, 
                     d_out, h, bias, res, ln_w, stats, T, act_rows, res_rows, param_rows, p, mask, (const RngState*)rng,
                     rng_stream, d_h, d_res, d_bias, d_ln_w, d_ln_b)));
   return check_launch("bias_dropout_res_ln_bwd");
@@ -466,7 +486,7 @@ int acsr_bias_act_fwd(const float* h, const float* bias, int T, int n, int act, 
   if (T == 0) return ACSR_OK;
   long long need = (T + kActTY - 1) / kActTY, cap = kNumSMs * 8;
   dim3 blk(kActTX, kActTY);
-  bias_act_fwd_kernel<<<(int)(need < cap ? need : cap), blk, 0, (cudaStream_t)stream>>>(
+  launch_pdl(bias_act_fwd_kernel, dim3((int)(need < cap ? need : cap)), blk, 0, (cudaStream_t)stream, 
       (const float4*)h, (const float4*)bias, T, n / 4, act, (float4*)out);
   return check_launch("bias_act_fwd");
 }
@@ -480,7 +500,7 @@ int acsr_bias_act_bwd(const float* d_out, const float* h, const float* bias, int
   if (T == 0) return ACSR_OK;
   long long need = (T + kActTY - 1) / kActTY, cap = kNumSMs * 4;
   dim3 blk(kActTX, kActTY);
-  bias_act_bwd_kernel<<<(int)(need < cap ? need : cap), blk, 0, (cudaStream_t)stream>>>(
+  launch_pdl(bias_act_bwd_kernel, dim3((int)(need < cap ? need : cap)), blk, 0, (cudaStream_t)stream, 
       (const float4*)d_out, (const float4*)h, (const float4*)bias, T, n / 4, act, act_rows, param_rows, (float4*)d_h, d_bias);
   return check_launch("bias_act_bwd");
 }
@@ -489,7 +509,7 @@ int acsr_gather_last_fwd(const float* x_att, const float* x_cal, const int64_t* 
                          void* stream) {
   ACSR_REQUIRE(x_cal && item_len && out, "gather_last_fwd: NULL pointer");
   if (B == 0) return ACSR_OK;
-  gather_last_fwd_kernel<<<x_att ? 2 * B : B, 64, 0, (cudaStream_t)stream>>>(x_att, x_cal, item_len, B, L, d, out);
+  launch_pdl(gather_last_fwd_kernel, dim3(x_att ? 2 * B : B), dim3(64), 0, (cudaStream_t)stream, x_att, x_cal, item_len, B, L, d, out);
   return check_launch("gather_last_fwd");
 }
 
@@ -497,7 +517,7 @@ int acsr_gather_last_bwd(const float* d_out, const int64_t* item_len, int B, int
                          void* stream) {
   ACSR_REQUIRE(d_out && item_len && d_x_cal, "gather_last_bwd: NULL pointer");
   if (B == 0) return ACSR_OK;
-  gather_last_bwd_kernel<<<d_x_att ? 2 * B : B, 64, 0, (cudaStream_t)stream>>>(d_out, item_len, B, L, d, d_x_att, d_x_cal);
+  launch_pdl(gather_last_bwd_kernel, dim3(d_x_att ? 2 * B : B), dim3(64), 0, (cudaStream_t)stream, d_out, item_len, B, L, d, d_x_att, d_x_cal);
   return check_launch("gather_last_bwd");
 }
 
@@ -506,10 +526,10 @@ int acsr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   ACSR_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_count, "adam_step: NULL pointer");
   if (n > 0) {
     long long need = (n + 255) / 256, cap = kNumSMs * 8;
-    adam_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(adam_kernel, dim3((int)(need < cap ? need : cap)), dim3(256), 0, (cudaStream_t)stream, 
         param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (const long long*)step_count);
   }
-  step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)step_count);
+  launch_pdl(step_inc_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (long long*)step_count);
   return check_launch("adam_step");
 }
 

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(kMergeThreads)
 topk_merge_kernel(const float* __restrict__ pval, const long long* __restrict__ pidx, int n_cand, int P, int k,
                   const long long* __restrict__ positive, float* __restrict__ oval, long long* __restrict__ oidx,
                   int* __restrict__ rec) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float smem_m[];
   float* sv = smem_m;                                   // [P]
   int* ss = reinterpret_cast<int*>(smem_m + P);         // [P] candidate slot
@@ -69,7 +71,7 @@ extern "C" int acsr_topk_merge(const float* partial_val, const int64_t* partial_
   const size_t smem = (size_t)P * 8;
   cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("topk_merge: smem attr: %s", cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
-  topk_merge_kernel<<<M, kMergeThreads, smem, (cudaStream_t)stream>>>(partial_val, (const long long*)partial_idx, n_cand, P, k,
+  launch_pdl(topk_merge_kernel, dim3(M), dim3(kMergeThreads), smem, (cudaStream_t)stream, partial_val, (const long long*)partial_idx, n_cand, P, k,
                                                                       (const long long*)positive, topk_val, (long long*)topk_idx,
                                                                       rec_topk);
   return check_launch("topk_merge");

@@ -53,6 +53,7 @@ class FusedTrainStep(object):
         self.overlap_wgrad = bool(getattr(model, 'overlap_wgrad', True))
         self.n_branches = int(getattr(model, 'step_branches', 1))
         self._streams = {}
+        self.pdl = bool(getattr(model, 'pdl', True))            # programmatic dependent launch between the step's kernels
 
     # ------------------------------------------------------------------------------------------
     def _stream_for(self, dev, key):
@@ -102,7 +103,7 @@ class FusedTrainStep(object):
             return torch.empty(s, dtype=torch.float32, device=dev)
         nc = ops.logits_num_chunks(2 * B, V)
         j = dict(pen=torch.zeros(N, dtype=torch.float64, device=dev), out2=f(2 * B, d), partial=f(2 * B, nc, 2), lse=f(2 * B),
-                 tgt=f(2 * B), row_loss=f(2 * B), loss=f(2), Gt=f(V, 2 * B), d_out2=f(2 * B, d),
+                 tgt=f(2 * B), row_loss=f(2 * B), loss=f(2), loss_att=f(1), dpen=f(N), Gt=f(V, 2 * B), d_out2=f(2 * B, d),
                  target2=torch.empty(2 * B, dtype=torch.int64, device=dev),
                  row_scale=torch.cat((torch.full((B,), 1.0 / B), torch.full((B,), -1.0 / B))).to(dev))
         self.buf[key] = j
@@ -112,6 +113,13 @@ class FusedTrainStep(object):
     @torch.no_grad()
     def __call__(self, interaction):
         """-> (final_attacked_loss, calibrated_loss) detached 0-d tensors; gradients land in the flat grad buffer."""
+        was = LIB.query('acsr_set_pdl', 1 if self.pdl else 0)
+        try:
+            return self._step(interaction)
+        finally:
+            LIB.query('acsr_set_pdl', was)
+
+    def _step(self, interaction):
         m, opt = self.m, self.opt
         seq = interaction[m.ITEM_SEQ].contiguous()
         ln = interaction[m.ITEM_SEQ_LEN].contiguous()
@@ -158,14 +166,16 @@ class FusedTrainStep(object):
             LIB.call('acsr_ce_finalize', _p(jb['partial']), jb['partial'].shape[1], _p(jb['out2']), _p(E),
                      _p(jb['target2'], torch.int64), 2 * B, d, V, 0, 2, _p(jb['lse']), _p(jb['tgt']), _p(jb['row_loss']),
                      _p(jb['loss']), st)
-        pen_norm = torch.sqrt(jb['pen'].to(torch.float32))
-        w = m.mask_loss_weight.detach()[0] if m.trainable_mask_loss_weight else float(m.mask_loss_weight)
+        # pen_l = sqrt(sum (1-M_l)^2); loss_att = -CE(attacked) + w * mean_l pen_l; d loss_att / d pen_sq_l  -- one launch
+        wp = m.mask_loss_weight.detach() if m.trainable_mask_loss_weight else None
+        LIB.call('acsr_loss_combine', jb['pen'].data_ptr(), N, _p(jb['loss'][1:]), _p(wp),
+                 0.0 if wp is not None else float(m.mask_loss_weight), _p(jb['loss_att']), _p(jb['dpen']), st)
         loss_cal = jb['loss'][0]
-        loss_att = -jb['loss'][1] + pen_norm.mean() * w
+        loss_att = jb['loss_att'][0]
         if not training:
             return loss_att, loss_cal
         # ---------------- backward ----------------
-        dpen = (w / (2.0 * N)) / pen_norm                     # d loss_att / d pen_sq_l
+        dpen = jb['dpen']
         opt.zero_grad()
         if self.vp is not None:       # shard-local G^T, reduce-scatter of d_out, dE into the owner's rows
             jb['d_out2'].copy_(self.vp.ce_backward(vst, E, jb['row_scale'], E.grad, table_half=0, n_groups=2))
@@ -179,13 +189,20 @@ class FusedTrainStep(object):
                 br['stream'].wait_stream(main)
         if self.vp is None:
             # dE += Gt[:, :B] . out[:B]: only the calibrated rows train the item table.  It reads and writes dE without
-            # atomics, so every branch's embedding scatter waits for it (dE_done).
-            if self.tc and B <= 256:
-                ops.linear_tok(jb['Gt'], V, B, jb['out2'], d, E.grad, d, ldx=2 * B, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
-            else:
-                E.grad.addmm_(jb['Gt'][:, :B], jb['out2'][:B])
+            # atomics, so every branch's embedding scatter waits for it (dE_done).  Nothing else consumes it: with a single
+            # branch it runs on that branch's weight-gradient stream.
+            dE_stream = branches[0]['side'] if (nb == 1 and branches[0]['side'] is not None) else main
+            if dE_stream is not main:
+                dE_stream.wait_stream(main)
+            with torch.cuda.stream(dE_stream):
+                if self.tc and B <= 256:
+                    ops.linear_tok(jb['Gt'], V, B, jb['out2'], d, E.grad, d, ldx=2 * B, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
+                else:
+                    E.grad.addmm_(jb['Gt'][:, :B], jb['out2'][:B])
+        else:
+            dE_stream = main
         dE_done = torch.cuda.Event()
-        dE_done.record(main)
+        dE_done.record(dE_stream)
         for br in branches:
             with torch.cuda.stream(br['stream']):
                 self._backward_branch(br, jb, B, L, rt, dpen, dE_done)
@@ -195,7 +212,7 @@ class FusedTrainStep(object):
         return loss_att, loss_cal
 
     # ------------------------------------------------------------------------------------------
-    def _forward_branch(self, br, jb, B, L, rt, training):
+    def _forward_branch(self, br, jb, B, L, rt, training, need_att=True):
         m = self.m
         b, seq, ln, s = br['buf'], br['seq'], br['ln'], br['idx']
         Bs = seq.shape[0]
@@ -225,7 +242,7 @@ class FusedTrainStep(object):
         b['xs'] = []
         act_id = ops.ACT_IDS[m.hidden_act]
         for l, layer in enumerate(m.trm_encoder.layer):
-            last = l == N - 1
+            last = l == N - 1 and need_att                 # the attacked branch only matters on the last layer (and not in eval)
             R = 2 * T if last else T
             lb = b['layers'][l]
             aa, ff = layer.attack_attention, layer.feed_forward
@@ -292,7 +309,24 @@ class FusedTrainStep(object):
         # rows [0,B) of out2 calibrated, [B,2B) attacked; this branch owns the rows of its sequences in both halves
         lo = br['sl'].start
         LIB.call('acsr_gather_last_fwd', None, _p(last_out[:T]), _p(ln, torch.int64), Bs, L, d, _p(jb['out2'][lo:lo + Bs]), st)
-        LIB.call('acsr_gather_last_fwd', None, _p(last_out[T:]), _p(ln, torch.int64), Bs, L, d, _p(jb['out2'][B + lo:B + lo + Bs]), st)
+        if need_att:
+            LIB.call('acsr_gather_last_fwd', None, _p(last_out[T:]), _p(ln, torch.int64), Bs, L, d, _p(jb['out2'][B + lo:B + lo + Bs]), st)
+
+    @torch.no_grad()
+    def encode_eval(self, item_seq, item_seq_len):
+        """calibrated last-position outputs [B,d] of an eval batch through the fused forward (no attacked branch, no
+        dropout, no saved-for-backward traffic beyond the reused buffers): ACSASRec.forward for full_sort_predict."""
+        m = self.m
+        seq, ln = item_seq.contiguous(), item_seq_len.contiguous()
+        B, L = seq.shape
+        dev = seq.device
+        rt = m._runtime(dev)
+        jb = self._joint_buffers(B, dev)
+        br = dict(idx=0, sl=slice(0, B), seq=seq, ln=ln, buf=self._branch_buffers(B, L, dev, 'eval'), rand=rt.rand,
+                  stream=torch.cuda.current_stream(), side=None)
+        jb['pen'].zero_()
+        self._forward_branch(br, jb, B, L, rt, False, need_att=False)
+        return jb['out2'][:B]
 
     # ------------------------------------------------------------------------------------------
     def _backward_branch(self, br, jb, B, L, rt, dpen, dE_done):

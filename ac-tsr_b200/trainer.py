@@ -150,6 +150,7 @@ class ACSASRecTrainer(object):
                 and getattr(model, 'loss_type', None) == 'CE' and not self.clip_grad_norm):
             from .fused_step import FusedTrainStep
             self.fused = FusedTrainStep(model, self.optimizer)
+            model._fused_step = self.fused          # eval batches reuse the fused forward (ACSASRec._encode)
         self.nan_check_interval = int(cfg_get(config, 'nan_check_interval', 50))
         self.logger.info('use attack trainer!!!')
 

@@ -38,6 +38,9 @@ int acsr_version(void);
 const char* acsr_last_error(void);
 /* number of SMs the persistent kernels size their grids for (148 on B200) */
 int acsr_num_sms(void);
+/* launch the library's kernels with programmatic dependent launch (next kernel's prologue overlaps the tail of the
+ * previous one).  Returns the previous setting.  Default: off (environment ACSR_PDL=1 turns it on). */
+int acsr_set_pdl(int on);
 
 /* rng state helper: rng->step += 1 (one tiny kernel; keeps graph replays distinct) */
 int acsr_rng_advance(void* rng, void* stream);
@@ -175,10 +178,15 @@ int acsr_logits_ce_partial(const float* out, const float* table, int M, int64_t 
 /* combine partial (max, sumexp) pairs -> lse [M]; tgt_logit[m] = out[m].E[target[m]-idx_offset] as an
  * fp32 dot when the target row lives in this table shard (else 0; sum across shards);
  * row_loss[m] = lse - tgt_logit; loss[g] = mean of row_loss over each of n_groups groups of
- * M/n_groups consecutive rows (attacked rows first, calibrated second).  Single-CTA kernel. */
+ * M/n_groups consecutive rows (attacked rows first, calibrated second).  Warp per row, then one CTA for the means. */
 int acsr_ce_finalize(const float* partial, int n_parts, const float* out, const float* table,
                      const int64_t* target, int M, int d, int64_t V, int64_t idx_offset, int n_groups,
                      float* lse, float* tgt_logit, float* row_loss, float* loss, void* stream);
+/* scalar glue of the adversarial losses (acsasrec.py:129-142) in one launch: pen_l = sqrt(pen_sq[l]);
+ * loss_attacked[0] = -ce_attacked[0] + w * mean_l pen_l ; d_pen_sq[l] = w / (2 n_layers pen_l) (NULL: skip).
+ * w = mask_loss_weight[0] when the pointer is given (trainable_mask_loss_weight), else mask_loss_weight_value. */
+int acsr_loss_combine(const double* pen_sq, int n_layers, const float* ce_attacked, const float* mask_loss_weight,
+                      float mask_loss_weight_value, float* loss_attacked, float* d_pen_sq, void* stream);
 /* CE backward part 1: Gt [V, ldg] (ldg >= M) = transpose of (exp(out.E^T - lse) - onehot(target)) * row_scale[m];
  * then d_E = Gt.out is a plain GEMM and d_out = Gt^T.E goes through acsr_linear_wgrad (reduction over V). */
 int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, const int64_t* target,
