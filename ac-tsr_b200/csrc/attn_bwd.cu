@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_kernel(const AttnPar
   constexpr int dhp = DH + 4;
   const int L = p.L, LP = (L + 3) & ~3;
   const int TRI = tri_off(L, LP);
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int b = p.order ? p.order[blockIdx.x / p.H] : (int)(blockIdx.x / p.H), h = blockIdx.x % p.H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* ptr = smem_f;
   AttnSmem sm = carve_common(ptr, LP, DH);
@@ -504,10 +504,10 @@ int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const fl
                         const float* rich_ratio, float p_attn, const float* D1, const float* D2, const float* D3,
                         const float* noise, const void* rng, uint32_t rng_stream, float* d_mq, float* d_mk, float* d_mv,
                         float* d_aq, float* d_ak, float* d_gate_logit, float* d_order_w, float* d_order_b, float* d_dist_w,
-                        float* d_dist_b, float* d_scalar, float* d_rich_ratio, void* stream) {
+                        float* d_dist_b, float* d_scalar, float* d_rich_ratio, const int32_t* order, void* stream) {
   AttnParams p = {};
   attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
-                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream);
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, order);
   p.t0 = d_ctx_cal; p.t1 = d_ctx_att; p.t1_is_att = 1; p.d_pen0 = d_pen_sq;
   p.d_mq = d_mq; p.d_mk = d_mk; p.d_mv = d_mv; p.d_aq = d_aq; p.d_ak = d_ak; p.d_gate = d_gate_logit;
   p.d_ow = d_order_w; p.d_ob = d_order_b; p.d_dw = d_dist_w; p.d_db = d_dist_b; p.d_scalar = d_scalar; p.d_ratio = d_rich_ratio;
@@ -527,10 +527,10 @@ int acsr_attn_calib_bwd2(const float* d_ctx_cal0, const float* d_pen_sq0, const 
                          float p_attn, const float* D1, const float* D2, const float* D3, const float* noise, const void* rng,
                          uint32_t rng_stream, float* d_mq, float* d_mk, float* d_mv, float* d_aq, float* d_ak,
                          float* d_gate_logit, float* d_order_w, float* d_order_b, float* d_dist_w, float* d_dist_b,
-                         float* d_scalar, float* d_rich_ratio, void* stream) {
+                         float* d_scalar, float* d_rich_ratio, const int32_t* order, void* stream) {
   AttnParams p = {};
   attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
-                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream);
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, order);
   ACSR_REQUIRE(!(d_ctx_att1 && d_ctx_cal1), "attn_calib_bwd2: stream 1 takes d_ctx_att or d_ctx_cal, not both");
   p.t0 = d_ctx_cal0; p.t1 = d_ctx_att1 ? d_ctx_att1 : d_ctx_cal1; p.t1_is_att = d_ctx_att1 != nullptr;
   p.d_pen0 = d_pen_sq0; p.d_pen1 = d_pen_sq1;

@@ -35,6 +35,7 @@ constexpr unsigned kFull = 0xffffffffu;
 struct AttnParams {
   const float *mq, *mk, *mv, *aq, *ak, *gate;
   const int64_t* item_seq;
+  const int32_t* order;      // sequence handled by CTA group g is order[g] (longest first), NULL = identity
   const float *ow, *ob, *dw, *db, *scalar;
   int B, L, H, dh, d;
   int two_level, combine, rich;
@@ -135,6 +136,7 @@ struct RowConst {      // per-launch scalars hoisted out of the row loop
   unsigned thr16;
   unsigned long long seed, step;
   bool philox_drop, philox_noise, need_p0;
+  bool bounded;      // dropout scaling <= 16: the logits of the C and R softmaxes are bounded (no max subtraction)
 };
 
 // fast-math forms (ex2/lg2/rcp approx, ~2 ulp): far inside the 1e-3 parity budget
@@ -169,6 +171,19 @@ __device__ __forceinline__ void softmax_row(const float* z, unsigned act, float*
   for (int jj = 0; jj < NJ; ++jj) { y[jj] = ((act >> jj) & 1u) ? fex2(fmaf(z[jj], 1.4426950408889634f, -m)) : 0.f; s += y[jj]; }
   s = grp_sum<G>(s);
   const float inv = frcp(s);
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) y[jj] *= inv;
+}
+
+// softmax of logits known to lie in [0, ~45] (or at the mask value): no running maximum is needed.  A row whose
+// columns are all masked (only possible for all-padding input) gets zeros.
+template <int G, int NJ>
+__device__ __forceinline__ void softmax_row_bounded(const float* z, unsigned act, float* y) {
+  float s = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) { y[jj] = ((act >> jj) & 1u) ? fex2(z[jj] * 1.4426950408889634f) : 0.f; s += y[jj]; }
+  s = grp_sum<G>(s);
+  const float inv = s > 0.f ? frcp(s) : 0.f;
 #pragma unroll
   for (int jj = 0; jj < NJ; ++jj) y[jj] *= inv;
 }
@@ -278,6 +293,7 @@ __device__ __forceinline__ RowConst make_consts(const AttnParams& p, bool need_a
   k.inv_sq = 1.0f / sqrtf((float)DH);
   k.inv_keep = p.p > 0.f ? 1.0f / (1.0f - p.p) : 1.0f;
   k.thr16 = (unsigned)(p.p * 65536.0f + 0.5f);
+  k.bounded = k.inv_keep <= 16.0f;
   k.philox_drop = p.p > 0.f && p.D1 == nullptr;
   k.philox_noise = need_att && p.noise == nullptr && p.rng != nullptr;
   k.need_p0 = !p.two_level || p.probs != nullptr;
@@ -444,7 +460,8 @@ __device__ __forceinline__ void row_forward(const AttnParams& p, const AttnSmem&
   }
 #pragma unroll
   for (int jj = 0; jj < NJ; ++jj) z[jj] = O[jj] * expm[jj] + (((valid >> jj) & 1u) ? 0.f : kMaskNeg);
-  softmax_row<G, NJ>(z, act, r.C);
+  if (kc.bounded) softmax_row_bounded<G, NJ>(z, act, r.C);
+  else softmax_row<G, NJ>(z, act, r.C);
   if (p.combine == ACSR_ATTN_COMBINE_FIXED) {
     // layers.py:885: softmax(origin + 0.5*calibrated) has NO mask: each of the L - bound columns outside the row's
     // range holds exp(0 - max) of the mass; they only enter through the normaliser.
@@ -470,7 +487,8 @@ __device__ __forceinline__ void row_forward(const AttnParams& p, const AttnSmem&
       z[jj] = g * O[jj] + (1.0f - g) * r.C[jj] + (((valid >> jj) & 1u) ? 0.f : kMaskNeg);
     }
   }
-  softmax_row<G, NJ>(z, act, r.R);
+  if (kc.bounded) softmax_row_bounded<G, NJ>(z, act, r.R);
+  else softmax_row<G, NJ>(z, act, r.R);
 }
 
 __device__ __forceinline__ AttnSmem carve_common(float*& ptr, int LP, int dh) {
@@ -535,7 +553,8 @@ static inline void attn_fill_common(AttnParams& p, const float* mq, const float*
                                     const float* order_b, const float* dist_w, const float* dist_b, const float* scalar, int B,
                                     int L, int H, int dh, int two_level, int combine_option, float comb_scalar, int rich_mode,
                                     const float* rich_ratio, float p_attn, const float* D1, const float* D2, const float* D3,
-                                    const float* noise, const void* rng, uint32_t rng_stream) {
+                                    const float* noise, const void* rng, uint32_t rng_stream, const int32_t* order) {
+  p.order = order;
   p.mq = mq; p.mk = mk; p.mv = mv; p.aq = aq; p.ak = ak; p.gate = combine_option == ACSR_ATTN_COMBINE_GATE ? gate_logit : nullptr;
   p.item_seq = item_seq;
   p.ow = order_w; p.ob = order_b; p.dw = dist_w; p.db = dist_b; p.scalar = scalar;

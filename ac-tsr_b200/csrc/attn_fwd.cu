@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kAttnThreads, 4) attn_fwd_kernel(const AttnPar
   pdl_wait();
   extern __shared__ __align__(16) float smem_f[];
   const int L = p.L, LP = (L + 3) & ~3;
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int b = p.order ? p.order[blockIdx.x / p.H] : (int)(blockIdx.x / p.H), h = blockIdx.x % p.H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* ptr = smem_f;
   AttnSmem sm = carve_common(ptr, LP, DH);
@@ -150,9 +150,42 @@ static int launch_fwd(const AttnParams& p, cudaStream_t st) {
   return check_launch("attn_calib_fwd");
 }
 
+// sequences sorted by the number of keys in play (1 + index of the last real item), longest first: the CTAs of the
+// attention kernels are scheduled in that order, so the long sequences start first and the short ones fill the tail
+__global__ void __launch_bounds__(256) seq_order_kernel(const int64_t* __restrict__ item_seq, int B, int L, int32_t* __restrict__ order) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ int cnt[66], off[66];
+  for (int i = threadIdx.x; i < 66; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int nkey = 0;
+    for (int j = L - 1; j >= 0; --j) if (item_seq[(long long)b * L + j] != 0) { nkey = j + 1; break; }
+    atomicAdd(cnt + nkey, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int k = 65; k >= 0; --k) { off[k] = run; run += cnt[k]; }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int nkey = 0;
+    for (int j = L - 1; j >= 0; --j) if (item_seq[(long long)b * L + j] != 0) { nkey = j + 1; break; }
+    order[atomicAdd(off + nkey, 1)] = b;
+  }
+}
+
 }  // namespace acsr
 
 using namespace acsr;
+
+extern "C" int acsr_seq_order(const int64_t* item_seq, int B, int L, int32_t* order, void* stream) {
+  ACSR_REQUIRE(item_seq && order && B > 0 && L > 0 && L <= 64, "seq_order: bad arguments");
+  launch_pdl(seq_order_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, item_seq, B, L, order);
+  return check_launch("seq_order");
+}
+
 
 extern "C" int acsr_attn_calib_fwd(const float* mq, const float* mk, const float* mv, const float* aq, const float* ak,
                                    const float* gate_logit, const int64_t* item_seq, const float* order_w, const float* order_b,
@@ -160,10 +193,10 @@ extern "C" int acsr_attn_calib_fwd(const float* mq, const float* mk, const float
                                    int two_level, int combine_option, float comb_scalar, int rich_mode, const float* rich_ratio,
                                    float p_attn, const float* D1, const float* D2, const float* D3, const float* noise,
                                    const void* rng, uint32_t rng_stream, float* ctx_att, float* ctx_cal, double* pen_sq,
-                                   float* probs_out, void* stream) {
+                                   float* probs_out, const int32_t* order, void* stream) {
   AttnParams p = {};
   attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
-                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream);
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, order);
   p.ctx_att = ctx_att; p.ctx_cal = ctx_cal; p.pen_sq = pen_sq; p.probs = probs_out;
   int rc = attn_validate(p, "attn_calib_fwd");
   if (rc) return rc;

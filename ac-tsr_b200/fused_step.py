@@ -53,6 +53,7 @@ class FusedTrainStep(object):
         self.overlap_wgrad = bool(getattr(model, 'overlap_wgrad', True))
         self.n_branches = int(getattr(model, 'step_branches', 1))
         self._streams = {}
+        self.compact_last = bool(getattr(model, 'compact_last', True))   # last layer's dense part on the len-1 rows only
         self.pdl = bool(getattr(model, 'pdl', True))            # programmatic dependent launch between the step's kernels
 
     # ------------------------------------------------------------------------------------------
@@ -72,7 +73,7 @@ class FusedTrainStep(object):
 
         def f(*s):
             return torch.empty(s, dtype=torch.float32, device=dev)
-        b = dict(T=T, x0=f(T, d), st_e=f(T, 2), layers=[])
+        b = dict(T=T, x0=f(T, d), st_e=f(T, 2), layers=[], order=torch.empty(Bs, dtype=torch.int32, device=dev))
         for l in range(N):
             R = 2 * T if l == N - 1 else T
             qkv, aqk = f(3, T, d), f(2, T, d)
@@ -86,6 +87,12 @@ class FusedTrainStep(object):
             lb['d_mq'], lb['d_mk'], lb['d_mv'] = lb['d_qkv'][0], lb['d_qkv'][1], lb['d_qkv'][2]
             lb['d_aq'], lb['d_ak'] = lb['d_aqk'][0], lb['d_aqk'][1]
             b['layers'].append(lb)
+        # last layer: only position len-1 of each sequence feeds the losses, so everything after its attention runs on
+        # 2*Bs compact rows ([calibrated ; attacked]) instead of 2*T
+        C = 2 * Bs
+        b['c'] = dict(ctx=f(C, d), x=f(Bs, d), hz=f(C, d), st_a=f(C, 2), h=f(C, d), z1=f(C, I), a1=f(C, I), z2=f(C, d), st_f=f(C, 2),
+                      out=f(C, d), d_out=f(C, d), d_z2=f(C, d), d_h=f(C, d), d_a1=f(C, I), d_z1=f(C, I), d_hz=f(C, d), d_x=f(C, d),
+                      d_ctx=f(C, d))
         for n, w in (('d_out', d), ('d_a1', I), ('d_h', d), ('d_x', d), ('d_ctx', d)):
             b[n] = f(2 * T, w)
         self.buf[key] = b
@@ -153,6 +160,8 @@ class FusedTrainStep(object):
         for br in branches:
             if br['stream'] is not main:
                 main.wait_stream(br['stream'])
+        if getattr(self, '_stop_after', None) == 'fwd':      # timeline probes (scripts/step_timeline.py)
+            return jb['loss'][0], jb['loss'][0]
         # ---------------- where the sequences meet: full-catalogue cross entropy + penalty norm ----------------
         st = _stream()
         torch.cat((pos_items, pos_items), out=jb['target2'])
@@ -172,7 +181,7 @@ class FusedTrainStep(object):
                  0.0 if wp is not None else float(m.mask_loss_weight), _p(jb['loss_att']), _p(jb['dpen']), st)
         loss_cal = jb['loss'][0]
         loss_att = jb['loss_att'][0]
-        if not training:
+        if not training or getattr(self, '_stop_after', None) == 'ce':
             return loss_att, loss_cal
         # ---------------- backward ----------------
         dpen = jb['dpen']
@@ -236,6 +245,8 @@ class FusedTrainStep(object):
         E = m.item_embedding.weight
         posw = m.position_embedding.weight if m.use_position_embedding else None
         b['me'] = mask('emb')
+        # longest sequences first: order of the attention CTAs of this batch (forward and backward)
+        LIB.call('acsr_seq_order', _p(seq, torch.int64), Bs, L, _p(b['order'], torch.int32), st)
         LIB.call('acsr_embed_ln_dropout_fwd', _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight), _p(m.LayerNorm.bias),
                  m.LayerNorm.eps, T, L, d, V, p_h, _p(b['me']), rngp, soff + 1, _p(b['x0']), _p(b['st_e']), st)
         x = b['x0']
@@ -278,32 +289,32 @@ class FusedTrainStep(object):
             p_attn = aa.attn_dropout.p if training else 0.0
             lb['attn_args'] = self._attn_args(layer, lb, seq, Bs, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base)
             ctx_cal, ctx_att = lb['ctx'][:T], (lb['ctx'][T:] if last else None)
-            LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal), jb['pen'][l:].data_ptr(), None, st)
-            lb['m_a'] = mask2(l, 'D5', 'D4', last)
-            lb['m_f'] = mask2(l, 'D7', 'D6', last)
-            if self.tc:
-                # out-projection + bias + dropout + residual + LayerNorm in one kernel; FFN: GEMM, bias + activation, then
-                # GEMM + bias + dropout + residual + LayerNorm
-                ops.linear_tok_bdrl(lb['ctx'], R, d, aa.dense.weight, aa.dense.bias, x, T, aa.LayerNorm.weight, aa.LayerNorm.bias,
-                                    aa.LayerNorm.eps, p_h, lb['m_a'], rngp, base + 3, lb['hz'], lb['h'], lb['st_a'])
-                # (the fused bias+activation epilogue, acsr_linear_tok_act, is slower than GEMM + the row-wise kernel at I=256:
-                # four epilogue warps per SM cannot hide the erf latency)
-                ops.linear_tok(lb['h'], R, d, ff.dense_1.weight, I, lb['z1'], I)
-                LIB.call('acsr_bias_act_fwd', _p(lb['z1']), _p(ff.dense_1.bias), R, I, act_id, _p(lb['a1']), st)
-                ops.linear_tok_bdrl(lb['a1'], R, I, ff.dense_2.weight, ff.dense_2.bias, lb['h'], R, ff.LayerNorm.weight,
-                                    ff.LayerNorm.bias, ff.LayerNorm.eps, p_h, lb['m_f'], rngp, base + 5, lb['z2'], lb['out'],
-                                    lb['st_f'])
-            else:
-                torch.mm(lb['ctx'], aa.dense.weight.t(), out=lb['hz'])
-                LIB.call('acsr_bias_dropout_res_ln_fwd', _p(lb['hz']), _p(aa.dense.bias), _p(x), _p(aa.LayerNorm.weight),
-                         _p(aa.LayerNorm.bias), aa.LayerNorm.eps, R, d, T, p_h, _p(lb['m_a']), rngp, base + 3, _p(lb['h']),
-                         _p(lb['st_a']), st)
-                torch.mm(lb['h'], ff.dense_1.weight.t(), out=lb['z1'])
-                LIB.call('acsr_bias_act_fwd', _p(lb['z1']), _p(ff.dense_1.bias), R, I, act_id, _p(lb['a1']), st)
-                torch.mm(lb['a1'], ff.dense_2.weight.t(), out=lb['z2'])
-                LIB.call('acsr_bias_dropout_res_ln_fwd', _p(lb['z2']), _p(ff.dense_2.bias), _p(lb['h']), _p(ff.LayerNorm.weight),
-                         _p(ff.LayerNorm.bias), ff.LayerNorm.eps, R, d, R, p_h, _p(lb['m_f']), rngp, base + 5, _p(lb['out']),
-                         _p(lb['st_f']), st)
+            LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal), jb['pen'][l:].data_ptr(), None,
+                     _p(b['order'], torch.int32), st)
+            m_a, m_f = mask2(l, 'D5', 'D4', last), mask2(l, 'D7', 'D6', last)
+            if l == N - 1 and self.compact_last:
+                # ---- last layer: gather position len-1 of every sequence, then the dense part on the compact rows ----
+                cb = b['c']
+                C = 2 * Bs if need_att else Bs
+                LIB.call('acsr_gather_last_fwd', _p(lb['ctx'][:T]) if need_att else None, _p(lb['ctx'][T:] if need_att else lb['ctx'][:T]),
+                         _p(ln, torch.int64), Bs, L, d, _p(cb['ctx']), st)
+                LIB.call('acsr_gather_last_fwd', None, _p(x), _p(ln, torch.int64), Bs, L, d, _p(cb['x']), st)
+                if m_a is not None or m_f is not None:           # explicit masks of a parity test: the same rows
+                    idx = torch.arange(Bs, device=seq.device) * L + ln - 1
+                    rows = torch.cat((idx, T + idx)) if need_att else idx
+                    m_a = None if m_a is None else m_a.reshape(-1, d)[rows].contiguous()
+                    m_f = None if m_f is None else m_f.reshape(-1, d)[rows].contiguous()
+                cb['m_a'], cb['m_f'] = m_a, m_f
+                out_buf = jb['out2'] if Bs == B else cb['out']   # a single branch writes the joint buffer directly
+                self._post_attn_fwd(layer, cb, cb['x'], Bs, C, out_buf, p_h, rngp, base, act_id, st)
+                if Bs != B:
+                    lo = br['sl'].start
+                    jb['out2'][lo:lo + Bs].copy_(cb['out'][:Bs])
+                    if need_att:
+                        jb['out2'][B + lo:B + lo + Bs].copy_(cb['out'][Bs:C])
+                return
+            lb['m_a'], lb['m_f'] = m_a, m_f
+            self._post_attn_fwd(layer, lb, x, T, R, lb['out'], p_h, rngp, base, act_id, st)
             x = lb['out'][:T]
         last_out = b['layers'][N - 1]['out']
         # rows [0,B) of out2 calibrated, [B,2B) attacked; this branch owns the rows of its sequences in both halves
@@ -311,6 +322,35 @@ class FusedTrainStep(object):
         LIB.call('acsr_gather_last_fwd', None, _p(last_out[:T]), _p(ln, torch.int64), Bs, L, d, _p(jb['out2'][lo:lo + Bs]), st)
         if need_att:
             LIB.call('acsr_gather_last_fwd', None, _p(last_out[T:]), _p(ln, torch.int64), Bs, L, d, _p(jb['out2'][B + lo:B + lo + Bs]), st)
+
+    def _post_attn_fwd(self, layer, bf, x_res, res_rows, R, out, p_h, rngp, base, act_id, st):
+        """out-projection + dropout + residual + LayerNorm, then the feed-forward block, on R rows of bf['ctx']
+        (layers.py:676-684, 790-798).  x_res [res_rows, d] is the layer input (residual)."""
+        m = self.m
+        d, I = m.hidden_size, m.inner_size
+        aa, ff = layer.attack_attention, layer.feed_forward
+        if self.tc:
+            # out-projection + bias + dropout + residual + LayerNorm in one kernel; FFN: GEMM, bias + activation, then
+            # GEMM + bias + dropout + residual + LayerNorm
+            ops.linear_tok_bdrl(bf['ctx'], R, d, aa.dense.weight, aa.dense.bias, x_res, res_rows, aa.LayerNorm.weight,
+                                aa.LayerNorm.bias, aa.LayerNorm.eps, p_h, bf['m_a'], rngp, base + 3, bf['hz'], bf['h'], bf['st_a'])
+            # (the fused bias+activation epilogue, acsr_linear_tok_act, is slower than GEMM + the row-wise kernel at I=256:
+            # four epilogue warps per SM cannot hide the erf latency)
+            ops.linear_tok(bf['h'], R, d, ff.dense_1.weight, I, bf['z1'], I)
+            LIB.call('acsr_bias_act_fwd', _p(bf['z1']), _p(ff.dense_1.bias), R, I, act_id, _p(bf['a1']), st)
+            ops.linear_tok_bdrl(bf['a1'], R, I, ff.dense_2.weight, ff.dense_2.bias, bf['h'], R, ff.LayerNorm.weight,
+                                ff.LayerNorm.bias, ff.LayerNorm.eps, p_h, bf['m_f'], rngp, base + 5, bf['z2'], out, bf['st_f'])
+        else:
+            torch.mm(bf['ctx'][:R], aa.dense.weight.t(), out=bf['hz'][:R])
+            LIB.call('acsr_bias_dropout_res_ln_fwd', _p(bf['hz']), _p(aa.dense.bias), _p(x_res), _p(aa.LayerNorm.weight),
+                     _p(aa.LayerNorm.bias), aa.LayerNorm.eps, R, d, res_rows, p_h, _p(bf['m_a']), rngp, base + 3, _p(bf['h']),
+                     _p(bf['st_a']), st)
+            torch.mm(bf['h'][:R], ff.dense_1.weight.t(), out=bf['z1'][:R])
+            LIB.call('acsr_bias_act_fwd', _p(bf['z1']), _p(ff.dense_1.bias), R, I, act_id, _p(bf['a1']), st)
+            torch.mm(bf['a1'][:R], ff.dense_2.weight.t(), out=bf['z2'][:R])
+            LIB.call('acsr_bias_dropout_res_ln_fwd', _p(bf['z2']), _p(ff.dense_2.bias), _p(bf['h']), _p(ff.LayerNorm.weight),
+                     _p(ff.LayerNorm.bias), ff.LayerNorm.eps, R, d, R, p_h, _p(bf['m_f']), rngp, base + 5, _p(out),
+                     _p(bf['st_f']), st)
 
     @torch.no_grad()
     def encode_eval(self, item_seq, item_seq_len):
@@ -352,11 +392,13 @@ class FusedTrainStep(object):
             return side.cuda_stream
 
         d_out, d_x = b['d_out'], b['d_x']
-        d_out.zero_()
         lo = br['sl'].start
-        LIB.call('acsr_gather_last_bwd', _p(jb['d_out2'][lo:lo + Bs]), _p(ln, torch.int64), Bs, L, d, None, _p(d_out[:T]), st)
-        LIB.call('acsr_gather_last_bwd', _p(jb['d_out2'][B + lo:B + lo + Bs]), _p(ln, torch.int64), Bs, L, d, None, _p(d_out[T:]), st)
         T2 = 2 * T
+        compact = self.compact_last
+        if not compact:
+            d_out.zero_()
+            LIB.call('acsr_gather_last_bwd', _p(jb['d_out2'][lo:lo + Bs]), _p(ln, torch.int64), Bs, L, d, None, _p(d_out[:T]), st)
+            LIB.call('acsr_gather_last_bwd', _p(jb['d_out2'][B + lo:B + lo + Bs]), _p(ln, torch.int64), Bs, L, d, None, _p(d_out[T:]), st)
         for l in reversed(range(N)):
             last = l == N - 1
             P = T2 if last else T                               # period of the saved forward tensors
@@ -366,35 +408,24 @@ class FusedTrainStep(object):
             base = soff + 16 * (l + 1)
             x = b['xs'][l]
             gate = layer.combine_option == 'gate'
-            # FFN
-            LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_out), _p(lb['z2']), _p(ff.dense_2.bias), _p(lb['h']),
-                     _p(ff.LayerNorm.weight), _p(lb['st_f']), T2, d, P, P, T, p_h, _p(lb['m_f']), rngp, base + 5,
-                     _p(lb['d_z2']), _p(b['d_h']), _p(ff.dense_2.bias.grad), _p(ff.LayerNorm.weight.grad),
-                     _p(ff.LayerNorm.bias.grad), st)
-            sst = fork()
-            LIB.call('acsr_linear_wgrad', _p(lb['d_z2']), _p(lb['a1']), T, d, I, _p(ff.dense_2.weight.grad), None, sst)
-            if self.tc:                                      # d_a1 = d_z2.W2 : the weight is read transposed
-                ops.linear_tok(lb['d_z2'], T2, d, ff.dense_2.weight, I, b['d_a1'], I, w_sn=1, w_sk=I, wkb=64 * I)
+            if last and compact:
+                # the dense part of the last layer on the 2*Bs rows that carry a cotangent, then scatter into the zeroed
+                # token-major buffers the attention backward (d_ctx) and the layer below (residual path, d_x) read
+                cb = b['c']
+                C = 2 * Bs
+                if Bs == B:
+                    dc_out = jb['d_out2']
+                else:
+                    dc_out = cb['d_out']
+                    dc_out[:Bs].copy_(jb['d_out2'][lo:lo + Bs])
+                    dc_out[Bs:].copy_(jb['d_out2'][B + lo:B + lo + Bs])
+                self._post_attn_bwd(layer, cb, cb, dc_out, cb['x'], C, C, Bs, Bs, cb['d_x'], cb['d_ctx'], p_h, rngp, base, act_id, st, fork)
+                b['d_ctx'].zero_()
+                d_x.zero_()
+                LIB.call('acsr_gather_last_bwd', _p(cb['d_ctx']), _p(ln, torch.int64), Bs, L, d, _p(b['d_ctx'][:T]), _p(b['d_ctx'][T:]), st)
+                LIB.call('acsr_gather_last_bwd', _p(cb['d_x']), _p(ln, torch.int64), Bs, L, d, _p(d_x[:T]), _p(d_x[T:]), st)
             else:
-                torch.mm(lb['d_z2'], ff.dense_2.weight, out=b['d_a1'])
-            LIB.call('acsr_bias_act_bwd', _p(b['d_a1']), _p(lb['z1']), _p(ff.dense_1.bias), T2, I, act_id, P, T, _p(lb['d_z1']),
-                     _p(ff.dense_1.bias.grad), st)
-            sst = fork()
-            LIB.call('acsr_linear_wgrad', _p(lb['d_z1']), _p(lb['h']), T, I, d, _p(ff.dense_1.weight.grad), None, sst)
-            if self.tc:
-                ops.linear_tok(lb['d_z1'], T2, I, ff.dense_1.weight, d, b['d_h'], d, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
-            else:
-                b['d_h'].addmm_(lb['d_z1'], ff.dense_1.weight)
-            # attention output projection
-            LIB.call('acsr_bias_dropout_res_ln_bwd', _p(b['d_h']), _p(lb['hz']), _p(aa.dense.bias), _p(x),
-                     _p(aa.LayerNorm.weight), _p(lb['st_a']), T2, d, P, T, T, p_h, _p(lb['m_a']), rngp, base + 3,
-                     _p(lb['d_hz']), _p(d_x), _p(aa.dense.bias.grad), _p(aa.LayerNorm.weight.grad), _p(aa.LayerNorm.bias.grad), st)
-            sst = fork()
-            LIB.call('acsr_linear_wgrad', _p(lb['d_hz']), _p(lb['ctx']), T, d, d, _p(aa.dense.weight.grad), None, sst)
-            if self.tc:
-                ops.linear_tok(lb['d_hz'], T2, d, aa.dense.weight, d, b['d_ctx'], d, w_sn=1, w_sk=d, wkb=64 * d)
-            else:
-                torch.mm(lb['d_hz'], aa.dense.weight, out=b['d_ctx'])
+                self._post_attn_bwd(layer, lb, lb, d_out, x, T2, P, T, T, d_x, b['d_ctx'], p_h, rngp, base, act_id, st, fork, b=b)
             # fused attention backward
             if gate:
                 lb['d_gl'].zero_()
@@ -408,7 +439,8 @@ class FusedTrainStep(object):
             d_att1, d_cal1 = (dc[T:], None) if last else (None, dc[T:])
             LIB.call('acsr_attn_calib_bwd2', _p(dc[:T]), None, _p(d_att1), _p(d_cal1), _p(dpen[l:l + 1]), *lb['attn_args'],
                      _p(lb['d_mq']), _p(lb['d_mk']), _p(lb['d_mv']), _p(lb['d_aq']), _p(lb['d_ak']),
-                     _p(lb['d_gl']) if gate else None, _p(g(ow)), _p(g(ob_)), _p(g(dw)), _p(g(db_)), _p(g(sc)), _p(g(rr)), st)
+                     _p(lb['d_gl']) if gate else None, _p(g(ow)), _p(g(ob_)), _p(g(dw)), _p(g(db_)), _p(g(sc)), _p(g(rr)),
+                     _p(b['order'], torch.int32), st)
             # projections: input gradients for both streams, weight gradients from the owning stream
             aqt, akt = aa.attack_query_transform, aa.attack_key_transform
             st3 = self._stacked(l)
@@ -461,6 +493,45 @@ class FusedTrainStep(object):
                  _p(m.LayerNorm.weight.grad), _p(m.LayerNorm.bias.grad), st)
         if side is not None:
             main.wait_stream(side)                            # join: every weight gradient of this branch landed
+
+    def _post_attn_bwd(self, layer, bf, gb, d_out, x_res, R2, P, res_rows, w_rows, d_xres, d_ctx, p_h, rngp, base, act_id, st, fork, b=None):
+        """backward of _post_attn_fwd over R2 cotangent rows ([stream 0 ; stream 1]); the saved forward tensors of bf repeat
+        with period P, the residual x_res with period res_rows; rows [0, w_rows) (stream 0) feed the parameter gradients.
+        Writes the gradient of the attention context to d_ctx and of the residual input to d_xres."""
+        m = self.m
+        d, I = m.hidden_size, m.inner_size
+        aa, ff = layer.attack_attention, layer.feed_forward
+        d_h = gb['d_h'] if b is None else b['d_h']
+        d_a1 = gb['d_a1'] if b is None else b['d_a1']
+        # FFN
+        LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_out), _p(bf['z2']), _p(ff.dense_2.bias), _p(bf['h']),
+                 _p(ff.LayerNorm.weight), _p(bf['st_f']), R2, d, P, P, w_rows, p_h, _p(bf['m_f']), rngp, base + 5,
+                 _p(gb['d_z2']), _p(d_h), _p(ff.dense_2.bias.grad), _p(ff.LayerNorm.weight.grad),
+                 _p(ff.LayerNorm.bias.grad), st)
+        sst = fork()
+        LIB.call('acsr_linear_wgrad', _p(gb['d_z2']), _p(bf['a1']), w_rows, d, I, _p(ff.dense_2.weight.grad), None, sst)
+        if self.tc:                                      # d_a1 = d_z2.W2 : the weight is read transposed
+            ops.linear_tok(gb['d_z2'], R2, d, ff.dense_2.weight, I, d_a1, I, w_sn=1, w_sk=I, wkb=64 * I)
+        else:
+            torch.mm(gb['d_z2'][:R2], ff.dense_2.weight, out=d_a1[:R2])
+        LIB.call('acsr_bias_act_bwd', _p(d_a1), _p(bf['z1']), _p(ff.dense_1.bias), R2, I, act_id, P, w_rows, _p(gb['d_z1']),
+                 _p(ff.dense_1.bias.grad), st)
+        sst = fork()
+        LIB.call('acsr_linear_wgrad', _p(gb['d_z1']), _p(bf['h']), w_rows, I, d, _p(ff.dense_1.weight.grad), None, sst)
+        if self.tc:
+            ops.linear_tok(gb['d_z1'], R2, I, ff.dense_1.weight, d, d_h, d, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
+        else:
+            d_h[:R2].addmm_(gb['d_z1'][:R2], ff.dense_1.weight)
+        # attention output projection
+        LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_h), _p(bf['hz']), _p(aa.dense.bias), _p(x_res),
+                 _p(aa.LayerNorm.weight), _p(bf['st_a']), R2, d, P, res_rows, w_rows, p_h, _p(bf['m_a']), rngp, base + 3,
+                 _p(gb['d_hz']), _p(d_xres), _p(aa.dense.bias.grad), _p(aa.LayerNorm.weight.grad), _p(aa.LayerNorm.bias.grad), st)
+        sst = fork()
+        LIB.call('acsr_linear_wgrad', _p(gb['d_hz']), _p(bf['ctx']), w_rows, d, d, _p(aa.dense.weight.grad), None, sst)
+        if self.tc:
+            ops.linear_tok(gb['d_hz'], R2, d, aa.dense.weight, d, d_ctx, d, w_sn=1, w_sk=d, wkb=64 * d)
+        else:
+            torch.mm(gb['d_hz'][:R2], aa.dense.weight, out=d_ctx[:R2])
 
     def _stacked(self, l):
         """stacked views [3,d,d]/[2,d,d] of the Q/K/V and attack-pair parameters (adjacent in FlatAdam's layout)."""

@@ -9,6 +9,8 @@ import ac_tsr_b200 as A
 from ac_tsr_b200 import ops
 
 dev = torch.device('cuda')
+ORDER = [None]
+USE_ORDER = os.environ.get('ATTN_ORDER', '1') == '1'
 H, dh, L = 2, 32, 50
 d = H * dh
 
@@ -24,6 +26,9 @@ def run(B, lens, p=0.5, need_att=True, iters=30, bwd=False, last=True):
     ow, ob = torch.randn(2 * dh).to(dev) * .1, torch.randn(1).to(dev) * .1
     dw, db, sc = torch.randn(2 * dh).to(dev) * .1, torch.randn(1).to(dev) * .1, torch.randn(1).to(dev)
     rng = ops.DeviceRng(1, dev)
+    order = torch.empty(B, dtype=torch.int32, device=dev)
+    A.LIB.call('acsr_seq_order', seq.data_ptr(), B, L, order.data_ptr(), ops._stream())
+    ORDER[0] = order.data_ptr() if USE_ORDER else None
     ca, cc = torch.empty(B, L, d, device=dev), torch.empty(B, L, d, device=dev)
     pen = torch.zeros(1, dtype=torch.float64, device=dev)
     P = ops._p
@@ -50,10 +55,10 @@ def run(B, lens, p=0.5, need_att=True, iters=30, bwd=False, last=True):
 
         def f():
             A.LIB.call('acsr_attn_calib_bwd2', P(dc[:T]), None, P(att1), P(cal1), P(dpen), *shared, *[P(o) for o in outs], P(dgl),
-                       P(pg[0]), P(pg[1]), P(pg[2]), P(pg[3]), P(pg[4]), None, ops._stream())
+                       P(pg[0]), P(pg[1]), P(pg[2]), P(pg[3]), P(pg[4]), None, ORDER[0], ops._stream())
     else:
         def f():
-            A.LIB.call('acsr_attn_calib_fwd', *shared, P(ca) if need_att else None, P(cc), pen.data_ptr(), None, ops._stream())
+            A.LIB.call('acsr_attn_calib_fwd', *shared, P(ca) if need_att else None, P(cc), pen.data_ptr(), None, ORDER[0], ops._stream())
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
         st = ops._stream()

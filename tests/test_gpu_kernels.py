@@ -282,7 +282,7 @@ def test_attn_calib_backward(A, case, which):
         assert float((got.cpu() - ref).abs().max()) <= 5e-4 * scale + 1e-6, (k, got, ref)
 
 
-def _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, cots, dual):
+def _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, cots, dual, order=None):
     """raw C-ABI call of the attention backward.  cots = (cal0, pen0, att1, cal1, pen1) device tensors or None."""
     H = cfg['n_heads']
     B, L, d = t['mq'].shape
@@ -311,9 +311,9 @@ def _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, cots, dual):
     cal0, pen0, att1, cal1, pen1 = cots
     st = A.ops._stream()
     if dual:
-        A.LIB.call('acsr_attn_calib_bwd2', P(cal0), P(pen0), P(att1), P(cal1), P(pen1), *shared, *outs, st)
+        A.LIB.call('acsr_attn_calib_bwd2', P(cal0), P(pen0), P(att1), P(cal1), P(pen1), *shared, *outs, P(order, torch.int32), st)
     else:
-        A.LIB.call('acsr_attn_calib_bwd', P(att1), P(cal0), P(pen0), *shared, *outs, st)
+        A.LIB.call('acsr_attn_calib_bwd', P(att1), P(cal0), P(pen0), *shared, *outs, P(order, torch.int32), st)
     torch.cuda.synchronize()
     return out, pg
 
@@ -333,7 +333,11 @@ def test_attn_calib_backward_two_streams(A, case, last):
         g1[:, :L - 1] = 0.0
     pen = torch.tensor([0.01]).cuda()
     att1, cal1 = (g1, None) if last else (None, g1)
-    both, pg_both = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (g0, None, att1, cal1, pen), dual=True)
+    order = torch.empty(B, dtype=torch.int32, device='cuda')          # longest-first CTA order must not change results
+    A.LIB.call('acsr_seq_order', seq.cuda().data_ptr(), B, L, order.data_ptr(), A.ops._stream())
+    nkey = [(int((seq[b] != 0).nonzero().max()) + 1) if bool((seq[b] != 0).any()) else 0 for b in range(B)]
+    assert sorted(order.tolist()) == list(range(B)) and all(nkey[order[i]] >= nkey[order[i + 1]] for i in range(B - 1))
+    both, pg_both = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (g0, None, att1, cal1, pen), dual=True, order=order)
     s0, pg0 = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (g0, None, None, None, None), dual=False)
     s1, _ = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (cal1, pen, att1, None, None), dual=False)
     T = B * L
