@@ -80,6 +80,35 @@ class _Lib:
         return getattr(self.load(), name)(*args)
 
 
+def _ab_linear_tok(a):
+    # (X, ldx, xkb, rows, K, W, w_sn, w_sk, wkb, N, bias, accumulate, Y, ldy, batch, ...)
+    rows, K, N, acc, batch = a[3], a[4], a[9], a[11], a[14]
+    return 4 * batch * (rows * K + rows * N * (2 if acc else 1) + N * K)
+
+
+def _ab_linear_tok_bdrl(a):
+    # (X, ldx, rows, K, W, bias, res, res_rows, ...): X, W in; HZ, out, stats out; residual in
+    rows, K = a[2], a[3]
+    return 4 * (rows * K + 64 * K + 3 * rows * 64 + 2 * rows)
+
+
+def _ab_linear_wgrad(a):
+    # (dY, X, T, N, K, dW, db, stream)
+    T, N, K = a[2], a[3], a[4]
+    return 4 * (T * (N + K) + N * K)
+
+
+def _ab_linear_wgrad_batched(a):
+    # (dY, X, T, N, K, dW, db, batch, ...)
+    T, N, K, batch = a[2], a[3], a[4], a[7]
+    return 4 * batch * (T * (N + K) + N * K)
+
+
+# ALGORITHMIC bytes of one launch, from the call's own arguments
+ALGO_BYTES = {'acsr_linear_tok': _ab_linear_tok, 'acsr_linear_tok_bdrl': _ab_linear_tok_bdrl,
+              'acsr_linear_wgrad': _ab_linear_wgrad, 'acsr_linear_wgrad_batched': _ab_linear_wgrad_batched}
+
+
 class KernelTimer:
     """Brackets every C-ABI launch with CUDA events on the launching (current torch) stream.
     Used by bench.py for the per-kernel share / roofline numbers; never active in the timed step."""
@@ -97,17 +126,20 @@ class KernelTimer:
         if rc != 0:
             msg = dll.acsr_last_error()
             raise AcsrError('%s failed (%d): %s' % (name, rc, msg.decode() if msg else ''))
-        self.events.append((name, e0, e1))
+        fn = ALGO_BYTES.get(name)
+        self.events.append((name, e0, e1, fn(args) if fn is not None else None))
         self.launches += 1
 
     def summary(self):
-        """-> {name: (n_calls, total_ms)} after a device synchronize."""
+        """-> {name: (n_calls, total_ms)} after a device synchronize; self.bytes = {name: algorithmic bytes or None}."""
         import torch
         torch.cuda.synchronize()
-        out = {}
-        for name, e0, e1 in self.events:
+        out, self.bytes = {}, {}
+        for name, e0, e1, ab in self.events:
             n, t = out.get(name, (0, 0.0))
             out[name] = (n + 1, t + e0.elapsed_time(e1))
+            if ab is not None:
+                self.bytes[name] = self.bytes.get(name, 0) + ab
         return out
 
 

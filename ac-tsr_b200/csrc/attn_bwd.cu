@@ -268,6 +268,67 @@ __device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem
   __syncwarp();
 }
 
+// row group iteration for rows whose context carries no cotangent by contract (ctx_rows): only the penalty reaches them,
+// through the attack mask: dS' of the streams with a penalty cotangent, dq'_i; everything else of the row is zero
+template <int DH, int G, int NJ, int NS>
+__device__ __forceinline__ void bwd_row_iter_m(const AttnParams& p, const AttnSmem& sm, const BwdSmem<NS>& bs, const RowConst& kc,
+                                               const float* dpen, int b, int h, int i, bool rowok, int bound, int grp, int sub,
+                                               int rstride, float* wbuf) {
+  constexpr int dhp = DH + 4;
+  using CM = CMap<DH, G>;
+  const int L = p.L, LP = (L + 3) & ~3;
+  float Msoft[NJ], D3[NJ];
+  unsigned act;
+  row_forward_m<DH, G, NJ>(p, sm, kc, b, h, i, bound, sub, Msoft, D3, act);
+  float* gbuf = wbuf + grp * 2 * NS * rstride;
+  const int c0 = CM::c0(sub);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const float dp = dpen[s];
+    float o2[CM::CPL];
+#pragma unroll
+    for (int k = 0; k < CM::CPL; ++k) o2[k] = 0.f;
+    if (dp != 0.f) {
+      float dM[NJ], dS2[NJ];
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) dM[jj] = ((act >> jj) & 1u) ? dp * (-2.0f) * (1.0f - Msoft[jj] * D3[jj]) * D3[jj] : 0.f;
+      softmax_bwd_row<G, NJ>(Msoft, dM, dS2);
+      float* bufS2 = gbuf + (2 * s + 1) * rstride;
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) {
+        const int j = sub + G * jj;
+        const bool a = ((act >> jj) & 1u) && rowok;
+        const float v = dS2[jj] * kc.inv_sq;
+        if (j < rstride) bufS2[j] = a ? v : 0.f;
+        if (a) bs.matS2T[s][tri_off(j, LP) - (j & ~3) + i] = v;
+      }
+      __syncwarp();
+      int lo, hi;
+      CM::slice(sub, 0, (bound + 3) & ~3, lo, hi);
+      for (int j = lo; j < hi; j += 4) {
+        const float4 s2 = *reinterpret_cast<const float4*>(bufS2 + j);
+        const float s2v[4] = {s2.x, s2.y, s2.z, s2.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float k2v[CM::CPL];
+          VecLd<CM::CPL>::ld(sm.K2 + (j + u) * dhp + c0, k2v);
+#pragma unroll
+          for (int k = 0; k < CM::CPL; ++k) o2[k] = fmaf(s2v[u], k2v[k], o2[k]);
+        }
+      }
+      __syncwarp();
+    }
+    float o1[CM::CPL];
+#pragma unroll
+    for (int k = 0; k < CM::CPL; ++k) { o2[k] = CM::reduce(o2[k]); o1[k] = 0.f; }
+    if (CM::split(sub) == 0 && rowok) {
+      const long long o = s * p.s1_td + ((long long)b * L + i) * p.d + h * DH + c0;
+      VecLd<CM::CPL>::st(p.d_mq + o, o1);
+      VecLd<CM::CPL>::st(p.d_aq + o, o2);
+    }
+  }
+}
+
 // row phase + column phase of the (b,h) tile with G-lane groups
 template <int DH, int G, int MAXNJ, int NS>
 __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm, const BwdSmem<NS>& bs, const RowConst& kc,
@@ -280,6 +341,7 @@ __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm
   const int grp = lane / G, sub = lane % G;
   const int c0 = CM::c0(sub);
   float* wbuf = bs.rowbuf + warp * rowbuf_floats_per_warp(LP, 2 * NS);
+  const int rt = p.ctx_rows ? (int)p.ctx_rows[b] - 1 : -1;     // the only row with a context cotangent, or -1: all rows
   float accOq[CM::CPL], accDq[CM::CPL], accOk[CM::CPL], accDk[CM::CPL];
 #pragma unroll
   for (int k = 0; k < CM::CPL; ++k) accOq[k] = accDq[k] = accOk[k] = accDk[k] = 0.f;
@@ -290,6 +352,15 @@ __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm
     const int i = rowok ? iraw : 0;
     const int bound = min(i + 1, nkey);
     const int nj = (min(iw + 1, nkey) + G - 1) / G;
+    if (rt >= 0 && (rt > iw || rt <= iw - RPW)) {       // rows without a context cotangent: penalty path only
+#define ACSR_BWD_ROW_M(NJV) bwd_row_iter_m<DH, G, NJV, NS>(p, sm, bs, kc, dpen, b, h, i, rowok, bound, grp, sub, rstride, wbuf)
+      if (MAXNJ == 1 || nj == 1) ACSR_BWD_ROW_M(1);
+      else if (nj == 2) ACSR_BWD_ROW_M((MAXNJ >= 2 ? 2 : 1));
+      else if (nj == 3) ACSR_BWD_ROW_M((MAXNJ >= 3 ? 3 : 1));
+      else ACSR_BWD_ROW_M((MAXNJ >= 4 ? 4 : 1));
+#undef ACSR_BWD_ROW_M
+      continue;
+    }
 #define ACSR_BWD_ROW(NJV) \
   bwd_row_iter<DH, G, NJV, NS>(p, sm, bs, kc, f, dpen, b, h, i, rowok, bound, grp, sub, rstride, wbuf, acc, accOq, accDq)
     if (MAXNJ == 1 || nj == 1) ACSR_BWD_ROW(1);
@@ -504,10 +575,11 @@ int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const fl
                         const float* rich_ratio, float p_attn, const float* D1, const float* D2, const float* D3,
                         const float* noise, const void* rng, uint32_t rng_stream, float* d_mq, float* d_mk, float* d_mv,
                         float* d_aq, float* d_ak, float* d_gate_logit, float* d_order_w, float* d_order_b, float* d_dist_w,
-                        float* d_dist_b, float* d_scalar, float* d_rich_ratio, const int32_t* order, void* stream) {
+                        float* d_dist_b, float* d_scalar, float* d_rich_ratio, const int32_t* order, const int64_t* ctx_rows,
+                        void* stream) {
   AttnParams p = {};
   attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
-                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, order);
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, order, ctx_rows);
   p.t0 = d_ctx_cal; p.t1 = d_ctx_att; p.t1_is_att = 1; p.d_pen0 = d_pen_sq;
   p.d_mq = d_mq; p.d_mk = d_mk; p.d_mv = d_mv; p.d_aq = d_aq; p.d_ak = d_ak; p.d_gate = d_gate_logit;
   p.d_ow = d_order_w; p.d_ob = d_order_b; p.d_dw = d_dist_w; p.d_db = d_dist_b; p.d_scalar = d_scalar; p.d_ratio = d_rich_ratio;
@@ -527,10 +599,10 @@ int acsr_attn_calib_bwd2(const float* d_ctx_cal0, const float* d_pen_sq0, const 
                          float p_attn, const float* D1, const float* D2, const float* D3, const float* noise, const void* rng,
                          uint32_t rng_stream, float* d_mq, float* d_mk, float* d_mv, float* d_aq, float* d_ak,
                          float* d_gate_logit, float* d_order_w, float* d_order_b, float* d_dist_w, float* d_dist_b,
-                         float* d_scalar, float* d_rich_ratio, const int32_t* order, void* stream) {
+                         float* d_scalar, float* d_rich_ratio, const int32_t* order, const int64_t* ctx_rows, void* stream) {
   AttnParams p = {};
   attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
-                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, order);
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, order, ctx_rows);
   ACSR_REQUIRE(!(d_ctx_att1 && d_ctx_cal1), "attn_calib_bwd2: stream 1 takes d_ctx_att or d_ctx_cal, not both");
   p.t0 = d_ctx_cal0; p.t1 = d_ctx_att1 ? d_ctx_att1 : d_ctx_cal1; p.t1_is_att = d_ctx_att1 != nullptr;
   p.d_pen0 = d_pen_sq0; p.d_pen1 = d_pen_sq1;

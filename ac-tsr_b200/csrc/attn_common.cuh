@@ -36,6 +36,8 @@ struct AttnParams {
   const float *mq, *mk, *mv, *aq, *ak, *gate;
   const int64_t* item_seq;
   const int32_t* order;      // sequence handled by CTA group g is order[g] (longest first), NULL = identity
+  const int64_t* ctx_rows;   // NULL, or [B]: only context row ctx_rows[b]-1 is consumed (last layer); the other rows only
+                             // contribute their attack mask to the penalty
   const float *ow, *ob, *dw, *db, *scalar;
   int B, L, H, dh, d;
   int two_level, combine, rich;
@@ -491,6 +493,52 @@ __device__ __forceinline__ void row_forward(const AttnParams& p, const AttnSmem&
   else softmax_row<G, NJ>(z, act, r.R);
 }
 
+// Attack mask of query row i only (softmax M and its dropout): all a row contributes when its context is not consumed.
+// Same column ownership and the same Philox words as row_forward.
+template <int DH, int G, int NJ>
+__device__ __forceinline__ void row_forward_m(const AttnParams& p, const AttnSmem& sm, const RowConst& kc, int b, int h, int i,
+                                              int bound, int sub, float* Msoft, float* D3, unsigned& act_out) {
+  constexpr int dhp = DH + 4;
+  const int L = p.L;
+  int jc[NJ];
+  float zM[NJ];
+  unsigned act = 0;
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const int j = sub + G * jj;
+    const bool a = j < bound;
+    act |= (a ? 1u : 0u) << jj;
+    jc[jj] = a ? j : 0;
+  }
+  act_out = act;
+  const long long ebase = (((long long)b * p.H + h) * L + i) * L;
+  const float4* q2i = reinterpret_cast<const float4*>(sm.Q2 + i * dhp);
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const float4* kj = reinterpret_cast<const float4*>(sm.K2 + jc[jj] * dhp);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < DH / 4; c4 += 2) { s0 = dot4(q2i[c4], kj[c4], s0); s1 = dot4(q2i[c4 + 1], kj[c4 + 1], s1); }
+    const bool v = ((act >> jj) & 1u) && (jc[jj] <= i) && (sm.keyok[jc[jj]] != 0.f);
+    zM[jj] = (s0 + s1) * kc.inv_sq + (v ? 0.f : kMaskNeg);
+  }
+  softmax_row<G, NJ>(zM, act, Msoft);
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) D3[jj] = 1.0f;
+  if (kc.philox_drop) {
+#pragma unroll
+    for (int jj = 0; jj < NJ; jj += 2) {
+      const uint4 w = philox4x32(kc.seed, kc.step, p.stream, (unsigned long long)(ebase + jc[jj]));
+      D3[jj] = ((w.x >> 16) >= kc.thr16) ? kc.inv_keep : 0.f;
+      if (jj + 1 < NJ) D3[jj + 1] = ((w.y >> 16) >= kc.thr16) ? kc.inv_keep : 0.f;
+    }
+  }
+  if (p.D3) {
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) if ((act >> jj) & 1u) D3[jj] = p.D3[ebase + jc[jj]];
+  }
+}
+
 __device__ __forceinline__ AttnSmem carve_common(float*& ptr, int LP, int dh) {
   AttnSmem sm;
   const int tile = LP * (dh + 4);
@@ -553,8 +601,8 @@ static inline void attn_fill_common(AttnParams& p, const float* mq, const float*
                                     const float* order_b, const float* dist_w, const float* dist_b, const float* scalar, int B,
                                     int L, int H, int dh, int two_level, int combine_option, float comb_scalar, int rich_mode,
                                     const float* rich_ratio, float p_attn, const float* D1, const float* D2, const float* D3,
-                                    const float* noise, const void* rng, uint32_t rng_stream, const int32_t* order) {
-  p.order = order;
+                                    const float* noise, const void* rng, uint32_t rng_stream, const int32_t* order, const int64_t* ctx_rows) {
+  p.order = order; p.ctx_rows = ctx_rows;
   p.mq = mq; p.mk = mk; p.mv = mv; p.aq = aq; p.ak = ak; p.gate = combine_option == ACSR_ATTN_COMBINE_GATE ? gate_logit : nullptr;
   p.item_seq = item_seq;
   p.ow = order_w; p.ob = order_b; p.dw = dist_w; p.db = dist_b; p.scalar = scalar;

@@ -74,6 +74,20 @@ __device__ __forceinline__ void fwd_row_iter(const AttnParams& p, const AttnSmem
   __syncwarp();
 }
 
+// row group iteration for rows whose context nobody reads: attack mask -> penalty only
+template <int DH, int G, int NJ>
+__device__ __forceinline__ void fwd_row_iter_m(const AttnParams& p, const AttnSmem& sm, const RowConst& kc, int b, int h, int i,
+                                               bool rowok, int bound, int sub, FwdCtx& cx) {
+  float Msoft[NJ], D3[NJ];
+  unsigned act;
+  row_forward_m<DH, G, NJ>(p, sm, kc, b, h, i, bound, sub, Msoft, D3, act);
+  if (!rowok) return;
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj)
+    if ((act >> jj) & 1u) { const float om = 1.0f - Msoft[jj] * D3[jj]; cx.pen = fmaf(om, om, cx.pen); }
+  if (sub == 0) cx.pen += (float)(p.L - bound);
+}
+
 // all rows of the (b,h) tile with G-lane row groups; the heaviest rows go first
 template <int DH, int G, int MAXNJ>
 __device__ __forceinline__ void fwd_rows(const AttnParams& p, const AttnSmem& sm, const RowConst& kc, int b, int h, int nkey,
@@ -82,6 +96,7 @@ __device__ __forceinline__ void fwd_rows(const AttnParams& p, const AttnSmem& sm
   const int L = p.L;
   const int lane = threadIdx.x & 31;
   const int grp = lane / G, sub = lane % G;
+  const int rt = p.ctx_rows ? (int)p.ctx_rows[b] - 1 : -1;     // the only consumed context row, or -1: all rows
   for (int t0 = next_task(sm.misc + 2, RPW); t0 < L; t0 = next_task(sm.misc + 2, RPW)) {   // heaviest rows first
     const int iw = L - 1 - t0;                    // largest row of this warp (>= 0)
     const int iraw = iw - grp;
@@ -89,6 +104,14 @@ __device__ __forceinline__ void fwd_rows(const AttnParams& p, const AttnSmem& sm
     const int i = rowok ? iraw : 0;
     const int bound = min(i + 1, nkey);
     const int nj = (min(iw + 1, nkey) + G - 1) / G;      // warp-uniform number of column groups
+    if (rt >= 0 && (rt > iw || rt <= iw - RPW)) {       // none of this warp's rows is the consumed one: mask + penalty only
+      if (p.pen_sq == nullptr) continue;
+      if (MAXNJ == 1 || nj == 1) fwd_row_iter_m<DH, G, 1>(p, sm, kc, b, h, i, rowok, bound, sub, cx);
+      else if (nj == 2) fwd_row_iter_m<DH, G, (MAXNJ >= 2 ? 2 : 1)>(p, sm, kc, b, h, i, rowok, bound, sub, cx);
+      else if (nj == 3) fwd_row_iter_m<DH, G, (MAXNJ >= 3 ? 3 : 1)>(p, sm, kc, b, h, i, rowok, bound, sub, cx);
+      else fwd_row_iter_m<DH, G, (MAXNJ >= 4 ? 4 : 1)>(p, sm, kc, b, h, i, rowok, bound, sub, cx);
+      continue;
+    }
     if (MAXNJ == 1 || nj == 1) fwd_row_iter<DH, G, 1>(p, sm, kc, b, h, i, rowok, bound, grp, sub, need_att, rstride, cx);
     else if (nj == 2) fwd_row_iter<DH, G, (MAXNJ >= 2 ? 2 : 1)>(p, sm, kc, b, h, i, rowok, bound, grp, sub, need_att, rstride, cx);
     else if (nj == 3) fwd_row_iter<DH, G, (MAXNJ >= 3 ? 3 : 1)>(p, sm, kc, b, h, i, rowok, bound, grp, sub, need_att, rstride, cx);
@@ -156,11 +179,17 @@ __global__ void __launch_bounds__(256) seq_order_kernel(const int64_t* __restric
   pdl_launch_dependents();
   pdl_wait();
   __shared__ int cnt[66], off[66];
+  __shared__ unsigned char key[2048];
   for (int i = threadIdx.x; i < 66; i += blockDim.x) cnt[i] = 0;
   __syncthreads();
+  // thread per sequence: the L loads of a row are independent, so they are all in flight at once
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    int nkey = 0;
-    for (int j = L - 1; j >= 0; --j) if (item_seq[(long long)b * L + j] != 0) { nkey = j + 1; break; }
+    const long long* row = reinterpret_cast<const long long*>(item_seq) + (long long)b * L;
+    unsigned long long m = 0ull;
+#pragma unroll 16
+    for (int j = 0; j < L; ++j) m |= (unsigned long long)(__ldg(row + j) != 0) << j;
+    const int nkey = m ? 64 - __clzll((long long)m) : 0;
+    key[b] = (unsigned char)nkey;
     atomicAdd(cnt + nkey, 1);
   }
   __syncthreads();
@@ -169,11 +198,7 @@ __global__ void __launch_bounds__(256) seq_order_kernel(const int64_t* __restric
     for (int k = 65; k >= 0; --k) { off[k] = run; run += cnt[k]; }
   }
   __syncthreads();
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    int nkey = 0;
-    for (int j = L - 1; j >= 0; --j) if (item_seq[(long long)b * L + j] != 0) { nkey = j + 1; break; }
-    order[atomicAdd(off + nkey, 1)] = b;
-  }
+  for (int b = threadIdx.x; b < B; b += blockDim.x) order[atomicAdd(off + key[b], 1)] = b;
 }
 
 }  // namespace acsr
@@ -181,7 +206,7 @@ __global__ void __launch_bounds__(256) seq_order_kernel(const int64_t* __restric
 using namespace acsr;
 
 extern "C" int acsr_seq_order(const int64_t* item_seq, int B, int L, int32_t* order, void* stream) {
-  ACSR_REQUIRE(item_seq && order && B > 0 && L > 0 && L <= 64, "seq_order: bad arguments");
+  ACSR_REQUIRE(item_seq && order && B > 0 && B <= 2048 && L > 0 && L <= 64, "seq_order: bad arguments (B <= 2048, L <= 64)");
   launch_pdl(seq_order_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, item_seq, B, L, order);
   return check_launch("seq_order");
 }
@@ -193,10 +218,10 @@ extern "C" int acsr_attn_calib_fwd(const float* mq, const float* mk, const float
                                    int two_level, int combine_option, float comb_scalar, int rich_mode, const float* rich_ratio,
                                    float p_attn, const float* D1, const float* D2, const float* D3, const float* noise,
                                    const void* rng, uint32_t rng_stream, float* ctx_att, float* ctx_cal, double* pen_sq,
-                                   float* probs_out, const int32_t* order, void* stream) {
+                                   float* probs_out, const int32_t* order, const int64_t* ctx_rows, void* stream) {
   AttnParams p = {};
   attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
-                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, order);
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, order, ctx_rows);
   p.ctx_att = ctx_att; p.ctx_cal = ctx_cal; p.pen_sq = pen_sq; p.probs = probs_out;
   int rc = attn_validate(p, "attn_calib_fwd");
   if (rc) return rc;

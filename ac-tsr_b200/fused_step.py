@@ -289,8 +289,9 @@ class FusedTrainStep(object):
             p_attn = aa.attn_dropout.p if training else 0.0
             lb['attn_args'] = self._attn_args(layer, lb, seq, Bs, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base)
             ctx_cal, ctx_att = lb['ctx'][:T], (lb['ctx'][T:] if last else None)
-            LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal), jb['pen'][l:].data_ptr(), None,
-                     _p(b['order'], torch.int32), st)
+            LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal),
+                     jb['pen'][l:].data_ptr() if need_att else None, None, _p(b['order'], torch.int32),
+                     _p(ln, torch.int64) if (l == N - 1 and self.compact_last) else None, st)
             m_a, m_f = mask2(l, 'D5', 'D4', last), mask2(l, 'D7', 'D6', last)
             if l == N - 1 and self.compact_last:
                 # ---- last layer: gather position len-1 of every sequence, then the dense part on the compact rows ----
@@ -440,7 +441,7 @@ class FusedTrainStep(object):
             LIB.call('acsr_attn_calib_bwd2', _p(dc[:T]), None, _p(d_att1), _p(d_cal1), _p(dpen[l:l + 1]), *lb['attn_args'],
                      _p(lb['d_mq']), _p(lb['d_mk']), _p(lb['d_mv']), _p(lb['d_aq']), _p(lb['d_ak']),
                      _p(lb['d_gl']) if gate else None, _p(g(ow)), _p(g(ob_)), _p(g(dw)), _p(g(db_)), _p(g(sc)), _p(g(rr)),
-                     _p(b['order'], torch.int32), st)
+                     _p(b['order'], torch.int32), _p(ln, torch.int64) if (last and compact) else None, st)
             # projections: input gradients for both streams, weight gradients from the owning stream
             aqt, akt = aa.attack_query_transform, aa.attack_key_transform
             st3 = self._stacked(l)

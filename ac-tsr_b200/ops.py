@@ -199,7 +199,7 @@ class AttnCalibFn(torch.autograd.Function):
                  _p(order_w), _p(order_b), _p(dist_w), _p(dist_b), _p(scalar), B, L, H, dh,
                  opts.two_level, opts.combine, float(comb_scalar), opts.rich, _p(rich_ratio),
                  p_attn, _p(D1), _p(D2), _p(D3), _p(noise), rngp, rng_stream,
-                 _p(ctx_att), _p(ctx_cal), pen.data_ptr(), _p(probs), None, _stream())
+                 _p(ctx_att), _p(ctx_cal), pen.data_ptr(), _p(probs), None, None, _stream())
         ctx.save_for_backward(mq, mk, mv, aq, ak, gate_logit, key_ids, order_w, order_b, dist_w, dist_b, scalar, rich_ratio,
                               D1, D2, D3, noise)
         ctx.meta = (B, L, H, dh, opts, float(comb_scalar), p_attn, rng, rng_stream, need_att)
@@ -229,7 +229,7 @@ class AttnCalibFn(torch.autograd.Function):
                  B, L, H, dh, opts.two_level, opts.combine, comb_scalar, opts.rich, _p(rich_ratio),
                  p_attn, _p(D1), _p(D2), _p(D3), _p(noise), rng.ptr if rng is not None else None, rng_stream,
                  _p(d_mq), _p(d_mk), _p(d_mv), _p(d_aq), _p(d_ak), _p(d_gate), _p(d_ow), _p(d_ob), _p(d_dw), _p(d_db),
-                 _p(d_sc), _p(d_rr), None, _stream())
+                 _p(d_sc), _p(d_rr), None, None, _stream())
         return (d_mq, d_mk, d_mv, d_aq, d_ak, d_gate, None, d_ow, d_ob, d_dw, d_db, d_sc, d_rr,
                 None, None, None, None, None, None, None, None)
 

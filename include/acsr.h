@@ -75,7 +75,10 @@ int acsr_embed_ln_dropout_bwd(const float* d_out, const int64_t* item_seq, const
  * accumulated: sum over b,h,i,j of (1-M)^2 (acsasrec.py:135).  probs_out NULL or
  * [6,B,H,L,L] = P0,P,M,A,C,R for introspection (layers.py:899-950).  L <= 64, dh <= 64. */
 /* order: NULL, or int32 [B] from acsr_seq_order: CTA group g works on sequence order[g] (longest first), which trims
- * the tail of the launch when lengths vary.  Results do not depend on it. */
+ * the tail of the launch when lengths vary.  Results do not depend on it.
+ * ctx_rows: NULL, or int64 [B] (the item_length tensor) for the LAST layer, where only context row ctx_rows[b]-1 of each
+ * sequence is consumed (gather_indexes, abstract_recommender.py:130-134): the other rows only compute their attack mask
+ * for the penalty, their context rows are not written, and in the backward their d_ctx rows are taken as zero. */
 int acsr_seq_order(const int64_t* item_seq, int B, int L, int32_t* order, void* stream);
 #define ACSR_ATTN_TWO_LEVEL 1
 #define ACSR_ATTN_COMBINE_GATE 0
@@ -93,7 +96,7 @@ int acsr_attn_calib_fwd(const float* mq, const float* mk, const float* mv, const
                         float p_attn, const float* D1, const float* D2, const float* D3, const float* noise,
                         const void* rng, uint32_t rng_stream,
                         float* ctx_att, float* ctx_cal, double* pen_sq, float* probs_out,
-                        const int32_t* order, void* stream);
+                        const int32_t* order, const int64_t* ctx_rows, void* stream);
 /* backward of the same block.  d_ctx_att / d_ctx_cal [B,L,d] (either may be NULL == zero),
  * d_pen_sq device float[1] or NULL.  Outputs (written, not accumulated): d_mq,d_mk,d_mv,d_aq,d_ak [B,L,d].
  * Accumulated with atomics (caller zeroes): d_gate_logit [B,L,L], d_order_w [2dh], d_order_b [1],
@@ -111,7 +114,7 @@ int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const fl
                         float* d_mq, float* d_mk, float* d_mv, float* d_aq, float* d_ak,
                         float* d_gate_logit, float* d_order_w, float* d_order_b,
                         float* d_dist_w, float* d_dist_b, float* d_scalar, float* d_rich_ratio,
-                        const int32_t* order, void* stream);
+                        const int32_t* order, const int64_t* ctx_rows, void* stream);
 /* the same backward for BOTH cotangent streams of the adversarial step in one launch (the reference's two
  * backward() traversals, trainer/trainer.py:672-684): stream 0 = d(calibrated loss) carries d_ctx_cal0 (+ d_pen_sq0),
  * stream 1 = d(attacked loss) carries d_ctx_att1 (last layer) OR d_ctx_cal1 (lower layers) and d_pen_sq1; any may be
@@ -131,7 +134,7 @@ int acsr_attn_calib_bwd2(const float* d_ctx_cal0, const float* d_pen_sq0,
                          float* d_mq, float* d_mk, float* d_mv, float* d_aq, float* d_ak,
                          float* d_gate_logit, float* d_order_w, float* d_order_b,
                          float* d_dist_w, float* d_dist_b, float* d_scalar, float* d_rich_ratio,
-                        const int32_t* order, void* stream);
+                        const int32_t* order, const int64_t* ctx_rows, void* stream);
 
 /* ---- epilogue of the output projection and of the FFN: LN(dropout(h + bias) + res) ----
  * replaces model/layers.py:681-683 and 794-796 (bias add of the preceding nn.Linear folded in).

@@ -10,12 +10,14 @@ from ac_tsr_b200 import ops
 
 dev = torch.device('cuda')
 ORDER = [None]
+CTXR = [None]
+KEEP = []
 USE_ORDER = os.environ.get('ATTN_ORDER', '1') == '1'
 H, dh, L = 2, 32, 50
 d = H * dh
 
 
-def run(B, lens, p=0.5, need_att=True, iters=30, bwd=False, last=True):
+def run(B, lens, p=0.5, need_att=True, iters=30, bwd=False, last=True, last_fwd=False):
     g = torch.Generator().manual_seed(0)
     t = [torch.randn(B, L, d, generator=g).to(dev) * 0.5 for _ in range(5)]
     gate = torch.randn(B, L, L, generator=g).to(dev)
@@ -29,6 +31,9 @@ def run(B, lens, p=0.5, need_att=True, iters=30, bwd=False, last=True):
     order = torch.empty(B, dtype=torch.int32, device=dev)
     A.LIB.call('acsr_seq_order', seq.data_ptr(), B, L, order.data_ptr(), ops._stream())
     ORDER[0] = order.data_ptr() if USE_ORDER else None
+    lens_dev = torch.tensor(lens, dtype=torch.int64, device=dev)
+    KEEP.append(lens_dev)
+    CTXR[0] = lens_dev.data_ptr() if os.environ.get('ATTN_CTXROWS', '1') == '1' else None
     ca, cc = torch.empty(B, L, d, device=dev), torch.empty(B, L, d, device=dev)
     pen = torch.zeros(1, dtype=torch.float64, device=dev)
     P = ops._p
@@ -55,10 +60,10 @@ def run(B, lens, p=0.5, need_att=True, iters=30, bwd=False, last=True):
 
         def f():
             A.LIB.call('acsr_attn_calib_bwd2', P(dc[:T]), None, P(att1), P(cal1), P(dpen), *shared, *[P(o) for o in outs], P(dgl),
-                       P(pg[0]), P(pg[1]), P(pg[2]), P(pg[3]), P(pg[4]), None, ORDER[0], ops._stream())
+                       P(pg[0]), P(pg[1]), P(pg[2]), P(pg[3]), P(pg[4]), None, ORDER[0], CTXR[0] if last else None, ops._stream())
     else:
         def f():
-            A.LIB.call('acsr_attn_calib_fwd', *shared, P(ca) if need_att else None, P(cc), pen.data_ptr(), None, ORDER[0], ops._stream())
+            A.LIB.call('acsr_attn_calib_fwd', *shared, P(ca) if need_att else None, P(cc), pen.data_ptr(), None, ORDER[0], CTXR[0] if last_fwd else None, ops._stream())
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
         st = ops._stream()
@@ -85,7 +90,7 @@ for B in (8, 37, 74, 148, 256, 512):
     lens = lnn.tolist()
     full = [L] * B
     short = [5] * B
-    print('B=%4d CTAs=%4d  fwd us: lognormal %.1f  all-50 %.1f  all-5 %.1f | fwd cal-only %.1f | bwd2 last %.1f / %.1f  lower %.1f / %.1f' % (
-        B, B * H, run(B, lens), run(B, full), run(B, short), run(B, lens, need_att=False),
+    print('B=%4d CTAs=%4d  fwd us: lognormal %.1f  all-50 %.1f  all-5 %.1f | fwd last-layer %.1f | bwd2 last %.1f / %.1f  lower %.1f / %.1f' % (
+        B, B * H, run(B, lens), run(B, full), run(B, short), run(B, lens, last_fwd=True),
         run(B, lens, bwd=True, last=True), run(B, full, bwd=True, last=True),
         run(B, lens, bwd=True, last=False), run(B, full, bwd=True, last=False)))

@@ -6,5 +6,5 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt
 tail -n 3 gpurun_out/t_kernels.log gpurun_out/t_model.log gpurun_out/smoke.log
-cat gpurun_out/bench.json
 tail -n 5 gpurun_out/bench.err
+if [ -n "$ATTN_MICRO" ]; then timeout 200 python scripts/attn_micro.py 2>&1 | tail -3; fi

@@ -282,7 +282,7 @@ def test_attn_calib_backward(A, case, which):
         assert float((got.cpu() - ref).abs().max()) <= 5e-4 * scale + 1e-6, (k, got, ref)
 
 
-def _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, cots, dual, order=None):
+def _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, cots, dual, order=None, ctx_rows=None):
     """raw C-ABI call of the attention backward.  cots = (cal0, pen0, att1, cal1, pen1) device tensors or None."""
     H = cfg['n_heads']
     B, L, d = t['mq'].shape
@@ -311,9 +311,9 @@ def _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, cots, dual, order=None):
     cal0, pen0, att1, cal1, pen1 = cots
     st = A.ops._stream()
     if dual:
-        A.LIB.call('acsr_attn_calib_bwd2', P(cal0), P(pen0), P(att1), P(cal1), P(pen1), *shared, *outs, P(order, torch.int32), st)
+        A.LIB.call('acsr_attn_calib_bwd2', P(cal0), P(pen0), P(att1), P(cal1), P(pen1), *shared, *outs, P(order, torch.int32), P(ctx_rows, torch.int64), st)
     else:
-        A.LIB.call('acsr_attn_calib_bwd', P(att1), P(cal0), P(pen0), *shared, *outs, P(order, torch.int32), st)
+        A.LIB.call('acsr_attn_calib_bwd', P(att1), P(cal0), P(pen0), *shared, *outs, P(order, torch.int32), P(ctx_rows, torch.int64), st)
     torch.cuda.synchronize()
     return out, pg
 
@@ -350,6 +350,20 @@ def test_attn_calib_backward_two_streams(A, case, last):
     for k in pg0:
         scale = float(pg0[k].abs().max())
         assert float((pg_both[k] - pg0[k]).abs().max()) <= 1e-4 * scale + 1e-6, k
+    if last:
+        # last-layer contract: only context row len-1 carries a cotangent -> the penalty-only row path must give the same
+        lens = torch.tensor([int((seq[b] != 0).sum()) for b in range(B)], dtype=torch.int64).cuda()
+        h0, h1 = torch.zeros_like(g0), torch.zeros_like(g1)
+        ar = torch.arange(B).cuda()
+        h0[ar, lens - 1] = g0[ar, lens - 1]
+        h1[ar, lens - 1] = g1[ar, lens - 1]
+        ref, pg_ref = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (h0, None, h1, None, pen), dual=True)
+        got, pg_got = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (h0, None, h1, None, pen), dual=True, order=order, ctx_rows=lens)
+        for k in ref:
+            if ref[k] is not None:
+                close(got[k], ref[k], 2e-5, 'ctx_rows d_' + k)
+        for k in pg_ref:
+            assert float((pg_got[k] - pg_ref[k]).abs().max()) <= 1e-4 * float(pg_ref[k].abs().max()) + 1e-6, k
 
 
 def test_philox_dropout_and_noise_statistics(A):
