@@ -151,6 +151,26 @@ class FusedTrainStep(object):
                                  side=self._stream_for(dev, ('side', s)) if self.overlap_wgrad else None))
         rng.advance()
         jb['pen'].zero_()
+        zero_done = None
+        if training:
+            # every buffer the backward accumulates into is cleared on its own stream while the forward runs
+            zs = self._stream_for(dev, ('zero',))
+            zs.wait_stream(main)
+            with torch.cuda.stream(zs):
+                opt.zero_grad()
+                jb['d_out2'].zero_()
+                for br in branches:
+                    bb = br['buf']
+                    if self.compact_last:
+                        bb['d_ctx'].zero_()
+                        bb['d_x'].zero_()
+                    else:
+                        bb['d_out'].zero_()
+                    for l, layer in enumerate(m.trm_encoder.layer):
+                        if layer.combine_option == 'gate':
+                            bb['layers'][l]['d_gl'].zero_()
+            zero_done = torch.cuda.Event()
+            zero_done.record(zs)
         # ---------------- forward: parallel branches ----------------
         for br in branches:
             if br['stream'] is not main:
@@ -161,6 +181,8 @@ class FusedTrainStep(object):
             if br['stream'] is not main:
                 main.wait_stream(br['stream'])
         if getattr(self, '_stop_after', None) == 'fwd':      # timeline probes (scripts/step_timeline.py)
+            if zero_done is not None:
+                main.wait_event(zero_done)
             return jb['loss'][0], jb['loss'][0]
         # ---------------- where the sequences meet: full-catalogue cross entropy + penalty norm ----------------
         st = _stream()
@@ -182,16 +204,17 @@ class FusedTrainStep(object):
         loss_cal = jb['loss'][0]
         loss_att = jb['loss_att'][0]
         if not training or getattr(self, '_stop_after', None) == 'ce':
+            if zero_done is not None:
+                main.wait_event(zero_done)
             return loss_att, loss_cal
         # ---------------- backward ----------------
         dpen = jb['dpen']
-        opt.zero_grad()
+        main.wait_event(zero_done)
         if self.vp is not None:       # shard-local G^T, reduce-scatter of d_out, dE into the owner's rows
             jb['d_out2'].copy_(self.vp.ce_backward(vst, E, jb['row_scale'], E.grad, table_half=0, n_groups=2))
         else:
             LIB.call('acsr_logits_ce_grad', _p(jb['out2']), _p(E), _p(jb['lse']), _p(jb['target2'], torch.int64),
                      _p(jb['row_scale']), 2 * B, V, d, passes, _p(jb['Gt']), 2 * B, st)
-            jb['d_out2'].zero_()
             LIB.call('acsr_linear_wgrad', _p(jb['Gt']), _p(E), V, 2 * B, d, _p(jb['d_out2']), None, st)
         for br in branches:
             if br['stream'] is not main:
@@ -397,7 +420,6 @@ class FusedTrainStep(object):
         T2 = 2 * T
         compact = self.compact_last
         if not compact:
-            d_out.zero_()
             LIB.call('acsr_gather_last_bwd', _p(jb['d_out2'][lo:lo + Bs]), _p(ln, torch.int64), Bs, L, d, None, _p(d_out[:T]), st)
             LIB.call('acsr_gather_last_bwd', _p(jb['d_out2'][B + lo:B + lo + Bs]), _p(ln, torch.int64), Bs, L, d, None, _p(d_out[T:]), st)
         for l in reversed(range(N)):
@@ -421,15 +443,11 @@ class FusedTrainStep(object):
                     dc_out[:Bs].copy_(jb['d_out2'][lo:lo + Bs])
                     dc_out[Bs:].copy_(jb['d_out2'][B + lo:B + lo + Bs])
                 self._post_attn_bwd(layer, cb, cb, dc_out, cb['x'], C, C, Bs, Bs, cb['d_x'], cb['d_ctx'], p_h, rngp, base, act_id, st, fork)
-                b['d_ctx'].zero_()
-                d_x.zero_()
                 LIB.call('acsr_gather_last_bwd', _p(cb['d_ctx']), _p(ln, torch.int64), Bs, L, d, _p(b['d_ctx'][:T]), _p(b['d_ctx'][T:]), st)
                 LIB.call('acsr_gather_last_bwd', _p(cb['d_x']), _p(ln, torch.int64), Bs, L, d, _p(d_x[:T]), _p(d_x[T:]), st)
             else:
                 self._post_attn_bwd(layer, lb, lb, d_out, x, T2, P, T, T, d_x, b['d_ctx'], p_h, rngp, base, act_id, st, fork, b=b)
-            # fused attention backward
-            if gate:
-                lb['d_gl'].zero_()
+            # fused attention backward (d_gate_logit accumulates over heads: cleared at the start of the step)
             g = lambda t: None if t is None else t.grad     # noqa: E731
             ow, ob_ = (aa.order_affine.weight, aa.order_affine.bias) if aa.use_order else (None, None)
             dw, db_, sc = (aa.distance_affine.weight, aa.distance_affine.bias, aa.scalar) if aa.use_distance else (None, None, None)
