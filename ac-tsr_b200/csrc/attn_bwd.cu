@@ -329,7 +329,7 @@ __device__ __forceinline__ void bwd_row_iter_m(const AttnParams& p, const AttnSm
   }
 }
 
-// row phase + column phase of the (b,h) tile with G-lane groups
+// row phase of the (b,h) tile with G-lane row groups
 template <int DH, int G, int MAXNJ, int NS>
 __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm, const BwdSmem<NS>& bs, const RowConst& kc,
                                          const BwdFlags& f, const float* dpen, int b, int h, int nkey, int rstride, BwdAcc& acc) {
@@ -342,9 +342,9 @@ __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm
   const int c0 = CM::c0(sub);
   float* wbuf = bs.rowbuf + warp * rowbuf_floats_per_warp(LP, 2 * NS);
   const int rt = p.ctx_rows ? (int)p.ctx_rows[b] - 1 : -1;     // the only row with a context cotangent, or -1: all rows
-  float accOq[CM::CPL], accDq[CM::CPL], accOk[CM::CPL], accDk[CM::CPL];
+  float accOq[CM::CPL], accDq[CM::CPL];
 #pragma unroll
-  for (int k = 0; k < CM::CPL; ++k) accOq[k] = accDq[k] = accOk[k] = accDk[k] = 0.f;
+  for (int k = 0; k < CM::CPL; ++k) accOq[k] = accDq[k] = 0.f;
   for (int t0 = next_task(sm.misc + 2, RPW); t0 < L; t0 = next_task(sm.misc + 2, RPW)) {      // heaviest rows first
     const int iw = L - 1 - t0;
     const int iraw = iw - grp;
@@ -356,7 +356,6 @@ __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm
 #define ACSR_BWD_ROW_M(NJV) bwd_row_iter_m<DH, G, NJV, NS>(p, sm, bs, kc, dpen, b, h, i, rowok, bound, grp, sub, rstride, wbuf)
       if (MAXNJ == 1 || nj == 1) ACSR_BWD_ROW_M(1);
       else if (nj == 2) ACSR_BWD_ROW_M((MAXNJ >= 2 ? 2 : 1));
-      else if (nj == 3) ACSR_BWD_ROW_M((MAXNJ >= 3 ? 3 : 1));
       else ACSR_BWD_ROW_M((MAXNJ >= 4 ? 4 : 1));
 #undef ACSR_BWD_ROW_M
       continue;
@@ -365,11 +364,35 @@ __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm
   bwd_row_iter<DH, G, NJV, NS>(p, sm, bs, kc, f, dpen, b, h, i, rowok, bound, grp, sub, rstride, wbuf, acc, accOq, accDq)
     if (MAXNJ == 1 || nj == 1) ACSR_BWD_ROW(1);
     else if (nj == 2) ACSR_BWD_ROW((MAXNJ >= 2 ? 2 : 1));
-    else if (nj == 3) ACSR_BWD_ROW((MAXNJ >= 3 ? 3 : 1));
     else ACSR_BWD_ROW((MAXNJ >= 4 ? 4 : 1));
 #undef ACSR_BWD_ROW
   }
-  __syncthreads();
+  // lane partials of the query-side halves of d_ow / d_dw -> CTA partials in smem
+  if ((p.d_ow || p.d_dw) && CM::split(sub) == 0) {
+#pragma unroll
+    for (int k = 0; k < CM::CPL; ++k) {
+      const int c = c0 + k;
+      if (accOq[k] != 0.f) atomicAdd(bs.pacc + c, accOq[k]);
+      if (accDq[k] != 0.f) atomicAdd(bs.pacc + 2 * DH + c, accDq[k]);
+    }
+  }
+}
+
+// column phase of the (b,h) tile: dk_j, dk'_j, dv_j.  CG lanes per column (lane = channel, rows i >= j); short sequences
+// use whole warps per column so that every warp has a column to work on
+template <int DH, int CG, int NS>
+__device__ __forceinline__ void bwd_cols(const AttnParams& p, const AttnSmem& sm, const BwdSmem<NS>& bs, const BwdFlags& f, int b, int h,
+                                         int nkey) {
+  constexpr int dhp = DH + 4;
+  constexpr int RPW = 32 / CG;
+  using CM = CMap<DH, CG>;
+  const int L = p.L, LP = (L + 3) & ~3;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / CG, sub = lane % CG;
+  const int c0 = CM::c0(sub);
+  float accOk[CM::CPL], accDk[CM::CPL];
+#pragma unroll
+  for (int k = 0; k < CM::CPL; ++k) accOk[k] = accDk[k] = 0.f;
   // column-side gradients: dk_j, dk'_j, dv_j  (group per column, lane = channel, rows i >= j)
   for (int t0 = next_task(sm.misc + 3, RPW); t0 < nkey; t0 = next_task(sm.misc + 3, RPW)) {    // heaviest columns (small j) first
     const int jraw = t0 + grp;
@@ -438,14 +461,11 @@ __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm
       }
     }
   }
-  // lane partials of d_ow / d_dw -> CTA partials in smem
   if ((p.d_ow || p.d_dw) && CM::split(sub) == 0) {
 #pragma unroll
     for (int k = 0; k < CM::CPL; ++k) {
       const int c = c0 + k;
-      if (accOq[k] != 0.f) atomicAdd(bs.pacc + c, accOq[k]);
       if (accOk[k] != 0.f) atomicAdd(bs.pacc + DH + c, accOk[k]);
-      if (accDq[k] != 0.f) atomicAdd(bs.pacc + 2 * DH + c, accDq[k]);
       if (accDk[k] != 0.f) atomicAdd(bs.pacc + 3 * DH + c, accDk[k]);
     }
   }
@@ -502,6 +522,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_kernel(const AttnPar
 
   if (nkey <= 8) bwd_body<DH, 8, 1, NS>(p, sm, bs, kc, f, dpen, b, h, nkey, 8, acc);
   else bwd_body<DH, 16, 4, NS>(p, sm, bs, kc, f, dpen, b, h, nkey, LP, acc);
+  __syncthreads();
+  if (nkey <= 8) bwd_cols<DH, 32, NS>(p, sm, bs, f, b, h, nkey);
+  else bwd_cols<DH, 16, NS>(p, sm, bs, f, b, h, nkey);
 
   // key positions behind the last real item receive no gradient
   for (int e = threadIdx.x; e < (L - nkey) * (DH / 4); e += blockDim.x) {

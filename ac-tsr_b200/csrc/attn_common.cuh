@@ -129,6 +129,7 @@ struct AttnSmem {
   float *Q, *K, *V, *Q2, *K2;                        // [LP][dh+4]
   float *rowO, *rowD, *colO, *colD, *logd, *keyok;   // [LP]
   float *wo, *wd;                                    // [2*dh] spatial-calibrator weights (0 when absent)
+  const float* G;                                    // gate-logit tile [L*L] staged in shared memory, or nullptr (read from global)
   int* misc;                                         // [8] 0,1: ballot words of the key-validity scan; 2,3: row / column task
                                                      // counters (dynamic heaviest-first scheduling); 4: warp arrival counter
 };
@@ -151,6 +152,9 @@ __device__ __forceinline__ float fsigmoid(float x) { return frcp(1.0f + fex2(x *
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -325,9 +329,15 @@ __device__ __forceinline__ void row_forward(const AttnParams& p, const AttnSmem&
   r.act = act;
   const long long ebase = (((long long)b * p.H + h) * L + i) * L;
   if (p.combine == ACSR_ATTN_COMBINE_GATE) {     // gate logits straight from global (read once per element), early
-    const float* gp = p.gate + ((long long)b * L + i) * L;
+    if (sm.G != nullptr) {
+      const float* gp = sm.G + i * L;
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) if ((act >> jj) & 1u) gl[jj] = __ldg(gp + jc[jj]);
+      for (int jj = 0; jj < NJ; ++jj) if ((act >> jj) & 1u) gl[jj] = gp[jc[jj]];
+    } else {
+      const float* gp = p.gate + ((long long)b * L + i) * L;
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) if ((act >> jj) & 1u) gl[jj] = __ldg(gp + jc[jj]);
+    }
   }
   {
     const float4* qi = reinterpret_cast<const float4*>(sm.Q + i * dhp);
@@ -556,6 +566,7 @@ __device__ __forceinline__ AttnSmem carve_common(float*& ptr, int LP, int dh) {
   sm.wo = ptr; ptr += 2 * dh;
   sm.wd = ptr; ptr += 2 * dh;
   sm.misc = reinterpret_cast<int*>(ptr); ptr += 8;
+  sm.G = nullptr;
   return sm;
 }
 static inline size_t common_floats(int LP, int dh) { return (size_t)5 * LP * (dh + 4) + 6 * LP + 4 * dh + 8; }
