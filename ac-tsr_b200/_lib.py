@@ -22,9 +22,9 @@ def parse_header(path=HEADER):
     src = open(path).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     protos = {}
-    for m in re.finditer(r'(const\s+char\s*\*|int)\s+(acsr_\w+)\s*\(([^)]*)\)\s*;', src, flags=re.S):
+    for m in re.finditer(r'(const\s+char\s*\*|int64_t|int)\s+(acsr_\w+)\s*\(([^)]*)\)\s*;', src, flags=re.S):
         ret, name, args = m.group(1), m.group(2), m.group(3)
-        restype = ctypes.c_char_p if 'char' in ret else ctypes.c_int
+        restype = ctypes.c_char_p if 'char' in ret else (ctypes.c_int64 if ret == 'int64_t' else ctypes.c_int)
         argl = []
         args = ' '.join(args.split())
         if args and args != 'void':
@@ -78,6 +78,26 @@ class _Lib:
 
     def query(self, name, *args):
         return getattr(self.load(), name)(*args)
+
+    def ensure_workspace(self, nbytes, device):
+        """caller-owned scratch of `device` (acsr_set_workspace): one torch allocation, grown on demand, never shrunk."""
+        import torch
+        if not hasattr(self, '_ws'):
+            self._ws = {}
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        cur = self._ws.get(idx)
+        if cur is not None and cur.numel() >= nbytes:
+            return cur
+        if torch.cuda.is_current_stream_capturing():
+            raise AcsrError('the attention workspace (%d bytes) must be allocated before CUDA-graph capture: run one eager step first' % nbytes)
+        with torch.cuda.device(idx):
+            torch.cuda.synchronize()
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=torch.device('cuda', idx))
+            rc = self.load().acsr_set_workspace(buf.data_ptr(), int(nbytes))
+            if rc != 0:
+                raise AcsrError('acsr_set_workspace failed (%d)' % rc)
+        self._ws[idx] = buf
+        return buf
 
 
 def _ab_linear_tok(a):

@@ -34,6 +34,16 @@ bool pdl_enabled() {
 }
 void pdl_set(int on) { g_pdl = on ? 1 : 0; }
 
+// caller-owned scratch memory of the current device (acsr_set_workspace): the library allocates nothing itself
+static void* g_ws_ptr[64] = {};
+static size_t g_ws_bytes[64] = {};
+void* workspace_ptr(size_t* bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { *bytes = 0; return nullptr; }
+  *bytes = g_ws_bytes[dev];
+  return g_ws_ptr[dev];
+}
+
 __global__ void rng_advance_kernel(RngState* s) {
   pdl_launch_dependents();
   pdl_wait(); s->step += 1ull; }
@@ -44,6 +54,20 @@ int acsr_version(void) { return ACSR_ABI_VERSION; }
 const char* acsr_last_error(void) { return acsr::g_err; }
 int acsr_num_sms(void) { return acsr::kNumSMs; }
 int acsr_set_pdl(int on) { int was = acsr::pdl_enabled() ? 1 : 0; acsr::pdl_set(on); return was; }
+
+int acsr_set_workspace(void* ptr, int64_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { acsr::set_error("acsr_set_workspace: %s", cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
+  ACSR_REQUIRE(dev >= 0 && dev < 64 && bytes >= 0 && (ptr != nullptr || bytes == 0), "acsr_set_workspace: bad arguments");
+  acsr::g_ws_ptr[dev] = ptr;
+  acsr::g_ws_bytes[dev] = (size_t)bytes;
+  return ACSR_OK;
+}
+int64_t acsr_attn_workspace_bytes(int L, int H, int n_streams) {
+  if (L <= 64) return 0;
+  return (int64_t)((size_t)(2 * n_streams + 2) * L * L + (size_t)2 * n_streams * L) * 4 * H;
+}
 
 int acsr_rng_advance(void* rng, void* stream) {
   ACSR_REQUIRE(rng != nullptr, "acsr_rng_advance: rng is NULL");

@@ -590,7 +590,7 @@ static int prep_kernel(K kernel, size_t smem, const char* who) {
 static inline int attn_validate(const AttnParams& p, const char* who) {
   ACSR_REQUIRE(p.mq && p.mk && p.mv && p.aq && p.ak && p.item_seq, "%s: NULL input", who);
   ACSR_REQUIRE(p.B > 0 && p.H > 0, "%s: bad B/H", who);
-  if (p.L < 1 || p.L > 64) { set_error("%s: L=%d unsupported in ABI v1 (1..64)", who, p.L); return ACSR_ERR_UNSUPPORTED; }
+  if (p.L < 1 || p.L > 256) { set_error("%s: L=%d unsupported (1..256)", who, p.L); return ACSR_ERR_UNSUPPORTED; }
   if (!(p.dh == 8 || p.dh == 16 || p.dh == 32 || p.dh == 64)) {
     set_error("%s: head size %d unsupported (8/16/32/64)", who, p.dh);
     return ACSR_ERR_UNSUPPORTED;
@@ -606,6 +606,11 @@ static inline int attn_validate(const AttnParams& p, const char* who) {
   ACSR_REQUIRE((p.D1 == nullptr) == (p.D3 == nullptr), "%s: D1/D3 must be given together", who);
   return ACSR_OK;
 }
+
+// attn_long.cu: 64 < L <= 256 (key-side tiles resident, query rows streamed, backward matrices in a global workspace)
+int attn_long_fwd(const AttnParams& p, cudaStream_t st);
+int attn_long_bwd(const AttnParams& p, int ns, cudaStream_t st);
+int seq_order_long(const int64_t* item_seq, int B, int L, int32_t* order, cudaStream_t st);
 
 static inline void attn_fill_common(AttnParams& p, const float* mq, const float* mk, const float* mv, const float* aq,
                                     const float* ak, const float* gate_logit, const int64_t* item_seq, const float* order_w,

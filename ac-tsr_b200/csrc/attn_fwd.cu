@@ -1,92 +1,8 @@
 // Fused calibrated causal attention, forward (see attn_common.cuh for the design).
 // Replaces layers.py:657-674, 686-742, 883-896, 917-936 and the probs.V of 676-678.
-#include "attn_common.cuh"
+#include "attn_fwd_rows.cuh"
 
 namespace acsr {
-
-struct FwdCtx {
-  float* rowbuf;     // this warp's row buffers
-  float pen;
-};
-
-// one row group iteration: probabilities of row i, penalty, probs.V
-template <int DH, int G, int NJ>
-__device__ __forceinline__ void fwd_row_iter(const AttnParams& p, const AttnSmem& sm, const RowConst& kc, int b, int h, int i,
-                                             bool rowok, int bound, int grp, int sub, bool need_att, int rstride, FwdCtx& cx) {
-  constexpr int dhp = DH + 4;
-  using CM = CMap<DH, G>;
-  const int L = p.L;
-  RowF<NJ> r;
-  row_forward<DH, G, NJ>(p, sm, kc, b, h, i, bound, sub, need_att, r);
-  float* bufR = cx.rowbuf + (grp * 2 + 0) * rstride;
-  float* bufA = cx.rowbuf + (grp * 2 + 1) * rstride;
-#pragma unroll
-  for (int jj = 0; jj < NJ; ++jj) {
-    const int j = sub + G * jj;
-    const bool a = (r.act >> jj) & 1u;
-    const float Pj = r.Psoft[jj] * r.D1[jj];
-    const float Rf = p.two_level ? r.R[jj] : (kc.rr * r.R[jj] + (1.0f - kc.rr) * Pj);
-    const float Mj = r.Msoft[jj] * r.D3[jj];
-    if (j < rstride) {                            // entries outside the row's range are written as 0
-      bufR[j] = a ? Rf : 0.f;
-      bufA[j] = a ? r.A[jj] : 0.f;
-    }
-    if (a && rowok) { const float om = 1.0f - Mj; cx.pen = fmaf(om, om, cx.pen); }
-    if (p.probs && a && rowok) {
-      const long long e = (((long long)b * p.H + h) * L + i) * L + j;
-      const long long plane = (long long)p.B * p.H * L * L;
-      p.probs[0 * plane + e] = r.P0soft[jj] * r.D2[jj]; p.probs[1 * plane + e] = Pj;
-      p.probs[2 * plane + e] = Mj; p.probs[3 * plane + e] = r.A[jj];
-      p.probs[4 * plane + e] = r.C[jj]; p.probs[5 * plane + e] = Rf;
-    }
-  }
-  if (rowok && sub == 0) cx.pen += (float)(L - bound);      // columns outside the range: M == 0 -> (1-M)^2 == 1
-  __syncwarp();
-  // ctx[i][c] = sum_{j<bound} prob[j] * V[j][c]
-  float accR[CM::CPL], accA[CM::CPL];
-#pragma unroll
-  for (int k = 0; k < CM::CPL; ++k) accR[k] = accA[k] = 0.f;
-  int lo, hi;
-  CM::slice(sub, 0, (bound + 3) & ~3, lo, hi);
-  const int c0 = CM::c0(sub);
-  for (int j = lo; j < hi; j += 4) {
-    const float4 pr = *reinterpret_cast<const float4*>(bufR + j);
-    const float4 pa = *reinterpret_cast<const float4*>(bufA + j);
-    const float prv[4] = {pr.x, pr.y, pr.z, pr.w}, pav[4] = {pa.x, pa.y, pa.z, pa.w};
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float v[CM::CPL];
-      VecLd<CM::CPL>::ld(sm.V + (j + u) * dhp + c0, v);
-#pragma unroll
-      for (int k = 0; k < CM::CPL; ++k) {
-        accR[k] = fmaf(prv[u], v[k], accR[k]);
-        if (need_att) accA[k] = fmaf(pav[u], v[k], accA[k]);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < CM::CPL; ++k) { accR[k] = CM::reduce(accR[k]); accA[k] = CM::reduce(accA[k]); }
-  if (CM::split(sub) == 0 && rowok) {
-    const long long o = ((long long)b * L + i) * p.d + h * DH + c0;
-    VecLd<CM::CPL>::st(p.ctx_cal + o, accR);
-    if (need_att) VecLd<CM::CPL>::st(p.ctx_att + o, accA);
-  }
-  __syncwarp();
-}
-
-// row group iteration for rows whose context nobody reads: attack mask -> penalty only
-template <int DH, int G, int NJ>
-__device__ __forceinline__ void fwd_row_iter_m(const AttnParams& p, const AttnSmem& sm, const RowConst& kc, int b, int h, int i,
-                                               bool rowok, int bound, int sub, FwdCtx& cx) {
-  float Msoft[NJ], D3[NJ];
-  unsigned act;
-  row_forward_m<DH, G, NJ>(p, sm, kc, b, h, i, bound, sub, Msoft, D3, act);
-  if (!rowok) return;
-#pragma unroll
-  for (int jj = 0; jj < NJ; ++jj)
-    if ((act >> jj) & 1u) { const float om = 1.0f - Msoft[jj] * D3[jj]; cx.pen = fmaf(om, om, cx.pen); }
-  if (sub == 0) cx.pen += (float)(p.L - bound);
-}
 
 // all rows of the (b,h) tile with G-lane row groups; the heaviest rows go first
 template <int DH, int G, int MAXNJ>
@@ -206,7 +122,8 @@ __global__ void __launch_bounds__(256) seq_order_kernel(const int64_t* __restric
 using namespace acsr;
 
 extern "C" int acsr_seq_order(const int64_t* item_seq, int B, int L, int32_t* order, void* stream) {
-  ACSR_REQUIRE(item_seq && order && B > 0 && B <= 2048 && L > 0 && L <= 64, "seq_order: bad arguments (B <= 2048, L <= 64)");
+  ACSR_REQUIRE(item_seq && order && B > 0 && B <= 2048 && L > 0 && L <= 1024, "seq_order: bad arguments (B <= 2048, L <= 1024)");
+  if (L > 64) return seq_order_long(item_seq, B, L, order, (cudaStream_t)stream);
   launch_pdl(seq_order_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, item_seq, B, L, order);
   return check_launch("seq_order");
 }
@@ -226,6 +143,7 @@ extern "C" int acsr_attn_calib_fwd(const float* mq, const float* mk, const float
   int rc = attn_validate(p, "attn_calib_fwd");
   if (rc) return rc;
   ACSR_REQUIRE(ctx_cal != nullptr, "attn_calib_fwd: ctx_cal is NULL");
+  if (L > 64) return attn_long_fwd(p, (cudaStream_t)stream);
   switch (dh) {
     case 8: return launch_fwd<8>(p, (cudaStream_t)stream);
     case 16: return launch_fwd<16>(p, (cudaStream_t)stream);

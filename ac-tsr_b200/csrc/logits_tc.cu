@@ -17,48 +17,10 @@
 //   warps 6-9   epilogue : tcgen05.ld 32 lanes x 32 columns -> one thread owns one logits row, so the
 //                          online softmax / top-k state is thread-private (no shuffles)
 // The activation tile A (128 x 64, hi and lo) is stationary in shared memory.
-#include "acsr_common.cuh"
+#include "logits_common.cuh"
 #include "../../include/acsr.h"
 
 namespace acsr {
-
-constexpr int kD = 64;                 // hidden size handled by ABI v1 of the tensor-core path
-constexpr int kBM = 128;               // rows per CTA tile  (UMMA M)
-constexpr int kBN = 64;                // catalogue rows per tile (UMMA N)
-constexpr int kKC = kD / 4;            // 16-byte K chunks per row
-constexpr int kTcThreads = 320;
-constexpr int kTmemCols = 128;         // 2 accumulator stages x 64 columns
-constexpr int kMaxTopK = 64;
-
-enum { MODE_STORE = 0, MODE_CE = 1, MODE_GRAD = 2, MODE_TOPK = 3, MODE_LINEAR = 4 };
-
-struct LogitsParams {
-  const float* out;      // [M,64]
-  const float* table;    // [V,64]
-  int M;
-  long long V;
-  int passes;
-  int m_tiles, n_tiles, n_chunks;
-  // STORE / GRAD
-  float* C;
-  long long ldc;
-  const float* lse;
-  const long long* target;
-  const float* row_scale;
-  // CE
-  float* partial;        // [M, n_chunks, 2]
-  // TOPK
-  int k;
-  long long idx_offset;
-  int skip_col0;
-  float* pval;           // [M, n_chunks, k]
-  long long* pidx;
-  // LINEAR: stationary operand element (r,k) = out[r*out_sn + k*out_sk]; Y[v*ldc + r] (+)= D[r][v] + bias[r]
-  long long out_sn, out_sk;
-  const float* bias;
-  int accumulate;
-  long long b_out, b_table, b_bias, b_C;   // per-problem strides of a batched launch (blockIdx.y)
-};
 
 template <int MODE>
 struct TcCfg {
@@ -420,20 +382,11 @@ __global__ void loss_combine_kernel(const double* __restrict__ pen_sq, int n_lay
   loss_att[0] = -ce[0] + (acc / n_layers) * w;
 }
 
-static void plan(LogitsParams& p, int batch = 1) {
-  p.m_tiles = (p.M + kBM - 1) / kBM;
-  p.n_tiles = (int)((p.V + kBN - 1) / kBN);
-  int nc = kNumSMs / ((p.m_tiles > 0 ? p.m_tiles : 1) * batch);
-  if (nc < 1) nc = 1;
-  if (nc > p.n_tiles) nc = p.n_tiles;
-  p.n_chunks = nc;
-}
-
 template <int MODE>
 static int launch_tc(LogitsParams& p, cudaStream_t st, const char* who, int batch = 1) {
   using Cfg = TcCfg<MODE>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
-  plan(p, batch);
+  logits_plan(p, batch);
   cudaError_t e = cudaFuncSetAttribute(logits_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) { set_error("%s: smem attr: %s", who, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
   launch_pdl(logits_tc_kernel<MODE>, dim3(p.m_tiles * p.n_chunks, batch), dim3(kTcThreads), Cfg::kSmemBytes, st, p);
@@ -443,7 +396,10 @@ static int launch_tc(LogitsParams& p, cudaStream_t st, const char* who, int batc
 static int validate_common(const float* out, const float* table, int M, long long V, int d, int passes, const char* who) {
   ACSR_REQUIRE(out && table, "%s: NULL input", who);
   ACSR_REQUIRE(M > 0 && V > 0, "%s: bad sizes M=%d V=%lld", who, M, V);
-  if (d != kD) { set_error("%s: hidden size %d unsupported by the tensor-core path in ABI v1 (64)", who, d); return ACSR_ERR_UNSUPPORTED; }
+  if (d != kD && (d < 4 || d > 1024 || (d & 3))) {
+    set_error("%s: hidden size %d unsupported (64 on the tensor-core path; multiples of 4 up to 1024 on the fp32 path)", who, d);
+    return ACSR_ERR_UNSUPPORTED;
+  }
   ACSR_REQUIRE(passes == 1 || passes == 3, "%s: passes must be 1 (TF32) or 3 (3xTF32)", who);
   ACSR_REQUIRE(V < (1ll << 31), "%s: V too large", who);
   return ACSR_OK;
@@ -459,7 +415,7 @@ int acsr_logits_num_chunks(int M, int64_t V) {
   LogitsParams p = {};
   p.M = M; p.V = V;
   if (M <= 0 || V <= 0) return 0;
-  plan(p);
+  logits_plan(p);
   return p.n_chunks;
 }
 
@@ -470,6 +426,7 @@ int acsr_logits_store(const float* out, const float* table, int M, int64_t V, in
   ACSR_REQUIRE(scores && ldc >= V, "logits_store: bad output");
   LogitsParams p = {};
   p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.C = scores; p.ldc = ldc;
+  if (d != kD) return launch_logits_simt(MODE_STORE, p, d, (cudaStream_t)stream, "logits_store");   // fp32 FMA path (logits_simt.cu)
   return launch_tc<MODE_STORE>(p, (cudaStream_t)stream, "logits_store");
 }
 
@@ -479,6 +436,7 @@ int acsr_logits_ce_partial(const float* out, const float* table, int M, int64_t 
   ACSR_REQUIRE(partial, "logits_ce_partial: NULL output");
   LogitsParams p = {};
   p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.partial = partial;
+  if (d != kD) return launch_logits_simt(MODE_CE, p, d, (cudaStream_t)stream, "logits_ce_partial");   // fp32 FMA path (logits_simt.cu)
   return launch_tc<MODE_CE>(p, (cudaStream_t)stream, "logits_ce_partial");
 }
 
@@ -509,6 +467,7 @@ int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, 
   LogitsParams p = {};
   p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.C = G; p.ldc = ldg;
   p.lse = lse; p.target = (const long long*)target; p.row_scale = row_scale;
+  if (d != kD) return launch_logits_simt(MODE_GRAD, p, d, (cudaStream_t)stream, "logits_ce_grad");   // fp32 FMA path (logits_simt.cu)
   return launch_tc<MODE_GRAD>(p, (cudaStream_t)stream, "logits_ce_grad");
 }
 
@@ -536,6 +495,7 @@ int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_
   LogitsParams p = {};
   p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes;
   p.k = k; p.idx_offset = idx_offset; p.skip_col0 = skip_col0; p.pval = partial_val; p.pidx = (long long*)partial_idx;
+  if (d != kD) return launch_logits_simt(MODE_TOPK, p, d, (cudaStream_t)stream, "logits_topk_partial");   // fp32 FMA path (logits_simt.cu)
   return launch_tc<MODE_TOPK>(p, (cudaStream_t)stream, "logits_topk_partial");
 }
 

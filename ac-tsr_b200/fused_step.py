@@ -456,6 +456,7 @@ class FusedTrainStep(object):
             # both cotangent streams in one launch: stream 0 = d(calibrated loss), stream 1 = d(attacked loss) which
             # enters through the attacked context on the last layer, through the calibrated chain below, plus the penalty
             d_att1, d_cal1 = (dc[T:], None) if last else (None, dc[T:])
+            ops.attn_workspace(Bs, L, m.n_heads, 2, seq.device)          # only sequences longer than 64 need one
             LIB.call('acsr_attn_calib_bwd2', _p(dc[:T]), None, _p(d_att1), _p(d_cal1), _p(dpen[l:l + 1]), *lb['attn_args'],
                      _p(lb['d_mq']), _p(lb['d_mk']), _p(lb['d_mv']), _p(lb['d_aq']), _p(lb['d_ak']),
                      _p(lb['d_gl']) if gate else None, _p(g(ow)), _p(g(ob_)), _p(g(dw)), _p(g(db_)), _p(g(sc)), _p(g(rr)),

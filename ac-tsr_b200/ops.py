@@ -164,6 +164,17 @@ class GatherLastFn(torch.autograd.Function):
         return d_att, d_cal, None
 
 
+def attn_workspace(B, L, H, n_streams, device):
+    """scratch for the attention backward of sequences longer than 64 (attn_long.cu): as many sequences' worth as fit
+    under ACSR_WORKSPACE_MB (default 4096); the library walks the batch in chunks of that many sequences."""
+    if L <= 64:
+        return
+    import os
+    per_seq = LIB.query('acsr_attn_workspace_bytes', int(L), int(H), int(n_streams))
+    cap = int(os.environ.get('ACSR_WORKSPACE_MB', 4096)) << 20
+    LIB.ensure_workspace(max(per_seq, min(B * per_seq, cap)), device)
+
+
 class AttnOpts:
     """static options of one fused-attention call (mirrors the AttackR* constructor flags)."""
 
@@ -224,6 +235,7 @@ class AttnCalibFn(torch.autograd.Function):
         d_db = z(dist_b) if dist_b is not None else None
         d_sc = z(scalar) if scalar is not None else None
         d_rr = z(rich_ratio) if rich_ratio is not None else None
+        attn_workspace(B, L, H, 1, mq.device)
         LIB.call('acsr_attn_calib_bwd', _p(d_att), _p(d_cal), _p(d_pen), _p(mq), _p(mk), _p(mv), _p(aq), _p(ak),
                  _p(gate_logit), _p(key_ids, torch.int64), _p(order_w), _p(order_b), _p(dist_w), _p(dist_b), _p(scalar),
                  B, L, H, dh, opts.two_level, opts.combine, comb_scalar, opts.rich, _p(rich_ratio),

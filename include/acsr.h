@@ -42,6 +42,14 @@ int acsr_num_sms(void);
  * previous one).  Returns the previous setting.  Default: off (environment ACSR_PDL=1 turns it on). */
 int acsr_set_pdl(int on);
 
+/* caller-owned scratch memory of the CURRENT device (the library allocates nothing).  Only the attention backward for
+ * sequences longer than 64 needs it: acsr_attn_workspace_bytes(L, H, n_streams) bytes per sequence (0 for L <= 64;
+ * n_streams = 1 for acsr_attn_calib_bwd, 2 for acsr_attn_calib_bwd2); with less than B sequences' worth the batch is
+ * processed in chunks, with less than one the call fails.  The pointer must stay valid until the work enqueued with it
+ * has completed. */
+int acsr_set_workspace(void* ptr, int64_t bytes);
+int64_t acsr_attn_workspace_bytes(int L, int H, int n_streams);
+
 /* rng state helper: rng->step += 1 (one tiny kernel; keeps graph replays distinct) */
 int acsr_rng_advance(void* rng, void* stream);
 

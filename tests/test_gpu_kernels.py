@@ -169,7 +169,14 @@ ATTN_CASES = [
     (2, 32, 50, 'gate', True, 'none', False, True, 0.5),
     (2, 32, 50, 'gate', True, 'none', True, False, 0.5),
     (2, 32, 50, 'gate', True, 'none', False, False, 0.0),
+    # sequences longer than 64 (attn_long.cu: key tiles resident, query rows streamed, backward matrices in a workspace);
+    # (4, 64, 200) is BASELINE configuration #5's attention shape
+    (4, 64, 200, 'gate', True, 'none', True, True, 0.5),
+    (2, 32, 80, 'gate', True, 'none', True, True, 0.3),
+    (4, 16, 130, 'fixed', False, 'trainable', True, True, 0.5),
+    (2, 64, 65, 'annealing', True, 'none', False, True, 0.0),
 ]
+LONG_CASES = [c for c in ATTN_CASES if c[2] > 64]
 
 
 def _attn_inputs(H, dh, L, combine, two_level, rich, use_order, use_distance, p, seed=0):
@@ -302,6 +309,7 @@ def _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, cots, dual, order=None, ctx_rows=N
               P(lpc.get('rich_calibrated_combine_ratio')), float(p), P(rand['D1']), P(rand['D2']), P(rand['D3']),
               P(rand['noise']), None, 16)
     S = 2 if dual else 1
+    A.ops.attn_workspace(B, L, H, S, torch.device('cuda'))
     out = {k: torch.full((S * B * L, d), float('nan'), device='cuda') for k in ('mq', 'mk', 'mv', 'aq', 'ak')}
     out['gate'] = torch.zeros(S * B * L, L, device='cuda') if tc['gate'] is not None else None
     pg = {k: torch.zeros_like(v) for k, v in lpc.items()}
@@ -318,7 +326,7 @@ def _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, cots, dual, order=None, ctx_rows=N
     return out, pg
 
 
-@pytest.mark.parametrize('case', [ATTN_CASES[0], ATTN_CASES[1], ATTN_CASES[5], ATTN_CASES[7], ATTN_CASES[9], ATTN_CASES[4]])
+@pytest.mark.parametrize('case', [ATTN_CASES[0], ATTN_CASES[1], ATTN_CASES[5], ATTN_CASES[7], ATTN_CASES[9], ATTN_CASES[4]] + LONG_CASES[:3])
 @pytest.mark.parametrize('last', [True, False])
 def test_attn_calib_backward_two_streams(A, case, last):
     """acsr_attn_calib_bwd2 == two single-stream launches (stream 0: d_cal; stream 1: d_att|d_cal + d_pen);
@@ -364,6 +372,35 @@ def test_attn_calib_backward_two_streams(A, case, last):
                 close(got[k], ref[k], 2e-5, 'ctx_rows d_' + k)
         for k in pg_ref:
             assert float((pg_got[k] - pg_ref[k]).abs().max()) <= 1e-4 * float(pg_ref[k].abs().max()) + 1e-6, k
+
+
+def test_attn_long_backward_chunked_workspace(A, monkeypatch):
+    """a workspace smaller than the batch: the library walks the batch in chunks of sequences; same gradients."""
+    case = LONG_CASES[1]
+    H, dh, L, combine, two_level, rich, uo, ud, p = case
+    cfg, seq, t, lp, rnd, g = _attn_inputs(*case)
+    B, d = t['mq'].shape[0], H * dh
+    g0, g1 = torch.randn(B, L, d, generator=g).cuda(), torch.randn(B, L, d, generator=g).cuda()
+    pen = torch.tensor([0.01]).cuda()
+    ref, pg_ref = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (g0, None, g1, None, pen), dual=True)
+    per_seq = A.LIB.query('acsr_attn_workspace_bytes', L, H, 2)
+    assert per_seq == ((2 * 2 + 2) * L * L + 2 * 2 * L) * 4 * H
+    small = torch.empty(2 * per_seq + 100, dtype=torch.uint8, device='cuda')          # room for 2 of the 5 sequences
+    monkeypatch.setattr(A.ops, 'attn_workspace', lambda *a, **k: None)
+    try:
+        assert A.LIB.query('acsr_set_workspace', small.data_ptr(), small.numel()) == 0
+        got, pg_got = _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (g0, None, g1, None, pen), dual=True)
+        for k in ref:
+            if ref[k] is not None:
+                close(got[k], ref[k], 1e-5, 'chunked d_' + k)
+        for k in pg_ref:
+            assert float((pg_got[k] - pg_ref[k]).abs().max()) <= 1e-4 * float(pg_ref[k].abs().max()) + 1e-6, k
+        assert A.LIB.query('acsr_set_workspace', small.data_ptr(), per_seq - 4) == 0         # not even one sequence fits
+        with pytest.raises(A.AcsrError, match='workspace'):
+            _raw_attn_bwd(A, cfg, seq, t, lp, rnd, p, (g0, None, g1, None, pen), dual=True)
+    finally:
+        ws = A.LIB._ws.get(torch.cuda.current_device())
+        A.LIB.query('acsr_set_workspace', ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0)
 
 
 def test_philox_dropout_and_noise_statistics(A):
@@ -467,9 +504,61 @@ def test_logits_topk_fused(A, M, V, k):
     assert torch.equal(rec[:, :-1], flags) and (rec[:, -1] == 1).all()
 
 
+# ---- hidden sizes other than 64 take the fp32 FMA path (logits_simt.cu): same entry points, same contracts ----
+@pytest.mark.parametrize('M,V,d', [(4, 301, 128), (130, 65, 256), (256, 12102, 128), (512, 12102, 256), (37, 20034, 32), (300, 1683, 100)])
+def test_logits_store_fp32_path(A, M, V, d):
+    g = torch.Generator().manual_seed(M + V + d)
+    out = torch.randn(M, d, generator=g)
+    E = torch.randn(V, d, generator=g) * 0.5
+    ref = out.double() @ E.double().t()
+    s = A.ops.logits_scores(out.cuda(), E.cuda(), 3).cpu().double()
+    e = float((s - ref).abs().max()) / float(ref.abs().max())
+    assert e < 2e-6, e
+
+
+@pytest.mark.parametrize('M,V,groups,d', [(8, 301, 2, 128), (512, 12102, 2, 256), (256, 1683, 1, 128), (6, 65, 2, 36)])
+def test_logits_ce_forward_backward_fp32_path(A, M, V, groups, d):
+    g = torch.Generator().manual_seed(M * 3 + V + d)
+    out = torch.randn(M, d, generator=g) * (16.0 / d ** 0.5)
+    E = torch.randn(V, d, generator=g) * 0.3
+    tgt = torch.randint(0, V, (M,), generator=g)
+    oo, Eo = out.double().requires_grad_(True), E.double().requires_grad_(True)
+    logits = oo @ Eo.t()
+    per = M // groups
+    ref = torch.stack([torch.nn.functional.cross_entropy(logits[i * per:(i + 1) * per], tgt[i * per:(i + 1) * per])
+                       for i in range(groups)])
+    wgt = torch.tensor([1.0, -0.7][:groups], dtype=torch.float64)
+    (ref * wgt).sum().backward()
+    oc, Ec = out.cuda().requires_grad_(True), E.cuda().requires_grad_(True)
+    loss = A.ops.LogitsCEFn.apply(oc, Ec, tgt.cuda(), groups, 3)
+    close(loss, ref, 1e-5, 'CE loss')
+    (loss * wgt.float().cuda()).sum().backward()
+    close(oc.grad, oo.grad, 2e-4, 'd_out')
+    close(Ec.grad, Eo.grad, 2e-4, 'd_E')
+
+
+@pytest.mark.parametrize('M,V,k,d', [(4, 301, 50, 128), (256, 12102, 50, 256), (100, 1683, 50, 128), (7, 70, 10, 256), (130, 20034, 20, 128)])
+def test_logits_topk_fused_fp32_path(A, M, V, k, d):
+    g = torch.Generator().manual_seed(M + V + k + d)
+    out = torch.randn(M, d, generator=g)
+    E = torch.randn(V, d, generator=g) * 0.5
+    pos = torch.randint(1, V, (M,), generator=g)
+    scores = (out.double() @ E.double().t())
+    _, ref_idx = O.full_sort_topk(scores.float(), k)
+    val, idx, rec = A.ops.full_sort_topk(out.cuda(), E.cuda(), k, pos.cuda(), 3)
+    idx, val, rec = idx.cpu(), val.cpu(), rec.cpu()
+    assert (idx != 0).all() and (idx >= 0).all()
+    assert (val[:, :-1] >= val[:, 1:]).all()
+    close(val, torch.gather(scores, 1, idx), 3e-6, 'top-k scores')
+    ok, nbad = O.topk_equal_modulo_ties(idx, ref_idx, scores.float())
+    assert ok, nbad
+    flags = O.hit_flags(idx, pos)
+    assert torch.equal(rec[:, :-1], flags) and (rec[:, -1] == 1).all()
+
+
 def test_unsupported_shapes_fail_loudly(A):
     with pytest.raises(A.AcsrError):
-        A.ops.logits_scores(torch.randn(4, 128).cuda(), torch.randn(10, 128).cuda(), 3)      # d != 64 (ABI v1)
+        A.ops.logits_scores(torch.randn(4, 66).cuda(), torch.randn(10, 66).cuda(), 3)        # d % 4 != 0
     with pytest.raises(A.AcsrError):
         A.ops.logits_scores(torch.randn(4, 64), torch.randn(10, 64), 3)                       # CPU tensors
     with pytest.raises(A.AcsrError):
