@@ -62,8 +62,8 @@ class FusedTrainStep(object):
             self._streams[key] = torch.cuda.Stream(device=dev)
         return self._streams[key]
 
-    def _branch_buffers(self, Bs, L, dev, idx):
-        """activations saved for the backward + gradient buffers of one group of Bs sequences."""
+    def _branch_buffers(self, Bs, L, dev, idx, grads=True):
+        """activations saved for the backward + (grads) gradient buffers of one group of Bs sequences."""
         key = ('branch', Bs, L, idx)
         if key in self.buf:
             return self.buf[key]
@@ -77,15 +77,17 @@ class FusedTrainStep(object):
         for l in range(N):
             R = 2 * T if l == N - 1 else T
             qkv, aqk = f(3, T, d), f(2, T, d)
+            Rp = 1 if (l == N - 1 and self.compact_last) else R      # the compact last layer keeps its dense part in b['c']
             lb = dict(qkv=qkv, aqk=aqk, mq=qkv[0], mk=qkv[1], mv=qkv[2], aq=aqk[0], ak=aqk[1], gl=f(T, L), ctx=f(R, d),
-                      hz=f(R, d), st_a=f(R, 2), h=f(R, d), z1=f(R, I), a1=f(R, I), z2=f(R, d), st_f=f(R, 2), out=f(R, d))
+                      hz=f(Rp, d), st_a=f(Rp, 2), h=f(Rp, d), z1=f(Rp, I), a1=f(Rp, I), z2=f(Rp, d), st_f=f(Rp, 2), out=f(Rp, d))
             # buffers read by the weight-gradient kernels are per layer: the side stream may still be reading layer l's
             # while the branch stream already writes layer l-1's
-            for n, w in (('d_z2', d), ('d_z1', I), ('d_hz', d), ('d_gl', L)):
-                lb[n] = f(2 * T, w)
-            lb['d_qkv'], lb['d_aqk'] = f(3, 2 * T, d), f(2, 2 * T, d)
-            lb['d_mq'], lb['d_mk'], lb['d_mv'] = lb['d_qkv'][0], lb['d_qkv'][1], lb['d_qkv'][2]
-            lb['d_aq'], lb['d_ak'] = lb['d_aqk'][0], lb['d_aqk'][1]
+            if grads:
+                for n, w in (('d_z2', d), ('d_z1', I), ('d_hz', d), ('d_gl', L)):
+                    lb[n] = f(2 * T if (Rp > 1 or n == 'd_gl') else 1, w)
+                lb['d_qkv'], lb['d_aqk'] = f(3, 2 * T, d), f(2, 2 * T, d)
+                lb['d_mq'], lb['d_mk'], lb['d_mv'] = lb['d_qkv'][0], lb['d_qkv'][1], lb['d_qkv'][2]
+                lb['d_aq'], lb['d_ak'] = lb['d_aqk'][0], lb['d_aqk'][1]
             b['layers'].append(lb)
         # last layer: only position len-1 of each sequence feeds the losses, so everything after its attention runs on
         # 2*Bs compact rows ([calibrated ; attacked]) instead of 2*T
@@ -93,8 +95,9 @@ class FusedTrainStep(object):
         b['c'] = dict(ctx=f(C, d), x=f(Bs, d), hz=f(C, d), st_a=f(C, 2), h=f(C, d), z1=f(C, I), a1=f(C, I), z2=f(C, d), st_f=f(C, 2),
                       out=f(C, d), d_out=f(C, d), d_z2=f(C, d), d_h=f(C, d), d_a1=f(C, I), d_z1=f(C, I), d_hz=f(C, d), d_x=f(C, d),
                       d_ctx=f(C, d))
-        for n, w in (('d_out', d), ('d_a1', I), ('d_h', d), ('d_x', d), ('d_ctx', d)):
-            b[n] = f(2 * T, w)
+        if grads:
+            for n, w in (('d_out', d), ('d_a1', I), ('d_h', d), ('d_x', d), ('d_ctx', d)):
+                b[n] = f(2 * T, w)
         self.buf[key] = b
         return b
 
@@ -386,7 +389,7 @@ class FusedTrainStep(object):
         dev = seq.device
         rt = m._runtime(dev)
         jb = self._joint_buffers(B, dev)
-        br = dict(idx=0, sl=slice(0, B), seq=seq, ln=ln, buf=self._branch_buffers(B, L, dev, 'eval'), rand=rt.rand,
+        br = dict(idx=0, sl=slice(0, B), seq=seq, ln=ln, buf=self._branch_buffers(B, L, dev, 'eval', grads=False), rand=rt.rand,
                   stream=torch.cuda.current_stream(), side=None)
         jb['pen'].zero_()
         self._forward_branch(br, jb, B, L, rt, False, need_att=False)

@@ -26,8 +26,17 @@ if ROOT not in sys.path:
 
 import torch
 
-WORKLOAD = dict(name='C2 synthetic Amazon-Beauty shape', users=22363, V=12102, L=50, d=64, n_layers=2, n_heads=2,
-                inner=256, B=256, topk=50)
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (default; the driver's bench line)
+    'c2': dict(name='C2 synthetic Amazon-Beauty shape', users=22363, V=12102, L=50, d=64, n_layers=2, n_heads=2, inner=256, B=256, topk=50),
+    # the other configs are parity-test cases (tests/); `--workload` times them with the same harness for DESIGN.md's table
+    'c3': dict(name='C3 synthetic Yelp shape', users=30431, V=20034, L=50, d=64, n_layers=2, n_heads=2, inner=256, B=256, topk=50),
+    'c3v': dict(name='C3 synthetic Yelp shape, repo variant (config/yelp.yaml)', users=30431, V=20034, L=50, d=128, n_layers=3, n_heads=8,
+                inner=64, B=256, topk=50),
+    'c4': dict(name='C4 1M-item catalogue', users=22363, V=1000001, L=50, d=64, n_layers=2, n_heads=2, inner=256, B=256, topk=50),
+    'c5': dict(name='C5 long-sequence stress', users=22363, V=12102, L=200, d=256, n_layers=4, n_heads=4, inner=1024, B=2048, topk=50),
+}
+WORKLOAD = dict(WORKLOADS['c2'])
 
 
 def model_cfg():
@@ -203,10 +212,11 @@ def run_ours(args):
         ge.build()
     if world > 1:
         dist.barrier()
-    use_graph = world == 1 or bool(args.dp_graph)
+    use_graph = (world == 1 or bool(args.dp_graph)) and not (world > 1 and WORKLOAD['V'] >= 500000) and WORKLOAD['L'] <= 64
     A, cfg, config, model, trainer = build(dev, rank, world, cuda_graph=use_graph)
+    vocab_parallel = world > 1 and WORKLOAD['V'] >= 500000     # C4: logits / CE / top-k sharded by catalogue rows over the ranks
     if world > 1:
-        trainer.enable_data_parallel()
+        trainer.enable_data_parallel(vocab_parallel=vocab_parallel)
     B, L, V, K, W = WORKLOAD['B'], WORKLOAD['L'], WORKLOAD['V'], args.steps, args.warmup
     nb = 8                                                             # distinct synthetic batches cycled through
     seq, ln, tgt = A.data.synth_sequences(nb * B, L, V, seed=42 + rank)
@@ -325,7 +335,7 @@ def run_ours(args):
     topk_ = kernels[top]
     calls = max(1.0, topk_['calls_per_step'])
     roof = {'kernel': top, 'bound': 'hbm', 'achieved': topk_['gbs'], 'peak': peak, 'unit': 'GB/s',
-            'frac': (round(topk_['gbs'] / peak, 4) if topk_['gbs'] else None), 'traffic': measured_traffic(top),
+            'frac': (round(topk_['gbs'] / peak, 4) if topk_['gbs'] else None), 'traffic': measured_traffic(top) if args.workload == 'c2' else None,
             'traffic_source': 'profiles/r01_traffic_v5.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, same workload)',
             'peak_source': peak_src,
             'avg_launch_us': round(topk_['ms_per_step'] / calls * 1e3, 2),
@@ -358,7 +368,7 @@ def run_ours(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(cfg, B, L, V, budget_s=20.0)
+        cpu = cpu_baseline(cfg, B if args.workload == 'c2' else min(B, 32), L, V, budget_s=20.0)
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in host[0].columns)
     line = {
         'metric': 'AC-SASRec train seq/s', 'value': round(world * B * K / (ms_dev / 1e3), 1), 'unit': 'seq/s',
@@ -368,7 +378,9 @@ def run_ours(args):
                                'lengths LogNormal(ln7,0.8), items Zipf(1); L2 flushed (256 MiB write) between timed steps'
                                % (WORKLOAD['name'], V, WORKLOAD['users'], L, WORKLOAD['d'], WORKLOAD['n_layers'], WORKLOAD['n_heads'],
                                   WORKLOAD['inner'], B, kmax),
-                   'parallelism': 'dp%d (batch-parallel, replicated item table, NCCL all-reduce of the flat gradient)' % world if world > 1 else 'single GPU',
+                   'parallelism': ('dp%d (batch-parallel, NCCL all-reduce of the flat gradient%s)'
+                                   % (world, '; logits/CE/top-k vocab-sharded: all-gather of out and of the (max, sum-exp) partials, '
+                                      'reduce-scatter of d_out' if vocab_parallel else ', replicated item table')) if world > 1 else 'single GPU',
                    'launch': ('CUDA graph replay of the whole step' + (' (NCCL all-reduce captured)' if world > 1 else '')) if use_graph else 'eager launches + NCCL',
                    'logits': '3xTF32 tcgen05 (fp32-level accuracy)'},
         'e2e': {'value': round(world * B * K / (ms_e2e / 1e3), 1), 'unit': 'seq/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8},
@@ -487,10 +499,16 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS), help='c2 = the headline configuration (default)')
+    ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the workload')
     ap.add_argument('--dp-graph', type=int, default=1, help='capture the NCCL all-reduce inside the CUDA graph at N>1 (0 = eager launches)')
     ap.add_argument('--profile', action='store_true',
                     help='launch-list mode for ncu: W+K eager training steps and K eval batches, nothing else')
     args = ap.parse_args()
+    WORKLOAD.clear()
+    WORKLOAD.update(WORKLOADS[args.workload])
+    if args.batch > 0:
+        WORKLOAD['B'] = args.batch
     if args.profile:
         return run_profile(args)
     if args.impl == 'reference':

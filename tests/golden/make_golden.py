@@ -189,6 +189,14 @@ CASES = [
                                                    rich_calibrated_combine='fixed')),
     ('relu_h8_eval', 131, 3, 20, False, dict(n_layers=1, n_heads=8, hidden_size=128, inner_size=64,
                                              hidden_act='relu')),
+    # long sequences (L > 64: attn_long.cu) at a hidden size off the tensor-core logits path (logits_simt.cu); the shape family
+    # of BASELINE configuration #5 (L=200, d=256, 4 heads) at a size that stays a small fixture
+    # (the reference's gate is Linear(d, 50) whatever the sequence length -- acsasrec.py never passes seq_length, layers.py:878 --
+    # so the unmodified reference only runs L != 50 with combine_option fixed / annealing)
+    ('long_train', 151, 2, 21, True, dict(n_layers=2, n_heads=4, hidden_size=128, inner_size=256, MAX_ITEM_LIST_LENGTH=100,
+                                          combine_option='fixed')),
+    ('long_eval', 151, 2, 22, False, dict(n_layers=2, n_heads=4, hidden_size=128, inner_size=256, MAX_ITEM_LIST_LENGTH=100,
+                                          combine_option='fixed', hidden_act='swish')),
 ]
 
 if __name__ == '__main__':

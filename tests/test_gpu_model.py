@@ -353,3 +353,60 @@ def test_full_size_properties_million_item_catalogue(A):
     d_out, _ = A.ops.linear_wgrad(Gt, E, want_bias=False)
     want_d = (Gt.double().t() @ E.double())
     assert float((d_out.double() - want_d).abs().max()) < 1e-4 * float(want_d.abs().max())
+
+
+SHAPES = {
+    # BASELINE.json configs at their own model shapes, small batch / catalogue so the CPU oracle finishes in seconds
+    'c3_yelp_variant': (dict(n_layers=3, n_heads=8, hidden_size=128, inner_size=64), 2003, 6),          # config/yelp.yaml:39-42
+    'c5_long_stress': (dict(n_layers=4, n_heads=4, hidden_size=256, inner_size=1024, MAX_ITEM_LIST_LENGTH=200), 1201, 3),
+    'c5_long_fixed': (dict(n_layers=2, n_heads=4, hidden_size=256, inner_size=512, MAX_ITEM_LIST_LENGTH=200,
+                           combine_option='fixed', two_level=False, rich_calibrated_combine='fixed'), 301, 2),
+}
+
+
+@pytest.mark.parametrize('shape', sorted(SHAPES))
+def test_config_shapes_train_step_and_eval_vs_oracle(A, shape):
+    """fused training step (losses + routed gradients) and full-sort eval against the oracle on seeded inputs with the
+    dropout masks / attack noise injected, at the model shapes of BASELINE configs #3 (repo variant) and #5."""
+    kw, V, B = SHAPES[shape]
+    cfg = O.default_cfg(**kw)
+    L, N, H = cfg['MAX_ITEM_LIST_LENGTH'], cfg['n_layers'], cfg['n_heads']
+    params = O.init_params(cfg, V, seed=7)
+    g = torch.Generator().manual_seed(8)
+    for n in params:                               # non-trivial biases / LayerNorm weights
+        if n.endswith('.bias'):
+            params[n] = params[n] + torch.randn(params[n].shape, generator=g) * 0.02
+    seq, ln, pos = O.synth_batch(B, L, V, seed=9)
+    ln[0] = L
+    seq[0] = torch.randint(1, V, (L,), generator=g)
+    rnd = O.draw_rand(cfg, B, L, seed=10, train=True)
+    la_o, lc_o, grads = O.train_grads(params, cfg, seq, ln, pos, rnd)
+    config = make_config(A, cfg)
+    model = A.ACSASRec(config, DS(V)).to('cuda')
+    model.load_state_dict({k: v.cuda() for k, v in params.items()}, strict=True)
+    model._debug_rand = {k: v.cuda() for k, v in rnd.d.items()}
+    trainer = A.ACSASRecTrainer(config, model)
+    assert trainer.fused is not None
+    model.train()
+    inter = A.Interaction({'item_id_list': seq.cuda(), 'item_length': ln.cuda(), 'item_id': pos.cuda()})
+    la, lc = trainer.fused(inter)
+    assert abs(float(la) - float(la_o)) < 1e-4 * abs(float(la_o)), (float(la), float(la_o))      # north_star: 1e-3
+    assert abs(float(lc) - float(lc_o)) < 1e-4 * abs(float(lc_o)), (float(lc), float(lc_o))
+    for n, p in model.named_parameters():
+        ref = grads[n]
+        scale = float(ref.abs().max())
+        err = float((p.grad.cpu() - ref).abs().max())
+        assert err <= 1e-3 * scale + 1e-8, (n, err, scale)
+    # eval: scores, top-k indices (modulo ties), hit flags
+    model.eval()
+    model._debug_rand = None
+    k = 50
+    with torch.no_grad():
+        _, scores = model.full_sort_predict(inter)
+        val, idx, rec = model.full_sort_topk(inter, k, inter['item_id'])
+    ref_scores = O.full_sort_scores(params, cfg, seq, ln)
+    assert rel(scores, ref_scores) < 1e-4
+    _, ref_idx = O.full_sort_topk(ref_scores, k)
+    ok, nbad = O.topk_equal_modulo_ties(idx.cpu(), ref_idx, ref_scores)
+    assert ok, nbad
+    assert torch.equal(rec.cpu()[:, :-1], O.hit_flags(idx.cpu(), pos))
