@@ -102,7 +102,18 @@ __device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem
     useA = useA && __any_sync(kFull, nzA && rowok);
     const float dp = dpen[s];
     live[s] = useR || useA || dp != 0.f;
-    if (!live[s]) continue;
+    if (!live[s]) {
+      if (LONG && rowok) {                  // the workspace is not pre-zeroed: every entry in play is written
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj)
+          if ((act >> jj) & 1u) {
+            const long long e = (long long)i * L + sub + G * jj;
+            bs.gS[s][e] = 0.f;
+            bs.gS2[s][e] = 0.f;
+          }
+      }
+      continue;
+    }
     const bool owner = s == 0;
     float dO[NJ], dP[NJ], dM[NJ], tmp[NJ];
 #pragma unroll
@@ -289,6 +300,20 @@ __device__ __forceinline__ void bwd_row_iter_m(const AttnParams& p, const AttnSm
   row_forward_m<DH, G, NJ>(p, sm, kc, b, h, i, bound, sub, Msoft, D3, act);
   float* gbuf = wbuf + grp * 2 * NS * rstride;
   const int c0 = CM::c0(sub);
+  if (LONG && rowok) {                      // the workspace is not pre-zeroed: this row's dS, R, A (and dS' without a penalty) are zero
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj)
+      if ((act >> jj) & 1u) {
+        const long long e = (long long)i * L + sub + G * jj;
+        bs.gR[e] = 0.f;
+        bs.gA[e] = 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          bs.gS[s][e] = 0.f;
+          if (dpen[s] == 0.f) bs.gS2[s][e] = 0.f;
+        }
+      }
+  }
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const float dp = dpen[s];

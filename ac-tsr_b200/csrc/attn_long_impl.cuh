@@ -8,7 +8,7 @@
 // private buffer and runs the same row iteration as the short kernels (attn_fwd_rows.cuh / attn_bwd_rows.cuh).
 // Rows are handed out heaviest first.
 //
-// Backward: the row phase writes dS, dS' (per cotangent stream) and R, A row-major into a caller-provided global
+// Backward: the row phase writes dS, dS' (per cotangent stream) and R, A row-major (every entry in play, no memset) into a caller-provided global
 // workspace (acsr_set_workspace; 4*(2*NS+2)*L*L bytes per (sequence, head), the batch is cut into chunks that fit),
 // and a second kernel finishes the column-side gradients dK, dK', dV as [L,L]^T x [L,dh] products: thread = key
 // column j, the [L,dh] right-hand tile broadcast from shared memory, rows i >= j only.
@@ -115,6 +115,25 @@ __device__ __forceinline__ void load_row(float* dst, const float* src, int b, in
   for (int c = lane; c < DH; c += 32) dst[c] = g[c];
 }
 
+// the same copy split in two so that the global loads of the NEXT row are in flight while the current row is processed
+template <int DH>
+struct RowRegs { float v[(DH + 31) / 32]; };
+template <int DH>
+__device__ __forceinline__ void fetch_row(RowRegs<DH>& r, const float* src, int b, int h, int i, int L, int d) {
+  const int lane = threadIdx.x & 31;
+  if (src == nullptr) return;
+  const float* g = src + ((long long)b * L + i) * d + h * DH;
+#pragma unroll
+  for (int q = 0; q < (DH + 31) / 32; ++q) if (lane + 32 * q < DH) r.v[q] = __ldg(g + lane + 32 * q);
+}
+template <int DH>
+__device__ __forceinline__ void put_row(float* dst, const RowRegs<DH>& r, const float* src) {
+  const int lane = threadIdx.x & 31;
+  if (src == nullptr) return;
+#pragma unroll
+  for (int q = 0; q < (DH + 31) / 32; ++q) if (lane + 32 * q < DH) dst[lane + 32 * q] = r.v[q];
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
@@ -147,27 +166,37 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_long_fwd_kernel(const At
   cx.rowbuf = lc.rowbuf + warp * 2 * LP;
   cx.pen = 0.f;
   const int rt = p.ctx_rows ? (int)p.ctx_rows[b] - 1 : -1;
-  for (int t0 = next_task(sm.misc + 2, 1); t0 < L; t0 = next_task(sm.misc + 2, 1)) {   // heaviest rows first
+  RowRegs<DH> rq, rq2;
+  int t0 = next_task(sm.misc + 2, 1);
+  if (t0 < L) {
+    if (!(rt >= 0 && rt != L - 1 - t0)) fetch_row<DH>(rq, p.mq, b, h, L - 1 - t0, L, p.d);
+    fetch_row<DH>(rq2, p.aq, b, h, L - 1 - t0, L, p.d);
+  }
+  while (t0 < L) {                                   // heaviest rows first
     const int i = L - 1 - t0;
     const int bound = min(i + 1, nkey);
     const int nj = (bound + 31) >> 5;
+    const bool mask_only = rt >= 0 && rt != i;       // context not consumed: attack mask -> penalty only
     AttnSmem s2 = sm;
     s2.Q = wq - i * dhp;
     s2.Q2 = wq2 - i * dhp;
     __syncwarp();
-    if (rt >= 0 && rt != i) {            // context not consumed: attack mask -> penalty only
+    if (!mask_only) put_row<DH>(wq, rq, p.mq);
+    put_row<DH>(wq2, rq2, p.aq);
+    __syncwarp();
+    t0 = next_task(sm.misc + 2, 1);
+    if (t0 < L) {                                    // next row's vectors: in flight while this row is processed
+      if (!(rt >= 0 && rt != L - 1 - t0)) fetch_row<DH>(rq, p.mq, b, h, L - 1 - t0, L, p.d);
+      fetch_row<DH>(rq2, p.aq, b, h, L - 1 - t0, L, p.d);
+    }
+    if (mask_only) {
       if (p.pen_sq == nullptr) continue;
-      load_row<DH>(wq2, p.aq, b, h, i, L, p.d);
-      __syncwarp();
       if (nj <= 2) fwd_row_iter_m<DH, 32, 2>(p, s2, kc, b, h, i, true, bound, lane, cx);
       else if (nj <= 4) fwd_row_iter_m<DH, 32, 4>(p, s2, kc, b, h, i, true, bound, lane, cx);
       else if (nj <= 6) fwd_row_iter_m<DH, 32, 6>(p, s2, kc, b, h, i, true, bound, lane, cx);
       else fwd_row_iter_m<DH, 32, 8>(p, s2, kc, b, h, i, true, bound, lane, cx);
       continue;
     }
-    load_row<DH>(wq, p.mq, b, h, i, L, p.d);
-    load_row<DH>(wq2, p.aq, b, h, i, L, p.d);
-    __syncwarp();
     if (nj <= 2) fwd_row_iter<DH, 32, 2>(p, s2, kc, b, h, i, true, bound, 0, lane, need_att, LP, cx);
     else if (nj <= 4) fwd_row_iter<DH, 32, 4>(p, s2, kc, b, h, i, true, bound, 0, lane, need_att, LP, cx);
     else if (nj <= 6) fwd_row_iter<DH, 32, 6>(p, s2, kc, b, h, i, true, bound, 0, lane, need_att, LP, cx);
@@ -239,10 +268,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_long_bwd_rows_kernel(con
   float* wbuf = bs.rowbuf + warp * 2 * NS * LP;
   for (int c = lane; c < 4 * dhp; c += 32) wr[c] = 0.f;
   const int rt = p.ctx_rows ? (int)p.ctx_rows[b] - 1 : -1;
-  for (int t0 = next_task(sm.misc + 2, 1); t0 < L; t0 = next_task(sm.misc + 2, 1)) {
+  RowRegs<DH> rq, rq2, rt0, rt1;
+  auto fetch = [&](int i) {
+    fetch_row<DH>(rq2, p.aq, b, h, i, L, p.d);
+    if (!(rt >= 0 && rt != i)) {
+      fetch_row<DH>(rq, p.mq, b, h, i, L, p.d);
+      fetch_row<DH>(rt0, p.t0, b, h, i, L, p.d);
+      fetch_row<DH>(rt1, p.t1, b, h, i, L, p.d);
+    }
+  };
+  int t0 = next_task(sm.misc + 2, 1);
+  if (t0 < L) fetch(L - 1 - t0);
+  while (t0 < L) {
     const int i = L - 1 - t0;
     const int bound = min(i + 1, nkey);
     const int nj = (bound + 31) >> 5;
+    const bool mask_only = rt >= 0 && rt != i;
     AttnSmem s2 = sm;
     s2.Q = wr - i * dhp;
     s2.Q2 = wr + dhp - i * dhp;
@@ -250,9 +291,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_long_bwd_rows_kernel(con
     b2.sT0 = wr + 2 * dhp - i * dhp;
     b2.sT1 = wr + 3 * dhp - i * dhp;
     __syncwarp();
-    if (rt >= 0 && rt != i) {
-      load_row<DH>(wr + dhp, p.aq, b, h, i, L, p.d);
-      __syncwarp();
+    put_row<DH>(wr + dhp, rq2, p.aq);
+    if (!mask_only) {
+      put_row<DH>(wr, rq, p.mq);
+      put_row<DH>(wr + 2 * dhp, rt0, p.t0);
+      put_row<DH>(wr + 3 * dhp, rt1, p.t1);
+    }
+    __syncwarp();
+    t0 = next_task(sm.misc + 2, 1);
+    if (t0 < L) fetch(L - 1 - t0);                   // next row's vectors: in flight while this row is processed
+    if (mask_only) {
 #define ACSR_LROW_M(NJV) bwd_row_iter_m<DH, 32, NJV, NS, true>(p, s2, b2, kc, dpen, b, h, i, true, bound, 0, lane, LP, wbuf)
       if (nj <= 2) ACSR_LROW_M(2);
       else if (nj <= 4) ACSR_LROW_M(4);
@@ -261,11 +309,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_long_bwd_rows_kernel(con
 #undef ACSR_LROW_M
       continue;
     }
-    load_row<DH>(wr, p.mq, b, h, i, L, p.d);
-    load_row<DH>(wr + dhp, p.aq, b, h, i, L, p.d);
-    load_row<DH>(wr + 2 * dhp, p.t0, b, h, i, L, p.d);
-    load_row<DH>(wr + 3 * dhp, p.t1, b, h, i, L, p.d);
-    __syncwarp();
 #define ACSR_LROW(NJV) \
   bwd_row_iter<DH, 32, NJV, NS, true>(p, s2, b2, kc, f, dpen, b, h, i, true, bound, 0, lane, LP, wbuf, acc, accOq, accDq)
     if (nj <= 2) ACSR_LROW(2);
@@ -320,92 +363,131 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_long_bwd_rows_kernel(con
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// backward, column phase: out[j][:] = sum_{i >= j} X[i][j] * Y[i][:]  for the (2 NS + 2) workspace matrices
+// backward, column phase: out[j][:] = sum_{i >= j} X[i][j] * Y[i][:]  for the (2 NS + 2) workspace matrices.
+// Lane = key column (groups of 32 columns, only the nkey columns in play), the rows of a column group are dealt
+// round-robin to the 8 warps -- so short sequences (few columns, all L rows: padded query rows still carry the attack
+// mask's penalty gradient) keep every warp busy -- and the warps' partial sums meet in a transposed [dh][L] shared
+// accumulator (lane = column: conflict-free shared atomics).  Y = the [L,dh] head slice of Q, Q', t0 or t1 is staged
+// in shared memory once per product and read as float4 broadcasts.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kColThreads = 256;
+__host__ __device__ static inline int cols_lpo(int L) { return ((L + 31) & ~31) + 1; }
+
 template <int DH, int NS>
-__global__ void __launch_bounds__(kLongMaxL, 1) attn_long_bwd_cols_kernel(const AttnParams p, const float* __restrict__ ws, const int b0) {
+__global__ void __launch_bounds__(kColThreads, 2) attn_long_bwd_cols_kernel(const AttnParams p, const float* __restrict__ ws, const int b0) {
   extern __shared__ __align__(16) float smem_f[];
-  float* Y = smem_f;                                // [L][DH]
   const int L = p.L;
+  const int LPO = cols_lpo(L);
+  float* Y = smem_f;                                // [L][DH]
+  float* OUT = smem_f + (size_t)((L + 3) & ~3) * DH;  // [DH][LPO]
   const int g = b0 + blockIdx.x / p.H;
   const int b = p.order ? p.order[g] : g, h = blockIdx.x % p.H;
-  const int j = threadIdx.x;
-  const bool jok = j < L;
-  const int i0 = threadIdx.x & ~31;                 // first row that can be non-zero for this warp's columns
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int s_nkey;
+  if (threadIdx.x == 0) s_nkey = 1;
+  __syncthreads();
+  for (int j = threadIdx.x; j < L; j += kColThreads)
+    if (p.item_seq[(long long)b * L + j] != 0) atomicMax(&s_nkey, j + 1);
+  __syncthreads();
+  const int nkey = s_nkey;
+  const int ng = (nkey + 31) >> 5;
   const size_t LL = (size_t)L * L;
   const float* slice = ws + (size_t)blockIdx.x * long_ws_floats(L, NS);
   const float* g_col = slice + (2 * NS + 2) * LL;
   const bool t1_att = NS == 1 ? true : (p.t1_is_att != 0);
-  float acc[DH];
 
-  auto zero = [&]() {
-#pragma unroll
-    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+  auto clear = [&]() {
+    for (int e = threadIdx.x; e < DH * LPO; e += kColThreads) OUT[e] = 0.f;
   };
-  auto accumulate = [&](const float* X, const float* ysrc) {     // acc += X^T . Y  (Y = head slice of ysrc, NULL: nothing)
-    if (ysrc == nullptr) return;                                  // uniform over the CTA
-    __syncthreads();
+  // OUT += X^T . Y   (Y = head slice of ysrc; NULL: nothing to add).  Ends with a barrier.
+  auto product = [&](const float* X, const float* ysrc) {
+    if (ysrc == nullptr) { __syncthreads(); return; }            // uniform over the CTA
     const float* yb = ysrc + (long long)b * L * p.d + h * DH;
-    for (int e = threadIdx.x; e < L * (DH / 4); e += blockDim.x) {
+#pragma unroll 4
+    for (int e = threadIdx.x; e < L * (DH / 4); e += kColThreads) {
       const int r = e / (DH / 4), c4 = e % (DH / 4);
-      *reinterpret_cast<float4*>(Y + r * DH + c4 * 4) = *reinterpret_cast<const float4*>(yb + (long long)r * p.d + c4 * 4);
+      *reinterpret_cast<float4*>(Y + r * DH + c4 * 4) = __ldg(reinterpret_cast<const float4*>(yb + (long long)r * p.d + c4 * 4));
     }
     __syncthreads();
-    if (!jok) return;
-#pragma unroll 2
-    for (int i = i0; i < L; ++i) {
-      const float x = X[(size_t)i * L + j];
-      const float4* y4 = reinterpret_cast<const float4*>(Y + i * DH);
+    for (int cg = 0; cg < ng; ++cg) {
+      const int j = cg * 32 + lane;
+      const bool jv = j < nkey;
+      float acc[DH];
 #pragma unroll
-      for (int c4 = 0; c4 < DH / 4; ++c4) {
-        const float4 y = y4[c4];
-        acc[4 * c4 + 0] = fmaf(x, y.x, acc[4 * c4 + 0]);
-        acc[4 * c4 + 1] = fmaf(x, y.y, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(x, y.z, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(x, y.w, acc[4 * c4 + 3]);
+      for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+      const float* xc = X + (jv ? j : 0);
+      for (int i = cg * 32 + warp; i < L; i += 4 * kAttnWarps) {
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int iu = i + u * kAttnWarps;
+          x[u] = (jv && iu < L && iu >= j) ? xc[(size_t)iu * L] : 0.f;     // entries above the diagonal are never written
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int iu = i + u * kAttnWarps;
+          if (iu >= L) break;
+          const float4* y4 = reinterpret_cast<const float4*>(Y + iu * DH);
+#pragma unroll
+          for (int c4 = 0; c4 < DH / 4; ++c4) {
+            const float4 y = y4[c4];
+            acc[4 * c4 + 0] = fmaf(x[u], y.x, acc[4 * c4 + 0]);
+            acc[4 * c4 + 1] = fmaf(x[u], y.y, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(x[u], y.z, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(x[u], y.w, acc[4 * c4 + 3]);
+          }
+        }
+      }
+      if (jv) {
+#pragma unroll
+        for (int c = 0; c < DH; ++c) atomicAdd(OUT + c * LPO + j, acc[c]);
       }
     }
+    __syncthreads();
   };
-  auto flush = [&](float* out, int s) {
-    if (!jok) return;
-    float* o = out + s * p.s1_td + ((long long)b * L + j) * p.d + h * DH;
+  // out rows of stream s <- OUT (+ the rank-1 part of the spatial calibrator for dK); columns behind the last key get zeros
+  auto flush = [&](float* out, int s, bool rank1) {
+    for (int e = threadIdx.x; e < L * (DH / 4); e += kColThreads) {
+      const int j = e / (DH / 4), c4 = e % (DH / 4);
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j < nkey) {
+        float cdu = 0.f, cdt = 0.f;
+        if (rank1) { cdu = g_col[(2 * s + 0) * L + j]; cdt = g_col[(2 * s + 1) * L + j]; }
 #pragma unroll
-    for (int c4 = 0; c4 < DH / 4; ++c4)
-      *reinterpret_cast<float4*>(o + 4 * c4) = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+        for (int u = 0; u < 4; ++u) {
+          const int c = 4 * c4 + u;
+          v[u] = OUT[c * LPO + j];
+          if (rank1 && p.ow) v[u] = fmaf(cdu, __ldg(p.ow + DH + c), v[u]);
+          if (rank1 && p.dw) v[u] = fmaf(cdt, __ldg(p.dw + DH + c), v[u]);
+        }
+      }
+      *reinterpret_cast<float4*>(out + s * p.s1_td + ((long long)b * L + j) * p.d + h * DH + 4 * c4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
   };
 
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    // dK_s = dS_s^T Q + colDU_s (x) wo[dh:] + colDT_s (x) wd[dh:]
-    zero();
-    accumulate(slice + (2 * s) * LL, p.mq);
-    if (jok) {
-      const float cdu = g_col[(2 * s + 0) * L + j], cdt = g_col[(2 * s + 1) * L + j];
-#pragma unroll
-      for (int c = 0; c < DH; ++c) {
-        if (p.ow) acc[c] = fmaf(cdu, __ldg(p.ow + DH + c), acc[c]);
-        if (p.dw) acc[c] = fmaf(cdt, __ldg(p.dw + DH + c), acc[c]);
-      }
-    }
-    flush(p.d_mk, s);
-    // dK'_s = dS'_s^T Q'
-    zero();
-    accumulate(slice + (2 * s + 1) * LL, p.aq);
-    flush(p.d_ak, s);
+    clear();                                         // (ordered before the atomics by the barrier inside product)
+    product(slice + (2 * s) * LL, p.mq);             // dK_s = dS_s^T Q + colDU_s (x) wo[dh:] + colDT_s (x) wd[dh:]
+    flush(p.d_mk, s, true);
+    clear();
+    product(slice + (2 * s + 1) * LL, p.aq);         // dK'_s = dS'_s^T Q'
+    flush(p.d_ak, s, false);
   }
   // dV: stream 0 <- R^T t0 ; last stream <- (A or R)^T t1
   const float* XR = slice + (2 * NS) * LL;
   const float* XA = slice + (2 * NS + 1) * LL;
-  zero();
-  accumulate(XR, p.t0);
+  clear();
+  product(XR, p.t0);
   if (NS == 1) {
-    accumulate(t1_att ? XA : XR, p.t1);
-    flush(p.d_mv, 0);
+    product(t1_att ? XA : XR, p.t1);
+    flush(p.d_mv, 0, false);
   } else {
-    flush(p.d_mv, 0);
-    zero();
-    accumulate(t1_att ? XA : XR, p.t1);
-    flush(p.d_mv, NS - 1);
+    flush(p.d_mv, 0, false);
+    clear();
+    product(t1_att ? XA : XR, p.t1);
+    flush(p.d_mv, NS - 1, false);
   }
 }
 
@@ -438,7 +520,7 @@ static int launch_long_bwd(const AttnParams& p, cudaStream_t st) {
   const char* who = NS == 1 ? "attn_calib_bwd" : "attn_calib_bwd2";
   const int LP = (p.L + 3) & ~3;
   const size_t smem_r = (long_floats(LP, DH, 4, 2 * NS) + 2 * NS * LP + 4 * DH + kAttnWarps * 4) * sizeof(float);
-  const size_t smem_c = (size_t)p.L * DH * sizeof(float);
+  const size_t smem_c = ((size_t)((p.L + 3) & ~3) * DH + (size_t)DH * cols_lpo(p.L)) * sizeof(float);
   int rc = prep_long(attn_long_bwd_rows_kernel<DH, NS>, smem_r, who, p.L, DH);
   if (rc) return rc;
   rc = prep_long(attn_long_bwd_cols_kernel<DH, NS>, smem_c, who, p.L, DH);
@@ -453,10 +535,8 @@ static int launch_long_bwd(const AttnParams& p, cudaStream_t st) {
   const int chunk = (int)((ws_bytes / per_seq) < (size_t)p.B ? (ws_bytes / per_seq) : (size_t)p.B);
   for (int b0 = 0; b0 < p.B; b0 += chunk) {
     const int nb = p.B - b0 < chunk ? p.B - b0 : chunk;
-    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)nb * per_seq, st);
-    if (e != cudaSuccess) { set_error("%s: workspace memset: %s", who, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
     attn_long_bwd_rows_kernel<DH, NS><<<dim3(nb * p.H), dim3(kAttnThreads), smem_r, st>>>(p, ws, b0);
-    attn_long_bwd_cols_kernel<DH, NS><<<dim3(nb * p.H), dim3(kLongMaxL), smem_c, st>>>(p, ws, b0);
+    attn_long_bwd_cols_kernel<DH, NS><<<dim3(nb * p.H), dim3(kColThreads), smem_c, st>>>(p, ws, b0);
   }
   return check_launch(who);
 }

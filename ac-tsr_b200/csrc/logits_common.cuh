@@ -2,6 +2,7 @@
 // logits_simt.cu (fp32 FMA, any other hidden size).
 #pragma once
 #include "acsr_common.cuh"
+#include <cstdlib>
 
 namespace acsr {
 
@@ -32,6 +33,7 @@ struct LogitsParams {
   float* partial;        // [M, n_chunks, 2]
   // TOPK
   int k;
+  int n_slots;           // lists per row in pval / pidx (= acsr_logits_num_chunks); the kernel fills n_chunks <= n_slots of them
   long long idx_offset;
   int skip_col0;
   float* pval;           // [M, n_chunks, k]
@@ -51,6 +53,22 @@ static inline void logits_plan(LogitsParams& p, int batch = 1) {
   if (nc < 1) nc = 1;
   if (nc > p.n_tiles) nc = p.n_tiles;
   p.n_chunks = nc;
+}
+
+// top-k mode: pval / pidx hold n_slots = acsr_logits_num_chunks lists per row; the kernel may fill fewer (n_chunks <= n_slots,
+// ACSR_TOPK_MIN_TILES catalogue tiles per CTA at least) and pads the rest.  Measured on B200 (scripts/topk_micro.py): the first
+// tile of a CTA (filling the k-best lists) costs as much as many later ones, so spreading over all SMs (1) wins at every size.
+static inline void logits_plan_topk(LogitsParams& p) {
+  p.n_slots = p.n_chunks;
+  static int min_tiles = 0;
+  if (min_tiles == 0) {
+    const char* e = getenv("ACSR_TOPK_MIN_TILES");       // tuning knob
+    min_tiles = e ? atoi(e) : 1;
+    if (min_tiles < 1) min_tiles = 1;
+  }
+  int nc = (p.n_tiles + min_tiles - 1) / min_tiles;
+  if (nc < 1) nc = 1;
+  if (nc < p.n_chunks) p.n_chunks = nc;
 }
 
 // logits_simt.cu: same modes, same partial layouts, hidden size d (multiple of 4, <= 1024)

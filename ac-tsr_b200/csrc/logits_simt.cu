@@ -211,12 +211,17 @@ __global__ void __launch_bounds__(kSimtThreads, 1) logits_simt_kernel(const Logi
         if (cnt < k || x > thr) simt_topk_insert(x, sm.lidx[s * kSimtThreads + oslot], sm.lval, sm.lidx, tid, k, cnt, thr, minpos);
       }
       if (row_ok) {
-        float* ov = p.pval + ((long long)grow * p.n_chunks + chunk) * k;
-        long long* oi = p.pidx + ((long long)grow * p.n_chunks + chunk) * k;
+        float* ov = p.pval + ((long long)grow * p.n_slots + chunk) * k;
+        long long* oi = p.pidx + ((long long)grow * p.n_slots + chunk) * k;
         for (int s = 0; s < k; ++s) {
           const bool ok = s < cnt;
           ov[s] = ok ? sm.lval[s * kSimtThreads + tid] : -INFINITY;
           oi[s] = ok ? (long long)sm.lidx[s * kSimtThreads + tid] + p.idx_offset : -1;
+        }
+        for (int c = p.n_chunks + chunk; c < p.n_slots; c += p.n_chunks) {     // lists no CTA produces
+          float* pv = p.pval + ((long long)grow * p.n_slots + c) * k;
+          long long* pi = p.pidx + ((long long)grow * p.n_slots + c) * k;
+          for (int s = 0; s < k; ++s) { pv[s] = -INFINITY; pi[s] = -1; }
         }
       }
     }
@@ -226,6 +231,7 @@ __global__ void __launch_bounds__(kSimtThreads, 1) logits_simt_kernel(const Logi
 template <int MODE>
 static int launch_simt(LogitsParams& p, int d, cudaStream_t st, const char* who) {
   logits_plan(p);
+  if (MODE == MODE_TOPK) logits_plan_topk(p);
   size_t smem = (size_t)(kSimtKC * kBM + kSimtKC * kBN + 2 * kBM + kBM) * 4;
   if (MODE == MODE_TOPK) smem += (size_t)2 * p.k * kSimtThreads * 4;
   cudaError_t e = cudaFuncSetAttribute(logits_simt_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

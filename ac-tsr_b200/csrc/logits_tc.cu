@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
     long long g_tgt = -1;
     float* lval = reinterpret_cast<float*>(smem + Cfg::kOffTopk);           // [k][128]
     int* lidx = reinterpret_cast<int*>(smem + Cfg::kOffTopk + kMaxTopK * kBM * 4);
-    int cnt = 0, minpos = 0;
+    int cnt = 0, minpos = 0, npend = 0;
     float thr = -INFINITY;
     if (MODE == MODE_GRAD && row_ok) { g_lse = p.lse[grow]; g_scale = p.row_scale[grow]; g_tgt = p.target[grow]; }
     float lin_bias = 0.f;
@@ -281,14 +281,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
             run_m = nm;
           }
         } else {   // MODE_TOPK
+          // Thread-private k-best list (unsorted, cached minimum `thr`).  The 32 rows of a warp beat their thresholds at
+          // different columns, so inserting on the spot would serialise the warp (one active lane per insert) and the
+          // per-score bookkeeping would dominate the kernel.  Instead: a score that beats the row's threshold is PARKED in
+          // the row's spare slots [k, kMaxTopK) (one compare + predicated stores per score), and the warp drains the parked
+          // scores in lockstep -- the number of insert rounds is the maximum over the lanes, not the sum.
           const int k = p.k;
+          const int pcap = kMaxTopK - k;
+          if (nvalid < 32 || (p.skip_col0 && c0 == 0)) {       // ragged last tile / excluded column 0: never candidates
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = v[i];
-            if (i < nvalid && !(p.skip_col0 && c0 + i == 0) && (cnt < k || x > thr))
-              topk_insert(x, (int)(c0 + i), lval, lidx, row, k, cnt, thr, minpos);
+            for (int i = 0; i < 32; ++i)
+              if (i >= nvalid || (p.skip_col0 && c0 + i == 0)) v[i] = -INFINITY;
           }
-          __syncwarp();
+          auto drain = [&]() {
+            while (__any_sync(0xffffffffu, npend > 0)) {
+              if (npend > 0) {
+                --npend;
+                const float y = lval[(k + npend) * kBM + row];
+                if (cnt < k || y > thr) topk_insert(y, lidx[(k + npend) * kBM + row], lval, lidx, row, k, cnt, thr, minpos);
+              }
+            }
+          };
+          if (__any_sync(0xffffffffu, cnt < k) || pcap < 8) {
+            // filling the list (first tile) or no room to park: insert on the spot
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = v[i];
+              if (x != -INFINITY && (cnt < k || x > thr)) topk_insert(x, (int)(c0 + i), lval, lidx, row, k, cnt, thr, minpos);
+            }
+          } else {
+#pragma unroll
+            for (int i0 = 0; i0 < 32; i0 += 8) {
+              // at most 8 scores are parked per row before the next check: drain when some row has fewer than 8 free slots
+              if (__any_sync(0xffffffffu, npend > pcap - 8)) drain();
+#pragma unroll
+              for (int i = i0; i < i0 + 8; ++i) {
+                const float x = v[i];
+                if (x > thr) {
+                  lval[(k + npend) * kBM + row] = x;
+                  lidx[(k + npend) * kBM + row] = (int)c0 + i;
+                  ++npend;
+                }
+              }
+            }
+            drain();
+          }
         }
       }
       tc_fence_before();
@@ -299,12 +336,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
       o[0] = run_m; o[1] = run_s;
     }
     if (MODE == MODE_TOPK && row_ok) {
-      float* ov = p.pval + ((long long)grow * p.n_chunks + chunk) * p.k;
-      long long* oi = p.pidx + ((long long)grow * p.n_chunks + chunk) * p.k;
+      float* ov = p.pval + ((long long)grow * p.n_slots + chunk) * p.k;
+      long long* oi = p.pidx + ((long long)grow * p.n_slots + chunk) * p.k;
       for (int s = 0; s < p.k; ++s) {
         const bool ok = s < cnt;
         ov[s] = ok ? lval[s * kBM + row] : -INFINITY;
         oi[s] = ok ? (long long)lidx[s * kBM + row] + p.idx_offset : -1;
+      }
+      // the partial layout has n_slots >= n_chunks lists per row: pad the ones no CTA produces
+      for (int c = p.n_chunks + chunk; c < p.n_slots; c += p.n_chunks) {
+        float* pv = p.pval + ((long long)grow * p.n_slots + c) * p.k;
+        long long* pi = p.pidx + ((long long)grow * p.n_slots + c) * p.k;
+        for (int s = 0; s < p.k; ++s) { pv[s] = -INFINITY; pi[s] = -1; }
       }
     }
   }
@@ -387,6 +430,7 @@ static int launch_tc(LogitsParams& p, cudaStream_t st, const char* who, int batc
   using Cfg = TcCfg<MODE>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
   logits_plan(p, batch);
+  if (MODE == MODE_TOPK) logits_plan_topk(p);
   cudaError_t e = cudaFuncSetAttribute(logits_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) { set_error("%s: smem attr: %s", who, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
   launch_pdl(logits_tc_kernel<MODE>, dim3(p.m_tiles * p.n_chunks, batch), dim3(kTcThreads), Cfg::kSmemBytes, st, p);

@@ -475,15 +475,19 @@ class FusedTrainStep(object):
                     lb['d_qkv'][:2].baddbmm_(lb['d_aqk'], st3['Waqk'])
                 # attack transforms are trained by the attacked-loss stream (rows [T,2T))
                 sst = fork()
-                LIB.call('acsr_linear_wgrad_batched', _p(lb['d_aqk'][0, T:]), _p(lb['qkv'][0]), T, d, d, _p(st3['gWaqk']),
-                         _p(st3['gbaqk']), 2, T2 * d, T * d, d * d, d, sst)
+                if self.tc or T * d * d < self.LIB_WGRAD_MACS:
+                    LIB.call('acsr_linear_wgrad_batched', _p(lb['d_aqk'][0, T:]), _p(lb['qkv'][0]), T, d, d, _p(st3['gWaqk']),
+                             _p(st3['gbaqk']), 2, T2 * d, T * d, d * d, d, sst)
+                else:
+                    for i2 in range(2):
+                        self._wgrad(lb['d_aqk'][i2, T:], lb['qkv'][i2], T, st3['gWaqk'][i2], st3['gbaqk'][i2], sst)
             else:
                 lb['d_mq'].addmm_(lb['d_aq'], aqt.weight)
                 lb['d_mk'].addmm_(lb['d_ak'], akt.weight)
                 sst = fork()
-                LIB.call('acsr_linear_wgrad', _p(lb['d_aq'][T:]), _p(lb['mq']), T, d, d, _p(aqt.weight.grad), _p(aqt.bias.grad), sst)
+                self._wgrad(lb['d_aq'][T:], lb['mq'], T, aqt.weight.grad, aqt.bias.grad, sst)
                 sst = fork()
-                LIB.call('acsr_linear_wgrad', _p(lb['d_ak'][T:]), _p(lb['mk']), T, d, d, _p(akt.weight.grad), _p(akt.bias.grad), sst)
+                self._wgrad(lb['d_ak'][T:], lb['mk'], T, akt.weight.grad, akt.bias.grad, sst)
             if gate:
                 if self.tc:
                     ops.linear_tok(lb['d_gl'], T2, L, layer.gate.weight, d, lb['d_mq'], d, ldx=L, w_sn=1, w_sk=d, wkb=64 * d,
@@ -491,16 +495,19 @@ class FusedTrainStep(object):
                 else:
                     lb['d_mq'].addmm_(lb['d_gl'], layer.gate.weight)
                 sst = fork()
-                LIB.call('acsr_linear_wgrad', _p(lb['d_gl']), _p(lb['mq']), T, L, d, _p(layer.gate.weight.grad),
-                         _p(layer.gate.bias.grad), sst)
+                self._wgrad(lb['d_gl'], lb['mq'], T, layer.gate.weight.grad, layer.gate.bias.grad, sst)
             if st3 is not None:
                 sst = fork()
-                LIB.call('acsr_linear_wgrad_batched', _p(lb['d_qkv'][0]), _p(x), T, d, d, _p(st3['gWqkv']), _p(st3['gbqkv']), 3,
-                         T2 * d, 0, d * d, d, sst)
+                if self.tc or T * d * d < self.LIB_WGRAD_MACS:
+                    LIB.call('acsr_linear_wgrad_batched', _p(lb['d_qkv'][0]), _p(x), T, d, d, _p(st3['gWqkv']), _p(st3['gbqkv']), 3,
+                             T2 * d, 0, d * d, d, sst)
+                else:
+                    for i3 in range(3):
+                        self._wgrad(lb['d_qkv'][i3], x, T, st3['gWqkv'][i3], st3['gbqkv'][i3], sst)
             else:
                 for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
                     sst = fork()
-                    LIB.call('acsr_linear_wgrad', _p(lb[dk]), _p(x), T, d, d, _p(lin.weight.grad), _p(lin.bias.grad), sst)
+                    self._wgrad(lb[dk], x, T, lin.weight.grad, lin.bias.grad, sst)
             rows_x = T2 if l > 0 else T                      # below the first layer only the calibrated stream trains anything
             if self.tc and st3 is not None:                  # d_x += [d_mq d_mk d_mv] . [Wq; Wk; Wv]: one K = 3d GEMM
                 ops.linear_tok(lb['d_qkv'], rows_x, 3 * d, st3['Wqkv'], d, d_x, d, ldx=d, xkb=T2 * d, w_sn=1, w_sk=d, wkb=d * d,
@@ -532,7 +539,7 @@ class FusedTrainStep(object):
                  _p(gb['d_z2']), _p(d_h), _p(ff.dense_2.bias.grad), _p(ff.LayerNorm.weight.grad),
                  _p(ff.LayerNorm.bias.grad), st)
         sst = fork()
-        LIB.call('acsr_linear_wgrad', _p(gb['d_z2']), _p(bf['a1']), w_rows, d, I, _p(ff.dense_2.weight.grad), None, sst)
+        self._wgrad(gb['d_z2'], bf['a1'], w_rows, ff.dense_2.weight.grad, None, sst)
         if self.tc:                                      # d_a1 = d_z2.W2 : the weight is read transposed
             ops.linear_tok(gb['d_z2'], R2, d, ff.dense_2.weight, I, d_a1, I, w_sn=1, w_sk=I, wkb=64 * I)
         else:
@@ -540,7 +547,7 @@ class FusedTrainStep(object):
         LIB.call('acsr_bias_act_bwd', _p(d_a1), _p(bf['z1']), _p(ff.dense_1.bias), R2, I, act_id, P, w_rows, _p(gb['d_z1']),
                  _p(ff.dense_1.bias.grad), st)
         sst = fork()
-        LIB.call('acsr_linear_wgrad', _p(gb['d_z1']), _p(bf['h']), w_rows, I, d, _p(ff.dense_1.weight.grad), None, sst)
+        self._wgrad(gb['d_z1'], bf['h'], w_rows, ff.dense_1.weight.grad, None, sst)
         if self.tc:
             ops.linear_tok(gb['d_z1'], R2, I, ff.dense_1.weight, d, d_h, d, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
         else:
@@ -550,11 +557,26 @@ class FusedTrainStep(object):
                  _p(aa.LayerNorm.weight), _p(bf['st_a']), R2, d, P, res_rows, w_rows, p_h, _p(bf['m_a']), rngp, base + 3,
                  _p(gb['d_hz']), _p(d_xres), _p(aa.dense.bias.grad), _p(aa.LayerNorm.weight.grad), _p(aa.LayerNorm.bias.grad), st)
         sst = fork()
-        LIB.call('acsr_linear_wgrad', _p(gb['d_hz']), _p(bf['ctx']), w_rows, d, d, _p(aa.dense.weight.grad), None, sst)
+        self._wgrad(gb['d_hz'], bf['ctx'], w_rows, aa.dense.weight.grad, None, sst)
         if self.tc:
             ops.linear_tok(gb['d_hz'], R2, d, aa.dense.weight, d, d_ctx, d, w_sn=1, w_sk=d, wkb=64 * d)
         else:
             torch.mm(gb['d_hz'][:R2], aa.dense.weight, out=d_ctx[:R2])
+
+    # weight-gradient reduction dW [N,K] += dY[:rows]^T . X[:rows] (+ db += column sums) on the stream `handle`.  The token-split
+    # kernel (acsr_linear_wgrad) is built for the small encoder matrices of the shipped configs; above LIB_WGRAD_MACS
+    # multiply-adds (config #5: 409 600 tokens x 256 x 1024) the reduction is a plain large GEMM and goes to the library.
+    LIB_WGRAD_MACS = 1 << 31
+
+    def _wgrad(self, dY, X, rows, dW, db, handle):
+        N, K = dY.shape[-1], X.shape[-1]
+        if self.tc or rows * N * K < self.LIB_WGRAD_MACS:
+            LIB.call('acsr_linear_wgrad', _p(dY), _p(X), rows, N, K, _p(dW), _p(db), handle)
+            return
+        with torch.cuda.stream(torch.cuda.ExternalStream(handle)):
+            dW.addmm_(dY[:rows].t(), X[:rows])
+            if db is not None:
+                db.add_(dY[:rows].sum(0))
 
     def _stacked(self, l):
         """stacked views [3,d,d]/[2,d,d] of the Q/K/V and attack-pair parameters (adjacent in FlatAdam's layout)."""

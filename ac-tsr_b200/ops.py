@@ -417,8 +417,33 @@ def topk_merge(pv, pi, k, positive=None):
     return val, idx, rec
 
 
+def topk_select(scores, k, positive=None, skip_col0=True, idx_offset=0):
+    """row-wise top-k of a dense score matrix (radix select in shared memory) -> (val, idx, rec_topk | None)."""
+    M, V = scores.shape
+    dev = scores.device
+    if not scores.is_cuda or scores.dtype != torch.float32 or scores.stride(1) != 1:
+        raise AcsrError('topk_select: scores must be a float32 CUDA matrix with unit column stride (rows may be strided)')
+    val = torch.empty((M, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((M, k), dtype=torch.int64, device=dev)
+    rec = torch.empty((M, k + 1), dtype=torch.int32, device=dev) if positive is not None else None
+    LIB.call('acsr_topk_select', scores.data_ptr(), M, V, scores.stride(0), k, int(skip_col0), idx_offset,
+             _p(positive.contiguous(), torch.int64) if positive is not None else None,
+             _p(val), _p(idx, torch.int64), _p(rec, torch.int32), _stream())
+    return val, idx, rec
+
+
+_SELECT_MAX = []
+
+
 def full_sort_topk(out, table, k, positive=None, passes=3):
-    """fused scores -> scores[:,0]=-inf -> top-k -> hit flags (trainer.py:941-942, collector.py:147-153)."""
+    """scores -> scores[:,0]=-inf -> top-k -> hit flags (trainer.py:941-942, collector.py:147-153).  Small catalogues
+    (one row of scores fits in shared memory): tensor-core scores, L2-resident, + radix select; large ones: the fused
+    logits + streaming top-k kernel and a merge of its per-chunk lists (the scores never exist)."""
+    if not _SELECT_MAX:
+        _SELECT_MAX.append(LIB.query('acsr_topk_select_max_items'))
+    V = table.shape[0]
+    if V <= _SELECT_MAX[0] and V - 1 >= k:
+        return topk_select(logits_scores(out, table, passes), k, positive)
     pv, pi = logits_topk_partial(out, table, k, 0, True, passes)
     return topk_merge(pv, pi, k, positive)
 

@@ -219,7 +219,7 @@ def run_ours(args):
         trainer.enable_data_parallel(vocab_parallel=vocab_parallel)
     B, L, V, K, W = WORKLOAD['B'], WORKLOAD['L'], WORKLOAD['V'], args.steps, args.warmup
     nb = 8                                                             # distinct synthetic batches cycled through
-    seq, ln, tgt = A.data.synth_sequences(nb * B, L, V, seed=42 + rank)
+    seq, ln, tgt = A.data.synth_sequences(nb * B, L, V, seed=42 + rank, full_len=bool(args.full_len))
     host = [A.Interaction({'item_id_list': seq[i * B:(i + 1) * B].pin_memory(), 'item_length': ln[i * B:(i + 1) * B].pin_memory(),
                            'item_id': tgt[i * B:(i + 1) * B].pin_memory()}) for i in range(nb)]
     devb = [h.to(dev) for h in host]
@@ -375,9 +375,9 @@ def run_ours(args):
         'n_gpus': world, 'steps': K, 'warmup': max(W, 3), 'ms_per_step': round(ms_dev / K, 4), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': '%s: V=%d, users=%d, L=%d, d=%d, layers=%d, heads=%d, inner=%d, train/eval batch %d per GPU, top-%d; '
-                               'lengths LogNormal(ln7,0.8), items Zipf(1); L2 flushed (256 MiB write) between timed steps'
+                               'lengths %s, items Zipf(1); L2 flushed (256 MiB write) between timed steps'
                                % (WORKLOAD['name'], V, WORKLOAD['users'], L, WORKLOAD['d'], WORKLOAD['n_layers'], WORKLOAD['n_heads'],
-                                  WORKLOAD['inner'], B, kmax),
+                                  WORKLOAD['inner'], B, kmax, 'all = L' if args.full_len else 'LogNormal(ln7,0.8)'),
                    'parallelism': ('dp%d (batch-parallel, NCCL all-reduce of the flat gradient%s)'
                                    % (world, '; logits/CE/top-k vocab-sharded: all-gather of out and of the (max, sum-exp) partials, '
                                       'reduce-scatter of d_out' if vocab_parallel else ', replicated item table')) if world > 1 else 'single GPU',
@@ -500,6 +500,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS), help='c2 = the headline configuration (default)')
+    ap.add_argument('--full-len', action='store_true', help='every sequence has the maximum length (worst case) instead of LogNormal lengths')
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the workload')
     ap.add_argument('--dp-graph', type=int, default=1, help='capture the NCCL all-reduce inside the CUDA graph at N>1 (0 = eager launches)')
     ap.add_argument('--profile', action='store_true',

@@ -219,6 +219,15 @@ int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_
 int acsr_topk_merge(const float* partial_val, const int64_t* partial_idx, int M, int n_parts, int k,
                     const int64_t* positive, float* topk_val, int64_t* topk_idx, int32_t* rec_topk, void* stream);
 
+/* dense variant for catalogues of at most acsr_topk_select_max_items() items (one row's scores as 32-bit keys in shared
+ * memory): top-k of every row of scores [M, ld] (first V columns) by a 4-pass radix select + a sort of the k winners.
+ * skip_col0 excludes column 0 (trainer.py:942); item id = column + idx_offset.  Together with acsr_logits_store this is the
+ * full-sort evaluation of small catalogues (the scores stay L2-resident); the fused acsr_logits_topk_partial path is for
+ * large / sharded ones. */
+int acsr_topk_select_max_items(void);
+int acsr_topk_select(const float* scores, int M, int64_t V, int64_t ld, int k, int skip_col0, int64_t idx_offset,
+                     const int64_t* positive, float* topk_val, int64_t* topk_idx, int32_t* rec_topk, void* stream);
+
 /* ---- encoder GEMMs on tcgen05 with the token rows on the UMMA M axis (3xTF32, fp32-level accuracy) ----
  * replaces the nn.Linear forward / input-gradient GEMMs of model/layers.py:658-659, 680, 687-689, 791-794, 887.
  * Y[r, n] (+)= sum_k X(r,k) * W(n,k) + bias[n], r < rows, n < N, k < K <= 256, with strided operands so that

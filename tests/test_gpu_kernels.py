@@ -493,15 +493,37 @@ def test_logits_topk_fused(A, M, V, k):
     pos = torch.randint(1, V, (M,), generator=g)
     scores = (out.double() @ E.double().t())
     _, ref_idx = O.full_sort_topk(scores.float(), k)
-    val, idx, rec = A.ops.full_sort_topk(out.cuda(), E.cuda(), k, pos.cuda(), 3)
-    idx, val, rec = idx.cpu(), val.cpu(), rec.cpu()
-    assert (idx != 0).all() and (idx >= 0).all()            # column 0 is excluded (trainer.py:942)
-    assert (val[:, :-1] >= val[:, 1:]).all()                # sorted descending
-    close(val, torch.gather(scores, 1, idx), 3e-6, 'top-k scores')
-    ok, nbad = O.topk_equal_modulo_ties(idx, ref_idx, scores.float())
-    assert ok, nbad
-    flags = O.hit_flags(idx, pos)
-    assert torch.equal(rec[:, :-1], flags) and (rec[:, -1] == 1).all()
+    for path in ('auto', 'fused'):          # auto: small catalogues take scores + radix select; fused: streaming top-k + merge
+        if path == 'auto':
+            val, idx, rec = A.ops.full_sort_topk(out.cuda(), E.cuda(), k, pos.cuda(), 3)
+        else:
+            pv, pi = A.ops.logits_topk_partial(out.cuda(), E.cuda(), k, 0, True, 3)
+            assert pv.shape[1] == A.ops.logits_num_chunks(M, V)
+            val, idx, rec = A.ops.topk_merge(pv, pi, k, pos.cuda())
+        idx, val, rec = idx.cpu(), val.cpu(), rec.cpu()
+        assert (idx != 0).all() and (idx >= 0).all()            # column 0 is excluded (trainer.py:942)
+        assert (val[:, :-1] >= val[:, 1:]).all()                # sorted descending
+        close(val, torch.gather(scores, 1, idx), 3e-6, 'top-k scores')
+        ok, nbad = O.topk_equal_modulo_ties(idx, ref_idx, scores.float())
+        assert ok, nbad
+        flags = O.hit_flags(idx, pos)
+        assert torch.equal(rec[:, :-1], flags) and (rec[:, -1] == 1).all()
+
+
+def test_topk_select_ties_and_short_rows(A):
+    """exact ties resolve to the lowest item id (stable descending sort); strided rows; k = V - 1."""
+    M, V, k = 9, 300, 50
+    g = torch.Generator().manual_seed(3)
+    sc = torch.randint(0, 12, (M, V + 7), generator=g).float()          # many exact ties, row stride > V
+    sc[0] = 1.0                                                          # a constant row
+    val, idx, _ = A.ops.topk_select(sc.cuda()[:, :V], k)
+    s2 = sc[:, :V].clone()
+    s2[:, 0] = -float('inf')
+    order = torch.sort(s2, dim=1, descending=True, stable=True)
+    assert torch.equal(val.cpu(), order.values[:, :k])
+    assert torch.equal(idx.cpu(), order.indices[:, :k])
+    val, idx, _ = A.ops.topk_select(sc.cuda()[:, :51], 50)              # k = V - 1: everything but column 0
+    assert torch.equal(idx.cpu().sort(dim=1).values, torch.arange(1, 51).expand(M, 50))
 
 
 # ---- hidden sizes other than 64 take the fp32 FMA path (logits_simt.cu): same entry points, same contracts ----
@@ -545,7 +567,8 @@ def test_logits_topk_fused_fp32_path(A, M, V, k, d):
     pos = torch.randint(1, V, (M,), generator=g)
     scores = (out.double() @ E.double().t())
     _, ref_idx = O.full_sort_topk(scores.float(), k)
-    val, idx, rec = A.ops.full_sort_topk(out.cuda(), E.cuda(), k, pos.cuda(), 3)
+    pv, pi = A.ops.logits_topk_partial(out.cuda(), E.cuda(), k, 0, True, 3)
+    val, idx, rec = A.ops.topk_merge(pv, pi, k, pos.cuda())
     idx, val, rec = idx.cpu(), val.cpu(), rec.cpu()
     assert (idx != 0).all() and (idx >= 0).all()
     assert (val[:, :-1] >= val[:, 1:]).all()
