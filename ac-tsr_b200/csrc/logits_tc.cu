@@ -425,6 +425,80 @@ __global__ void loss_combine_kernel(const double* __restrict__ pen_sq, int n_lay
   loss_att[0] = -ce[0] + (acc / n_layers) * w;
 }
 
+// ---- the three kernels above in ONE launch (the step's critical path runs through them): warp per row over the whole GPU ->
+// lse / target logit / row loss; the LAST CTA to finish (device-scope counter, reset for the next launch) then takes the group
+// means in a fixed order and evaluates the adversarial-loss glue -----------------------------------------------------------
+__global__ void __launch_bounds__(256) ce_finalize_losses_kernel(const float* __restrict__ partial, int n_parts, const float* __restrict__ out,
+                                                                 const float* __restrict__ table, const long long* __restrict__ target,
+                                                                 int M, int d, long long V, long long idx_offset, int n_groups,
+                                                                 float* __restrict__ lse, float* __restrict__ tgt_logit,
+                                                                 float* row_loss, float* __restrict__ loss,
+                                                                 const double* __restrict__ pen_sq, int n_layers, const float* w_ptr,
+                                                                 float w_val, float* __restrict__ loss_att, float* __restrict__ d_pen_sq,
+                                                                 unsigned int* counter) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double red[8];
+  __shared__ float s_loss[8];
+  __shared__ bool s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (m < M) {
+    float mx = -INFINITY;
+    for (int i = lane; i < n_parts; i += 32) mx = fmaxf(mx, partial[((long long)m * n_parts + i) * 2]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int i = lane; i < n_parts; i += 32) {
+      const float pm = partial[((long long)m * n_parts + i) * 2], ps = partial[((long long)m * n_parts + i) * 2 + 1];
+      if (ps > 0.f) s += ps * expf(pm - mx);
+    }
+    s = warp_sum(s);
+    const float l = mx + logf(s);
+    const long long t = target[m] - idx_offset;
+    float dot = 0.f;
+    if (t >= 0 && t < V)
+      for (int j = lane; j < d; j += 32) dot = fmaf(out[(long long)m * d + j], table[t * d + j], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) { lse[m] = l; tgt_logit[m] = dot; row_loss[m] = l - dot; }
+  }
+  __threadfence();                                  // this CTA's row losses are visible device-wide before it checks in
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const volatile float* rl = row_loss;
+  const int per_group = M / n_groups;
+  for (int g = 0; g < n_groups; ++g) {              // fixed summation order: deterministic
+    double s = 0.0;
+    for (int i = threadIdx.x; i < per_group; i += blockDim.x) s += (double)rl[g * per_group + i];
+    s = warp_sum_d(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+      const float lg = (float)(t / per_group);
+      loss[g] = lg;
+      s_loss[g] = lg;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *counter = 0u;                                  // ready for the next launch (graph replays included)
+    if (loss_att != nullptr) {
+      const float w = w_ptr ? w_ptr[0] : w_val;
+      float acc = 0.f;
+      for (int l = 0; l < n_layers; ++l) {
+        const float pn = sqrtf((float)pen_sq[l]);
+        acc += pn;
+        if (d_pen_sq) d_pen_sq[l] = (w / (2.0f * n_layers)) / pn;
+      }
+      loss_att[0] = -s_loss[n_groups - 1] + (acc / n_layers) * w;
+    }
+  }
+}
+
 template <int MODE>
 static int launch_tc(LogitsParams& p, cudaStream_t st, const char* who, int batch = 1) {
   using Cfg = TcCfg<MODE>;
@@ -493,6 +567,19 @@ int acsr_ce_finalize(const float* partial, int n_parts, const float* out, const 
              (const long long*)target, M, d, (long long)V, (long long)idx_offset, lse, tgt_logit, row_loss);
   launch_pdl(ce_mean_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, (const float*)row_loss, M, n_groups, loss);
   return check_launch("ce_finalize");
+}
+
+int acsr_ce_finalize_losses(const float* partial, int n_parts, const float* out, const float* table, const int64_t* target, int M, int d,
+                            int64_t V, int64_t idx_offset, int n_groups, float* lse, float* tgt_logit, float* row_loss, float* loss,
+                            const double* pen_sq, int n_layers, const float* mask_loss_weight, float mask_loss_weight_value,
+                            float* loss_attacked, float* d_pen_sq, uint32_t* counter, void* stream) {
+  ACSR_REQUIRE(partial && out && table && target && lse && tgt_logit && row_loss && loss && counter, "ce_finalize_losses: NULL pointer");
+  ACSR_REQUIRE(M > 0 && n_parts > 0 && n_groups > 0 && n_groups <= 8 && M % n_groups == 0, "ce_finalize_losses: bad sizes");
+  ACSR_REQUIRE(loss_attacked == nullptr || (pen_sq != nullptr && n_layers > 0), "ce_finalize_losses: penalty inputs missing");
+  launch_pdl(ce_finalize_losses_kernel, dim3((M + 7) / 8), dim3(256), 0, (cudaStream_t)stream, partial, n_parts, out, table,
+             (const long long*)target, M, d, (long long)V, (long long)idx_offset, n_groups, lse, tgt_logit, row_loss, loss, pen_sq, n_layers,
+             mask_loss_weight, mask_loss_weight_value, loss_attacked, d_pen_sq, (unsigned int*)counter);
+  return check_launch("ce_finalize_losses");
 }
 
 int acsr_loss_combine(const double* pen_sq, int n_layers, const float* ce_attacked, const float* mask_loss_weight, float mask_loss_weight_value,

@@ -54,6 +54,8 @@ class FusedTrainStep(object):
         self.n_branches = int(getattr(model, 'step_branches', 1))
         self._streams = {}
         self.compact_last = bool(getattr(model, 'compact_last', True))   # last layer's dense part on the len-1 rows only
+        import os
+        self.order_side = os.environ.get('ACSR_ORDER_SIDE', '1') == '1'     # sequence ordering next to, not in front of, the embedding
         self.pdl = bool(getattr(model, 'pdl', True))            # programmatic dependent launch between the step's kernels
 
     # ------------------------------------------------------------------------------------------
@@ -114,7 +116,7 @@ class FusedTrainStep(object):
         nc = ops.logits_num_chunks(2 * B, V)
         j = dict(pen=torch.zeros(N, dtype=torch.float64, device=dev), out2=f(2 * B, d), partial=f(2 * B, nc, 2), lse=f(2 * B),
                  tgt=f(2 * B), row_loss=f(2 * B), loss=f(2), loss_att=f(1), dpen=f(N), Gt=f(V, 2 * B), d_out2=f(2 * B, d),
-                 target2=torch.empty(2 * B, dtype=torch.int64, device=dev),
+                 target2=torch.empty(2 * B, dtype=torch.int64, device=dev), ce_cnt=torch.zeros(1, dtype=torch.int32, device=dev),
                  row_scale=torch.cat((torch.full((B,), 1.0 / B), torch.full((B,), -1.0 / B))).to(dev))
         self.buf[key] = j
         return j
@@ -195,15 +197,18 @@ class FusedTrainStep(object):
         if self.vp is not None:       # all-gather out -> shard-local partial CE -> all-gather (max, sum-exp) -> combine
             loss2, vst = self.vp.ce_forward(jb['out2'], E, jb['target2'], 2)
             jb['loss'].copy_(loss2)
-        else:
-            LIB.call('acsr_logits_ce_partial', _p(jb['out2']), _p(E), 2 * B, V, d, passes, _p(jb['partial']), st)
-            LIB.call('acsr_ce_finalize', _p(jb['partial']), jb['partial'].shape[1], _p(jb['out2']), _p(E),
-                     _p(jb['target2'], torch.int64), 2 * B, d, V, 0, 2, _p(jb['lse']), _p(jb['tgt']), _p(jb['row_loss']),
-                     _p(jb['loss']), st)
-        # pen_l = sqrt(sum (1-M_l)^2); loss_att = -CE(attacked) + w * mean_l pen_l; d loss_att / d pen_sq_l  -- one launch
         wp = m.mask_loss_weight.detach() if m.trainable_mask_loss_weight else None
-        LIB.call('acsr_loss_combine', jb['pen'].data_ptr(), N, _p(jb['loss'][1:]), _p(wp),
-                 0.0 if wp is not None else float(m.mask_loss_weight), _p(jb['loss_att']), _p(jb['dpen']), st)
+        wv = 0.0 if wp is not None else float(m.mask_loss_weight)
+        if self.vp is None:
+            # per-chunk (max, sum-exp) -> lse / target logit / row losses -> the two CE means -> pen_l = sqrt(sum (1-M_l)^2),
+            # loss_att = -CE(attacked) + w * mean_l pen_l, d loss_att / d pen_sq_l: one single-CTA launch after the GEMM
+            LIB.call('acsr_logits_ce_partial', _p(jb['out2']), _p(E), 2 * B, V, d, passes, _p(jb['partial']), st)
+            LIB.call('acsr_ce_finalize_losses', _p(jb['partial']), jb['partial'].shape[1], _p(jb['out2']), _p(E),
+                     _p(jb['target2'], torch.int64), 2 * B, d, V, 0, 2, _p(jb['lse']), _p(jb['tgt']), _p(jb['row_loss']),
+                     _p(jb['loss']), jb['pen'].data_ptr(), N, _p(wp), wv, _p(jb['loss_att']), _p(jb['dpen']),
+                     jb['ce_cnt'].data_ptr(), st)
+        else:
+            LIB.call('acsr_loss_combine', jb['pen'].data_ptr(), N, _p(jb['loss'][1:]), _p(wp), wv, _p(jb['loss_att']), _p(jb['dpen']), st)
         loss_cal = jb['loss'][0]
         loss_att = jb['loss_att'][0]
         if not training or getattr(self, '_stop_after', None) == 'ce':
@@ -271,8 +276,15 @@ class FusedTrainStep(object):
         E = m.item_embedding.weight
         posw = m.position_embedding.weight if m.use_position_embedding else None
         b['me'] = mask('emb')
-        # longest sequences first: order of the attention CTAs of this batch (forward and backward)
-        LIB.call('acsr_seq_order', _p(seq, torch.int64), Bs, L, _p(b['order'], torch.int32), st)
+        # longest sequences first: order of the attention CTAs of this batch (forward and backward).  Only the attention
+        # kernels read it, so the single-CTA sort runs next to the embedding and the first projections, not in front of them.
+        cur = torch.cuda.current_stream()
+        so = self._stream_for(seq.device, ('order', s)) if self.order_side else cur
+        if so is not cur:
+            so.wait_stream(cur)
+        LIB.call('acsr_seq_order', _p(seq, torch.int64), Bs, L, _p(b['order'], torch.int32), so.cuda_stream)
+        order_done = torch.cuda.Event()
+        order_done.record(so)
         LIB.call('acsr_embed_ln_dropout_fwd', _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight), _p(m.LayerNorm.bias),
                  m.LayerNorm.eps, T, L, d, V, p_h, _p(b['me']), rngp, soff + 1, _p(b['x0']), _p(b['st_e']), st)
         x = b['x0']
@@ -315,6 +327,8 @@ class FusedTrainStep(object):
             p_attn = aa.attn_dropout.p if training else 0.0
             lb['attn_args'] = self._attn_args(layer, lb, seq, Bs, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base)
             ctx_cal, ctx_att = lb['ctx'][:T], (lb['ctx'][T:] if last else None)
+            if l == 0:
+                cur.wait_event(order_done)
             LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal),
                      jb['pen'][l:].data_ptr() if need_att else None, None, _p(b['order'], torch.int32),
                      _p(ln, torch.int64) if (l == N - 1 and self.compact_last) else None, st)

@@ -204,6 +204,14 @@ int acsr_ce_finalize(const float* partial, int n_parts, const float* out, const 
  * w = mask_loss_weight[0] when the pointer is given (trainable_mask_loss_weight), else mask_loss_weight_value. */
 int acsr_loss_combine(const double* pen_sq, int n_layers, const float* ce_attacked, const float* mask_loss_weight,
                       float mask_loss_weight_value, float* loss_attacked, float* d_pen_sq, void* stream);
+/* acsr_ce_finalize + acsr_loss_combine in ONE launch (they sit on the training step's critical path): same outputs;
+ * loss_attacked[0] = -loss[n_groups-1] + w * mean_l sqrt(pen_sq[l]) (the attacked rows are the last group); loss_attacked may
+ * be NULL (then pen_sq / d_pen_sq are ignored).  counter: one uint32 in device memory, zero before the first call; the last
+ * CTA to finish does the reductions and resets it. */
+int acsr_ce_finalize_losses(const float* partial, int n_parts, const float* out, const float* table, const int64_t* target, int M, int d,
+                            int64_t V, int64_t idx_offset, int n_groups, float* lse, float* tgt_logit, float* row_loss, float* loss,
+                            const double* pen_sq, int n_layers, const float* mask_loss_weight, float mask_loss_weight_value,
+                            float* loss_attacked, float* d_pen_sq, uint32_t* counter, void* stream);
 /* CE backward part 1: Gt [V, ldg] (ldg >= M) = transpose of (exp(out.E^T - lse) - onehot(target)) * row_scale[m];
  * then d_E = Gt.out is a plain GEMM and d_out = Gt^T.E goes through acsr_linear_wgrad (reduction over V). */
 int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, const int64_t* target,

@@ -746,3 +746,45 @@ def test_linear_tok_bdrl(A, K, p, explicit):
         var = ((x - mean) ** 2).mean(-1, keepdim=True)
         ref = (x - mean) / torch.sqrt(var + 1e-12) * lw.double() + lb.double()
         close(out, ref, 2e-5, 'out')
+
+
+def test_ce_finalize_losses_equals_separate_kernels(A):
+    """single-launch CE finalize + adversarial-loss glue == acsr_ce_finalize followed by acsr_loss_combine."""
+    M, V, d, N = 512, 3001, 64, 3
+    g = torch.Generator().manual_seed(5)
+    out, E = torch.randn(M, d, generator=g).cuda(), (torch.randn(V, d, generator=g) * 0.3).cuda()
+    tgt = torch.randint(0, V, (M,), generator=g).cuda()
+    pen = (torch.rand(N, generator=g).double() * 1000 + 10).cuda()
+    part = A.ops.ce_partial(out, E, 3)
+    lse, tl, rl, loss = A.ops.ce_finalize(part, out, E, tgt, 2)
+    P = A.ops._p
+    la, dp = torch.empty(1, device='cuda'), torch.empty(N, device='cuda')
+    A.LIB.call('acsr_loss_combine', pen.data_ptr(), N, P(loss[1:]), None, 0.03, P(la), P(dp), A.ops._stream())
+    lse2, tl2, rl2, loss2 = (torch.empty_like(t) for t in (lse, tl, rl, loss))
+    la2, dp2 = torch.empty_like(la), torch.empty_like(dp)
+    cnt = torch.zeros(1, dtype=torch.int32, device='cuda')
+    A.LIB.call('acsr_ce_finalize_losses', P(part), part.shape[1], P(out), P(E), P(tgt, torch.int64), M, d, V, 0, 2, P(lse2), P(tl2),
+               P(rl2), P(loss2), pen.data_ptr(), N, None, 0.03, P(la2), P(dp2), cnt.data_ptr(), A.ops._stream())
+    assert int(cnt.item()) == 0                           # the last CTA resets the arrival counter
+    for a, b in ((lse, lse2), (tl, tl2), (rl, rl2), (loss, loss2), (la, la2), (dp, dp2)):
+        assert torch.equal(a, b)
+    ref = torch.nn.functional.cross_entropy((out.double() @ E.double().t())[:M // 2], tgt[:M // 2])
+    assert abs(float(loss2[0]) - float(ref)) < 1e-5 * abs(float(ref))
+
+
+def test_attention_edge_rows(A):
+    """edge inputs the reference handles: a batch of one, a sequence of one item, a full-length row, L = 1."""
+    for (B, L, H, dh) in ((1, 50, 2, 32), (3, 1, 2, 32), (2, 7, 1, 16)):
+        case = (H, dh, L, 'gate', True, 'none', True, True, 0.0)
+        cfg, seq, t, lp, rnd, g = _attn_inputs(*case)
+        seq, t = seq[:B].clone(), {k: (v[:B].clone() if v is not None else None) for k, v in t.items()}
+        rnd = {k: v[:B].clone() for k, v in rnd.items()}
+        seq[0] = torch.randint(1, 50, (L,), generator=g)
+        if B > 1:
+            seq[1] = 0
+            seq[1, 0] = 7                                   # a single item followed by padding
+        r = O.attn_calib(t['mq'], t['mk'], t['mv'], t['aq'], t['ak'], t['gate'], O.additive_mask(seq), lp, cfg, 0, O.Rand(rnd), anneal_rate=0.37)
+        (ctx_att, ctx_cal, pen, probs), _, _ = _run_cuda_attn(A, cfg, seq, t, lp, rnd, 0.0)
+        close(ctx_att, r['ctx_att'], 3e-5, 'ctx_att')
+        close(ctx_cal, r['ctx_cal'], 3e-5, 'ctx_cal')
+        close(pen, r['pen_sq'].view(1), 1e-5, 'pen_sq')
