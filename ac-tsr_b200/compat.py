@@ -105,6 +105,46 @@ class Interaction(object):
         for k in new_inter.interaction:
             self.interaction[k] = new_inter.interaction[k]
 
+    def pack(self, fields=None, out=None, pin=True):
+        """-> PackedInteraction: the int64 `fields` laid out back to back in ONE (pinned) buffer, each field a contiguous view of it,
+        so that a batch crosses PCIe / NVLink-C2C as a single copy instead of one per field."""
+        fields = list(fields) if fields is not None else [k for k, v in self.interaction.items() if v.dtype == torch.int64]
+        return PackedInteraction.from_fields({k: self.interaction[k] for k in fields}, out=out, pin=pin)
+
+
+class PackedInteraction(Interaction):
+    """Interaction whose fields are views of one flat int64 buffer (`packed`); `layout` = [(field, offset, shape)]."""
+
+    def __init__(self, packed, layout):
+        self.packed, self.layout = packed, list(layout)
+        super().__init__({k: packed[off:off + int(np.prod(shape))].view(shape) for k, off, shape in self.layout})
+
+    @staticmethod
+    def layout_of(fields):
+        lay, off = [], 0
+        for k, v in fields.items():
+            if v.dtype != torch.int64:
+                raise ValueError('packed batches hold int64 fields only (%s is %s)' % (k, v.dtype))
+            lay.append((k, off, tuple(v.shape)))
+            off += v.numel()
+        return lay, off
+
+    @classmethod
+    def from_fields(cls, fields, out=None, pin=True):
+        lay, total = cls.layout_of(fields)
+        if out is None:
+            out = torch.empty(total, dtype=torch.int64)
+            if pin and torch.cuda.is_available():
+                out = out.pin_memory()
+        for k, off, shape in lay:
+            out[off:off + fields[k].numel()].view(shape).copy_(fields[k])
+        return cls(out[:total], lay)
+
+    def to(self, device, selected_field=None):
+        if selected_field is not None:
+            return super().to(device, selected_field)
+        return PackedInteraction(self.packed.to(device, non_blocking=True), self.layout)
+
 
 # ---------------------------------------------------------------------------------------------
 _DEFAULTS = dict(

@@ -4,6 +4,7 @@ Only what AC-SASRec reads is carried: item_id_list int64[B,L], item_length int64
 (the reference moves 5 more unused fields per step)."""
 import math
 
+import numpy as np
 import torch
 
 from .compat import Interaction
@@ -47,6 +48,44 @@ class SyntheticSequentialDataset(object):
         return len(self.inter_feat)
 
 
+def _model_fields(config):
+    iid = config['ITEM_ID_FIELD']
+    return [iid + config['LIST_SUFFIX'], config['ITEM_LIST_LENGTH_FIELD'], iid]
+
+
+class _PackedBatches(object):
+    """The three int64 fields the model reads, re-laid out batch by batch in ONE pinned buffer (refilled in place after every
+    shuffle), so that each batch is a single contiguous host->device copy.  Full batches only; a ragged tail stays unpacked."""
+
+    def __init__(self, config, batch_size):
+        self.fields, self.bs, self.buf = _model_fields(config), batch_size, None
+
+    def fill(self, inter_feat):
+        n = len(inter_feat)
+        nb = n // self.bs
+        if nb == 0 or any(f not in inter_feat for f in self.fields):
+            self.nb = 0
+            return
+        per = [int(np.prod(inter_feat[f].shape[1:])) for f in self.fields]
+        P = self.bs * sum(per)
+        if self.buf is None or self.buf.shape != (nb, P):
+            self.buf = torch.empty((nb, P), dtype=torch.int64)
+            if torch.cuda.is_available():
+                self.buf = self.buf.pin_memory()
+        off = 0
+        self.layout = []
+        for f, w in zip(self.fields, per):
+            src = inter_feat[f][:nb * self.bs].reshape(nb, self.bs * w)
+            self.buf[:, off:off + self.bs * w].copy_(src)
+            self.layout.append((f, off, (self.bs,) + tuple(inter_feat[f].shape[1:])))
+            off += self.bs * w
+        self.nb = nb
+
+    def batch(self, i):
+        from .compat import PackedInteraction
+        return PackedInteraction(self.buf[i], self.layout)
+
+
 class TrainDataLoader(object):
     """general_dataloader.py:23-65: per-epoch CPU randperm shuffle, then contiguous batch slices."""
 
@@ -54,6 +93,8 @@ class TrainDataLoader(object):
         self.config, self.dataset, self.shuffle = config, dataset, shuffle
         self.batch_size = batch_size or config['train_batch_size']
         self.pr = 0
+        self._packed = _PackedBatches(config, self.batch_size) if config.get('packed_batches', True) else None
+        self._filled = False
 
     @property
     def pr_end(self):
@@ -65,15 +106,23 @@ class TrainDataLoader(object):
     def __iter__(self):
         if self.shuffle:
             self.dataset.inter_feat.shuffle()
-            if torch.cuda.is_available():
-                self.dataset.inter_feat = Interaction({k: v.pin_memory() for k, v in self.dataset.inter_feat.interaction.items()})
+            self._filled = False
+        if self._packed is not None and not self._filled:
+            self._packed.fill(self.dataset.inter_feat)
+            self._filled = True
+        elif self.shuffle and torch.cuda.is_available():
+            self.dataset.inter_feat = Interaction({k: v.pin_memory() for k, v in self.dataset.inter_feat.interaction.items()})
         return self
 
     def __next__(self):
         if self.pr >= self.pr_end:
             self.pr = 0
             raise StopIteration()
-        cur = self.dataset.inter_feat[self.pr:self.pr + self.batch_size]
+        i = self.pr // self.batch_size
+        if self._packed is not None and self._filled and i < self._packed.nb:
+            cur = self._packed.batch(i)
+        else:
+            cur = self.dataset.inter_feat[self.pr:self.pr + self.batch_size]
         self.pr += self.batch_size
         return cur
 
@@ -86,6 +135,9 @@ class FullSortEvalDataLoader(object):
         self.batch_size = batch_size or config['eval_batch_size']
         self.iid_field = config['ITEM_ID_FIELD']
         self.pr = 0
+        self._packed = _PackedBatches(config, self.batch_size) if config.get('packed_batches', True) else None
+        if self._packed is not None:
+            self._packed.fill(dataset.inter_feat)
 
     @property
     def pr_end(self):
@@ -101,7 +153,11 @@ class FullSortEvalDataLoader(object):
         if self.pr >= self.pr_end:
             self.pr = 0
             raise StopIteration()
-        interaction = self.dataset.inter_feat[self.pr:self.pr + self.batch_size]
+        i = self.pr // self.batch_size
+        if self._packed is not None and i < self._packed.nb:
+            interaction = self._packed.batch(i)
+        else:
+            interaction = self.dataset.inter_feat[self.pr:self.pr + self.batch_size]
         n = len(interaction)
         self.pr += self.batch_size
         return interaction, None, torch.arange(n), interaction[self.iid_field]

@@ -114,8 +114,10 @@ class FusedTrainStep(object):
         def f(*s):
             return torch.empty(s, dtype=torch.float32, device=dev)
         nc = ops.logits_num_chunks(2 * B, V)
+        loss3 = f(3)              # [CE(calibrated), CE(attacked), final attacked loss]: one buffer, one read-back
         j = dict(pen=torch.zeros(N, dtype=torch.float64, device=dev), out2=f(2 * B, d), partial=f(2 * B, nc, 2), lse=f(2 * B),
-                 tgt=f(2 * B), row_loss=f(2 * B), loss=f(2), loss_att=f(1), dpen=f(N), Gt=f(V, 2 * B), d_out2=f(2 * B, d),
+                 tgt=f(2 * B), row_loss=f(2 * B), loss3=loss3, loss=loss3[:2], loss_att=loss3[2:], dpen=f(N), Gt=f(V, 2 * B),
+                 d_out2=f(2 * B, d),
                  target2=torch.empty(2 * B, dtype=torch.int64, device=dev), ce_cnt=torch.zeros(1, dtype=torch.int32, device=dev),
                  row_scale=torch.cat((torch.full((B,), 1.0 / B), torch.full((B,), -1.0 / B))).to(dev))
         self.buf[key] = j
@@ -211,6 +213,7 @@ class FusedTrainStep(object):
             LIB.call('acsr_loss_combine', jb['pen'].data_ptr(), N, _p(jb['loss'][1:]), _p(wp), wv, _p(jb['loss_att']), _p(jb['dpen']), st)
         loss_cal = jb['loss'][0]
         loss_att = jb['loss_att'][0]
+        self.last_losses = jb['loss3']
         if not training or getattr(self, '_stop_after', None) == 'ce':
             if zero_done is not None:
                 main.wait_event(zero_done)

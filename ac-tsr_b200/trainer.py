@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .compat import Interaction, cfg_get
+from .compat import Interaction, PackedInteraction, cfg_get
 from .evaluator import Evaluator
 
 ATTACK_KEYS = ('attack_key_transform', 'attack_query_transform')      # trainer.py:673
@@ -238,10 +238,12 @@ class ACSASRecTrainer(object):
 
     def _capture(self, interaction):
         dev = self.device
-        static = {k: torch.empty_like(interaction[k], device=dev) for k in self._fields()}
+        # static input buffers: one flat buffer with the fields as views, so a packed host batch arrives as ONE copy
+        lay, total = PackedInteraction.layout_of({k: interaction[k] for k in self._fields()})
+        static_inter = PackedInteraction(torch.empty(total, dtype=torch.int64, device=dev), lay)
+        static = {k: static_inter[k] for k in self._fields()}
         for k in static:
             static[k].copy_(interaction[k])
-        static_inter = Interaction(static)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm-up on a side stream (allocator + lazy inits), state restored after
@@ -257,7 +259,7 @@ class ACSASRecTrainer(object):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             la, lc = self._step_body(static_inter)
-        self._graph = dict(graph=g, static=static, key=self._graph_key(interaction), la=la, lc=lc)
+        self._graph = dict(graph=g, static=static, static_inter=static_inter, key=self._graph_key(interaction), la=la, lc=lc)
 
     def graphed_step(self, interaction):
         """interaction: host (pinned) or device tensors of the captured shape.  Copies the batch into the
@@ -266,9 +268,13 @@ class ACSASRecTrainer(object):
             if self._graph is not None:
                 return self._step_body(interaction.to(self.device))      # ragged last batch: eager launch
             self._capture(interaction)
-        st = self._graph['static']
-        for k in st:
-            st[k].copy_(interaction[k], non_blocking=True)
+        si = self._graph['static_inter']
+        if getattr(interaction, 'layout', None) == si.layout:
+            si.packed.copy_(interaction.packed, non_blocking=True)          # packed batch: one copy
+        else:
+            st = self._graph['static']
+            for k in st:
+                st[k].copy_(interaction[k], non_blocking=True)
         self._graph['graph'].replay()
         return self._graph['la'], self._graph['lc']
 
@@ -383,24 +389,31 @@ class ACSASRecTrainer(object):
             scores[history_index] = -np.inf
         return interaction, scores, positive_u, positive_i
 
-    def eval_batch(self, batched_data):
-        """-> rec_topk [B, kmax+1] int32 on the device (collector.py:145-153 'rec.topk')."""
+    def eval_batch(self, batched_data, rec_out=None):
+        """-> rec_topk [B, kmax+1] int32 on the device (collector.py:145-153 'rec.topk'); with rec_out (a pinned host tensor)
+        the graphed path copies the result straight into it (no device-side clone) and returns rec_out."""
         interaction, history_index, positive_u, positive_i = batched_data
         kmax = max(self.topk)
         if self.fused_topk and history_index is None:
             if self.use_graph and not self.model.training:
-                return self._graphed_eval(interaction, positive_i, kmax)
+                return self._graphed_eval(interaction, positive_i, kmax, rec_out)
             inter = interaction.to(self.device)
-            _, _, rec = self.model.full_sort_topk(inter, kmax, positive_i.to(self.device, non_blocking=True))
-            return rec
-        interaction, scores, positive_u, positive_i = self._full_sort_batch_eval(batched_data)
-        _, topk_idx = torch.topk(scores, kmax, dim=-1)
-        pos = positive_i.to(self.device)
-        flags = (topk_idx == pos.view(-1, 1)).to(torch.int32)
-        return torch.cat((flags, torch.ones_like(flags[:, :1])), dim=1)
+            pos = inter[self.model.POS_ITEM_ID] if positive_i is interaction.interaction.get(self.model.POS_ITEM_ID) else \
+                positive_i.to(self.device, non_blocking=True)
+            _, _, rec = self.model.full_sort_topk(inter, kmax, pos)
+        else:
+            interaction, scores, positive_u, positive_i = self._full_sort_batch_eval(batched_data)
+            _, topk_idx = torch.topk(scores, kmax, dim=-1)
+            pos = positive_i.to(self.device)
+            flags = (topk_idx == pos.view(-1, 1)).to(torch.int32)
+            rec = torch.cat((flags, torch.ones_like(flags[:, :1])), dim=1)
+        if rec_out is not None:
+            rec_out.copy_(rec, non_blocking=True)
+            return rec_out
+        return rec
 
     @torch.no_grad()
-    def _graphed_eval(self, interaction, positive_i, kmax):
+    def _graphed_eval(self, interaction, positive_i, kmax, rec_out=None):
         """forward + fused logits/top-k + hit flags of one eval batch as a CUDA-graph replay (one graph per batch shape).
         The batch (host or device) is copied into static buffers; the returned rec tensor is a fresh copy."""
         m = self.model
@@ -409,12 +422,14 @@ class ACSASRecTrainer(object):
         g = self._eval_graphs.get(key)
         if g is None:
             dev = self.device
-            static = {k: torch.empty_like(interaction[k], device=dev) for k in fields}
+            # static inputs (sequence, length, held-out item) as views of one flat buffer: a packed batch is ONE copy
+            lay, total = PackedInteraction.layout_of({**{k: interaction[k] for k in fields}, m.POS_ITEM_ID: positive_i})
+            inter = PackedInteraction(torch.empty(total, dtype=torch.int64, device=dev), lay)
+            static = {k: inter[k] for k in fields}
             for k in fields:
                 static[k].copy_(interaction[k])
-            pos = torch.empty_like(positive_i, device=dev)
+            pos = inter[m.POS_ITEM_ID]
             pos.copy_(positive_i)
-            inter = Interaction(static)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -424,12 +439,18 @@ class ACSASRecTrainer(object):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 _, _, rec = m.full_sort_topk(inter, kmax, pos)
-            g = dict(graph=graph, static=static, pos=pos, rec=rec)
+            g = dict(graph=graph, static=static, pos=pos, rec=rec, inter=inter)
             self._eval_graphs[key] = g
-        for k in fields:
-            g['static'][k].copy_(interaction[k], non_blocking=True)
-        g['pos'].copy_(positive_i, non_blocking=True)
+        if getattr(interaction, 'layout', None) == g['inter'].layout and positive_i is interaction.interaction.get(m.POS_ITEM_ID):
+            g['inter'].packed.copy_(interaction.packed, non_blocking=True)
+        else:
+            for k in fields:
+                g['static'][k].copy_(interaction[k], non_blocking=True)
+            g['pos'].copy_(positive_i, non_blocking=True)
         g['graph'].replay()
+        if rec_out is not None:
+            rec_out.copy_(g['rec'], non_blocking=True)
+            return rec_out
         return g['rec'].clone()
 
     @torch.no_grad()

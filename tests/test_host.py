@@ -166,3 +166,35 @@ def test_early_stopping_rule():
     assert es(0.3, 0.4, 0, 10, bigger=False) == (0.3, 0, False, True)
     assert A.trainer.is_attack_param('trm_encoder.layer.0.attack_attention.attack_key_transform.weight')
     assert not A.trainer.is_attack_param('trm_encoder.layer.0.attack_attention.key.weight')
+
+
+def test_packed_batches_equal_sliced_batches():
+    """loaders hand out the model's three fields as views of one buffer (a single host->device copy per batch); same values
+    as slicing the dataset, ragged tail unpacked, layout stable across shuffles."""
+    import ac_tsr_b200 as A
+    cfg = A.Config(model='ACSASRec', config_dict=dict(train_batch_size=64, eval_batch_size=64, device=torch.device('cpu')))
+    ds = A.data.SyntheticSequentialDataset(cfg, 200, 301, seed=3, pin=False)
+    ev = A.data.FullSortEvalDataLoader(cfg, ds)
+    batches = list(ev)
+    assert len(batches) == 4
+    for i, (inter, hist, pu, pi) in enumerate(batches):
+        ref = ds.inter_feat[i * 64:(i + 1) * 64]
+        for k in ('item_id_list', 'item_length', 'item_id'):
+            assert torch.equal(inter[k], ref[k]) and inter[k].is_contiguous()
+        assert pi is inter.interaction['item_id'] and hist is None
+        if i < 3:
+            assert isinstance(inter, A.compat.PackedInteraction) and inter.packed.numel() == 64 * 52
+            assert [f for f, _, _ in inter.layout] == ['item_id_list', 'item_length', 'item_id']
+            moved = inter.to(torch.device('cpu'))
+            assert moved.layout == inter.layout and torch.equal(moved['item_id_list'], inter['item_id_list'])
+        else:
+            assert not isinstance(inter, A.compat.PackedInteraction) and len(inter) == 8
+    tr = A.data.TrainDataLoader(cfg, ds, shuffle=True)
+    torch.manual_seed(0)
+    seen = torch.cat([b['item_id'] for b in tr])
+    assert sorted(seen.tolist()) == sorted(ds.inter_feat['item_id'].tolist()) and len(seen) == 200
+    first = next(iter(tr))
+    assert torch.equal(first['item_id_list'], ds.inter_feat['item_id_list'][:64])      # packed view of the reshuffled rows
+    tr.pr = 0
+    with pytest.raises(ValueError):
+        A.Interaction({'x': torch.zeros(3)}).pack(['x'])
