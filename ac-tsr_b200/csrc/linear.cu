@@ -123,9 +123,67 @@ linear_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, i
   }
 }
 
+// ---- projection weights of one AC layer folded for ONE batched forward GEMM -------------------------------------------------
+// layers.py:658-659, 687-689: mixed_q/k/v = x.Wq/k/v^T + b ; attack_q = mixed_q.Waq^T + baq ; attack_k = mixed_k.Wak^T + bak.
+// attack_q = x.(Waq.Wq)^T + (Waq.bq + baq), so with the folded weights all five projections read the same x and run as one
+// batched launch.  Slots 0-2 of out_W [5,d,d] / out_b [5,d] are copies of Wq, Wk, Wv; slots 3, 4 the folded attack pair.
+// One CTA per slot; parameters only (read before the dependency wait), a few microseconds next to the embedding kernel.
+constexpr int kFoldRows = 8;       // output rows per CTA
+__global__ void __launch_bounds__(256) fold_attack_weights_kernel(const float* __restrict__ Wqkv, const float* __restrict__ bqkv,
+                                                                  const float* __restrict__ Waqk, const float* __restrict__ baqk, int d,
+                                                                  float* __restrict__ out_W, float* __restrict__ out_b) {
+  extern __shared__ float fsm[];                    // B [d][d], A rows [kFoldRows][d], b1 [d]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int slot = blockIdx.y, r0 = blockIdx.x * kFoldRows;
+  const int nr = min(kFoldRows, d - r0);
+  float* oW = out_W + (long long)slot * d * d + (long long)r0 * d;
+  float* ob = out_b + (long long)slot * d + r0;
+  if (slot < 3) {
+    for (int e = threadIdx.x; e < nr * d; e += blockDim.x) oW[e] = Wqkv[(long long)slot * d * d + (long long)r0 * d + e];
+    for (int e = threadIdx.x; e < nr; e += blockDim.x) ob[e] = bqkv[slot * d + r0 + e];
+    return;
+  }
+  float* sB = fsm;
+  float* sA = sB + d * d;
+  float* sb1 = sA + kFoldRows * d;
+  const float* A = Waqk + (long long)(slot - 3) * d * d + (long long)r0 * d;     // rows r0.. of the second projection
+  const float* Bm = Wqkv + (long long)(slot - 3) * d * d;                        // first projection (Wq for slot 3, Wk for slot 4)
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) sB[e] = Bm[e];
+  for (int e = threadIdx.x; e < nr * d; e += blockDim.x) sA[e] = A[e];
+  for (int e = threadIdx.x; e < d; e += blockDim.x) sb1[e] = bqkv[(slot - 3) * d + e];
+  __syncthreads();
+  for (int e = threadIdx.x; e < nr * d; e += blockDim.x) {
+    const int r = e / d, c = e - r * d;             // out[r][c] = sum_k A[r][k] * B[k][c]: lanes walk c (conflict-free), A broadcast
+    float s = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < d; ++k) s = fmaf(sA[r * d + k], sB[k * d + c], s);
+    oW[e] = s;
+  }
+  for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+    float s = baqk[(slot - 3) * d + r0 + r];
+    for (int k = 0; k < d; ++k) s = fmaf(sA[r * d + k], sb1[k], s);
+    ob[r] = s;
+  }
+}
+
 }  // namespace acsr
 
 using namespace acsr;
+
+extern "C" int acsr_fold_attack_weights(const float* Wqkv, const float* bqkv, const float* Waqk, const float* baqk, int d, float* out_W,
+                                        float* out_b, void* stream) {
+  ACSR_REQUIRE(Wqkv && bqkv && Waqk && baqk && out_W && out_b && d > 0 && d <= 1024, "fold_attack_weights: bad arguments");
+  ACSR_REQUIRE(d <= 128, "fold_attack_weights: hidden size %d > 128", d);
+  const size_t smem = (size_t)(d * d + kFoldRows * d + d) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fold_attack_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("fold_attack_weights: smem attr: %s", cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
+  }
+  launch_pdl(fold_attack_weights_kernel, dim3((d + kFoldRows - 1) / kFoldRows, 5), dim3(256), smem, (cudaStream_t)stream, Wqkv, bqkv, Waqk,
+             baqk, d, out_W, out_b);
+  return check_launch("fold_attack_weights");
+}
 
 static int launch_wgrad(const float* dY, const float* X, int T, int N, int K, float* dW, float* db, int batch, long long sY,
                         long long sX, long long sW, long long sB, cudaStream_t stream, const char* who) {

@@ -56,6 +56,7 @@ class FusedTrainStep(object):
         self.compact_last = bool(getattr(model, 'compact_last', True))   # last layer's dense part on the len-1 rows only
         import os
         self.order_side = os.environ.get('ACSR_ORDER_SIDE', '1') == '1'     # sequence ordering next to, not in front of, the embedding
+        self.fold_attack = os.environ.get('ACSR_FOLD_ATTACK', '1') == '1'   # attack transforms folded into the Q/K/V launch (forward)
         self.pdl = bool(getattr(model, 'pdl', True))            # programmatic dependent launch between the step's kernels
 
     # ------------------------------------------------------------------------------------------
@@ -78,9 +79,10 @@ class FusedTrainStep(object):
         b = dict(T=T, x0=f(T, d), st_e=f(T, 2), layers=[], order=torch.empty(Bs, dtype=torch.int32, device=dev))
         for l in range(N):
             R = 2 * T if l == N - 1 else T
-            qkv, aqk = f(3, T, d), f(2, T, d)
+            qkv5 = f(5, T, d)                  # mixed_q, mixed_k, mixed_v, attack_q, attack_k: one batched GEMM writes all five
+            qkv, aqk = qkv5[:3], qkv5[3:]
             Rp = 1 if (l == N - 1 and self.compact_last) else R      # the compact last layer keeps its dense part in b['c']
-            lb = dict(qkv=qkv, aqk=aqk, mq=qkv[0], mk=qkv[1], mv=qkv[2], aq=aqk[0], ak=aqk[1], gl=f(T, L), ctx=f(R, d),
+            lb = dict(qkv5=qkv5, qkv=qkv, aqk=aqk, mq=qkv[0], mk=qkv[1], mv=qkv[2], aq=aqk[0], ak=aqk[1], gl=f(T, L), ctx=f(R, d),
                       hz=f(Rp, d), st_a=f(Rp, 2), h=f(Rp, d), z1=f(Rp, I), a1=f(Rp, I), z2=f(Rp, d), st_f=f(Rp, 2), out=f(Rp, d))
             # buffers read by the weight-gradient kernels are per layer: the side stream may still be reading layer l's
             # while the branch stream already writes layer l-1's
@@ -285,6 +287,18 @@ class FusedTrainStep(object):
         so = self._stream_for(seq.device, ('order', s)) if self.order_side else cur
         if so is not cur:
             so.wait_stream(cur)
+        folded = {}
+        if self.tc and self.fold_attack:                  # first on the side stream: the first projection launch needs layer 0's
+            for l in range(N):
+                st3 = self._stacked(l)
+                if st3 is None:
+                    continue
+                fw = self._folded_buffers(l, seq.device)
+                LIB.call('acsr_fold_attack_weights', _p(st3['Wqkv']), _p(st3['bqkv']), _p(st3['Waqk']), _p(st3['baqk']), d,
+                         _p(fw['W']), _p(fw['b']), so.cuda_stream)
+                fw['done'] = torch.cuda.Event()
+                fw['done'].record(so)
+                folded[l] = fw
         LIB.call('acsr_seq_order', _p(seq, torch.int64), Bs, L, _p(b['order'], torch.int32), so.cuda_stream)
         order_done = torch.cuda.Event()
         order_done.record(so)
@@ -301,7 +315,14 @@ class FusedTrainStep(object):
             base = soff + 16 * (l + 1)
             b['xs'].append(x)
             st3 = self._stacked(l)
-            if st3 is not None and self.tc:                   # stacked Q/K/V and attack pair: two batched tcgen05 launches
+            if l in folded and so is not cur:
+                cur.wait_event(folded[l]['done'])  # this layer's folded weights (side stream) are ready
+            if st3 is not None and self.tc and self.fold_attack:
+                # all five projections read x: one batched tcgen05 launch over the folded weights (prepared at the start of the
+                # step on the ordering stream, next to the embedding kernel)
+                fw = folded[l]
+                ops.linear_tok(x, T, d, fw['W'], d, lb['qkv5'], d, bias=fw['b'], batch=5, sx=0, sw=d * d, sb=d, sy=T * d)
+            elif st3 is not None and self.tc:                 # stacked Q/K/V and attack pair: two batched tcgen05 launches
                 ops.linear_tok(x, T, d, st3['Wqkv'], d, lb['qkv'], d, bias=st3['bqkv'], batch=3, sx=0, sw=d * d, sb=d, sy=T * d)
                 ops.linear_tok(lb['qkv'], T, d, st3['Waqk'], d, lb['aqk'], d, bias=st3['baqk'], batch=2, sx=T * d, sw=d * d,
                                sb=d, sy=T * d)
@@ -330,8 +351,8 @@ class FusedTrainStep(object):
             p_attn = aa.attn_dropout.p if training else 0.0
             lb['attn_args'] = self._attn_args(layer, lb, seq, Bs, L, H, dh, comb_scalar, p_attn, rand, l, rngp, base)
             ctx_cal, ctx_att = lb['ctx'][:T], (lb['ctx'][T:] if last else None)
-            if l == 0:
-                cur.wait_event(order_done)
+            if l == 0 and so is not cur:
+                cur.wait_event(order_done)         # sequence order (side stream) is ready
             LIB.call('acsr_attn_calib_fwd', *lb['attn_args'], _p(ctx_att), _p(ctx_cal),
                      jb['pen'][l:].data_ptr() if need_att else None, None, _p(b['order'], torch.int32),
                      _p(ln, torch.int64) if (l == N - 1 and self.compact_last) else None, st)
@@ -594,6 +615,13 @@ class FusedTrainStep(object):
             dW.addmm_(dY[:rows].t(), X[:rows])
             if db is not None:
                 db.add_(dY[:rows].sum(0))
+
+    def _folded_buffers(self, l, dev):
+        key = ('folded', l)
+        if key not in self.buf:
+            d = self.m.hidden_size
+            self.buf[key] = dict(W=torch.empty((5, d, d), dtype=torch.float32, device=dev), b=torch.empty((5, 1, d), dtype=torch.float32, device=dev))
+        return self.buf[key]
 
     def _stacked(self, l):
         """stacked views [3,d,d]/[2,d,d] of the Q/K/V and attack-pair parameters (adjacent in FlatAdam's layout)."""

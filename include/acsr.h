@@ -236,6 +236,12 @@ int acsr_topk_select_max_items(void);
 int acsr_topk_select(const float* scores, int M, int64_t V, int64_t ld, int k, int skip_col0, int64_t idx_offset,
                      const int64_t* positive, float* topk_val, int64_t* topk_idx, int32_t* rec_topk, void* stream);
 
+/* Fold the attack transforms into the first projections (layers.py:658-659, 687-689) so that the five projections of a layer
+ * read the same input and run as ONE batched GEMM: out_W [5,d,d] / out_b [5,d] = {Wq, Wk, Wv, Waq.Wq, Wak.Wk} and
+ * {bq, bk, bv, Waq.bq + baq, Wak.bk + bak}.  Wqkv [3,d,d], bqkv [3,d], Waqk [2,d,d], baqk [2,d] (row-major [out,in]). */
+int acsr_fold_attack_weights(const float* Wqkv, const float* bqkv, const float* Waqk, const float* baqk, int d, float* out_W,
+                             float* out_b, void* stream);
+
 /* ---- encoder GEMMs on tcgen05 with the token rows on the UMMA M axis (3xTF32, fp32-level accuracy) ----
  * replaces the nn.Linear forward / input-gradient GEMMs of model/layers.py:658-659, 680, 687-689, 791-794, 887.
  * Y[r, n] (+)= sum_k X(r,k) * W(n,k) + bias[n], r < rows, n < N, k < K <= 256, with strided operands so that

@@ -788,3 +788,22 @@ def test_attention_edge_rows(A):
         close(ctx_att, r['ctx_att'], 3e-5, 'ctx_att')
         close(ctx_cal, r['ctx_cal'], 3e-5, 'ctx_cal')
         close(pen, r['pen_sq'].view(1), 1e-5, 'pen_sq')
+
+
+def test_fold_attack_weights(A):
+    """{Wq, Wk, Wv, Waq.Wq, Wak.Wk} and the matching biases: attack_q = x.(Waq.Wq)^T + (Waq.bq + baq)."""
+    d = 64
+    g = torch.Generator().manual_seed(9)
+    Wqkv, bqkv = torch.randn(3, d, d, generator=g) * 0.1, torch.randn(3, d, generator=g) * 0.1
+    Waqk, baqk = torch.randn(2, d, d, generator=g) * 0.1, torch.randn(2, d, generator=g) * 0.1
+    oW, ob = torch.empty(5, d, d, device='cuda'), torch.empty(5, d, device='cuda')
+    P = A.ops._p
+    dev = [t.cuda() for t in (Wqkv, bqkv, Waqk, baqk)]                  # keep the device copies alive across the launch
+    A.LIB.call('acsr_fold_attack_weights', P(dev[0]), P(dev[1]), P(dev[2]), P(dev[3]), d, P(oW), P(ob), A.ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(oW[:3].cpu(), Wqkv) and torch.equal(ob[:3].cpu(), bqkv)
+    x = torch.randn(7, d, generator=g).double()
+    for i in range(2):
+        ref = (x @ Wqkv[i].double().t() + bqkv[i].double()) @ Waqk[i].double().t() + baqk[i].double()
+        got = x @ oW[3 + i].cpu().double().t() + ob[3 + i].cpu().double()
+        close(got, ref, 2e-5, 'folded attack projection %d' % i)
