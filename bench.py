@@ -168,7 +168,7 @@ def build(dev, rank, world, cuda_graph=True):
     return A, cfg, config, model, trainer
 
 
-TRAFFIC_PROFILE = os.path.join(ROOT, 'profiles', 'r01_traffic_v6.json')     # ncu dram__bytes_{read,write}.sum per launch
+TRAFFIC_PROFILE = os.path.join(ROOT, 'profiles', 'r01_traffic_v8.json')     # ncu dram__bytes_{read,write}.sum per launch
 NCU_NAMES = {'acsr_linear_tok': 'void acsr::linear_tok_kernel<0>', 'acsr_linear_tok_bdrl': 'void acsr::linear_tok_kernel<2>',
              'acsr_attn_calib_bwd2': 'void acsr::attn_bwd_kernel<32, 2>', 'acsr_attn_calib_fwd': 'void acsr::attn_fwd_kernel<32>',
              'acsr_linear_wgrad': 'void acsr::linear_wgrad_kernel<2>'}
@@ -340,7 +340,7 @@ def run_ours(args):
     calls = max(1.0, topk_['calls_per_step'])
     roof = {'kernel': top, 'bound': 'hbm', 'achieved': topk_['gbs'], 'peak': peak, 'unit': 'GB/s',
             'frac': (round(topk_['gbs'] / peak, 4) if topk_['gbs'] else None), 'traffic': measured_traffic(top) if args.workload == 'c2' else None,
-            'traffic_source': 'profiles/r01_traffic_v6.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, same workload)',
+            'traffic_source': 'profiles/r01_traffic_v8.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, same workload)',
             'peak_source': peak_src,
             'avg_launch_us': round(topk_['ms_per_step'] / calls * 1e3, 2),
             'algo_bytes_per_launch': (int(topk_['algo_bytes_per_step'] / calls) if topk_['algo_bytes_per_step'] else None),
