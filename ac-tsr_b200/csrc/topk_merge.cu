@@ -11,6 +11,7 @@ namespace acsr {
 constexpr int kMergeThreads = 256;
 constexpr int kMergeMaxCand = 56 * 1024;      // 32-bit keys of one row in shared memory (224 KB)
 constexpr int kMergeMaxK = 64;
+constexpr int kFastCap = 512;        // candidates the fast path sorts (P/2 <= 256 threads)
 
 __device__ __forceinline__ unsigned f2key(float v) {        // larger float <-> larger unsigned
   const unsigned u = __float_as_uint(v);
@@ -42,6 +43,63 @@ topk_merge_kernel(const float* __restrict__ pval, const long long* __restrict__ 
   }
   if (tid == 0) { s_prefix = 0u; s_need = k; s_cnt = 0; }
   if (tid < kMergeMaxK) sel[tid] = 0ull;
+  // ---- fast path: a lower bound T0 of the k-th largest key from the threads' local maxima (at least k keys are >= the k-th
+  // largest of the 256 local maxima), then only the handful of keys >= T0 are gathered and sorted.  Exact, ties included
+  // (every key equal to the k-th largest is >= T0); rows with more than kFastCap such keys (heavy ties) take the radix select.
+  __shared__ unsigned lmax[kMergeThreads];
+  __shared__ unsigned long long cand[kFastCap];
+  __shared__ int s_ncand;
+  bool fast_done = false;
+  {
+    unsigned m = 0u;
+    for (int i = tid; i < n_cand; i += kMergeThreads) m = max(m, keys[i]);     // own writes: no barrier needed yet
+    lmax[tid] = m;
+    if (tid == 0) s_ncand = 0;
+    __syncthreads();
+    for (int size = 2; size <= kMergeThreads; size <<= 1) {                    // bitonic sort of the 256 maxima, descending
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        if (tid < kMergeThreads / 2) {
+          const int l = 2 * tid - (tid & (stride - 1)), h = l + stride;
+          const bool desc = (l & size) == 0;
+          const unsigned a = lmax[l], b = lmax[h];
+          if ((a > b) != desc) { lmax[l] = b; lmax[h] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    const unsigned T0 = lmax[k - 1];
+    if (T0 != 0u) {
+      for (int i = tid; i < n_cand; i += kMergeThreads) {
+        const unsigned key = keys[i];
+        if (key >= T0) {
+          const int pos = atomicAdd(&s_ncand, 1);
+          if (pos < kFastCap) cand[pos] = ((unsigned long long)key << 32) | (unsigned)(~(unsigned)i);
+        }
+      }
+    }
+    __syncthreads();
+    const int nc = T0 != 0u ? s_ncand : kFastCap + 1;
+    if (nc <= kFastCap) {                                                       // uniform over the CTA
+      int P = 64;
+      while (P < nc) P <<= 1;
+      for (int i = nc + tid; i < P; i += kMergeThreads) cand[i] = 0ull;
+      __syncthreads();
+      for (int size = 2; size <= P; size <<= 1) {                               // sort the candidates: (score desc, slot asc)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          if (tid < P / 2) {
+            const int l = 2 * tid - (tid & (stride - 1)), h = l + stride;
+            const bool desc = (l & size) == 0;
+            const unsigned long long a = cand[l], b = cand[h];
+            if ((a > b) != desc) { cand[l] = b; cand[h] = a; }
+          }
+          __syncthreads();
+        }
+      }
+      if (tid < k) sel[tid] = cand[tid];
+      fast_done = true;
+    }
+  }
+  if (!fast_done) {
   unsigned mask = 0u;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
@@ -137,6 +195,7 @@ topk_merge_kernel(const float* __restrict__ pval, const long long* __restrict__ 
       }
     }
   }
+  }   // radix-select path
   __syncthreads();
   const long long pos_item = positive ? positive[row] : -1;
   for (int j = tid; j < k; j += kMergeThreads) {
