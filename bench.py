@@ -30,6 +30,7 @@ WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on (default; the driver's bench line)
     'c2': dict(name='C2 synthetic Amazon-Beauty shape', users=22363, V=12102, L=50, d=64, n_layers=2, n_heads=2, inner=256, B=256, topk=50),
     # the other configs are parity-test cases (tests/); `--workload` times them with the same harness for DESIGN.md's table
+    'c1': dict(name='C1 ml-100k shape', users=943, V=1683, L=50, d=64, n_layers=2, n_heads=2, inner=256, B=256, topk=50),
     'c3': dict(name='C3 synthetic Yelp shape', users=30431, V=20034, L=50, d=64, n_layers=2, n_heads=2, inner=256, B=256, topk=50),
     'c3v': dict(name='C3 synthetic Yelp shape, repo variant (config/yelp.yaml)', users=30431, V=20034, L=50, d=128, n_layers=3, n_heads=8,
                 inner=64, B=256, topk=50),
