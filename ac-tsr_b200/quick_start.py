@@ -56,3 +56,34 @@ def run_recbole(model=None, dataset=None, config_file_list=None, config_dict=Non
     logger.info('test result: %s' % test_result)
     return {'best_valid_score': best_valid_score, 'valid_score_bigger': config['valid_metric_bigger'],
             'best_valid_result': best_valid_result, 'test_result': test_result}
+
+
+def objective_function(config_dict=None, config_file_list=None, saved=True):
+    """quick_start.py:80-107: the hyper-tuning objective (same training run, quiet logging)."""
+    config = Config(config_dict=config_dict, config_file_list=config_file_list)
+    init_seed(config['seed'], config['reproducibility'])
+    logging.basicConfig(level=logging.ERROR)
+    ds = create_dataset(config)
+    train_data, valid_data, test_data = data_preparation(config, ds)
+    init_seed(config['seed'], config['reproducibility'])
+    net = get_model(config['model'])(config, train_data.dataset).to(config['device'])
+    trainer = get_trainer(config['MODEL_TYPE'], config['model'])(config, net)
+    best_valid_score, best_valid_result = trainer.fit(train_data, valid_data, verbose=False, saved=saved)
+    test_result = trainer.evaluate(test_data, load_best_model=saved)
+    return {'best_valid_score': best_valid_score, 'valid_score_bigger': config['valid_metric_bigger'],
+            'best_valid_result': best_valid_result, 'test_result': test_result}
+
+
+def load_data_and_model(model_file):
+    """quick_start.py:110-146: rebuild config, dataset, loaders and the trained model from a checkpoint written by the trainer
+    (the checkpoint pickles the Config, hence weights_only=False -- SURVEY §8c)."""
+    checkpoint = torch.load(model_file, map_location='cpu', weights_only=False)
+    config = checkpoint['config']
+    init_seed(config['seed'], config['reproducibility'])
+    ds = create_dataset(config)
+    train_data, valid_data, test_data = data_preparation(config, ds)
+    init_seed(config['seed'], config['reproducibility'])
+    net = get_model(config['model'])(config, train_data.dataset).to(config['device'])
+    net.load_state_dict(checkpoint['state_dict'])
+    net.load_other_parameter(checkpoint.get('other_parameter'))
+    return config, net, ds, train_data, valid_data, test_data
