@@ -34,6 +34,10 @@ def main():
         'kcore_dedup': dict(rm_dup_inter='first', user_inter_num_interval='[30,inf)', item_inter_num_interval='[20,inf)',
                             val_interval={'rating': '[3,inf)'}, MAX_ITEM_LIST_LENGTH=20),
     }
+    cases['window5_valid_only'] = dict(MAX_ITEM_LIST_LENGTH=5, eval_args={'split': {'LS': 'valid_only'}, 'group_by': 'user', 'order': 'TO',
+                                                                            'mode': 'full'})
+    cases['dedup_last_test_only'] = dict(rm_dup_inter='last', item_inter_num_interval='[50,300]', MAX_ITEM_LIST_LENGTH=10,
+                                         eval_args={'split': {'LS': 'test_only'}, 'group_by': 'user', 'order': 'TO', 'mode': 'full'})
     for name, extra in cases.items():
         cd = dict(data_path=tmp + '/', load_col={'inter': ['user_id', 'item_id', 'rating', 'timestamp']},
                   eval_args={'split': {'LS': 'valid_and_test'}, 'group_by': 'user', 'order': 'TO', 'mode': 'full'},
