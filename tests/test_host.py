@@ -198,3 +198,16 @@ def test_packed_batches_equal_sliced_batches():
     tr.pr = 0
     with pytest.raises(ValueError):
         A.Interaction({'x': torch.zeros(3)}).pack(['x'])
+
+
+def test_evaluator_matches_reference_evaluator_outputs():
+    """metric@k values of the UNMODIFIED reference Evaluator on seeded rec.topk matrices (tests/golden/make_metrics_golden.py):
+    Hit / MRR / NDCG / Recall / Precision / MAP, one or several positives per user, rounding to 4 places included."""
+    import json
+    gold = json.load(open(os.path.join(GOLDEN_DIR, 'metrics_golden.json')))
+    for name, c in gold.items():
+        cfg = {'metrics': ['Hit', 'MRR', 'NDCG', 'Recall', 'Precision', 'MAP'], 'topk': c['topk'], 'metric_decimal_place': 4}
+        got = A.evaluator.Evaluator(cfg).evaluate(np.array(c['rec_topk']))
+        assert set(got) == set(c['result']), name
+        for k, v in c['result'].items():
+            assert abs(got[k] - v) <= 1.0001e-4, (name, k, got[k], v)          # north_star: Recall@10 / NDCG@10 within 1e-4
