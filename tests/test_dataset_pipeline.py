@@ -77,3 +77,27 @@ def test_loaders_and_errors():
         A.SequentialDataset(A.Config(model='ACSASRec', dataset='nope', config_dict=dict(data_path=GOLD + '/', device=torch.device('cpu'))))
     with pytest.raises(ValueError):
         A.quick_start.get_model('SASRec')
+
+
+def test_train_loader_epochs_cover_every_row_once():
+    """two epochs over the real training split: every augmented row exactly once per epoch, full batches arrive packed (one
+    buffer per epoch, refilled in place), the ragged tail as a plain Interaction."""
+    config = make_config({})
+    ds = A.create_dataset(config)
+    train_data, _, _ = A.data_preparation(config, ds)
+    n = len(train_data.dataset)
+    key = lambda it: (it['item_id'] * 100003 + it['item_length'] * 7 + it['item_id_list'].sum(1))      # row fingerprint
+    want = torch.sort(key(train_data.dataset.inter_feat)).values
+    ptrs = []
+    for epoch in range(2):
+        torch.manual_seed(epoch)
+        rows, packed = [], 0
+        for batch in train_data:
+            rows.append(key(batch))
+            if isinstance(batch, A.compat.PackedInteraction):
+                packed += 1
+                assert batch['item_id_list'].shape == (256, 50)
+        assert packed == n // 256 and len(rows) == int(np.ceil(n / 256))
+        assert torch.equal(torch.sort(torch.cat(rows)).values, want)
+        ptrs.append(train_data._packed.buf.data_ptr())
+    assert ptrs[0] == ptrs[1]
