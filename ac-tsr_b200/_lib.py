@@ -40,6 +40,29 @@ def parse_header(path=HEADER):
     return protos
 
 
+
+class GemmProblem(ctypes.Structure):
+    """mirror of `acsr_gemm_problem` (include/acsr.h); strides in floats, pointers are device addresses."""
+    _fields_ = [
+        ('A', ctypes.c_void_p), ('a_row_stride', ctypes.c_int64), ('a_k_stride', ctypes.c_int64), ('a_kb_stride', ctypes.c_int64),
+        ('B', ctypes.c_void_p), ('b_row_stride', ctypes.c_int64), ('b_k_stride', ctypes.c_int64), ('b_kb_stride', ctypes.c_int64),
+        ('C', ctypes.c_void_p), ('ldc', ctypes.c_int64),
+        ('M', ctypes.c_int64),
+        ('bias', ctypes.c_void_p), ('colsum', ctypes.c_void_p), ('C2', ctypes.c_void_p),
+        ('res', ctypes.c_void_p), ('res_rows', ctypes.c_int64),
+        ('ln_w', ctypes.c_void_p), ('ln_b', ctypes.c_void_p),
+        ('mask', ctypes.c_void_p), ('rng', ctypes.c_void_p),
+        ('out', ctypes.c_void_p), ('stats', ctypes.c_void_p),
+        ('a_kblk', ctypes.c_int32), ('b_kblk', ctypes.c_int32),
+        ('N', ctypes.c_int32), ('K', ctypes.c_int32),
+        ('epilogue', ctypes.c_int32), ('accumulate', ctypes.c_int32), ('k_splits', ctypes.c_int32), ('act', ctypes.c_int32),
+        ('rng_stream', ctypes.c_uint32), ('eps', ctypes.c_float), ('p_drop', ctypes.c_float), ('reserved', ctypes.c_int32),
+    ]
+
+
+EPI_STORE, EPI_ATOMIC, EPI_ACT, EPI_BDRL = 0, 1, 2, 3
+GEMM_MAX_PROBLEMS = 16
+
 class AcsrError(RuntimeError):
     pass
 
@@ -124,9 +147,23 @@ def _ab_linear_wgrad_batched(a):
     return 4 * batch * (T * (N + K) + N * K)
 
 
+def _ab_gemm_batch(a):
+    # (problems array, n, passes, stream): operands read once, result written once (read-modify-write when accumulating)
+    arr, n = a[0], a[1]
+    tot = 0
+    for i in range(n):
+        p = arr[i]
+        out_mult = 2 if (p.accumulate or p.epilogue in (EPI_ATOMIC, EPI_ACT)) else 1
+        tot += 4 * (p.M * p.K + p.N * p.K + p.M * p.N * out_mult)
+        if p.epilogue == EPI_BDRL:
+            tot += 4 * (2 * p.M * p.N + 2 * p.M)       # residual in, normalised row out, stats
+    return tot
+
+
 # ALGORITHMIC bytes of one launch, from the call's own arguments
 ALGO_BYTES = {'acsr_linear_tok': _ab_linear_tok, 'acsr_linear_tok_bdrl': _ab_linear_tok_bdrl,
-              'acsr_linear_wgrad': _ab_linear_wgrad, 'acsr_linear_wgrad_batched': _ab_linear_wgrad_batched}
+              'acsr_linear_wgrad': _ab_linear_wgrad, 'acsr_linear_wgrad_batched': _ab_linear_wgrad_batched,
+              'acsr_gemm_batch': _ab_gemm_batch}
 
 
 class KernelTimer:

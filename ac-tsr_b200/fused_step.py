@@ -50,6 +50,11 @@ class FusedTrainStep(object):
         # other widths stay library GEMMs + the row-wise epilogue kernels
         self.tc = (bool(getattr(model, 'tc_linear', True)) and model.hidden_size == 64 and model.inner_size <= 256
                    and model.inner_size % 4 == 0)
+        # every other width (d = 128 of the shipped yelp / sports / toys configs, d = 256 of BASELINE config #5): the K-streamed
+        # tcgen05 kernel (gemm_ks.cu) through problem lists.  At every width the weight gradients of a layer go through it as
+        # ONE launch (token axis on K, split over the CTAs).  No library GEMM is left on the step.
+        self.tc_wgrad = bool(getattr(model, 'tc_wgrad', True))
+        self.passes = 3                                   # encoder GEMMs: 3xTF32 (fp32-level accuracy)
         self.overlap_wgrad = bool(getattr(model, 'overlap_wgrad', True))
         self.n_branches = int(getattr(model, 'step_branches', 1))
         self._streams = {}
@@ -228,7 +233,10 @@ class FusedTrainStep(object):
         else:
             LIB.call('acsr_logits_ce_grad', _p(jb['out2']), _p(E), _p(jb['lse']), _p(jb['target2'], torch.int64),
                      _p(jb['row_scale']), 2 * B, V, d, passes, _p(jb['Gt']), 2 * B, st)
-            LIB.call('acsr_linear_wgrad', _p(jb['Gt']), _p(E), V, 2 * B, d, _p(jb['d_out2']), None, st)
+            if self.tc_wgrad:          # d_out2 [2B,d] += Gt^T . E : contraction over the catalogue, split over the CTAs
+                ops.gemm_batch([ops.wgrad_problem(jb['Gt'], E, V, 2 * B, d, jb['d_out2'])])
+            else:
+                LIB.call('acsr_linear_wgrad', _p(jb['Gt']), _p(E), V, 2 * B, d, _p(jb['d_out2']), None, st)
         for br in branches:
             if br['stream'] is not main:
                 br['stream'].wait_stream(main)
@@ -242,8 +250,9 @@ class FusedTrainStep(object):
             with torch.cuda.stream(dE_stream):
                 if self.tc and B <= 256:
                     ops.linear_tok(jb['Gt'], V, B, jb['out2'], d, E.grad, d, ldx=2 * B, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
-                else:
-                    E.grad.addmm_(jb['Gt'][:, :B], jb['out2'][:B])
+                else:                   # dE [V,d] += Gt[:, :B] . out[:B]  (rows of the table on the M axis, K = B)
+                    ops.gemm_batch([ops.gemm_problem(jb['Gt'], jb['out2'], E.grad, V, d, B, a_strides=(2 * B, 1, 0, B),
+                                                     b_strides=(1, d, 0, B), accumulate=True)])
         else:
             dE_stream = main
         dE_done = torch.cuda.Event()
@@ -326,15 +335,19 @@ class FusedTrainStep(object):
                 ops.linear_tok(x, T, d, st3['Wqkv'], d, lb['qkv'], d, bias=st3['bqkv'], batch=3, sx=0, sw=d * d, sb=d, sy=T * d)
                 ops.linear_tok(lb['qkv'], T, d, st3['Waqk'], d, lb['aqk'], d, bias=st3['baqk'], batch=2, sx=T * d, sw=d * d,
                                sb=d, sy=T * d)
-            elif st3 is not None:                             # Q/K/V and the attack pair as two batched GEMMs
-                torch.baddbmm(st3['bqkv'], x.unsqueeze(0).expand(3, T, d), st3['Wqkv'].transpose(1, 2), out=lb['qkv'])
-                torch.baddbmm(st3['baqk'], lb['qkv'][:2], st3['Waqk'].transpose(1, 2), out=lb['aqk'])
             else:
-                torch.addmm(aa.query.bias, x, aa.query.weight.t(), out=lb['mq'])
-                torch.addmm(aa.key.bias, x, aa.key.weight.t(), out=lb['mk'])
-                torch.addmm(aa.value.bias, x, aa.value.weight.t(), out=lb['mv'])
-                torch.addmm(aa.attack_query_transform.bias, lb['mq'], aa.attack_query_transform.weight.t(), out=lb['aq'])
-                torch.addmm(aa.attack_key_transform.bias, lb['mk'], aa.attack_key_transform.weight.t(), out=lb['ak'])
+                # any width: Q / K / V in one launch of the K-streamed tcgen05 kernel, then the attack pair (+ the gate logits,
+                # which read mixed_q as well) in a second one
+                gp = ops.gemm_problem
+                ops.gemm_batch([gp(x, lin.weight, lb[k], T, d, d, bias=lin.bias)
+                                for lin, k in ((aa.query, 'mq'), (aa.key, 'mk'), (aa.value, 'mv'))], passes=self.passes)
+                second = [gp(lb['mq'], aa.attack_query_transform.weight, lb['aq'], T, d, d, bias=aa.attack_query_transform.bias),
+                          gp(lb['mk'], aa.attack_key_transform.weight, lb['ak'], T, d, d, bias=aa.attack_key_transform.bias)]
+                if layer.combine_option == 'gate' and not self.tc:
+                    if layer.gate.out_features != L:
+                        raise ValueError('gate width %d != sequence length %d' % (layer.gate.out_features, L))
+                    second.append(gp(lb['mq'], layer.gate.weight, lb['gl'], T, L, d, bias=layer.gate.bias))
+                ops.gemm_batch(second, passes=self.passes)
             gate = layer.combine_option == 'gate'
             comb_scalar = 0.0
             if gate:
@@ -342,8 +355,6 @@ class FusedTrainStep(object):
                     raise ValueError('gate width %d != sequence length %d' % (layer.gate.out_features, L))
                 if self.tc:
                     ops.linear_tok(lb['mq'], T, d, layer.gate.weight, L, lb['gl'], L, bias=layer.gate.bias)
-                else:
-                    torch.addmm(layer.gate.bias, lb['mq'], layer.gate.weight.t(), out=lb['gl'])
             elif layer.combine_option == 'annealing':
                 comb_scalar = math.exp(-layer.anneal_step / 100000)
                 if s == 0:
@@ -406,16 +417,17 @@ class FusedTrainStep(object):
             ops.linear_tok_bdrl(bf['a1'], R, I, ff.dense_2.weight, ff.dense_2.bias, bf['h'], R, ff.LayerNorm.weight,
                                 ff.LayerNorm.bias, ff.LayerNorm.eps, p_h, bf['m_f'], rngp, base + 5, bf['z2'], out, bf['st_f'])
         else:
-            torch.mm(bf['ctx'][:R], aa.dense.weight.t(), out=bf['hz'][:R])
-            LIB.call('acsr_bias_dropout_res_ln_fwd', _p(bf['hz']), _p(aa.dense.bias), _p(x_res), _p(aa.LayerNorm.weight),
-                     _p(aa.LayerNorm.bias), aa.LayerNorm.eps, R, d, res_rows, p_h, _p(bf['m_a']), rngp, base + 3, _p(bf['h']),
-                     _p(bf['st_a']), st)
-            torch.mm(bf['h'][:R], ff.dense_1.weight.t(), out=bf['z1'][:R])
-            LIB.call('acsr_bias_act_fwd', _p(bf['z1']), _p(ff.dense_1.bias), R, I, act_id, _p(bf['a1']), st)
-            torch.mm(bf['a1'][:R], ff.dense_2.weight.t(), out=bf['z2'][:R])
-            LIB.call('acsr_bias_dropout_res_ln_fwd', _p(bf['z2']), _p(ff.dense_2.bias), _p(bf['h']), _p(ff.LayerNorm.weight),
-                     _p(ff.LayerNorm.bias), ff.LayerNorm.eps, R, d, R, p_h, _p(bf['m_f']), rngp, base + 5, _p(out),
-                     _p(bf['st_f']), st)
+            # any width: three launches of the K-streamed tcgen05 kernel, everything that follows a GEMM in the reference fused
+            # into its TMEM epilogue (bias + dropout + residual + LayerNorm; bias + activation)
+            gp, ps = ops.gemm_problem, self.passes
+            ops.gemm_batch([gp(bf['ctx'], aa.dense.weight, bf['hz'], R, d, d, bias=aa.dense.bias, epilogue=ops.EPI_BDRL, res=x_res,
+                               res_rows=res_rows, ln_w=aa.LayerNorm.weight, ln_b=aa.LayerNorm.bias, eps=aa.LayerNorm.eps, p_drop=p_h,
+                               mask=bf['m_a'], rngp=rngp, rng_stream=base + 3, out=bf['h'], stats=bf['st_a'])], passes=ps)
+            ops.gemm_batch([gp(bf['h'], ff.dense_1.weight, bf['z1'], R, I, d, bias=ff.dense_1.bias, epilogue=ops.EPI_ACT, act=act_id,
+                               C2=bf['a1'])], passes=ps)
+            ops.gemm_batch([gp(bf['a1'], ff.dense_2.weight, bf['z2'], R, d, I, bias=ff.dense_2.bias, epilogue=ops.EPI_BDRL, res=bf['h'],
+                               res_rows=R, ln_w=ff.LayerNorm.weight, ln_b=ff.LayerNorm.bias, eps=ff.LayerNorm.eps, p_drop=p_h,
+                               mask=bf['m_f'], rngp=rngp, rng_stream=base + 5, out=out, stats=bf['st_f'])], passes=ps)
 
     @torch.no_grad()
     def encode_eval(self, item_seq, item_seq_len):
@@ -472,6 +484,7 @@ class FusedTrainStep(object):
             base = soff + 16 * (l + 1)
             x = b['xs'][l]
             gate = layer.combine_option == 'gate'
+            wg = []                                          # weight-gradient problems of this layer (one launch at its end)
             if last and compact:
                 # the dense part of the last layer on the 2*Bs rows that carry a cotangent, then scatter into the zeroed
                 # token-major buffers the attention backward (d_ctx) and the layer below (residual path, d_x) read
@@ -483,11 +496,11 @@ class FusedTrainStep(object):
                     dc_out = cb['d_out']
                     dc_out[:Bs].copy_(jb['d_out2'][lo:lo + Bs])
                     dc_out[Bs:].copy_(jb['d_out2'][B + lo:B + lo + Bs])
-                self._post_attn_bwd(layer, cb, cb, dc_out, cb['x'], C, C, Bs, Bs, cb['d_x'], cb['d_ctx'], p_h, rngp, base, act_id, st, fork)
+                self._post_attn_bwd(layer, cb, cb, dc_out, cb['x'], C, C, Bs, Bs, cb['d_x'], cb['d_ctx'], p_h, rngp, base, act_id, st, fork, wg)
                 LIB.call('acsr_gather_last_bwd', _p(cb['d_ctx']), _p(ln, torch.int64), Bs, L, d, _p(b['d_ctx'][:T]), _p(b['d_ctx'][T:]), st)
                 LIB.call('acsr_gather_last_bwd', _p(cb['d_x']), _p(ln, torch.int64), Bs, L, d, _p(d_x[:T]), _p(d_x[T:]), st)
             else:
-                self._post_attn_bwd(layer, lb, lb, d_out, x, T2, P, T, T, d_x, b['d_ctx'], p_h, rngp, base, act_id, st, fork, b=b)
+                self._post_attn_bwd(layer, lb, lb, d_out, x, T2, P, T, T, d_x, b['d_ctx'], p_h, rngp, base, act_id, st, fork, wg, b=b)
             # fused attention backward (d_gate_logit accumulates over heads: cleared at the start of the step)
             g = lambda t: None if t is None else t.grad     # noqa: E731
             ow, ob_ = (aa.order_affine.weight, aa.order_affine.bias) if aa.use_order else (None, None)
@@ -505,54 +518,43 @@ class FusedTrainStep(object):
             # projections: input gradients for both streams, weight gradients from the owning stream
             aqt, akt = aa.attack_query_transform, aa.attack_key_transform
             st3 = self._stacked(l)
-            if st3 is not None:
-                if self.tc:
-                    ops.linear_tok(lb['d_aqk'], T2, d, st3['Waqk'], d, lb['d_qkv'], d, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True,
-                                   batch=2, sx=T2 * d, sw=d * d, sb=0, sy=T2 * d)
-                else:
-                    lb['d_qkv'][:2].baddbmm_(lb['d_aqk'], st3['Waqk'])
-                # attack transforms are trained by the attacked-loss stream (rows [T,2T))
-                sst = fork()
-                if self.tc or T * d * d < self.LIB_WGRAD_MACS:
-                    LIB.call('acsr_linear_wgrad_batched', _p(lb['d_aqk'][0, T:]), _p(lb['qkv'][0]), T, d, d, _p(st3['gWaqk']),
-                             _p(st3['gbaqk']), 2, T2 * d, T * d, d * d, d, sst)
-                else:
-                    for i2 in range(2):
-                        self._wgrad(lb['d_aqk'][i2, T:], lb['qkv'][i2], T, st3['gWaqk'][i2], st3['gbaqk'][i2], sst)
-            else:
-                lb['d_mq'].addmm_(lb['d_aq'], aqt.weight)
-                lb['d_mk'].addmm_(lb['d_ak'], akt.weight)
-                sst = fork()
-                self._wgrad(lb['d_aq'][T:], lb['mq'], T, aqt.weight.grad, aqt.bias.grad, sst)
-                sst = fork()
-                self._wgrad(lb['d_ak'][T:], lb['mk'], T, akt.weight.grad, akt.bias.grad, sst)
-            if gate:
-                if self.tc:
+            gp = ops.gemm_problem
+            rows_x = T2 if l > 0 else T                      # below the first layer only the calibrated stream trains anything
+            if self.tc and st3 is not None:
+                ops.linear_tok(lb['d_aqk'], T2, d, st3['Waqk'], d, lb['d_qkv'], d, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True,
+                               batch=2, sx=T2 * d, sw=d * d, sb=0, sy=T2 * d)
+                if gate:
                     ops.linear_tok(lb['d_gl'], T2, L, layer.gate.weight, d, lb['d_mq'], d, ldx=L, w_sn=1, w_sk=d, wkb=64 * d,
                                    accumulate=True)
-                else:
-                    lb['d_mq'].addmm_(lb['d_gl'], layer.gate.weight)
-                sst = fork()
-                self._wgrad(lb['d_gl'], lb['mq'], T, layer.gate.weight.grad, layer.gate.bias.grad, sst)
-            if st3 is not None:
-                sst = fork()
-                if self.tc or T * d * d < self.LIB_WGRAD_MACS:
-                    LIB.call('acsr_linear_wgrad_batched', _p(lb['d_qkv'][0]), _p(x), T, d, d, _p(st3['gWqkv']), _p(st3['gbqkv']), 3,
-                             T2 * d, 0, d * d, d, sst)
-                else:
-                    for i3 in range(3):
-                        self._wgrad(lb['d_qkv'][i3], x, T, st3['gWqkv'][i3], st3['gbqkv'][i3], sst)
-            else:
-                for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
-                    sst = fork()
-                    self._wgrad(lb[dk], x, T, lin.weight.grad, lin.bias.grad, sst)
-            rows_x = T2 if l > 0 else T                      # below the first layer only the calibrated stream trains anything
-            if self.tc and st3 is not None:                  # d_x += [d_mq d_mk d_mv] . [Wq; Wk; Wv]: one K = 3d GEMM
+                # d_x += [d_mq d_mk d_mv] . [Wq; Wk; Wv]: one K = 3d GEMM
                 ops.linear_tok(lb['d_qkv'], rows_x, 3 * d, st3['Wqkv'], d, d_x, d, ldx=d, xkb=T2 * d, w_sn=1, w_sk=d, wkb=d * d,
                                accumulate=True)
             else:
-                for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
-                    d_x[:rows_x].addmm_(lb[dk][:rows_x], lin.weight)
+                # any width (K-streamed tcgen05 kernel): d_mq += d_aq.Waq, d_mk += d_ak.Wak in one launch; the gate's d_mq += d_gl.Wg
+                # accumulates into the same rows, so it follows in its own launch; then d_x += sum of the three projections
+                ops.gemm_batch([gp(lb['d_aq'], aqt.weight, lb['d_mq'], T2, d, d, b_strides=(1, d, 0, d), accumulate=True),
+                                gp(lb['d_ak'], akt.weight, lb['d_mk'], T2, d, d, b_strides=(1, d, 0, d), accumulate=True)],
+                               passes=self.passes)
+                if gate:
+                    ops.gemm_batch([gp(lb['d_gl'], layer.gate.weight, lb['d_mq'], T2, d, L, b_strides=(1, d, 0, L), accumulate=True)],
+                                   passes=self.passes)
+                if st3 is not None:                          # K-concatenated: [d_mq d_mk d_mv] . [Wq; Wk; Wv]
+                    ops.gemm_batch([gp(lb['d_qkv'], st3['Wqkv'], d_x, rows_x, d, 3 * d, a_strides=(d, 1, T2 * d, d),
+                                       b_strides=(1, d, d * d, d), accumulate=True)], passes=self.passes)
+                else:
+                    for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
+                        ops.gemm_batch([gp(lb[dk], lin.weight, d_x, rows_x, d, d, b_strides=(1, d, 0, d), accumulate=True)],
+                                       passes=self.passes)
+            # weight gradients of the projections: attack transforms are trained by the attacked-loss stream (rows [T,2T)), the
+            # gate by both halves of d_gl's stream-0 rows, Q / K / V by the calibrated-loss stream
+            self._wgrad(lb['d_aq'][T:], lb['mq'], T, aqt.weight.grad, aqt.bias.grad, fork, wg)
+            self._wgrad(lb['d_ak'][T:], lb['mk'], T, akt.weight.grad, akt.bias.grad, fork, wg)
+            if gate:
+                self._wgrad(lb['d_gl'], lb['mq'], T, layer.gate.weight.grad, layer.gate.bias.grad, fork, wg)
+            for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
+                self._wgrad(lb[dk], x, T, lin.weight.grad, lin.bias.grad, fork, wg)
+            if wg:                                           # all weight gradients of the layer: ONE launch on the side stream
+                ops.gemm_batch(wg, passes=self.passes, stream=fork())
             if l > 0:
                 d_out, d_x = d_x, d_out                       # this layer's input gradient is the next one's output gradient
         main.wait_event(dE_done)                              # the dE GEMM is a plain read-modify-write of the table gradient
@@ -562,59 +564,53 @@ class FusedTrainStep(object):
         if side is not None:
             main.wait_stream(side)                            # join: every weight gradient of this branch landed
 
-    def _post_attn_bwd(self, layer, bf, gb, d_out, x_res, R2, P, res_rows, w_rows, d_xres, d_ctx, p_h, rngp, base, act_id, st, fork, b=None):
+    def _post_attn_bwd(self, layer, bf, gb, d_out, x_res, R2, P, res_rows, w_rows, d_xres, d_ctx, p_h, rngp, base, act_id, st, fork, wg, b=None):
         """backward of _post_attn_fwd over R2 cotangent rows ([stream 0 ; stream 1]); the saved forward tensors of bf repeat
         with period P, the residual x_res with period res_rows; rows [0, w_rows) (stream 0) feed the parameter gradients.
-        Writes the gradient of the attention context to d_ctx and of the residual input to d_xres."""
+        Writes the gradient of the attention context to d_ctx and of the residual input to d_xres; weight-gradient problems
+        are appended to wg (launched together at the end of the layer)."""
         m = self.m
         d, I = m.hidden_size, m.inner_size
         aa, ff = layer.attack_attention, layer.feed_forward
         d_h = gb['d_h'] if b is None else b['d_h']
         d_a1 = gb['d_a1'] if b is None else b['d_a1']
+        gp, ps = ops.gemm_problem, self.passes
         # FFN
         LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_out), _p(bf['z2']), _p(ff.dense_2.bias), _p(bf['h']),
                  _p(ff.LayerNorm.weight), _p(bf['st_f']), R2, d, P, P, w_rows, p_h, _p(bf['m_f']), rngp, base + 5,
                  _p(gb['d_z2']), _p(d_h), _p(ff.dense_2.bias.grad), _p(ff.LayerNorm.weight.grad),
                  _p(ff.LayerNorm.bias.grad), st)
-        sst = fork()
-        self._wgrad(gb['d_z2'], bf['a1'], w_rows, ff.dense_2.weight.grad, None, sst)
+        self._wgrad(gb['d_z2'], bf['a1'], w_rows, ff.dense_2.weight.grad, None, fork, wg)
         if self.tc:                                      # d_a1 = d_z2.W2 : the weight is read transposed
             ops.linear_tok(gb['d_z2'], R2, d, ff.dense_2.weight, I, d_a1, I, w_sn=1, w_sk=I, wkb=64 * I)
         else:
-            torch.mm(gb['d_z2'][:R2], ff.dense_2.weight, out=d_a1[:R2])
+            ops.gemm_batch([gp(gb['d_z2'], ff.dense_2.weight, d_a1, R2, I, d, b_strides=(1, I, 0, d))], passes=ps)
         LIB.call('acsr_bias_act_bwd', _p(d_a1), _p(bf['z1']), _p(ff.dense_1.bias), R2, I, act_id, P, w_rows, _p(gb['d_z1']),
                  _p(ff.dense_1.bias.grad), st)
-        sst = fork()
-        self._wgrad(gb['d_z1'], bf['h'], w_rows, ff.dense_1.weight.grad, None, sst)
+        self._wgrad(gb['d_z1'], bf['h'], w_rows, ff.dense_1.weight.grad, None, fork, wg)
         if self.tc:
             ops.linear_tok(gb['d_z1'], R2, I, ff.dense_1.weight, d, d_h, d, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
         else:
-            d_h[:R2].addmm_(gb['d_z1'][:R2], ff.dense_1.weight)
+            ops.gemm_batch([gp(gb['d_z1'], ff.dense_1.weight, d_h, R2, d, I, b_strides=(1, d, 0, I), accumulate=True)], passes=ps)
         # attention output projection
         LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_h), _p(bf['hz']), _p(aa.dense.bias), _p(x_res),
                  _p(aa.LayerNorm.weight), _p(bf['st_a']), R2, d, P, res_rows, w_rows, p_h, _p(bf['m_a']), rngp, base + 3,
                  _p(gb['d_hz']), _p(d_xres), _p(aa.dense.bias.grad), _p(aa.LayerNorm.weight.grad), _p(aa.LayerNorm.bias.grad), st)
-        sst = fork()
-        self._wgrad(gb['d_hz'], bf['ctx'], w_rows, aa.dense.weight.grad, None, sst)
+        self._wgrad(gb['d_hz'], bf['ctx'], w_rows, aa.dense.weight.grad, None, fork, wg)
         if self.tc:
             ops.linear_tok(gb['d_hz'], R2, d, aa.dense.weight, d, d_ctx, d, w_sn=1, w_sk=d, wkb=64 * d)
         else:
-            torch.mm(gb['d_hz'][:R2], aa.dense.weight, out=d_ctx[:R2])
+            ops.gemm_batch([gp(gb['d_hz'], aa.dense.weight, d_ctx, R2, d, d, b_strides=(1, d, 0, d))], passes=ps)
 
-    # weight-gradient reduction dW [N,K] += dY[:rows]^T . X[:rows] (+ db += column sums) on the stream `handle`.  The token-split
-    # kernel (acsr_linear_wgrad) is built for the small encoder matrices of the shipped configs; above LIB_WGRAD_MACS
-    # multiply-adds (config #5: 409 600 tokens x 256 x 1024) the reduction is a plain large GEMM and goes to the library.
-    LIB_WGRAD_MACS = 1 << 31
-
-    def _wgrad(self, dY, X, rows, dW, db, handle):
+    def _wgrad(self, dY, X, rows, dW, db, fork, wg):
+        """weight-gradient reduction dW [N,K] += dY[:rows]^T . X[:rows] (+ db += column sums): a problem of the layer's single
+        tcgen05 launch (gemm_ks.cu, token axis on K, split over the CTAs), or -- tc_wgrad off -- one launch of the fp32
+        token-split kernel on the side stream."""
         N, K = dY.shape[-1], X.shape[-1]
-        if self.tc or rows * N * K < self.LIB_WGRAD_MACS:
-            LIB.call('acsr_linear_wgrad', _p(dY), _p(X), rows, N, K, _p(dW), _p(db), handle)
-            return
-        with torch.cuda.stream(torch.cuda.ExternalStream(handle)):
-            dW.addmm_(dY[:rows].t(), X[:rows])
-            if db is not None:
-                db.add_(dY[:rows].sum(0))
+        if self.tc_wgrad:
+            wg.append(ops.wgrad_problem(dY, X, rows, N, K, dW, db))
+        else:
+            LIB.call('acsr_linear_wgrad', _p(dY), _p(X), rows, N, K, _p(dW), _p(db), fork())
 
     def _folded_buffers(self, l, dev):
         key = ('folded', l)

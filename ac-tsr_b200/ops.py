@@ -327,25 +327,43 @@ def linear_tok_bdrl(X, rows, K, W, bias, res, res_rows, ln_w, ln_b, eps, p, mask
 
 
 class LinearFn(torch.autograd.Function):
-    """y = x.W^T (+ b).  Forward and dX are library GEMMs; dW/db use the token-split kernel."""
+    """y = x.W^T (+ b) -- every nn.Linear of the API-compatible (autograd) path.  Forward, dX and dW/db all run on the
+    K-streamed tcgen05 kernel (acsr_gemm_batch, 3xTF32): no library GEMM."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        x2 = x.reshape(-1, x.shape[-1])
-        y = torch.addmm(bias, x2, weight.t()) if bias is not None else x2 @ weight.t()
-        return y.view(*x.shape[:-1], weight.shape[0])
+        N, K = weight.shape
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        w = weight if weight.is_contiguous() else weight.contiguous()
+        y = torch.empty((x2.shape[0], N), dtype=torch.float32, device=x.device)
+        gemm_batch([gemm_problem(x2, w, y, x2.shape[0], N, K, bias=bias)])
+        return y.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        dy = dy.contiguous()
+        N, K = weight.shape
+        dy2 = dy.reshape(-1, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        rows = dy2.shape[0]
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
-            dx = (dy.reshape(-1, dy.shape[-1]) @ weight).view_as(x)
+            w = weight if weight.is_contiguous() else weight.contiguous()
+            dx = torch.empty((rows, K), dtype=torch.float32, device=dy.device)
+            gemm_batch([gemm_problem(dy2, w, dx, rows, K, N, b_strides=(1, K, 0, N))])      # dx = dy.W: weight read transposed
+            dx = dx.view_as(x)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dW, db = linear_wgrad(dy, x, want_bias=ctx.has_bias)
+            x2 = x.reshape(-1, K)
+            if not x2.is_contiguous():
+                x2 = x2.contiguous()
+            dW = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
+            db = torch.zeros(N, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+            gemm_batch([wgrad_problem(dy2, x2, rows, N, K, dW, db)])
         return dx, dW, db
 
 
@@ -355,8 +373,8 @@ def linear(x, weight, bias=None):
 
 class LogitsCEFn(torch.autograd.Function):
     """loss[g] = mean CE over row group g of softmax(out.E^T) vs target -- acsasrec.py:117-121.
-    Logits never materialise in the forward; the backward writes Gt once, then d_E = Gt.out (library
-    GEMM) and d_out = Gt^T.E (token-split kernel, reduction over the catalogue)."""
+    Logits never materialise in the forward; the backward writes Gt once, then d_E = Gt.out and d_out = Gt^T.E
+    (reduction over the catalogue) as two problems of one tcgen05 launch (acsr_gemm_batch)."""
 
     @staticmethod
     def forward(ctx, out, table, target, n_groups, passes):
@@ -375,8 +393,17 @@ class LogitsCEFn(torch.autograd.Function):
         per = M // n_groups
         row_scale = (d_loss.to(torch.float32) / per).view(n_groups, 1).expand(n_groups, per).reshape(-1).contiguous()
         Gt = ce_grad_matrix_t(out, table, lse, target, row_scale, passes)
-        d_out = linear_wgrad(Gt, table, want_bias=False)[0] if ctx.needs_input_grad[0] else None
-        d_table = Gt @ out if ctx.needs_input_grad[1] else None
+        V, d = table.shape
+        d_out = d_table = None
+        pr = []
+        if ctx.needs_input_grad[0]:            # d_out [M,d] = Gt^T . E : contraction over the catalogue, split over the CTAs
+            d_out = torch.zeros((M, d), dtype=torch.float32, device=out.device)
+            pr.append(wgrad_problem(Gt, table, V, M, d, d_out))
+        if ctx.needs_input_grad[1]:            # d_E [V,d] = Gt . out
+            d_table = torch.empty((V, d), dtype=torch.float32, device=out.device)
+            pr.append(gemm_problem(Gt, out, d_table, V, d, M, b_strides=(1, d, 0, M)))
+        if pr:
+            gemm_batch(pr)
         return d_out, d_table, None, None, None
 
 
@@ -451,3 +478,59 @@ def full_sort_topk(out, table, k, positive=None, passes=3):
 def adam_step(param, grad, exp_avg, exp_avg_sq, step_count, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
     LIB.call('acsr_adam_step', _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, beta1, beta2, eps,
              weight_decay, _p(step_count, torch.int64), _stream())
+
+
+# ------------------------------------------------------------------------------------------
+# general tcgen05 GEMM (gemm_ks.cu): any hidden size, strided / transposed operands, problem lists
+# ------------------------------------------------------------------------------------------
+from ._lib import GemmProblem, EPI_STORE, EPI_ATOMIC, EPI_ACT, EPI_BDRL, GEMM_MAX_PROBLEMS  # noqa: E402
+
+
+def gemm_problem(A, B, C, M, N, K, a_strides=None, b_strides=None, ldc=None, bias=None, epilogue=EPI_STORE, accumulate=False,
+                 k_splits=0, colsum=None, act=0, C2=None, res=None, res_rows=0, ln_w=None, ln_b=None, eps=0.0, p_drop=0.0,
+                 mask=None, rngp=None, rng_stream=0, out=None, stats=None):
+    """one problem C[M,N] (+)= A[M,K].B[N,K]^T of an acsr_gemm_batch launch.  A / B / C are tensors (their data_ptr is the
+    base address; views are fine) and a_strides / b_strides = (row_stride, k_stride, kblock_stride, kblock_len) in floats
+    (default: row-major [rows, K]).  The caller keeps the tensors alive until the launch has been enqueued."""
+    for t in (A, B, C, bias, colsum, C2, res, ln_w, ln_b, mask, out, stats):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise AcsrError('gemm_problem: float32 CUDA tensors only (no CPU fallback)')
+    g = GemmProblem()
+    ar, ak, akb, akl = a_strides if a_strides is not None else (K, 1, 0, K)
+    br, bk, bkb, bkl = b_strides if b_strides is not None else (K, 1, 0, K)
+    g.A, g.a_row_stride, g.a_k_stride, g.a_kb_stride, g.a_kblk = A.data_ptr(), int(ar), int(ak), int(akb), int(akl)
+    g.B, g.b_row_stride, g.b_k_stride, g.b_kb_stride, g.b_kblk = B.data_ptr(), int(br), int(bk), int(bkb), int(bkl)
+    g.C = C.data_ptr() if C is not None else None
+    g.ldc = int(N if ldc is None else ldc)
+    g.M, g.N, g.K = int(M), int(N), int(K)
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.colsum = colsum.data_ptr() if colsum is not None else None
+    g.C2 = C2.data_ptr() if C2 is not None else None
+    g.res = res.data_ptr() if res is not None else None
+    g.res_rows = int(res_rows)
+    g.ln_w = ln_w.data_ptr() if ln_w is not None else None
+    g.ln_b = ln_b.data_ptr() if ln_b is not None else None
+    g.mask = mask.data_ptr() if mask is not None else None
+    g.rng = rngp
+    g.out = out.data_ptr() if out is not None else None
+    g.stats = stats.data_ptr() if stats is not None else None
+    g.epilogue, g.accumulate, g.k_splits, g.act = int(epilogue), int(bool(accumulate)), int(k_splits), int(act)
+    g.rng_stream, g.eps, g.p_drop = int(rng_stream), float(eps), float(p_drop)
+    return g
+
+
+def gemm_batch(problems, passes=3, stream=None):
+    """launch a list of gemm_problem()s (chunks of 16 per launch) on `stream` (default: the current torch stream)."""
+    st = _stream() if stream is None else stream
+    for i in range(0, len(problems), GEMM_MAX_PROBLEMS):
+        chunk = problems[i:i + GEMM_MAX_PROBLEMS]
+        arr = (GemmProblem * len(chunk))(*chunk)
+        LIB.call('acsr_gemm_batch', arr, len(chunk), int(passes), st)
+
+
+def wgrad_problem(dY, X, rows, N, K, dW, db=None, ldy=None, ldx=None, ldw=None, k_splits=0):
+    """dW[N,K] += dY[:rows, :N]^T . X[:rows, :K]  (+ db[N] += column sums of dY): the token axis is the contraction."""
+    ldy = N if ldy is None else ldy
+    ldx = K if ldx is None else ldx
+    return gemm_problem(dY, X, dW, N, K, rows, a_strides=(1, ldy, 0, rows), b_strides=(1, ldx, 0, rows), ldc=(K if ldw is None else ldw),
+                        epilogue=EPI_ATOMIC, colsum=db, k_splits=k_splits)

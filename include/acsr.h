@@ -284,6 +284,57 @@ int acsr_linear_wgrad(const float* dY, const float* X, int T, int N, int K, floa
 int acsr_linear_wgrad_batched(const float* dY, const float* X, int T, int N, int K, float* dW, float* db, int batch,
                               int64_t stride_dy, int64_t stride_x, int64_t stride_dw, int64_t stride_db, void* stream);
 
+/* ---- general encoder GEMM on tcgen05 (3xTF32), any hidden size: K streamed in 32-wide slabs, up to 16 problems per launch ----
+ * replaces EVERY nn.Linear forward, input-gradient and weight-gradient GEMM of model/layers.py:658-659, 680, 687-689,
+ * 791-794, 887 (and their autograd backward) for hidden sizes the width-64 kernels above do not cover (d = 128 of
+ * config/yelp.yaml:39-42, amazon-sports-outdoors.yaml:31-34, amazon-toys-games.yaml:29-32; d = 256 of BASELINE config #5).
+ *   C[m, n] (+)= sum_k A(m,k) * B(n,k)        m < M, n < N, k < K
+ *   A(m,k) = A[(k / a_kblk) * a_kb_stride + m * a_row_stride + (k % a_kblk) * a_k_stride]      (B alike; strides in floats)
+ * so transposed operands (input gradients: B = W^T; weight gradients: A = dY^T, B = X^T with the token axis on K) and
+ * K-concatenated inputs need no copies.  a_kblk / b_kblk: multiples of 4 (or >= K when the operand is one block).
+ * Epilogues (thread-per-row out of TMEM):
+ *   ACSR_EPI_STORE  C = acc + bias (accumulate != 0: C += ...)
+ *   ACSR_EPI_ATOMIC C += acc with vector atomics; the K range is cut into k_splits work items (0 = chosen by the library);
+ *                   colsum[m] += sum_k A(m,k) when colsum != NULL (the bias gradient of a weight-gradient problem; needs
+ *                   a_k_stride != 1, i.e. the transposed-operand form)
+ *   ACSR_EPI_ACT    C = acc (saved for the backward), C2 = act(acc + bias)                       layers.py:776-792
+ *   ACSR_EPI_BDRL   C = acc (may be NULL), out = LayerNorm(dropout(acc + bias) + res[m % res_rows]), stats[m] = (mean, rstd);
+ *                   N <= 256 and a multiple of 4                                                 layers.py:681-683, 794-796 */
+#define ACSR_EPI_STORE 0
+#define ACSR_EPI_ATOMIC 1
+#define ACSR_EPI_ACT 2
+#define ACSR_EPI_BDRL 3
+#define ACSR_GEMM_MAX_PROBLEMS 16
+typedef struct acsr_gemm_problem {
+  const float* A; int64_t a_row_stride; int64_t a_k_stride; int64_t a_kb_stride;
+  const float* B; int64_t b_row_stride; int64_t b_k_stride; int64_t b_kb_stride;
+  float* C; int64_t ldc;
+  int64_t M;
+  const float* bias;
+  float* colsum;
+  float* C2;
+  const float* res; int64_t res_rows;
+  const float* ln_w; const float* ln_b;
+  const float* mask; const void* rng;
+  float* out; float* stats;
+  int32_t a_kblk; int32_t b_kblk;
+  int32_t N; int32_t K;
+  int32_t epilogue; int32_t accumulate; int32_t k_splits; int32_t act;
+  uint32_t rng_stream; float eps; float p_drop; int32_t reserved;
+} acsr_gemm_problem;
+int acsr_gemm_batch(const acsr_gemm_problem* problems, int n_problems, int passes, void* stream);
+
+/* ---- loss_type BPR (model/sequential_recommender/acsasrec.py:109-116, model/loss.py:21-47) ----
+ * x_m = out_m . (E[pos_m] - E[neg_m]); row_loss[m] = -log(gamma + sigmoid(x_m)); loss[g] = mean over row group g
+ * (M rows in n_groups equal groups: [calibrated ; attacked] in the fused step).  row_x [M] is saved for the backward. */
+int acsr_bpr_loss_fwd(const float* out, const float* table, const int64_t* pos_items, const int64_t* neg_items, int M, int d,
+                      int n_groups, float gamma, float* row_x, float* row_loss, float* loss, void* stream);
+/* d_out[m] = row_scale[m] * dloss/dx_m * (E[pos_m] - E[neg_m]) (may be NULL); rows m in [table_row_begin, table_row_end)
+ * scatter +-row_scale[m] * dloss/dx_m * out_m into d_table rows pos_m / neg_m with atomics (d_table may be NULL). */
+int acsr_bpr_loss_bwd(const float* out, const float* table, const int64_t* pos_items, const int64_t* neg_items, const float* row_x,
+                      const float* row_scale, int M, int d, float gamma, int table_row_begin, int table_row_end, float* d_out,
+                      float* d_table, void* stream);
+
 /* ---- K13: fused Adam over one flat fp32 buffer (trainer/trainer.py:614-615,687) ---------
  * torch.optim.Adam semantics (no amsgrad); step_count device int64[1], incremented by the call. */
 int acsr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

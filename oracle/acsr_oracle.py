@@ -23,7 +23,7 @@ Reference lines each function follows (relative to /root/reference/recbole):
   ac_layer           model/layers.py:898-951
   encoder            model/layers.py:1097-1131
   forward            model/sequential_recommender/acsasrec.py:86-104
-  calculate_loss     model/sequential_recommender/acsasrec.py:107-144
+  calculate_loss     model/sequential_recommender/acsasrec.py:107-144 (CE and BPR branches; model/loss.py:21-47)
   predict/full_sort  model/sequential_recommender/acsasrec.py:146-164
   train_grads        trainer/trainer.py:660-687 (two backward passes routed by name)
   full_sort_topk     trainer/trainer.py:941-942, evaluator/collector.py:145-153
@@ -268,13 +268,24 @@ def cross_entropy(out, E, target):
     return (lse - logits[torch.arange(out.shape[0]), target]).mean()
 
 
-def calculate_loss(params, cfg, item_seq, item_len, pos_items, rnd=None, anneal_rates=None):
-    """-> (final_attacked_loss, calibrated_loss)  acsasrec.py:123-144 (CE branch)."""
+def bpr_loss(out, E, pos_items, neg_items, gamma=1e-10):
+    """acsasrec.py:109-116 + loss.py:21-47: -log(gamma + sigmoid(out.E[pos] - out.E[neg])) averaged over the batch."""
+    pos_score = (out * E[pos_items]).sum(-1)
+    neg_score = (out * E[neg_items]).sum(-1)
+    return -torch.log(gamma + torch.sigmoid(pos_score - neg_score)).mean()
+
+
+def calculate_loss(params, cfg, item_seq, item_len, pos_items, rnd=None, anneal_rates=None, neg_items=None):
+    """-> (final_attacked_loss, calibrated_loss)  acsasrec.py:123-144 (CE branch, or BPR when cfg['loss_type'] == 'BPR')."""
     att, cal, Ms = forward(params, cfg, item_seq, item_len, rnd, anneal_rates)
     E = params['item_embedding.weight']
     pens = [torch.sqrt(torch.sum((1 - (M['M'] if isinstance(M, dict) else M)) ** 2)) for M in Ms]
     pen = torch.stack(pens).mean()
     w = params['mask_loss_weight'][0] if cfg.get('trainable_mask_loss_weight') else cfg['mask_loss_weight']
+    if cfg.get('loss_type', 'CE') == 'BPR':
+        l_att = -bpr_loss(att, E, pos_items, neg_items) + pen * w
+        l_cal = bpr_loss(cal, E, pos_items, neg_items)
+        return l_att, l_cal
     l_att = -cross_entropy(att, E, pos_items) + pen * w
     l_cal = cross_entropy(cal, E, pos_items)
     return l_att, l_cal
@@ -283,13 +294,13 @@ def calculate_loss(params, cfg, item_seq, item_len, pos_items, rnd=None, anneal_
 ATTACK_KEYS = ('attack_key_transform', 'attack_query_transform')   # trainer.py:673
 
 
-def train_grads(params, cfg, item_seq, item_len, pos_items, rnd=None, anneal_rates=None):
+def train_grads(params, cfg, item_seq, item_len, pos_items, rnd=None, anneal_rates=None, neg_items=None):
     """The two backward passes of trainer.py:672-686 -> (l_att, l_cal, {name: grad}).
 
     attack_{query,key}_transform get d l_att, every other parameter gets d l_cal;
     a trainable mask_loss_weight gets nothing (it only enters l_att)."""
     p = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in params.items())
-    l_att, l_cal = calculate_loss(p, cfg, item_seq, item_len, pos_items, rnd, anneal_rates)
+    l_att, l_cal = calculate_loss(p, cfg, item_seq, item_len, pos_items, rnd, anneal_rates, neg_items)
     names = list(p)
     g_cal = torch.autograd.grad(l_cal, [p[n] for n in names], retain_graph=True, allow_unused=True)
     g_att = torch.autograd.grad(l_att, [p[n] for n in names], allow_unused=True)

@@ -109,9 +109,16 @@ def make_case(name, V, B, seed, train, k=50, **cfgkw):
     seq[0] = torch.randint(1, V, (L,), generator=g)
     ln[1] = 1                                   # one minimal row
     seq[1, 1:] = 0
-    inter = Interaction({'item_id_list': seq, 'item_length': ln, 'item_id': pos})
+    fields = {'item_id_list': seq, 'item_length': ln, 'item_id': pos}
+    if cfg['loss_type'] == 'BPR':                # one sampled negative per row (acsasrec.py:110), never the positive
+        neg = torch.randint(1, V - 1, (B,), generator=g)
+        neg = neg + (neg >= pos).long()
+        fields['neg_item_id'] = neg
+    inter = Interaction(fields)
     out = {'V': V, 'B': B, 'k': min(k, V - 1), 'train': int(train), 'seed': seed,
            'item_id_list': seq.numpy(), 'item_length': ln.numpy(), 'item_id': pos.numpy()}
+    if 'neg_item_id' in fields:
+        out['neg_item_id'] = fields['neg_item_id'].numpy()
     for kk, vv in cfgkw.items():
         out['cfg.' + kk] = np.array(vv)
     for n, p in model.state_dict().items():
@@ -193,6 +200,8 @@ CASES = [
     # of BASELINE configuration #5 (L=200, d=256, 4 heads) at a size that stays a small fixture
     # (the reference's gate is Linear(d, 50) whatever the sequence length -- acsasrec.py never passes seq_length, layers.py:878 --
     # so the unmodified reference only runs L != 50 with combine_option fixed / annealing)
+    # loss_type BPR (acsasrec.py:109-116, loss.py:21-47): one sampled negative per row
+    ('bpr_train', 131, 4, 23, True, dict(n_layers=2, loss_type='BPR')),
     ('long_train', 151, 2, 21, True, dict(n_layers=2, n_heads=4, hidden_size=128, inner_size=256, MAX_ITEM_LIST_LENGTH=100,
                                           combine_option='fixed')),
     ('long_eval', 151, 2, 22, False, dict(n_layers=2, n_heads=4, hidden_size=128, inner_size=256, MAX_ITEM_LIST_LENGTH=100,

@@ -49,7 +49,7 @@ def test_eval_forward_scores_topk(name):
 def test_train_losses_and_routed_grads(name):
     c = load_case(name)
     b = c['batch']
-    l_att, l_cal, grads = O.train_grads(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['pos'], c['rand'])
+    l_att, l_cal, grads = O.train_grads(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['pos'], c['rand'], neg_items=b.get('neg'))
     z = c['z']
     assert abs(float(l_att) - float(z['loss_att'])) < 1e-5 * abs(float(z['loss_att']))
     assert abs(float(l_cal) - float(z['loss_cal'])) < 1e-5 * abs(float(z['loss_cal']))
