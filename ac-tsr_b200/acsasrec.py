@@ -150,9 +150,7 @@ class ACSASRec(SequentialRecommender):
         pos_items = interaction[self.POS_ITEM_ID]
         if self.loss_type == 'BPR':
             neg_items = interaction[self.NEG_ITEM_ID]
-            pos_score = torch.sum(output * self.item_embedding(pos_items), dim=-1)
-            neg_score = torch.sum(output * self.item_embedding(neg_items), dim=-1)
-            return self.loss_fct(pos_score, neg_score)
+            return ops.BprLossFn.apply(output, self.item_embedding.weight, pos_items, neg_items, 1, self.loss_fct.gamma)[0]
         return ops.LogitsCEFn.apply(output, self.item_embedding.weight, pos_items, 1, self.logits_passes)[0]
 
     def calculate_loss(self, interaction):
@@ -167,9 +165,11 @@ class ACSASRec(SequentialRecommender):
             ce = ops.LogitsCEFn.apply(out, self.item_embedding.weight, torch.cat((pos_items, pos_items)), 2,
                                       self.logits_passes)
             attacked_ce, calibrated_loss = ce[0], ce[1]
-        else:
-            attacked_ce = self._cal_loss(out[:B], interaction, attack_loss=True)
-            calibrated_loss = self._cal_loss(out[B:], interaction)
+        else:                                   # BPR: both row groups through one pair of kernels
+            pos_items, neg_items = interaction[self.POS_ITEM_ID], interaction[self.NEG_ITEM_ID]
+            bl = ops.BprLossFn.apply(out, self.item_embedding.weight, torch.cat((pos_items, pos_items)),
+                                     torch.cat((neg_items, neg_items)), 2, self.loss_fct.gamma)
+            attacked_ce, calibrated_loss = bl[0], bl[1]
         assert len(masks) > 0
         mask_penalty = torch.mean(torch.stack([m.penalty() for m in masks], dim=0))
         w = self.mask_loss_weight[0] if self.trainable_mask_loss_weight else self.mask_loss_weight

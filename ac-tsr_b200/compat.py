@@ -218,7 +218,16 @@ class Config(object):
             c['metrics'] = [c['metrics']]
         if 'device' not in c or c['device'] is None:
             use = c.get('use_gpu', True) and torch.cuda.is_available()
-            c['device'] = torch.device('cuda:%d' % 0 if use else 'cpu')
+            # configurator.py:344-348 exports gpu_id as CUDA_VISIBLE_DEVICES before CUDA is initialised; here CUDA may already
+            # be up (one process per GPU sets its own device), so gpu_id selects the device index directly
+            gpu_id = c.get('gpu_id', 0)
+            try:
+                gpu_id = int(str(gpu_id).split(',')[0])
+            except (TypeError, ValueError):
+                gpu_id = 0
+            if use and gpu_id >= torch.cuda.device_count():
+                raise ValueError('gpu_id %d: only %d CUDA device(s) visible' % (gpu_id, torch.cuda.device_count()))
+            c['device'] = torch.device('cuda:%d' % gpu_id if use else 'cpu')
         c.setdefault('data_path', 'dataset/')
         if c.get('dataset') and not str(c['data_path']).rstrip('/').endswith(str(c['dataset'])):
             c['data_path'] = os.path.join(c['data_path'], c['dataset'])

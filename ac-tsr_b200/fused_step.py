@@ -41,8 +41,8 @@ class _RandSlice(object):
 
 class FusedTrainStep(object):
     def __init__(self, model, optimizer):
-        if model.loss_type != 'CE':
-            raise NotImplementedError('fused step covers loss_type CE (the shipped configs); BPR takes the autograd path')
+        if model.loss_type not in ('CE', 'BPR'):
+            raise NotImplementedError("Make sure 'loss_type' in ['BPR', 'CE']!")
         self.m, self.opt = model, optimizer
         self.buf = {}
         self.vp = None            # dist.VocabParallel when the logits are sharded over ranks
@@ -123,9 +123,10 @@ class FusedTrainStep(object):
         nc = ops.logits_num_chunks(2 * B, V)
         loss3 = f(3)              # [CE(calibrated), CE(attacked), final attacked loss]: one buffer, one read-back
         j = dict(pen=torch.zeros(N, dtype=torch.float64, device=dev), out2=f(2 * B, d), partial=f(2 * B, nc, 2), lse=f(2 * B),
-                 tgt=f(2 * B), row_loss=f(2 * B), loss3=loss3, loss=loss3[:2], loss_att=loss3[2:], dpen=f(N), Gt=f(V, 2 * B),
+                 tgt=f(2 * B), row_loss=f(2 * B), loss3=loss3, loss=loss3[:2], loss_att=loss3[2:], dpen=f(N), Gt=(f(V, 2 * B) if m.loss_type == 'CE' else None),
                  d_out2=f(2 * B, d),
                  target2=torch.empty(2 * B, dtype=torch.int64, device=dev), ce_cnt=torch.zeros(1, dtype=torch.int32, device=dev),
+                 neg2=torch.empty(2 * B, dtype=torch.int64, device=dev), row_x=f(2 * B),
                  row_scale=torch.cat((torch.full((B,), 1.0 / B), torch.full((B,), -1.0 / B))).to(dev))
         self.buf[key] = j
         return j
@@ -153,7 +154,8 @@ class FusedTrainStep(object):
         training = m.training
         E = m.item_embedding.weight
         main = torch.cuda.current_stream()
-        nb = self.n_branches if (self.n_branches > 1 and B % self.n_branches == 0) else 1
+        # (sequences longer than 64: the attention backward's workspace is one per device, so the branches would race on it)
+        nb = self.n_branches if (self.n_branches > 1 and B % self.n_branches == 0 and L <= 64) else 1
         Bs = B // nb
         jb = self._joint_buffers(B, dev)
         branches = []
@@ -208,7 +210,17 @@ class FusedTrainStep(object):
             jb['loss'].copy_(loss2)
         wp = m.mask_loss_weight.detach() if m.trainable_mask_loss_weight else None
         wv = 0.0 if wp is not None else float(m.mask_loss_weight)
-        if self.vp is None:
+        bpr = m.loss_type == 'BPR'
+        if bpr:
+            # acsasrec.py:109-116: one sampled negative per row; rows [0,B) calibrated, [B,2B) attacked share the two kernels
+            if self.vp is not None:
+                raise NotImplementedError('vocab-parallel logits are a CE construct; loss_type BPR touches two table rows per sequence')
+            neg_items = interaction[m.NEG_ITEM_ID]
+            torch.cat((neg_items, neg_items), out=jb['neg2'])
+            LIB.call('acsr_bpr_loss_fwd', _p(jb['out2']), _p(E), _p(jb['target2'], torch.int64), _p(jb['neg2'], torch.int64), 2 * B, d, 2,
+                     float(m.loss_fct.gamma), _p(jb['row_x']), _p(jb['row_loss']), _p(jb['loss']), st)
+            LIB.call('acsr_loss_combine', jb['pen'].data_ptr(), N, _p(jb['loss'][1:]), _p(wp), wv, _p(jb['loss_att']), _p(jb['dpen']), st)
+        elif self.vp is None:
             # per-chunk (max, sum-exp) -> lse / target logit / row losses -> the two CE means -> pen_l = sqrt(sum (1-M_l)^2),
             # loss_att = -CE(attacked) + w * mean_l pen_l, d loss_att / d pen_sq_l: one single-CTA launch after the GEMM
             LIB.call('acsr_logits_ce_partial', _p(jb['out2']), _p(E), 2 * B, V, d, passes, _p(jb['partial']), st)
@@ -228,7 +240,10 @@ class FusedTrainStep(object):
         # ---------------- backward ----------------
         dpen = jb['dpen']
         main.wait_event(zero_done)
-        if self.vp is not None:       # shard-local G^T, reduce-scatter of d_out, dE into the owner's rows
+        if bpr:                       # d_out2 = +-g (E[pos] - E[neg]) / B ; the calibrated rows scatter +-g.out into dE[pos], dE[neg]
+            LIB.call('acsr_bpr_loss_bwd', _p(jb['out2']), _p(E), _p(jb['target2'], torch.int64), _p(jb['neg2'], torch.int64),
+                     _p(jb['row_x']), _p(jb['row_scale']), 2 * B, d, float(m.loss_fct.gamma), 0, B, _p(jb['d_out2']), _p(E.grad), st)
+        elif self.vp is not None:       # shard-local G^T, reduce-scatter of d_out, dE into the owner's rows
             jb['d_out2'].copy_(self.vp.ce_backward(vst, E, jb['row_scale'], E.grad, table_half=0, n_groups=2))
         else:
             LIB.call('acsr_logits_ce_grad', _p(jb['out2']), _p(E), _p(jb['lse']), _p(jb['target2'], torch.int64),
@@ -240,7 +255,7 @@ class FusedTrainStep(object):
         for br in branches:
             if br['stream'] is not main:
                 br['stream'].wait_stream(main)
-        if self.vp is None:
+        if self.vp is None and not bpr:
             # dE += Gt[:, :B] . out[:B]: only the calibrated rows train the item table.  It reads and writes dE without
             # atomics, so every branch's embedding scatter waits for it (dE_done).  Nothing else consumes it: with a single
             # branch it runs on that branch's weight-gradient stream.

@@ -407,6 +407,39 @@ class LogitsCEFn(torch.autograd.Function):
         return d_out, d_table, None, None, None
 
 
+
+class BprLossFn(torch.autograd.Function):
+    """loss[g] = mean over row group g of -log(gamma + sigmoid(out.E[pos] - out.E[neg])) -- acsasrec.py:109-116, loss.py:21-47."""
+
+    @staticmethod
+    def forward(ctx, out, table, pos_items, neg_items, n_groups, gamma):
+        out, table = out.contiguous(), table.contiguous()
+        pos_items, neg_items = pos_items.contiguous(), neg_items.contiguous()
+        M, d = out.shape
+        dev = out.device
+        row_x = torch.empty(M, dtype=torch.float32, device=dev)
+        row_loss = torch.empty(M, dtype=torch.float32, device=dev)
+        loss = torch.empty(n_groups, dtype=torch.float32, device=dev)
+        LIB.call('acsr_bpr_loss_fwd', _p(out), _p(table), _p(pos_items, torch.int64), _p(neg_items, torch.int64), M, d, n_groups,
+                 float(gamma), _p(row_x), _p(row_loss), _p(loss), _stream())
+        ctx.save_for_backward(out, table, pos_items, neg_items, row_x)
+        ctx.meta = (n_groups, float(gamma))
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        out, table, pos_items, neg_items, row_x = ctx.saved_tensors
+        n_groups, gamma = ctx.meta
+        M, d = out.shape
+        per = M // n_groups
+        row_scale = (d_loss.to(torch.float32) / per).view(n_groups, 1).expand(n_groups, per).reshape(-1).contiguous()
+        d_out = torch.empty_like(out) if ctx.needs_input_grad[0] else None
+        d_table = torch.zeros_like(table) if ctx.needs_input_grad[1] else None
+        LIB.call('acsr_bpr_loss_bwd', _p(out), _p(table), _p(pos_items, torch.int64), _p(neg_items, torch.int64), _p(row_x),
+                 _p(row_scale), M, d, gamma, 0, M, _p(d_out), _p(d_table), _stream())
+        return d_out, d_table, None, None, None, None
+
+
 def logits_scores(out, table, passes=3):
     """scores [M,V] = out.E^T (contiguous)  -- acsasrec.py:162-163."""
     out, table = out.contiguous(), table.contiguous()

@@ -83,6 +83,7 @@ class FlatAdam(object):
         assert off <= n + align * len(layout)
         self.lr, self.weight_decay, self.betas, self.eps = float(lr), float(weight_decay or 0.0), betas, eps
         self.params = params
+        self.no_grad_params = [p for n, p in model.named_parameters() if n == 'mask_loss_weight']
 
     def stacked(self, plist, grad=False):
         """view of adjacent, equally shaped parameters (or their grads) as one [len, *shape] tensor; None if not adjacent."""
@@ -98,19 +99,67 @@ class FlatAdam(object):
         self.flat_grad.zero_()
 
     def step(self):
+        # torch.optim.Adam skips parameters whose .grad is None -- in the reference that is a trainable mask_loss_weight, which
+        # only enters the attacked loss and is routed away (trainer.py:672-686): with weight decay the flat kernel would
+        # still shrink it, so its value is put back after the step
+        keep = [(p, p.detach().clone()) for p in self.no_grad_params] if (self.weight_decay and self.no_grad_params) else []
         ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
                       self.betas[0], self.betas[1], self.eps, self.weight_decay)
+        for p, v in keep:
+            p.data.copy_(v)
+
+    def _view(self, flat, p):
+        off = self.offsets[id(p)]
+        return flat[off:off + p.numel()].view(p.shape)
 
     def state_dict(self):
-        return {'flat_adam': True, 'exp_avg': self.exp_avg.cpu(), 'exp_avg_sq': self.exp_avg_sq.cpu(),
-                'step': int(self.step_count.item()), 'lr': self.lr, 'weight_decay': self.weight_decay}
+        """torch.optim.Adam's format (trainer.py:718-728 saves `self.optimizer.state_dict()`): per-parameter step / exp_avg /
+        exp_avg_sq indexed by the position in model.parameters(), one param group -- a checkpoint written here resumes in
+        the reference trainer and vice versa."""
+        step = int(self.step_count.item())
+        state = {}
+        if step > 0:
+            for i, p in enumerate(self.params):
+                state[i] = {'step': torch.tensor(float(step)), 'exp_avg': self._view(self.exp_avg, p).detach().cpu().clone(),
+                            'exp_avg_sq': self._view(self.exp_avg_sq, p).detach().cpu().clone()}
+        group = {'lr': self.lr, 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': self.weight_decay, 'amsgrad': False,
+                 'maximize': False, 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None,
+                 'params': list(range(len(self.params)))}
+        return {'state': state, 'param_groups': [group]}
 
     def load_state_dict(self, sd):
-        if not sd.get('flat_adam'):
-            raise ValueError('optimizer state was not written by FlatAdam')
-        self.exp_avg.copy_(sd['exp_avg'])
-        self.exp_avg_sq.copy_(sd['exp_avg_sq'])
-        self.step_count.fill_(sd['step'])
+        """accepts torch.optim.Adam's state_dict (a reference checkpoint's 'optimizer' entry) or the round-1 flat format"""
+        if sd.get('flat_adam'):                       # checkpoints written by the first version of this trainer
+            if sd['exp_avg'].numel() != self.exp_avg.numel():
+                raise ValueError('flat optimizer state has %d elements, this model needs %d' % (sd['exp_avg'].numel(), self.exp_avg.numel()))
+            self.exp_avg.copy_(sd['exp_avg'])
+            self.exp_avg_sq.copy_(sd['exp_avg_sq'])
+            self.step_count.fill_(sd['step'])
+            return
+        if 'state' not in sd or 'param_groups' not in sd:
+            raise ValueError('optimizer state is neither a torch.optim.Adam state_dict nor a FlatAdam one')
+        order = [i for g in sd['param_groups'] for i in g['params']]
+        if len(order) != len(self.params):
+            raise ValueError('optimizer state covers %d parameters, this model has %d' % (len(order), len(self.params)))
+        steps = set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for pos, key in enumerate(order):
+            st = sd['state'].get(key)
+            if st is None:                            # parameter that never received a gradient (torch keeps no state for it)
+                continue
+            p = self.params[pos]
+            if tuple(st['exp_avg'].shape) != tuple(p.shape):
+                raise ValueError('optimizer state %s has shape %s, parameter %d has %s' % (key, tuple(st['exp_avg'].shape), pos, tuple(p.shape)))
+            self._view(self.exp_avg, p).copy_(st['exp_avg'])
+            self._view(self.exp_avg_sq, p).copy_(st['exp_avg_sq'])
+            steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise ValueError('per-parameter step counts differ (%s): not representable by the single-step flat Adam' % sorted(steps))
+        self.step_count.fill_(steps.pop() if steps else 0)
+        g0 = sd['param_groups'][0]
+        self.lr, self.betas, self.eps = float(g0.get('lr', self.lr)), tuple(g0.get('betas', self.betas)), float(g0.get('eps', self.eps))
+        self.weight_decay = float(g0.get('weight_decay', self.weight_decay) or 0.0)
 
 
 class ACSASRecTrainer(object):
@@ -147,7 +196,7 @@ class ACSASRecTrainer(object):
         self.dp_world = 1
         self.fused = None
         if (bool(cfg_get(config, 'fused_step', True)) and isinstance(self.optimizer, FlatAdam)
-                and getattr(model, 'loss_type', None) == 'CE' and not self.clip_grad_norm):
+                and getattr(model, 'loss_type', None) in ('CE', 'BPR') and not self.clip_grad_norm):
             from .fused_step import FusedTrainStep
             self.fused = FusedTrainStep(model, self.optimizer)
             model._fused_step = self.fused          # eval batches reuse the fused forward (ACSASRec._encode)
@@ -244,6 +293,7 @@ class ACSASRecTrainer(object):
         static = {k: static_inter[k] for k in self._fields()}
         for k in static:
             static[k].copy_(interaction[k])
+        self.model._runtime(dev)               # creates the device RNG state, so the snapshot below covers it
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm-up on a side stream (allocator + lazy inits), state restored after
@@ -261,9 +311,18 @@ class ACSASRecTrainer(object):
             la, lc = self._step_body(static_inter)
         self._graph = dict(graph=g, static=static, static_inter=static_inter, key=self._graph_key(interaction), la=la, lc=lc)
 
+    def _host_schedule(self):
+        """combine_option 'annealing' (layers.py:889-891): the mixing rate exp(-anneal_step / 1e5) is a host float that changes
+        with EVERY forward, train or eval.  A captured graph would freeze it, so such models always launch eagerly."""
+        enc = getattr(self.model, 'trm_encoder', None)
+        return enc is not None and any(getattr(l, 'combine_option', None) == 'annealing' for l in enc.layer)
+
     def graphed_step(self, interaction):
         """interaction: host (pinned) or device tensors of the captured shape.  Copies the batch into the
         static buffers on the current stream and replays the captured step."""
+        if self._host_schedule() or int(interaction[self.model.ITEM_SEQ].shape[1]) > 64:
+            # annealing: see _host_schedule; sequences longer than 64: the attention backward's workspace may have to grow
+            return self._step_body(interaction.to(self.device))
         if self._graph is None or self._graph['key'] != self._graph_key(interaction):
             if self._graph is not None:
                 return self._step_body(interaction.to(self.device))      # ragged last batch: eager launch
@@ -288,7 +347,7 @@ class ACSASRecTrainer(object):
         self.model.train()
         tot_a = torch.zeros((), dtype=torch.float64, device=self.device)
         tot_c = torch.zeros((), dtype=torch.float64, device=self.device)
-        graph_ok = self.use_graph and isinstance(self.optimizer, FlatAdam) and not self.clip_grad_norm
+        graph_ok = self.use_graph and self.fused is not None and isinstance(self.optimizer, FlatAdam) and not self.clip_grad_norm
         for batch_idx, interaction in enumerate(train_data):
             if graph_ok:
                 la, lc = self.graphed_step(interaction)
@@ -306,7 +365,7 @@ class ACSASRecTrainer(object):
         return valid_result[self.valid_metric] if self.valid_metric else valid_result['recall@10'], valid_result
 
     def _save_checkpoint(self, epoch, verbose=True, **kwargs):
-        """trainer.py:710-731 (same keys)."""
+        """trainer.py:710-731: same keys; 'optimizer' is in torch.optim.Adam's state_dict format (FlatAdam.state_dict)."""
         saved_model_file = kwargs.pop('saved_model_file', self.saved_model_file)
         state = {
             'config': self.config, 'epoch': epoch, 'cur_step': self.cur_step, 'best_valid_score': self.best_valid_score,
@@ -383,7 +442,7 @@ class ACSASRecTrainer(object):
         """trainer.py:926-945 with the API-compatible materialised scores (used when fused_topk is off)."""
         interaction, history_index, positive_u, positive_i = batched_data
         _, scores = self.model.full_sort_predict(interaction.to(self.device))
-        scores = scores.view(-1, self.tot_item_num)
+        scores = scores.view(-1, self.tot_item_num or self.model.n_items)
         scores[:, 0] = -np.inf
         if history_index is not None:
             scores[history_index] = -np.inf
@@ -395,18 +454,28 @@ class ACSASRecTrainer(object):
         interaction, history_index, positive_u, positive_i = batched_data
         kmax = max(self.topk)
         if self.fused_topk and history_index is None:
-            if self.use_graph and not self.model.training:
+            if kmax > 64:                      # the fused top-k keeps at most 64 candidates per row: materialised scores + torch.topk
+                return self._eval_materialised(batched_data, kmax, rec_out)
+            if self.use_graph and not self.model.training and not self._host_schedule():
                 return self._graphed_eval(interaction, positive_i, kmax, rec_out)
             inter = interaction.to(self.device)
             pos = inter[self.model.POS_ITEM_ID] if positive_i is interaction.interaction.get(self.model.POS_ITEM_ID) else \
                 positive_i.to(self.device, non_blocking=True)
             _, _, rec = self.model.full_sort_topk(inter, kmax, pos)
         else:
-            interaction, scores, positive_u, positive_i = self._full_sort_batch_eval(batched_data)
-            _, topk_idx = torch.topk(scores, kmax, dim=-1)
-            pos = positive_i.to(self.device)
-            flags = (topk_idx == pos.view(-1, 1)).to(torch.int32)
-            rec = torch.cat((flags, torch.ones_like(flags[:, :1])), dim=1)
+            return self._eval_materialised(batched_data, kmax, rec_out)
+        if rec_out is not None:
+            rec_out.copy_(rec, non_blocking=True)
+            return rec_out
+        return rec
+
+    def _eval_materialised(self, batched_data, kmax, rec_out=None):
+        """trainer.py:926-945 + collector.py:145-153 on materialised scores (API-compatible path)."""
+        interaction, scores, positive_u, positive_i = self._full_sort_batch_eval(batched_data)
+        _, topk_idx = torch.topk(scores, kmax, dim=-1)
+        pos = positive_i.to(self.device)
+        flags = (topk_idx == pos.view(-1, 1)).to(torch.int32)
+        rec = torch.cat((flags, torch.ones_like(flags[:, :1])), dim=1)
         if rec_out is not None:
             rec_out.copy_(rec, non_blocking=True)
             return rec_out

@@ -40,6 +40,14 @@ WORKLOADS = {
 WORKLOAD = dict(WORKLOADS['c2'])
 
 
+def workload_string(full_len=False):
+    """names the workload; IDENTICAL in both arms (`--impl ours` / `--impl reference`)"""
+    w = WORKLOAD
+    return ('%s: V=%d, users=%d, L=%d, d=%d, layers=%d, heads=%d, inner=%d, train/eval batch %d per GPU, top-%d; lengths %s, items Zipf(1)'
+            % (w['name'], w['V'], w['users'], w['L'], w['d'], w['n_layers'], w['n_heads'], w['inner'], w['B'], w['topk'],
+               'all = L' if full_len else 'LogNormal(ln7,0.8)'))
+
+
 def model_cfg():
     return dict(n_layers=WORKLOAD['n_layers'], n_heads=WORKLOAD['n_heads'], hidden_size=WORKLOAD['d'],
                 inner_size=WORKLOAD['inner'], hidden_dropout_prob=0.5, attn_dropout_prob=0.5, hidden_act='gelu',
@@ -147,13 +155,14 @@ def algorithmic_bytes(name, per_step_calls, cfg, B, V):
     return None
 
 
-def build(dev, rank, world, cuda_graph=True):
+def build(dev, rank, world, cuda_graph=True, B=None):
     import ac_tsr_b200 as A
     cfg = model_cfg()
     d = dict(cfg)
+    B = WORKLOAD['B'] if B is None else B
     d.update(USER_ID_FIELD='user_id', ITEM_ID_FIELD='item_id', LIST_SUFFIX='_list', ITEM_LIST_LENGTH_FIELD='item_length',
-             NEG_PREFIX='neg_', device=dev, seed=42, learning_rate=1e-4, epochs=1, train_batch_size=WORKLOAD['B'],
-             eval_batch_size=WORKLOAD['B'], topk=[1, 3, 5, 10, 20, 50], metrics=['Hit', 'MRR', 'NDCG'], valid_metric='Hit@10',
+             NEG_PREFIX='neg_', device=dev, seed=42, learning_rate=1e-4, epochs=1, train_batch_size=B,
+             eval_batch_size=B, topk=[1, 3, 5, 10, 20, 50], metrics=['Hit', 'MRR', 'NDCG'], valid_metric='Hit@10',
              checkpoint_dir='/tmp/acsr_bench_ckpt', cuda_graph=cuda_graph, logits_passes=3,
              step_branches=int(os.environ.get('ACSR_STEP_BRANCHES', 1)))
     config = A.Config(model='ACSASRec', config_dict=d)
@@ -198,6 +207,139 @@ class StdoutGuard:
         os.write(self.real, (text + '\n').encode())
 
 
+def kernel_breakdown(A, trainer, devb, nb, cfg, B, V, K):
+    """per-kernel device time of the training step: eager (non-graph) steps with every C-ABI launch bracketed by events on the
+    launching stream.  -> (kernels dict sorted by time, launches per step, eager ms per step)"""
+    kt_steps = min(K, 10)
+    timer = A._lib.KernelTimer()
+    A.LIB.timer = timer
+    saved_branches = None
+    if trainer.fused is not None:
+        trainer.fused.overlap_wgrad = False       # per-kernel events are recorded on the launching (main) stream
+        saved_branches, trainer.fused.n_branches = trainer.fused.n_branches, 1
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    # the host needs ~15 us per eager launch, most kernels take less: park the GPU behind a spin kernel so the launches
+    # queue up and the event pairs bracket device time only (kernel + its launch gap), not host submission time
+    torch.cuda._sleep(int(0.25 * 1.9e9))
+    t0.record()
+    for i in range(kt_steps):
+        trainer.train_step(devb[i % nb])
+    t1.record()
+    ksum = timer.summary()
+    A.LIB.timer = None
+    if trainer.fused is not None:
+        trainer.fused.overlap_wgrad = True
+        trainer.fused.n_branches = saved_branches
+    eager_ms = t0.elapsed_time(t1) / kt_steps
+    launches_per_step = timer.launches / kt_steps + 1                   # adam_step enqueues two kernels
+    n_param = trainer.optimizer.flat_param.numel()
+    kernels = {}
+    total_k = sum(t for _, t in ksum.values())
+    for name, (n, t) in sorted(ksum.items(), key=lambda x: -x[1][1]):
+        per_step_calls = n / kt_steps
+        ab = algorithmic_bytes(name, per_step_calls, cfg, B, V)
+        if name in timer.bytes:
+            ab = timer.bytes[name] / kt_steps
+        if name == 'acsr_adam_step':
+            ab = 28 * n_param
+        ms = t / kt_steps
+        kernels[name] = {'calls_per_step': per_step_calls, 'ms_per_step': round(ms, 5), 'share': round(t / total_k, 4),
+                         'algo_bytes_per_step': ab, 'gbs': (round(ab / ms / 1e6, 1) if ab else None)}
+    return kernels, launches_per_step, eager_ms
+
+
+def roofline_of(kernels, workload_is_c2):
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak, peak_src = (peaks.get('hbm_gbs'), 'measured (MEASURED_PEAKS.json hbm_gbs)') if peaks.get('hbm_gbs') else (6650.0, 'fallback 6.65 TB/s')
+    top = next(iter(kernels))
+    tk = kernels[top]
+    calls = max(1.0, tk['calls_per_step'])
+    return {'kernel': top, 'bound': 'hbm', 'achieved': tk['gbs'], 'peak': peak, 'unit': 'GB/s',
+            'frac': (round(tk['gbs'] / peak, 4) if tk['gbs'] else None), 'traffic': measured_traffic(top) if workload_is_c2 else None,
+            'traffic_source': os.path.relpath(TRAFFIC_PROFILE, ROOT) + ' (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, same workload)',
+            'peak_source': peak_src,
+            'avg_launch_us': round(tk['ms_per_step'] / calls * 1e3, 2),
+            'algo_bytes_per_launch': (int(tk['algo_bytes_per_step'] / calls) if tk['algo_bytes_per_step'] else None),
+            'share_of_kernel_time': tk['share']}
+
+
+def parity_check(A, dev, cfg, B, L, V):
+    """parity asserted inside the bench run.  One fused training step of the headline shape on the
+    first synthetic batch, every dropout mask and the attack noise injected, against the CPU oracle: both losses and every
+    routed gradient.  Raises when out of tolerance (losses 1e-3 relative = north_star; gradients 1e-3 of max |g|)."""
+    from oracle import acsr_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = O.init_params(cfg, V, seed=42)
+    seq, ln, pos = O.synth_batch(B, L, V, seed=42)
+    rnd = O.draw_rand(cfg, B, L, seed=43, train=True)
+    la_o, lc_o, grads = O.train_grads(params, cfg, seq, ln, pos, rnd)
+    _, _, config, model, trainer = build(dev, 0, 1, cuda_graph=False, B=B)
+    model.load_state_dict({k: v.to(dev) for k, v in params.items()}, strict=True)
+    model._debug_rand = {k: v.to(dev) for k, v in rnd.d.items()}
+    model.train()
+    inter = A.Interaction({'item_id_list': seq.to(dev), 'item_length': ln.to(dev), 'item_id': pos.to(dev)})
+    la, lc = trainer.fused(inter)
+    ra = abs(float(la) - float(la_o)) / abs(float(la_o))
+    rc = abs(float(lc) - float(lc_o)) / abs(float(lc_o))
+    worst, worst_name, grads_ok = 0.0, '', True
+    for n, p in model.named_parameters():
+        ref = grads[n]
+        scale = float(ref.abs().max())
+        err = float((p.grad.cpu() - ref).abs().max())
+        # same criterion as tests/: 1e-3 of max |g| plus an absolute floor (a key-side bias has an exactly-zero true gradient --
+        # softmax is shift invariant -- so both sides hold rounding noise only)
+        grads_ok = grads_ok and err <= 1e-3 * scale + 1e-8
+        if scale > 1e-6 and err / scale > worst:
+            worst, worst_name = err / scale, n
+    ok = ra < 1e-3 and rc < 1e-3 and grads_ok
+    out = {'checked': 'fused train step vs CPU oracle, B=%d V=%d, injected masks/noise' % (B, V), 'loss_attacked_rel_err': float('%.3g' % ra),
+           'loss_calibrated_rel_err': float('%.3g' % rc), 'max_grad_rel_err': float('%.3g' % worst), 'worst_grad': worst_name,
+           'tolerance': 1e-3, 'ok': bool(ok)}
+    if not ok:
+        raise AssertionError('bench parity check failed: %s' % json.dumps(out))
+    del model, trainer
+    return out
+
+
+def eager_cuda_baseline(cfg, B, L, V, dev, steps=10):
+    """Reference-SEMANTICS step in eager PyTorch on the same B200 (proxy for running /root/reference with device='cuda',
+    trainer.py:660-687; the reference itself cannot travel to the GPU box): the oracle restatement -- stock ATen / cuBLAS
+    kernels, autograd, two routed backward passes, Adam -- with the masks / noise drawn once and reused (the reference draws its
+    attack noise on the CPU every step, layers.py:917, so this proxy is faster than the real thing)."""
+    from oracle import acsr_oracle as O
+    params = {k: v.to(dev) for k, v in O.init_params(cfg, V, seed=42).items()}
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in params.items()}
+    seq, ln, pos = (t.to(dev) for t in O.synth_batch(B, L, V, seed=42))
+    rnd = O.draw_rand(cfg, B, L, seed=1, train=True)
+    rnd = O.Rand({k: v.to(dev) for k, v in rnd.d.items()})
+    cnt = [0]
+
+    def step():
+        cnt[0] += 1
+        la, lc, grads = O.train_grads(params, cfg, seq, ln, pos, rnd)
+        for k in params:
+            params[k], m, v = O.adam_step(params[k], grads[k], state[k][0], state[k][1], cnt[0], 1e-4)
+            state[k] = (m, v)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {'value': round(B / (ms / 1e3), 1), 'unit': 'seq/s', 'ms_per_step': round(ms, 3), 'kind': 'port',
+            'sample': '%d eager-CUDA steps of B=%d: oracle restatement of the reference step on cuda:0 (stock ATen/cuBLAS kernels, autograd, '
+                      'Adam; masks and noise drawn once)' % (steps, B)}
+
+
 def run_ours(args):
     guard = StdoutGuard()
     rank = int(os.environ.get('RANK', 0))
@@ -219,6 +361,9 @@ def run_ours(args):
     if world > 1:
         trainer.enable_data_parallel(vocab_parallel=vocab_parallel)
     B, L, V, K, W = WORKLOAD['B'], WORKLOAD['L'], WORKLOAD['V'], args.steps, args.warmup
+    parity = None
+    if rank == 0 and world == 1 and not args.no_parity and WORKLOAD['L'] <= 64 and V <= 100000:
+        parity = parity_check(A, dev, cfg, min(B, 256), L, V)
     nb = 8                                                             # distinct synthetic batches cycled through
     seq, ln, tgt = A.data.synth_sequences(nb * B, L, V, seed=42 + rank, full_len=bool(args.full_len))
     # host batches in pinned memory, the three fields of a batch back to back (what TrainDataLoader yields): one H2D copy per step
@@ -293,65 +438,16 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
 
-    # ---- per-kernel device time: eager (non-graph) steps with every C-ABI launch bracketed by events ----
     model.train()
-    kt_steps = min(K, 10)
-    timer = A._lib.KernelTimer()
-    A.LIB.timer = timer
-    if trainer.fused is not None:
-        trainer.fused.overlap_wgrad = False       # per-kernel events are recorded on the launching (main) stream
-        saved_branches, trainer.fused.n_branches = trainer.fused.n_branches, 1
-    torch.cuda.synchronize()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    # the host needs ~15 us per eager launch, most kernels take less: park the GPU behind a spin kernel so the launches
-    # queue up and the event pairs bracket device time only (kernel + its launch gap), not host submission time
-    torch.cuda._sleep(int(0.25 * 1.9e9))
-    t0.record()
-    for i in range(kt_steps):
-        trainer.train_step(devb[i % nb])
-    t1.record()
-    ksum = timer.summary()
-    A.LIB.timer = None
-    if trainer.fused is not None:
-        trainer.fused.overlap_wgrad = True
-        trainer.fused.n_branches = saved_branches
-    eager_ms = t0.elapsed_time(t1) / kt_steps
-    launches_per_step = timer.launches / kt_steps + 1                   # adam_step enqueues two kernels
-    n_param = trainer.optimizer.flat_param.numel()
-    kernels = {}
-    total_k = sum(t for _, t in ksum.values())
-    for name, (n, t) in sorted(ksum.items(), key=lambda x: -x[1][1]):
-        per_step_calls = n / kt_steps
-        ab = algorithmic_bytes(name, per_step_calls, cfg, B, V)
-        if name in timer.bytes:
-            ab = timer.bytes[name] / kt_steps
-        if name == 'acsr_adam_step':
-            ab = 28 * n_param
-        ms = t / kt_steps
-        kernels[name] = {'calls_per_step': per_step_calls, 'ms_per_step': round(ms, 5), 'share': round(t / total_k, 4),
-                         'algo_bytes_per_step': ab, 'gbs': (round(ab / ms / 1e6, 1) if ab else None)}
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    peak, peak_src = (peaks.get('hbm_gbs'), 'measured (MEASURED_PEAKS.json hbm_gbs)') if peaks.get('hbm_gbs') else (6650.0, 'fallback 6.65 TB/s')
-    top = next(iter(kernels))
-    topk_ = kernels[top]
-    calls = max(1.0, topk_['calls_per_step'])
-    roof = {'kernel': top, 'bound': 'hbm', 'achieved': topk_['gbs'], 'peak': peak, 'unit': 'GB/s',
-            'frac': (round(topk_['gbs'] / peak, 4) if topk_['gbs'] else None), 'traffic': measured_traffic(top) if args.workload == 'c2' else None,
-            'traffic_source': 'profiles/r01_traffic_v8.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, same workload)',
-            'peak_source': peak_src,
-            'avg_launch_us': round(topk_['ms_per_step'] / calls * 1e3, 2),
-            'algo_bytes_per_launch': (int(topk_['algo_bytes_per_step'] / calls) if topk_['algo_bytes_per_step'] else None),
-            'share_of_kernel_time': topk_['share']}
+    kernels, launches_per_step, eager_ms = kernel_breakdown(A, trainer, devb, nb, cfg, B, V, K)
+    roof = roofline_of(kernels, args.workload == 'c2')
 
     # max over ranks
     t = torch.tensor([ms_dev, ms_e2e, ms_eval, ms_eval_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e, ms_eval, ms_eval_e2e = [float(x) for x in t.tolist()]
+
     def shutdown():
         """release the captured graph (it pins NCCL resources) before tearing the process group down; never hang at exit"""
         if world == 1:
@@ -371,23 +467,31 @@ def run_ours(args):
     if rank != 0:
         shutdown()
         return
-    cpu = None
+    # ---- large-batch record ("report throughput at B=256 and at large B"): B = 2048, the RecBole default the
+    # reference's dataset YAMLs inherit; same model, own per-kernel roofline ----
+    large = None
+    if world == 1 and not args.no_large_batch and args.workload == 'c2' and args.batch == 0:
+        large = large_batch_record(A, dev, cfg, 2048, L, V, max(10, K // 4), flush)
+    cpu = eager = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(cfg, B if args.workload == 'c2' else min(B, 32), L, V, budget_s=20.0)
+        if WORKLOAD['L'] <= 64 and V <= 100000:
+            try:
+                eager = eager_cuda_baseline(cfg, B, L, V, dev)
+            except Exception as e:                                      # a proxy measurement must never sink the bench line
+                eager = {'error': str(e)[:200]}
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in host[0].columns)
     line = {
         'metric': 'AC-SASRec train seq/s', 'value': round(world * B * K / (ms_dev / 1e3), 1), 'unit': 'seq/s',
         'n_gpus': world, 'steps': K, 'warmup': max(W, 3), 'ms_per_step': round(ms_dev / K, 4), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': '%s: V=%d, users=%d, L=%d, d=%d, layers=%d, heads=%d, inner=%d, train/eval batch %d per GPU, top-%d; '
-                               'lengths %s, items Zipf(1); L2 flushed (256 MiB write) between timed steps'
-                               % (WORKLOAD['name'], V, WORKLOAD['users'], L, WORKLOAD['d'], WORKLOAD['n_layers'], WORKLOAD['n_heads'],
-                                  WORKLOAD['inner'], B, kmax, 'all = L' if args.full_len else 'LogNormal(ln7,0.8)'),
-                   'parallelism': ('dp%d (batch-parallel, NCCL all-reduce of the flat gradient%s)'
-                                   % (world, '; logits/CE/top-k vocab-sharded: all-gather of out and of the (max, sum-exp) partials, '
-                                      'reduce-scatter of d_out' if vocab_parallel else ', replicated item table')) if world > 1 else 'single GPU',
-                   'launch': ('CUDA graph replay of the whole step' + (' (NCCL all-reduce captured)' if world > 1 else '')) if use_graph else 'eager launches + NCCL',
-                   'logits': '3xTF32 tcgen05 (fp32-level accuracy)'},
+        'config': {'workload': workload_string(bool(args.full_len))},
+        'notes': {'timing': 'CUDA events around every step on the launching stream; L2 flushed (256 MiB write) between timed steps',
+                  'parallelism': ('dp%d (batch-parallel, NCCL all-reduce of the flat gradient%s)'
+                                  % (world, '; logits/CE/top-k vocab-sharded: all-gather of out and of the (max, sum-exp) partials, '
+                                     'reduce-scatter of d_out' if vocab_parallel else ', replicated item table')) if world > 1 else 'single GPU',
+                  'launch': ('CUDA graph replay of the whole step' + (' (NCCL all-reduce captured)' if world > 1 else '')) if use_graph else 'eager launches + NCCL',
+                  'gemm': '3xTF32 tcgen05 (fp32-level accuracy), no library GEMM on the step'},
         'e2e': {'value': round(world * B * K / (ms_e2e / 1e3), 1), 'unit': 'seq/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12},
         'gpu_launches': int(round(launches_per_step * K)),
         'clocks': clocks,
@@ -399,10 +503,41 @@ def run_ours(args):
         'kernels': kernels,
         'eager_ms_per_step': round(eager_ms, 4),
     }
+    if parity is not None:
+        line['parity'] = parity
+    if large is not None:
+        line['large_batch'] = large
     if cpu is not None:
         line['cpu_baseline'] = cpu
+        line['cpu_baseline_eval'] = cpu_baseline_eval(cfg, B if args.workload == 'c2' else min(B, 32), L, V, kmax, budget_s=8.0)
+    if eager is not None:
+        line['eager_cuda_baseline'] = eager
     guard.emit(json.dumps(line))
     shutdown()
+
+
+def large_batch_record(A, dev, cfg, B, L, V, K, flush):
+    """the training step at a large batch (B sequences, CUDA-graph replay, batch resident in HBM) + its per-kernel roofline"""
+    _, _, config, model, trainer = build(dev, 0, 1, cuda_graph=True, B=B)
+    nb = 4
+    seq, ln, tgt = A.data.synth_sequences(nb * B, L, V, seed=7)
+    devb = [A.Interaction({'item_id_list': seq[i * B:(i + 1) * B], 'item_length': ln[i * B:(i + 1) * B],
+                           'item_id': tgt[i * B:(i + 1) * B]}).pack(['item_id_list', 'item_length', 'item_id']).to(dev) for i in range(nb)]
+    model.train()
+    it = [0]
+
+    def dev_step():
+        trainer.graphed_step(devb[it[0] % nb])
+        it[0] += 1
+    for _ in range(3):
+        dev_step()
+    torch.cuda.synchronize()
+    ms = timed_steps(dev_step, K, flush)
+    kernels, launches, eager_ms = kernel_breakdown(A, trainer, devb, nb, cfg, B, V, K)
+    roof = roofline_of(kernels, False)
+    top3 = {k: kernels[k] for k in list(kernels)[:3]}
+    return {'batch': B, 'value': round(B * K / (ms / 1e3), 1), 'unit': 'seq/s', 'ms_per_step': round(ms / K, 4), 'steps': K,
+            'launches_per_step': launches, 'roofline': roof, 'top_kernels': top3}
 
 
 def run_profile(args):
@@ -446,20 +581,47 @@ def oracle_step_fn(cfg, B, L, V, seed=42):
     return step
 
 
-def cpu_baseline(cfg, B, L, V, budget_s=20.0):
-    torch.set_num_threads(os.cpu_count() or 1)
-    step = oracle_step_fn(cfg, B, L, V)
+def oracle_eval_fn(cfg, B, L, V, k, seed=42):
+    """one reference-semantics full-sort eval batch on the CPU (oracle port): forward, scores, scores[:,0] = -inf, top-k, hit flags
+    (acsasrec.py:157-164, trainer.py:941-942, collector.py:145-153)."""
+    from oracle import acsr_oracle as O
+    params = O.init_params(cfg, V, seed=seed)
+    seq, ln, pos = O.synth_batch(B, L, V, seed=seed)
+
+    def step():
+        with torch.no_grad():
+            scores = O.full_sort_scores(params, cfg, seq, ln)
+            _, idx = O.full_sort_topk(scores, k)
+            return O.hit_flags(idx, pos)
+    return step
+
+
+def _timed_cpu(step, budget_s, max_n):
     step()                                       # warm-up
     t0 = time.time()
     n = 0
     while True:
         step()
         n += 1
-        if time.time() - t0 > budget_s or n >= 10:
+        if time.time() - t0 > budget_s or n >= max_n:
             break
-    dt = time.time() - t0
+    return n, time.time() - t0
+
+
+def cpu_baseline(cfg, B, L, V, budget_s=20.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    n, dt = _timed_cpu(oracle_step_fn(cfg, B, L, V), budget_s, 10)
     return {'value': round(B * n / dt, 2), 'unit': 'seq/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': '%d training steps of B=%d (oracle/acsr_oracle.py: CPU restatement of the reference step, all host threads)' % (n, B)}
+            'sample': '%d training steps of B=%d (oracle/acsr_oracle.py: CPU restatement of the reference step, all host threads; anomaly '
+                      'mode OFF -- the reference as shipped runs with autograd anomaly detection ON (sine.py:25) and measured 1.3-1.8x '
+                      'slower in the build container, BASELINE.md section 2)' % (n, B)}
+
+
+def cpu_baseline_eval(cfg, B, L, V, k, budget_s=8.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    n, dt = _timed_cpu(oracle_eval_fn(cfg, B, L, V, k), budget_s, 20)
+    return {'value': round(B * n / dt, 2), 'unit': 'users/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d full-sort eval batches of B=%d (oracle port: forward + scores + top-%d + hit flags)' % (n, B, k)}
 
 
 def run_reference(args):
@@ -486,15 +648,18 @@ def run_reference(args):
     dt = time.time() - t0
     val = round(Bs * K / dt, 2)
     cb = {'value': val, 'unit': 'seq/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-          'sample': '%d steps of B=%d of the C2 workload (oracle port of the reference CPU path; /root/reference is Python and '
+          'sample': '%d steps of B=%d of the workload (oracle port of the reference CPU path, anomaly mode OFF; /root/reference is Python and '
                     'cannot travel to the GPU box)' % (K, Bs)}
+    ev = cpu_baseline_eval(cfg, Bs, L, V, WORKLOAD['topk'], budget_s=15.0)
     print(json.dumps({
         'impl': 'reference', 'metric': 'AC-SASRec train seq/s', 'value': val, 'unit': 'seq/s', 'n_gpus': int(args.gpus), 'steps': K,
         'warmup': W, 'ms_per_step': round(dt / K * 1e3, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': '%s: V=%d, L=%d, d=%d, layers=%d, heads=%d, inner=%d, batch %d (CPU sample batch %d)'
-                               % (WORKLOAD['name'], V, L, WORKLOAD['d'], WORKLOAD['n_layers'], WORKLOAD['n_heads'], WORKLOAD['inner'], B, Bs)},
-        'cpu_baseline': cb, 'e2e': {'value': val, 'unit': 'seq/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        'config': {'workload': workload_string(bool(args.full_len))},
+        'notes': {'cpu_sample_batch': Bs},
+        'cpu_baseline': cb, 'e2e': {'value': val, 'unit': 'seq/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'eval': {'metric': 'AC-SASRec full-sort eval users/s', 'value': ev['value'], 'unit': 'users/s', 'cpu_baseline': ev,
+                 'e2e': {'value': ev['value'], 'unit': 'users/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}}))
 
 
 def main():
@@ -504,6 +669,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true', help='skip the in-run parity check against the CPU oracle')
+    ap.add_argument('--no-large-batch', action='store_true', help='skip the B=2048 sub-record')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS), help='c2 = the headline configuration (default)')
     ap.add_argument('--full-len', action='store_true', help='every sequence has the maximum length (worst case) instead of LogNormal lengths')
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the workload')

@@ -158,7 +158,7 @@ def attn_calib(mq, mk, mv, aq, ak, gate_logit, mask, lp, cfg, l, rnd, anneal_rat
     dt = S.dtype
     e_o = torch.zeros_like(S)
     e_d = torch.zeros_like(S)
-    idx = torch.arange(L)
+    idx = torch.arange(L, device=S.device)
     if cfg['use_order']:
         wo, bo = lp['order_affine.weight'][0], lp['order_affine.bias'][0]
         u = (q @ wo[:dh]).unsqueeze(-1) + (k @ wo[dh:]).unsqueeze(-2) + bo
@@ -258,14 +258,14 @@ def forward(params, cfg, item_seq, item_len, rnd=None, anneal_rates=None, want_p
         att, x, M = ac_layer(x, mask, params, cfg, l, rnd, ar, want_probs)
         Ms.append(M)
     B = item_seq.shape[0]
-    rows = torch.arange(B)
+    rows = torch.arange(B, device=item_seq.device)
     return att[rows, item_len - 1], x[rows, item_len - 1], Ms
 
 
 def cross_entropy(out, E, target):
     logits = out @ E.t()
     lse = torch.logsumexp(logits, -1)
-    return (lse - logits[torch.arange(out.shape[0]), target]).mean()
+    return (lse - logits[torch.arange(out.shape[0], device=out.device), target]).mean()
 
 
 def bpr_loss(out, E, pos_items, neg_items, gamma=1e-10):

@@ -55,7 +55,10 @@ def build_model(A, c, **extra):
 
 def inter_of(A, c):
     b = c['batch']
-    return A.Interaction({'item_id_list': b['item_seq'].cuda(), 'item_length': b['item_len'].cuda(), 'item_id': b['pos'].cuda()})
+    f = {'item_id_list': b['item_seq'].cuda(), 'item_length': b['item_len'].cuda(), 'item_id': b['pos'].cuda()}
+    if 'neg' in b:                                 # loss_type BPR
+        f['neg_item_id'] = b['neg'].cuda()
+    return A.Interaction(f)
 
 
 def rel(a, b):
@@ -119,7 +122,7 @@ def test_golden_train_losses_and_routed_grads(A, name):
         assert err <= 1e-3 * scale + 1e-8, (n, err, scale)
 
 
-@pytest.mark.parametrize('name', ['c1_train', 'beauty_train'])
+@pytest.mark.parametrize('name', ['c1_train', 'beauty_train', 'bpr_train'])
 def test_trainer_step_matches_oracle_adam(A, name):
     """one full optimisation step (both losses, routed grads, fused Adam) == oracle grads + oracle Adam."""
     c = load_case(name)
@@ -128,7 +131,7 @@ def test_trainer_step_matches_oracle_adam(A, name):
     model.train()
     la, lc = trainer.train_step(inter_of(A, c))
     b = c['batch']
-    _, _, grads = O.train_grads(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['pos'], c['rand'])
+    _, _, grads = O.train_grads(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['pos'], c['rand'], neg_items=b.get('neg'))
     sd = model.state_dict()
     for n, p0 in c['params'].items():
         want, _, _ = O.adam_step(p0, grads[n], torch.zeros_like(p0), torch.zeros_like(p0), 1, 1e-3)
@@ -410,3 +413,75 @@ def test_config_shapes_train_step_and_eval_vs_oracle(A, shape):
     ok, nbad = O.topk_equal_modulo_ties(idx.cpu(), ref_idx, ref_scores)
     assert ok, nbad
     assert torch.equal(rec.cpu()[:, :-1], O.hit_flags(idx.cpu(), pos))
+
+
+def test_resume_from_reference_format_checkpoint(A, tmp_path):
+    """trainer.py:733-761: a checkpoint whose 'optimizer' entry is torch.optim.Adam's state_dict (what the reference writes)
+    resumes in this trainer: the step after the resume equals the step of an uninterrupted run (dropout off)."""
+    cfg = O.default_cfg(hidden_dropout_prob=0.0, attn_dropout_prob=0.0, n_layers=1)
+    V, B, L = 300, 32, 50
+    params = O.init_params(cfg, V, seed=2)
+    seq, ln, pos = O.synth_batch(B, L, V, seed=3)
+
+    def fresh():
+        config = make_config(A, cfg, checkpoint_dir=str(tmp_path))
+        model = A.ACSASRec(config, DS(V)).to('cuda')
+        model.load_state_dict({k: v.cuda() for k, v in params.items()})
+        model._debug_rand = {(l, 'noise'): torch.zeros(B, cfg['n_heads'], L, L).cuda() for l in range(cfg['n_layers'])}
+        trainer = A.ACSASRecTrainer(config, model)
+        model.train()
+        return model, trainer
+    inter = A.Interaction({'item_id_list': seq.cuda(), 'item_length': ln.cuda(), 'item_id': pos.cuda()})
+    m1, t1 = fresh()
+    t1.train_step(inter)
+    t1._save_checkpoint(0, verbose=False)
+    ck = torch.load(t1.saved_model_file, map_location='cpu', weights_only=False)
+    assert set(ck['optimizer']) == {'state', 'param_groups'}                     # torch.optim.Adam's layout
+    ref_adam = torch.optim.Adam([torch.nn.Parameter(p.detach().cpu().clone()) for p in m1.parameters()], lr=1e-3)
+    ref_adam.load_state_dict(ck['optimizer'])                                    # the reference trainer's resume_checkpoint does this
+    t1.train_step(inter)
+    m2, t2 = fresh()
+    t2.resume_checkpoint(t1.saved_model_file)
+    assert t2.start_epoch == 1
+    m2.train()
+    t2.train_step(inter)
+    for (n, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert float((a - b).abs().max()) < 1e-6, n
+
+
+def test_annealing_schedule_advances_through_the_graph_path(A):
+    """combine_option 'annealing' (layers.py:889-891): the rate is a host float that changes every forward; graphed_step must not
+    freeze it (such models launch eagerly) and the warm-up of a capture must not advance it."""
+    cfg = O.default_cfg(hidden_dropout_prob=0.0, attn_dropout_prob=0.0, combine_option='annealing', n_layers=2)
+    V, B, L = 300, 16, 50
+    params = O.init_params(cfg, V, seed=4)
+    seq, ln, pos = O.synth_batch(B, L, V, seed=5)
+    res = []
+    for graph in (False, True):
+        config = make_config(A, cfg, cuda_graph=graph)
+        model = A.ACSASRec(config, DS(V)).to('cuda')
+        model.load_state_dict({k: v.cuda() for k, v in params.items()})
+        for layer in model.trm_encoder.layer:
+            layer.anneal_step = 70000                                            # exp(-0.7): far from both ends
+        model._debug_rand = {(l, 'noise'): torch.zeros(B, cfg['n_heads'], L, L).cuda() for l in range(cfg['n_layers'])}
+        trainer = A.ACSASRecTrainer(config, model)
+        model.train()
+        inter = A.Interaction({'item_id_list': seq, 'item_length': ln, 'item_id': pos})
+        losses = []
+        for _ in range(3):
+            la, lc = trainer.graphed_step(inter) if graph else trainer.train_step(inter.to('cuda'))
+            losses.append((float(la), float(lc)))
+        assert [layer.anneal_step for layer in model.trm_encoder.layer] == [70003, 70003]
+        model.eval()
+        with torch.no_grad():
+            trainer.eval_batch((inter.to('cuda'), None, None, pos.cuda()))
+        assert [layer.anneal_step for layer in model.trm_encoder.layer] == [70004, 70004]
+        res.append(losses)
+    for a, b in zip(*res):
+        assert abs(a[0] - b[0]) < 1e-5 * abs(a[0]) and abs(a[1] - b[1]) < 1e-5 * abs(a[1])
+    # and the rate really enters the result: the oracle with the same three rates reproduces the first loss
+    import math
+    rates = [math.exp(-70000 / 100000)] * cfg['n_layers']
+    rnd = O.Rand({(l, 'noise'): torch.zeros(B, cfg['n_heads'], L, L) for l in range(cfg['n_layers'])})
+    la_o, lc_o, _ = O.train_grads(params, cfg, seq, ln, pos, rnd, anneal_rates=rates)
+    assert abs(res[0][0][1] - float(lc_o)) < 1e-4 * abs(float(lc_o))

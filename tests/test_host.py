@@ -211,3 +211,57 @@ def test_evaluator_matches_reference_evaluator_outputs():
         assert set(got) == set(c['result']), name
         for k, v in c['result'].items():
             assert abs(got[k] - v) <= 1.0001e-4, (name, k, got[k], v)          # north_star: Recall@10 / NDCG@10 within 1e-4
+
+
+def test_flat_adam_state_dict_is_torch_adam_format():
+    """FlatAdam <-> torch.optim.Adam checkpoints (trainer.py:718-728 saves optimizer.state_dict(), :733-761 loads it):
+    a reference-written 'optimizer' entry resumes here and ours resumes in the reference trainer."""
+    torch.manual_seed(0)
+    model = A.ACSASRec(cfg_for(n_layers=1, trainable_mask_loss_weight=True), DS(37))
+    ref_model = A.ACSASRec(cfg_for(n_layers=1, trainable_mask_loss_weight=True), DS(37))
+    ref_model.load_state_dict(model.state_dict())
+    # a reference-side optimizer with real state: two torch Adam steps on random gradients (mask_loss_weight gets none)
+    adam = torch.optim.Adam(ref_model.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(2):
+        for n, p in ref_model.named_parameters():
+            p.grad = None if n == 'mask_loss_weight' else torch.randn(p.shape, generator=g)
+        adam.step()
+    sd = adam.state_dict()
+    flat = A.FlatAdam(model, lr=5e-4)
+    flat.load_state_dict(sd)                                  # reference format in
+    assert int(flat.step_count.item()) == 2 and flat.lr == 1e-3
+    for i, p in enumerate(model.parameters()):
+        if i in sd['state']:
+            assert torch.equal(flat._view(flat.exp_avg, p), sd['state'][i]['exp_avg'])
+            assert torch.equal(flat._view(flat.exp_avg_sq, p), sd['state'][i]['exp_avg_sq'])
+        else:
+            assert float(flat._view(flat.exp_avg, p).abs().max()) == 0.0
+    out = flat.state_dict()                                   # reference format out: torch's own Adam accepts it
+    adam2 = torch.optim.Adam(ref_model.parameters(), lr=1.0)
+    adam2.load_state_dict(out)
+    assert adam2.param_groups[0]['lr'] == 1e-3
+    names = [n for n, _ in ref_model.named_parameters()]
+    for i, p in enumerate(ref_model.parameters()):
+        if names[i] == 'mask_loss_weight':
+            continue
+        assert torch.equal(adam2.state[p]['exp_avg'], adam.state[p]['exp_avg'])
+        assert float(adam2.state[p]['step']) == 2.0
+    # shape / count mismatches are errors, not silent mis-assignment
+    bad = {'state': dict(sd['state']), 'param_groups': [dict(sd['param_groups'][0], params=sd['param_groups'][0]['params'][:-1])]}
+    with pytest.raises(ValueError):
+        flat.load_state_dict(bad)
+    bad2 = {'state': {k: dict(v) for k, v in sd['state'].items()}, 'param_groups': sd['param_groups']}
+    bad2['state'][sorted(bad2['state'])[0]]['exp_avg'] = torch.zeros(3)
+    with pytest.raises(ValueError):
+        flat.load_state_dict(bad2)
+    with pytest.raises(ValueError):
+        flat.load_state_dict({'something': 1})
+
+
+def test_config_gpu_id_selects_the_device():
+    c = cfg_for()
+    assert c['device'].type == 'cpu'
+    d = O.default_cfg()
+    d.update(seed=42, learning_rate=1e-3, epochs=1, eval_batch_size=8, train_batch_size=8, topk=[10], metrics=['Hit'], gpu_id=0, use_gpu=False)
+    assert A.Config(model='ACSASRec', config_dict=d)['device'].type == 'cpu'
