@@ -1,0 +1,61 @@
+// Debug tool (not part of the product path): runs ONE tcgen05.mma.kind::tf32 128 x N x 8 on a caller-supplied shared-memory image
+// with caller-supplied raw descriptors and returns the accumulator, so the operand layouts a descriptor combination
+// really addresses can be measured on the device (scripts/umma_probe.py).  TMEM is pre-filled with a sentinel to tell a
+// skipped instruction from one that wrote zeros.
+#include "acsr_common.cuh"
+
+namespace acsr {
+
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restrict__ image, int image_bytes, unsigned long long adesc,
+                                                            unsigned long long bdesc, unsigned int idesc, int ncols, float sentinel,
+                                                            float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < image_bytes / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = image[i];
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = sentinel;
+  for (int cc = 0; cc < 8; ++cc) tmem_st32(t_lane + cc * 32, v);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    const unsigned long long base16 = (unsigned long long)(smem_u32(smem) >> 4);
+    // the start-address fields (low 14 bits) are relative to the image: add the shared-memory base
+    const unsigned long long ad = (adesc & ~0x3FFFull) | (((adesc & 0x3FFFull) + base16) & 0x3FFFull);
+    const unsigned long long bd = (bdesc & ~0x3FFFull) | (((bdesc & 0x3FFFull) + base16) & 0x3FFFull);
+    umma_tf32(tmem_base, ad, bd, idesc, 0);
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int cc = 0; cc < ncols / 32; ++cc) {
+    tmem_ld32(t_lane + cc * 32, v);
+    for (int i = 0; i < 32; ++i) D[row * ncols + cc * 32 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<256>(tmem_base); }
+}
+
+}  // namespace acsr
+
+extern "C" int acsr_debug_umma_probe(const float* image, int image_bytes, unsigned long long adesc, unsigned long long bdesc,
+                                     unsigned int idesc, int ncols, float sentinel, float* D, void* stream) {
+  using namespace acsr;
+  if (image_bytes > 200 * 1024 || ncols > 256 || (ncols & 31)) return ACSR_ERR_ARG;
+  cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  umma_probe_kernel<<<1, 128, 200 * 1024, (cudaStream_t)stream>>>(image, image_bytes, adesc, bdesc, idesc, ncols, sentinel, D);
+  return check_launch("umma_probe");
+}

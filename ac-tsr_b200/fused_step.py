@@ -246,6 +246,8 @@ class FusedTrainStep(object):
         elif self.vp is not None:       # shard-local G^T, reduce-scatter of d_out, dE into the owner's rows
             jb['d_out2'].copy_(self.vp.ce_backward(vst, E, jb['row_scale'], E.grad, table_half=0, n_groups=2))
         else:
+            if jb['Gt'] is None:
+                jb['Gt'] = torch.empty((V, 2 * B), dtype=torch.float32, device=dev)
             LIB.call('acsr_logits_ce_grad', _p(jb['out2']), _p(E), _p(jb['lse']), _p(jb['target2'], torch.int64),
                      _p(jb['row_scale']), 2 * B, V, d, passes, _p(jb['Gt']), 2 * B, st)
             if self.tc_wgrad:          # d_out2 [2B,d] += Gt^T . E : contraction over the catalogue, split over the CTAs

@@ -284,6 +284,7 @@ def ce_grad_matrix_t(out, table, lse, target, row_scale, passes=3):
     return Gt
 
 
+
 def linear_wgrad(dY, X, dW=None, db=None, want_bias=True):
     """dW [N,K] += dY^T.X and db [N] += colsum(dY) with the token axis split over the GPU (acsr_linear_wgrad)."""
     N, K = dY.shape[-1], X.shape[-1]
@@ -392,8 +393,8 @@ class LogitsCEFn(torch.autograd.Function):
         M = out.shape[0]
         per = M // n_groups
         row_scale = (d_loss.to(torch.float32) / per).view(n_groups, 1).expand(n_groups, per).reshape(-1).contiguous()
-        Gt = ce_grad_matrix_t(out, table, lse, target, row_scale, passes)
         V, d = table.shape
+        Gt = ce_grad_matrix_t(out, table, lse, target, row_scale, passes)
         d_out = d_table = None
         pr = []
         if ctx.needs_input_grad[0]:            # d_out [M,d] = Gt^T . E : contraction over the catalogue, split over the CTAs

@@ -335,6 +335,15 @@ int acsr_bpr_loss_bwd(const float* out, const float* table, const int64_t* pos_i
                       const float* row_scale, int M, int d, float gamma, int table_row_begin, int table_row_end, float* d_out,
                       float* d_table, void* stream);
 
+/* ---- vocab-sharded item table (north_star; the reference has only the dense nn.Embedding of acsasrec.py:37) ----
+ * this rank stores table rows [row_lo, row_hi).  gather: out[i] = shard[ids[i] - row_lo] when the row is owned, else 0 (the owners'
+ * answers are summed by a reduce-scatter, so every token gets its row from exactly one rank).  scatter_add: shard_grad[ids[i] -
+ * row_lo] += rows[i] for owned ids != 0 (row 0 is nn.Embedding's padding_idx: no gradient through the gather). */
+int acsr_shard_gather_rows(const int64_t* ids, int64_t n, const float* shard, int64_t row_lo, int64_t row_hi, int d, float* out,
+                           void* stream);
+int acsr_shard_scatter_add_rows(const int64_t* ids, int64_t n, const float* rows, int64_t row_lo, int64_t row_hi, int d,
+                                float* shard_grad, void* stream);
+
 /* ---- K13: fused Adam over one flat fp32 buffer (trainer/trainer.py:614-615,687) ---------
  * torch.optim.Adam semantics (no amsgrad); step_count device int64[1], incremented by the call. */
 int acsr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

@@ -807,3 +807,4 @@ def test_fold_attack_weights(A):
         ref = (x @ Wqkv[i].double().t() + bqkv[i].double()) @ Waqk[i].double().t() + baqk[i].double()
         got = x @ oW[3 + i].cpu().double().t() + ob[3 + i].cpu().double()
         close(got, ref, 2e-5, 'folded attack projection %d' % i)
+
