@@ -193,6 +193,15 @@ class ACSASRec(SequentialRecommender):
         item_seq = interaction[self.ITEM_SEQ]
         item_seq_len = interaction[self.ITEM_SEQ_LEN]
         out, _ = self._encode(item_seq, item_seq_len, need_attacked=False)
+        vp = getattr(self, '_vp', None)
+        if vp is not None and vp.sharded:         # vocab-sharded table: every shard scores all ranks' rows, my rows are gathered back
+            B = out.shape[0]
+            out_all = vp._all_gather(out).reshape(vp.world * B, -1)
+            part = ops.logits_scores(out_all, vp.shard(self.item_embedding.weight).contiguous(), self.logits_passes)
+            padded = part.new_zeros((vp.world * B, vp.per))
+            padded[:, :part.shape[1]] = part
+            mine = vp._all_gather(padded)[:, vp.rank * B:(vp.rank + 1) * B]               # [W, B, per]
+            return None, mine.permute(1, 0, 2).reshape(B, vp.world * vp.per)[:, :self.n_items].contiguous()
         scores = ops.logits_scores(out, self.item_embedding.weight, self.logits_passes)
         return None, scores
 
@@ -202,4 +211,7 @@ class ACSASRec(SequentialRecommender):
         item_seq = interaction[self.ITEM_SEQ]
         item_seq_len = interaction[self.ITEM_SEQ_LEN]
         out, _ = self._encode(item_seq, item_seq_len, need_attacked=False)
+        vp = getattr(self, '_vp', None)
+        if vp is not None:                        # vocab-parallel: partial top-k per shard, all-gather, merge (dist.py)
+            return vp.full_sort_topk(out, self.item_embedding.weight, k, positive)
         return ops.full_sort_topk(out, self.item_embedding.weight, k, positive, self.logits_passes)

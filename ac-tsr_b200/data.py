@@ -127,6 +127,109 @@ class TrainDataLoader(object):
         return cur
 
 
+
+class DeviceTrainDataLoader(object):
+    """TrainDataLoader with the data resident in HBM: the fields the model reads are uploaded once, the
+    epoch permutation is drawn ON the device (torch.randperm on the CUDA generator seeded from the config seed; the reference
+    uses a CPU randperm, interaction.py:293-297, so the order differs the way any two seeds differ), and acsr_batch_gather
+    writes batch `cursor` into a packed device buffer.  The trainer captures gather + cursor advance inside its CUDA graph, so
+    an epoch is nothing but graph replays: no host->device traffic, no host work per step.  Iterating the loader the usual
+    way also works (each batch is gathered eagerly) and yields the same batches, including the ragged last one."""
+
+    device_resident = True
+
+    def __init__(self, config, dataset, shuffle=True, batch_size=None, device=None):
+        from ._lib import LIB
+        from .compat import PackedInteraction
+        self.LIB, self.PackedInteraction = LIB, PackedInteraction
+        self.config, self.dataset, self.shuffle = config, dataset, shuffle
+        self.batch_size = int(batch_size or config['train_batch_size'])
+        self.device = torch.device(device if device is not None else config['device'])
+        if self.device.type != 'cuda':
+            raise ValueError('DeviceTrainDataLoader needs a CUDA device (got %s); use TrainDataLoader for host-side batches' % self.device)
+        f = _model_fields(config)
+        feat = dataset.inter_feat
+        self.fields = list(f)
+        self.seqs = feat[f[0]].to(self.device).contiguous()
+        self.lens = feat[f[1]].to(self.device).contiguous()
+        self.tgts = feat[f[2]].to(self.device).contiguous()
+        neg_field = config['NEG_PREFIX'] + config['ITEM_ID_FIELD']
+        self.negs = feat[neg_field].to(self.device).contiguous() if neg_field in feat else None
+        if self.negs is not None:
+            self.fields.append(neg_field)
+        self.n, self.L = int(self.seqs.shape[0]), int(self.seqs.shape[1])
+        self.perm = torch.arange(self.n, dtype=torch.int64, device=self.device)
+        self.cursor = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(int(config['seed'] if config['seed'] is not None else 0))
+        self.pr = 0
+        self._out = None
+
+    # ---- layout of one packed batch (what the trainer's static input buffer looks like) ----
+    def layout(self, rows=None):
+        B = self.batch_size if rows is None else rows
+        lay, off = [], 0
+        for k, shape in zip(self.fields, [(B, self.L), (B,), (B,), (B,)]):
+            lay.append((k, off, shape))
+            off += int(np.prod(shape))
+        return lay, off
+
+    @property
+    def pr_end(self):
+        return self.n
+
+    @property
+    def full_batches(self):
+        return self.n // self.batch_size
+
+    def __len__(self):
+        return math.ceil(self.n / self.batch_size)
+
+    def new_epoch(self):
+        """draws the epoch's permutation on the device and rewinds the cursor"""
+        if self.shuffle:
+            torch.randperm(self.n, generator=self.gen, device=self.device, out=self.perm)
+        self.cursor.zero_()
+        self.pr = 0
+
+    def gather_into(self, packed, stream=None):
+        """enqueue: packed <- batch `cursor` of the permutation; cursor += 1  (two launches; graph-capturable)"""
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        self.LIB.call('acsr_batch_gather', self.seqs.data_ptr(), self.lens.data_ptr(), self.tgts.data_ptr(),
+                      self.negs.data_ptr() if self.negs is not None else None, self.perm.data_ptr(), self.cursor.data_ptr(), self.n,
+                      self.batch_size, self.L, packed.data_ptr(), st)
+        self.LIB.call('acsr_cursor_advance', self.cursor.data_ptr(), st)
+
+    def tail_batch(self):
+        """the ragged last batch (n % batch_size rows) as a device Interaction, or None"""
+        r = self.n % self.batch_size
+        if r == 0:
+            return None
+        idx = self.perm[self.n - r:]
+        f = {self.fields[0]: self.seqs[idx], self.fields[1]: self.lens[idx], self.fields[2]: self.tgts[idx]}
+        if self.negs is not None:
+            f[self.fields[3]] = self.negs[idx]
+        return Interaction(f)
+
+    def __iter__(self):
+        self.new_epoch()
+        return self
+
+    def __next__(self):
+        if self.pr >= self.n:
+            self.pr = 0
+            raise StopIteration()
+        if self.pr + self.batch_size <= self.n:
+            lay, total = self.layout()
+            out = torch.empty(total, dtype=torch.int64, device=self.device)
+            self.gather_into(out)
+            cur = self.PackedInteraction(out, lay)
+        else:
+            cur = self.tail_batch()
+        self.pr += self.batch_size
+        return cur
+
+
 class FullSortEvalDataLoader(object):
     """general_dataloader.py:246-253: (interaction, history_index=None, positive_u=arange(B), positive_i=item_id)."""
 

@@ -296,9 +296,12 @@ def create_dataset(config):
 
 def data_preparation(config, dataset):
     """data/utils.py:96-150 -> (train_data, valid_data, test_data)"""
-    from .data import TrainDataLoader, FullSortEvalDataLoader
+    from .data import TrainDataLoader, DeviceTrainDataLoader, FullSortEvalDataLoader
     train, valid, test = dataset.build()
     if (config['eval_args'] or {}).get('mode', 'full') != 'full':
         raise NotImplementedError('eval_args.mode: only full-sort evaluation is on the hot path')
-    return (TrainDataLoader(config, train, shuffle=True), FullSortEvalDataLoader(config, valid),
-            FullSortEvalDataLoader(config, test))
+    # training data resident in HBM with the epoch shuffle on the device (f-2) unless `device_resident_data: False`
+    dev = config['device']
+    on_gpu = getattr(dev, 'type', str(dev)) == 'cuda' and config.get('device_resident_data', True)
+    train_loader = DeviceTrainDataLoader(config, train, shuffle=True) if on_gpu else TrainDataLoader(config, train, shuffle=True)
+    return (train_loader, FullSortEvalDataLoader(config, valid), FullSortEvalDataLoader(config, test))

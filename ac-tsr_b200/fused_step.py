@@ -123,7 +123,7 @@ class FusedTrainStep(object):
         nc = ops.logits_num_chunks(2 * B, V)
         loss3 = f(3)              # [CE(calibrated), CE(attacked), final attacked loss]: one buffer, one read-back
         j = dict(pen=torch.zeros(N, dtype=torch.float64, device=dev), out2=f(2 * B, d), partial=f(2 * B, nc, 2), lse=f(2 * B),
-                 tgt=f(2 * B), row_loss=f(2 * B), loss3=loss3, loss=loss3[:2], loss_att=loss3[2:], dpen=f(N), Gt=(f(V, 2 * B) if m.loss_type == 'CE' else None),
+                 tgt=f(2 * B), row_loss=f(2 * B), loss3=loss3, loss=loss3[:2], loss_att=loss3[2:], dpen=f(N), Gt=None,      # [V, 2B] transposed CE gradient: allocated on first use (never under vocab-parallel / BPR)
                  d_out2=f(2 * B, d),
                  target2=torch.empty(2 * B, dtype=torch.int64, device=dev), ce_cnt=torch.zeros(1, dtype=torch.int32, device=dev),
                  neg2=torch.empty(2 * B, dtype=torch.int64, device=dev), row_x=f(2 * B),
@@ -155,7 +155,7 @@ class FusedTrainStep(object):
         E = m.item_embedding.weight
         main = torch.cuda.current_stream()
         # (sequences longer than 64: the attention backward's workspace is one per device, so the branches would race on it)
-        nb = self.n_branches if (self.n_branches > 1 and B % self.n_branches == 0 and L <= 64) else 1
+        nb = self.n_branches if (self.n_branches > 1 and B % self.n_branches == 0 and L <= 64 and self.vp is None) else 1
         Bs = B // nb
         jb = self._joint_buffers(B, dev)
         branches = []
@@ -177,6 +177,8 @@ class FusedTrainStep(object):
                 jb['d_out2'].zero_()
                 for br in branches:
                     bb = br['buf']
+                    if self._sharded():
+                        self._shard_buffers(bb, dev)['d_xrows'].zero_()
                     if self.compact_last:
                         bb['d_ctx'].zero_()
                         bb['d_x'].zero_()
@@ -328,8 +330,16 @@ class FusedTrainStep(object):
         LIB.call('acsr_seq_order', _p(seq, torch.int64), Bs, L, _p(b['order'], torch.int32), so.cuda_stream)
         order_done = torch.cuda.Event()
         order_done.record(so)
-        LIB.call('acsr_embed_ln_dropout_fwd', _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight), _p(m.LayerNorm.bias),
-                 m.LayerNorm.eps, T, L, d, V, p_h, _p(b['me']), rngp, soff + 1, _p(b['x0']), _p(b['st_e']), st)
+        if self._sharded():
+            # the table rows of my tokens live on their owners: ids all-gathered, owners answer, reduce-scatter delivers (dist.py).
+            # The rows land in xrows[1:], and the kernel gathers row t+1 for token t (ids 1..T: no token looks like padding)
+            sb = self._shard_buffers(b, seq.device)
+            _, b['ids_all'] = self.vp.fetch_rows(seq.reshape(-1), E, out=sb['xrows'][1:])
+            LIB.call('acsr_embed_ln_dropout_fwd', _p(sb['iota1'], torch.int64), _p(sb['xrows']), _p(posw), _p(m.LayerNorm.weight),
+                     _p(m.LayerNorm.bias), m.LayerNorm.eps, T, L, d, T + 1, p_h, _p(b['me']), rngp, soff + 1, _p(b['x0']), _p(b['st_e']), st)
+        else:
+            LIB.call('acsr_embed_ln_dropout_fwd', _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight), _p(m.LayerNorm.bias),
+                     m.LayerNorm.eps, T, L, d, V, p_h, _p(b['me']), rngp, soff + 1, _p(b['x0']), _p(b['st_e']), st)
         x = b['x0']
         b['xs'] = []
         act_id = ops.ACT_IDS[m.hidden_act]
@@ -575,9 +585,17 @@ class FusedTrainStep(object):
             if l > 0:
                 d_out, d_x = d_x, d_out                       # this layer's input gradient is the next one's output gradient
         main.wait_event(dE_done)                              # the dE GEMM is a plain read-modify-write of the table gradient
-        LIB.call('acsr_embed_ln_dropout_bwd', _p(d_x[:T]), _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight),
-                 _p(b['st_e']), T, L, d, V, p_h, _p(b['me']), rngp, soff + 1, _p(E.grad), _p(posw.grad if posw is not None else None),
-                 _p(m.LayerNorm.weight.grad), _p(m.LayerNorm.bias.grad), st)
+        if self._sharded():
+            # per-token gradient rows (LayerNorm backward), then home to the owners of the table rows (padding id 0 gets none)
+            sb = self._shard_buffers(b, seq.device)
+            LIB.call('acsr_embed_ln_dropout_bwd', _p(d_x[:T]), _p(sb['iota1'], torch.int64), _p(sb['xrows']), _p(posw), _p(m.LayerNorm.weight),
+                     _p(b['st_e']), T, L, d, T + 1, p_h, _p(b['me']), rngp, soff + 1, _p(sb['d_xrows']),
+                     _p(posw.grad if posw is not None else None), _p(m.LayerNorm.weight.grad), _p(m.LayerNorm.bias.grad), st)
+            self.vp.scatter_grad_rows(b['ids_all'], sb['d_xrows'][1:], E.grad)
+        else:
+            LIB.call('acsr_embed_ln_dropout_bwd', _p(d_x[:T]), _p(seq, torch.int64), _p(E), _p(posw), _p(m.LayerNorm.weight),
+                     _p(b['st_e']), T, L, d, V, p_h, _p(b['me']), rngp, soff + 1, _p(E.grad), _p(posw.grad if posw is not None else None),
+                     _p(m.LayerNorm.weight.grad), _p(m.LayerNorm.bias.grad), st)
         if side is not None:
             main.wait_stream(side)                            # join: every weight gradient of this branch landed
 
@@ -628,6 +646,18 @@ class FusedTrainStep(object):
             wg.append(ops.wgrad_problem(dY, X, rows, N, K, dW, db))
         else:
             LIB.call('acsr_linear_wgrad', _p(dY), _p(X), rows, N, K, _p(dW), _p(db), fork())
+
+    def _sharded(self):
+        return self.vp is not None and self.vp.sharded
+
+    def _shard_buffers(self, b, dev):
+        """buffers of the sharded-table row exchange of one branch: fetched rows / their gradients (row 0 unused), ids 1..T"""
+        if 'shard' not in b:
+            T, d = b['T'], self.m.hidden_size
+            b['shard'] = dict(xrows=torch.zeros((T + 1, d), dtype=torch.float32, device=dev),
+                              d_xrows=torch.zeros((T + 1, d), dtype=torch.float32, device=dev),
+                              iota1=torch.arange(1, T + 1, dtype=torch.int64, device=dev))
+        return b['shard']
 
     def _folded_buffers(self, l, dev):
         key = ('folded', l)

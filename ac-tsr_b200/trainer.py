@@ -112,7 +112,7 @@ class FlatAdam(object):
         off = self.offsets[id(p)]
         return flat[off:off + p.numel()].view(p.shape)
 
-    def state_dict(self):
+    def state_dict(self, gather=None):
         """torch.optim.Adam's format (trainer.py:718-728 saves `self.optimizer.state_dict()`): per-parameter step / exp_avg /
         exp_avg_sq indexed by the position in model.parameters(), one param group -- a checkpoint written here resumes in
         the reference trainer and vice versa."""
@@ -120,14 +120,16 @@ class FlatAdam(object):
         state = {}
         if step > 0:
             for i, p in enumerate(self.params):
-                state[i] = {'step': torch.tensor(float(step)), 'exp_avg': self._view(self.exp_avg, p).detach().cpu().clone(),
-                            'exp_avg_sq': self._view(self.exp_avg_sq, p).detach().cpu().clone()}
+                ea, es = self._view(self.exp_avg, p).detach(), self._view(self.exp_avg_sq, p).detach()
+                if gather is not None:            # vocab-sharded item table: moments gathered into the reference layout
+                    ea, es = gather(p, ea), gather(p, es)
+                state[i] = {'step': torch.tensor(float(step)), 'exp_avg': ea.cpu().clone(), 'exp_avg_sq': es.cpu().clone()}
         group = {'lr': self.lr, 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': self.weight_decay, 'amsgrad': False,
                  'maximize': False, 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None,
                  'params': list(range(len(self.params)))}
         return {'state': state, 'param_groups': [group]}
 
-    def load_state_dict(self, sd):
+    def load_state_dict(self, sd, scatter=None):
         """accepts torch.optim.Adam's state_dict (a reference checkpoint's 'optimizer' entry) or the round-1 flat format"""
         if sd.get('flat_adam'):                       # checkpoints written by the first version of this trainer
             if sd['exp_avg'].numel() != self.exp_avg.numel():
@@ -149,6 +151,8 @@ class FlatAdam(object):
             if st is None:                            # parameter that never received a gradient (torch keeps no state for it)
                 continue
             p = self.params[pos]
+            if scatter is not None:               # vocab-sharded item table: keep this rank's rows of the full-size moments
+                st = dict(st, exp_avg=scatter(p, st['exp_avg']), exp_avg_sq=scatter(p, st['exp_avg_sq']))
             if tuple(st['exp_avg'].shape) != tuple(p.shape):
                 raise ValueError('optimizer state %s has shape %s, parameter %d has %s' % (key, tuple(st['exp_avg'].shape), pos, tuple(p.shape)))
             self._view(self.exp_avg, p).copy_(st['exp_avg'])
@@ -192,6 +196,7 @@ class ACSASRecTrainer(object):
         self.use_graph = bool(cfg_get(config, 'cuda_graph', True))
         self.fused_topk = bool(cfg_get(config, 'fused_topk', True))
         self._graph = None
+        self._dgraph = None
         self._eval_graphs = {}
         self.dp_world = 1
         self.fused = None
@@ -230,9 +235,7 @@ class ACSASRecTrainer(object):
         if self.fused is not None:
             attacked_loss, calibrated_loss = self.fused(interaction)      # both cotangent streams in one pass
             if self.dp_world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(self.optimizer.flat_grad)
-                self.optimizer.flat_grad.mul_(1.0 / self.dp_world)
+                self._allreduce_grads()
             self.optimizer.step()
             return attacked_loss.detach(), calibrated_loss.detach()
         self.optimizer.zero_grad()
@@ -245,30 +248,69 @@ class ACSASRecTrainer(object):
         for p in self.model.parameters():
             p.requires_grad = True
         if self.dp_world > 1:               # batch data-parallel: average the flat gradient over ranks (NCCL / NVLink)
-            import torch.distributed as dist
-            dist.all_reduce(self.optimizer.flat_grad)
-            self.optimizer.flat_grad.mul_(1.0 / self.dp_world)
+            self._allreduce_grads()
         if self.clip_grad_norm:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
         self.optimizer.step()
         return attacked_loss.detach(), calibrated_loss.detach()
 
-    def enable_data_parallel(self, vocab_parallel=False):
-        """One process per GPU, replicated parameters: broadcast rank 0's weights, then all-reduce gradients every step.
-        vocab_parallel=True additionally splits the full-catalogue logits/CE (and top-k) by item rows across ranks
-        (dist.VocabParallel: all-gather of `out`, all-gather of per-row (max, sum-exp), reduce-scatter of d_out)."""
+    def enable_data_parallel(self, vocab_parallel=False, shard_table=None):
+        """One process per GPU: broadcast rank 0's weights, then all-reduce gradients every step (batch data-parallel).
+        vocab_parallel=True additionally splits the full-catalogue logits / CE / top-k by item rows across ranks
+        (dist.VocabParallel: all-gather of `out`, all-gather of per-row (max, sum-exp, target logit), reduce-scatter of d_out).
+        shard_table=True (default for catalogues above the break-even 2*W*B*L rows, see dist.py) also shards the STORAGE: this
+        rank keeps rows [lo, hi) of the item table, their gradient and their Adam moments; the embedding rows of its own tokens
+        are exchanged every step and the data-parallel all-reduce shrinks to the encoder parameters."""
         import torch.distributed as dist
         if not isinstance(self.optimizer, FlatAdam):
             raise ValueError('data-parallel training needs the flat Adam optimizer')
         self.dp_world = dist.get_world_size()
         dist.broadcast(self.optimizer.flat_param, src=0)
         self.vp = None
-        if vocab_parallel:
-            if self.fused is None:
-                raise ValueError('vocab-parallel logits need the fused step (loss_type CE)')
-            from .dist import VocabParallel, CudaCompute
-            self.vp = VocabParallel(self.model.n_items, compute=CudaCompute(self.model.logits_passes))
-            self.fused.vp = self.vp
+        if not vocab_parallel:
+            return
+        if self.fused is None or self.model.loss_type != 'CE':
+            raise ValueError('vocab-parallel logits need the fused step with loss_type CE')
+        from .dist import VocabParallel, CudaCompute
+        m = self.model
+        if shard_table is None:
+            L = int(cfg_get(self.config, 'MAX_ITEM_LIST_LENGTH', 50))
+            shard_table = m.n_items > 2 * self.dp_world * int(self.config['train_batch_size']) * L
+        self.vp = VocabParallel(m.n_items, compute=CudaCompute(m.logits_passes), sharded=bool(shard_table))
+        if shard_table:
+            # swap the replicated table for this rank's shard and rebuild the flat optimizer state around it
+            full = m.item_embedding.weight.detach()
+            shard = self.vp.make_shard(full)
+            step = int(self.optimizer.step_count.item())
+            if step != 0:
+                raise ValueError('shard the item table before the first optimisation step (or resume from a checkpoint afterwards)')
+            m.item_embedding.weight = torch.nn.Parameter(shard)
+            del full
+            self.optimizer = self._build_optimizer()
+            from .fused_step import FusedTrainStep
+            self.fused = FusedTrainStep(m, self.optimizer)
+            m._fused_step = self.fused
+            self._graph, self._eval_graphs = None, {}
+            torch.cuda.empty_cache()
+        self.fused.vp = self.vp
+        m._vp = self.vp                           # eval: sharded top-k (ACSASRec.full_sort_topk / full_sort_predict)
+
+    def _allreduce_grads(self):
+        """average the gradients over the ranks (NCCL over NVLink).  With a sharded item table its gradient shard is already the
+        owner's sum over all ranks' rows: only the other (replicated, encoder) parameters are all-reduced."""
+        import torch.distributed as dist
+        g = self.optimizer.flat_grad
+        if self.vp is not None and self.vp.sharded:
+            E = self.model.item_embedding.weight
+            a = self.optimizer.offsets[id(E)]
+            b = a + (E.numel() + 63) // 64 * 64
+            if a > 0:
+                dist.all_reduce(g[:a])
+            if b < g.numel():
+                dist.all_reduce(g[b:])
+        else:
+            dist.all_reduce(g)
+        g.mul_(1.0 / self.dp_world)
 
     def train_step(self, interaction):
         """One optimisation step on a device-resident Interaction (eager launch path)."""
@@ -285,31 +327,60 @@ class ACSASRecTrainer(object):
             f.append(m.NEG_ITEM_ID)
         return f
 
-    def _capture(self, interaction):
+    def _capture(self, interaction=None, loader=None):
+        """capture the whole step as one CUDA graph.  interaction: the batch arrives by a copy into the static input buffers
+        before each replay; loader (data.DeviceTrainDataLoader): the batch is gathered from the HBM-resident data by the first
+        two nodes of the graph itself (acsr_batch_gather + acsr_cursor_advance) -- a replay needs no input at all."""
         dev = self.device
         # static input buffers: one flat buffer with the fields as views, so a packed host batch arrives as ONE copy
-        lay, total = PackedInteraction.layout_of({k: interaction[k] for k in self._fields()})
+        if loader is not None:
+            lay, total = loader.layout()
+        else:
+            lay, total = PackedInteraction.layout_of({k: interaction[k] for k in self._fields()})
         static_inter = PackedInteraction(torch.empty(total, dtype=torch.int64, device=dev), lay)
         static = {k: static_inter[k] for k in self._fields()}
-        for k in static:
-            static[k].copy_(interaction[k])
+        if loader is None:
+            for k in static:
+                static[k].copy_(interaction[k])
         self.model._runtime(dev)               # creates the device RNG state, so the snapshot below covers it
+
+        def body():
+            if loader is not None:
+                loader.gather_into(static_inter.packed)
+            return self._step_body(static_inter)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm-up on a side stream (allocator + lazy inits), state restored after
             snap = (self.optimizer.flat_param.clone(), self.optimizer.exp_avg.clone(), self.optimizer.exp_avg_sq.clone(),
-                    self.optimizer.step_count.clone(), self.model._rng.state.clone() if self.model._rng else None)
+                    self.optimizer.step_count.clone(), self.model._rng.state.clone() if self.model._rng else None,
+                    loader.cursor.clone() if loader is not None else None)
             for _ in range(2):
-                self._step_body(static_inter)
+                body()
             self.optimizer.flat_param.copy_(snap[0]); self.optimizer.exp_avg.copy_(snap[1])
             self.optimizer.exp_avg_sq.copy_(snap[2]); self.optimizer.step_count.copy_(snap[3])
             if snap[4] is not None:
                 self.model._rng.state.copy_(snap[4])
+            if snap[5] is not None:
+                loader.cursor.copy_(snap[5])
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            la, lc = self._step_body(static_inter)
-        self._graph = dict(graph=g, static=static, static_inter=static_inter, key=self._graph_key(interaction), la=la, lc=lc)
+            la, lc = body()
+        rec = dict(graph=g, static=static, static_inter=static_inter, la=la, lc=lc)
+        if loader is not None:
+            self._dgraph = dict(rec, loader=loader)
+        else:
+            self._graph = dict(rec, key=self._graph_key(interaction))
+
+    def device_loader_step(self, loader):
+        """one optimisation step on the next batch of a data.DeviceTrainDataLoader: a bare graph replay (the batch is gathered
+        from HBM inside the graph; nothing crosses PCIe).  -> (attacked_loss, calibrated_loss) device tensors."""
+        dg = getattr(self, '_dgraph', None)
+        if dg is None or dg['loader'] is not loader:
+            self._capture(loader=loader)
+            dg = self._dgraph
+        dg['graph'].replay()
+        return dg['la'], dg['lc']
 
     def _host_schedule(self):
         """combine_option 'annealing' (layers.py:889-891): the mixing rate exp(-anneal_step / 1e5) is a host float that changes
@@ -348,6 +419,23 @@ class ACSASRecTrainer(object):
         tot_a = torch.zeros((), dtype=torch.float64, device=self.device)
         tot_c = torch.zeros((), dtype=torch.float64, device=self.device)
         graph_ok = self.use_graph and self.fused is not None and isinstance(self.optimizer, FlatAdam) and not self.clip_grad_norm
+        if (getattr(train_data, 'device_resident', False) and graph_ok and not self._host_schedule()
+                and train_data.L <= 64 and train_data.full_batches > 0):
+            # HBM-resident data (f-2): the epoch is graph replays + one eager step for the ragged tail
+            train_data.new_epoch()
+            for batch_idx in range(train_data.full_batches):
+                la, lc = self.device_loader_step(train_data)
+                tot_a += la
+                tot_c += lc
+                if self.nan_check_interval and (batch_idx + 1) % self.nan_check_interval == 0:
+                    self._check_nan(tot_a + tot_c)
+            tail = train_data.tail_batch()
+            if tail is not None:
+                la, lc = self.train_step(tail)
+                tot_a += la
+                tot_c += lc
+            self._check_nan(tot_a + tot_c)
+            return float(tot_a.item()), float(tot_c.item())
         for batch_idx, interaction in enumerate(train_data):
             if graph_ok:
                 la, lc = self.graphed_step(interaction)
@@ -369,12 +457,30 @@ class ACSASRecTrainer(object):
         saved_model_file = kwargs.pop('saved_model_file', self.saved_model_file)
         state = {
             'config': self.config, 'epoch': epoch, 'cur_step': self.cur_step, 'best_valid_score': self.best_valid_score,
-            'state_dict': {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
-            'other_parameter': self.model.other_parameter(), 'optimizer': self.optimizer.state_dict(),
+            'state_dict': self._full_state_dict(),
+            'other_parameter': self.model.other_parameter(), 'optimizer': self.optimizer.state_dict(gather=self._gather_fn()),
         }
         torch.save(state, saved_model_file)
         if verbose:
             self.logger.info('Saving current: %s' % saved_model_file)
+
+    def _sharded(self):
+        return getattr(self, 'vp', None) is not None and self.vp.sharded
+
+    def _gather_fn(self):
+        """-> fn(param, tensor_of_param_shape) -> tensor in the reference layout: the item table's shard (or its moments) is
+        gathered into the full [V, d] table; every rank takes part in the collective"""
+        if not self._sharded():
+            return None
+        E = self.model.item_embedding.weight
+        return lambda p, t: self.vp.gather_full(t) if p is E else t
+
+    def _full_state_dict(self):
+        """the model's state_dict in the reference layout (a sharded item table is gathered: SURVEY section 5, checkpoints)"""
+        sd = {k: v.detach() for k, v in self.model.state_dict().items()}
+        if self._sharded():
+            sd['item_embedding.weight'] = self.vp.gather_full(sd['item_embedding.weight'])
+        return {k: v.cpu().clone() for k, v in sd.items()}
 
     def _load_state(self, state_dict):
         with torch.no_grad():               # copy in place: parameters are views of the flat buffer
@@ -383,7 +489,10 @@ class ACSASRecTrainer(object):
             if missing:
                 raise KeyError('missing keys in checkpoint: %s' % sorted(missing))
             for k, v in own.items():
-                v.copy_(state_dict[k])
+                src = state_dict[k]
+                if k == 'item_embedding.weight' and self._sharded():
+                    src = self.vp.make_shard(src.to(v.device))
+                v.copy_(src)
 
     def resume_checkpoint(self, resume_file):
         """trainer.py:733-761."""
@@ -395,7 +504,11 @@ class ACSASRecTrainer(object):
         self.best_valid_score = checkpoint['best_valid_score']
         self._load_state(checkpoint['state_dict'])
         self.model.load_other_parameter(checkpoint.get('other_parameter'))
-        self.optimizer.load_state_dict(checkpoint['optimizer'])
+        scatter = None
+        if self._sharded():
+            E = self.model.item_embedding.weight
+            scatter = lambda p, t: self.vp.make_shard(t.to(E.device)) if p is E else t      # noqa: E731
+        self.optimizer.load_state_dict(checkpoint['optimizer'], scatter=scatter)
         self.logger.info('Checkpoint loaded. Resume training from epoch {}'.format(self.start_epoch))
 
     def fit(self, train_data, valid_data=None, verbose=True, saved=True, show_progress=False, callback_fn=None):

@@ -355,7 +355,7 @@ def run_ours(args):
         ge.build()
     if world > 1:
         dist.barrier()
-    use_graph = (world == 1 or bool(args.dp_graph)) and not (world > 1 and WORKLOAD['V'] >= 500000) and WORKLOAD['L'] <= 64
+    use_graph = (world == 1 or bool(args.dp_graph)) and WORKLOAD['L'] <= 64
     A, cfg, config, model, trainer = build(dev, rank, world, cuda_graph=use_graph)
     vocab_parallel = world > 1 and WORKLOAD['V'] >= 500000     # C4: logits / CE / top-k sharded by catalogue rows over the ranks
     if world > 1:
@@ -410,6 +410,28 @@ def run_ours(args):
     barrier()
     ms_e2e = timed_steps(e2e_step, K, flush)
     barrier()
+    # ---- epoch mode: training data resident in HBM, on-device shuffle, the batch gathered inside the captured step (f-2):
+    # nothing crosses PCIe on the way in; the three losses are still read back every step ----
+    ms_e2e_dev = None
+    if use_graph and world == 1 and trainer.fused is not None:
+        ds = A.data.SyntheticSequentialDataset(config, 64 * B, V, seed=4242)
+        dloader = A.data.DeviceTrainDataLoader(config, ds, shuffle=True)
+        dloader.new_epoch()
+        dstate = [0]
+
+        def epoch_step():
+            if dstate[0] == dloader.full_batches:                      # next epoch: new permutation drawn on the device
+                dloader.new_epoch()
+                dstate[0] = 0
+            trainer.device_loader_step(dloader)
+            dstate[0] += 1
+            loss_pin.copy_(trainer.fused.last_losses, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(3):
+            epoch_step()
+        barrier()
+        ms_e2e_dev = timed_steps(epoch_step, K, flush)
+        barrier()
     # ---- full-sort eval (fused logits + top-k), same batch size ----
     model.eval()
     kmax = WORKLOAD['topk']
@@ -464,6 +486,11 @@ def run_ours(args):
         except Exception:
             pass
         os._exit(0)
+    # ---- the 1M-item catalogue (BASELINE config #4) at this N: item table / logits / CE / top-k vocab-sharded over the ranks
+    # (N = 1: the same model on one GPU, the base of the curve).  All ranks take part.
+    sharded = None
+    if args.workload == 'c2' and args.batch == 0 and not args.no_vocab_sharded:
+        sharded = vocab_sharded_record(A, dev, rank, world, max(10, min(K, 30)), flush)
     if rank != 0:
         shutdown()
         return
@@ -493,6 +520,10 @@ def run_ours(args):
                   'launch': ('CUDA graph replay of the whole step' + (' (NCCL all-reduce captured)' if world > 1 else '')) if use_graph else 'eager launches + NCCL',
                   'gemm': '3xTF32 tcgen05 (fp32-level accuracy), no library GEMM on the step'},
         'e2e': {'value': round(world * B * K / (ms_e2e / 1e3), 1), 'unit': 'seq/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12},
+        'e2e_device_resident': ({'value': round(B * K / (ms_e2e_dev / 1e3), 1), 'unit': 'seq/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 12,
+                                 'how': 'data.DeviceTrainDataLoader: training rows resident in HBM, per-epoch permutation drawn on the device, '
+                                        'batch gathered by the first kernel of the captured step; losses read back every step'}
+                                if ms_e2e_dev is not None else None),
         'gpu_launches': int(round(launches_per_step * K)),
         'clocks': clocks,
         'eval': {'metric': 'AC-SASRec full-sort eval users/s', 'value': round(world * B * K / (ms_eval / 1e3), 1), 'unit': 'users/s',
@@ -507,6 +538,8 @@ def run_ours(args):
         line['parity'] = parity
     if large is not None:
         line['large_batch'] = large
+    if sharded is not None:
+        line['vocab_sharded'] = sharded
     if cpu is not None:
         line['cpu_baseline'] = cpu
         line['cpu_baseline_eval'] = cpu_baseline_eval(cfg, B if args.workload == 'c2' else min(B, 32), L, V, kmax, budget_s=8.0)
@@ -514,6 +547,77 @@ def run_ours(args):
         line['eager_cuda_baseline'] = eager
     guard.emit(json.dumps(line))
     shutdown()
+
+
+def vocab_sharded_record(A, dev, rank, world, K, flush):
+    """BASELINE config #4 (V = 1,000,001, B = 256 per GPU) at `world` GPUs: batch data-parallel encoder, the item table
+    (rows, gradient, Adam moments), the logits / CE and the top-k sharded by item rows (dist.py); weak scaling."""
+    import torch.distributed as dist
+    saved = dict(WORKLOAD)
+    WORKLOAD.clear()
+    WORKLOAD.update(WORKLOADS['c4'])
+    try:
+        B, L, V, kmax = WORKLOAD['B'], WORKLOAD['L'], WORKLOAD['V'], WORKLOAD['topk']
+        _, cfg, config, model, trainer = build(dev, rank, world, cuda_graph=True)
+        if world > 1:
+            trainer.enable_data_parallel(vocab_parallel=True)
+        nb = 4
+        seq, ln, tgt = A.data.synth_sequences(nb * B, L, V, seed=142 + rank)
+        devb = [A.Interaction({'item_id_list': seq[i * B:(i + 1) * B], 'item_length': ln[i * B:(i + 1) * B],
+                               'item_id': tgt[i * B:(i + 1) * B]}).pack(['item_id_list', 'item_length', 'item_id']).to(dev) for i in range(nb)]
+        it = [0]
+
+        def sync():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+
+        def dev_step():
+            trainer.graphed_step(devb[it[0] % nb])
+            it[0] += 1
+
+        def eval_dev():
+            b = devb[it[0] % nb]
+            with torch.no_grad():
+                trainer.eval_batch((b, None, None, b['item_id']))
+            it[0] += 1
+        model.train()
+        for _ in range(3):
+            dev_step()
+        sync()
+        ms = timed_steps(dev_step, K, flush)
+        sync()
+        model.eval()
+        for _ in range(3):
+            eval_dev()
+        sync()
+        ms_eval = timed_steps(eval_dev, K, flush)
+        sync()
+        t = torch.tensor([ms, ms_eval], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_eval = [float(x) for x in t.tolist()]
+        vp = getattr(trainer, 'vp', None)
+        rec = {'workload': workload_string(False), 'n_gpus': world, 'steps': K, 'scaling': 'weak',
+               'value': round(world * B * K / (ms / 1e3), 1), 'unit': 'seq/s', 'ms_per_step': round(ms / K, 4),
+               'eval': {'value': round(world * B * K / (ms_eval / 1e3), 1), 'unit': 'users/s', 'ms_per_batch': round(ms_eval / K, 4)},
+               'storage': ('item table sharded by rows: %d rows (+ gradient + Adam moments) per rank' % vp.per) if (vp is not None and vp.sharded)
+               else ('replicated table' if world > 1 else 'single GPU'),
+               'collectives_per_step': ([] if world == 1 else [
+                   'all-gather item ids [B*L] + reduce-scatter embedding rows [W*B*L, d]', 'all-gather out [2B, d]',
+                   'all-gather (max, sum-exp, target logit) partials', 'reduce-scatter d_out [W*2B, d]',
+                   'all-gather gradient rows [B*L, d]', 'all-reduce encoder gradients (%d floats)' % (trainer.optimizer.flat_grad.numel() - model.item_embedding.weight.numel())]),
+               'launch': 'CUDA graph replay (NCCL collectives captured)'}
+        trainer._graph, trainer._eval_graphs = None, {}
+        del trainer, model
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        return rec
+    finally:
+        WORKLOAD.clear()
+        WORKLOAD.update(saved)
 
 
 def large_batch_record(A, dev, cfg, B, L, V, K, flush):
@@ -671,6 +775,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-parity', action='store_true', help='skip the in-run parity check against the CPU oracle')
     ap.add_argument('--no-large-batch', action='store_true', help='skip the B=2048 sub-record')
+    ap.add_argument('--no-vocab-sharded', action='store_true', help='skip the 1M-item vocab-sharded sub-record')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS), help='c2 = the headline configuration (default)')
     ap.add_argument('--full-len', action='store_true', help='every sequence has the maximum length (worst case) instead of LogNormal lengths')
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the workload')

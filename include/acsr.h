@@ -344,6 +344,16 @@ int acsr_shard_gather_rows(const int64_t* ids, int64_t n, const float* shard, in
 int acsr_shard_scatter_add_rows(const int64_t* ids, int64_t n, const float* rows, int64_t row_lo, int64_t row_hi, int d,
                                 float* shard_grad, void* stream);
 
+/* ---- device-resident training data ----
+ * replaces the per-epoch CPU shuffle + host slicing + per-step host->device copy of data/interaction.py:293-297,
+ * data/dataloader/general_dataloader.py:62-65 and trainer/trainer.py:661.  seqs [n_rows, L], lens / targets / negs [n_rows]
+ * (negs may be NULL) and the epoch permutation perm [n_rows] live in device memory; the batch cursor[0] (rows perm[cursor*B ..
+ * cursor*B + B)) is written in the packed layout [item_id_list | item_length | item_id | neg_item_id] of the captured step's
+ * static input buffer.  acsr_cursor_advance: cursor[0] += 1 (a second node of the captured step). */
+int acsr_batch_gather(const int64_t* seqs, const int64_t* lens, const int64_t* targets, const int64_t* negs, const int64_t* perm,
+                      const int64_t* cursor, int64_t n_rows, int B, int L, int64_t* out_packed, void* stream);
+int acsr_cursor_advance(int64_t* cursor, void* stream);
+
 /* ---- K13: fused Adam over one flat fp32 buffer (trainer/trainer.py:614-615,687) ---------
  * torch.optim.Adam semantics (no amsgrad); step_count device int64[1], incremented by the call. */
 int acsr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

@@ -28,8 +28,18 @@ class TorchCompute(object):
         G[rows, target_local[rows]] -= 1.0
         return (G * row_scale[:, None]).t().contiguous()
 
-    def gt_times_table(self, Gt, table):
+    def grad_gemms(self, Gt, table, row_begin, n_rows, out_all, table_grad):
+        if table_grad is not None:
+            table_grad += Gt[:, row_begin:row_begin + n_rows] @ out_all[row_begin:row_begin + n_rows]
         return Gt.t() @ table
+
+    def gather_rows(self, ids, shard, lo, hi):
+        own = (ids >= lo) & (ids < hi)
+        return shard[(ids - lo).clamp(0, shard.shape[0] - 1)] * own.to(shard.dtype)[:, None]
+
+    def scatter_add_rows(self, ids, rows, lo, hi, shard_grad):
+        own = (ids >= lo) & (ids < hi) & (ids != 0)
+        shard_grad.index_add_(0, (ids - lo)[own], rows[own])
 
     def topk_partial(self, out, table, k, idx_offset, skip_col0):
         s = out @ table.t()
@@ -99,6 +109,31 @@ def _worker(rank, world, port, V, ret):
         rv, ri = torch.topk(s, k, dim=1)
         assert torch.equal(idx, ri) and torch.allclose(val, rv)
         assert torch.equal(rec[:, :-1].bool(), ri == pos.view(-1, 1))
+        # ---- sharded STORAGE: every rank holds only its rows; same losses / gradients / top-k, plus the row exchange ----
+        vs = A.dist.VocabParallel(V, compute=TorchCompute(), align=8, sharded=True)
+        shard = vs.make_shard(E)
+        assert shard.shape[0] == vs.per and torch.equal(vs.gather_full(shard), E)
+        loss_s, st_s = vs.ce_forward(out, shard, tgt, 2)
+        assert torch.allclose(loss_s, want, atol=1e-10)
+        g_shard = torch.zeros_like(shard)
+        d_out_s = vs.ce_backward(st_s, shard, scale, g_shard, table_half=1, n_groups=2)
+        assert torch.allclose(d_out_s, o.grad, atol=1e-10)
+        assert torch.allclose(g_shard[:vs.hi - vs.lo], Eg.grad[vs.lo:vs.hi], atol=1e-10)
+        val_s, idx_s, rec_s = vs.full_sort_topk(out[:B], shard, k, pos)
+        assert torch.equal(idx_s, ri) and torch.allclose(val_s, rv)
+        # embedding rows of my tokens come from their owners; gradient rows go back to them (id 0 = padding gets none)
+        T = 11
+        ids_all_ref = torch.randint(0, V, (world, T))
+        ids_all_ref[:, 0] = 0
+        rows, ids_all = vs.fetch_rows(ids_all_ref[rank], shard)
+        assert torch.equal(ids_all, ids_all_ref) and torch.equal(rows, E[ids_all_ref[rank]])
+        d_rows_all = torch.randn(world, T, d, dtype=torch.float64)
+        g2 = torch.zeros_like(shard)
+        vs.scatter_grad_rows(ids_all, d_rows_all[rank], g2)
+        full = torch.zeros_like(E)
+        keep = ids_all_ref.reshape(-1) != 0
+        full.index_add_(0, ids_all_ref.reshape(-1)[keep], d_rows_all.reshape(-1, d)[keep])
+        assert torch.allclose(g2[:vs.hi - vs.lo], full[vs.lo:vs.hi], atol=1e-12)
         ret[rank] = 'ok'
     finally:
         dist.destroy_process_group()

@@ -485,3 +485,51 @@ def test_annealing_schedule_advances_through_the_graph_path(A):
     rnd = O.Rand({(l, 'noise'): torch.zeros(B, cfg['n_heads'], L, L) for l in range(cfg['n_layers'])})
     la_o, lc_o, _ = O.train_grads(params, cfg, seq, ln, pos, rnd, anneal_rates=rates)
     assert abs(res[0][0][1] - float(lc_o)) < 1e-4 * abs(float(lc_o))
+
+
+def test_device_resident_loader_epoch_equals_host_loader_steps(A):
+    """f-2: the HBM-resident loader (on-device permutation, batch gathered INSIDE the captured step) trains exactly like the
+    same batches fed one by one: every row of the epoch exactly once, same parameters after the epoch (dropout off)."""
+    cfg = O.default_cfg(hidden_dropout_prob=0.0, attn_dropout_prob=0.0, n_layers=1)
+    V, L, B, n = 300, 50, 32, 32 * 5 + 7                      # five full batches + a ragged tail of 7 rows
+    params = O.init_params(cfg, V, seed=2)
+
+    def fresh(graph):
+        config = make_config(A, cfg, train_batch_size=B, cuda_graph=graph, seed=123)
+        ds = A.data.SyntheticSequentialDataset(config, n, V, seed=5)
+        model = A.ACSASRec(config, ds).to('cuda')
+        model.load_state_dict({k: v.cuda() for k, v in params.items()})
+        model._debug_rand = {(l, 'noise'): torch.zeros(B, cfg['n_heads'], L, L).cuda() for l in range(cfg['n_layers'])}
+        trainer = A.ACSASRecTrainer(config, model)
+        model.train()
+        return config, ds, model, trainer
+    config, ds, m1, t1 = fresh(True)
+    loader = A.data.DeviceTrainDataLoader(config, ds, shuffle=True)
+    # iterating the loader yields every row exactly once, in the order of its device permutation
+    seen = torch.cat([b['item_id'].cpu() for b in loader])
+    perm = loader.perm.cpu()
+    assert torch.equal(seen, ds.inter_feat['item_id'][perm]) and sorted(perm.tolist()) == list(range(n))
+    assert not torch.equal(perm, torch.arange(n))
+    # epoch through the trainer: graph replays that gather their own batch + eager tail
+    loader.gen.manual_seed(77)
+    la, lc = t1._train_epoch(loader, 0)
+    assert t1._dgraph is not None and int(loader.cursor.item()) == n // B
+    perm = loader.perm.cpu()
+    # the same batches, one eager step each, from host tensors
+    config2, ds2, m2, t2 = fresh(False)
+    m2._debug_rand = None
+    tot_c = 0.0
+    feat = ds2.inter_feat
+    for i in range(0, n, B):
+        idx = perm[i:i + B]
+        rows = len(idx)
+        m2._debug_rand = {(l, 'noise'): torch.zeros(rows, cfg['n_heads'], L, L).cuda() for l in range(cfg['n_layers'])}
+        inter = A.Interaction({k: feat[k][idx].cuda() for k in ('item_id_list', 'item_length', 'item_id')})
+        _, c = t2.train_step(inter)
+        tot_c += float(c)
+    assert abs(lc - tot_c) < 1e-4 * abs(tot_c), (lc, tot_c)
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert float((a - b).abs().max()) < 2e-5, k
+    # a second epoch draws a new permutation and rewinds the cursor
+    t1._train_epoch(loader, 1)
+    assert not torch.equal(loader.perm.cpu(), perm) and int(loader.cursor.item()) == n // B
