@@ -9,13 +9,14 @@ All arithmetic runs in csrc/libacsr.so (C ABI: include/acsr.h).  No CPU fallback
 
 The directory name contains a hyphen; import it as `ac_tsr_b200` (shim module at the repo root).
 """
-from . import _lib, build, compat, data, dataset, evaluator, layers, ops, trainer, acsasrec, fused_step, dist, quick_start    # noqa: F401
+from . import _lib, build, compat, data, dataset, evaluator, layers, ops, trainer, acsasrec, acbert4rec, fused_step, dist, quick_start    # noqa: F401
 from ._lib import LIB, AcsrError                                                      # noqa: F401
 from .acsasrec import ACSASRec                                                        # noqa: F401
+from .acbert4rec import AcBERT4Rec                                                    # noqa: F401
 from .compat import Config, Interaction, ModelType                                    # noqa: F401
 from .layers import (AttackRMultiHeadAttention, AttackRTransformerEncoder,            # noqa: F401
                      AttackRTransformerLayer, FeedForward)
-from .trainer import ACSASRecTrainer, FlatAdam                                        # noqa: F401
+from .trainer import ACSASRecTrainer, AcBERT4RecTrainer, FlatAdam                     # noqa: F401
 from .dataset import SequentialDataset, create_dataset, data_preparation             # noqa: F401
 from .quick_start import run_recbole                                                  # noqa: F401
 

@@ -76,7 +76,7 @@ __device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem
         bs.gR[(long long)i * L + j] = rfin;
         bs.gA[(long long)i * L + j] = r.A[jj];
       } else {
-        const int t = tri_off(j, LP) - (j & ~3) + i;
+        const int t = mat_row(p, j, LP) + i;
         bs.matRT[t] = rfin;
         bs.matAT[t] = r.A[jj];
       }
@@ -196,7 +196,8 @@ __device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem
       if (!a) continue;
       if (p.ow) {
         const float sg = r.sig[jj];
-        const float de = -sg * (1.0f - sg) * frcp((1.0f - sg) + kOrderEps);     // j <= i branch of layers.py:719
+        // layers.py:719: d/du log(1 - sg + eps) for j <= i; d/du log(sg + eps) for j > i (only in play under the bidirectional mask)
+        const float de = (j > i) ? sg * (1.0f - sg) * frcp(sg + kOrderEps) : -sg * (1.0f - sg) * frcp((1.0f - sg) + kOrderEps);
         const float du = dz[jj] * de;
         rdu += du;
         if (du != 0.f) atomicAdd(bs.colDU + s * LP + j, du);
@@ -212,7 +213,7 @@ __device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem
         bs.gS[s][(long long)i * L + j] = dS[jj];
         bs.gS2[s][(long long)i * L + j] = dS2[jj];
       } else {
-        const int t = tri_off(j, LP) - (j & ~3) + i;
+        const int t = mat_row(p, j, LP) + i;
         bs.matST[s][t] = dS[jj];
         bs.matS2T[s][t] = dS2[jj];
       }
@@ -334,7 +335,7 @@ __device__ __forceinline__ void bwd_row_iter_m(const AttnParams& p, const AttnSm
         if (j < rstride) bufS2[j] = a ? v : 0.f;
         if (a) {
           if (LONG) bs.gS2[s][(long long)i * L + j] = v;
-          else bs.matS2T[s][tri_off(j, LP) - (j & ~3) + i] = v;
+          else bs.matS2T[s][mat_row(p, j, LP) + i] = v;
         }
       }
       __syncwarp();

@@ -41,6 +41,7 @@ struct AttnParams {
   const float *ow, *ob, *dw, *db, *scalar;
   int B, L, H, dh, d;
   int two_level, combine, rich;
+  int bidir;                 // bidirectional attention mask (AcBERT4Rec, get_attention_mask(bidirectional=True)): keys j > i stay in play
   float comb_scalar;
   const float* rich_ratio;
   float p;
@@ -218,6 +219,11 @@ __host__ __device__ __forceinline__ int tri_off(int j, int LP) {
   return j * LP - 8 * a * (a - 1) - 4 * a * b;
 }
 
+// offset of row j of a transposed [j][i] shared-memory matrix such that element i sits at mat_row(...) + i: packed lower
+// triangular for causal attention (i >= j & ~3), dense [L][LP] for the bidirectional mask
+__device__ __forceinline__ int mat_row(const AttnParams& p, int j, int LP) { return p.bidir ? j * LP : tri_off(j, LP) - (j & ~3); }
+__host__ __device__ __forceinline__ int mat_floats(int bidir, int L, int LP) { return bidir ? L * LP : tri_off(L, LP); }
+
 // async copy of rows [0,rows) of one [L, DH] head slice into a padded smem tile; rows [rows, rows_pad) are zeroed
 template <int DH>
 __device__ __forceinline__ void stage_tile(float* dst, const float* __restrict__ src, int b, int h, int L, int d, int rows,
@@ -385,7 +391,7 @@ __device__ __forceinline__ void row_forward(const AttnParams& p, const AttnSmem&
   for (int jj = 0; jj < NJ; ++jj) {
     const int j = jc[jj];
     const bool a = (act >> jj) & 1u;
-    const bool v = a && (j <= i) && (sm.keyok[j] != 0.f);
+    const bool v = a && (p.bidir || j <= i) && (sm.keyok[j] != 0.f);
     valid |= (v ? 1u : 0u) << jj;
     const float msk = v ? 0.f : kMaskNeg;
     r.sig[jj] = 0.f; r.delta[jj] = 0.f;
@@ -529,7 +535,7 @@ __device__ __forceinline__ void row_forward_m(const AttnParams& p, const AttnSme
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int c4 = 0; c4 < DH / 4; c4 += 2) { s0 = dot4(q2i[c4], kj[c4], s0); s1 = dot4(q2i[c4 + 1], kj[c4 + 1], s1); }
-    const bool v = ((act >> jj) & 1u) && (jc[jj] <= i) && (sm.keyok[jc[jj]] != 0.f);
+    const bool v = ((act >> jj) & 1u) && (p.bidir || jc[jj] <= i) && (sm.keyok[jc[jj]] != 0.f);
     zM[jj] = (s0 + s1) * kc.inv_sq + (v ? 0.f : kMaskNeg);
   }
   softmax_row<G, NJ>(zM, act, Msoft);
@@ -591,6 +597,7 @@ static inline int attn_validate(const AttnParams& p, const char* who) {
   ACSR_REQUIRE(p.mq && p.mk && p.mv && p.aq && p.ak && p.item_seq, "%s: NULL input", who);
   ACSR_REQUIRE(p.B > 0 && p.H > 0, "%s: bad B/H", who);
   if (p.L < 1 || p.L > 256) { set_error("%s: L=%d unsupported (1..256)", who, p.L); return ACSR_ERR_UNSUPPORTED; }
+  if (p.bidir && p.L > 64) { set_error("%s: the bidirectional mask is implemented for L <= 64 (L=%d)", who, p.L); return ACSR_ERR_UNSUPPORTED; }
   if (!(p.dh == 8 || p.dh == 16 || p.dh == 32 || p.dh == 64)) {
     set_error("%s: head size %d unsupported (8/16/32/64)", who, p.dh);
     return ACSR_ERR_UNSUPPORTED;
@@ -623,7 +630,7 @@ static inline void attn_fill_common(AttnParams& p, const float* mq, const float*
   p.item_seq = item_seq;
   p.ow = order_w; p.ob = order_b; p.dw = dist_w; p.db = dist_b; p.scalar = scalar;
   p.B = B; p.L = L; p.H = H; p.dh = dh; p.d = H * dh;
-  p.two_level = two_level; p.combine = combine_option; p.rich = rich_mode; p.comb_scalar = comb_scalar; p.rich_ratio = rich_ratio;
+  p.two_level = two_level & 1; p.bidir = (two_level >> 1) & 1; p.combine = combine_option; p.rich = rich_mode; p.comb_scalar = comb_scalar; p.rich_ratio = rich_ratio;
   p.p = p_attn; p.D1 = D1; p.D2 = D2; p.D3 = D3; p.noise = noise; p.rng = (const RngState*)rng; p.stream = rng_stream;
 }
 

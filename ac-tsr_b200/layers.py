@@ -30,10 +30,11 @@ class AttackMask:
 class Runtime:
     """Per-call execution context threaded from the model down to the kernels."""
 
-    def __init__(self, rng=None, rand=None, attacked_last_only=False):
+    def __init__(self, rng=None, rand=None, attacked_last_only=False, bidirectional=False):
         self.rng = rng                  # ops.DeviceRng or None
         self.rand = rand                # explicit masks/noise {key: tensor} (parity tests) or None
         self.attacked_last_only = attacked_last_only
+        self.bidirectional = bidirectional      # get_attention_mask(bidirectional=True) of AcBERT4Rec (abstract_recommender.py:136-143)
 
     def mask(self, key):
         return None if self.rand is None else self.rand.get(key)
@@ -123,7 +124,7 @@ def key_ids_from_mask(attention_mask):
     if attention_mask.dim() == 2:
         return attention_mask if attention_mask.dtype == torch.int64 else attention_mask.to(torch.int64)
     if attention_mask.dim() != 4:
-        raise ValueError('attention_mask must be [B,1,L,L] or [B,L]')
+        raise ValueError('attention_mask must be [B,1,L,L], [B,1,1,L] or [B,L]')
     return (attention_mask[:, 0, -1, :] == 0).to(torch.int64)
 
 
@@ -182,7 +183,8 @@ class AttackRTransformerLayer(nn.Module):
                 rand['D1'] = rand['D2'] = rand['D3'] = None
         want_probs = bool(return_attention_prob or return_all_attention_prob)
         opts = ops.AttnOpts(aa.num_attention_heads, self.two_level, self.combine_option,
-                            self.rich_calibrated_combine if not self.two_level else 'none', p_attn)
+                            self.rich_calibrated_combine if not self.two_level else 'none', p_attn,
+                            bidirectional=bool(getattr(rt, 'bidirectional', False)))
         ctx_att, ctx_cal, pen_sq, probs = ops.AttnCalibFn.apply(
             mq, mk, mv, aq, ak, gate_logit, key_ids,
             aa.order_affine.weight if aa.use_order else None, aa.order_affine.bias if aa.use_order else None,

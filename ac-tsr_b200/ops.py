@@ -178,9 +178,10 @@ def attn_workspace(B, L, H, n_streams, device):
 class AttnOpts:
     """static options of one fused-attention call (mirrors the AttackR* constructor flags)."""
 
-    def __init__(self, n_heads, two_level, combine_option, rich_mode, p_attn):
+    def __init__(self, n_heads, two_level, combine_option, rich_mode, p_attn, bidirectional=False):
         self.n_heads = n_heads
-        self.two_level = int(bool(two_level))
+        # the ABI's `two_level` argument carries two flags: bit 0 two_level, bit 1 bidirectional attention mask (AcBERT4Rec)
+        self.two_level = int(bool(two_level)) | (2 if bidirectional else 0)
         self.combine = COMBINE_IDS[combine_option]
         self.rich = RICH_IDS.get(rich_mode, 0)
         self.p_attn = float(p_attn)
@@ -372,27 +373,61 @@ def linear(x, weight, bias=None):
     return LinearFn.apply(x, weight, bias)
 
 
+class GatherRowsFn(torch.autograd.Function):
+    """rows x[idx] of a [T, d] matrix (AcBERT4Rec: the hidden states of the masked positions, acbert4rec.py:214-222 does it with a
+    one-hot bmm); backward: scatter-add of the gradient rows."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        x = x.contiguous()
+        T, d = x.shape
+        ids = (idx.reshape(-1) + 1).contiguous()          # ids 1..T over a table whose first row is id 1: no id looks like padding
+        out = torch.empty((ids.numel(), d), dtype=torch.float32, device=x.device)
+        LIB.call('acsr_shard_gather_rows', _p(ids, torch.int64), ids.numel(), _p(x), 1, T + 1, d, _p(out), _stream())
+        ctx.save_for_backward(ids)
+        ctx.meta = (T, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (ids,) = ctx.saved_tensors
+        T, d = ctx.meta
+        d_x = torch.zeros((T, d), dtype=torch.float32, device=d_out.device)
+        LIB.call('acsr_shard_scatter_add_rows', _p(ids, torch.int64), ids.numel(), _p(d_out.contiguous()), 1, T + 1, d, _p(d_x), _stream())
+        return d_x, None
+
+
 class LogitsCEFn(torch.autograd.Function):
     """loss[g] = mean CE over row group g of softmax(out.E^T) vs target -- acsasrec.py:117-121.
     Logits never materialise in the forward; the backward writes Gt once, then d_E = Gt.out and d_out = Gt^T.E
     (reduction over the catalogue) as two problems of one tcgen05 launch (acsr_gemm_batch)."""
 
     @staticmethod
-    def forward(ctx, out, table, target, n_groups, passes):
+    def forward(ctx, out, table, target, n_groups, passes, row_weight=None):
+        """row_weight [M] (optional): loss[g] = sum(w * row_loss) / sum(w) over the group (AcBERT4Rec's masked-item CE,
+        acbert4rec.py:198-205); default: the plain mean."""
         out, table, target = out.contiguous(), table.contiguous(), target.contiguous()
         part = ce_partial(out, table, passes)
-        lse, _, _, loss = ce_finalize(part, out, table, target, n_groups)
-        ctx.save_for_backward(out, table, target, lse)
+        lse, _, row_loss, loss = ce_finalize(part, out, table, target, n_groups)
+        wn = None
+        if row_weight is not None:
+            w = row_weight.to(torch.float32).view(n_groups, -1)
+            wn = (w / w.sum(1, keepdim=True)).reshape(-1).contiguous()      # normalised weights: d loss[g] / d row_loss
+            loss = (row_loss.view(n_groups, -1) * wn.view(n_groups, -1)).sum(1)
+        ctx.save_for_backward(out, table, target, lse, wn)
         ctx.meta = (n_groups, passes)
         return loss
 
     @staticmethod
     def backward(ctx, d_loss):
-        out, table, target, lse = ctx.saved_tensors
+        out, table, target, lse, wn = ctx.saved_tensors
         n_groups, passes = ctx.meta
         M = out.shape[0]
         per = M // n_groups
-        row_scale = (d_loss.to(torch.float32) / per).view(n_groups, 1).expand(n_groups, per).reshape(-1).contiguous()
+        if wn is not None:
+            row_scale = (d_loss.to(torch.float32).view(n_groups, 1) * wn.view(n_groups, per)).reshape(-1).contiguous()
+        else:
+            row_scale = (d_loss.to(torch.float32) / per).view(n_groups, 1).expand(n_groups, per).reshape(-1).contiguous()
         V, d = table.shape
         Gt = ce_grad_matrix_t(out, table, lse, target, row_scale, passes)
         d_out = d_table = None
@@ -405,7 +440,7 @@ class LogitsCEFn(torch.autograd.Function):
             pr.append(gemm_problem(Gt, out, d_table, V, d, M, b_strides=(1, d, 0, M)))
         if pr:
             gemm_batch(pr)
-        return d_out, d_table, None, None, None
+        return d_out, d_table, None, None, None, None
 
 
 

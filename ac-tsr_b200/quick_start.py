@@ -9,11 +9,12 @@ import numpy as np
 import torch
 
 from .acsasrec import ACSASRec
+from .acbert4rec import AcBERT4Rec
 from .compat import Config
 from .dataset import create_dataset, data_preparation
-from .trainer import ACSASRecTrainer
+from .trainer import ACSASRecTrainer, AcBERT4RecTrainer
 
-_MODELS = {'ACSASRec': (ACSASRec, ACSASRecTrainer)}
+_MODELS = {'ACSASRec': (ACSASRec, ACSASRecTrainer), 'AcBERT4Rec': (AcBERT4Rec, AcBERT4RecTrainer)}
 
 
 def init_seed(seed, reproducibility):

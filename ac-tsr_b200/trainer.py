@@ -200,7 +200,7 @@ class ACSASRecTrainer(object):
         self._eval_graphs = {}
         self.dp_world = 1
         self.fused = None
-        if (bool(cfg_get(config, 'fused_step', True)) and isinstance(self.optimizer, FlatAdam)
+        if (bool(cfg_get(config, 'fused_step', True)) and isinstance(self.optimizer, FlatAdam) and type(model).__name__ == 'ACSASRec'
                 and getattr(model, 'loss_type', None) in ('CE', 'BPR') and not self.clip_grad_norm):
             from .fused_step import FusedTrainStep
             self.fused = FusedTrainStep(model, self.optimizer)
@@ -651,3 +651,9 @@ class ACSASRecTrainer(object):
         recs = [self.eval_batch(b) for b in eval_data]
         rec = torch.cat(recs, dim=0).cpu().numpy()
         return self.evaluator.evaluate(rec)
+
+
+class AcBERT4RecTrainer(ACSASRecTrainer):
+    """trainer.py:1046-1048: AcBERT4Rec trains with the same adversarial two-loss step (the routed double backward of
+    trainer.py:672-686, here through the autograd Functions over the same kernels) and the same full-sort evaluation."""
+    pass

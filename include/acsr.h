@@ -89,6 +89,10 @@ int acsr_embed_ln_dropout_bwd(const float* d_out, const int64_t* item_seq, const
  * for the penalty, their context rows are not written, and in the backward their d_ctx rows are taken as zero. */
 int acsr_seq_order(const int64_t* item_seq, int B, int L, int32_t* order, void* stream);
 #define ACSR_ATTN_TWO_LEVEL 1
+/* second bit of the `two_level` argument: bidirectional attention mask, i.e. get_attention_mask(item_seq, bidirectional=True)
+ * of model/abstract_recommender.py:136-143 as AcBERT4Rec uses it (acbert4rec.py:168): only padded KEYS are masked, query
+ * row i sees keys j > i too (both branches of the order calibrator, layers.py:715-719, are then in play).  L <= 64. */
+#define ACSR_ATTN_BIDIRECTIONAL 2
 #define ACSR_ATTN_COMBINE_GATE 0
 #define ACSR_ATTN_COMBINE_FIXED 1
 #define ACSR_ATTN_COMBINE_ANNEAL 2

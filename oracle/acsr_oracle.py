@@ -25,6 +25,7 @@ Reference lines each function follows (relative to /root/reference/recbole):
   forward            model/sequential_recommender/acsasrec.py:86-104
   calculate_loss     model/sequential_recommender/acsasrec.py:107-144 (CE and BPR branches; model/loss.py:21-47)
   predict/full_sort  model/sequential_recommender/acsasrec.py:146-164
+  bert_*             model/sequential_recommender/acbert4rec.py:152-160, 162-179, 198-245, 260-267 (AcBERT4Rec)
   train_grads        trainer/trainer.py:660-687 (two backward passes routed by name)
   full_sort_topk     trainer/trainer.py:941-942, evaluator/collector.py:145-153
   metrics            evaluator/metrics.py:62-64,88-96,159-160,186-202; base_metric.py:65-80
@@ -116,11 +117,12 @@ def act_fn(name):
     raise KeyError(name)
 
 
-def additive_mask(item_seq):
-    """[B,1,L,L]: 0 where key j is not padding and j<=i, else -10000."""
+def additive_mask(item_seq, bidirectional=False):
+    """[B,1,L,L]: 0 where key j is not padding and (j<=i, unless bidirectional), else -10000  (abstract_recommender.py:136-143)."""
     B, L = item_seq.shape
     keep = (item_seq != 0).view(B, 1, 1, L).expand(B, 1, L, L)
-    keep = torch.tril(keep)
+    if not bidirectional:
+        keep = torch.tril(keep)
     return torch.where(keep, 0.0, MASK_NEG)
 
 
@@ -245,18 +247,24 @@ def ac_layer(x, mask, params, cfg, l, rnd, anneal_rate=None, want_probs=False):
     return out_att, out_cal, r['M']
 
 
-def forward(params, cfg, item_seq, item_len, rnd=None, anneal_rates=None, want_probs=False):
-    """-> attacked[B,d], calibrated[B,d], [M_l] (acsasrec.py:86-104)."""
+def encode(params, cfg, item_seq, rnd=None, anneal_rates=None, want_probs=False, bidirectional=False):
+    """-> attacked[B,L,d], calibrated[B,L,d] of the last layer, [M_l]: embedding + LayerNorm + dropout + the encoder stack."""
     rnd = rnd or Rand()
     pos = params.get('position_embedding.weight') if cfg.get('use_position_embedding') else None
     x = embed_ln_dropout(item_seq, params['item_embedding.weight'], params['LayerNorm.weight'],
                          params['LayerNorm.bias'], cfg['layer_norm_eps'], rnd, pos)
-    mask = additive_mask(item_seq).to(x.dtype)
+    mask = additive_mask(item_seq, bidirectional).to(x.dtype)
     Ms, att = [], None
     for l in range(cfg['n_layers']):
         ar = None if anneal_rates is None else anneal_rates[l]
         att, x, M = ac_layer(x, mask, params, cfg, l, rnd, ar, want_probs)
         Ms.append(M)
+    return att, x, Ms
+
+
+def forward(params, cfg, item_seq, item_len, rnd=None, anneal_rates=None, want_probs=False):
+    """-> attacked[B,d], calibrated[B,d], [M_l] (acsasrec.py:86-104)."""
+    att, x, Ms = encode(params, cfg, item_seq, rnd, anneal_rates, want_probs)
     B = item_seq.shape[0]
     rows = torch.arange(B, device=item_seq.device)
     return att[rows, item_len - 1], x[rows, item_len - 1], Ms
@@ -289,6 +297,57 @@ def calculate_loss(params, cfg, item_seq, item_len, pos_items, rnd=None, anneal_
     l_att = -cross_entropy(att, E, pos_items) + pen * w
     l_cal = cross_entropy(cal, E, pos_items)
     return l_att, l_cal
+
+
+# ---- AcBERT4Rec (acbert4rec.py:11-267): bidirectional mask, masked-item CE over table[:n_items] ---------------- #
+def bert_calculate_loss(params, cfg, masked_seq, pos_items, masked_index, rnd=None, anneal_rates=None):
+    """acbert4rec.py:207-245 given the masked sequence of reconstruct_train_data -> (final_attacked_loss, calibrated_loss)."""
+    att, cal, Ms = encode(params, cfg, masked_seq, rnd, anneal_rates, bidirectional=True)
+    B, L = masked_seq.shape
+    rows = torch.arange(B, device=masked_seq.device).view(B, 1)
+    E = params['item_embedding.weight'][:-1]                       # the last row is the mask token (acbert4rec.py:200)
+    targets = (masked_index > 0).to(att.dtype).view(-1)
+
+    def loss_of(h):
+        seq_out = h[rows, masked_index].reshape(-1, h.shape[-1])   # one-hot bmm of acbert4rec.py:214-222 == a gather
+        logits = seq_out @ E.t()
+        ce = torch.logsumexp(logits, -1) - logits[torch.arange(seq_out.shape[0], device=h.device), pos_items.reshape(-1)]
+        return (ce * targets).sum() / targets.sum()
+    pens = [torch.sqrt(torch.sum((1 - (M['M'] if isinstance(M, dict) else M)) ** 2)) for M in Ms]
+    w = params['mask_loss_weight'][0] if cfg.get('trainable_mask_loss_weight') else cfg['mask_loss_weight']
+    return -loss_of(att) + torch.stack(pens).mean() * w, loss_of(cal)
+
+
+def bert_test_sequence(item_seq, item_len, mask_token):
+    """acbert4rec.py:152-160: one more position, the mask token at index item_len."""
+    seq = torch.cat((item_seq, torch.zeros(item_seq.shape[0], 1, dtype=item_seq.dtype)), 1)
+    seq[torch.arange(seq.shape[0]), item_len] = mask_token
+    return seq
+
+
+def bert_full_sort_scores(params, cfg, item_seq, item_len, rnd=None):
+    """acbert4rec.py:260-267 -> (attacked_scores, scores) [B, n_items]."""
+    E = params['item_embedding.weight']
+    seq = bert_test_sequence(item_seq, item_len, E.shape[0] - 1)
+    att, cal, _ = encode(params, cfg, seq, rnd, bidirectional=True)
+    rows = torch.arange(seq.shape[0])
+    return att[rows, item_len] @ E[:-1].t(), cal[rows, item_len] @ E[:-1].t()
+
+
+def bert_train_grads(params, cfg, masked_seq, pos_items, masked_index, rnd=None, anneal_rates=None):
+    """the two routed backward passes of trainer.py:672-686 for AcBERT4Rec -> (l_att, l_cal, {name: grad})."""
+    p = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in params.items())
+    l_att, l_cal = bert_calculate_loss(p, cfg, masked_seq, pos_items, masked_index, rnd, anneal_rates)
+    names = list(p)
+    g_cal = torch.autograd.grad(l_cal, [p[n] for n in names], retain_graph=True, allow_unused=True)
+    g_att = torch.autograd.grad(l_att, [p[n] for n in names], allow_unused=True)
+    grads = {}
+    for n, gc, ga in zip(names, g_cal, g_att):
+        g = ga if any(s in n for s in ATTACK_KEYS) else gc
+        if n == 'mask_loss_weight':
+            g = None
+        grads[n] = torch.zeros_like(p[n]) if g is None else g.detach()
+    return l_att.detach(), l_cal.detach(), grads
 
 
 ATTACK_KEYS = ('attack_key_transform', 'attack_query_transform')   # trainer.py:673

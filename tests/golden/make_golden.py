@@ -181,6 +181,107 @@ def make_case(name, V, B, seed, train, k=50, **cfgkw):
     print(name, os.path.getsize(path) // 1024, 'KB')
 
 
+def make_bert_case(name, V, B, seed, train, k=50, **cfgkw):
+    """AcBERT4Rec (acbert4rec.py): bidirectional mask, masked-item CE.  The host-side masking of reconstruct_train_data
+    (python `random`) is recorded, so the case pins both the masking procedure (random.seed given) and the arithmetic."""
+    import random
+    from oracle.acsr_oracle import synth_batch
+    import_reference()
+    from recbole.model.sequential_recommender.acbert4rec import AcBERT4Rec
+    from recbole.data.interaction import Interaction
+    cfg = base_config(**cfgkw)
+    cfg['mask_ratio'] = cfgkw.get('mask_ratio', 0.2)
+    L = cfg['MAX_ITEM_LIST_LENGTH']
+    torch.manual_seed(seed)
+    model = AcBERT4Rec(cfg, FakeDataset(V))
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('.bias'):
+                p.add_(torch.randn(p.shape, generator=g) * 0.02)
+            if 'LayerNorm.weight' in n:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    seq, ln, pos = synth_batch(B, L, V, seed=seed + 2)
+    ln[0] = L - 1                               # eval appends one position: keep room for the mask token (acbert4rec.py:152-160)
+    seq[0] = torch.randint(1, V, (L,), generator=g)
+    seq[0, L - 1] = 0
+    ln = ln.clamp(max=L - 1)
+    seq[torch.arange(L).view(1, L) >= ln.view(B, 1)] = 0
+    inter = Interaction({'item_id_list': seq, 'item_length': ln, 'item_id': pos})
+    out = {'V': V, 'B': B, 'k': min(k, V - 1), 'train': int(train), 'seed': seed, 'bert': 1,
+           'item_id_list': seq.numpy(), 'item_length': ln.numpy(), 'item_id': pos.numpy()}
+    for kk, vv in cfgkw.items():
+        out['cfg.' + kk] = np.array(vv)
+    out['cfg.mask_ratio'] = np.array(cfg['mask_ratio'])
+    for n, p in model.state_dict().items():
+        out['param.' + n] = p.detach().numpy().copy()
+    model.train(train)
+    N = cfg['n_layers']
+    if train:
+        captured = []
+        orig = model.reconstruct_train_data
+
+        def wrap(x):
+            r = orig(x)
+            captured.append(r)
+            return r
+        model.reconstruct_train_data = wrap
+        random.seed(seed + 5)
+        with Recorder(seed + 3) as rec:
+            l_att, l_cal = model.calculate_loss(inter)
+        masked_seq, pos_items, neg_items, masked_index = captured[0]
+        out['masked_seq'] = masked_seq.numpy(); out['pos_items'] = pos_items.numpy()
+        out['neg_items'] = neg_items.numpy(); out['masked_index'] = masked_index.numpy()
+        out['random_seed'] = seed + 5
+        assert len(rec.masks) == 1 + 7 * N, len(rec.masks)
+        out['rand.emb'] = rec.masks[0].numpy().astype(np.uint8)
+        for l in range(N):
+            for j, key in enumerate(('D1', 'D2', 'D3', 'D4', 'D5', 'D6', 'D7')):
+                out['rand.%d.%s' % (l, key)] = rec.masks[1 + 7 * l + j].numpy().astype(np.uint8)
+        for l in range(N):
+            out['rand.%d.noise' % l] = rec.noises[l].numpy()
+        out['loss_att'] = l_att.detach().numpy()
+        out['loss_cal'] = l_cal.detach().numpy()
+
+        def is_attack(n):
+            return 'attack_key_transform' in n or 'attack_query_transform' in n
+        for n, p in model.named_parameters():
+            p.requires_grad = not is_attack(n)
+        l_cal.backward(retain_graph=True)
+        for n, p in model.named_parameters():
+            p.requires_grad = is_attack(n)
+        l_att.backward()
+        for n, p in model.named_parameters():
+            gr = p.grad if p.grad is not None else torch.zeros_like(p)
+            out['grad.' + n] = gr.detach().numpy().copy()
+    else:
+        with Recorder(seed + 3) as rec:
+            a_scores, scores = model.full_sort_predict(inter)
+        for l in range(N):
+            out['rand.%d.noise' % l] = rec.noises[l].numpy()
+        scores = scores.detach().clone()
+        out['scores'] = scores.numpy().copy()
+        out['scores_att'] = a_scores.detach().numpy().copy()
+        scores[:, 0] = -np.inf
+        _, idx = torch.topk(scores, out['k'], dim=-1)
+        out['topk_idx'] = idx.numpy()
+        with Recorder(seed + 3):
+            a_s, c_s = model.predict(inter)
+        out['predict_att'] = a_s.detach().numpy()
+        out['predict_cal'] = c_s.detach().numpy()
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **out)
+    print(name, os.path.getsize(path) // 1024, 'KB')
+
+
+BERT_CASES = [
+    # AcBERT4Rec (SURVEY section 8 f-4).  `gate` trains in the reference but cannot be evaluated there (the gate is Linear(d, 50)
+    # and evaluation runs on L+1 = 51 positions, layers.py:878/887), so the eval case uses `fixed`.
+    ('bert_fixed_train', 151, 3, 31, True, dict(n_layers=2, combine_option='fixed')),
+    ('bert_gate_train', 151, 3, 32, True, dict(n_layers=1, n_heads=4)),
+    ('bert_fixed_eval', 151, 3, 33, False, dict(n_layers=2, combine_option='fixed')),
+]
+
 CASES = [
     # name, V, B, seed, train, cfg overrides
     ('c1_eval', 301, 4, 11, False, {}),
@@ -214,3 +315,7 @@ if __name__ == '__main__':
         if only and name not in only:
             continue
         make_case(name, V, B, seed, train, **kw)
+    for name, V, B, seed, train, kw in BERT_CASES:
+        if only and name not in only:
+            continue
+        make_bert_case(name, V, B, seed, train, **kw)

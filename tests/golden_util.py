@@ -46,7 +46,10 @@ def load_case(name, dtype=torch.float32):
             r[(int(parts[1]), parts[2])] = a.to(dtype) / (1 - p)
     batch = dict(item_seq=torch.from_numpy(z['item_id_list']), item_len=torch.from_numpy(z['item_length']),
                  pos=torch.from_numpy(z['item_id']))
+    for key in ('masked_seq', 'pos_items', 'neg_items', 'masked_index'):        # AcBERT4Rec: the recorded host-side masking
+        if key in z.files:
+            batch[key] = torch.from_numpy(z[key])
     if 'neg_item_id' in z.files:                  # loss_type BPR: the sampled negative of every row
         batch['neg'] = torch.from_numpy(z['neg_item_id'])
-    return dict(z=z, cfg=cfg, params=params, grads=grads, rand=O.Rand(r), batch=batch,
+    return dict(z=z, cfg=cfg, bert=('bert' in z.files), params=params, grads=grads, rand=O.Rand(r), batch=batch,
                 train=bool(z['train']), V=int(z['V']), k=int(z['k']))

@@ -206,10 +206,10 @@ def _attn_inputs(H, dh, L, combine, two_level, rich, use_order, use_distance, p,
     return cfg, seq, t, lp, rnd, g
 
 
-def _run_cuda_attn(A, cfg, seq, t, lp, rnd, p, need_att=True, want_probs=True, grad=False):
+def _run_cuda_attn(A, cfg, seq, t, lp, rnd, p, need_att=True, want_probs=True, grad=False, bidirectional=False):
     H = cfg['n_heads']
     opts = A.ops.AttnOpts(H, cfg['two_level'], cfg['combine_option'],
-                          cfg['rich_calibrated_combine'] if not cfg['two_level'] else 'none', p)
+                          cfg['rich_calibrated_combine'] if not cfg['two_level'] else 'none', p, bidirectional=bidirectional)
     def c(x):
         if x is None:
             return None
@@ -808,3 +808,75 @@ def test_fold_attack_weights(A):
         got = x @ oW[3 + i].cpu().double().t() + ob[3 + i].cpu().double()
         close(got, ref, 2e-5, 'folded attack projection %d' % i)
 
+
+
+# bidirectional attention mask (AcBERT4Rec: get_attention_mask(item_seq, bidirectional=True), abstract_recommender.py:136-143)
+BIDIR_CASES = [ATTN_CASES[i] for i in (0, 1, 4, 5, 7, 9, 10, 13)] + [(2, 32, 51, 'fixed', True, 'none', True, True, 0.5)]
+
+
+@pytest.mark.parametrize('case', BIDIR_CASES)
+def test_attn_calib_bidirectional_forward_backward(A, case):
+    """only padded keys are masked: rows see keys j > i (both branches of the order calibrator in play); forward
+    probabilities / contexts / penalty and every gradient against the oracle with the bidirectional additive mask."""
+    H, dh, L, combine, two_level, rich, uo, ud, p = case
+    cfg, seq, t, lp, rnd, g = _attn_inputs(*case)
+    B, d = t['mq'].shape[0], H * dh
+    mask = O.additive_mask(seq, bidirectional=True)
+    g_att, g_cal = torch.randn(B, L, d, generator=g), torch.randn(B, L, d, generator=g)
+    g_pen = torch.tensor([0.01])
+    to = {k: (v.clone().requires_grad_(True) if v is not None else None) for k, v in t.items()}
+    lpo = {k: v.clone().requires_grad_(True) for k, v in lp.items()}
+    r = O.attn_calib(to['mq'], to['mk'], to['mv'], to['aq'], to['ak'], to['gate'], mask, lpo, cfg, 0, O.Rand(rnd), anneal_rate=0.37)
+    ((r['ctx_cal'] * g_cal).sum() + (r['ctx_att'] * g_att).sum() + (r['pen_sq'] * g_pen).sum()).backward()
+    (ctx_att, ctx_cal, pen, probs), _, _ = _run_cuda_attn(A, cfg, seq, t, lp, rnd, p, bidirectional=True)
+    for i, n in enumerate(['P0', 'P', 'M', 'A', 'C', 'R']):
+        close(probs[i], r[n].detach(), 3e-5, n)
+    close(ctx_att, r['ctx_att'].detach(), 3e-5, 'ctx_att')
+    close(ctx_cal, r['ctx_cal'].detach(), 3e-5, 'ctx_cal')
+    close(pen, r['pen_sq'].detach().view(1), 1e-5, 'pen_sq')
+    # rows really see later keys: the upper triangle of a full-length row carries probability mass
+    upper = torch.triu(torch.ones(L, L, dtype=torch.bool), 1)
+    assert float(probs[5].cpu()[0][:, upper].abs().max()) > 0.0
+    (ctx_att, ctx_cal, pen, _), tc, lpc = _run_cuda_attn(A, cfg, seq, t, lp, rnd, p, want_probs=False, grad=True, bidirectional=True)
+    ((ctx_cal * g_cal.cuda()).sum() + (ctx_att * g_att.cuda()).sum() + (pen * g_pen.cuda()).sum()).backward()
+    for k in ('mq', 'mk', 'mv', 'aq', 'ak', 'gate'):
+        if to[k] is None:
+            continue
+        close(tc[k].grad, to[k].grad, 3e-4, 'd_' + k)
+    for k in lpo:
+        ref = lpo[k].grad if lpo[k].grad is not None else torch.zeros_like(lpo[k])
+        got = lpc[k].grad if lpc[k].grad is not None else torch.zeros_like(lpc[k])
+        scale = float(ref.abs().max())
+        assert float((got.cpu() - ref).abs().max()) <= 5e-4 * scale + 1e-6, (k, got, ref)
+
+
+def test_gather_rows_and_weighted_ce(A):
+    """the two pieces AcBERT4Rec adds around the encoder (acbert4rec.py:198-222): row gather (+ scatter-add backward) and the
+    masked-item cross entropy with per-row weights."""
+    g = torch.Generator().manual_seed(3)
+    T, d, n, V = 300, 64, 77, 501
+    x = torch.randn(T, d, generator=g)
+    idx = torch.randint(0, T, (n,), generator=g)
+    idx[0] = 0
+    xc = x.clone().cuda().requires_grad_(True)
+    y = A.ops.GatherRowsFn.apply(xc, idx.cuda())
+    assert torch.equal(y.detach().cpu(), x[idx])
+    gy = torch.randn(n, d, generator=g)
+    y.backward(gy.cuda())
+    want = torch.zeros(T, d).index_add_(0, idx, gy)
+    close(xc.grad, want, 1e-6, 'gather backward')
+    out = (torch.randn(2 * n, d, generator=g) * 0.7)
+    E = (torch.randn(V, d, generator=g) * 0.3)
+    tgt = torch.randint(0, V, (2 * n,), generator=g)
+    w = (torch.rand(2 * n, generator=g) > 0.4).float()
+    oo, Eo = out.clone().double().requires_grad_(True), E.clone().double().requires_grad_(True)
+    lg = oo @ Eo.t()
+    rl = torch.logsumexp(lg, 1) - lg[torch.arange(2 * n), tgt]
+    want_loss = torch.stack([(rl[:n] * w[:n].double()).sum() / w[:n].sum(), (rl[n:] * w[n:].double()).sum() / w[n:].sum()])
+    (want_loss[0] * 0.7 - want_loss[1] * 1.3).backward()
+    oc, Ec = out.clone().cuda().requires_grad_(True), E.clone().cuda().requires_grad_(True)
+    loss = A.ops.LogitsCEFn.apply(oc, Ec, tgt.cuda(), 2, 3, w.cuda())
+    close(loss, want_loss, 1e-5, 'weighted CE')
+    (loss[0] * 0.7 - loss[1] * 1.3).backward()
+    close(oc.grad, oo.grad, 2e-4, 'd_out')
+    close(Ec.grad, Eo.grad, 2e-4, 'd_table')

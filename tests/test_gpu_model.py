@@ -13,7 +13,9 @@ pytestmark = pytest.mark.gpu
 from oracle import acsr_oracle as O
 from golden_util import GOLDEN_DIR, load_case
 
-ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+EVERY = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+ALL = [n for n in EVERY if not n.startswith('bert_')]
+BERT = [n for n in EVERY if n.startswith('bert_')]          # AcBERT4Rec cases (acbert4rec.py)
 TRAIN = [n for n in ALL if '_train' in n]
 EVAL = [n for n in ALL if '_eval' in n]
 
@@ -533,3 +535,87 @@ def test_device_resident_loader_epoch_equals_host_loader_steps(A):
     # a second epoch draws a new permutation and rewinds the cursor
     t1._train_epoch(loader, 1)
     assert not torch.equal(loader.perm.cpu(), perm) and int(loader.cursor.item()) == n // B
+
+
+# ---- AcBERT4Rec: goldens from the real reference (tests/golden/make_golden.py: make_bert_case) ----
+def build_bert(A, c, **extra):
+    cfg = dict(c['cfg'])
+    config = make_config(A, cfg, **extra)
+    model = A.AcBERT4Rec(config, DS(c['V'])).to('cuda')
+    model.load_state_dict({k: v.cuda() for k, v in c['params'].items()}, strict=True)      # reference state_dict loads unchanged
+    model._debug_rand = {k: v.cuda() for k, v in c['rand'].d.items()}
+    return config, model
+
+
+@pytest.mark.parametrize('name', [n for n in BERT if '_train' in n])
+def test_bert_golden_train_losses_and_routed_grads(A, name):
+    c = load_case(name)
+    z, b = c['z'], c['batch']
+    config, model = build_bert(A, c)
+    assert tuple(model.item_embedding.weight.shape) == (c['V'] + 1, c['cfg']['hidden_size'])
+    model._debug_masked = tuple(b[k].cuda() for k in ('masked_seq', 'pos_items', 'neg_items', 'masked_index'))
+    model.train()
+    l_att, l_cal = model.calculate_loss(inter_of(A, c))
+    assert abs(float(l_att) - float(z['loss_att'])) < 1e-4 * abs(float(z['loss_att']))
+    assert abs(float(l_cal) - float(z['loss_cal'])) < 1e-4 * abs(float(z['loss_cal']))
+    for n, p in model.named_parameters():
+        p.requires_grad = not ('attack_key_transform' in n or 'attack_query_transform' in n)
+    l_cal.backward(retain_graph=True)
+    for n, p in model.named_parameters():
+        p.requires_grad = ('attack_key_transform' in n or 'attack_query_transform' in n)
+    l_att.backward()
+    assert set(n for n, _ in model.named_parameters()) == set(c['grads'])
+    for n, p in model.named_parameters():
+        ref = c['grads'][n]
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(ref)
+        scale = float(ref.abs().max())
+        err = float((got - ref).abs().max())
+        assert err <= 1e-3 * scale + 1e-8, (n, err, scale)
+
+
+@pytest.mark.parametrize('name', [n for n in BERT if '_eval' in n])
+def test_bert_golden_eval(A, name):
+    c = load_case(name)
+    z = c['z']
+    config, model = build_bert(A, c)
+    model.eval()
+    inter = inter_of(A, c)
+    with torch.no_grad():
+        sa, sc = model.full_sort_predict(inter)
+        assert rel(sc, z['scores']) < 1e-4 and rel(sa, z['scores_att']) < 1e-4
+        assert sc.shape == (c['batch']['pos'].shape[0], c['V'])
+        val, idx, rec = model.full_sort_topk(inter, c['k'], inter['item_id'])
+        ok, nbad = O.topk_equal_modulo_ties(idx.cpu(), torch.from_numpy(z['topk_idx']), torch.from_numpy(z['scores']))
+        assert ok, nbad
+        pa, pc = model.predict(inter)
+        assert rel(pa, z['predict_att']) < 1e-4 and rel(pc, z['predict_cal']) < 1e-4
+
+
+def test_bert_gate_cannot_be_evaluated_like_the_reference(A):
+    """combine_option gate: Linear(hidden, 50) against the 51 positions of reconstruct_test_data -- a shape error in the reference
+    (layers.py:887-888), a ValueError here."""
+    c = load_case('bert_gate_train')
+    config, model = build_bert(A, c)
+    model.eval()
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            model.full_sort_predict(inter_of(A, c))
+
+
+def test_bert_trainer_epoch_and_eval(A, tmp_path):
+    """AcBERT4RecTrainer: the adversarial two-loss step (routed double backward) + full-sort evaluation run end to end"""
+    cfg = O.default_cfg(n_layers=1, combine_option='fixed')
+    cfg['mask_ratio'] = 0.2
+    V = 200
+    config = make_config(A, cfg, checkpoint_dir=str(tmp_path), epochs=1, train_batch_size=32, eval_batch_size=32, MAX_ITEM_LIST_LENGTH=49)
+    torch.manual_seed(0)
+    train_ds = A.data.SyntheticSequentialDataset(config, 32 * 3, V, seed=1)
+    valid_ds = A.data.SyntheticSequentialDataset(config, 64, V, seed=2)
+    model = A.AcBERT4Rec(config, train_ds).to('cuda')
+    trainer = A.AcBERT4RecTrainer(config, model)
+    assert trainer.fused is None                      # the autograd path over the same kernels
+    before = model.item_embedding.weight.detach().clone()
+    score, result = trainer.fit(A.data.TrainDataLoader(config, train_ds, shuffle=True), A.data.FullSortEvalDataLoader(config, valid_ds),
+                                verbose=False, saved=True)
+    assert float((model.item_embedding.weight.detach() - before).abs().max()) > 0
+    assert all(np.isfinite(v) for v in result.values()) and 'hit@10' in result

@@ -265,3 +265,24 @@ def test_config_gpu_id_selects_the_device():
     d = O.default_cfg()
     d.update(seed=42, learning_rate=1e-3, epochs=1, eval_batch_size=8, train_batch_size=8, topk=[10], metrics=['Hit'], gpu_id=0, use_gpu=False)
     assert A.Config(model='ACSASRec', config_dict=d)['device'].type == 'cpu'
+
+
+def test_bert_masking_follows_the_reference_procedure():
+    """AcBERT4Rec.reconstruct_train_data / reconstruct_test_data (acbert4rec.py:86-160): with the reference's random.seed the
+    masked sequence, positives, negatives and masked indices are the ones the reference produced (tests/golden/bert_*_train)."""
+    import random
+    c = load_case('bert_fixed_train')
+    z, b = c['z'], c['batch']
+    cfg = dict(c['cfg'])
+    cfg.update(device=torch.device('cpu'), seed=42, learning_rate=1e-3, epochs=1, eval_batch_size=8, train_batch_size=8,
+               topk=[10], metrics=['Hit'], valid_metric='Hit@10', checkpoint_dir='/tmp/acsr_ckpt')
+    model = A.AcBERT4Rec(A.Config(model='AcBERT4Rec', config_dict=cfg), DS(c['V']))
+    assert model.mask_token == c['V'] and model.mask_item_length == int(cfg['mask_ratio'] * 50)
+    random.seed(int(z['random_seed']))
+    masked, pos, neg, index = model.reconstruct_train_data(b['item_seq'])
+    assert torch.equal(masked, b['masked_seq']) and torch.equal(pos, b['pos_items'])
+    assert torch.equal(neg, b['neg_items']) and torch.equal(index, b['masked_index'])
+    seq = model.reconstruct_test_data(b['item_seq'].clone(), b['item_len'])
+    assert seq.shape[1] == b['item_seq'].shape[1] + 1
+    assert torch.equal(seq, O.bert_test_sequence(b['item_seq'], b['item_len'], c['V']))
+    assert set(model.state_dict()) == set(c['params'])

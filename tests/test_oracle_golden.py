@@ -9,7 +9,9 @@ import torch
 from oracle import acsr_oracle as O
 from golden_util import GOLDEN_DIR, load_case
 
-ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+EVERY = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+ALL = [n for n in EVERY if not n.startswith('bert_')]
+BERT = [n for n in EVERY if n.startswith('bert_')]          # AcBERT4Rec cases (acbert4rec.py)
 TRAIN = [n for n in ALL if '_train' in n]
 EVAL = [n for n in ALL if '_eval' in n]
 
@@ -73,3 +75,29 @@ def test_metrics_against_reference_formulas():
         rank = np.where(pos.any(1), pos.argmax(1), 10 ** 6)
         assert m['mrr@%d' % k] == round(float(np.where(rank < k, 1.0 / (rank + 1), 0).mean()), 4)
         assert m['ndcg@%d' % k] == round(float(np.where(rank < k, 1.0 / np.log2(rank + 2), 0).mean()), 4)
+
+
+@pytest.mark.parametrize('name', [n for n in BERT if '_train' in n])
+def test_bert_train_losses_and_routed_grads(name):
+    """AcBERT4Rec (acbert4rec.py:207-245): bidirectional mask + masked-item CE, against the reference's losses and routed .grad"""
+    c = load_case(name)
+    b, z = c['batch'], c['z']
+    l_att, l_cal, grads = O.bert_train_grads(c['params'], c['cfg'], b['masked_seq'], b['pos_items'], b['masked_index'], c['rand'])
+    assert abs(float(l_att) - float(z['loss_att'])) < 1e-5 * abs(float(z['loss_att']))
+    assert abs(float(l_cal) - float(z['loss_cal'])) < 1e-5 * abs(float(z['loss_cal']))
+    assert set(grads) == set(c['grads'])
+    for n, g in c['grads'].items():
+        scale = float(g.abs().max())
+        err = float((grads[n] - g).abs().max())
+        assert err <= 2e-4 * scale + 1e-9, (n, err, scale)
+
+
+@pytest.mark.parametrize('name', [n for n in BERT if '_eval' in n])
+def test_bert_eval_scores(name):
+    c = load_case(name)
+    b, z = c['batch'], c['z']
+    sa, sc = O.bert_full_sort_scores(c['params'], c['cfg'], b['item_seq'], b['item_len'], c['rand'])
+    assert rel(sc, z['scores']) < 2e-5 and rel(sa, z['scores_att']) < 2e-5
+    _, idx = O.full_sort_topk(sc, c['k'])
+    ok, nbad = O.topk_equal_modulo_ties(idx, torch.from_numpy(z['topk_idx']), torch.from_numpy(z['scores']))
+    assert ok, nbad
