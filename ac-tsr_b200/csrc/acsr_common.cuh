@@ -39,6 +39,9 @@ constexpr float kOrderEps = 1e-24f;     // layers.py:719
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// memory registered with acsr_register_static: parameters that no kernel of a training step but the optimizer (its last node)
+// writes, so a kernel launched with programmatic dependent launch may read them before griddepcontrol.wait
+bool is_static_memory(const void* p);
 bool pdl_enabled();
 void pdl_set(int on);
 

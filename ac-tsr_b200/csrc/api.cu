@@ -34,6 +34,16 @@ bool pdl_enabled() {
 }
 void pdl_set(int on) { g_pdl = on ? 1 : 0; }
 
+struct StaticRange { const char* lo; const char* hi; };
+static StaticRange g_static[64];
+static int g_n_static = 0;
+bool is_static_memory(const void* p) {
+  const char* c = (const char*)p;
+  for (int i = 0; i < g_n_static; ++i)
+    if (c >= g_static[i].lo && c < g_static[i].hi) return true;
+  return false;
+}
+
 // caller-owned scratch memory of the current device (acsr_set_workspace): the library allocates nothing itself
 static void* g_ws_ptr[64] = {};
 static size_t g_ws_bytes[64] = {};
@@ -54,6 +64,18 @@ int acsr_version(void) { return ACSR_ABI_VERSION; }
 const char* acsr_last_error(void) { return acsr::g_err; }
 int acsr_num_sms(void) { return acsr::kNumSMs; }
 int acsr_set_pdl(int on) { int was = acsr::pdl_enabled() ? 1 : 0; acsr::pdl_set(on); return was; }
+
+int acsr_register_static(const void* ptr, int64_t bytes) {
+  if (ptr == nullptr) { acsr::g_n_static = 0; return ACSR_OK; }           // NULL clears the registry
+  ACSR_REQUIRE(bytes > 0, "acsr_register_static: bad size");
+  for (int i = 0; i < acsr::g_n_static; ++i)
+    if (acsr::g_static[i].lo == (const char*)ptr) { acsr::g_static[i].hi = (const char*)ptr + bytes; return ACSR_OK; }
+  ACSR_REQUIRE(acsr::g_n_static < 64, "acsr_register_static: registry full");
+  acsr::g_static[acsr::g_n_static].lo = (const char*)ptr;
+  acsr::g_static[acsr::g_n_static].hi = (const char*)ptr + bytes;
+  ++acsr::g_n_static;
+  return ACSR_OK;
+}
 
 int acsr_set_workspace(void* ptr, int64_t bytes) {
   int dev = 0;

@@ -44,6 +44,7 @@ struct GkProblem {
 
 struct GkParams {
   int n_problems, total_items, stages, stage_bytes, passes;
+  int b_static;          // every B operand is registered parameter memory: the B loaders need not wait for the previous kernel
   GkProblem pr[ACSR_GEMM_MAX_PROBLEMS];
 };
 
@@ -218,7 +219,9 @@ __global__ void __launch_bounds__(kGkThreads, 1) gemm_ks_kernel(const __grid_con
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<2 * kGkAccCols>(tmem_slot);
-  pdl_wait();                 // everything above overlaps the tail of the previous kernel
+  // Everything above overlaps the tail of the previous kernel; when all B operands are registered parameters (weights) the B
+  // loader warps start streaming them at once -- they touch nothing the previous kernel wrote.
+  if (!(P.b_static && warp >= 5 && warp <= 8)) pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -416,6 +419,52 @@ __global__ void __launch_bounds__(kGkThreads, 1) gemm_ks_kernel(const __grid_con
           }
         }
         if (row_ok) { p.stats[2 * grow] = mean; p.stats[2 * grow + 1] = rstd; }
+      } else if (p.epilogue == ACSR_EPI_CE) {
+        // full-catalogue logits of any hidden size (acsasrec.py:118-120): (max, sum exp) of this block's columns per row;
+        // C2 = partial [M, n_blocks, 2], combined by acsr_ce_finalize.  The logits never leave TMEM.
+        float run_m = -INFINITY, run_s = 0.f;
+#pragma unroll 1
+        for (int cc = 0; cc < nch; ++cc) {
+          float v[32];
+          tmem_ld32(t_acc + cc * 32, v);
+          const int nvalid = min(32, p.N - (n0 + cc * 32));
+          float cm = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < nvalid) cm = fmaxf(cm, v[i]);
+          const float nm = fmaxf(run_m, cm);
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < nvalid) sum += __expf(v[i] - nm);
+          run_s = run_s * __expf(run_m - nm) + sum;
+          run_m = nm;
+        }
+        if (row_ok) {
+          float* o = p.C2 + (grow * g.n_blocks + w.n_block) * 2;
+          o[0] = run_m; o[1] = run_s;
+        }
+      } else if (p.epilogue == ACSR_EPI_CE_GRAD) {
+        // C = Gt [N, ldc]: transpose of (exp(logit - lse[m]) - onehot(target[m])) * row_scale[m]; lse = res, row_scale = ln_w,
+        // target = rng (int64).  A warp's 32 rows are 32 consecutive floats of a Gt row: coalesced 128-byte lines.
+        float g_lse = 0.f, g_scale = 0.f;
+        long long g_tgt = -1;
+        if (row_ok) { g_lse = p.res[grow]; g_scale = p.ln_w[grow]; g_tgt = reinterpret_cast<const long long*>(p.rng)[grow]; }
+#pragma unroll 1
+        for (int cc = 0; cc < nch; ++cc) {
+          float v[32];
+          tmem_ld32(t_acc + cc * 32, v);
+          const long long c0 = n0 + cc * 32;
+          const int nvalid = min(32, (int)(p.N - c0));
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < nvalid) {
+                float gv = __expf(v[i] - g_lse);
+                if (c0 + i == g_tgt) gv -= 1.0f;
+                p.C[(c0 + i) * p.ldc + grow] = gv * g_scale;
+              }
+            }
+          }
+        }
       } else {
 #pragma unroll 1
         for (int cc = 0; cc < nch; ++cc) {
@@ -526,7 +575,7 @@ int acsr_gemm_batch(const acsr_gemm_problem* problems, int n_problems, int passe
     ACSR_REQUIRE(p.M >= 0 && p.N > 0 && p.K > 0 && p.M < (1ll << 31), "gemm_batch[%d]: bad sizes M=%lld N=%d K=%d", i, (long long)p.M, p.N, p.K);
     ACSR_REQUIRE(p.a_kblk > 0 && p.b_kblk > 0 && (p.a_kblk >= p.K || (p.a_kblk & 3) == 0) && (p.b_kblk >= p.K || (p.b_kblk & 3) == 0),
                  "gemm_batch[%d]: k-block lengths must be multiples of 4 (or cover K)", i);
-    ACSR_REQUIRE(p.epilogue >= ACSR_EPI_STORE && p.epilogue <= ACSR_EPI_BDRL, "gemm_batch[%d]: unknown epilogue %d", i, p.epilogue);
+    ACSR_REQUIRE(p.epilogue >= ACSR_EPI_STORE && p.epilogue <= ACSR_EPI_CE_GRAD, "gemm_batch[%d]: unknown epilogue %d", i, p.epilogue);
     if (p.M == 0) continue;
     GkProblem& g = P.pr[n];
     g.p = p;
@@ -536,6 +585,10 @@ int acsr_gemm_batch(const acsr_gemm_problem* problems, int n_problems, int passe
       ACSR_REQUIRE(p.p_drop >= 0.f && p.p_drop < 1.f, "gemm_batch[%d]: dropout p=%f", i, p.p_drop);
       ACSR_REQUIRE(!(p.p_drop > 0.f && p.mask == nullptr && p.rng == nullptr), "gemm_batch[%d]: p>0 needs mask or rng", i);
       ACSR_REQUIRE(p.C == nullptr || (p.ldc >= p.N && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0), "gemm_batch[%d]: C layout", i);
+    } else if (p.epilogue == ACSR_EPI_CE) {
+      ACSR_REQUIRE(p.C2 != nullptr, "gemm_batch[%d]: CE epilogue needs the partial buffer in C2", i);
+    } else if (p.epilogue == ACSR_EPI_CE_GRAD) {
+      ACSR_REQUIRE(p.C && p.res && p.ln_w && p.rng && p.ldc >= p.M, "gemm_batch[%d]: CE-gradient epilogue arguments", i);
     } else {
       ACSR_REQUIRE(p.C != nullptr && p.ldc >= p.N, "gemm_batch[%d]: bad output", i);
       if (p.epilogue == ACSR_EPI_ACT) {
@@ -557,6 +610,9 @@ int acsr_gemm_batch(const acsr_gemm_problem* problems, int n_problems, int passe
   }
   if (n == 0) return ACSR_OK;
   P.n_problems = n;
+  P.b_static = 1;
+  for (int i = 0; i < n; ++i)
+    if (!is_static_memory(P.pr[i].p.B)) P.b_static = 0;
   int items = 0;
   for (int i = 0; i < n; ++i) {
     GkProblem& g = P.pr[i];
@@ -594,4 +650,21 @@ int acsr_gemm_batch(const acsr_gemm_problem* problems, int n_problems, int passe
   return check_launch("gemm_batch");
 }
 
+int acsr_gemm_ce_parts(int64_t V) { return V > 0 ? (int)((V + 255) / 256) : 0; }
+
 }  // extern "C"
+
+namespace acsr {
+// full-catalogue logits for hidden sizes other than 64 (logits_tc.cu keeps the A-stationary width-64 kernel): the K-streamed GEMM
+// with rows of `out` on M, table rows on N and the consumer in the TMEM epilogue
+int gemm_logits(int mode, const float* out, const float* table, int M, long long V, int d, int passes, float* C, long long ldc,
+                float* partial, const float* lse, const long long* target, const float* row_scale, cudaStream_t st) {
+  acsr_gemm_problem p = {};
+  p.A = out; p.a_row_stride = d; p.a_k_stride = 1; p.a_kblk = d;
+  p.B = table; p.b_row_stride = d; p.b_k_stride = 1; p.b_kblk = d;
+  p.M = M; p.N = (int)V; p.K = d;
+  p.C = C; p.ldc = ldc; p.C2 = partial; p.epilogue = mode;
+  p.res = lse; p.ln_w = row_scale; p.rng = target;
+  return acsr_gemm_batch(&p, 1, passes, (void*)st);
+}
+}  // namespace acsr

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) fold_attack_weights_kernel(const float* _
                                                                   const float* __restrict__ Waqk, const float* __restrict__ baqk, int d,
                                                                   float* __restrict__ out_W, float* __restrict__ out_b) {
   extern __shared__ float fsm[];                    // B [d][d], A rows [kFoldRows][d], b1 [d]
-  pdl_launch_dependents();
+  // (no early programmatic-launch trigger: the folded weights it writes are registered as static, see acsr_register_static)
   pdl_wait();
   const int slot = blockIdx.y, r0 = blockIdx.x * kFoldRows;
   const int nr = min(kFoldRows, d - r0);

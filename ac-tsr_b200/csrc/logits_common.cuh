@@ -71,6 +71,10 @@ static inline void logits_plan_topk(LogitsParams& p) {
   if (nc < p.n_chunks) p.n_chunks = nc;
 }
 
+// gemm_ks.cu: logits for hidden sizes other than 64 on the K-streamed tcgen05 GEMM (mode = ACSR_EPI_STORE / _CE / _CE_GRAD)
+int gemm_logits(int mode, const float* out, const float* table, int M, long long V, int d, int passes, float* C, long long ldc,
+                float* partial, const float* lse, const long long* target, const float* row_scale, cudaStream_t st);
+
 // logits_simt.cu: same modes, same partial layouts, hidden size d (multiple of 4, <= 1024)
 int launch_logits_simt(int mode, LogitsParams& p, int d, cudaStream_t st, const char* who);
 

@@ -537,6 +537,11 @@ int acsr_logits_num_chunks(int M, int64_t V) {
   return p.n_chunks;
 }
 
+int acsr_logits_num_chunks_d(int M, int64_t V, int d) {
+  if (d == kD) return acsr_logits_num_chunks(M, V);
+  return acsr_gemm_ce_parts(V);
+}
+
 int acsr_logits_store(const float* out, const float* table, int M, int64_t V, int d, int passes, float* scores, int64_t ldc,
                       void* stream) {
   int rc = validate_common(out, table, M, V, d, passes, "logits_store");
@@ -544,7 +549,8 @@ int acsr_logits_store(const float* out, const float* table, int M, int64_t V, in
   ACSR_REQUIRE(scores && ldc >= V, "logits_store: bad output");
   LogitsParams p = {};
   p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.C = scores; p.ldc = ldc;
-  if (d != kD) return launch_logits_simt(MODE_STORE, p, d, (cudaStream_t)stream, "logits_store");   // fp32 FMA path (logits_simt.cu)
+  // other hidden sizes: the K-streamed tcgen05 GEMM (gemm_ks.cu), rows of `out` on M, table rows on N
+  if (d != kD) return gemm_logits(ACSR_EPI_STORE, out, table, M, V, d, passes, scores, ldc, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
   return launch_tc<MODE_STORE>(p, (cudaStream_t)stream, "logits_store");
 }
 
@@ -554,7 +560,8 @@ int acsr_logits_ce_partial(const float* out, const float* table, int M, int64_t 
   ACSR_REQUIRE(partial, "logits_ce_partial: NULL output");
   LogitsParams p = {};
   p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.partial = partial;
-  if (d != kD) return launch_logits_simt(MODE_CE, p, d, (cudaStream_t)stream, "logits_ce_partial");   // fp32 FMA path (logits_simt.cu)
+  // other hidden sizes: K-streamed tcgen05 GEMM with the (max, sum exp) epilogue; partial is [M, acsr_logits_num_chunks_d(M, V, d), 2]
+  if (d != kD) return gemm_logits(ACSR_EPI_CE, out, table, M, V, d, passes, nullptr, V, partial, nullptr, nullptr, nullptr, (cudaStream_t)stream);
   return launch_tc<MODE_CE>(p, (cudaStream_t)stream, "logits_ce_partial");
 }
 
@@ -598,7 +605,7 @@ int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, 
   LogitsParams p = {};
   p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes; p.C = G; p.ldc = ldg;
   p.lse = lse; p.target = (const long long*)target; p.row_scale = row_scale;
-  if (d != kD) return launch_logits_simt(MODE_GRAD, p, d, (cudaStream_t)stream, "logits_ce_grad");   // fp32 FMA path (logits_simt.cu)
+  if (d != kD) return gemm_logits(ACSR_EPI_CE_GRAD, out, table, M, V, d, passes, G, ldg, nullptr, lse, (const long long*)target, row_scale, (cudaStream_t)stream);
   return launch_tc<MODE_GRAD>(p, (cudaStream_t)stream, "logits_ce_grad");
 }
 

@@ -387,7 +387,8 @@ __global__ void gather_last_bwd_kernel(const float* __restrict__ d_out, const in
 // ------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float wd, const long long* __restrict__ step_count) {
-  pdl_launch_dependents();
+  // (no early programmatic-launch trigger: this kernel WRITES the parameters, which later kernels may read ahead of their
+  // griddepcontrol.wait -- acsr_register_static -- so nothing that follows may start before it has completed)
   pdl_wait();
   const double step = (double)(step_count[0] + 1);
   const float bc1 = (float)(1.0 - pow((double)b1, step));

@@ -30,13 +30,13 @@ import torch.distributed as dist
 class CudaCompute(object):
     """the local kernels, bound to libacsr.so through ops.py"""
 
-    def __init__(self, passes=3):
+    def __init__(self, passes=3, d=64):
         from . import ops
         from ._lib import LIB
-        self.ops, self.passes, self.LIB = ops, passes, LIB
+        self.ops, self.passes, self.LIB, self.d = ops, passes, LIB, d
 
     def num_chunks(self, rows, shard_rows):
-        return self.ops.logits_num_chunks(rows, shard_rows) if shard_rows > 0 else 1
+        return self.ops.logits_num_chunks(rows, shard_rows, self.d) if shard_rows > 0 else 1
 
     def ce_partial(self, out, table):
         return self.ops.ce_partial(out, table, self.passes)

@@ -120,7 +120,7 @@ class FusedTrainStep(object):
 
         def f(*s):
             return torch.empty(s, dtype=torch.float32, device=dev)
-        nc = ops.logits_num_chunks(2 * B, V)
+        nc = ops.logits_num_chunks(2 * B, V, d)
         loss3 = f(3)              # [CE(calibrated), CE(attacked), final attacked loss]: one buffer, one read-back
         j = dict(pen=torch.zeros(N, dtype=torch.float64, device=dev), out2=f(2 * B, d), partial=f(2 * B, nc, 2), lse=f(2 * B),
                  tgt=f(2 * B), row_loss=f(2 * B), loss3=loss3, loss=loss3[:2], loss_att=loss3[2:], dpen=f(N), Gt=None,      # [V, 2B] transposed CE gradient: allocated on first use (never under vocab-parallel / BPR)
@@ -664,6 +664,10 @@ class FusedTrainStep(object):
         if key not in self.buf:
             d = self.m.hidden_size
             self.buf[key] = dict(W=torch.empty((5, d, d), dtype=torch.float32, device=dev), b=torch.empty((5, 1, d), dtype=torch.float32, device=dev))
+            # written once per step by acsr_fold_attack_weights, which completes (full event dependency) before the first kernel
+            # of the chain that reads them starts: safe to read ahead of programmatic-launch synchronisation
+            for t in self.buf[key].values():
+                LIB.query('acsr_register_static', t.data_ptr(), t.numel() * 4)
         return self.buf[key]
 
     def _stacked(self, l):

@@ -250,15 +250,15 @@ class AttnCalibFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------
 # full-catalogue logits on tcgen05
 # ------------------------------------------------------------------------------------------
-def logits_num_chunks(M, V):
-    return LIB.query('acsr_logits_num_chunks', int(M), int(V))
+def logits_num_chunks(M, V, d=64):
+    return LIB.query('acsr_logits_num_chunks_d', int(M), int(V), int(d))
 
 
 def ce_partial(out, table, passes=3):
     """-> partial [M, n_chunks, 2] (max, sumexp) over this table (shard)."""
     M, d = out.shape
     V = table.shape[0]
-    part = torch.empty((M, logits_num_chunks(M, V), 2), dtype=torch.float32, device=out.device)
+    part = torch.empty((M, logits_num_chunks(M, V, d), 2), dtype=torch.float32, device=out.device)
     LIB.call('acsr_logits_ce_partial', _p(out), _p(table), M, V, d, passes, _p(part), _stream())
     return part
 

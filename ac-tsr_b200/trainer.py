@@ -83,6 +83,11 @@ class FlatAdam(object):
         assert off <= n + align * len(layout)
         self.lr, self.weight_decay, self.betas, self.eps = float(lr), float(weight_decay or 0.0), betas, eps
         self.params = params
+        if self.flat_param.is_cuda:
+            # parameters: only this optimizer (the last node of a step) writes them -> kernels may read them ahead of
+            # programmatic dependent launch synchronisation
+            from ._lib import LIB
+            LIB.query('acsr_register_static', self.flat_param.data_ptr(), self.flat_param.numel() * 4)
         self.no_grad_params = [p for n, p in model.named_parameters() if n == 'mask_loss_weight']
 
     def stacked(self, plist, grad=False):
@@ -276,7 +281,7 @@ class ACSASRecTrainer(object):
         if shard_table is None:
             L = int(cfg_get(self.config, 'MAX_ITEM_LIST_LENGTH', 50))
             shard_table = m.n_items > 2 * self.dp_world * int(self.config['train_batch_size']) * L
-        self.vp = VocabParallel(m.n_items, compute=CudaCompute(m.logits_passes), sharded=bool(shard_table))
+        self.vp = VocabParallel(m.n_items, compute=CudaCompute(m.logits_passes, m.hidden_size), sharded=bool(shard_table))
         if shard_table:
             # swap the replicated table for this rank's shard and rebuild the flat optimizer state around it
             full = m.item_embedding.weight.detach()

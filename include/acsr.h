@@ -42,6 +42,11 @@ int acsr_num_sms(void);
  * previous one).  Returns the previous setting.  Default: off (environment ACSR_PDL=1 turns it on). */
 int acsr_set_pdl(int on);
 
+/* Registers [ptr, ptr + bytes) as parameter memory: within a chain of kernels launched with programmatic dependent launch nothing
+ * but the optimizer step (the chain's last node) writes it, so the GEMM kernels may stage weights that live there before they wait
+ * for the previous kernel (their weight staging then overlaps its tail).  ptr == NULL clears the registry. */
+int acsr_register_static(const void* ptr, int64_t bytes);
+
 /* caller-owned scratch memory of the CURRENT device (the library allocates nothing).  Only the attention backward for
  * sequences longer than 64 needs it: acsr_attn_workspace_bytes(L, H, n_streams) bytes per sequence (0 for L <= 64;
  * n_streams = 1 for acsr_attn_calib_bwd, 2 for acsr_attn_calib_bwd2); with less than B sequences' worth the batch is
@@ -189,6 +194,11 @@ int acsr_gather_last_bwd(const float* d_out, const int64_t* item_len, int B, int
  * n_chunks = acsr_logits_num_chunks(M, V).
  */
 int acsr_logits_num_chunks(int M, int64_t V);
+/* number of (max, sum exp) parts per row acsr_logits_ce_partial writes at hidden size d: the chunk plan above at d = 64; at every
+ * other width the scores / CE / CE-gradient run on the K-streamed tcgen05 GEMM (acsr_gemm_batch, ACSR_EPI_CE*), one part per
+ * 256-column block (d = 128 of config/yelp.yaml:39-42, d = 256 of BASELINE config #5).  Only the streaming top-k of a
+ * catalogue too large for acsr_topk_select still takes the fp32 FMA kernel (logits_simt.cu) at d != 64. */
+int acsr_logits_num_chunks_d(int M, int64_t V, int d);
 /* scores [M, ldc] = out.E^T  (full_sort_predict, predict-all) */
 int acsr_logits_store(const float* out, const float* table, int M, int64_t V, int d, int passes,
                       float* scores, int64_t ldc, void* stream);
@@ -308,6 +318,12 @@ int acsr_linear_wgrad_batched(const float* dY, const float* X, int T, int N, int
 #define ACSR_EPI_ATOMIC 1
 #define ACSR_EPI_ACT 2
 #define ACSR_EPI_BDRL 3
+/* full-catalogue logits at any hidden size (model/sequential_recommender/acsasrec.py:118-120; rows of `out` on M, table rows on N):
+ *   ACSR_EPI_CE      C2 = partial [M, acsr_gemm_ce_parts(N), 2]: (max, sum exp) of every 256-column block, for acsr_ce_finalize
+ *   ACSR_EPI_CE_GRAD C = Gt [N, ldc >= M] = ((softmax - onehot(target)) * row_scale)^T with lse = res [M], row_scale = ln_w [M],
+ *                    target = rng (int64 [M]) */
+#define ACSR_EPI_CE 4
+#define ACSR_EPI_CE_GRAD 5
 #define ACSR_GEMM_MAX_PROBLEMS 16
 typedef struct acsr_gemm_problem {
   const float* A; int64_t a_row_stride; int64_t a_k_stride; int64_t a_kb_stride;
@@ -327,6 +343,7 @@ typedef struct acsr_gemm_problem {
   uint32_t rng_stream; float eps; float p_drop; int32_t reserved;
 } acsr_gemm_problem;
 int acsr_gemm_batch(const acsr_gemm_problem* problems, int n_problems, int passes, void* stream);
+int acsr_gemm_ce_parts(int64_t V);
 
 /* ---- loss_type BPR (model/sequential_recommender/acsasrec.py:109-116, model/loss.py:21-47) ----
  * x_m = out_m . (E[pos_m] - E[neg_m]); row_loss[m] = -log(gamma + sigmoid(x_m)); loss[g] = mean over row group g

@@ -526,7 +526,8 @@ def test_topk_select_ties_and_short_rows(A):
     assert torch.equal(idx.cpu().sort(dim=1).values, torch.arange(1, 51).expand(M, 50))
 
 
-# ---- hidden sizes other than 64 take the fp32 FMA path (logits_simt.cu): same entry points, same contracts ----
+# ---- hidden sizes other than 64: scores / CE / CE-gradient on the K-streamed tcgen05 GEMM (gemm_ks.cu epilogues), the streaming
+# top-k on the fp32 FMA kernel (logits_simt.cu): same entry points, same contracts ----
 @pytest.mark.parametrize('M,V,d', [(4, 301, 128), (130, 65, 256), (256, 12102, 128), (512, 12102, 256), (37, 20034, 32), (300, 1683, 100)])
 def test_logits_store_fp32_path(A, M, V, d):
     g = torch.Generator().manual_seed(M + V + d)
@@ -535,7 +536,7 @@ def test_logits_store_fp32_path(A, M, V, d):
     ref = out.double() @ E.double().t()
     s = A.ops.logits_scores(out.cuda(), E.cuda(), 3).cpu().double()
     e = float((s - ref).abs().max()) / float(ref.abs().max())
-    assert e < 2e-6, e
+    assert e < 4e-6, e          # 3xTF32 on the tensor cores: fp32-level (the K = 256 chain is 96 truncating accumulations)
 
 
 @pytest.mark.parametrize('M,V,groups,d', [(8, 301, 2, 128), (512, 12102, 2, 256), (256, 1683, 1, 128), (6, 65, 2, 36)])
