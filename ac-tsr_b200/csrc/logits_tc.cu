@@ -34,7 +34,13 @@ struct TcCfg {
   static constexpr int kOffStg = kOffBlo + 2 * kBbytes;  // [kStages]
   static constexpr int kOffTopk = kOffStg + kStages * kBbytes;
   static constexpr int kTopkBytes = MODE == MODE_TOPK ? 2 * kMaxTopK * kBM * 4 : 0;
-  static constexpr int kOffBar = kOffTopk + kTopkBytes;
+  // MODE_CE: the epilogue is instruction-issue bound (one thread per logits row), so it runs on EIGHT warps, two per TMEM lane
+  // quarter, each owning one 32-column half of every tile; the halves meet once, at the end, through kOffPair
+  static constexpr int kEpiWarps = MODE == MODE_CE ? 8 : 4;
+  static constexpr int kThreads = 192 + 32 * kEpiWarps;
+  static constexpr int kOffPair = kOffTopk + kTopkBytes;
+  static constexpr int kPairBytes = MODE == MODE_CE ? kBM * 8 : 0;
+  static constexpr int kOffBar = kOffPair + kPairBytes;
   static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 2;
   static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
 };
@@ -64,7 +70,7 @@ __device__ __noinline__ void topk_insert(float x, int col, float* lval, int* lid
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsParams p) {
+__global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(const LogitsParams p) {
   pdl_launch_dependents();
   pdl_wait();
   using Cfg = TcCfg<MODE>;
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(stg_full + s, 1); mbar_init(stg_empty + s, 128); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(op_full + s, 128); mbar_init(op_empty + s, 1);
-      mbar_init(tm_full + s, 1); mbar_init(tm_empty + s, 128);
+      mbar_init(tm_full + s, 1); mbar_init(tm_empty + s, 32 * Cfg::kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
   {
     float* Ahi = reinterpret_cast<float*>(smem + Cfg::kOffAhi);
     float* Alo = reinterpret_cast<float*>(smem + Cfg::kOffAlo);
-    for (int item = threadIdx.x; item < kBM * kKC; item += kTcThreads) {
+    for (int item = threadIdx.x; item < kBM * kKC; item += Cfg::kThreads) {
       const int r = item / kKC, kc = item % kKC;
       const int grow = m_tile * kBM + r;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -206,6 +212,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
   } else {
     // ------------------------------ epilogue ------------------------------
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 6) >> 2;             // MODE_CE: the 32-column half of every tile this warp owns
     const int row = quarter * 32 + lane;
     const int grow = m_tile * kBM + row;
     const bool row_ok = grow < p.M;
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
       mbar_wait(tm_full + ob, ph);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < kBN / 32; ++cc) {
+      for (int cc = (MODE == MODE_CE ? half : 0); cc < (MODE == MODE_CE ? half + 1 : kBN / 32); ++cc) {
         float v[32];
         tmem_ld32(t_lane + ob * kBN + cc * 32, v);
         const long long c0 = n0 + cc * 32;
@@ -269,7 +276,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
             }
           }
         } else if (MODE == MODE_CE) {
-          if (nvalid > 0) {
+          // running (max, sum exp) of this warp's column half: one max and three instructions (fma, ex2, add) per logit
+          constexpr float kL2e = 1.4426950408889634f;
+          if (nvalid == 32) {
+            float cm = v[0];
+#pragma unroll
+            for (int i = 1; i < 32; ++i) cm = fmaxf(cm, v[i]);
+            const float nm = fmaxf(run_m, cm);
+            const float off = -nm * kL2e;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float e0, e1;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(v[i], kL2e, off)));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(v[i + 1], kL2e, off)));
+              s0 += e0; s1 += e1;
+            }
+            float rs;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaf(run_m, kL2e, off)));     // ex2(-inf) = 0 on the first tile
+            run_s = run_s * rs + (s0 + s1);
+            run_m = nm;
+          } else if (nvalid > 0) {
             float cm = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 32; ++i) if (i < nvalid) cm = fmaxf(cm, v[i]);
@@ -331,9 +358,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) logits_tc_kernel(const LogitsPa
       tc_fence_before();
       mbar_arrive(tm_empty + ob);
     }
-    if (MODE == MODE_CE && row_ok) {
-      float* o = p.partial + ((long long)grow * p.n_chunks + chunk) * 2;
-      o[0] = run_m; o[1] = run_s;
+    if (MODE == MODE_CE) {
+      // the two column halves of a row meet once: the upper warp parks its pair, the lower one combines and stores
+      float2* pair = reinterpret_cast<float2*>(smem + Cfg::kOffPair);
+      if (half == 1) pair[row] = make_float2(run_m, run_s);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::kEpiWarps) : "memory");
+      if (half == 0 && row_ok) {
+        const float2 o2 = pair[row];
+        const float nm = fmaxf(run_m, o2.x);
+        float s = 0.f;
+        if (run_s > 0.f) s += run_s * __expf(run_m - nm);
+        if (o2.y > 0.f) s += o2.y * __expf(o2.x - nm);
+        float* o = p.partial + ((long long)grow * p.n_chunks + chunk) * 2;
+        o[0] = nm; o[1] = s;
+      }
     }
     if (MODE == MODE_TOPK && row_ok) {
       float* ov = p.pval + ((long long)grow * p.n_slots + chunk) * p.k;
@@ -507,7 +545,7 @@ static int launch_tc(LogitsParams& p, cudaStream_t st, const char* who, int batc
   if (MODE == MODE_TOPK) logits_plan_topk(p);
   cudaError_t e = cudaFuncSetAttribute(logits_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) { set_error("%s: smem attr: %s", who, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
-  launch_pdl(logits_tc_kernel<MODE>, dim3(p.m_tiles * p.n_chunks, batch), dim3(kTcThreads), Cfg::kSmemBytes, st, p);
+  launch_pdl(logits_tc_kernel<MODE>, dim3(p.m_tiles * p.n_chunks, batch), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, p);
   return check_launch(who);
 }
 

@@ -14,8 +14,9 @@ Two storage modes:
 
   training  : all-gather `out` -> every rank runs the fused tcgen05 CE-partial kernel on ITS table rows for ALL rows ->
               all-gather of the per-row (max, sum-exp) pairs and of the owner's target logit -> local combine (log-sum-exp);
-              backward: shard-local G^T; d_out partial = G.E_shard and dE_shard = G^T.out_calibrated are two problems of one
-              tcgen05 launch (acsr_gemm_batch); reduce-scatter(sum) of d_out; dE_shard needs no traffic.
+              backward: d_out partial = G.E_shard and dE_shard = G^T.out_calibrated with the shard-local G recomputed tile by
+              tile inside the two kernels (acsr_ce_bwd_dout / _dtable: no gradient matrix in HBM); reduce-scatter(sum) of
+              d_out; dE_shard needs no traffic.
   evaluation: all-gather `out` -> fused top-k on the shard (indices offset by the shard start, column 0 skipped on shard 0)
               -> all-gather of the partial lists -> merge of the rank's own rows.
 
@@ -41,16 +42,22 @@ class CudaCompute(object):
     def ce_partial(self, out, table):
         return self.ops.ce_partial(out, table, self.passes)
 
-    def ce_grad_t(self, out, table, lse, target_local, row_scale):
-        return self.ops.ce_grad_matrix_t(out, table, lse, target_local, row_scale, self.passes)
-
-    def grad_gemms(self, Gt, table, row_begin, n_rows, out_all, table_grad):
-        """d_out_all [M,d] = Gt^T . table (contraction over this shard's items) and, when table_grad is given,
-        table_grad += Gt[:, row_begin:row_begin+n_rows] . out_all[row_begin:row_begin+n_rows]: two problems of ONE tcgen05 launch."""
+    def ce_backward_local(self, out_all, table, lse, target_local, row_scale, row_begin, n_rows, table_grad):
+        """-> d_out_all [M,d] = G . table over this shard's items, G = (softmax - onehot(target_local)) * row_scale; when
+        table_grad is given, table_grad += G[row_begin:row_begin+n_rows]^T . out_all[row_begin:row_begin+n_rows].  Hidden size
+        64: G is recomputed tile by tile and stays in registers (acsr_ce_bwd_dout / _dtable); other widths write the shard-local
+        Gt [rows, M] once and run both contractions as two problems of ONE tcgen05 launch."""
         ops = self.ops
-        V, M = Gt.shape
-        d = table.shape[1]
-        d_out = torch.zeros((M, d), dtype=torch.float32, device=Gt.device)
+        M, d = out_all.shape
+        V = table.shape[0]
+        d_out = torch.zeros((M, d), dtype=torch.float32, device=out_all.device)
+        if d == 64:
+            ops.ce_bwd_dout(out_all, table, lse, target_local, row_scale, d_out, self.passes)
+            if table_grad is not None and n_rows > 0:
+                sl = slice(row_begin, row_begin + n_rows)
+                ops.ce_bwd_dtable(out_all[sl], table, lse[sl], target_local[sl], row_scale[sl], table_grad, self.passes)
+            return d_out
+        Gt = ops.ce_grad_matrix_t(out_all, table, lse, target_local, row_scale, self.passes)
         pr = [ops.wgrad_problem(Gt, table, V, M, d, d_out)]
         if table_grad is not None and n_rows > 0:
             pr.append(ops.gemm_problem(Gt[:, row_begin:], out_all[row_begin:], table_grad, V, d, n_rows, a_strides=(M, 1, 0, n_rows),
@@ -185,10 +192,10 @@ class VocabParallel(object):
         lse_all = self._all_gather(st['lse'].view(n_groups, per)).permute(1, 0, 2).reshape(W * R).contiguous()
         scale_all = self._all_gather(row_scale_local.view(n_groups, per)).permute(1, 0, 2).reshape(W * R).contiguous()
         E_s = self.shard(table)
-        Gt = self.compute.ce_grad_t(st['out_all'], E_s, lse_all, (st['tgt_all'] - self.lo).contiguous(), scale_all)     # [rows_s, W*R]
         tg = self.shard(table_grad) if table_grad is not None else None
         # [W*R, d] partial over my item rows; dE of my rows from the training group of every rank (no traffic)
-        d_out_all = self.compute.grad_gemms(Gt, E_s, (table_half or 0) * W * per, W * per, st['out_all'], tg)
+        d_out_all = self.compute.ce_backward_local(st['out_all'], E_s, lse_all, (st['tgt_all'] - self.lo).contiguous(), scale_all,
+                                                   (table_half or 0) * W * per, W * per, tg)
         # back to [rank][group][row] blocks, then every rank receives the sum of its own rows
         d_out_all = d_out_all.view(n_groups, W, per, d).permute(1, 0, 2, 3).reshape(W * R, d)
         return self._reduce_scatter(d_out_all, R)

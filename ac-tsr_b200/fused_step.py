@@ -63,6 +63,8 @@ class FusedTrainStep(object):
         self.order_side = os.environ.get('ACSR_ORDER_SIDE', '1') == '1'     # sequence ordering next to, not in front of, the embedding
         self.fold_attack = os.environ.get('ACSR_FOLD_ATTACK', '1') == '1'   # attack transforms folded into the Q/K/V launch (forward)
         self.pdl = bool(getattr(model, 'pdl', True))            # programmatic dependent launch between the step's kernels
+        # CE backward without the [2B,V] gradient matrix (acsr_ce_bwd_dout / _dtable, hidden size 64); ACSR_CE_FUSED_BWD=0 keeps Gt
+        self.ce_fused_bwd = model.hidden_size == 64 and os.environ.get('ACSR_CE_FUSED_BWD', '1') == '1'
 
     # ------------------------------------------------------------------------------------------
     def _stream_for(self, dev, key):
@@ -247,6 +249,10 @@ class FusedTrainStep(object):
                      _p(jb['row_x']), _p(jb['row_scale']), 2 * B, d, float(m.loss_fct.gamma), 0, B, _p(jb['d_out2']), _p(E.grad), st)
         elif self.vp is not None:       # shard-local G^T, reduce-scatter of d_out, dE into the owner's rows
             jb['d_out2'].copy_(self.vp.ce_backward(vst, E, jb['row_scale'], E.grad, table_half=0, n_groups=2))
+        elif self.ce_fused_bwd:
+            # no [2B,V] gradient matrix: the logits are recomputed tile by tile and G = (softmax - onehot) * row_scale lives in
+            # registers; d_out2 += G . E on the critical path (d_out2 was cleared on the zeroing stream)
+            ops.ce_bwd_dout(jb['out2'], E, jb['lse'], jb['target2'], jb['row_scale'], jb['d_out2'], passes)
         else:
             if jb['Gt'] is None:
                 jb['Gt'] = torch.empty((V, 2 * B), dtype=torch.float32, device=dev)
@@ -267,7 +273,9 @@ class FusedTrainStep(object):
             if dE_stream is not main:
                 dE_stream.wait_stream(main)
             with torch.cuda.stream(dE_stream):
-                if self.tc and B <= 256:
+                if self.ce_fused_bwd:     # dE += G[:B]^T . out[:B], G recomputed (table rows on the UMMA M axis)
+                    ops.ce_bwd_dtable(jb['out2'][:B], E, jb['lse'][:B], jb['target2'][:B], jb['row_scale'][:B], E.grad, passes)
+                elif self.tc and B <= 256:
                     ops.linear_tok(jb['Gt'], V, B, jb['out2'], d, E.grad, d, ldx=2 * B, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
                 else:                   # dE [V,d] += Gt[:, :B] . out[:B]  (rows of the table on the M axis, K = B)
                     ops.gemm_batch([ops.gemm_problem(jb['Gt'], jb['out2'], E.grad, V, d, B, a_strides=(2 * B, 1, 0, B),

@@ -285,6 +285,22 @@ def ce_grad_matrix_t(out, table, lse, target, row_scale, passes=3):
     return Gt
 
 
+def ce_bwd_dout(out, table, lse, target, row_scale, d_out, passes=3):
+    """d_out [M,64] += G . E with G = (softmax - onehot) * row_scale recomputed tile by tile and kept in registers
+    (acsr_ce_bwd_dout, hidden size 64): no [M,V] gradient matrix."""
+    M, d = out.shape
+    LIB.call('acsr_ce_bwd_dout', _p(out), _p(table), _p(lse), _p(target, torch.int64), _p(row_scale), M, table.shape[0], d, passes,
+             _p(d_out), _stream())
+    return d_out
+
+
+def ce_bwd_dtable(out, table, lse, target, row_scale, d_table, passes=3, stream=None):
+    """d_table [V,64] += G^T . out (acsr_ce_bwd_dtable, hidden size 64); rows of `out` whose row_scale is 0 contribute nothing."""
+    M, d = out.shape
+    LIB.call('acsr_ce_bwd_dtable', _p(out), _p(table), _p(lse), _p(target, torch.int64), _p(row_scale), M, table.shape[0], d, passes,
+             _p(d_table), _stream() if stream is None else stream)
+    return d_table
+
 
 def linear_wgrad(dY, X, dW=None, db=None, want_bias=True):
     """dW [N,K] += dY^T.X and db [N] += colsum(dY) with the token axis split over the GPU (acsr_linear_wgrad)."""
@@ -399,8 +415,10 @@ class GatherRowsFn(torch.autograd.Function):
 
 class LogitsCEFn(torch.autograd.Function):
     """loss[g] = mean CE over row group g of softmax(out.E^T) vs target -- acsasrec.py:117-121.
-    Logits never materialise in the forward; the backward writes Gt once, then d_E = Gt.out and d_out = Gt^T.E
-    (reduction over the catalogue) as two problems of one tcgen05 launch (acsr_gemm_batch)."""
+    Logits never materialise, forward or backward: at hidden size 64 the backward recomputes the logits tile by tile on the
+    tensor cores and consumes G = (softmax - onehot) * row_scale in registers (acsr_ce_bwd_dout / acsr_ce_bwd_dtable).  Other
+    widths write Gt once, then d_E = Gt.out and d_out = Gt^T.E (reduction over the catalogue) as two problems of one tcgen05
+    launch (acsr_gemm_batch)."""
 
     @staticmethod
     def forward(ctx, out, table, target, n_groups, passes, row_weight=None):
@@ -429,8 +447,14 @@ class LogitsCEFn(torch.autograd.Function):
         else:
             row_scale = (d_loss.to(torch.float32) / per).view(n_groups, 1).expand(n_groups, per).reshape(-1).contiguous()
         V, d = table.shape
-        Gt = ce_grad_matrix_t(out, table, lse, target, row_scale, passes)
         d_out = d_table = None
+        if d == 64:
+            if ctx.needs_input_grad[0]:
+                d_out = ce_bwd_dout(out, table, lse, target, row_scale, torch.zeros((M, d), dtype=torch.float32, device=out.device), passes)
+            if ctx.needs_input_grad[1]:
+                d_table = ce_bwd_dtable(out, table, lse, target, row_scale, torch.zeros((V, d), dtype=torch.float32, device=out.device), passes)
+            return d_out, d_table, None, None, None, None
+        Gt = ce_grad_matrix_t(out, table, lse, target, row_scale, passes)
         pr = []
         if ctx.needs_input_grad[0]:            # d_out [M,d] = Gt^T . E : contraction over the catalogue, split over the CTAs
             d_out = torch.zeros((M, d), dtype=torch.float32, device=out.device)

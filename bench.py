@@ -150,6 +150,10 @@ def algorithmic_bytes(name, per_step_calls, cfg, B, V):
         return V * d * 4 + 2 * B * d * 4
     if name == 'acsr_logits_ce_grad':
         return per_step_calls * (V * d * 4 + 2 * B * d * 4 + 2 * B * V * 4)
+    if name == 'acsr_ce_bwd_dout':                  # table + out in, d_out read-modify-write (2B rows)
+        return per_step_calls * (V * d * 4 + 2 * B * d * 4 + 2 * (2 * B * d * 4))
+    if name == 'acsr_ce_bwd_dtable':                # table + the calibrated rows of out in, d_table read-modify-write
+        return per_step_calls * (V * d * 4 + B * d * 4 + 2 * V * d * 4)
     if name == 'acsr_adam_step':
         return None                                # filled by caller (28 B / parameter)
     return None

@@ -231,6 +231,17 @@ int acsr_ce_finalize_losses(const float* partial, int n_parts, const float* out,
 int acsr_logits_ce_grad(const float* out, const float* table, const float* lse, const int64_t* target,
                         const float* row_scale, int M, int64_t V, int d, int passes,
                         float* Gt, int64_t ldg, void* stream);
+/* CE backward WITHOUT the [M,V] gradient matrix (hidden size 64; the backward of acsasrec.py:117-121 as autograd runs it through
+ * CrossEntropyLoss and the matmul with item_embedding.weight^T).  G = (exp(out.E^T - lse) - onehot(target)) * row_scale is
+ * recomputed tile by tile on the tensor cores and consumed in registers by the thread that owns the logits row:
+ *   acsr_ce_bwd_dout   : d_out [M,64]   += G . E        (critical path of the step)
+ *   acsr_ce_bwd_dtable : d_table [V,64] += G^T . out    (nothing but the embedding scatter / optimizer consumes it)
+ * Both ACCUMULATE into their output with vector reductions (clear it first); target[m] outside [0,V) = no one-hot in this
+ * table (shard-local targets of the vocab-sharded path).  Other hidden sizes: ACSR_ERR_UNSUPPORTED (acsr_logits_ce_grad). */
+int acsr_ce_bwd_dout(const float* out, const float* table, const float* lse, const int64_t* target, const float* row_scale, int M,
+                     int64_t V, int d, int passes, float* d_out, void* stream);
+int acsr_ce_bwd_dtable(const float* out, const float* table, const float* lse, const int64_t* target, const float* row_scale, int M,
+                       int64_t V, int d, int passes, float* d_table, void* stream);
 /* fused logits + streaming top-k: partial_val/partial_idx [M, n_chunks, k] (each chunk's k best, UNSORTED,
  * padded with -inf/-1); column 0 is excluded (trainer.py:942); idx_offset is added to indices (vocab shards). */
 int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_t V, int d, int passes,

@@ -21,17 +21,15 @@ class TorchCompute(object):
         m = logits.max(1).values
         return torch.stack((m, torch.exp(logits - m[:, None]).sum(1)), -1).unsqueeze(1)
 
-    def ce_grad_t(self, out, table, lse, target_local, row_scale):
-        G = torch.exp(out @ table.t() - lse[:, None])
+    def ce_backward_local(self, out_all, table, lse, target_local, row_scale, row_begin, n_rows, table_grad):
+        G = torch.exp(out_all @ table.t() - lse[:, None])
         ok = (target_local >= 0) & (target_local < table.shape[0])
         rows = torch.nonzero(ok).view(-1)
         G[rows, target_local[rows]] -= 1.0
-        return (G * row_scale[:, None]).t().contiguous()
-
-    def grad_gemms(self, Gt, table, row_begin, n_rows, out_all, table_grad):
+        G = G * row_scale[:, None]
         if table_grad is not None:
-            table_grad += Gt[:, row_begin:row_begin + n_rows] @ out_all[row_begin:row_begin + n_rows]
-        return Gt.t() @ table
+            table_grad += G[row_begin:row_begin + n_rows].t() @ out_all[row_begin:row_begin + n_rows]
+        return G @ table
 
     def gather_rows(self, ids, shard, lo, hi):
         own = (ids >= lo) & (ids < hi)

@@ -485,6 +485,37 @@ def test_logits_ce_forward_backward(A, M, V, groups):
     close(Ec.grad, Eo.grad, 2e-4, 'd_E')
 
 
+@pytest.mark.parametrize('M,V', [(4, 301), (130, 65), (256, 12102), (512, 12102), (300, 20034), (37, 1000), (1024, 129), (128, 128)])
+def test_ce_backward_without_gradient_matrix(A, M, V):
+    """acsr_ce_bwd_dout / acsr_ce_bwd_dtable: d_out = G.E and d_E = G^T.out with G = (softmax - onehot) * row_scale recomputed
+    inside the kernels (no [M,V] matrix); targets outside [0,V) carry no one-hot (shard-local targets); outputs accumulate."""
+    g = torch.Generator().manual_seed(M * 7 + V)
+    out = torch.randn(M, 64, generator=g) * 2
+    E = torch.randn(V, 64, generator=g) * 0.3
+    tgt = torch.randint(-V // 3, V + V // 3, (M,), generator=g)
+    tgt[0] = 0
+    tgt[-1] = V - 1
+    scale = torch.randn(M, generator=g) / M
+    scale[M // 2] = 0.0
+    logits = out.double() @ E.double().t()
+    lse = torch.logsumexp(logits, 1)
+    G = torch.exp(logits - lse[:, None])
+    ok = (tgt >= 0) & (tgt < V)
+    G[torch.nonzero(ok).view(-1), tgt[ok]] -= 1.0
+    G = G * scale.double()[:, None]
+    base_o = torch.randn(M, 64, generator=g) * 1e-3
+    base_e = torch.randn(V, 64, generator=g) * 1e-3
+    ref_dout, ref_dE = base_o.double() + G @ E.double(), base_e.double() + G.t() @ out.double()
+    oc, Ec, lc, tc, sc = out.cuda(), E.cuda(), lse.float().cuda(), tgt.cuda(), scale.cuda()
+    for passes, tol in ((3, 1e-5), (1, 4e-3)):
+        d_out = A.ops.ce_bwd_dout(oc, Ec, lc, tc, sc, base_o.cuda(), passes)
+        d_E = A.ops.ce_bwd_dtable(oc, Ec, lc, tc, sc, base_e.cuda(), passes)
+        close(d_out, ref_dout, tol, 'd_out (passes=%d)' % passes)
+        close(d_E, ref_dE, tol, 'd_E (passes=%d)' % passes)
+    with pytest.raises(A.AcsrError):
+        A.ops.ce_bwd_dout(torch.randn(4, 128).cuda(), torch.randn(9, 128).cuda(), lc[:4], tc[:4], sc[:4], torch.zeros(4, 128).cuda(), 3)
+
+
 @pytest.mark.parametrize('M,V,k', [(4, 301, 50), (256, 12102, 50), (100, 1683, 50), (7, 70, 10), (130, 20034, 20)])
 def test_logits_topk_fused(A, M, V, k):
     g = torch.Generator().manual_seed(M + V + k)
