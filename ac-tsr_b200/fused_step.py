@@ -63,6 +63,8 @@ class FusedTrainStep(object):
         self.order_side = os.environ.get('ACSR_ORDER_SIDE', '1') == '1'     # sequence ordering next to, not in front of, the embedding
         self.fold_attack = os.environ.get('ACSR_FOLD_ATTACK', '1') == '1'   # attack transforms folded into the Q/K/V launch (forward)
         self.pdl = bool(getattr(model, 'pdl', True))            # programmatic dependent launch between the step's kernels
+        # last layer's dense part on the compact rows as ONE launch per direction (acsr_tail_fwd / _bwd); ACSR_TAIL_FUSED=0: six launches
+        self.tail_fused = (self.tc and model.inner_size % 16 == 0 and os.environ.get('ACSR_TAIL_FUSED', '1') == '1')
         # CE backward without the [2B,V] gradient matrix (acsr_ce_bwd_dout / _dtable, hidden size 64); ACSR_CE_FUSED_BWD=0 keeps Gt
         self.ce_fused_bwd = model.hidden_size == 64 and os.environ.get('ACSR_CE_FUSED_BWD', '1') == '1'
 
@@ -407,9 +409,6 @@ class FusedTrainStep(object):
                 # ---- last layer: gather position len-1 of every sequence, then the dense part on the compact rows ----
                 cb = b['c']
                 C = 2 * Bs if need_att else Bs
-                LIB.call('acsr_gather_last_fwd', _p(lb['ctx'][:T]) if need_att else None, _p(lb['ctx'][T:] if need_att else lb['ctx'][:T]),
-                         _p(ln, torch.int64), Bs, L, d, _p(cb['ctx']), st)
-                LIB.call('acsr_gather_last_fwd', None, _p(x), _p(ln, torch.int64), Bs, L, d, _p(cb['x']), st)
                 if m_a is not None or m_f is not None:           # explicit masks of a parity test: the same rows
                     idx = torch.arange(Bs, device=seq.device) * L + ln - 1
                     rows = torch.cat((idx, T + idx)) if need_att else idx
@@ -417,7 +416,19 @@ class FusedTrainStep(object):
                     m_f = None if m_f is None else m_f.reshape(-1, d)[rows].contiguous()
                 cb['m_a'], cb['m_f'] = m_a, m_f
                 out_buf = jb['out2'] if Bs == B else cb['out']   # a single branch writes the joint buffer directly
-                self._post_attn_fwd(layer, cb, cb['x'], Bs, C, out_buf, p_h, rngp, base, act_id, st)
+                if self.tail_fused:
+                    # gather + out-projection + LayerNorm + feed-forward + LayerNorm of the 2*Bs rows: one launch
+                    LIB.call('acsr_tail_fwd', _p(lb['ctx'][:T]), _p(lb['ctx'][T:]) if need_att else None, _p(x), _p(ln, torch.int64),
+                             Bs, L, d, I, act_id, _p(aa.dense.weight), _p(aa.dense.bias), _p(aa.LayerNorm.weight), _p(aa.LayerNorm.bias),
+                             aa.LayerNorm.eps, _p(ff.dense_1.weight), _p(ff.dense_1.bias), _p(ff.dense_2.weight), _p(ff.dense_2.bias),
+                             _p(ff.LayerNorm.weight), _p(ff.LayerNorm.bias), ff.LayerNorm.eps, p_h, _p(m_a), _p(m_f), rngp, base + 3,
+                             base + 5, _p(cb['ctx']), _p(cb['x']), _p(cb['hz']), _p(cb['st_a']), _p(cb['h']), _p(cb['z1']), _p(cb['a1']),
+                             _p(cb['z2']), _p(cb['st_f']), _p(out_buf), st)
+                else:
+                    LIB.call('acsr_gather_last_fwd', _p(lb['ctx'][:T]) if need_att else None, _p(lb['ctx'][T:] if need_att else lb['ctx'][:T]),
+                             _p(ln, torch.int64), Bs, L, d, _p(cb['ctx']), st)
+                    LIB.call('acsr_gather_last_fwd', None, _p(x), _p(ln, torch.int64), Bs, L, d, _p(cb['x']), st)
+                    self._post_attn_fwd(layer, cb, cb['x'], Bs, C, out_buf, p_h, rngp, base, act_id, st)
                 if Bs != B:
                     lo = br['sl'].start
                     jb['out2'][lo:lo + Bs].copy_(cb['out'][:Bs])
@@ -531,9 +542,22 @@ class FusedTrainStep(object):
                     dc_out = cb['d_out']
                     dc_out[:Bs].copy_(jb['d_out2'][lo:lo + Bs])
                     dc_out[Bs:].copy_(jb['d_out2'][B + lo:B + lo + Bs])
-                self._post_attn_bwd(layer, cb, cb, dc_out, cb['x'], C, C, Bs, Bs, cb['d_x'], cb['d_ctx'], p_h, rngp, base, act_id, st, fork, wg)
-                LIB.call('acsr_gather_last_bwd', _p(cb['d_ctx']), _p(ln, torch.int64), Bs, L, d, _p(b['d_ctx'][:T]), _p(b['d_ctx'][T:]), st)
-                LIB.call('acsr_gather_last_bwd', _p(cb['d_x']), _p(ln, torch.int64), Bs, L, d, _p(d_x[:T]), _p(d_x[T:]), st)
+                if self.tail_fused:
+                    g = lambda t: _p(t.grad)     # noqa: E731
+                    LIB.call('acsr_tail_bwd', _p(dc_out), _p(ln, torch.int64), Bs, L, d, I, act_id, 2, _p(cb['x']), _p(cb['hz']),
+                             _p(cb['st_a']), _p(cb['h']), _p(cb['z1']), _p(cb['z2']), _p(cb['st_f']), _p(aa.dense.weight), _p(aa.dense.bias),
+                             _p(aa.LayerNorm.weight), _p(ff.dense_1.weight), _p(ff.dense_1.bias), _p(ff.dense_2.weight),
+                             _p(ff.dense_2.bias), _p(ff.LayerNorm.weight), p_h, _p(cb['m_a']), _p(cb['m_f']), rngp, base + 3, base + 5,
+                             _p(cb['d_z2']), _p(cb['d_z1']), _p(cb['d_hz']), _p(d_x[:T]), _p(d_x[T:]), _p(b['d_ctx'][:T]),
+                             _p(b['d_ctx'][T:]), g(aa.dense.bias), g(aa.LayerNorm.weight), g(aa.LayerNorm.bias), g(ff.dense_1.bias),
+                             g(ff.dense_2.bias), g(ff.LayerNorm.weight), g(ff.LayerNorm.bias), st)
+                    self._wgrad(cb['d_z2'], cb['a1'], Bs, ff.dense_2.weight.grad, None, fork, wg)
+                    self._wgrad(cb['d_z1'], cb['h'], Bs, ff.dense_1.weight.grad, None, fork, wg)
+                    self._wgrad(cb['d_hz'], cb['ctx'], Bs, aa.dense.weight.grad, None, fork, wg)
+                else:
+                    self._post_attn_bwd(layer, cb, cb, dc_out, cb['x'], C, C, Bs, Bs, cb['d_x'], cb['d_ctx'], p_h, rngp, base, act_id, st, fork, wg)
+                    LIB.call('acsr_gather_last_bwd', _p(cb['d_ctx']), _p(ln, torch.int64), Bs, L, d, _p(b['d_ctx'][:T]), _p(b['d_ctx'][T:]), st)
+                    LIB.call('acsr_gather_last_bwd', _p(cb['d_x']), _p(ln, torch.int64), Bs, L, d, _p(d_x[:T]), _p(d_x[T:]), st)
             else:
                 self._post_attn_bwd(layer, lb, lb, d_out, x, T2, P, T, T, d_x, b['d_ctx'], p_h, rngp, base, act_id, st, fork, wg, b=b)
             # fused attention backward (d_gate_logit accumulates over heads: cleared at the start of the step)

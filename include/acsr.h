@@ -356,6 +356,31 @@ typedef struct acsr_gemm_problem {
 int acsr_gemm_batch(const acsr_gemm_problem* problems, int n_problems, int passes, void* stream);
 int acsr_gemm_ce_parts(int64_t V);
 
+/* ---- the last encoder layer after its attention, on the rows that feed the losses (one launch per direction) ----
+ * Replaces, for hidden size 64 and inner size <= 256 (multiple of 16), the chain the reference runs on all T rows although only
+ * position len-1 of every sequence reaches the loss (abstract_recommender.py:130-134 gather_indexes after layers.py:676-684 and
+ * layers.py:790-798): gather -> dense + dropout + residual + LayerNorm -> FeedForward (dense_1, activation, dense_2, dropout,
+ * residual, LayerNorm).  Rows [0,B) come from ctx_first (calibrated), rows [B,2B) from ctx_second (attacked; NULL: B rows only);
+ * x [T,64] is the layer input (residual).  Saved for the backward, same meaning as in the unfused path: c_ctx [C,64], c_x [B,64],
+ * hz / z2 = GEMM outputs before bias, st_a / st_f = (mean, rstd) [C,2], h, z1 / a1 [C,I], out [C,64].  Dropout: explicit masks
+ * [C,64] or Philox streams stream_a / stream_f with the counters of acsr_bias_dropout_res_ln_fwd. */
+int acsr_tail_fwd(const float* ctx_first, const float* ctx_second, const float* x, const int64_t* item_len, int B, int L, int d, int I,
+                  int act, const float* Wo, const float* bo, const float* lnA_w, const float* lnA_b, float epsA, const float* W1,
+                  const float* b1, const float* W2, const float* b2, const float* lnF_w, const float* lnF_b, float epsF, float p_drop,
+                  const float* mask_a, const float* mask_f, const void* rng, uint32_t stream_a, uint32_t stream_f, float* c_ctx,
+                  float* c_x, float* hz, float* st_a, float* h, float* z1, float* a1, float* z2, float* st_f, float* out, void* stream);
+/* backward of acsr_tail_fwd over C = n_groups * B cotangent rows d_out [C,64]: writes d_z2, d_hz [C,64] and d_z1 [C,I] (the
+ * left operands of the three weight-gradient reductions), scatters the gradients of the attention context and of the layer input
+ * to position len-1 of the token-major buffers d_ctx_* / d_x_* [T,64] (cleared by the caller), and ACCUMULATES the bias /
+ * LayerNorm gradients from rows [0,B) (the calibrated stream owns the parameters, trainer.py:672-686). */
+int acsr_tail_bwd(const float* d_out, const int64_t* item_len, int B, int L, int d, int I, int act, int n_groups, const float* c_x,
+                  const float* hz, const float* st_a, const float* h, const float* z1, const float* z2, const float* st_f,
+                  const float* Wo, const float* bo, const float* lnA_w, const float* W1, const float* b1, const float* W2,
+                  const float* b2, const float* lnF_w, float p_drop, const float* mask_a, const float* mask_f, const void* rng,
+                  uint32_t stream_a, uint32_t stream_f, float* d_z2, float* d_z1, float* d_hz, float* d_x_first, float* d_x_second,
+                  float* d_ctx_first, float* d_ctx_second, float* g_bo, float* g_lnA_w, float* g_lnA_b, float* g_b1, float* g_b2,
+                  float* g_lnF_w, float* g_lnF_b, void* stream);
+
 /* ---- loss_type BPR (model/sequential_recommender/acsasrec.py:109-116, model/loss.py:21-47) ----
  * x_m = out_m . (E[pos_m] - E[neg_m]); row_loss[m] = -log(gamma + sigmoid(x_m)); loss[g] = mean over row group g
  * (M rows in n_groups equal groups: [calibrated ; attacked] in the fused step).  row_x [M] is saved for the backward. */

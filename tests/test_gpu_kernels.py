@@ -113,6 +113,84 @@ def test_bias_act(A, act, n):
     close(bc.grad, bo.grad, 2e-4, 'dbias')
 
 
+@pytest.mark.parametrize('B,L,I,groups,act,p', [(37, 7, 256, 2, 'gelu', 0.3), (256, 50, 256, 2, 'gelu', 0.5), (5, 50, 64, 1, 'relu', 0.0),
+                                                (130, 20, 48, 2, 'swish', 0.2)])
+def test_tail_fused_last_layer(A, B, L, I, groups, act, p):
+    """acsr_tail_fwd / acsr_tail_bwd (the last layer's dense part on the rows that feed the losses, one launch per direction)
+    against fp64 autograd of the same chain (layers.py:676-684, 790-798 + gather_indexes) with injected dropout masks."""
+    from ac_tsr_b200._lib import LIB
+    _p = A.ops._p
+    g = torch.Generator().manual_seed(B * 3 + L + I)
+    T, d, C = B * L, 64, groups * B
+    r = lambda *s: torch.randn(*s, generator=g)       # noqa: E731
+    ctx = [r(T, d) for _ in range(groups)]
+    x = r(T, d)
+    ln = torch.randint(1, L + 1, (B,), generator=g)
+    ln[0] = 1
+    ln[-1] = L
+    Wo, bo, W1, b1, W2, b2 = r(d, d) * 0.2, r(d) * 0.1, r(I, d) * 0.2, r(I) * 0.1, r(d, I) * 0.1, r(d) * 0.1
+    lnAw, lnAb, lnFw, lnFb = 1 + 0.1 * r(d), 0.1 * r(d), 1 + 0.1 * r(d), 0.1 * r(d)
+    m_a, m_f = drop((C, d), p, g), drop((C, d), p, g)
+    d_out = r(C, d)
+    # ---- fp64 reference ----
+    P = [t.double().requires_grad_(True) for t in (Wo, bo, W1, b1, W2, b2, lnAw, lnAb, lnFw, lnFb)]
+    cd = [t.double().requires_grad_(True) for t in ctx]
+    xd = x.double().requires_grad_(True)
+    pos = torch.arange(B) * L + ln - 1
+    c_ctx = torch.cat([c[pos] for c in cd])
+    c_x = xd[pos].repeat(groups, 1)
+    hz = c_ctx @ P[0].t()
+    h = torch.nn.functional.layer_norm((hz + P[1]) * m_a.double() + c_x, (d,), P[6], P[7], 1e-12)
+    z1 = h @ P[2].t()
+    a1 = O.act_fn(act)(z1 + P[3])
+    z2 = a1 @ P[4].t()
+    out = torch.nn.functional.layer_norm((z2 + P[5]) * m_f.double() + h, (d,), P[8], P[9], 1e-12)
+    # parameters are trained by the first group's rows only (trainer.py:672-686); inputs receive every row's gradient
+    w_in = d_out.double().clone()
+    (out * w_in).sum().backward(retain_graph=True)
+    d_ctx_ref = [c.grad.clone() for c in cd]
+    d_x_ref = None
+    # ---- CUDA ----
+    dev = 'cuda'
+    f = lambda *s: torch.empty(*s, device=dev)        # noqa: E731
+    S = dict(ctx=f(C, d), x=f(B, d), hz=f(C, d), st_a=f(C, 2), h=f(C, d), z1=f(C, I), a1=f(C, I), z2=f(C, d), st_f=f(C, 2), out=f(C, d))
+    W = [t.to(dev) for t in (Wo, bo, lnAw, lnAb, W1, b1, W2, b2, lnFw, lnFb)]
+    cg = [t.to(dev) for t in ctx]
+    xg, lng, mag, mfg = x.to(dev), ln.to(dev), m_a.to(dev), m_f.to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    aid = A.ops.ACT_IDS[act]
+    LIB.call('acsr_tail_fwd', _p(cg[0]), _p(cg[1]) if groups == 2 else None, _p(xg), _p(lng, torch.int64), B, L, d, I, aid,
+             _p(W[0]), _p(W[1]), _p(W[2]), _p(W[3]), 1e-12, _p(W[4]), _p(W[5]), _p(W[6]), _p(W[7]), _p(W[8]), _p(W[9]), 1e-12, p,
+             _p(mag), _p(mfg), None, 0, 0, _p(S['ctx']), _p(S['x']), _p(S['hz']), _p(S['st_a']), _p(S['h']), _p(S['z1']), _p(S['a1']),
+             _p(S['z2']), _p(S['st_f']), _p(S['out']), st)
+    close(S['out'], out, 2e-5, 'out')
+    close(S['h'], h, 2e-5, 'h')
+    close(S['a1'], a1, 2e-5, 'a1')
+    close(S['hz'], hz, 1e-5, 'hz')
+    assert torch.equal(S['ctx'].cpu(), torch.cat([c[pos] for c in ctx]))
+    G = dict(d_z2=f(C, d), d_z1=f(C, I), d_hz=f(C, d), d_x=torch.zeros(groups, T, d, device=dev), d_ctx=torch.zeros(groups, T, d, device=dev))
+    gp = [torch.zeros(n, device=dev) for n in (d, d, d, I, d, d, d)]          # bo, lnA_w, lnA_b, b1, b2, lnF_w, lnF_b
+    LIB.call('acsr_tail_bwd', _p(d_out.to(dev)), _p(lng, torch.int64), B, L, d, I, aid, groups, _p(S['x']), _p(S['hz']), _p(S['st_a']),
+             _p(S['h']), _p(S['z1']), _p(S['z2']), _p(S['st_f']), _p(W[0]), _p(W[1]), _p(W[2]), _p(W[4]), _p(W[5]), _p(W[6]), _p(W[7]),
+             _p(W[8]), p, _p(mag), _p(mfg), None, 0, 0, _p(G['d_z2']), _p(G['d_z1']), _p(G['d_hz']), _p(G['d_x'][0]),
+             _p(G['d_x'][1]) if groups == 2 else None, _p(G['d_ctx'][0]), _p(G['d_ctx'][1]) if groups == 2 else None,
+             *[_p(t) for t in gp], st)
+    for gi in range(groups):
+        close(G['d_ctx'][gi], d_ctx_ref[gi], 5e-5, 'd_ctx[%d]' % gi)
+    close(G['d_x'].sum(0), xd.grad, 5e-5, 'd_x')
+    # parameter gradients: only the first group's rows
+    for t in P + cd + [xd]:
+        t.grad = None
+    w_in[B:] = 0
+    (out * w_in).sum().backward()
+    for got, ref, name in zip(gp, (P[1], P[6], P[7], P[3], P[5], P[8], P[9]), ('bo', 'lnA_w', 'lnA_b', 'b1', 'b2', 'lnF_w', 'lnF_b')):
+        close(got, ref.grad, 1e-4, 'grad ' + name)
+    # the weight gradients come from the saved left operands: dW2 = d_z2[:B]^T . a1[:B] etc.
+    close(G['d_z2'][:B].double().t() @ S['a1'][:B].double(), P[4].grad, 1e-4, 'dW2')
+    close(G['d_z1'][:B].double().t() @ S['h'][:B].double(), P[2].grad, 1e-4, 'dW1')
+    close(G['d_hz'][:B].double().t() @ S['ctx'][:B].double(), P[0].grad, 1e-4, 'dWo')
+
+
 def test_gather_last(A):
     g = torch.Generator().manual_seed(1)
     B, L, d = 9, 50, 64
