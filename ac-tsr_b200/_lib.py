@@ -170,9 +170,10 @@ class KernelTimer:
     """Brackets every C-ABI launch with CUDA events on the launching (current torch) stream.
     Used by bench.py for the per-kernel share / roofline numbers; never active in the timed step."""
 
-    def __init__(self):
+    def __init__(self, keep_calls=False):
         self.events = []             # (name, start, stop)
         self.launches = 0
+        self.calls = [] if keep_calls else None      # (name, args, algorithmic bytes) of every launch, for replay_in_graph
 
     def timed_call(self, lib, dll, name, args):
         import torch
@@ -184,7 +185,10 @@ class KernelTimer:
             msg = dll.acsr_last_error()
             raise AcsrError('%s failed (%d): %s' % (name, rc, msg.decode() if msg else ''))
         fn = ALGO_BYTES.get(name)
-        self.events.append((name, e0, e1, fn(args) if fn is not None else None))
+        ab = fn(args) if fn is not None else None
+        self.events.append((name, e0, e1, ab))
+        if self.calls is not None:
+            self.calls.append((name, args, ab, torch.cuda.current_stream()))
         self.launches += 1
 
     def summary(self):
@@ -198,6 +202,56 @@ class KernelTimer:
             if ab is not None:
                 self.bytes[name] = self.bytes.get(name, 0) + ab
         return out
+
+
+def replay_in_graph(lib, calls, reps=16, skip=('acsr_adam_step', 'acsr_rng_advance'), per_call=None):
+    """Device time of every recorded launch INSIDE a CUDA graph: each call (same arguments, same buffers) is captured `reps`
+    times back to back into its own graph and the replay is bracketed by events -- no host launch path and no event-record
+    overhead between the kernels (an event pair around one eager launch costs ~12 us on B200, more than most kernels of the
+    step), warm L2 as in the real step, programmatic dependent launch between the copies as between the step's kernels.
+    -> {name: [n_calls, total_us, total_algorithmic_bytes]}.  Calls that change persistent state (optimizer, rng) are skipped."""
+    import torch
+    dll = lib.load()
+    out = {}
+    side = torch.cuda.Stream()
+    for name, args, ab, _ in calls:
+        if name in skip:
+            continue
+        a = list(args)
+        fn = getattr(dll, name)
+        argl = lib.protos[name][1]
+        si = [i for i, (an, _) in enumerate(argl) if an == 'stream']
+        g = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            if si:
+                a[si[0]] = side.cuda_stream
+            rc = fn(*a)                                        # warm-up outside the capture (function attributes, L2)
+            side.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                if si:
+                    a[si[0]] = torch.cuda.current_stream().cuda_stream
+                for _ in range(reps):
+                    rc |= fn(*a)
+            if rc != 0:
+                raise AcsrError('%s failed during the in-graph replay' % name)
+            g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            g.replay()
+            e1.record()
+            side.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (2 * reps)
+        rec = out.setdefault(name, [0, 0.0, 0])
+        rec[0] += 1
+        rec[1] += us
+        rec[2] += ab or 0
+        if per_call is not None:
+            per_call.append((name, [x for x in args if isinstance(x, int) and abs(x) < (1 << 24)][:12], round(us, 2), ab))
+        del g
+    torch.cuda.current_stream().wait_stream(side)
+    return out
 
 
 LIB = _Lib()
