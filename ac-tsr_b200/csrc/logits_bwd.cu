@@ -17,7 +17,9 @@
 
 namespace acsr {
 
-constexpr int kBwThreads = 448;        // warp 0 producer, warp 1 MMA, warps 2-5 splitter, warps 6-13 epilogue
+constexpr int kBwThreads = 480;        // warp 0 producer, warp 1 MMA1 issuer, warps 2-5 splitter, warps 6-13 epilogue, warp 14 MMA2 issuer
+constexpr int kBwIssuer2 = 14;         // (one thread issues a 128 x N x 8 TF32 MMA every ~90 cycles whatever N <= 128 is -- scripts/umma_rate.py;
+                                       // two issuing threads double the rate, so the logits MMAs and the G-consuming MMAs get a warp each)
 constexpr int kBwEpiThreads = 256;
 constexpr int kBwTmemCols = 512;
 
@@ -94,7 +96,7 @@ struct DoutCfg {
   static constexpr int kOpsBytes = 4 * kBbytes;
   static constexpr int kOffStg = kOffOps + 2 * kOpsBytes;
   static constexpr int kOffBar = kOffStg + kStages * kBbytes;
-  static constexpr int kNumBars = 2 * kStages + 4 + 4 + 2 + 2 + 1;
+  static constexpr int kNumBars = 2 * kStages + 4 + 4 + 2 + 2 + 2 + 1;
   static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
   static constexpr int kColX = 0, kColY = 128, kColD = 256, kColAhi = 320, kColAlo = 384;
 };
@@ -116,7 +118,8 @@ __global__ void __launch_bounds__(kBwThreads, 1) ce_dout_kernel(const CeBwdParam
   uint64_t* t_empty = t_full + 2;
   uint64_t* l_full = t_empty + 2;                  // logits in X[b]       : MMA1 -> epilogue
   uint64_t* g_full = l_full + 2;                   // G in X[b] / Y[b]     : epilogue -> MMA2
-  uint64_t* d_full = g_full + 2;
+  uint64_t* g_empty = g_full + 2;                  // MMA2 retired: X[b] / Y[b] may take the next logits (the two issuers are not ordered)
+  uint64_t* d_full = g_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
 
   if (threadIdx.x == 0) {
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) ce_dout_kernel(const CeBwdParam
     for (int s = 0; s < 2; ++s) {
       mbar_init(e_full + s, 128); mbar_init(e_empty + s, 1);
       mbar_init(t_full + s, 128); mbar_init(t_empty + s, 1);
-      mbar_init(l_full + s, 1); mbar_init(g_full + s, kBwEpiThreads);
+      mbar_init(l_full + s, 1); mbar_init(g_full + s, kBwEpiThreads); mbar_init(g_empty + s, 1);
     }
     mbar_init(d_full, 1);
     mbar_fence_init();
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) ce_dout_kernel(const CeBwdParam
   const int grow = m_tile * kBM + row;
   const bool row_ok = grow < p.M;
   const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 32;
-  if (warp >= 6) {   // the thread's row of `out` (its 32 columns) -> TMEM, hi and lo
+  if (warp >= 6 && warp < kBwIssuer2) {   // the thread's row of `out` (its 32 columns) -> TMEM, hi and lo
     float hi[32], lo[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -171,59 +174,61 @@ __global__ void __launch_bounds__(kBwThreads, 1) ce_dout_kernel(const CeBwdParam
         bulk_g2s(smem + Cfg::kOffStg + s * Cfg::kBbytes, p.table + n0 * kD, (uint32_t)(rows * kD * 4), stg_full + s);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == kBwIssuer2) {
     if (lane == 0 && my_tiles > 0) {
       const uint32_t idesc = umma_idesc_tf32(kBM, kBN);          // both MMAs are 128 x 64 x 8
       const uint32_t a_hi = tmem_base + Cfg::kColAhi, a_lo = tmem_base + Cfg::kColAlo;
       constexpr uint32_t kBLbo = kBN * 16, kSbo = 128;
       const int npass = p.passes == 3 ? 3 : 1;
-      auto issue_logits = [&](int it) {
-        const int ob = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(e_full + ob, ph);
-        tc_fence_after();
-        const uint32_t b_hi = smem_u32(smem + Cfg::kOffOps + ob * Cfg::kOpsBytes);
-        const uint32_t b_lo = b_hi + Cfg::kBbytes;
-        const uint32_t d_tmem = tmem_base + Cfg::kColX + ob * kBN;
-        uint32_t acc = 0;
-        for (int ps = 0; ps < npass; ++ps) {
-          const uint32_t a_base = (npass == 3 && ps == 0) ? a_lo : a_hi;
-          const uint32_t b_base = (npass == 3 && ps == 1) ? b_lo : b_hi;
+      if (warp == 1) {
+        // ---- MMA1: logits of every tile into X[b] ----
+        for (int it = 0; it < my_tiles; ++it) {
+          const int ob = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          mbar_wait(e_full + ob, ph);
+          mbar_wait(g_empty + ob, ph ^ 1);        // MMA2 of tile it-2 no longer reads X[b] / Y[b]
+          tc_fence_after();
+          const uint32_t b_hi = smem_u32(smem + Cfg::kOffOps + ob * Cfg::kOpsBytes);
+          const uint32_t b_lo = b_hi + Cfg::kBbytes;
+          const uint32_t d_tmem = tmem_base + Cfg::kColX + ob * kBN;
+          uint32_t acc = 0;
+          for (int ps = 0; ps < npass; ++ps) {
+            const uint32_t a_base = (npass == 3 && ps == 0) ? a_lo : a_hi;
+            const uint32_t b_base = (npass == 3 && ps == 1) ? b_lo : b_hi;
 #pragma unroll
-          for (int ks = 0; ks < kD / 8; ++ks) {
-            umma_tf32_ts(d_tmem, a_base + ks * 8, umma_desc_kmajor(b_base + ks * 2 * kBLbo, kBLbo, kSbo), idesc, acc);
-            acc = 1;
+            for (int ks = 0; ks < kD / 8; ++ks) {
+              umma_tf32_ts(d_tmem, a_base + ks * 8, umma_desc_kmajor(b_base + ks * 2 * kBLbo, kBLbo, kSbo), idesc, acc);
+              acc = 1;
+            }
           }
+          umma_commit(e_empty + ob);      // the K = hidden layout of this table tile is free once the logits MMAs retired
+          umma_commit(l_full + ob);
         }
-        umma_commit(e_empty + ob);      // the K = hidden layout of this table tile is free once the logits MMAs retired
-        umma_commit(l_full + ob);
-      };
-      auto issue_dout = [&](int it) {
-        const int ob = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(t_full + ob, ph);
-        mbar_wait(g_full + ob, ph);
-        tc_fence_after();
-        const uint32_t t_hi = smem_u32(smem + Cfg::kOffOps + ob * Cfg::kOpsBytes + 2 * Cfg::kBbytes);   // E^T: N = hidden, K = table rows
-        const uint32_t t_lo = t_hi + Cfg::kBbytes;
-        const uint32_t g_hi = tmem_base + Cfg::kColX + ob * kBN, g_lo = tmem_base + Cfg::kColY + ob * kBN;
-        const uint32_t d_tmem = tmem_base + Cfg::kColD;
-        for (int ps = 0; ps < npass; ++ps) {
-          const uint32_t a_base = (npass == 3 && ps == 0) ? g_lo : g_hi;
-          const uint32_t b_base = (npass == 3 && ps == 1) ? t_lo : t_hi;
+      } else {
+        // ---- MMA2: d_out += G . E of every tile, from its own issuing thread ----
+        for (int it = 0; it < my_tiles; ++it) {
+          const int ob = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          mbar_wait(t_full + ob, ph);
+          mbar_wait(g_full + ob, ph);
+          tc_fence_after();
+          const uint32_t t_hi = smem_u32(smem + Cfg::kOffOps + ob * Cfg::kOpsBytes + 2 * Cfg::kBbytes);   // E^T: N = hidden, K = table rows
+          const uint32_t t_lo = t_hi + Cfg::kBbytes;
+          const uint32_t g_hi = tmem_base + Cfg::kColX + ob * kBN, g_lo = tmem_base + Cfg::kColY + ob * kBN;
+          const uint32_t d_tmem = tmem_base + Cfg::kColD;
+          for (int ps = 0; ps < npass; ++ps) {
+            const uint32_t a_base = (npass == 3 && ps == 0) ? g_lo : g_hi;
+            const uint32_t b_base = (npass == 3 && ps == 1) ? t_lo : t_hi;
 #pragma unroll
-          for (int ks = 0; ks < kBN / 8; ++ks)
-            umma_tf32_ts(d_tmem, a_base + ks * 8, umma_desc_kmajor(b_base + ks * 2 * kBLbo, kBLbo, kSbo), idesc,
-                         (it > 0 || ps > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < kBN / 8; ++ks)
+              umma_tf32_ts(d_tmem, a_base + ks * 8, umma_desc_kmajor(b_base + ks * 2 * kBLbo, kBLbo, kSbo), idesc,
+                           (it > 0 || ps > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(t_empty + ob);
+          umma_commit(g_empty + ob);
         }
-        umma_commit(t_empty + ob);
-      };
-      issue_logits(0);
-      for (int it = 0; it < my_tiles; ++it) {
-        if (it + 1 < my_tiles) issue_logits(it + 1);      // the next tile's logits run while the epilogue turns this one into G
-        issue_dout(it);
+        umma_commit(d_full);
       }
-      umma_commit(d_full);
     }
   } else if (warp < 6) {
     const int tid = threadIdx.x - 64;   // 0..127
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) ce_dout_kernel(const CeBwdParam
       mbar_arrive(t_full + ob);
       mbar_arrive(stg_empty + s);
     }
-  } else {
+  } else if (warp < kBwIssuer2) {
     // ------------------------------ epilogue: logits -> G (hi in place, lo next to it); at the end the accumulator -> d_out ------------------------------
     float g_c = -INFINITY, g_scale = 0.f;
     long long g_tgt = -1;
@@ -449,7 +454,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) ce_dtable_kernel(const CeBwdPar
         bulk_g2s(smem + Cfg::kOffStg, p.table + n0 * kD, (uint32_t)(rows * kD * 4), stg_full);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == kBwIssuer2) {
     if (lane == 0 && my_tiles > 0) {
       const uint32_t idesc1 = umma_idesc_tf32(kTN, kTM);      // logits^T: 128 table rows x 128 rows of out, K = hidden
       const uint32_t idesc2 = umma_idesc_tf32(kTN, kD);       // d_E tile : 128 table rows x 64, K = rows of out
@@ -496,10 +501,10 @@ __global__ void __launch_bounds__(kBwThreads, 1) ce_dtable_kernel(const CeBwdPar
         umma_commit(g_empty);
         umma_commit(d_full + db);
       };
-      issue_logits(0);
-      for (int it = 0; it < my_tiles; ++it) {
-        if (it + 1 < my_tiles) issue_logits(it + 1);
-        issue_dtable(it);
+      if (warp == 1) {
+        for (int it = 0; it < my_tiles; ++it) issue_logits(it);
+      } else {
+        for (int it = 0; it < my_tiles; ++it) issue_dtable(it);
       }
     }
   } else if (warp < 6) {
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) ce_dtable_kernel(const CeBwdPar
       mbar_arrive(op_full);
       mbar_arrive(stg_empty);
     }
-  } else {
+  } else if (warp < kBwIssuer2) {
     // ------------------------------ epilogue: thread = table row; 64 of the block's 128 rows of `out` per warp ------------------------------
     const int quarter = warp & 3;
     const int half = (warp - 6) >> 2;

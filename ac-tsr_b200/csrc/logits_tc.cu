@@ -37,7 +37,10 @@ struct TcCfg {
   // MODE_CE: the epilogue is instruction-issue bound (one thread per logits row), so it runs on EIGHT warps, two per TMEM lane
   // quarter, each owning one 32-column half of every tile; the halves meet once, at the end, through kOffPair
   static constexpr int kEpiWarps = MODE == MODE_CE ? 8 : 4;
-  static constexpr int kThreads = 192 + 32 * kEpiWarps;
+  // Two MMA-issuing threads (warp 1: even tiles, the last warp: odd tiles -- each owns one operand buffer and one accumulator
+  // stage): a thread issues one 128 x 64 x 8 TF32 MMA every ~90 cycles against a 32-cycle tensor floor (scripts/umma_rate.py)
+  static constexpr int kIssuer2 = 6 + kEpiWarps;
+  static constexpr int kThreads = 192 + 32 * kEpiWarps + 32;
   static constexpr int kOffPair = kOffTopk + kTopkBytes;
   static constexpr int kPairBytes = MODE == MODE_CE ? kBM * 8 : 0;
   static constexpr int kOffBar = kOffPair + kPairBytes;
@@ -144,13 +147,13 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
         bulk_g2s(smem + Cfg::kOffStg + s * Cfg::kBbytes, table_p + n0 * kD, (uint32_t)(rows * kD * 4), stg_full + s);
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
+  } else if (warp == 1 || warp == Cfg::kIssuer2) {
+    // ------------------------------ MMA issuers ------------------------------
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(kBM, kBN);
       const uint32_t a_hi = smem_u32(smem + Cfg::kOffAhi), a_lo = smem_u32(smem + Cfg::kOffAlo);
       constexpr uint32_t kALbo = kBM * 16, kBLbo = kBN * 16, kSbo = 128;
-      for (int it = 0; it < my_tiles; ++it) {
+      for (int it = (warp == 1 ? 0 : 1); it < my_tiles; it += 2) {
         const int ob = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         mbar_wait(op_full + ob, ph);
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
       mbar_arrive(op_full + ob);
       mbar_arrive(stg_empty + s);
     }
-  } else {
+  } else if (warp < Cfg::kIssuer2) {
     // ------------------------------ epilogue ------------------------------
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 6) >> 2;             // MODE_CE: the 32-column half of every tile this warp owns

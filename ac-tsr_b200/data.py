@@ -130,7 +130,7 @@ class TrainDataLoader(object):
 
 class DeviceTrainDataLoader(object):
     """TrainDataLoader with the data resident in HBM: the fields the model reads are uploaded once, the
-    epoch permutation is drawn ON the device (torch.randperm on the CUDA generator seeded from the config seed; the reference
+    epoch permutation is drawn ON the device (sort order of uniform keys from the CUDA generator seeded with the config seed; the reference
     uses a CPU randperm, interaction.py:293-297, so the order differs the way any two seeds differ), and acsr_batch_gather
     writes batch `cursor` into a packed device buffer.  The trainer captures gather + cursor advance inside its CUDA graph, so
     an epoch is nothing but graph replays: no host->device traffic, no host work per step.  Iterating the loader the usual
@@ -188,7 +188,12 @@ class DeviceTrainDataLoader(object):
     def new_epoch(self):
         """draws the epoch's permutation on the device and rewinds the cursor"""
         if self.shuffle:
-            torch.randperm(self.n, generator=self.gen, device=self.device, out=self.perm)
+            # a uniformly random permutation as the sort order of i.i.d. keys, entirely on the device and asynchronous
+            # (torch.randperm on CUDA synchronises / detours through the host for small n: ~80 ms per epoch on the GPU box)
+            if getattr(self, '_keys', None) is None:
+                self._keys = torch.empty(self.n, dtype=torch.float64, device=self.device)
+            self._keys.uniform_(generator=self.gen)
+            self.perm.copy_(torch.sort(self._keys).indices)
         self.cursor.zero_()
         self.pr = 0
 

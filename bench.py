@@ -535,6 +535,15 @@ def run_ours(args):
     sharded = None
     if args.workload == 'c2' and args.batch == 0 and not args.no_vocab_sharded:
         sharded = vocab_sharded_record(A, dev, rank, world, max(10, min(K, 30)), flush)
+    # ---- the long-sequence stress configuration (BASELINE config #5: L=200, d=256, 4 layers, B=2048 per GPU) at this N, batch
+    # data-parallel: eager launches (the long-sequence attention backward walks the batch in workspace-sized chunks) ----
+    longseq = None
+    if args.workload == 'c2' and args.batch == 0 and not args.no_long_seq:
+        try:
+            longseq = long_sequence_record(A, dev, rank, world, 3)
+        except Exception as e:                                          # a sub-record must never sink the bench line
+            longseq = {'error': str(e)[:300]}
+            torch.cuda.empty_cache()
     if rank != 0:
         shutdown()
         return
@@ -584,6 +593,8 @@ def run_ours(args):
         line['large_batch'] = large
     if sharded is not None:
         line['vocab_sharded'] = sharded
+    if longseq is not None:
+        line['long_sequence'] = longseq
     if cpu is not None:
         line['cpu_baseline'] = cpu
         line['cpu_baseline_eval'] = cpu_baseline_eval(cfg, B if args.workload == 'c2' else min(B, 32), L, V, kmax, budget_s=8.0)
@@ -654,6 +665,75 @@ def vocab_sharded_record(A, dev, rank, world, K, flush):
                    'all-gather gradient rows [B*L, d]', 'all-reduce encoder gradients (%d floats)' % (trainer.optimizer.flat_grad.numel() - model.item_embedding.weight.numel())]),
                'launch': 'CUDA graph replay (NCCL collectives captured)'}
         trainer._graph, trainer._eval_graphs = None, {}
+        del trainer, model
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        return rec
+    finally:
+        WORKLOAD.clear()
+        WORKLOAD.update(saved)
+
+
+def long_sequence_record(A, dev, rank, world, K):
+    """BASELINE config #5 (L = 200, d = 256, 4 layers, 4 heads, inner 1024, B = 2048 per GPU; calibrators forward + backward) at
+    `world` GPUs, batch data-parallel, weak scaling: train step and full-sort eval batch, device-timed, max over ranks."""
+    import torch.distributed as dist
+    saved = dict(WORKLOAD)
+    WORKLOAD.clear()
+    WORKLOAD.update(WORKLOADS['c5'])
+    try:
+        B, L, V = WORKLOAD['B'], WORKLOAD['L'], WORKLOAD['V']
+        _, cfg, config, model, trainer = build(dev, rank, world, cuda_graph=False)
+        if world > 1:
+            trainer.enable_data_parallel()
+        nb = 2
+        seq, ln, tgt = A.data.synth_sequences(nb * B, L, V, seed=542 + rank)
+        devb = [A.Interaction({'item_id_list': seq[i * B:(i + 1) * B], 'item_length': ln[i * B:(i + 1) * B],
+                               'item_id': tgt[i * B:(i + 1) * B]}).pack(['item_id_list', 'item_length', 'item_id']).to(dev) for i in range(nb)]
+        it = [0]
+
+        def sync():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+
+        def timed(fn, n):
+            sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            sync()
+            return e0.elapsed_time(e1) / n
+
+        def dev_step():
+            trainer.train_step(devb[it[0] % nb])
+            it[0] += 1
+
+        def eval_dev():
+            b = devb[it[0] % nb]
+            with torch.no_grad():
+                trainer.eval_batch((b, None, None, b['item_id']))
+            it[0] += 1
+        model.train()
+        for _ in range(2):
+            dev_step()
+        ms = timed(dev_step, K)
+        model.eval()
+        eval_dev()
+        ms_eval = timed(eval_dev, K)
+        t = torch.tensor([ms, ms_eval], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_eval = [float(x) for x in t.tolist()]
+        rec = {'workload': workload_string(False), 'n_gpus': world, 'steps': K, 'scaling': 'weak',
+               'value': round(world * B / (ms / 1e3), 1), 'unit': 'seq/s', 'ms_per_step': round(ms, 3),
+               'eval': {'value': round(world * B / (ms_eval / 1e3), 1), 'unit': 'users/s', 'ms_per_batch': round(ms_eval, 3)},
+               'parallelism': 'single GPU' if world == 1 else 'dp%d: NCCL all-reduce of the flat gradient (%d floats)' % (world, trainer.optimizer.flat_grad.numel()),
+               'launch': 'eager launches; inputs larger than L2 (no flush needed: the step touches ~80 GB)'}
         del trainer, model
         import gc
         gc.collect()
@@ -820,6 +900,7 @@ def main():
     ap.add_argument('--no-parity', action='store_true', help='skip the in-run parity check against the CPU oracle')
     ap.add_argument('--no-large-batch', action='store_true', help='skip the B=2048 sub-record')
     ap.add_argument('--no-vocab-sharded', action='store_true', help='skip the 1M-item vocab-sharded sub-record')
+    ap.add_argument('--no-long-seq', action='store_true', help='skip the long-sequence (config #5) sub-record')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS), help='c2 = the headline configuration (default)')
     ap.add_argument('--full-len', action='store_true', help='every sequence has the maximum length (worst case) instead of LogNormal lengths')
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the workload')
