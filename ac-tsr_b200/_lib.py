@@ -161,7 +161,7 @@ def _ab_gemm_batch(a):
 
 
 # ALGORITHMIC bytes of one launch, from the call's own arguments
-ALGO_BYTES = {'acsr_linear_tok': _ab_linear_tok, 'acsr_linear_tok_bdrl': _ab_linear_tok_bdrl,
+ALGO_BYTES = {'acsr_linear_tok': _ab_linear_tok, 'acsr_linear_tok_ragged': _ab_linear_tok, 'acsr_linear_tok_bdrl': _ab_linear_tok_bdrl,
               'acsr_linear_wgrad': _ab_linear_wgrad, 'acsr_linear_wgrad_batched': _ab_linear_wgrad_batched,
               'acsr_gemm_batch': _ab_gemm_batch}
 

@@ -43,6 +43,7 @@ struct LinTokParams {
   // plan
   int m_tiles, n_blocks, NB, KBn, nbuf;                              // NB: features per CTA (multiple of 16), KBn = ceil(K/64)
   int w_static;                                                      // W / bias are registered parameters (acsr_register_static): staged before griddepcontrol.wait
+  int last_n; long long last_ldy;                                    // > 0: the LAST problem of a batched launch has this many features / this row stride of Y
 };
 
 struct LtSmem {
@@ -79,6 +80,9 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
   const float* biasp = p.bias ? p.bias + bz * p.bb : nullptr;
   float* Yp = p.Y + bz * p.by;
   const int NB = p.NB, KBn = p.KBn, nbuf = p.nbuf;
+  const bool is_last = p.last_n > 0 && bz == p.batch - 1;
+  const int Neff = is_last ? p.last_n : p.N;                      // (the gate logits ride along with the five projections: 50 features, row stride 50)
+  const long long ldy_eff = is_last ? p.last_ldy : p.ldy;
   const int b_bytes = NB * KBn * kLtKB * 4;
   uint8_t* sBhi = smem;
   uint8_t* sBlo = smem + b_bytes;
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
         const int n = item % NB, kc = item / NB;
         const int kb = kc / (kLtKB / 4), kcl = kc % (kLtKB / 4);
         const int k0 = kb * kLtKB + kcl * 4;
-        if (n0 + n < p.N && k0 < p.K) {
+        if (n0 + n < Neff && k0 < p.K) {
           const float* w = Wp + kb * p.wkb + (long long)(n0 + n) * p.w_sn + (long long)(kcl * 4) * p.w_sk;
           if (vec_ok && k0 + 4 <= p.K) xs[u] = __ldg(reinterpret_cast<const float4*>(w));
           else {
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
         lt_split_store(Bhi + off, Blo + off, xs[u]);
       }
     }
-    for (int i = sid; i < 128; i += kStagers) sBias[i] = (biasp != nullptr && n0 + i < p.N) ? biasp[n0 + i] : 0.f;
+    for (int i = sid; i < 128; i += kStagers) sBias[i] = (biasp != nullptr && n0 + i < Neff) ? biasp[n0 + i] : 0.f;
   }
   if (stage_early) pdl_wait();
   fence_proxy_async();
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int ncols = min(NB, p.N - n0);          // valid features of this block
+    const int ncols = min(NB, Neff - n0);         // valid features of this block
     int it = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
       const int ts = it & 1;
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
           tmem_ld32(t_lane + ts * NB + cc * 32, v);
           const int nvalid = min(32, ncols - cc * 32);
           if (row_ok) {
-            float* y = Yp + grow * p.ldy + n0 + cc * 32;
+            float* y = Yp + grow * ldy_eff + n0 + cc * 32;
             const bool vec = nvalid == 32 && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
             if (EPI == EPI_ACT) {
               // Y = raw GEMM output (pre-bias, saved for the backward), Y2 = act(Y + bias)
@@ -414,8 +418,17 @@ extern "C" {
 int acsr_linear_tok(const float* X, int64_t ldx, int64_t x_kblock_stride, int64_t rows, int K, const float* W, int64_t w_stride_n,
                     int64_t w_stride_k, int64_t w_kblock_stride, int N, const float* bias, int accumulate, float* Y, int64_t ldy,
                     int batch, int64_t stride_x, int64_t stride_w, int64_t stride_bias, int64_t stride_y, int passes, void* stream) {
+  return acsr_linear_tok_ragged(X, ldx, x_kblock_stride, rows, K, W, w_stride_n, w_stride_k, w_kblock_stride, N, bias, accumulate, Y, ldy,
+                                batch, stride_x, stride_w, stride_bias, stride_y, 0, 0, passes, stream);
+}
+
+int acsr_linear_tok_ragged(const float* X, int64_t ldx, int64_t x_kblock_stride, int64_t rows, int K, const float* W, int64_t w_stride_n,
+                           int64_t w_stride_k, int64_t w_kblock_stride, int N, const float* bias, int accumulate, float* Y, int64_t ldy,
+                           int batch, int64_t stride_x, int64_t stride_w, int64_t stride_bias, int64_t stride_y, int last_n,
+                           int64_t last_ldy, int passes, void* stream) {
   ACSR_REQUIRE(X && W && Y, "linear_tok: NULL pointer");
   ACSR_REQUIRE(rows >= 0 && N > 0 && K > 0 && batch > 0 && batch < 65536 && ldy >= N, "linear_tok: bad sizes");
+  ACSR_REQUIRE(last_n == 0 || (last_n > 0 && last_n <= N && last_ldy >= last_n && batch > 1), "linear_tok: bad ragged last problem");
   ACSR_REQUIRE(passes == 1 || passes == 3, "linear_tok: passes must be 1 or 3");
   if (rows == 0) return ACSR_OK;
   LinTokParams p = {};
@@ -423,7 +436,7 @@ int acsr_linear_tok(const float* X, int64_t ldx, int64_t x_kblock_stride, int64_
   p.W = W; p.w_sn = w_stride_n; p.w_sk = w_stride_k; p.wkb = w_kblock_stride; p.N = N;
   p.bias = bias; p.accumulate = accumulate; p.Y = Y; p.ldy = ldy;
   p.batch = batch; p.bx = stride_x; p.bw = stride_w; p.bb = stride_bias; p.by = stride_y;
-  p.passes = passes; p.epi = EPI_PLAIN;
+  p.passes = passes; p.epi = EPI_PLAIN; p.last_n = last_n; p.last_ldy = last_ldy;
   p.w_static = is_static_memory(p.W) && (p.bias == nullptr || is_static_memory(p.bias));
   return lt_launch<EPI_PLAIN>(p, (cudaStream_t)stream, "linear_tok");
 }

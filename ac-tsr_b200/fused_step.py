@@ -62,6 +62,9 @@ class FusedTrainStep(object):
         import os
         self.order_side = os.environ.get('ACSR_ORDER_SIDE', '1') == '1'     # sequence ordering next to, not in front of, the embedding
         self.fold_attack = os.environ.get('ACSR_FOLD_ATTACK', '1') == '1'   # attack transforms folded into the Q/K/V launch (forward)
+        # ... and the gate logits as a sixth problem of that launch: correct (tests run it), but measured no faster on B200 (0.742 vs
+        # 0.735 ms per C2 step: the sixth problem adds a round to the persistent CTAs, the separate 100-CTA launch hides under PDL) -> off
+        self.fold_gate = os.environ.get('ACSR_FOLD_GATE', '0') == '1'
         self.pdl = bool(getattr(model, 'pdl', True))            # programmatic dependent launch between the step's kernels
         # last layer's dense part on the compact rows as ONE launch per direction (acsr_tail_fwd / _bwd); ACSR_TAIL_FUSED=0: six launches
         self.tail_fused = (self.tc and model.inner_size % 16 == 0 and os.environ.get('ACSR_TAIL_FUSED', '1') == '1')
@@ -88,10 +91,12 @@ class FusedTrainStep(object):
         b = dict(T=T, x0=f(T, d), st_e=f(T, 2), layers=[], order=torch.empty(Bs, dtype=torch.int32, device=dev))
         for l in range(N):
             R = 2 * T if l == N - 1 else T
-            qkv5 = f(5, T, d)                  # mixed_q, mixed_k, mixed_v, attack_q, attack_k: one batched GEMM writes all five
-            qkv, aqk = qkv5[:3], qkv5[3:]
+            # mixed_q, mixed_k, mixed_v, attack_q, attack_k (+ the gate logits [T, L] in a sixth slot): one batched GEMM writes all
+            qkv5 = f(6, T, d)
+            qkv, aqk = qkv5[:3], qkv5[3:5]
             Rp = 1 if (l == N - 1 and self.compact_last) else R      # the compact last layer keeps its dense part in b['c']
-            lb = dict(qkv5=qkv5, qkv=qkv, aqk=aqk, mq=qkv[0], mk=qkv[1], mv=qkv[2], aq=aqk[0], ak=aqk[1], gl=f(T, L), ctx=f(R, d),
+            lb = dict(qkv5=qkv5, qkv=qkv, aqk=aqk, mq=qkv[0], mk=qkv[1], mv=qkv[2], aq=aqk[0], ak=aqk[1],
+                      gl=(qkv5[5].view(-1)[:T * L].view(T, L) if L <= d else f(T, L)), ctx=f(R, d),
                       hz=f(Rp, d), st_a=f(Rp, 2), h=f(Rp, d), z1=f(Rp, I), a1=f(Rp, I), z2=f(Rp, d), st_f=f(Rp, 2), out=f(Rp, d))
             # buffers read by the weight-gradient kernels are per layer: the side stream may still be reading layer l's
             # while the branch stream already writes layer l-1's
@@ -332,7 +337,11 @@ class FusedTrainStep(object):
                 if st3 is None:
                     continue
                 fw = self._folded_buffers(l, seq.device)
-                LIB.call('acsr_fold_attack_weights', _p(st3['Wqkv']), _p(st3['bqkv']), _p(st3['Waqk']), _p(st3['baqk']), d,
+                lay = m.trm_encoder.layer[l]
+                # combine_option 'gate': gate(mixed_q) = x.(Wg.Wq)^T + (Wg.bq + bg) rides along as a sixth, L-feature problem
+                fw['gate'] = lay.combine_option == 'gate' and lay.gate.out_features == L and L <= d and self.fold_gate
+                LIB.call('acsr_fold_projection_weights', _p(st3['Wqkv']), _p(st3['bqkv']), _p(st3['Waqk']), _p(st3['baqk']), d,
+                         _p(lay.gate.weight) if fw['gate'] else None, _p(lay.gate.bias) if fw['gate'] else None, L if fw['gate'] else 0,
                          _p(fw['W']), _p(fw['b']), so.cuda_stream)
                 fw['done'] = torch.cuda.Event()
                 fw['done'].record(so)
@@ -367,7 +376,11 @@ class FusedTrainStep(object):
                 # all five projections read x: one batched tcgen05 launch over the folded weights (prepared at the start of the
                 # step on the ordering stream, next to the embedding kernel)
                 fw = folded[l]
-                ops.linear_tok(x, T, d, fw['W'], d, lb['qkv5'], d, bias=fw['b'], batch=5, sx=0, sw=d * d, sb=d, sy=T * d)
+                if fw['gate']:
+                    ops.linear_tok(x, T, d, fw['W'], d, lb['qkv5'], d, bias=fw['b'], batch=6, sx=0, sw=d * d, sb=d, sy=T * d,
+                                   last_n=L, last_ldy=L)
+                else:
+                    ops.linear_tok(x, T, d, fw['W'], d, lb['qkv5'], d, bias=fw['b'], batch=5, sx=0, sw=d * d, sb=d, sy=T * d)
             elif st3 is not None and self.tc:                 # stacked Q/K/V and attack pair: two batched tcgen05 launches
                 ops.linear_tok(x, T, d, st3['Wqkv'], d, lb['qkv'], d, bias=st3['bqkv'], batch=3, sx=0, sw=d * d, sb=d, sy=T * d)
                 ops.linear_tok(lb['qkv'], T, d, st3['Waqk'], d, lb['aqk'], d, bias=st3['baqk'], batch=2, sx=T * d, sw=d * d,
@@ -390,7 +403,7 @@ class FusedTrainStep(object):
             if gate:
                 if layer.gate.out_features != L:
                     raise ValueError('gate width %d != sequence length %d' % (layer.gate.out_features, L))
-                if self.tc:
+                if self.tc and not (l in folded and folded[l].get('gate')):
                     ops.linear_tok(lb['mq'], T, d, layer.gate.weight, L, lb['gl'], L, bias=layer.gate.bias)
             elif layer.combine_option == 'annealing':
                 comb_scalar = math.exp(-layer.anneal_step / 100000)
@@ -695,10 +708,10 @@ class FusedTrainStep(object):
         key = ('folded', l)
         if key not in self.buf:
             d = self.m.hidden_size
-            self.buf[key] = dict(W=torch.empty((5, d, d), dtype=torch.float32, device=dev), b=torch.empty((5, 1, d), dtype=torch.float32, device=dev))
+            self.buf[key] = dict(W=torch.zeros((6, d, d), dtype=torch.float32, device=dev), b=torch.zeros((6, 1, d), dtype=torch.float32, device=dev))
             # written once per step by acsr_fold_attack_weights, which completes (full event dependency) before the first kernel
             # of the chain that reads them starts: safe to read ahead of programmatic-launch synchronisation
-            for t in self.buf[key].values():
+            for t in list(self.buf[key].values()):
                 LIB.query('acsr_register_static', t.data_ptr(), t.numel() * 4)
         return self.buf[key]
 

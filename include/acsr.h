@@ -266,6 +266,10 @@ int acsr_topk_select(const float* scores, int M, int64_t V, int64_t ld, int k, i
  * {bq, bk, bv, Waq.bq + baq, Wak.bk + bak}.  Wqkv [3,d,d], bqkv [3,d], Waqk [2,d,d], baqk [2,d] (row-major [out,in]). */
 int acsr_fold_attack_weights(const float* Wqkv, const float* bqkv, const float* Waqk, const float* baqk, int d, float* out_W,
                              float* out_b, void* stream);
+/* the same with the gate of combine_option 'gate' (layers.py:887, gate(mixed_q)) folded in as a sixth slot: out_W [6,d,d] /
+ * out_b [6,d], slot 5 rows [0,Lg) = Wg.Wq and Wg.bq + bg (Wg [Lg,d], Lg <= d); Lg = 0: five slots as above. */
+int acsr_fold_projection_weights(const float* Wqkv, const float* bqkv, const float* Waqk, const float* baqk, int d,
+                                 const float* Wg, const float* bg, int Lg, float* out_W, float* out_b, void* stream);
 
 /* ---- encoder GEMMs on tcgen05 with the token rows on the UMMA M axis (3xTF32, fp32-level accuracy) ----
  * replaces the nn.Linear forward / input-gradient GEMMs of model/layers.py:658-659, 680, 687-689, 791-794, 887.
@@ -279,6 +283,12 @@ int acsr_linear_tok(const float* X, int64_t ldx, int64_t x_kblock_stride, int64_
                     const float* bias, int accumulate, float* Y, int64_t ldy,
                     int batch, int64_t stride_x, int64_t stride_w, int64_t stride_bias, int64_t stride_y,
                     int passes, void* stream);
+/* batched launch whose LAST problem is narrower: last_n <= N features written with row stride last_ldy (the gate logits
+ * [T, L] riding along with the five [T, d] projections of a layer); last_n = 0: acsr_linear_tok. */
+int acsr_linear_tok_ragged(const float* X, int64_t ldx, int64_t x_kblock_stride, int64_t rows, int K, const float* W, int64_t w_stride_n,
+                           int64_t w_stride_k, int64_t w_kblock_stride, int N, const float* bias, int accumulate, float* Y, int64_t ldy,
+                           int batch, int64_t stride_x, int64_t stride_w, int64_t stride_bias, int64_t stride_y, int last_n,
+                           int64_t last_ldy, int passes, void* stream);
 /* FFN first half fused (model/layers.py:776-792): Z = X.W^T (saved pre-bias for the backward), A = act(Z + bias).
  * X [rows,K] (row stride ldx), W [N,K] row-major, Z,A [rows,N] (row stride ldy). */
 int acsr_linear_tok_act(const float* X, int64_t ldx, int64_t rows, int K, const float* W, int N, const float* bias, int act,

@@ -268,6 +268,33 @@ def test_fused_step_matches_reference_grads(A, name):
         assert err <= 1e-3 * scale + 1e-8, (n, err, scale)
 
 
+@pytest.mark.parametrize('name', ['c1_train', 'beauty_train'])
+def test_fused_step_optional_paths_match_reference_grads(A, name):
+    """switches that are off by default still reproduce the reference: the gate logits as a sixth (ragged) problem of the
+    projection launch (acsr_fold_projection_weights + acsr_linear_tok_ragged), the CE backward through the gradient matrix,
+    the last layer's dense part as separate launches."""
+    c = load_case(name)
+    z = c['z']
+    for switch in ('fold_gate', 'no_ce_fused_bwd', 'no_tail_fused'):
+        config, model = build_model(A, c)
+        trainer = A.ACSASRecTrainer(config, model)
+        f = trainer.fused
+        if switch == 'fold_gate':
+            f.fold_gate = True
+        elif switch == 'no_ce_fused_bwd':
+            f.ce_fused_bwd = False
+        else:
+            f.tail_fused = False
+        model.train()
+        l_att, l_cal = f(inter_of(A, c))
+        assert abs(float(l_att) - float(z['loss_att'])) < 1e-4 * abs(float(z['loss_att'])), switch
+        assert abs(float(l_cal) - float(z['loss_cal'])) < 1e-4 * abs(float(z['loss_cal'])), switch
+        for n, p in model.named_parameters():
+            ref = c['grads'][n]
+            err = float((p.grad.cpu() - ref).abs().max())
+            assert err <= 1e-3 * float(ref.abs().max()) + 1e-8, (switch, n, err)
+
+
 def test_fused_step_equals_autograd_step_full_batch(A):
     """B=256 Beauty shape, dropout on (Philox): fused explicit step vs autograd path cannot share masks
     (different stream layout), so compare with dropout off and injected zero noise."""
