@@ -113,7 +113,7 @@ __device__ __forceinline__ void block_col_reduce(float (*acc)[D / 32], float* co
 template <int D>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 embed_ln_fwd_kernel(const int64_t* __restrict__ item_seq, const float* __restrict__ table, const float* __restrict__ pos_emb,
-                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int T, int L,
+                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int T, int L, long long V,
                     float p, const float* __restrict__ mask, const RngState* rng, uint32_t stream,
                     float* __restrict__ out, float* __restrict__ stats) {
   pdl_launch_dependents();
@@ -124,7 +124,8 @@ embed_ln_fwd_kernel(const int64_t* __restrict__ item_seq, const float* __restric
   RV::load(ln_w, lane, w);
   RV::load(ln_b, lane, b);
   for (long long t = (long long)blockIdx.x * kWarpsPerBlock + warp; t < T; t += (long long)gridDim.x * kWarpsPerBlock) {
-    const int64_t idx = item_seq[t];
+    int64_t idx = item_seq[t];
+    if (idx < 0 || idx >= V) idx = 0;       // an id outside the table reads (and trains) nothing: treated as padding, never out of bounds
     float x[RV::VPT], m[RV::VPT];
     RV::load(table + idx * D, lane, x);
     if (pos_emb != nullptr) {
@@ -147,7 +148,7 @@ template <int D>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 embed_ln_bwd_kernel(const float* __restrict__ d_out, const int64_t* __restrict__ item_seq, const float* __restrict__ table,
                     const float* __restrict__ pos_emb, const float* __restrict__ ln_w, const float* __restrict__ stats,
-                    int T, int L, float p, const float* __restrict__ mask, const RngState* rng, uint32_t stream,
+                    int T, int L, long long V, float p, const float* __restrict__ mask, const RngState* rng, uint32_t stream,
                     float* __restrict__ d_table, float* __restrict__ d_pos, float* __restrict__ d_ln_w, float* __restrict__ d_ln_b) {
   pdl_launch_dependents();
   pdl_wait();
@@ -160,7 +161,8 @@ embed_ln_bwd_kernel(const float* __restrict__ d_out, const int64_t* __restrict__
 #pragma unroll
   for (int i = 0; i < RV::VPT; ++i) acc[0][i] = acc[1][i] = 0.f;
   for (long long t = (long long)blockIdx.x * kWarpsPerBlock + warp; t < T; t += (long long)gridDim.x * kWarpsPerBlock) {
-    const int64_t idx = item_seq[t];
+    int64_t idx = item_seq[t];
+    if (idx < 0 || idx >= V) idx = 0;       // an id outside the table reads (and trains) nothing: treated as padding, never out of bounds
     float x[RV::VPT], g[RV::VPT], m[RV::VPT];
     RV::load(table + idx * D, lane, x);
     if (pos_emb != nullptr) {
@@ -437,7 +439,7 @@ int acsr_embed_ln_dropout_fwd(const int64_t* item_seq, const float* table, const
   ACSR_REQUIRE(!(p > 0.f && mask == nullptr && rng == nullptr), "embed_ln_dropout_fwd: p>0 needs mask or rng");
   if (T == 0) return ACSR_OK;
   DISPATCH_D(d, (launch_pdl(embed_ln_fwd_kernel<D_>, dim3(row_grid(T)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, 
-                    item_seq, table, pos_emb, ln_w, ln_b, eps, T, L, p, mask, (const RngState*)rng, rng_stream, out, stats)));
+                    item_seq, table, pos_emb, ln_w, ln_b, eps, T, L, (long long)V, p, mask, (const RngState*)rng, rng_stream, out, stats)));
   return check_launch("embed_ln_dropout_fwd");
 }
 
@@ -449,7 +451,7 @@ int acsr_embed_ln_dropout_bwd(const float* d_out, const int64_t* item_seq, const
   ACSR_REQUIRE((pos_emb == nullptr) == (d_pos == nullptr), "embed_ln_dropout_bwd: pos_emb/d_pos mismatch");
   if (T == 0) return ACSR_OK;
   DISPATCH_D(d, (launch_pdl(embed_ln_bwd_kernel<D_>, dim3(row_grid(T)), dim3(kWarpsPerBlock * 32), 0, (cudaStream_t)stream, 
-                    d_out, item_seq, table, pos_emb, ln_w, stats, T, L, p, mask, (const RngState*)rng, rng_stream, d_table,
+                    d_out, item_seq, table, pos_emb, ln_w, stats, T, L, (long long)V, p, mask, (const RngState*)rng, rng_stream, d_table,
                     d_pos, d_ln_w, d_ln_b)));
   return check_launch("embed_ln_dropout_bwd");
 }

@@ -61,7 +61,8 @@ int acsr_rng_advance(void* rng, void* stream);
 /* ---- K1: item-embedding gather (+position add) + LayerNorm + dropout ------------------
  * replaces model/sequential_recommender/acsasrec.py:87-95.
  * item_seq [T] int64 (T = B*L tokens), table [V,d], pos_emb [L,d] or NULL, out [T,d],
- * stats [T,2] (mean, rstd) saved for backward.  d in {32,64,128,256}. */
+ * stats [T,2] (mean, rstd) saved for backward.  d in {32,64,128,256}.  Ids outside [0,V) are treated as the padding id 0 (no
+ * out-of-bounds access; nn.Embedding would raise -- the host pipeline, dataset.py, guarantees the range). */
 int acsr_embed_ln_dropout_fwd(const int64_t* item_seq, const float* table, const float* pos_emb,
                               const float* ln_w, const float* ln_b, float eps,
                               int T, int L, int d, int64_t V,
