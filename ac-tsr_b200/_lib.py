@@ -129,6 +129,12 @@ def _ab_linear_tok(a):
     return 4 * batch * (rows * K + rows * N * (2 if acc else 1) + N * K)
 
 
+def _ab_linear_tok_actbwd(a):
+    # (X, ldx, rows, K, W, w_sn, w_sk, wkb, N, Z, z_rows, ...): X, W, Z in; Y out
+    rows, K, N = a[2], a[3], a[8]
+    return 4 * (rows * K + N * K + 2 * rows * N)
+
+
 def _ab_linear_tok_bdrl(a):
     # (X, ldx, rows, K, W, bias, res, res_rows, ...): X, W in; HZ, out, stats out; residual in
     rows, K = a[2], a[3]
@@ -161,7 +167,7 @@ def _ab_gemm_batch(a):
 
 
 # ALGORITHMIC bytes of one launch, from the call's own arguments
-ALGO_BYTES = {'acsr_linear_tok': _ab_linear_tok, 'acsr_linear_tok_ragged': _ab_linear_tok, 'acsr_linear_tok_bdrl': _ab_linear_tok_bdrl,
+ALGO_BYTES = {'acsr_linear_tok': _ab_linear_tok, 'acsr_linear_tok_ragged': _ab_linear_tok, 'acsr_linear_tok_bdrl': _ab_linear_tok_bdrl, 'acsr_linear_tok_actbwd': _ab_linear_tok_actbwd,
               'acsr_linear_wgrad': _ab_linear_wgrad, 'acsr_linear_wgrad_batched': _ab_linear_wgrad_batched,
               'acsr_gemm_batch': _ab_gemm_batch}
 

@@ -26,7 +26,7 @@ constexpr int kLtKB = 64;            // K block (floats) held per A buffer
 constexpr int kLtABytes = kLtBM * kLtKB * 4;     // 32 KB per (hi | lo)
 constexpr int kLtTmemCols = 256;     // 2 accumulator stages x <= 128 columns
 
-enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_BDRL = 2 };
+enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_BDRL = 2, EPI_ACTBWD = 3 };
 
 struct LinTokParams {
   const float* X; long long ldx, xkb; long long rows; int K;       // element (r, k) = X[(k / 64) * xkb + r * ldx + k % 64]
@@ -324,7 +324,22 @@ __global__ void __launch_bounds__(kLtThreads, 1) linear_tok_kernel(const LinTokP
           if (row_ok) {
             float* y = Yp + grow * ldy_eff + n0 + cc * 32;
             const bool vec = nvalid == 32 && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
-            if (EPI == EPI_ACT) {
+            if (EPI == EPI_ACTBWD) {
+              // Y = acc * act'(Z + bias): the activation backward (layers.py:776-792) applied to the input gradient d_a1 = d_z2.W2
+              // while it is still in registers; Z = the saved pre-activation GEMM output (p.res, rows repeat with period res_rows)
+              const float* z = p.res + (grow % p.res_rows) * p.ldy + n0 + cc * 32;
+              if (vec && ((reinterpret_cast<uintptr_t>(z) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + i));
+                  *reinterpret_cast<float4*>(y + i) = make_float4(v[i] * act_bwd(p.act, z4.x + sBias[cc * 32 + i]), v[i + 1] * act_bwd(p.act, z4.y + sBias[cc * 32 + i + 1]),
+                                                                  v[i + 2] * act_bwd(p.act, z4.z + sBias[cc * 32 + i + 2]), v[i + 3] * act_bwd(p.act, z4.w + sBias[cc * 32 + i + 3]));
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < nvalid) y[i] = v[i] * act_bwd(p.act, __ldg(z + i) + sBias[cc * 32 + i]);
+              }
+            } else if (EPI == EPI_ACT) {
               // Y = raw GEMM output (pre-bias, saved for the backward), Y2 = act(Y + bias)
               float* y2 = p.Y2 + bz * p.by + grow * p.ldy + n0 + cc * 32;
               if (vec) {
@@ -455,6 +470,23 @@ int acsr_linear_tok_act(const float* X, int64_t ldx, int64_t rows, int K, const 
   p.batch = 1; p.passes = passes; p.epi = EPI_ACT;
   p.w_static = is_static_memory(p.W) && (p.bias == nullptr || is_static_memory(p.bias));
   return lt_launch<EPI_ACT>(p, (cudaStream_t)stream, "linear_tok_act");
+}
+
+int acsr_linear_tok_actbwd(const float* X, int64_t ldx, int64_t rows, int K, const float* W, int64_t w_stride_n, int64_t w_stride_k,
+                           int64_t w_kblock_stride, int N, const float* Z, int64_t z_rows, const float* bias, int act, float* Y,
+                           int passes, void* stream) {
+  ACSR_REQUIRE(X && W && Z && Y, "linear_tok_actbwd: NULL pointer");
+  ACSR_REQUIRE(rows >= 0 && N > 0 && K > 0 && z_rows > 0, "linear_tok_actbwd: bad sizes");
+  ACSR_REQUIRE(act >= 0 && act <= 4, "linear_tok_actbwd: unknown activation %d", act);
+  ACSR_REQUIRE(passes == 1 || passes == 3, "linear_tok_actbwd: passes must be 1 or 3");
+  if (rows == 0) return ACSR_OK;
+  LinTokParams p = {};
+  p.X = X; p.ldx = ldx; p.xkb = kLtKB; p.rows = rows; p.K = K;
+  p.W = W; p.w_sn = w_stride_n; p.w_sk = w_stride_k; p.wkb = w_kblock_stride; p.N = N;
+  p.bias = bias; p.Y = Y; p.ldy = N; p.act = act; p.res = Z; p.res_rows = z_rows;
+  p.batch = 1; p.passes = passes; p.epi = EPI_ACTBWD;
+  p.w_static = is_static_memory(p.W) && (p.bias == nullptr || is_static_memory(p.bias));
+  return lt_launch<EPI_ACTBWD>(p, (cudaStream_t)stream, "linear_tok_actbwd");
 }
 
 int acsr_linear_tok_bdrl(const float* X, int64_t ldx, int64_t rows, int K, const float* W, const float* bias, const float* res,

@@ -68,6 +68,10 @@ class FusedTrainStep(object):
         self.pdl = bool(getattr(model, 'pdl', True))            # programmatic dependent launch between the step's kernels
         # last layer's dense part on the compact rows as ONE launch per direction (acsr_tail_fwd / _bwd); ACSR_TAIL_FUSED=0: six launches
         self.tail_fused = (self.tc and model.inner_size % 16 == 0 and os.environ.get('ACSR_TAIL_FUSED', '1') == '1')
+        # activation backward inside the d_a1 GEMM's TMEM epilogue (acsr_linear_tok_actbwd): correct (tests run it) but SLOWER on B200 --
+        # 65 us against 22 + 21 us for GEMM + row-wise kernel: four epilogue warps (one thread per token row) cannot issue the erf
+        # derivative of 128 x 256 elements fast enough -> off
+        self.fuse_act_bwd = os.environ.get('ACSR_FUSE_ACT_BWD', '0') == '1'
         # CE backward without the [2B,V] gradient matrix (acsr_ce_bwd_dout / _dtable, hidden size 64); ACSR_CE_FUSED_BWD=0 keeps Gt
         self.ce_fused_bwd = model.hidden_size == 64 and os.environ.get('ACSR_CE_FUSED_BWD', '1') == '1'
 
@@ -661,13 +665,20 @@ class FusedTrainStep(object):
                  _p(gb['d_z2']), _p(d_h), _p(ff.dense_2.bias.grad), _p(ff.LayerNorm.weight.grad),
                  _p(ff.LayerNorm.bias.grad), st)
         self._wgrad(gb['d_z2'], bf['a1'], w_rows, ff.dense_2.weight.grad, None, fork, wg)
-        if self.tc:                                      # d_a1 = d_z2.W2 : the weight is read transposed
-            ops.linear_tok(gb['d_z2'], R2, d, ff.dense_2.weight, I, d_a1, I, w_sn=1, w_sk=I, wkb=64 * I)
+        if self.tc and self.tc_wgrad and self.fuse_act_bwd:
+            # d_z1 = (d_z2.W2) * act'(z1 + b1) in ONE launch (the activation backward in the GEMM's TMEM epilogue); the bias gradient
+            # comes out of the weight-gradient launch (row sums of its left operand)
+            ops.linear_tok_actbwd(gb['d_z2'], R2, d, ff.dense_2.weight, I, bf['z1'], P, ff.dense_1.bias, act_id, gb['d_z1'],
+                                  w_sn=1, w_sk=I, wkb=64 * I)
+            self._wgrad(gb['d_z1'], bf['h'], w_rows, ff.dense_1.weight.grad, ff.dense_1.bias.grad, fork, wg)
         else:
-            ops.gemm_batch([gp(gb['d_z2'], ff.dense_2.weight, d_a1, R2, I, d, b_strides=(1, I, 0, d))], passes=ps)
-        LIB.call('acsr_bias_act_bwd', _p(d_a1), _p(bf['z1']), _p(ff.dense_1.bias), R2, I, act_id, P, w_rows, _p(gb['d_z1']),
-                 _p(ff.dense_1.bias.grad), st)
-        self._wgrad(gb['d_z1'], bf['h'], w_rows, ff.dense_1.weight.grad, None, fork, wg)
+            if self.tc:                                      # d_a1 = d_z2.W2 : the weight is read transposed
+                ops.linear_tok(gb['d_z2'], R2, d, ff.dense_2.weight, I, d_a1, I, w_sn=1, w_sk=I, wkb=64 * I)
+            else:
+                ops.gemm_batch([gp(gb['d_z2'], ff.dense_2.weight, d_a1, R2, I, d, b_strides=(1, I, 0, d))], passes=ps)
+            LIB.call('acsr_bias_act_bwd', _p(d_a1), _p(bf['z1']), _p(ff.dense_1.bias), R2, I, act_id, P, w_rows, _p(gb['d_z1']),
+                     _p(ff.dense_1.bias.grad), st)
+            self._wgrad(gb['d_z1'], bf['h'], w_rows, ff.dense_1.weight.grad, None, fork, wg)
         if self.tc:
             ops.linear_tok(gb['d_z1'], R2, I, ff.dense_1.weight, d, d_h, d, w_sn=1, w_sk=d, wkb=64 * d, accumulate=True)
         else:

@@ -338,6 +338,12 @@ def linear_tok(X, rows, K, W, N, Y, ldy, ldx=None, xkb=64, w_sn=None, w_sk=1, wk
              int(batch), int(sx), int(sw), int(sb), int(sy), int(last_n), int(last_ldy), passes, _stream())
 
 
+def linear_tok_actbwd(X, rows, K, W, N, Z, z_rows, bias, act, Y, w_sn, w_sk, wkb, passes=3):
+    """Y = (X.W^T) * act'(Z + bias): input gradient through dense_2 and the activation in one launch (acsr_linear_tok_actbwd)."""
+    LIB.call('acsr_linear_tok_actbwd', _p(X), int(K), int(rows), int(K), _p(W), int(w_sn), int(w_sk), int(wkb), int(N), _p(Z),
+             int(z_rows), _p(bias), int(act), _p(Y), passes, _stream())
+
+
 def linear_tok_act(X, rows, K, W, N, bias, act, Z, A, passes=3):
     """Z = X.W^T, A = act(Z + bias)  (acsr_linear_tok_act)."""
     LIB.call('acsr_linear_tok_act', _p(X), int(K), int(rows), int(K), _p(W), int(N), _p(bias), int(act), _p(Z), _p(A), int(N),

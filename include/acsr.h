@@ -290,6 +290,12 @@ int acsr_linear_tok_ragged(const float* X, int64_t ldx, int64_t x_kblock_stride,
                            int64_t w_stride_k, int64_t w_kblock_stride, int N, const float* bias, int accumulate, float* Y, int64_t ldy,
                            int batch, int64_t stride_x, int64_t stride_w, int64_t stride_bias, int64_t stride_y, int last_n,
                            int64_t last_ldy, int passes, void* stream);
+/* input gradient through a linear layer AND the activation in front of it in one launch (layers.py:776-792 backward):
+ * Y[r, n] = (sum_k X(r,k) * W(n,k)) * act'(Z[(r % z_rows), n] + bias[n]), Z [z_rows, N] = the saved pre-activation GEMM output,
+ * Y [rows, N] contiguous.  X / W strides as acsr_linear_tok (the weight is usually read transposed). */
+int acsr_linear_tok_actbwd(const float* X, int64_t ldx, int64_t rows, int K, const float* W, int64_t w_stride_n, int64_t w_stride_k,
+                           int64_t w_kblock_stride, int N, const float* Z, int64_t z_rows, const float* bias, int act, float* Y,
+                           int passes, void* stream);
 /* FFN first half fused (model/layers.py:776-792): Z = X.W^T (saved pre-bias for the backward), A = act(Z + bias).
  * X [rows,K] (row stride ldx), W [N,K] row-major, Z,A [rows,N] (row stride ldy). */
 int acsr_linear_tok_act(const float* X, int64_t ldx, int64_t rows, int K, const float* W, int N, const float* bias, int act,

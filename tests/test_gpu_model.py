@@ -275,7 +275,7 @@ def test_fused_step_optional_paths_match_reference_grads(A, name):
     the last layer's dense part as separate launches."""
     c = load_case(name)
     z = c['z']
-    for switch in ('fold_gate', 'no_ce_fused_bwd', 'no_tail_fused'):
+    for switch in ('fold_gate', 'no_ce_fused_bwd', 'no_tail_fused', 'fuse_act_bwd'):
         config, model = build_model(A, c)
         trainer = A.ACSASRecTrainer(config, model)
         f = trainer.fused
@@ -283,8 +283,10 @@ def test_fused_step_optional_paths_match_reference_grads(A, name):
             f.fold_gate = True
         elif switch == 'no_ce_fused_bwd':
             f.ce_fused_bwd = False
-        else:
+        elif switch == 'no_tail_fused':
             f.tail_fused = False
+        else:
+            f.fuse_act_bwd = True
         model.train()
         l_att, l_cal = f(inter_of(A, c))
         assert abs(float(l_att) - float(z['loss_att'])) < 1e-4 * abs(float(z['loss_att'])), switch
