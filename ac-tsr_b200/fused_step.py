@@ -72,6 +72,7 @@ class FusedTrainStep(object):
         # 65 us against 22 + 21 us for GEMM + row-wise kernel: four epilogue warps (one thread per token row) cannot issue the erf
         # derivative of 128 x 256 elements fast enough -> off
         self.fuse_act_bwd = os.environ.get('ACSR_FUSE_ACT_BWD', '0') == '1'
+        self.split_wgrad = int(os.environ.get('ACSR_SPLIT_WGRAD', '1'))       # 1: two weight-gradient launches for the first layer (see _backward_branch); 2: every layer
         # CE backward without the [2B,V] gradient matrix (acsr_ce_bwd_dout / _dtable, hidden size 64); ACSR_CE_FUSED_BWD=0 keeps Gt
         self.ce_fused_bwd = model.hidden_size == 64 and os.environ.get('ACSR_CE_FUSED_BWD', '1') == '1'
 
@@ -180,6 +181,7 @@ class FusedTrainStep(object):
                                  side=self._stream_for(dev, ('side', s)) if self.overlap_wgrad else None))
         rng.advance()
         jb['pen'].zero_()
+        torch.cat((pos_items, pos_items), out=jb['target2'])      # targets of the [calibrated ; attacked] rows: off the CE's critical path
         zero_done = None
         if training:
             # every buffer the backward accumulates into is cleared on its own stream while the forward runs
@@ -217,7 +219,6 @@ class FusedTrainStep(object):
             return jb['loss'][0], jb['loss'][0]
         # ---------------- where the sequences meet: full-catalogue cross entropy + penalty norm ----------------
         st = _stream()
-        torch.cat((pos_items, pos_items), out=jb['target2'])
         passes = m.logits_passes
         vst = None
         if self.vp is not None:       # all-gather out -> shard-local partial CE -> all-gather (max, sum-exp) -> combine
@@ -577,6 +578,12 @@ class FusedTrainStep(object):
                     LIB.call('acsr_gather_last_bwd', _p(cb['d_x']), _p(ln, torch.int64), Bs, L, d, _p(d_x[:T]), _p(d_x[T:]), st)
             else:
                 self._post_attn_bwd(layer, lb, lb, d_out, x, T2, P, T, T, d_x, b['d_ctx'], p_h, rngp, base, act_id, st, fork, wg, b=b)
+            if wg and self.split_wgrad and (l == 0 or self.split_wgrad > 1):
+                # the out-projection / feed-forward weight gradients are complete here: their launch runs on the side stream
+                # under the attention backward, so the launch left for the end of the layer (the projections') is short --
+                # the first layer's is the tail of the step's critical path
+                ops.gemm_batch(wg, passes=self.passes, stream=fork())
+                wg = []
             # fused attention backward (d_gate_logit accumulates over heads: cleared at the start of the step)
             g = lambda t: None if t is None else t.grad     # noqa: E731
             ow, ob_ = (aa.order_affine.weight, aa.order_affine.bias) if aa.use_order else (None, None)
@@ -593,6 +600,14 @@ class FusedTrainStep(object):
                      _p(b['order'], torch.int32), _p(ln, torch.int64) if (last and compact) else None, st)
             # projections: input gradients for both streams, weight gradients from the owning stream
             aqt, akt = aa.attack_query_transform, aa.attack_key_transform
+            # weight gradients of the projections: attack transforms are trained by the attacked-loss stream (rows [T,2T)), the
+            # gate by both halves of d_gl's stream-0 rows, Q / K / V by the calibrated-loss stream.  (A third launch for the attack pair
+            # + gate, whose operands are final right after the attention backward, measured no further gain: 0.7162 vs 0.7179 ms.)
+            self._wgrad(lb['d_aq'][T:], lb['mq'], T, aqt.weight.grad, aqt.bias.grad, fork, wg)
+            self._wgrad(lb['d_ak'][T:], lb['mk'], T, akt.weight.grad, akt.bias.grad, fork, wg)
+            if gate:
+                self._wgrad(lb['d_gl'], lb['mq'], T, layer.gate.weight.grad, layer.gate.bias.grad, fork, wg)
+
             st3 = self._stacked(l)
             gp = ops.gemm_problem
             rows_x = T2 if l > 0 else T                      # below the first layer only the calibrated stream trains anything
@@ -621,12 +636,6 @@ class FusedTrainStep(object):
                     for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
                         ops.gemm_batch([gp(lb[dk], lin.weight, d_x, rows_x, d, d, b_strides=(1, d, 0, d), accumulate=True)],
                                        passes=self.passes)
-            # weight gradients of the projections: attack transforms are trained by the attacked-loss stream (rows [T,2T)), the
-            # gate by both halves of d_gl's stream-0 rows, Q / K / V by the calibrated-loss stream
-            self._wgrad(lb['d_aq'][T:], lb['mq'], T, aqt.weight.grad, aqt.bias.grad, fork, wg)
-            self._wgrad(lb['d_ak'][T:], lb['mk'], T, akt.weight.grad, akt.bias.grad, fork, wg)
-            if gate:
-                self._wgrad(lb['d_gl'], lb['mq'], T, layer.gate.weight.grad, layer.gate.bias.grad, fork, wg)
             for lin, dk in ((aa.query, 'd_mq'), (aa.key, 'd_mk'), (aa.value, 'd_mv')):
                 self._wgrad(lb[dk], x, T, lin.weight.grad, lin.bias.grad, fork, wg)
             if wg:                                           # all weight gradients of the layer: ONE launch on the side stream
