@@ -72,6 +72,8 @@ class ACSASRec(SequentialRecommender):
 
         # B200 runtime state (not parameters, not in the state_dict)
         self.logits_passes = int(cfg_get(config, 'logits_passes', 3))
+        import os
+        self._eval_pdl = os.environ.get('ACSR_EVAL_PDL', '0') == '1'
         self.step_branches = int(cfg_get(config, 'step_branches', 1))     # parallel sequence groups of the fused step (measured: no gain at B=256)
         self._seed = int(cfg_get(config, 'seed', 2020))
         self._rng = None
@@ -210,8 +212,14 @@ class ACSASRec(SequentialRecommender):
         (trainer.py:941-942, collector.py:145-153): -> (topk_scores[B,k], topk_idx[B,k], rec_topk[B,k+1]|None)."""
         item_seq = interaction[self.ITEM_SEQ]
         item_seq_len = interaction[self.ITEM_SEQ_LEN]
-        out, _ = self._encode(item_seq, item_seq_len, need_attacked=False)
-        vp = getattr(self, '_vp', None)
-        if vp is not None:                        # vocab-parallel: partial top-k per shard, all-gather, merge (dist.py)
-            return vp.full_sort_topk(out, self.item_embedding.weight, k, positive)
-        return ops.full_sort_topk(out, self.item_embedding.weight, k, positive, self.logits_passes)
+        # programmatic dependent launch between the eval kernels (prologues overlap the previous kernel's tail), as in the training step
+        was = ops.LIB.query('acsr_set_pdl', 1) if self._eval_pdl else None
+        try:
+            out, _ = self._encode(item_seq, item_seq_len, need_attacked=False)
+            vp = getattr(self, '_vp', None)
+            if vp is not None:                        # vocab-parallel: partial top-k per shard, all-gather, merge (dist.py)
+                return vp.full_sort_topk(out, self.item_embedding.weight, k, positive)
+            return ops.full_sort_topk(out, self.item_embedding.weight, k, positive, self.logits_passes)
+        finally:
+            if was is not None:
+                ops.LIB.query('acsr_set_pdl', was)
