@@ -73,7 +73,7 @@ class ACSASRec(SequentialRecommender):
         # B200 runtime state (not parameters, not in the state_dict)
         self.logits_passes = int(cfg_get(config, 'logits_passes', 3))
         import os
-        self._eval_pdl = os.environ.get('ACSR_EVAL_PDL', '0') == '1'
+        self._eval_pdl = os.environ.get('ACSR_EVAL_PDL', '1') == '1'      # measured +1 % eval users/s on B200
         self.step_branches = int(cfg_get(config, 'step_branches', 1))     # parallel sequence groups of the fused step (measured: no gain at B=256)
         self._seed = int(cfg_get(config, 'seed', 2020))
         self._rng = None

@@ -34,7 +34,7 @@ constexpr float kOrderEps = 1e-24f;     // layers.py:719
 // allocation, WEIGHT staging) while this one still runs; pdl_wait() returns once every kernel it
 // depends on has completed and its writes are visible.  Only parameters, which no kernel but Adam
 // (the last node of the step) writes, may be read before pdl_wait().  Off unless acsr_set_pdl(1) / ACSR_PDL=1:
-// the fused training step turns it on for its own launches (measured +1.5 %; the eval graph is slower with it).
+// the fused training step and the eval forward turn it on for their own launches (measured +1.5 % / +1 %).
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
