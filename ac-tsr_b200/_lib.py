@@ -135,6 +135,12 @@ def _ab_linear_tok_actbwd(a):
     return 4 * (rows * K + N * K + 2 * rows * N)
 
 
+def _ab_dense_fwd(a):
+    # (ctx, res, rows, res_rows, d, I, ...): ctx + residual in; hz, h, z2, out [rows,64], z1, a1 [rows,I], stats out; weights in
+    rows, res_rows, d, I = a[2], a[3], a[4], a[5]
+    return 4 * (rows * d + min(rows, res_rows) * d + 4 * rows * d + 2 * rows * I + 4 * rows + d * d + 2 * d * I)
+
+
 def _ab_linear_tok_bdrl(a):
     # (X, ldx, rows, K, W, bias, res, res_rows, ...): X, W in; HZ, out, stats out; residual in
     rows, K = a[2], a[3]
@@ -167,7 +173,7 @@ def _ab_gemm_batch(a):
 
 
 # ALGORITHMIC bytes of one launch, from the call's own arguments
-ALGO_BYTES = {'acsr_linear_tok': _ab_linear_tok, 'acsr_linear_tok_ragged': _ab_linear_tok, 'acsr_linear_tok_bdrl': _ab_linear_tok_bdrl, 'acsr_linear_tok_actbwd': _ab_linear_tok_actbwd,
+ALGO_BYTES = {'acsr_linear_tok': _ab_linear_tok, 'acsr_linear_tok_ragged': _ab_linear_tok, 'acsr_linear_tok_bdrl': _ab_linear_tok_bdrl, 'acsr_dense_fwd': _ab_dense_fwd, 'acsr_linear_tok_actbwd': _ab_linear_tok_actbwd,
               'acsr_linear_wgrad': _ab_linear_wgrad, 'acsr_linear_wgrad_batched': _ab_linear_wgrad_batched,
               'acsr_gemm_batch': _ab_gemm_batch}
 

@@ -72,6 +72,13 @@ class FusedTrainStep(object):
         # 65 us against 22 + 21 us for GEMM + row-wise kernel: four epilogue warps (one thread per token row) cannot issue the erf
         # derivative of 128 x 256 elements fast enough -> off
         self.fuse_act_bwd = os.environ.get('ACSR_FUSE_ACT_BWD', '0') == '1'
+        # out-projection + LayerNorm + feed-forward + LayerNorm of a token tile as ONE tcgen05 kernel (acsr_dense_fwd: activations stay
+        # in tensor memory between the GEMMs).  Correct (tests run it) and two launches fewer, but NOT faster on B200: 54.7 us against
+        # 13 + 17 + 5 + 24 us for the four launches it replaces, step 0.7233 vs 0.7177 ms.  ncu (profiles/r02_ncu_full_dense.txt): IPC
+        # 0.37, 17 % warps active -- the chain load -> MMA -> LayerNorm epilogue -> 4 x (MMA -> erf epilogue -> MMA) -> LayerNorm epilogue
+        # is serial inside a tile and each per-row epilogue (Philox + LayerNorm / erf, one warp per SM sub-partition) costs microseconds;
+        # separate launches spread the same epilogues over more CTAs.  Off by default (ACSR_DENSE_FUSED=1 turns it on).
+        self.dense_fused = (self.tc and model.inner_size % 64 == 0 and os.environ.get('ACSR_DENSE_FUSED', '0') == '1')
         self.split_wgrad = int(os.environ.get('ACSR_SPLIT_WGRAD', '1'))       # 1: two weight-gradient launches for the first layer (see _backward_branch); 2: every layer
         # CE backward without the [2B,V] gradient matrix (acsr_ce_bwd_dout / _dtable, hidden size 64); ACSR_CE_FUSED_BWD=0 keeps Gt
         self.ce_fused_bwd = model.hidden_size == 64 and os.environ.get('ACSR_CE_FUSED_BWD', '1') == '1'
@@ -351,6 +358,21 @@ class FusedTrainStep(object):
                 fw['done'] = torch.cuda.Event()
                 fw['done'].record(so)
                 folded[l] = fw
+        dense_ops = {}
+        if self.dense_fused:
+            # the layers' dense weights as pre-split (hi, lo) TF32 operands, once per step next to the embedding kernel.  The last
+            # layer's dense part runs on the compact rows (acsr_tail_fwd) and needs none.
+            for l in range(N):
+                if l == N - 1 and self.compact_last and self.tail_fused:
+                    continue
+                lay = m.trm_encoder.layer[l]
+                dbuf = self._dense_ops_buffer(l, seq.device)
+                LIB.call('acsr_dense_prep', _p(lay.attack_attention.dense.weight), _p(lay.feed_forward.dense_1.weight),
+                         _p(lay.feed_forward.dense_2.weight), d, I, _p(dbuf['ops']), so.cuda_stream)
+                dbuf['done'] = torch.cuda.Event()
+                dbuf['done'].record(so)
+                dense_ops[l] = dbuf
+        b['dense_ops'] = dense_ops
         LIB.call('acsr_seq_order', _p(seq, torch.int64), Bs, L, _p(b['order'], torch.int32), so.cuda_stream)
         order_done = torch.cuda.Event()
         order_done.record(so)
@@ -454,7 +476,10 @@ class FusedTrainStep(object):
                         jb['out2'][B + lo:B + lo + Bs].copy_(cb['out'][Bs:C])
                 return
             lb['m_a'], lb['m_f'] = m_a, m_f
-            self._post_attn_fwd(layer, lb, x, T, R, lb['out'], p_h, rngp, base, act_id, st)
+            dops = dense_ops.get(l)
+            if dops is not None and so is not cur:
+                cur.wait_event(dops['done'])
+            self._post_attn_fwd(layer, lb, x, T, R, lb['out'], p_h, rngp, base, act_id, st, dops)
             x = lb['out'][:T]
         last_out = b['layers'][N - 1]['out']
         # rows [0,B) of out2 calibrated, [B,2B) attacked; this branch owns the rows of its sequences in both halves
@@ -463,12 +488,19 @@ class FusedTrainStep(object):
         if need_att:
             LIB.call('acsr_gather_last_fwd', None, _p(last_out[T:]), _p(ln, torch.int64), Bs, L, d, _p(jb['out2'][B + lo:B + lo + Bs]), st)
 
-    def _post_attn_fwd(self, layer, bf, x_res, res_rows, R, out, p_h, rngp, base, act_id, st):
+    def _post_attn_fwd(self, layer, bf, x_res, res_rows, R, out, p_h, rngp, base, act_id, st, dops=None):
         """out-projection + dropout + residual + LayerNorm, then the feed-forward block, on R rows of bf['ctx']
         (layers.py:676-684, 790-798).  x_res [res_rows, d] is the layer input (residual)."""
         m = self.m
         d, I = m.hidden_size, m.inner_size
         aa, ff = layer.attack_attention, layer.feed_forward
+        if dops is not None:
+            LIB.call('acsr_dense_fwd', _p(bf['ctx']), _p(x_res), R, res_rows, d, I, act_id, _p(dops['ops']), _p(aa.dense.bias),
+                     _p(aa.LayerNorm.weight), _p(aa.LayerNorm.bias), aa.LayerNorm.eps, _p(ff.dense_1.bias), _p(ff.dense_2.bias),
+                     _p(ff.LayerNorm.weight), _p(ff.LayerNorm.bias), ff.LayerNorm.eps, p_h, _p(bf['m_a']), _p(bf['m_f']), rngp, base + 3,
+                     base + 5, _p(bf['hz']), _p(bf['st_a']), _p(bf['h']), _p(bf['z1']), _p(bf['a1']), _p(bf['z2']), _p(bf['st_f']), _p(out),
+                     self.passes, st)
+            return
         if self.tc:
             # out-projection + bias + dropout + residual + LayerNorm in one kernel; FFN: GEMM, bias + activation, then
             # GEMM + bias + dropout + residual + LayerNorm
@@ -733,6 +765,16 @@ class FusedTrainStep(object):
             # of the chain that reads them starts: safe to read ahead of programmatic-launch synchronisation
             for t in list(self.buf[key].values()):
                 LIB.query('acsr_register_static', t.data_ptr(), t.numel() * 4)
+        return self.buf[key]
+
+    def _dense_ops_buffer(self, l, dev):
+        key = ('dense_ops', l)
+        if key not in self.buf:
+            n = LIB.query('acsr_dense_prep_floats', int(self.m.inner_size))
+            t = torch.empty(n, dtype=torch.float32, device=dev)
+            # written once per step by acsr_dense_prep, complete (event dependency) before its reader starts: static for the PDL chain
+            LIB.query('acsr_register_static', t.data_ptr(), t.numel() * 4)
+            self.buf[key] = dict(ops=t)
         return self.buf[key]
 
     def _stacked(self, l):

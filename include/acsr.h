@@ -398,6 +398,21 @@ int acsr_tail_bwd(const float* d_out, const int64_t* item_len, int B, int L, int
                   float* d_ctx_first, float* d_ctx_second, float* g_bo, float* g_lnA_w, float* g_lnA_b, float* g_b1, float* g_b2,
                   float* g_lnF_w, float* g_lnF_b, void* stream);
 
+/* ---- an encoder layer's dense part after its attention, forward, as ONE tcgen05 kernel (hidden size 64, inner size a multiple of
+ * 64 up to 256): hz = ctx.Wo^T ; h = LN(drop(hz + bo) + res) ; z1 = h.W1^T ; a1 = act(z1 + b1) ; z2 = a1.W2^T ;
+ * out = LN(drop(z2 + b2) + h)  (layers.py:676-684, 790-798).  The activations stay in tensor memory between the GEMMs (each
+ * epilogue's output is the next MMA's A operand).  `ops` = the layer's weights pre-split by acsr_dense_prep (once per step) into
+ * (hi, lo) TF32 operands: acsr_dense_prep_floats(I) floats.  res [res_rows, 64] is the layer input (row r uses res[r % res_rows]).
+ * Outputs (all saved for the backward, same meaning as the unfused path): hz, h, z2, out [rows,64]; z1, a1 [rows,I];
+ * st_a, st_f [rows,2] = (mean, rstd).  Dropout: masks [rows,64] or Philox streams as acsr_bias_dropout_res_ln_fwd. */
+int64_t acsr_dense_prep_floats(int I);
+int acsr_dense_prep(const float* Wo, const float* W1, const float* W2, int d, int I, float* ops, void* stream);
+int acsr_dense_fwd(const float* ctx, const float* res, int64_t rows, int64_t res_rows, int d, int I, int act, const float* ops,
+                   const float* bo, const float* lnA_w, const float* lnA_b, float epsA, const float* b1, const float* b2,
+                   const float* lnF_w, const float* lnF_b, float epsF, float p_drop, const float* mask_a, const float* mask_f,
+                   const void* rng, uint32_t stream_a, uint32_t stream_f, float* hz, float* st_a, float* h, float* z1, float* a1,
+                   float* z2, float* st_f, float* out, int passes, void* stream);
+
 /* ---- loss_type BPR (model/sequential_recommender/acsasrec.py:109-116, model/loss.py:21-47) ----
  * x_m = out_m . (E[pos_m] - E[neg_m]); row_loss[m] = -log(gamma + sigmoid(x_m)); loss[g] = mean over row group g
  * (M rows in n_groups equal groups: [calibrated ; attacked] in the fused step).  row_x [M] is saved for the backward. */

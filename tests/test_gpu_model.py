@@ -275,7 +275,7 @@ def test_fused_step_optional_paths_match_reference_grads(A, name):
     the last layer's dense part as separate launches."""
     c = load_case(name)
     z = c['z']
-    for switch in ('fold_gate', 'no_ce_fused_bwd', 'no_tail_fused', 'fuse_act_bwd'):
+    for switch in ('fold_gate', 'no_ce_fused_bwd', 'no_tail_fused', 'fuse_act_bwd', 'dense_fused'):
         config, model = build_model(A, c)
         trainer = A.ACSASRecTrainer(config, model)
         f = trainer.fused
@@ -285,8 +285,10 @@ def test_fused_step_optional_paths_match_reference_grads(A, name):
             f.ce_fused_bwd = False
         elif switch == 'no_tail_fused':
             f.tail_fused = False
-        else:
+        elif switch == 'fuse_act_bwd':
             f.fuse_act_bwd = True
+        else:
+            f.dense_fused = True
         model.train()
         l_att, l_cal = f(inter_of(A, c))
         assert abs(float(l_att) - float(z['loss_att'])) < 1e-4 * abs(float(z['loss_att'])), switch
