@@ -38,6 +38,7 @@ struct LogitsParams {
   int skip_col0;
   float* pval;           // [M, n_chunks, k]
   long long* pidx;
+  int* row_bound;        // [M] or NULL: order-preserving int image of a lower bound of each row's k-th best score, shared by the CTAs of a launch
   // LINEAR: stationary operand element (r,k) = out[r*out_sn + k*out_sk]; Y[v*ldc + r] (+)= D[r][v] + bias[r]
   long long out_sn, out_sk;
   const float* bias;

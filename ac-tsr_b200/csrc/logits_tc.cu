@@ -51,6 +51,8 @@ struct TcCfg {
 // Thread-private top-k candidate set kept UNSORTED with a cached minimum (slot-major in shared memory so
 // lane == bank for every slot).  A new score replaces the current minimum and the k slots are rescanned
 // with independent loads -- no dependent shift chain as in a sorted insert; acsr_topk_merge sorts at the end.
+// (A binary min-heap with one sift-down per insert was measured too: 720 vs 734 us at 1M items, slower at k = 10 -- the cost
+// of an insertion is the lockstep drain round around it, not the rescan.)
 __device__ __noinline__ void topk_insert(float x, int col, float* lval, int* lidx, int row, int k, int& cnt, float& thr,
                                          int& minpos) {
   if (cnt < k) {
@@ -71,6 +73,10 @@ __device__ __noinline__ void topk_insert(float x, int col, float* lval, int* lid
   thr = m;
   minpos = mp;
 }
+
+// order-preserving int image of a float (signed integer compare == float compare), for atomicMax on a shared lower bound
+__device__ __forceinline__ int bound_enc(float x) { const int b = __float_as_int(x); return b >= 0 ? b : b ^ 0x7fffffff; }
+__device__ __forceinline__ float bound_dec(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 
 template <int MODE>
 __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(const LogitsParams p) {
@@ -227,6 +233,8 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
     int* lidx = reinterpret_cast<int*>(smem + Cfg::kOffTopk + kMaxTopK * kBM * 4);
     int cnt = 0, minpos = 0, npend = 0;
     float thr = -INFINITY;
+    float gb = -INFINITY;                         // MODE_TOPK: lower bound of the row's overall k-th best score, from p.row_bound
+    float rmax = -INFINITY, rmax_pub = -INFINITY;  // best score of this CTA's stream for the row, and the value last published
     if (MODE == MODE_GRAD && row_ok) { g_lse = p.lse[grow]; g_scale = p.row_scale[grow]; g_tgt = p.target[grow]; }
     float lin_bias = 0.f;
     if (MODE == MODE_LINEAR && row_ok && p.bias != nullptr) lin_bias = p.bias[blockIdx.y * p.b_bias + grow];
@@ -236,6 +244,24 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
       const long long n0 = (long long)(chunk + it * p.n_chunks) * kBN;
       mbar_wait(tm_full + ob, ph);
       tc_fence_after();
+      if (MODE == MODE_TOPK && p.row_bound != nullptr && row_ok && (it < 16 ? (it & 3) == 1 : (it & 15) == 1)) {
+        // Every CTA of this row tile publishes the best score of its own stream (slot [chunk][row]).  Those are n_chunks DIFFERENT
+        // catalogue items, so once n_chunks >= k of them are known, their minimum is a lower bound of the row's overall k-th best:
+        // a score at or below it cannot make the top-k and never touches the candidate list.  (Each stream's own k-th best is a far
+        // weaker bound: all streams are equally long, so sharing THAT gains nothing -- measured.)
+        int mn = 0x7fffffff;                 // (the encoding is order preserving: take the minimum on the integer images)
+        const int* rb = p.row_bound + grow;
+        int c = 0;
+        for (; c + 8 <= p.n_chunks; c += 8) {
+          int t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = __ldcg(rb + (long long)(c + u) * p.M);      // eight independent loads in flight
+#pragma unroll
+          for (int u = 0; u < 8; ++u) mn = min(mn, t[u]);
+        }
+        for (; c < p.n_chunks; ++c) mn = min(mn, __ldcg(rb + (long long)c * p.M));
+        gb = fmaxf(gb, bound_dec(mn));
+      }
 #pragma unroll 1
       for (int cc = (MODE == MODE_CE ? half : 0); cc < (MODE == MODE_CE ? half + 1 : kBN / 32); ++cc) {
         float v[32];
@@ -323,23 +349,33 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
             for (int i = 0; i < 32; ++i)
               if (i >= nvalid || (p.skip_col0 && c0 + i == 0)) v[i] = -INFINITY;
           }
+          // A score at or below `gb` cannot be among the row's k best of the WHOLE catalogue (see the refresh above).  Without it
+          // every CTA's stream pays k (1 + ln(n/k)) list insertions per row, each a rescan of the k slots.
+          float cmax = v[0];                                     // best score of this chunk for the row
+#pragma unroll
+          for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, v[i]);
+          rmax = fmaxf(rmax, cmax);
           auto drain = [&]() {
             while (__any_sync(0xffffffffu, npend > 0)) {
               if (npend > 0) {
                 --npend;
                 const float y = lval[(k + npend) * kBM + row];
-                if (cnt < k || y > thr) topk_insert(y, lidx[(k + npend) * kBM + row], lval, lidx, row, k, cnt, thr, minpos);
+                if (y > gb && (cnt < k || y > thr)) topk_insert(y, lidx[(k + npend) * kBM + row], lval, lidx, row, k, cnt, thr, minpos);
               }
             }
           };
-          if (__any_sync(0xffffffffu, cnt < k) || pcap < 8) {
-            // filling the list (first tile) or no room to park: insert on the spot
+          if (__any_sync(0xffffffffu, cnt < k && !(gb > -INFINITY)) || pcap < 8) {
+            // filling the list (first tile, no bound yet) or no room to park: insert on the spot
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float x = v[i];
-              if (x != -INFINITY && (cnt < k || x > thr)) topk_insert(x, (int)(c0 + i), lval, lidx, row, k, cnt, thr, minpos);
+              if (x != -INFINITY && x > gb && (cnt < k || x > thr)) topk_insert(x, (int)(c0 + i), lval, lidx, row, k, cnt, thr, minpos);
             }
           } else {
+            const float eff = fmaxf(thr, gb);
+            // most chunks hold no candidate for any of the warp's 32 rows once the bounds are tight: the chunk maximum decides
+            // that, and the parking loop (whose slot index is a serial dependency) is skipped altogether
+            if (__any_sync(0xffffffffu, cmax > eff))
 #pragma unroll
             for (int i0 = 0; i0 < 32; i0 += 8) {
               // at most 8 scores are parked per row before the next check: drain when some row has fewer than 8 free slots
@@ -347,7 +383,7 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
 #pragma unroll
               for (int i = i0; i < i0 + 8; ++i) {
                 const float x = v[i];
-                if (x > thr) {
+                if (x > eff) {
                   lval[(k + npend) * kBM + row] = x;
                   lidx[(k + npend) * kBM + row] = (int)c0 + i;
                   ++npend;
@@ -360,6 +396,10 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
       }
       tc_fence_before();
       mbar_arrive(tm_empty + ob);
+      if (MODE == MODE_TOPK && p.row_bound != nullptr && row_ok && rmax > rmax_pub) {
+        __stcg(p.row_bound + (long long)chunk * p.M + grow, bound_enc(rmax));
+        rmax_pub = rmax;
+      }
     }
     if (MODE == MODE_CE) {
       // the two column halves of a row meet once: the upper warp parks its pair, the lower one combines and stores
@@ -667,6 +707,11 @@ int acsr_linear_tc(const float* X, int64_t rows, int K, const float* W, int N, i
 
 int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_t V, int d, int passes, int k, int64_t idx_offset,
                              int skip_col0, float* partial_val, int64_t* partial_idx, void* stream) {
+  return acsr_logits_topk_partial_ws(out, table, M, V, d, passes, k, idx_offset, skip_col0, partial_val, partial_idx, nullptr, stream);
+}
+
+int acsr_logits_topk_partial_ws(const float* out, const float* table, int M, int64_t V, int d, int passes, int k, int64_t idx_offset,
+                                int skip_col0, float* partial_val, int64_t* partial_idx, int32_t* row_bound, void* stream) {
   int rc = validate_common(out, table, M, V, d, passes, "logits_topk_partial");
   if (rc) return rc;
   ACSR_REQUIRE(partial_val && partial_idx, "logits_topk_partial: NULL output");
@@ -675,6 +720,17 @@ int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_
   p.out = out; p.table = table; p.M = M; p.V = V; p.passes = passes;
   p.k = k; p.idx_offset = idx_offset; p.skip_col0 = skip_col0; p.pval = partial_val; p.pidx = (long long*)partial_idx;
   if (d != kD) return launch_logits_simt(MODE_TOPK, p, d, (cudaStream_t)stream, "logits_topk_partial");   // fp32 FMA path (logits_simt.cu)
+  {
+    LogitsParams q = p;                    // the plan decides how many CTAs share a row tile: the bound needs at least k of them
+    logits_plan(q);
+    logits_plan_topk(q);
+    p.row_bound = (row_bound != nullptr && q.n_chunks >= k) ? row_bound : nullptr;
+    if (p.row_bound != nullptr) {
+      // every byte 0x80: a very negative score (-3.4e38) in the order-preserving int encoding = "nothing published yet"
+      cudaError_t e = cudaMemsetAsync(row_bound, 0x80, (size_t)M * q.n_chunks * sizeof(int32_t), (cudaStream_t)stream);
+      if (e != cudaSuccess) { set_error("logits_topk_partial: memset: %s", cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
+    }
+  }
   return launch_tc<MODE_TOPK>(p, (cudaStream_t)stream, "logits_topk_partial");
 }
 

@@ -248,6 +248,13 @@ int acsr_ce_bwd_dtable(const float* out, const float* table, const float* lse, c
 int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_t V, int d, int passes,
                              int k, int64_t idx_offset, int skip_col0,
                              float* partial_val, int64_t* partial_idx, void* stream);
+/* the same with a caller-owned scratch row_bound [M * acsr_logits_num_chunks(M, V)] (int32, contents irrelevant): every CTA of a
+ * row tile publishes the best score of its own stream; once at least k streams have, the minimum of those (k or more different
+ * items) is a lower bound of the row's overall k-th best, and scores at or below it never touch a candidate list.  Results are
+ * identical (up to exact score ties).  row_bound == NULL, or fewer than k CTAs per row tile: acsr_logits_topk_partial. */
+int acsr_logits_topk_partial_ws(const float* out, const float* table, int M, int64_t V, int d, int passes,
+                                int k, int64_t idx_offset, int skip_col0,
+                                float* partial_val, int64_t* partial_idx, int32_t* row_bound, void* stream);
 /* merge n_parts partial lists per row (any order) -> topk_val [M,k], topk_idx [M,k] int64 and, when
  * positive != NULL, rec_topk [M,k+1] int32 = hit flags + pos_len(=1) (collector.py:148-153). */
 int acsr_topk_merge(const float* partial_val, const int64_t* partial_idx, int M, int n_parts, int k,

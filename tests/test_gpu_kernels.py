@@ -644,11 +644,11 @@ def test_logits_topk_fused(A, M, V, k):
     pos = torch.randint(1, V, (M,), generator=g)
     scores = (out.double() @ E.double().t())
     _, ref_idx = O.full_sort_topk(scores.float(), k)
-    for path in ('auto', 'fused'):          # auto: small catalogues take scores + radix select; fused: streaming top-k + merge
+    for path in ('auto', 'fused', 'fused-private'):   # auto: small catalogues take scores + radix select; fused: streaming top-k (CTAs share a per-row bound) + merge; fused-private: every CTA on its own
         if path == 'auto':
             val, idx, rec = A.ops.full_sort_topk(out.cuda(), E.cuda(), k, pos.cuda(), 3)
         else:
-            pv, pi = A.ops.logits_topk_partial(out.cuda(), E.cuda(), k, 0, True, 3)
+            pv, pi = A.ops.logits_topk_partial(out.cuda(), E.cuda(), k, 0, True, 3, share_bound=(path == 'fused'))
             assert pv.shape[1] == A.ops.logits_num_chunks(M, V)
             val, idx, rec = A.ops.topk_merge(pv, pi, k, pos.cuda())
         idx, val, rec = idx.cpu(), val.cpu(), rec.cpu()
