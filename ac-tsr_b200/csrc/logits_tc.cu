@@ -27,25 +27,31 @@ struct TcCfg {
   static constexpr int kStages = MODE == MODE_TOPK ? 2 : 4;
   static constexpr int kAbytes = kBM * kD * 4;          // 32 KB per (hi|lo)
   static constexpr int kBbytes = kBN * kD * 4;          // 16 KB per (hi|lo) per buffer
+  // MODE_TOPK keeps the stationary tile of `out` in TENSOR MEMORY (hi / lo halves written once with tcgen05.st; the MMAs take
+  // it as their A operand, TS form): its shared memory goes to a second set of candidate lists, so that the top-k epilogue --
+  // the bottleneck of the kernel, one thread per logits row -- runs on eight warps like the CE epilogue.
+  static constexpr bool kATmem = MODE == MODE_TOPK;
   static constexpr int kOffAhi = 0;
-  static constexpr int kOffAlo = kOffAhi + kAbytes;
-  static constexpr int kOffBhi = kOffAlo + kAbytes;      // [2]
+  static constexpr int kOffAlo = kOffAhi + (kATmem ? 0 : kAbytes);
+  static constexpr int kOffBhi = kOffAlo + (kATmem ? 0 : kAbytes);      // [2]
   static constexpr int kOffBlo = kOffBhi + 2 * kBbytes;  // [2]
   static constexpr int kOffStg = kOffBlo + 2 * kBbytes;  // [kStages]
   static constexpr int kOffTopk = kOffStg + kStages * kBbytes;
-  static constexpr int kTopkBytes = MODE == MODE_TOPK ? 2 * kMaxTopK * kBM * 4 : 0;
-  // MODE_CE: the epilogue is instruction-issue bound (one thread per logits row), so it runs on EIGHT warps, two per TMEM lane
-  // quarter, each owning one 32-column half of every tile; the halves meet once, at the end, through kOffPair
-  static constexpr int kEpiWarps = MODE == MODE_CE ? 8 : 4;
+  static constexpr int kListBytes = 2 * kMaxTopK * kBM * 4;              // values + indices of one warp set: 64 KB
+  static constexpr int kTopkBytes = MODE == MODE_TOPK ? 2 * kListBytes : 0;
+  // MODE_CE / MODE_TOPK: the epilogue is instruction-issue / latency bound (one thread per logits row), so it runs on EIGHT warps,
+  // two per TMEM lane quarter, each owning one 32-column half of every tile; the halves meet once, at the end, through kOffPair
+  static constexpr int kEpiWarps = (MODE == MODE_CE || MODE == MODE_TOPK) ? 8 : 4;
   // Two MMA-issuing threads (warp 1: even tiles, the last warp: odd tiles -- each owns one operand buffer and one accumulator
   // stage): a thread issues one 128 x 64 x 8 TF32 MMA every ~90 cycles against a 32-cycle tensor floor (scripts/umma_rate.py)
   static constexpr int kIssuer2 = 6 + kEpiWarps;
   static constexpr int kThreads = 192 + 32 * kEpiWarps + 32;
   static constexpr int kOffPair = kOffTopk + kTopkBytes;
-  static constexpr int kPairBytes = MODE == MODE_CE ? kBM * 8 : 0;
+  static constexpr int kPairBytes = (MODE == MODE_CE || MODE == MODE_TOPK) ? kBM * 8 : 0;
   static constexpr int kOffBar = kOffPair + kPairBytes;
   static constexpr int kNumBars = 2 * kStages + 2 + 2 + 2 + 2;
   static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
+  static constexpr int kTmem = kATmem ? 256 : kTmemCols;                 // 2 accumulator stages (+ out hi / lo at columns 128 / 192)
 };
 
 // Thread-private top-k candidate set kept UNSORTED with a cached minimum (slot-major in shared memory so
@@ -109,10 +115,10 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 1) tmem_alloc<Cfg::kTmem>(tmem_slot);
 
   // stationary A tile: rows of `out`, split into hi/lo TF32, canonical K-major layout
-  {
+  if (!Cfg::kATmem) {
     float* Ahi = reinterpret_cast<float*>(smem + Cfg::kOffAhi);
     float* Alo = reinterpret_cast<float*>(smem + Cfg::kOffAlo);
     for (int item = threadIdx.x; item < kBM * kKC; item += Cfg::kThreads) {
@@ -139,6 +145,27 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (Cfg::kATmem) {
+    // the thread's row of `out` (its 32 columns) -> TMEM columns 128.. (hi) and 192.. (lo): the A operand of every MMA
+    if (warp >= 6 && warp < Cfg::kIssuer2) {
+      const int quarter = warp & 3, half = (warp - 6) >> 2;
+      const int grow = m_tile * kBM + quarter * 32 + lane;
+      float hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grow < p.M) x = *reinterpret_cast<const float4*>(out_p + (long long)grow * kD + half * 32 + 4 * j);
+        hi[4 * j + 0] = to_tf32(x.x); hi[4 * j + 1] = to_tf32(x.y); hi[4 * j + 2] = to_tf32(x.z); hi[4 * j + 3] = to_tf32(x.w);
+        lo[4 * j + 0] = x.x - hi[4 * j + 0]; lo[4 * j + 1] = x.y - hi[4 * j + 1]; lo[4 * j + 2] = x.z - hi[4 * j + 2]; lo[4 * j + 3] = x.w - hi[4 * j + 3];
+      }
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 32;
+      tmem_st32(t_row + 128, hi);
+      tmem_st32(t_row + 192, lo);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   if (warp == 0) {
     // ------------------------------ producer ------------------------------
@@ -176,9 +203,14 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
           const uint32_t b_base = (npass == 3 && ps == 1) ? b_lo : b_hi;
 #pragma unroll
           for (int ks = 0; ks < kD / 8; ++ks) {
-            const uint64_t ad = umma_desc_kmajor(a_base + ks * 2 * kALbo, kALbo, kSbo);
             const uint64_t bd = umma_desc_kmajor(b_base + ks * 2 * kBLbo, kBLbo, kSbo);
-            umma_tf32(d_tmem, ad, bd, idesc, acc);
+            if (Cfg::kATmem) {
+              const uint32_t at = tmem_base + ((npass == 3 && ps == 0) ? 192 : 128) + ks * 8;
+              umma_tf32_ts(d_tmem, at, bd, idesc, acc);
+            } else {
+              const uint64_t ad = umma_desc_kmajor(a_base + ks * 2 * kALbo, kALbo, kSbo);
+              umma_tf32(d_tmem, ad, bd, idesc, acc);
+            }
             acc = 1;
           }
         }
@@ -229,8 +261,9 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
     float run_m = -INFINITY, run_s = 0.f;         // MODE_CE
     float g_lse = 0.f, g_scale = 0.f;             // MODE_GRAD
     long long g_tgt = -1;
-    float* lval = reinterpret_cast<float*>(smem + Cfg::kOffTopk);           // [k][128]
-    int* lidx = reinterpret_cast<int*>(smem + Cfg::kOffTopk + kMaxTopK * kBM * 4);
+    const int lhalf = MODE == MODE_TOPK ? half : 0;                          // MODE_TOPK: each warp set keeps its own candidate lists
+    float* lval = reinterpret_cast<float*>(smem + Cfg::kOffTopk + lhalf * Cfg::kListBytes);           // [k][128]
+    int* lidx = reinterpret_cast<int*>(smem + Cfg::kOffTopk + lhalf * Cfg::kListBytes + kMaxTopK * kBM * 4);
     int cnt = 0, minpos = 0, npend = 0;
     float thr = -INFINITY;
     float gb = -INFINITY;                         // MODE_TOPK: lower bound of the row's overall k-th best score, from p.row_bound
@@ -244,26 +277,27 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
       const long long n0 = (long long)(chunk + it * p.n_chunks) * kBN;
       mbar_wait(tm_full + ob, ph);
       tc_fence_after();
-      if (MODE == MODE_TOPK && p.row_bound != nullptr && row_ok && (it < 16 ? (it & 3) == 1 : (it & 15) == 1)) {
-        // Every CTA of this row tile publishes the best score of its own stream (slot [chunk][row]).  Those are n_chunks DIFFERENT
-        // catalogue items, so once n_chunks >= k of them are known, their minimum is a lower bound of the row's overall k-th best:
+      if (MODE == MODE_TOPK && p.row_bound != nullptr && row_ok && (it < 8 ? (it & 3) == 1 : (it & 31) == 9)) {
+        // Every warp set of every CTA of this row tile publishes the best score of its own stream (slot [2 chunk + half][row]).
+        // Those are 2 n_chunks DIFFERENT catalogue items, so once >= k of them are known, their minimum is a lower bound of the row's overall k-th best:
         // a score at or below it cannot make the top-k and never touches the candidate list.  (Each stream's own k-th best is a far
         // weaker bound: all streams are equally long, so sharing THAT gains nothing -- measured.)
         int mn = 0x7fffffff;                 // (the encoding is order preserving: take the minimum on the integer images)
         const int* rb = p.row_bound + grow;
         int c = 0;
-        for (; c + 8 <= p.n_chunks; c += 8) {
+        const int n_streams = 2 * p.n_chunks;
+        for (; c + 8 <= n_streams; c += 8) {
           int t[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) t[u] = __ldcg(rb + (long long)(c + u) * p.M);      // eight independent loads in flight
 #pragma unroll
           for (int u = 0; u < 8; ++u) mn = min(mn, t[u]);
         }
-        for (; c < p.n_chunks; ++c) mn = min(mn, __ldcg(rb + (long long)c * p.M));
+        for (; c < n_streams; ++c) mn = min(mn, __ldcg(rb + (long long)c * p.M));
         gb = fmaxf(gb, bound_dec(mn));
       }
 #pragma unroll 1
-      for (int cc = (MODE == MODE_CE ? half : 0); cc < (MODE == MODE_CE ? half + 1 : kBN / 32); ++cc) {
+      for (int cc = (Cfg::kEpiWarps == 8 ? half : 0); cc < (Cfg::kEpiWarps == 8 ? half + 1 : kBN / 32); ++cc) {
         float v[32];
         tmem_ld32(t_lane + ob * kBN + cc * 32, v);
         const long long c0 = n0 + cc * 32;
@@ -397,7 +431,7 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
       tc_fence_before();
       mbar_arrive(tm_empty + ob);
       if (MODE == MODE_TOPK && p.row_bound != nullptr && row_ok && rmax > rmax_pub) {
-        __stcg(p.row_bound + (long long)chunk * p.M + grow, bound_enc(rmax));
+        __stcg(p.row_bound + (long long)(2 * chunk + half) * p.M + grow, bound_enc(rmax));
         rmax_pub = rmax;
       }
     }
@@ -416,7 +450,22 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
         o[0] = nm; o[1] = s;
       }
     }
-    if (MODE == MODE_TOPK && row_ok) {
+    if (MODE == MODE_TOPK) {
+      // the two warp sets of a row meet once: the upper set's candidates are inserted into the lower set's list
+      int* pcnt = reinterpret_cast<int*>(smem + Cfg::kOffPair);
+      if (half == 1) pcnt[row] = cnt;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::kEpiWarps) : "memory");
+      if (half == 0) {
+        const int cnt1 = pcnt[row];
+        const float* oval = reinterpret_cast<const float*>(smem + Cfg::kOffTopk + Cfg::kListBytes);
+        const int* oidx = reinterpret_cast<const int*>(smem + Cfg::kOffTopk + Cfg::kListBytes + kMaxTopK * kBM * 4);
+        for (int s2 = 0; s2 < cnt1; ++s2) {
+          const float y = oval[s2 * kBM + row];
+          if (cnt < p.k || y > thr) topk_insert(y, oidx[s2 * kBM + row], lval, lidx, row, p.k, cnt, thr, minpos);
+        }
+      }
+    }
+    if (MODE == MODE_TOPK && row_ok && half == 0) {
       float* ov = p.pval + ((long long)grow * p.n_slots + chunk) * p.k;
       long long* oi = p.pidx + ((long long)grow * p.n_slots + chunk) * p.k;
       for (int s = 0; s < p.k; ++s) {
@@ -436,7 +485,7 @@ __global__ void __launch_bounds__(TcCfg<MODE>::kThreads, 1) logits_tc_kernel(con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    tmem_dealloc<Cfg::kTmem>(tmem_base);
   }
 }
 
@@ -724,10 +773,10 @@ int acsr_logits_topk_partial_ws(const float* out, const float* table, int M, int
     LogitsParams q = p;                    // the plan decides how many CTAs share a row tile: the bound needs at least k of them
     logits_plan(q);
     logits_plan_topk(q);
-    p.row_bound = (row_bound != nullptr && q.n_chunks >= k) ? row_bound : nullptr;
+    p.row_bound = (row_bound != nullptr && 2 * q.n_chunks >= k) ? row_bound : nullptr;     // two streams (warp sets) per CTA
     if (p.row_bound != nullptr) {
       // every byte 0x80: a very negative score (-3.4e38) in the order-preserving int encoding = "nothing published yet"
-      cudaError_t e = cudaMemsetAsync(row_bound, 0x80, (size_t)M * q.n_chunks * sizeof(int32_t), (cudaStream_t)stream);
+      cudaError_t e = cudaMemsetAsync(row_bound, 0x80, (size_t)M * 2 * q.n_chunks * sizeof(int32_t), (cudaStream_t)stream);
       if (e != cudaSuccess) { set_error("logits_topk_partial: memset: %s", cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
     }
   }

@@ -530,7 +530,7 @@ def logits_topk_partial(out, table, k, idx_offset=0, skip_col0=True, passes=3, s
     pv = torch.empty((M, nc, k), dtype=torch.float32, device=out.device)
     pi = torch.empty((M, nc, k), dtype=torch.int64, device=out.device)
     # scratch for the per-row lower bound the CTAs of the launch share (acsr_logits_topk_partial_ws)
-    rb = torch.empty(M * nc, dtype=torch.int32, device=out.device) if share_bound else None
+    rb = torch.empty(2 * M * nc, dtype=torch.int32, device=out.device) if share_bound else None
     LIB.call('acsr_logits_topk_partial_ws', _p(out), _p(table), M, V, d, passes, k, idx_offset, int(skip_col0),
              _p(pv), _p(pi, torch.int64), _p(rb, torch.int32), _stream())
     return pv, pi

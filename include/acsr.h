@@ -248,8 +248,8 @@ int acsr_ce_bwd_dtable(const float* out, const float* table, const float* lse, c
 int acsr_logits_topk_partial(const float* out, const float* table, int M, int64_t V, int d, int passes,
                              int k, int64_t idx_offset, int skip_col0,
                              float* partial_val, int64_t* partial_idx, void* stream);
-/* the same with a caller-owned scratch row_bound [M * acsr_logits_num_chunks(M, V)] (int32, contents irrelevant): every CTA of a
- * row tile publishes the best score of its own stream; once at least k streams have, the minimum of those (k or more different
+/* the same with a caller-owned scratch row_bound [2 * M * acsr_logits_num_chunks(M, V)] (int32, contents irrelevant): every warp set
+ * of every CTA of a row tile publishes the best score of its own stream; once at least k streams have, the minimum of those (k or more different
  * items) is a lower bound of the row's overall k-th best, and scores at or below it never touch a candidate list.  Results are
  * identical (up to exact score ties).  row_bound == NULL, or fewer than k CTAs per row tile: acsr_logits_topk_partial. */
 int acsr_logits_topk_partial_ws(const float* out, const float* table, int M, int64_t V, int d, int passes,
