@@ -32,8 +32,8 @@ __device__ __forceinline__ void bwd_body(const AttnParams& p, const AttnSmem& sm
     const int iraw = iw - grp;
     const bool rowok = iraw >= 0;
     const int i = rowok ? iraw : 0;
-    const int bound = p.bidir ? nkey : min(i + 1, nkey);
-    const int nj = ((p.bidir ? nkey : min(iw + 1, nkey)) + G - 1) / G;
+    const int bound = p.full ? nkey : min(i + 1, nkey);
+    const int nj = ((p.full ? nkey : min(iw + 1, nkey)) + G - 1) / G;
     if (rt >= 0 && (rt > iw || rt <= iw - RPW)) {       // rows without a context cotangent: penalty path only
 #define ACSR_BWD_ROW_M(NJV) bwd_row_iter_m<DH, G, NJV, NS>(p, sm, bs, kc, dpen, b, h, i, rowok, bound, grp, sub, rstride, wbuf)
       if (MAXNJ == 1 || nj == 1) ACSR_BWD_ROW_M(1);
@@ -86,7 +86,7 @@ __device__ __forceinline__ void bwd_cols(const AttnParams& p, const AttnSmem& sm
 #pragma unroll
       for (int k = 0; k < CM::CPL; ++k) ak_[s][k] = ak2_[s][k] = av_[s][k] = 0.f;
     int lo, hi;
-    CM::slice(sub, p.bidir ? 0 : (j & ~3), LP, lo, hi);      // rows i that see column j
+    CM::slice(sub, p.full ? 0 : (j & ~3), LP, lo, hi);      // rows i that see column j
     const int off = mat_row(p, j, LP);
     for (int i = lo; i < hi; i += 4) {
       float s1v[NS][4], s2v[NS][4];
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_kernel(const AttnPar
   extern __shared__ __align__(16) float smem_f[];
   constexpr int dhp = DH + 4;
   const int L = p.L, LP = (L + 3) & ~3;
-  const int TRI = mat_floats(p.bidir, L, LP);
+  const int TRI = mat_floats(p.full, L, LP);
   const int b = p.order ? p.order[blockIdx.x / p.H] : (int)(blockIdx.x / p.H), h = blockIdx.x % p.H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* ptr = smem_f;
@@ -249,7 +249,7 @@ static size_t bwd_smem_bytes(int L, int dh, int ns, int bidir) {
 
 template <int DH, int NS>
 static int launch_bwd(const AttnParams& p, cudaStream_t st) {
-  size_t smem = bwd_smem_bytes(p.L, DH, NS, p.bidir);
+  size_t smem = bwd_smem_bytes(p.L, DH, NS, p.full);
   int rc = prep_kernel(attn_bwd_kernel<DH, NS>, smem, "attn_calib_bwd");
   if (rc) return rc;
   launch_pdl(attn_bwd_kernel<DH, NS>, dim3(p.B * p.H), dim3(kAttnThreads), smem, st, p);

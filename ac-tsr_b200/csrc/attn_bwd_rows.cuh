@@ -129,7 +129,10 @@ __device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem
           if (owner && rowok) acc.s_ratio += dRf[jj] * (r.R[jj] - Pj[jj]);
         }
       }
-      softmax_bwd_row<G, NJ>(r.R, dR, dcm);            // grad wrt (comb + mask)
+      if (p.plain) {                                   // transformer_layers.py: no re-normalising softmax to go through
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) dcm[jj] = dR[jj];
+      } else softmax_bwd_row<G, NJ>(r.R, dR, dcm);     // grad wrt (comb + mask)
       if (p.combine == ACSR_ATTN_COMBINE_FIXED) {
         softmax_bwd_row<G, NJ>(r.F, dcm, tmp);          // grad wrt (O + 0.5 C); columns outside the range carry no cotangent
 #pragma unroll
@@ -146,7 +149,10 @@ __device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem
           }
         }
       }
-      softmax_bwd_row<G, NJ>(r.C, dC, tmp);             // grad wrt (O*expm + mask)
+      if (p.plain) {
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) tmp[jj] = dC[jj];
+      } else softmax_bwd_row<G, NJ>(r.C, dC, tmp);      // grad wrt (O*expm + mask)
 #pragma unroll
       for (int jj = 0; jj < NJ; ++jj) {
         dO[jj] += tmp[jj] * expm[jj];
@@ -154,7 +160,10 @@ __device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem
       }
     }
     if (useA) {
-      softmax_bwd_row<G, NJ>(r.A, dA, tmp);             // grad wrt (O*M + n(1-M) + mask)
+      if (p.plain) {
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) tmp[jj] = dA[jj];
+      } else softmax_bwd_row<G, NJ>(r.A, dA, tmp);      // grad wrt (O*M + n(1-M) + mask)
 #pragma unroll
       for (int jj = 0; jj < NJ; ++jj) {
         dO[jj] += tmp[jj] * Mj[jj];

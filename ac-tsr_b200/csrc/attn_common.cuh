@@ -42,6 +42,9 @@ struct AttnParams {
   int B, L, H, dh, d;
   int two_level, combine, rich;
   int bidir;                 // bidirectional attention mask (AcBERT4Rec, get_attention_mask(bidirectional=True)): keys j > i stay in play
+  int plain;                 // transformer_layers.py:873-953 (ACSSEPT): A, C and the combined attention are NOT re-normalised by a
+                             // masked softmax (layers.py:917-925 does); the attacked weights of masked keys are then pure noise
+  int full;                  // bidir | plain: all keys of a row are in play (no causal work skipping, dense [L][LP] matrices)
   float comb_scalar;
   const float* rich_ratio;
   float p;
@@ -221,7 +224,7 @@ __host__ __device__ __forceinline__ int tri_off(int j, int LP) {
 
 // offset of row j of a transposed [j][i] shared-memory matrix such that element i sits at mat_row(...) + i: packed lower
 // triangular for causal attention (i >= j & ~3), dense [L][LP] for the bidirectional mask
-__device__ __forceinline__ int mat_row(const AttnParams& p, int j, int LP) { return p.bidir ? j * LP : tri_off(j, LP) - (j & ~3); }
+__device__ __forceinline__ int mat_row(const AttnParams& p, int j, int LP) { return p.full ? j * LP : tri_off(j, LP) - (j & ~3); }
 __host__ __device__ __forceinline__ int mat_floats(int bidir, int L, int LP) { return bidir ? L * LP : tri_off(L, LP); }
 
 // async copy of rows [0,rows) of one [L, DH] head slice into a padded smem tile; rows [rows, rows_pad) are zeroed
@@ -261,6 +264,7 @@ __device__ __forceinline__ int stage_common(const AttnParams& p, const AttnSmem&
   const unsigned m0 = (unsigned)sm.misc[0], m1 = (unsigned)sm.misc[1];
   int nkey = m1 ? 64 - __clz(m1) : (m0 ? 32 - __clz(m0) : 0);
   nkey = max(nkey, 1);
+  if (p.plain) nkey = L;       // masked keys keep a weight (the attack noise): every key row is staged
   const int nkp = (nkey + 3) & ~3;
   stage_tile<DH>(sm.K, p.mk, b, h, L, p.d, nkey, nkp);
   stage_tile<DH>(sm.V, p.mv, b, h, L, p.d, nkey, nkp);
@@ -470,15 +474,21 @@ __device__ __forceinline__ void row_forward(const AttnParams& p, const AttnSmem&
   if (need_att) {
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj)
-      z[jj] = O[jj] * M[jj] + r.nz[jj] * (1.0f - M[jj]) + (((valid >> jj) & 1u) ? 0.f : kMaskNeg);
-    softmax_row<G, NJ>(z, act, r.A);
+      z[jj] = O[jj] * M[jj] + r.nz[jj] * (1.0f - M[jj]) + ((p.plain || ((valid >> jj) & 1u)) ? 0.f : kMaskNeg);
+    if (p.plain) {              // transformer_layers.py:919: used as is
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) r.A[jj] = ((act >> jj) & 1u) ? z[jj] : 0.f;
+    } else softmax_row<G, NJ>(z, act, r.A);
   } else {
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) r.A[jj] = 0.f;
   }
 #pragma unroll
-  for (int jj = 0; jj < NJ; ++jj) z[jj] = O[jj] * expm[jj] + (((valid >> jj) & 1u) ? 0.f : kMaskNeg);
-  if (kc.bounded) softmax_row_bounded<G, NJ>(z, act, r.C);
+  for (int jj = 0; jj < NJ; ++jj) z[jj] = O[jj] * expm[jj] + ((p.plain || ((valid >> jj) & 1u)) ? 0.f : kMaskNeg);
+  if (p.plain) {                // transformer_layers.py:921
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) r.C[jj] = z[jj];
+  } else if (kc.bounded) softmax_row_bounded<G, NJ>(z, act, r.C);
   else softmax_row<G, NJ>(z, act, r.C);
   if (p.combine == ACSR_ATTN_COMBINE_FIXED) {
     // layers.py:885: softmax(origin + 0.5*calibrated) has NO mask: each of the L - bound columns outside the row's
@@ -502,8 +512,14 @@ __device__ __forceinline__ void row_forward(const AttnParams& p, const AttnSmem&
       float g = p.comb_scalar;
       if (p.combine == ACSR_ATTN_COMBINE_GATE) g = fsigmoid(gl[jj]);
       r.g[jj] = g; r.F[jj] = 0.f;
-      z[jj] = g * O[jj] + (1.0f - g) * r.C[jj] + (((valid >> jj) & 1u) ? 0.f : kMaskNeg);
+      z[jj] = g * O[jj] + (1.0f - g) * r.C[jj] + ((p.plain || ((valid >> jj) & 1u)) ? 0.f : kMaskNeg);
     }
+  }
+  if (p.plain) {                // transformer_layers.py:897-908: the combination itself is the attention
+    const bool fixed = p.combine == ACSR_ATTN_COMBINE_FIXED;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) r.R[jj] = fixed ? r.F[jj] : (((act >> jj) & 1u) ? z[jj] : 0.f);
+    return;
   }
   if (kc.bounded) softmax_row_bounded<G, NJ>(z, act, r.R);
   else softmax_row<G, NJ>(z, act, r.R);
@@ -597,7 +613,7 @@ static inline int attn_validate(const AttnParams& p, const char* who) {
   ACSR_REQUIRE(p.mq && p.mk && p.mv && p.aq && p.ak && p.item_seq, "%s: NULL input", who);
   ACSR_REQUIRE(p.B > 0 && p.H > 0, "%s: bad B/H", who);
   if (p.L < 1 || p.L > 256) { set_error("%s: L=%d unsupported (1..256)", who, p.L); return ACSR_ERR_UNSUPPORTED; }
-  if (p.bidir && p.L > 64) { set_error("%s: the bidirectional mask is implemented for L <= 64 (L=%d)", who, p.L); return ACSR_ERR_UNSUPPORTED; }
+  if (p.full && p.L > 64) { set_error("%s: the bidirectional mask / the transformer_layers variant are implemented for L <= 64 (L=%d)", who, p.L); return ACSR_ERR_UNSUPPORTED; }
   if (!(p.dh == 8 || p.dh == 16 || p.dh == 32 || p.dh == 64)) {
     set_error("%s: head size %d unsupported (8/16/32/64)", who, p.dh);
     return ACSR_ERR_UNSUPPORTED;
@@ -630,7 +646,7 @@ static inline void attn_fill_common(AttnParams& p, const float* mq, const float*
   p.item_seq = item_seq;
   p.ow = order_w; p.ob = order_b; p.dw = dist_w; p.db = dist_b; p.scalar = scalar;
   p.B = B; p.L = L; p.H = H; p.dh = dh; p.d = H * dh;
-  p.two_level = two_level & 1; p.bidir = (two_level >> 1) & 1; p.combine = combine_option; p.rich = rich_mode; p.comb_scalar = comb_scalar; p.rich_ratio = rich_ratio;
+  p.two_level = two_level & 1; p.bidir = (two_level >> 1) & 1; p.plain = (two_level >> 2) & 1; p.full = p.bidir | p.plain; p.combine = combine_option; p.rich = rich_mode; p.comb_scalar = comb_scalar; p.rich_ratio = rich_ratio;
   p.p = p_attn; p.D1 = D1; p.D2 = D2; p.D3 = D3; p.noise = noise; p.rng = (const RngState*)rng; p.stream = rng_stream;
 }
 

@@ -18,8 +18,8 @@ __device__ __forceinline__ void fwd_rows(const AttnParams& p, const AttnSmem& sm
     const int iraw = iw - grp;
     const bool rowok = iraw >= 0;
     const int i = rowok ? iraw : 0;
-    const int bound = p.bidir ? nkey : min(i + 1, nkey);
-    const int nj = ((p.bidir ? nkey : min(iw + 1, nkey)) + G - 1) / G;      // warp-uniform number of column groups
+    const int bound = p.full ? nkey : min(i + 1, nkey);
+    const int nj = ((p.full ? nkey : min(iw + 1, nkey)) + G - 1) / G;      // warp-uniform number of column groups
     if (rt >= 0 && (rt > iw || rt <= iw - RPW)) {       // none of this warp's rows is the consumed one: mask + penalty only
       if (p.pen_sq == nullptr) continue;
       if (MAXNJ == 1 || nj == 1) fwd_row_iter_m<DH, G, 1>(p, sm, kc, b, h, i, rowok, bound, sub, cx);

@@ -34,7 +34,8 @@ class SyntheticSequentialDataset(object):
         self.iid_field = config['ITEM_ID_FIELD']
         self.uid_field = config['USER_ID_FIELD']
         seq, ln, tgt = synth_sequences(n_rows, L, n_items, seed, full_len)
-        feat = {self.iid_field + config['LIST_SUFFIX']: seq, config['ITEM_LIST_LENGTH_FIELD']: ln, self.iid_field: tgt}
+        feat = {self.iid_field + config['LIST_SUFFIX']: seq, config['ITEM_LIST_LENGTH_FIELD']: ln, self.iid_field: tgt,
+                self.uid_field: torch.arange(n_rows, dtype=torch.int64) % max(n_rows - 1, 1) + 1}
         if pin and torch.cuda.is_available():
             feat = {k: v.pin_memory() for k, v in feat.items()}
         self.inter_feat = Interaction(feat)
@@ -50,7 +51,10 @@ class SyntheticSequentialDataset(object):
 
 def _model_fields(config):
     iid = config['ITEM_ID_FIELD']
-    return [iid + config['LIST_SUFFIX'], config['ITEM_LIST_LENGTH_FIELD'], iid]
+    f = [iid + config['LIST_SUFFIX'], config['ITEM_LIST_LENGTH_FIELD'], iid]
+    if str(config.get('model', '')) == 'ACSSEPT':          # the one model that reads the user id (acssept.py:177)
+        f.append(config['USER_ID_FIELD'])
+    return f
 
 
 class _PackedBatches(object):
@@ -147,6 +151,8 @@ class DeviceTrainDataLoader(object):
         self.device = torch.device(device if device is not None else config['device'])
         if self.device.type != 'cuda':
             raise ValueError('DeviceTrainDataLoader needs a CUDA device (got %s); use TrainDataLoader for host-side batches' % self.device)
+        if len(_model_fields(config)) != 3:
+            raise ValueError('DeviceTrainDataLoader serves the three fields of ACSASRec / AcBERT4Rec; use TrainDataLoader for %s' % config.get('model'))
         f = _model_fields(config)
         feat = dataset.inter_feat
         self.fields = list(f)

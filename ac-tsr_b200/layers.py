@@ -131,6 +131,8 @@ def key_ids_from_mask(attention_mask):
 class AttackRTransformerLayer(nn.Module):
     """layers.py:859-951."""
 
+    plain_variant = False       # True in transformer_layers.py's subclass: no re-normalising softmaxes (ACSR_ATTN_PLAIN)
+
     def __init__(self, n_heads, hidden_size, intermediate_size, hidden_dropout_prob, attn_dropout_prob, hidden_act,
                  layer_norm_eps, combine_option='fixed', use_order=True, use_distance=True, two_level=True,
                  rich_calibrated_combine='fixed', seq_length=50):
@@ -184,7 +186,7 @@ class AttackRTransformerLayer(nn.Module):
         want_probs = bool(return_attention_prob or return_all_attention_prob)
         opts = ops.AttnOpts(aa.num_attention_heads, self.two_level, self.combine_option,
                             self.rich_calibrated_combine if not self.two_level else 'none', p_attn,
-                            bidirectional=bool(getattr(rt, 'bidirectional', False)))
+                            bidirectional=bool(getattr(rt, 'bidirectional', False)), plain=self.plain_variant)
         ctx_att, ctx_cal, pen_sq, probs = ops.AttnCalibFn.apply(
             mq, mk, mv, aq, ak, gate_logit, key_ids,
             aa.order_affine.weight if aa.use_order else None, aa.order_affine.bias if aa.use_order else None,
@@ -210,12 +212,14 @@ class AttackRTransformerLayer(nn.Module):
 class AttackRTransformerEncoder(nn.Module):
     """layers.py:1070-1131: n identical layers chained on the calibrated stream."""
 
+    layer_class = AttackRTransformerLayer
+
     def __init__(self, n_layers=2, n_heads=2, hidden_size=64, inner_size=256, hidden_dropout_prob=0.5,
                  attn_dropout_prob=0.5, hidden_act='gelu', layer_norm_eps=1e-12, combine_option='fixed', use_order=True,
                  use_distance=True, two_level=True, rich_calibrated_combine='fixed', seq_length=50):
         super().__init__()
         self.layer = nn.ModuleList([
-            AttackRTransformerLayer(n_heads, hidden_size, inner_size, hidden_dropout_prob, attn_dropout_prob, hidden_act,
+            self.layer_class(n_heads, hidden_size, inner_size, hidden_dropout_prob, attn_dropout_prob, hidden_act,
                                     layer_norm_eps, combine_option, use_order=use_order, use_distance=use_distance,
                                     two_level=two_level, rich_calibrated_combine=rich_calibrated_combine,
                                     seq_length=seq_length)

@@ -178,10 +178,11 @@ def attn_workspace(B, L, H, n_streams, device):
 class AttnOpts:
     """static options of one fused-attention call (mirrors the AttackR* constructor flags)."""
 
-    def __init__(self, n_heads, two_level, combine_option, rich_mode, p_attn, bidirectional=False):
+    def __init__(self, n_heads, two_level, combine_option, rich_mode, p_attn, bidirectional=False, plain=False):
         self.n_heads = n_heads
-        # the ABI's `two_level` argument carries two flags: bit 0 two_level, bit 1 bidirectional attention mask (AcBERT4Rec)
-        self.two_level = int(bool(two_level)) | (2 if bidirectional else 0)
+        # the ABI's `two_level` argument carries three flags: bit 0 two_level, bit 1 bidirectional attention mask (AcBERT4Rec),
+        # bit 2 the transformer_layers.py variant without the re-normalising softmaxes (ACSSEPT), see ACSR_ATTN_PLAIN
+        self.two_level = int(bool(two_level)) | (2 if bidirectional else 0) | (4 if plain else 0)
         self.combine = COMBINE_IDS[combine_option]
         self.rich = RICH_IDS.get(rich_mode, 0)
         self.p_attn = float(p_attn)

@@ -10,11 +10,13 @@ import torch
 
 from .acsasrec import ACSASRec
 from .acbert4rec import AcBERT4Rec
+from .acssept import ACSSEPT
 from .compat import Config
 from .dataset import create_dataset, data_preparation
-from .trainer import ACSASRecTrainer, AcBERT4RecTrainer
+from .trainer import ACSASRecTrainer, AcBERT4RecTrainer, ACSSEPTTrainer
 
-_MODELS = {'ACSASRec': (ACSASRec, ACSASRecTrainer), 'AcBERT4Rec': (AcBERT4Rec, AcBERT4RecTrainer)}
+_MODELS = {'ACSASRec': (ACSASRec, ACSASRecTrainer), 'AcBERT4Rec': (AcBERT4Rec, AcBERT4RecTrainer),
+           'ACSSEPT': (ACSSEPT, ACSSEPTTrainer)}
 
 
 def init_seed(seed, reproducibility):

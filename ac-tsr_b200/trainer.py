@@ -604,7 +604,7 @@ class ACSASRecTrainer(object):
         """forward + fused logits/top-k + hit flags of one eval batch as a CUDA-graph replay (one graph per batch shape).
         The batch (host or device) is copied into static buffers; the returned rec tensor is a fresh copy."""
         m = self.model
-        fields = [m.ITEM_SEQ, m.ITEM_SEQ_LEN]
+        fields = list(getattr(m, 'EVAL_FIELDS', None) or [m.ITEM_SEQ, m.ITEM_SEQ_LEN])      # ACSSEPT also reads the user id
         key = tuple(tuple(interaction[k].shape) for k in fields) + (kmax,)
         g = self._eval_graphs.get(key)
         if g is None:
@@ -661,4 +661,12 @@ class ACSASRecTrainer(object):
 class AcBERT4RecTrainer(ACSASRecTrainer):
     """trainer.py:1046-1048: AcBERT4Rec trains with the same adversarial two-loss step (the routed double backward of
     trainer.py:672-686, here through the autograd Functions over the same kernels) and the same full-sort evaluation."""
+    pass
+
+
+class ACSSEPTTrainer(ACSASRecTrainer):
+    """ACSSEPT (acssept.py) under the AC training step of trainer.py:505-1036.  The reference registers no trainer of this name
+    (trainer.py:1038-1048), so get_trainer (utils.py:89-100) hands its ACSSEPT the stock Trainer, which sums the two losses and
+    cannot evaluate the tuple full_sort_predict returns; this class is the trainer the model's (attacked, calibrated) API is
+    written for, on the autograd Functions over the same kernels."""
     pass

@@ -99,6 +99,13 @@ int acsr_seq_order(const int64_t* item_seq, int B, int L, int32_t* order, void* 
  * of model/abstract_recommender.py:136-143 as AcBERT4Rec uses it (acbert4rec.py:168): only padded KEYS are masked, query
  * row i sees keys j > i too (both branches of the order calibrator, layers.py:715-719, are then in play).  L <= 64. */
 #define ACSR_ATTN_BIDIRECTIONAL 2
+/* third bit: the layer of model/transformer_layers.py:873-953 (ACSSEPT, acssept.py:61-75) instead of model/layers.py:859-951.
+ * Same projections, calibrators, attack mask and combine options, but attacked = origin*M + noise*(1-M), calibrated =
+ * origin*exp(1-M) and the combination are used AS THEY ARE (transformer_layers.py:919-927), without the masked softmax
+ * layers.py:917-925 puts around each of them.  Masked keys (future or padding) therefore keep an attacked weight -- the bare
+ * noise -- and, with combine_option fixed, a share of softmax(origin + 0.5*calibrated): all L keys of every row are in play.
+ * L <= 64. */
+#define ACSR_ATTN_PLAIN 4
 #define ACSR_ATTN_COMBINE_GATE 0
 #define ACSR_ATTN_COMBINE_FIXED 1
 #define ACSR_ATTN_COMBINE_ANNEAL 2

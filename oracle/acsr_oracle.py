@@ -26,6 +26,8 @@ Reference lines each function follows (relative to /root/reference/recbole):
   calculate_loss     model/sequential_recommender/acsasrec.py:107-144 (CE and BPR branches; model/loss.py:21-47)
   predict/full_sort  model/sequential_recommender/acsasrec.py:146-164
   bert_*             model/sequential_recommender/acbert4rec.py:152-160, 162-179, 198-245, 260-267 (AcBERT4Rec)
+  ssept_*            model/sequential_recommender/acssept.py:124-228 (ACSSEPT) on model/transformer_layers.py:742-953,
+                     the encoder variant without the re-normalising softmaxes (cfg['attn_variant'] == 'transformer_layers')
   train_grads        trainer/trainer.py:660-687 (two backward passes routed by name)
   full_sort_topk     trainer/trainer.py:941-942, evaluator/collector.py:145-153
   metrics            evaluator/metrics.py:62-64,88-96,159-160,186-202; base_metric.py:65-80
@@ -178,8 +180,12 @@ def attn_calib(mq, mk, mv, aq, ak, gate_logit, mask, lp, cfg, l, rnd, anneal_rat
     Sa = split_heads(aq, H) @ split_heads(ak, H).transpose(-1, -2)
     M = rnd.mask((l, 'D3'), torch.softmax(Sa / sq + mask, -1))
     n = rnd.noise(l, M)
-    A = torch.softmax(origin * M + n * (1 - M) + mask, -1)
-    C = torch.softmax(origin * torch.exp(1 - M) + mask, -1)
+    # transformer_layers.py:919-927 (ACSSEPT / ACTiSASRec) is the same layer WITHOUT the three re-normalising softmaxes of
+    # layers.py:917-925: the attacked "probabilities" are origin*M + noise*(1-M) as they come (pure noise on masked keys)
+    plain = cfg.get('attn_variant', 'layers') == 'transformer_layers'
+    renorm = (lambda z: z) if plain else (lambda z: torch.softmax(z + mask, -1))
+    A = renorm(origin * M + n * (1 - M))
+    C = renorm(origin * torch.exp(1 - M))
     opt = cfg['combine_option']
     if opt == 'gate':
         g = torch.sigmoid(gate_logit).unsqueeze(1)
@@ -190,7 +196,7 @@ def attn_calib(mq, mk, mv, aq, ak, gate_logit, mask, lp, cfg, l, rnd, anneal_rat
         comb = anneal_rate * origin + (1 - anneal_rate) * C
     else:
         raise KeyError(opt)
-    R = torch.softmax(comb + mask, -1)
+    R = renorm(comb)
     if not cfg['two_level']:
         rc = cfg['rich_calibrated_combine']
         if rc == 'fixed':
@@ -351,6 +357,92 @@ def bert_train_grads(params, cfg, masked_seq, pos_items, masked_index, rnd=None,
 
 
 ATTACK_KEYS = ('attack_key_transform', 'attack_query_transform')   # trainer.py:673
+
+
+# ---- ACSSEPT (acssept.py:21-228): user embedding concatenated to every position, transformer_layers.py encoder ---- #
+def ssept_cfg(cfg):
+    """the encoder ACSSEPT builds: hidden = item_hidden_size + user_hidden_size, transformer_layers.py:873-953 layers"""
+    c = dict(cfg)
+    c['hidden_size'] = cfg['item_hidden_size'] + cfg['user_hidden_size']
+    c['attn_variant'] = 'transformer_layers'
+    return c
+
+
+def ssept_forward(params, cfg, item_seq, item_len, user_id, rnd=None, anneal_rates=None):
+    """acssept.py:124-145 -> attacked[B,d], calibrated[B,d], [M_l]"""
+    rnd = rnd or Rand()
+    c = ssept_cfg(cfg)
+    B, L = item_seq.shape
+    item_emb = torch.nn.functional.embedding(item_seq, params['item_embedding.weight'], padding_idx=0)
+    user_emb = torch.nn.functional.embedding(user_id, params['user_embedding.weight'], padding_idx=0)
+    x = torch.cat((item_emb, user_emb.unsqueeze(1).expand(B, L, user_emb.shape[-1])), -1)
+    if cfg.get('use_position_embedding'):
+        x = x + params['position_embedding.weight'][:L].unsqueeze(0)
+    x = rnd.mask('emb', layer_norm(x, params['LayerNorm.weight'], params['LayerNorm.bias'], cfg['layer_norm_eps']))
+    mask = additive_mask(item_seq).to(x.dtype)
+    Ms, att = [], None
+    for l in range(cfg['n_layers']):
+        ar = None if anneal_rates is None else anneal_rates[l]
+        att, x, M = ac_layer(x, mask, params, c, l, rnd, ar)
+        Ms.append(M)
+    rows = torch.arange(B, device=item_seq.device)
+    return att[rows, item_len - 1], x[rows, item_len - 1], Ms
+
+
+def ssept_logits(out, E, user_vec):
+    """acssept.py:164-171 / 212-224: every candidate row is cat(E[v], user_vec[b]) -> out_item.E^T + (out_user.user_vec)"""
+    di = E.shape[1]
+    return out[:, :di] @ E.t() + (out[:, di:] * user_vec).sum(-1, keepdim=True)
+
+
+def ssept_calculate_loss(params, cfg, item_seq, item_len, user_id, pos_items, rnd=None, anneal_rates=None, neg_items=None):
+    """acssept.py:174-190 -> (final_attacked_loss, calibrated_loss); the loss uses user_embedding (acssept.py:150,166)"""
+    att, cal, Ms = ssept_forward(params, cfg, item_seq, item_len, user_id, rnd, anneal_rates)
+    E = params['item_embedding.weight']
+    u = torch.nn.functional.embedding(user_id, params['user_embedding.weight'], padding_idx=0)
+    rows = torch.arange(att.shape[0])
+
+    def loss_of(out):
+        if cfg.get('loss_type', 'CE') == 'BPR':
+            pe, ne = torch.cat((E[pos_items], u), -1), torch.cat((E[neg_items], u), -1)
+            return -torch.log(1e-10 + torch.sigmoid((out * pe).sum(-1) - (out * ne).sum(-1))).mean()
+        logits = ssept_logits(out, E, u)
+        return (torch.logsumexp(logits, -1) - logits[rows, pos_items]).mean()
+    pen = torch.stack([torch.sqrt(torch.sum((1 - M) ** 2)) for M in Ms]).mean()
+    w = params['mask_loss_weight'][0] if cfg.get('trainable_mask_loss_weight') else cfg['mask_loss_weight']
+    return -loss_of(att) + pen * w, loss_of(cal)
+
+
+def ssept_full_sort_scores(params, cfg, item_seq, item_len, user_id, rnd=None):
+    """acssept.py:209-228 -> (attacked_scores, scores) [B, n_items]; scoring uses user_TEST_embedding (acssept.py:213)"""
+    att, cal, _ = ssept_forward(params, cfg, item_seq, item_len, user_id, rnd)
+    ut = torch.nn.functional.embedding(user_id, params['user_test_embedding.weight'], padding_idx=0)
+    E = params['item_embedding.weight']
+    return ssept_logits(att, E, ut), ssept_logits(cal, E, ut)
+
+
+def ssept_predict(params, cfg, item_seq, item_len, user_id, test_item, rnd=None):
+    """acssept.py:192-207"""
+    att, cal, _ = ssept_forward(params, cfg, item_seq, item_len, user_id, rnd)
+    ut = torch.nn.functional.embedding(user_id, params['user_test_embedding.weight'], padding_idx=0)
+    e = torch.cat((params['item_embedding.weight'][test_item], ut), -1)
+    return (att * e).sum(1), (cal * e).sum(1)
+
+
+def ssept_train_grads(params, cfg, item_seq, item_len, user_id, pos_items, rnd=None, anneal_rates=None, neg_items=None):
+    """the two routed backward passes of trainer.py:672-686 (AttackSASRecTrainer) for ACSSEPT -> (l_att, l_cal, {name: grad})"""
+    p = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in params.items())
+    l_att, l_cal = ssept_calculate_loss(p, cfg, item_seq, item_len, user_id, pos_items, rnd, anneal_rates, neg_items)
+    names = list(p)
+    g_cal = torch.autograd.grad(l_cal, [p[n] for n in names], retain_graph=True, allow_unused=True)
+    g_att = torch.autograd.grad(l_att, [p[n] for n in names], allow_unused=True)
+    grads = {}
+    for n, gc, ga in zip(names, g_cal, g_att):
+        g = ga if any(s in n for s in ATTACK_KEYS) else gc
+        if n == 'mask_loss_weight':
+            g = None
+        grads[n] = torch.zeros_like(p[n]) if g is None else g.detach()
+    return l_att.detach(), l_cal.detach(), grads
 
 
 def train_grads(params, cfg, item_seq, item_len, pos_items, rnd=None, anneal_rates=None, neg_items=None):

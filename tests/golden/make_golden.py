@@ -274,6 +274,114 @@ def make_bert_case(name, V, B, seed, train, k=50, **cfgkw):
     print(name, os.path.getsize(path) // 1024, 'KB')
 
 
+def make_ssept_case(name, V, U, B, seed, train, k=50, **cfgkw):
+    """ACSSEPT (acssept.py on transformer_layers.py:742-953): user embedding concatenated to every position, the encoder
+    variant without the re-normalising softmaxes.  The reference registers no ACSSEPTTrainer; the recorded gradients are those
+    of the AC training step the model's tuple API is written for (AttackSASRecTrainer, trainer.py:672-686)."""
+    from oracle.acsr_oracle import synth_batch
+    import_reference()
+    from recbole.model.sequential_recommender.acssept import ACSSEPT
+    from recbole.data.interaction import Interaction
+    cfg = base_config(**cfgkw)
+    cfg.setdefault('user_hidden_size', 32)
+    cfg.setdefault('item_hidden_size', 32)
+    L = cfg['MAX_ITEM_LIST_LENGTH']
+
+    class DS:
+        def num(self, field):
+            return U if field == 'user_id' else V
+    torch.manual_seed(seed)
+    model = ACSSEPT(cfg, DS())
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('.bias'):
+                p.add_(torch.randn(p.shape, generator=g) * 0.02)
+            if 'LayerNorm.weight' in n:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    seq, ln, pos = synth_batch(B, L, V, seed=seed + 2)
+    ln[0] = L
+    seq[0] = torch.randint(1, V, (L,), generator=g)
+    ln[1] = 1
+    seq[1, 1:] = 0
+    user = torch.randint(1, U, (B,), generator=g)
+    fields = {'item_id_list': seq, 'item_length': ln, 'item_id': pos, 'user_id': user}
+    if cfg['loss_type'] == 'BPR':
+        neg = torch.randint(1, V - 1, (B,), generator=g)
+        neg = neg + (neg >= pos).long()
+        fields['neg_item_id'] = neg
+    inter = Interaction(fields)
+    out = {'V': V, 'U': U, 'B': B, 'k': min(k, V - 1), 'train': int(train), 'seed': seed, 'ssept': 1,
+           'item_id_list': seq.numpy(), 'item_length': ln.numpy(), 'item_id': pos.numpy(), 'user_id': user.numpy()}
+    if 'neg_item_id' in fields:
+        out['neg_item_id'] = fields['neg_item_id'].numpy()
+    for kk, vv in cfgkw.items():
+        out['cfg.' + kk] = np.array(vv)
+    out['cfg.user_hidden_size'] = np.array(cfg['user_hidden_size'])
+    out['cfg.item_hidden_size'] = np.array(cfg['item_hidden_size'])
+    for n, p in model.state_dict().items():
+        out['param.' + n] = p.detach().numpy().copy()
+    model.train(train)
+    N = cfg['n_layers']
+    if train:
+        with Recorder(seed + 3) as rec:
+            l_att, l_cal = model.calculate_loss(inter)
+        assert len(rec.masks) == 1 + 7 * N, len(rec.masks)
+        out['rand.emb'] = rec.masks[0].numpy().astype(np.uint8)
+        for l in range(N):
+            for j, key in enumerate(('D1', 'D2', 'D3', 'D4', 'D5', 'D6', 'D7')):
+                out['rand.%d.%s' % (l, key)] = rec.masks[1 + 7 * l + j].numpy().astype(np.uint8)
+        for l in range(N):
+            out['rand.%d.noise' % l] = rec.noises[l].numpy()
+        out['loss_att'] = l_att.detach().numpy()
+        out['loss_cal'] = l_cal.detach().numpy()
+
+        def is_attack(n):
+            return 'attack_key_transform' in n or 'attack_query_transform' in n
+        for n, p in model.named_parameters():
+            p.requires_grad = not is_attack(n)
+        l_cal.backward(retain_graph=True)
+        for n, p in model.named_parameters():
+            p.requires_grad = is_attack(n)
+        l_att.backward()
+        for n, p in model.named_parameters():
+            gr = p.grad if p.grad is not None else torch.zeros_like(p)
+            out['grad.' + n] = gr.detach().numpy().copy()
+    else:
+        with Recorder(seed + 3) as rec:
+            a_scores, scores = model.full_sort_predict(inter)
+        for l in range(N):
+            out['rand.%d.noise' % l] = rec.noises[l].numpy()
+        with Recorder(seed + 3):
+            att, cal, Ms = model.forward(seq, ln, user)
+        out['out_att'] = att.detach().numpy()
+        out['out_cal'] = cal.detach().numpy()
+        for l, M in enumerate(Ms):
+            out['pen_sq.%d' % l] = torch.sum((1 - M) ** 2).detach().numpy()
+        scores = scores.detach().clone()
+        out['scores'] = scores.numpy().copy()
+        out['scores_att'] = a_scores.detach().numpy().copy()
+        scores[:, 0] = -np.inf
+        _, idx = torch.topk(scores, out['k'], dim=-1)
+        out['topk_idx'] = idx.numpy()
+        with Recorder(seed + 3):
+            a_s, c_s = model.predict(inter)
+        out['predict_att'] = a_s.detach().numpy()
+        out['predict_cal'] = c_s.detach().numpy()
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **out)
+    print(name, os.path.getsize(path) // 1024, 'KB')
+
+
+SSEPT_CASES = [
+    # ACSSEPT (SURVEY section 8 f-4).  hidden = item_hidden_size + user_hidden_size
+    ('ssept_gate_train', 151, 23, 3, 41, True, dict(n_layers=2)),
+    ('ssept_fixed_onelevel_train', 131, 17, 3, 42, True, dict(n_layers=1, n_heads=4, combine_option='fixed', two_level=False,
+                                                             rich_calibrated_combine='fixed', use_position_embedding=True)),
+    ('ssept_bpr_train', 131, 17, 3, 44, True, dict(n_layers=1, loss_type='BPR', item_hidden_size=64, user_hidden_size=64)),
+    ('ssept_gate_eval', 151, 23, 3, 43, False, dict(n_layers=2)),
+]
+
 BERT_CASES = [
     # AcBERT4Rec (SURVEY section 8 f-4).  `gate` trains in the reference but cannot be evaluated there (the gate is Linear(d, 50)
     # and evaluation runs on L+1 = 51 positions, layers.py:878/887), so the eval case uses `fixed`.
@@ -319,3 +427,7 @@ if __name__ == '__main__':
         if only and name not in only:
             continue
         make_bert_case(name, V, B, seed, train, **kw)
+    for name, V, U, B, seed, train, kw in SSEPT_CASES:
+        if only and name not in only:
+            continue
+        make_ssept_case(name, V, U, B, seed, train, **kw)

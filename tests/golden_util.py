@@ -49,7 +49,9 @@ def load_case(name, dtype=torch.float32):
     for key in ('masked_seq', 'pos_items', 'neg_items', 'masked_index'):        # AcBERT4Rec: the recorded host-side masking
         if key in z.files:
             batch[key] = torch.from_numpy(z[key])
+    if 'user_id' in z.files:                      # ACSSEPT: the user of every row
+        batch['user'] = torch.from_numpy(z['user_id'])
     if 'neg_item_id' in z.files:                  # loss_type BPR: the sampled negative of every row
         batch['neg'] = torch.from_numpy(z['neg_item_id'])
-    return dict(z=z, cfg=cfg, bert=('bert' in z.files), params=params, grads=grads, rand=O.Rand(r), batch=batch,
+    return dict(z=z, cfg=cfg, bert=('bert' in z.files), ssept=('ssept' in z.files), params=params, grads=grads, rand=O.Rand(r), batch=batch,
                 train=bool(z['train']), V=int(z['V']), k=int(z['k']))

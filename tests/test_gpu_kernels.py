@@ -326,10 +326,10 @@ def _attn_inputs(H, dh, L, combine, two_level, rich, use_order, use_distance, p,
     return cfg, seq, t, lp, rnd, g
 
 
-def _run_cuda_attn(A, cfg, seq, t, lp, rnd, p, need_att=True, want_probs=True, grad=False, bidirectional=False):
+def _run_cuda_attn(A, cfg, seq, t, lp, rnd, p, need_att=True, want_probs=True, grad=False, bidirectional=False, plain=False):
     H = cfg['n_heads']
     opts = A.ops.AttnOpts(H, cfg['two_level'], cfg['combine_option'],
-                          cfg['rich_calibrated_combine'] if not cfg['two_level'] else 'none', p, bidirectional=bidirectional)
+                          cfg['rich_calibrated_combine'] if not cfg['two_level'] else 'none', p, bidirectional=bidirectional, plain=plain)
     def c(x):
         if x is None:
             return None
@@ -1000,6 +1000,54 @@ def test_attn_calib_bidirectional_forward_backward(A, case):
         got = lpc[k].grad if lpc[k].grad is not None else torch.zeros_like(lpc[k])
         scale = float(ref.abs().max())
         assert float((got.cpu() - ref).abs().max()) <= 5e-4 * scale + 1e-6, (k, got, ref)
+
+
+# the layer of transformer_layers.py:873-953 (ACSSEPT): attacked / calibrated / combined attention WITHOUT the re-normalising softmaxes
+PLAIN_CASES = [ATTN_CASES[i] for i in (0, 1, 4, 5, 7, 9, 10, 13)] + [(2, 32, 50, 'gate', True, 'none', True, True, 0.5),
+                                                                     (4, 32, 50, 'fixed', False, 'trainable', True, True, 0.5)]
+PLAIN_CASES = [c for c in PLAIN_CASES if c[2] <= 64]
+
+
+@pytest.mark.parametrize('case', PLAIN_CASES)
+def test_attn_calib_transformer_layers_variant(A, case):
+    """ACSR_ATTN_PLAIN: A = origin*M + noise*(1-M), C = origin*exp(1-M) and the combination are used as computed
+    (transformer_layers.py:919-927).  Masked keys keep the bare noise as attacked weight, so every key of a row is in play;
+    forward probabilities / contexts / penalty and every gradient against the oracle restatement of that variant."""
+    H, dh, L, combine, two_level, rich, uo, ud, p = case
+    cfg, seq, t, lp, rnd, g = _attn_inputs(*case)
+    cfg['attn_variant'] = 'transformer_layers'
+    B, d = t['mq'].shape[0], H * dh
+    mask = O.additive_mask(seq)
+    g_att, g_cal = torch.randn(B, L, d, generator=g), torch.randn(B, L, d, generator=g)
+    g_pen = torch.tensor([0.01])
+    to = {k: (v.clone().requires_grad_(True) if v is not None else None) for k, v in t.items()}
+    lpo = {k: v.clone().requires_grad_(True) for k, v in lp.items()}
+    r = O.attn_calib(to['mq'], to['mk'], to['mv'], to['aq'], to['ak'], to['gate'], mask, lpo, cfg, 0, O.Rand(rnd), anneal_rate=0.37)
+    ((r['ctx_cal'] * g_cal).sum() + (r['ctx_att'] * g_att).sum() + (r['pen_sq'] * g_pen).sum()).backward()
+    (ctx_att, ctx_cal, pen, probs), _, _ = _run_cuda_attn(A, cfg, seq, t, lp, rnd, p, plain=True)
+    for i, n in enumerate(['P0', 'P', 'M', 'A', 'C', 'R']):
+        close(probs[i], r[n].detach(), 3e-5, n)
+    close(ctx_att, r['ctx_att'].detach(), 3e-5, 'ctx_att')
+    close(ctx_cal, r['ctx_cal'].detach(), 3e-5, 'ctx_cal')
+    close(pen, r['pen_sq'].detach().view(1), 1e-5, 'pen_sq')
+    # the attacked weights of future keys are the noise itself
+    upper = torch.triu(torch.ones(L, L, dtype=torch.bool), 1)
+    assert torch.equal(probs[3].cpu()[0][:, upper], rnd[(0, 'noise')][0][:, upper])
+    (ctx_att, ctx_cal, pen, _), tc, lpc = _run_cuda_attn(A, cfg, seq, t, lp, rnd, p, want_probs=False, grad=True, plain=True)
+    ((ctx_cal * g_cal.cuda()).sum() + (ctx_att * g_att.cuda()).sum() + (pen * g_pen.cuda()).sum()).backward()
+    for k in ('mq', 'mk', 'mv', 'aq', 'ak', 'gate'):
+        if to[k] is None:
+            continue
+        close(tc[k].grad, to[k].grad, 3e-4, 'd_' + k)
+    for k in lpo:
+        ref = lpo[k].grad if lpo[k].grad is not None else torch.zeros_like(lpo[k])
+        got = lpc[k].grad if lpc[k].grad is not None else torch.zeros_like(lpc[k])
+        scale = float(ref.abs().max())
+        assert float((got.cpu() - ref).abs().max()) <= 5e-4 * scale + 1e-6, (k, got, ref)
+    # calibrated stream alone (evaluation, non-final layers): no attacked context asked for
+    (na, ctx_cal2, pen2, _), _, _ = _run_cuda_attn(A, cfg, seq, t, lp, rnd, p, need_att=False, want_probs=False, plain=True)
+    assert na is None
+    close(ctx_cal2, r['ctx_cal'].detach(), 3e-5, 'ctx_cal (calibrated only)')
 
 
 def test_gather_rows_and_weighted_ce(A):

@@ -14,7 +14,8 @@ from oracle import acsr_oracle as O
 from golden_util import GOLDEN_DIR, load_case
 
 EVERY = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
-ALL = [n for n in EVERY if not n.startswith('bert_')]
+ALL = [n for n in EVERY if not n.startswith(('bert_', 'ssept_'))]
+SSEPT = [n for n in EVERY if n.startswith('ssept_')]        # ACSSEPT cases (acssept.py on transformer_layers.py)
 BERT = [n for n in EVERY if n.startswith('bert_')]          # AcBERT4Rec cases (acbert4rec.py)
 TRAIN = [n for n in ALL if '_train' in n]
 EVAL = [n for n in ALL if '_eval' in n]
@@ -650,3 +651,106 @@ def test_bert_trainer_epoch_and_eval(A, tmp_path):
                                 verbose=False, saved=True)
     assert float((model.item_embedding.weight.detach() - before).abs().max()) > 0
     assert all(np.isfinite(v) for v in result.values()) and 'hit@10' in result
+
+
+# ---- ACSSEPT: goldens from the real reference (tests/golden/make_golden.py: make_ssept_case) ----
+class DSU:
+    def __init__(self, n_items, n_users):
+        self.n_items, self.n_users, self.item_num = n_items, n_users, n_items
+
+    def num(self, field):
+        return self.n_users if field == 'user_id' else self.n_items
+
+
+def build_ssept(A, c, **extra):
+    config = make_config(A, dict(c['cfg']), **extra)
+    config['model'] = 'ACSSEPT'
+    model = A.ACSSEPT(config, DSU(c['V'], int(c['z']['U']))).to('cuda')
+    model.load_state_dict({k: v.cuda() for k, v in c['params'].items()}, strict=True)      # reference state_dict loads unchanged
+    model._debug_rand = {k: v.cuda() for k, v in c['rand'].d.items()}
+    return config, model
+
+
+def ssept_inter(A, c):
+    inter = inter_of(A, c)
+    inter.interaction['user_id'] = c['batch']['user'].cuda()
+    return inter
+
+
+@pytest.mark.parametrize('name', [n for n in SSEPT if '_train' in n])
+def test_ssept_golden_train_losses_and_routed_grads(A, name):
+    c = load_case(name)
+    z = c['z']
+    config, model = build_ssept(A, c)
+    assert model.hidden_size == c['cfg']['item_hidden_size'] + c['cfg']['user_hidden_size']
+    model.train()
+    l_att, l_cal = model.calculate_loss(ssept_inter(A, c))
+    assert abs(float(l_att) - float(z['loss_att'])) < 1e-4 * abs(float(z['loss_att']))
+    assert abs(float(l_cal) - float(z['loss_cal'])) < 1e-4 * abs(float(z['loss_cal']))
+    for n, p in model.named_parameters():
+        p.requires_grad = not ('attack_key_transform' in n or 'attack_query_transform' in n)
+    l_cal.backward(retain_graph=True)
+    for n, p in model.named_parameters():
+        p.requires_grad = ('attack_key_transform' in n or 'attack_query_transform' in n)
+    l_att.backward()
+    assert set(n for n, _ in model.named_parameters()) == set(c['grads'])
+    for n, p in model.named_parameters():
+        ref = c['grads'][n]
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(ref)
+        scale = float(ref.abs().max())
+        err = float((got - ref).abs().max())
+        # the reference's own gradient of user_embedding through the loss is rounding noise around an exact zero (a per-row
+        # constant added to every logit): compare against the scale of the whole tensor
+        assert err <= 1e-3 * scale + 1e-7, (n, err, scale)
+
+
+@pytest.mark.parametrize('name', [n for n in SSEPT if '_eval' in n])
+def test_ssept_golden_eval(A, name):
+    c = load_case(name)
+    z = c['z']
+    config, model = build_ssept(A, c)
+    model.eval()
+    inter = ssept_inter(A, c)
+    with torch.no_grad():
+        att, cal, masks = model.forward(inter['item_id_list'], inter['item_length'], inter['user_id'])
+        assert rel(att, z['out_att']) < 1e-4 and rel(cal, z['out_cal']) < 1e-4
+        for l, m in enumerate(masks):
+            assert rel(m.pen_sq, z['pen_sq.%d' % l]) < 1e-5
+        sa, sc = model.full_sort_predict(inter)
+        assert rel(sc, z['scores']) < 1e-4 and rel(sa, z['scores_att']) < 1e-4
+        val, idx, rec = model.full_sort_topk(inter, c['k'], inter['item_id'])
+        ok, nbad = O.topk_equal_modulo_ties(idx.cpu(), torch.from_numpy(z['topk_idx']), torch.from_numpy(z['scores']))
+        assert ok, nbad
+        want = torch.gather(torch.from_numpy(z['scores']), 1, idx.cpu())
+        assert rel(val, want) < 1e-4
+        pa, pc = model.predict(inter)
+        assert rel(pa, z['predict_att']) < 1e-4 and rel(pc, z['predict_cal']) < 1e-4
+
+
+def test_ssept_trainer_epoch_and_eval(A, tmp_path):
+    """ACSSEPTTrainer: the adversarial two-loss step (routed double backward) + graphed full-sort evaluation, end to end"""
+    cfg = O.default_cfg(n_layers=1)
+    cfg.update(user_hidden_size=32, item_hidden_size=32)
+    V = 200
+    config = make_config(A, cfg, checkpoint_dir=str(tmp_path), epochs=1, train_batch_size=32, eval_batch_size=32, cuda_graph=True)
+    config['model'] = 'ACSSEPT'
+    torch.manual_seed(0)
+    train_ds = A.data.SyntheticSequentialDataset(config, 32 * 3, V, seed=1)
+    valid_ds = A.data.SyntheticSequentialDataset(config, 64, V, seed=2)
+    model = A.ACSSEPT(config, train_ds).to('cuda')
+    trainer = A.ACSSEPTTrainer(config, model)
+    assert trainer.fused is None                      # the autograd path over the same kernels
+    before_i = model.item_embedding.weight.detach().clone()
+    before_u = model.user_embedding.weight.detach().clone()
+    loader = A.data.TrainDataLoader(config, train_ds, shuffle=True)
+    score, result = trainer.fit(loader, A.data.FullSortEvalDataLoader(config, valid_ds), verbose=False, saved=True)
+    assert float((model.item_embedding.weight.detach() - before_i).abs().max()) > 0
+    assert float((model.user_embedding.weight.detach() - before_u).abs().max()) > 0       # trained through the input concat
+    assert all(np.isfinite(v) for v in result.values()) and 'hit@10' in result
+    # the graphed evaluation and the eager one agree
+    model.eval()
+    batch = next(iter(A.data.FullSortEvalDataLoader(config, valid_ds)))
+    rec_g = trainer.eval_batch(batch).cpu()
+    trainer.use_graph = False
+    rec_e = trainer.eval_batch(batch).cpu()
+    assert torch.equal(rec_g, rec_e)

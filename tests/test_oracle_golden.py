@@ -10,7 +10,8 @@ from oracle import acsr_oracle as O
 from golden_util import GOLDEN_DIR, load_case
 
 EVERY = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
-ALL = [n for n in EVERY if not n.startswith('bert_')]
+ALL = [n for n in EVERY if not n.startswith(('bert_', 'ssept_'))]
+SSEPT = [n for n in EVERY if n.startswith('ssept_')]        # ACSSEPT cases (acssept.py on transformer_layers.py)
 BERT = [n for n in EVERY if n.startswith('bert_')]          # AcBERT4Rec cases (acbert4rec.py)
 TRAIN = [n for n in ALL if '_train' in n]
 EVAL = [n for n in ALL if '_eval' in n]
@@ -101,3 +102,36 @@ def test_bert_eval_scores(name):
     _, idx = O.full_sort_topk(sc, c['k'])
     ok, nbad = O.topk_equal_modulo_ties(idx, torch.from_numpy(z['topk_idx']), torch.from_numpy(z['scores']))
     assert ok, nbad
+
+
+@pytest.mark.parametrize('name', [n for n in SSEPT if '_train' in n])
+def test_ssept_train_losses_and_routed_grads(name):
+    """ACSSEPT (acssept.py:174-190) on the transformer_layers.py encoder (no re-normalising softmaxes): losses + routed .grad"""
+    c = load_case(name)
+    b, z = c['batch'], c['z']
+    l_att, l_cal, grads = O.ssept_train_grads(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['user'], b['pos'], c['rand'],
+                                              neg_items=b.get('neg'))
+    assert abs(float(l_att) - float(z['loss_att'])) < 1e-5 * abs(float(z['loss_att']))
+    assert abs(float(l_cal) - float(z['loss_cal'])) < 1e-5 * abs(float(z['loss_cal']))
+    assert set(grads) == set(c['grads'])
+    for n, g in c['grads'].items():
+        scale = float(g.abs().max())
+        err = float((grads[n] - g).abs().max())
+        assert err <= 2e-4 * scale + 2e-9, (n, err, scale)
+
+
+@pytest.mark.parametrize('name', [n for n in SSEPT if '_eval' in n])
+def test_ssept_eval_scores(name):
+    c = load_case(name)
+    b, z = c['batch'], c['z']
+    att, cal, Ms = O.ssept_forward(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['user'], c['rand'])
+    assert rel(att, z['out_att']) < 2e-5 and rel(cal, z['out_cal']) < 2e-5
+    for l, M in enumerate(Ms):
+        assert rel(torch.sum((1 - M) ** 2), z['pen_sq.%d' % l]) < 1e-5
+    sa, sc = O.ssept_full_sort_scores(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['user'], c['rand'])
+    assert rel(sc, z['scores']) < 2e-5 and rel(sa, z['scores_att']) < 2e-5
+    _, idx = O.full_sort_topk(sc, c['k'])
+    ok, nbad = O.topk_equal_modulo_ties(idx, torch.from_numpy(z['topk_idx']), torch.from_numpy(z['scores']))
+    assert ok, nbad
+    pa, pc = O.ssept_predict(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['user'], b['pos'], c['rand'])
+    assert rel(pa, z['predict_att']) < 2e-5 and rel(pc, z['predict_cal']) < 2e-5
