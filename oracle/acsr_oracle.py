@@ -26,6 +26,7 @@ Reference lines each function follows (relative to /root/reference/recbole):
   calculate_loss     model/sequential_recommender/acsasrec.py:107-144 (CE and BPR branches; model/loss.py:21-47)
   predict/full_sort  model/sequential_recommender/acsasrec.py:146-164
   bert_*             model/sequential_recommender/acbert4rec.py:152-160, 162-179, 198-245, 260-267 (AcBERT4Rec)
+  ti_*               model/sequential_recommender/actisasrec.py:104-224 (ACTiSASRec) on model/transformer_layers.py:1010-1327
   ssept_*            model/sequential_recommender/acssept.py:124-228 (ACSSEPT) on model/transformer_layers.py:742-953,
                      the encoder variant without the re-normalising softmaxes (cfg['attn_variant'] == 'transformer_layers')
   train_grads        trainer/trainer.py:660-687 (two backward passes routed by name)
@@ -146,7 +147,7 @@ def merge_heads(x):
     return x.permute(0, 2, 1, 3).reshape(B, L, H * dh)
 
 
-def attn_calib(mq, mk, mv, aq, ak, gate_logit, mask, lp, cfg, l, rnd, anneal_rate=None):
+def attn_calib(mq, mk, mv, aq, ak, gate_logit, mask, lp, cfg, l, rnd, anneal_rate=None, s_bias=None, ctx_extra=None):
     """Core of one AC layer on already-projected tensors.
 
     mq,mk,mv : x.Wq+bq etc. [B,L,d];  aq,ak : attack transforms of mq,mk [B,L,d]
@@ -159,6 +160,8 @@ def attn_calib(mq, mk, mv, aq, ak, gate_logit, mask, lp, cfg, l, rnd, anneal_rat
     sq = math.sqrt(dh)
     q, k, v = split_heads(mq, H), split_heads(mk, H), split_heads(mv, H)
     S = q @ k.transpose(-1, -2)
+    if s_bias is not None:          # ACTiSASRec: q.posK + q.timeK[t_ij] join the raw scores (transformer_layers.py:1128-1134)
+        S = S + s_bias
     dt = S.dtype
     e_o = torch.zeros_like(S)
     e_d = torch.zeros_like(S)
@@ -206,8 +209,10 @@ def attn_calib(mq, mk, mv, aq, ak, gate_logit, mask, lp, cfg, l, rnd, anneal_rat
             R = ratio * R + (1 - ratio) * P
         else:
             raise KeyError(rc)
-    return dict(P0=P0, P=P, M=M, A=A, C=C, R=R,
-                ctx_att=merge_heads(A @ v), ctx_cal=merge_heads(R @ v),
+    ca, cc = A @ v, R @ v
+    if ctx_extra is not None:       # ACTiSASRec: probs.posV + probs.timeV[t_ij] join the context (transformer_layers.py:1088-1091)
+        ca, cc = ca + ctx_extra(A), cc + ctx_extra(R)
+    return dict(P0=P0, P=P, M=M, A=A, C=C, R=R, ctx_att=merge_heads(ca), ctx_cal=merge_heads(cc),
                 pen_sq=torch.sum((1 - M) ** 2))
 
 
@@ -227,8 +232,8 @@ def feed_forward(h, fp, cfg, rnd, key):
     return layer_norm(rnd.mask(key, z) + h, fp['LayerNorm.weight'], fp['LayerNorm.bias'], cfg['layer_norm_eps'])
 
 
-def ac_layer(x, mask, params, cfg, l, rnd, anneal_rate=None, want_probs=False):
-    lp_all = sub(params, 'trm_encoder.layer.%d.' % l)
+def ac_layer(x, mask, params, cfg, l, rnd, anneal_rate=None, want_probs=False, time_terms=None, prefix='trm_encoder'):
+    lp_all = sub(params, '%s.layer.%d.' % (prefix, l))
     ap = sub(lp_all, 'attack_attention.')
     mq = linear(x, ap['query.weight'], ap['query.bias'])
     mk = linear(x, ap['key.weight'], ap['key.bias'])
@@ -241,7 +246,10 @@ def ac_layer(x, mask, params, cfg, l, rnd, anneal_rate=None, want_probs=False):
     ap2 = dict(ap)
     if 'rich_calibrated_combine_ratio' in lp_all:
         ap2['rich_calibrated_combine_ratio'] = lp_all['rich_calibrated_combine_ratio']
-    r = attn_calib(mq, mk, mv, aq, ak, gl, mask, ap2, cfg, l, rnd, anneal_rate)
+    s_bias = ctx_extra = None
+    if time_terms is not None:
+        s_bias, ctx_extra = time_terms(mq)
+    r = attn_calib(mq, mk, mv, aq, ak, gl, mask, ap2, cfg, l, rnd, anneal_rate, s_bias, ctx_extra)
     eps = cfg['layer_norm_eps']
     h_att = adjusted_output(r['ctx_att'], x, ap, eps, rnd, (l, 'D4'))
     h_cal = adjusted_output(r['ctx_cal'], x, ap, eps, rnd, (l, 'D5'))
@@ -357,6 +365,93 @@ def bert_train_grads(params, cfg, masked_seq, pos_items, masked_index, rnd=None,
 
 
 ATTACK_KEYS = ('attack_key_transform', 'attack_query_transform')   # trainer.py:673
+
+
+# ---- ACTiSASRec (actisasrec.py:20-224): time-interval aware keys / values on the transformer_layers.py layer ---------- #
+def ti_time_matrix(time_seq, time_span):
+    """actisasrec.py:146-155: |t_i - t_j| clipped to time_span, as integers"""
+    tm = (time_seq.unsqueeze(-1) - time_seq.unsqueeze(1)).abs()
+    return torch.where(tm > time_span, torch.full_like(tm, time_span), tm).int()
+
+
+def ti_forward(params, cfg, item_seq, item_len, time_seq, rnd=None, anneal_rates=None):
+    """actisasrec.py:104-144 + transformer_layers.py:1010-1327 -> attacked[B,d], calibrated[B,d], [M_l].
+    Dropout keys beyond the per-layer ones: 'emb', 'posK', 'posV' ([B,L,d]) and 'timeK', 'timeV' ([B,L,L,d]), drawn once per
+    forward and shared by all layers (actisasrec.py:120-124)."""
+    rnd = rnd or Rand()
+    c = dict(cfg)
+    c['attn_variant'] = 'transformer_layers'
+    B, L = item_seq.shape
+    H = cfg['n_heads']
+    tmat = ti_time_matrix(time_seq, cfg['time_span']).long()
+    emb = lambda name, idx: torch.nn.functional.embedding(idx, params[name + '.weight'], padding_idx=0)
+    pos_ids = torch.arange(L).unsqueeze(0).expand(B, L)
+    x = rnd.mask('emb', layer_norm(emb('item_embedding', item_seq), params['LayerNorm.weight'], params['LayerNorm.bias'],
+                                   cfg['layer_norm_eps']))
+    pK = rnd.mask('posK', emb('absolute_pos_K_embedding', pos_ids))            # [B,L,d]
+    pV = rnd.mask('posV', emb('absolute_pos_V_embedding', pos_ids))
+    tK = rnd.mask('timeK', emb('time_matrix_emb_K_embedding', tmat))           # [B,L,L,d]
+    tV = rnd.mask('timeV', emb('time_matrix_emb_V_embedding', tmat))
+    d = x.shape[-1]
+    dh = d // H
+    tKh = tK.view(B, L, L, H, dh).permute(0, 3, 1, 2, 4)                       # [B,H,L,L,dh]
+    tVh = tV.view(B, L, L, H, dh).permute(0, 3, 1, 2, 4)
+
+    def time_terms(mq):
+        q = split_heads(mq, H)
+        s_bias = q @ split_heads(pK, H).transpose(-1, -2) + (tKh @ q.unsqueeze(-1)).squeeze(-1)
+
+        def ctx_extra(prob):
+            return prob @ split_heads(pV, H) + (prob.unsqueeze(-2) @ tVh).squeeze(-2)
+        return s_bias, ctx_extra
+    mask = additive_mask(item_seq).to(x.dtype)
+    Ms, att = [], None
+    for l in range(cfg['n_layers']):
+        ar = None if anneal_rates is None else anneal_rates[l]
+        att, x, M = ac_layer(x, mask, params, c, l, rnd, ar, time_terms=time_terms, prefix='ti_trm_encoder')
+        Ms.append(M)
+    rows = torch.arange(B)
+    return att[rows, item_len - 1], x[rows, item_len - 1], Ms
+
+
+def ti_calculate_loss(params, cfg, item_seq, item_len, time_seq, pos_items, rnd=None, anneal_rates=None, neg_items=None):
+    """actisasrec.py:173-193 -> (final_attacked_loss, calibrated_loss)"""
+    att, cal, Ms = ti_forward(params, cfg, item_seq, item_len, time_seq, rnd, anneal_rates)
+    E = params['item_embedding.weight']
+    pen = torch.stack([torch.sqrt(torch.sum((1 - M) ** 2)) for M in Ms]).mean()
+    w = params['mask_loss_weight'][0] if cfg.get('trainable_mask_loss_weight') else cfg['mask_loss_weight']
+    if cfg.get('loss_type', 'CE') == 'BPR':
+        return -bpr_loss(att, E, pos_items, neg_items) + pen * w, bpr_loss(cal, E, pos_items, neg_items)
+    return -cross_entropy(att, E, pos_items) + pen * w, cross_entropy(cal, E, pos_items)
+
+
+def ti_full_sort_scores(params, cfg, item_seq, item_len, time_seq, rnd=None):
+    """actisasrec.py:211-224 -> (attacked_scores, scores) [B, n_items]"""
+    att, cal, _ = ti_forward(params, cfg, item_seq, item_len, time_seq, rnd)
+    E = params['item_embedding.weight']
+    return att @ E.t(), cal @ E.t()
+
+
+def ti_predict(params, cfg, item_seq, item_len, time_seq, test_item, rnd=None):
+    att, cal, _ = ti_forward(params, cfg, item_seq, item_len, time_seq, rnd)
+    e = params['item_embedding.weight'][test_item]
+    return (att * e).sum(1), (cal * e).sum(1)
+
+
+def ti_train_grads(params, cfg, item_seq, item_len, time_seq, pos_items, rnd=None, anneal_rates=None, neg_items=None):
+    """the two routed backward passes of trainer.py:672-686 for ACTiSASRec -> (l_att, l_cal, {name: grad})"""
+    p = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in params.items())
+    l_att, l_cal = ti_calculate_loss(p, cfg, item_seq, item_len, time_seq, pos_items, rnd, anneal_rates, neg_items)
+    names = list(p)
+    g_cal = torch.autograd.grad(l_cal, [p[n] for n in names], retain_graph=True, allow_unused=True)
+    g_att = torch.autograd.grad(l_att, [p[n] for n in names], allow_unused=True)
+    grads = {}
+    for n, gc, ga in zip(names, g_cal, g_att):
+        g = ga if any(s in n for s in ATTACK_KEYS) else gc
+        if n == 'mask_loss_weight':
+            g = None
+        grads[n] = torch.zeros_like(p[n]) if g is None else g.detach()
+    return l_att.detach(), l_cal.detach(), grads
 
 
 # ---- ACSSEPT (acssept.py:21-228): user embedding concatenated to every position, transformer_layers.py encoder ---- #

@@ -373,6 +373,111 @@ def make_ssept_case(name, V, U, B, seed, train, k=50, **cfgkw):
     print(name, os.path.getsize(path) // 1024, 'KB')
 
 
+def make_ti_case(name, V, B, seed, train, k=50, **cfgkw):
+    """ACTiSASRec (actisasrec.py on transformer_layers.py:1010-1327): time-interval aware keys / values.  As for ACSSEPT the
+    reference registers no trainer of that name; the recorded gradients are those of the AC step (trainer.py:672-686)."""
+    from oracle.acsr_oracle import synth_batch
+    import_reference()
+    from recbole.model.sequential_recommender.actisasrec import ACTiSASRec
+    from recbole.data.interaction import Interaction
+    cfg = base_config(**cfgkw)
+    cfg.setdefault('time_span', 16)
+    cfg['TIME_FIELD'] = 'timestamp'
+    L = cfg['MAX_ITEM_LIST_LENGTH']
+    torch.manual_seed(seed)
+    model = ACTiSASRec(cfg, FakeDataset(V))
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('.bias'):
+                p.add_(torch.randn(p.shape, generator=g) * 0.02)
+            if 'LayerNorm.weight' in n:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    seq, ln, pos = synth_batch(B, L, V, seed=seed + 2)
+    ln[0] = L
+    seq[0] = torch.randint(1, V, (L,), generator=g)
+    ln[1] = 1
+    seq[1, 1:] = 0
+    # increasing integer-valued timestamps (float field, like the atomic files), 0 on the padding (sequential_dataset.py:128-132)
+    gaps = torch.randint(0, 7, (B, L), generator=g)
+    ts = (torch.cumsum(gaps, 1) + 1000).float()
+    ts[seq == 0] = 0.0
+    fields = {'item_id_list': seq, 'item_length': ln, 'item_id': pos, 'timestamp_list': ts}
+    if cfg['loss_type'] == 'BPR':
+        neg = torch.randint(1, V - 1, (B,), generator=g)
+        neg = neg + (neg >= pos).long()
+        fields['neg_item_id'] = neg
+    inter = Interaction(fields)
+    out = {'V': V, 'B': B, 'k': min(k, V - 1), 'train': int(train), 'seed': seed, 'ti': 1,
+           'item_id_list': seq.numpy(), 'item_length': ln.numpy(), 'item_id': pos.numpy(), 'timestamp_list': ts.numpy()}
+    if 'neg_item_id' in fields:
+        out['neg_item_id'] = fields['neg_item_id'].numpy()
+    for kk, vv in cfgkw.items():
+        out['cfg.' + kk] = np.array(vv)
+    out['cfg.time_span'] = np.array(cfg['time_span'])
+    for n, p in model.state_dict().items():
+        out['param.' + n] = p.detach().numpy().copy()
+    model.train(train)
+    N = cfg['n_layers']
+    if train:
+        with Recorder(seed + 3) as rec:
+            l_att, l_cal = model.calculate_loss(inter)
+        assert len(rec.masks) == 5 + 7 * N, len(rec.masks)
+        for j, key in enumerate(('emb', 'posK', 'posV', 'timeK', 'timeV')):      # actisasrec.py:118-124
+            out['rand.' + key] = rec.masks[j].numpy().astype(np.uint8)
+        for l in range(N):
+            for j, key in enumerate(('D1', 'D2', 'D3', 'D4', 'D5', 'D6', 'D7')):
+                out['rand.%d.%s' % (l, key)] = rec.masks[5 + 7 * l + j].numpy().astype(np.uint8)
+        for l in range(N):
+            out['rand.%d.noise' % l] = rec.noises[l].numpy()
+        out['loss_att'] = l_att.detach().numpy()
+        out['loss_cal'] = l_cal.detach().numpy()
+
+        def is_attack(n):
+            return 'attack_key_transform' in n or 'attack_query_transform' in n
+        for n, p in model.named_parameters():
+            p.requires_grad = not is_attack(n)
+        l_cal.backward(retain_graph=True)
+        for n, p in model.named_parameters():
+            p.requires_grad = is_attack(n)
+        l_att.backward()
+        for n, p in model.named_parameters():
+            gr = p.grad if p.grad is not None else torch.zeros_like(p)
+            out['grad.' + n] = gr.detach().numpy().copy()
+    else:
+        with Recorder(seed + 3) as rec:
+            a_scores, scores = model.full_sort_predict(inter)
+        for l in range(N):
+            out['rand.%d.noise' % l] = rec.noises[l].numpy()
+        with Recorder(seed + 3):
+            att, cal, Ms = model.forward(seq, ln, model.get_time_matrix(ts))
+        out['out_att'] = att.detach().numpy()
+        out['out_cal'] = cal.detach().numpy()
+        for l, M in enumerate(Ms):
+            out['pen_sq.%d' % l] = torch.sum((1 - M) ** 2).detach().numpy()
+        scores = scores.detach().clone()
+        out['scores'] = scores.numpy().copy()
+        out['scores_att'] = a_scores.detach().numpy().copy()
+        scores[:, 0] = -np.inf
+        _, idx = torch.topk(scores, out['k'], dim=-1)
+        out['topk_idx'] = idx.numpy()
+        with Recorder(seed + 3):
+            a_s, c_s = model.predict(inter)
+        out['predict_att'] = a_s.detach().numpy()
+        out['predict_cal'] = c_s.detach().numpy()
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **out)
+    print(name, os.path.getsize(path) // 1024, 'KB')
+
+
+TI_CASES = [
+    # ACTiSASRec (SURVEY section 8 f-4)
+    ('ti_gate_train', 131, 3, 51, True, dict(n_layers=2, hidden_size=32, inner_size=64)),
+    ('ti_fixed_train', 131, 3, 52, True, dict(n_layers=1, n_heads=4, hidden_size=32, inner_size=64, combine_option='fixed',
+                                              two_level=False, rich_calibrated_combine='fixed')),
+    ('ti_gate_eval', 131, 3, 53, False, dict(n_layers=2, hidden_size=32, inner_size=64)),
+]
+
 SSEPT_CASES = [
     # ACSSEPT (SURVEY section 8 f-4).  hidden = item_hidden_size + user_hidden_size
     ('ssept_gate_train', 151, 23, 3, 41, True, dict(n_layers=2)),
@@ -427,6 +532,10 @@ if __name__ == '__main__':
         if only and name not in only:
             continue
         make_bert_case(name, V, B, seed, train, **kw)
+    for name, V, B, seed, train, kw in TI_CASES:
+        if only and name not in only:
+            continue
+        make_ti_case(name, V, B, seed, train, **kw)
     for name, V, U, B, seed, train, kw in SSEPT_CASES:
         if only and name not in only:
             continue

@@ -37,8 +37,8 @@ def load_case(name, dtype=torch.float32):
             continue
         parts = k.split('.')
         a = torch.from_numpy(z[k])
-        if parts[1] == 'emb':
-            r['emb'] = a.to(dtype) / (1 - ph)
+        if parts[1] in ('emb', 'posK', 'posV', 'timeK', 'timeV'):      # hidden-dropout masks drawn once per forward
+            r[parts[1]] = a.to(dtype) / (1 - ph)
         elif parts[2] == 'noise':
             r[(int(parts[1]), 'noise')] = a.to(dtype)
         else:
@@ -49,9 +49,11 @@ def load_case(name, dtype=torch.float32):
     for key in ('masked_seq', 'pos_items', 'neg_items', 'masked_index'):        # AcBERT4Rec: the recorded host-side masking
         if key in z.files:
             batch[key] = torch.from_numpy(z[key])
+    if 'timestamp_list' in z.files:               # ACTiSASRec: the time stamp of every position
+        batch['time'] = torch.from_numpy(z['timestamp_list'])
     if 'user_id' in z.files:                      # ACSSEPT: the user of every row
         batch['user'] = torch.from_numpy(z['user_id'])
     if 'neg_item_id' in z.files:                  # loss_type BPR: the sampled negative of every row
         batch['neg'] = torch.from_numpy(z['neg_item_id'])
-    return dict(z=z, cfg=cfg, bert=('bert' in z.files), ssept=('ssept' in z.files), params=params, grads=grads, rand=O.Rand(r), batch=batch,
+    return dict(z=z, cfg=cfg, bert=('bert' in z.files), ssept=('ssept' in z.files), ti=('ti' in z.files), params=params, grads=grads, rand=O.Rand(r), batch=batch,
                 train=bool(z['train']), V=int(z['V']), k=int(z['k']))

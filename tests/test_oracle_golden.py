@@ -10,7 +10,8 @@ from oracle import acsr_oracle as O
 from golden_util import GOLDEN_DIR, load_case
 
 EVERY = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
-ALL = [n for n in EVERY if not n.startswith(('bert_', 'ssept_'))]
+ALL = [n for n in EVERY if not n.startswith(('bert_', 'ssept_', 'ti_'))]
+TI = [n for n in EVERY if n.startswith('ti_')]              # ACTiSASRec cases (actisasrec.py on transformer_layers.py)
 SSEPT = [n for n in EVERY if n.startswith('ssept_')]        # ACSSEPT cases (acssept.py on transformer_layers.py)
 BERT = [n for n in EVERY if n.startswith('bert_')]          # AcBERT4Rec cases (acbert4rec.py)
 TRAIN = [n for n in ALL if '_train' in n]
@@ -134,4 +135,37 @@ def test_ssept_eval_scores(name):
     ok, nbad = O.topk_equal_modulo_ties(idx, torch.from_numpy(z['topk_idx']), torch.from_numpy(z['scores']))
     assert ok, nbad
     pa, pc = O.ssept_predict(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['user'], b['pos'], c['rand'])
+    assert rel(pa, z['predict_att']) < 2e-5 and rel(pc, z['predict_cal']) < 2e-5
+
+
+@pytest.mark.parametrize('name', [n for n in TI if '_train' in n])
+def test_ti_train_losses_and_routed_grads(name):
+    """ACTiSASRec (actisasrec.py:173-193): time-interval aware keys / values on the transformer_layers.py layer"""
+    c = load_case(name)
+    b, z = c['batch'], c['z']
+    l_att, l_cal, grads = O.ti_train_grads(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['time'], b['pos'], c['rand'],
+                                           neg_items=b.get('neg'))
+    assert abs(float(l_att) - float(z['loss_att'])) < 1e-5 * abs(float(z['loss_att']))
+    assert abs(float(l_cal) - float(z['loss_cal'])) < 1e-5 * abs(float(z['loss_cal']))
+    assert set(grads) == set(c['grads'])
+    for n, g in c['grads'].items():
+        scale = float(g.abs().max())
+        err = float((grads[n] - g).abs().max())
+        assert err <= 2e-4 * scale + 2e-9, (n, err, scale)
+
+
+@pytest.mark.parametrize('name', [n for n in TI if '_eval' in n])
+def test_ti_eval_scores(name):
+    c = load_case(name)
+    b, z = c['batch'], c['z']
+    att, cal, Ms = O.ti_forward(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['time'], c['rand'])
+    assert rel(att, z['out_att']) < 2e-5 and rel(cal, z['out_cal']) < 2e-5
+    for l, M in enumerate(Ms):
+        assert rel(torch.sum((1 - M) ** 2), z['pen_sq.%d' % l]) < 1e-5
+    sa, sc = O.ti_full_sort_scores(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['time'], c['rand'])
+    assert rel(sc, z['scores']) < 2e-5 and rel(sa, z['scores_att']) < 2e-5
+    _, idx = O.full_sort_topk(sc, c['k'])
+    ok, nbad = O.topk_equal_modulo_ties(idx, torch.from_numpy(z['topk_idx']), torch.from_numpy(z['scores']))
+    assert ok, nbad
+    pa, pc = O.ti_predict(c['params'], c['cfg'], b['item_seq'], b['item_len'], b['time'], b['pos'], c['rand'])
     assert rel(pa, z['predict_att']) < 2e-5 and rel(pc, z['predict_cal']) < 2e-5
