@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_kernel(const AttnPar
   bs.pacc = ptr; ptr += 4 * DH;
   bs.red = ptr; ptr += kAttnWarps * 4;
   BwdFlags f;
-  f.has_t0 = p.t0 != nullptr; f.has_t1 = p.t1 != nullptr;
+  f.has_t0 = p.t0 != nullptr || p.dprob_cal != nullptr; f.has_t1 = p.t1 != nullptr || p.dprob_att != nullptr;
   f.t1_att = NS == 1 ? true : (p.t1_is_att != 0);
   f.has_att = f.has_t1 && f.t1_att;          // the attacked probabilities A are needed
   f.gate = p.combine == ACSR_ATTN_COMBINE_GATE;
@@ -294,6 +294,32 @@ int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const fl
   ACSR_REQUIRE(combine_option != ACSR_ATTN_COMBINE_GATE || d_gate_logit != nullptr, "attn_calib_bwd: d_gate_logit is NULL");
   // d_order_*, d_dist_*, d_scalar, d_rich_ratio may be NULL: that cotangent stream does not own those parameters
   if (L > 64) return attn_long_bwd(p, 1, (cudaStream_t)stream);
+  return dispatch_bwd<1>(p, (cudaStream_t)stream);
+}
+
+/* ACTiSASRec: acsr_attn_calib_bwd with the raw-score bias, the cotangents of the attention matrices handed out by
+ * acsr_attn_calib_ti_fwd, and the gradient of the bias (written where a row's chain runs; the caller zero-fills). */
+int acsr_attn_calib_ti_bwd(const float* d_ctx_att, const float* d_ctx_cal, const float* d_pen_sq, const float* d_prob_att,
+                           const float* d_prob_cal, const float* s_bias, const float* mq, const float* mk,
+                           const float* mv, const float* aq, const float* ak, const float* gate_logit, const int64_t* item_seq,
+                           const float* order_w, const float* order_b, const float* dist_w, const float* dist_b, const float* scalar,
+                           int B, int L, int H, int dh, int two_level, int combine_option, float comb_scalar, int rich_mode,
+                           const float* rich_ratio, float p_attn, const float* D1, const float* D2, const float* D3,
+                           const float* noise, const void* rng, uint32_t rng_stream, float* d_mq, float* d_mk, float* d_mv,
+                           float* d_aq, float* d_ak, float* d_gate_logit, float* d_order_w, float* d_order_b, float* d_dist_w,
+                           float* d_dist_b, float* d_scalar, float* d_rich_ratio, float* d_s_bias, void* stream) {
+  AttnParams p = {};
+  attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, nullptr, nullptr);
+  p.t0 = d_ctx_cal; p.t1 = d_ctx_att; p.t1_is_att = 1; p.d_pen0 = d_pen_sq;
+  p.s_bias = s_bias; p.dprob_att = d_prob_att; p.dprob_cal = d_prob_cal; p.d_s_bias = d_s_bias;
+  p.d_mq = d_mq; p.d_mk = d_mk; p.d_mv = d_mv; p.d_aq = d_aq; p.d_ak = d_ak; p.d_gate = d_gate_logit;
+  p.d_ow = d_order_w; p.d_ob = d_order_b; p.d_dw = d_dist_w; p.d_db = d_dist_b; p.d_scalar = d_scalar; p.d_ratio = d_rich_ratio;
+  int rc = attn_validate(p, "attn_calib_ti_bwd");
+  if (rc) return rc;
+  ACSR_REQUIRE(d_mq && d_mk && d_mv && d_aq && d_ak, "attn_calib_ti_bwd: NULL output");
+  ACSR_REQUIRE(combine_option != ACSR_ATTN_COMBINE_GATE || d_gate_logit != nullptr, "attn_calib_ti_bwd: d_gate_logit is NULL");
+  ACSR_REQUIRE(p.plain && L <= 64, "attn_calib_ti_bwd: the time-aware terms need ACSR_ATTN_PLAIN and L <= 64");
   return dispatch_bwd<1>(p, (cudaStream_t)stream);
 }
 

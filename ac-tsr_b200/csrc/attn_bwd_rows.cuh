@@ -60,6 +60,16 @@ __device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem
       if ((act >> jj) & 1u) { d0[jj] = x0; d1[jj] = x1; }
     }
   }
+  if (p.dprob_cal != nullptr || p.dprob_att != nullptr) {       // cotangents of the attention matrices themselves (ACTiSASRec)
+    const long long ebase = (((long long)b * p.H + h) * L + i) * L;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj)
+      if ((act >> jj) & 1u) {
+        const int j = sub + G * jj;
+        if (p.dprob_cal != nullptr) d0[jj] += __ldg(p.dprob_cal + ebase + j);
+        if (p.dprob_att != nullptr) d1[jj] += __ldg(p.dprob_att + ebase + j);
+      }
+  }
   // forward quantities shared by the streams
   float Pj[NJ], Mj[NJ], Oj[NJ], expm[NJ];
 #pragma unroll
@@ -225,6 +235,7 @@ __device__ __forceinline__ void bwd_row_iter(const AttnParams& p, const AttnSmem
         const int t = mat_row(p, j, LP) + i;
         bs.matST[s][t] = dS[jj];
         bs.matS2T[s][t] = dS2[jj];
+        if (NS == 1 && p.d_s_bias != nullptr) p.d_s_bias[(((long long)b * p.H + h) * L + i) * L + j] = dS[jj];
       }
     }
     row_du[s] = grp_sum<G>(rdu);

@@ -55,6 +55,13 @@ struct AttnParams {
   float *ctx_att, *ctx_cal;
   double* pen_sq;
   float* probs;
+  // ACTiSASRec (timeaware.cu): additive raw-score bias [B,H,L,L] (q.posK + q.timeK), the attacked / final calibrated attention
+  // written out [B,H,L,L] so that the time-aware context terms can be formed, and in the backward their cotangents coming
+  // back plus the gradient of the bias going out.  All optional; plain variant only.
+  const float* s_bias;
+  float *prob_att_out, *prob_cal_out;
+  const float *dprob_att, *dprob_cal;
+  float* d_s_bias;
   // backward: two cotangent tiles.  One stream: t0 = d_ctx_cal, t1 = d_ctx_att.  Two streams: t0 = stream 0's
   // d_ctx_cal, t1 = stream 1's d_ctx_cal or (t1_is_att) d_ctx_att.
   const float *t0, *t1;
@@ -387,6 +394,10 @@ __device__ __forceinline__ void row_forward(const AttnParams& p, const AttnSmem&
         }
       }
     }
+  }
+  if (p.s_bias != nullptr) {
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) if ((act >> jj) & 1u) S[jj] += __ldg(p.s_bias + ebase + jc[jj]);
   }
   const float rowO = sm.rowO[i], rowD = sm.rowD[i];
   float zP[NJ], z0[NJ], zM[NJ];

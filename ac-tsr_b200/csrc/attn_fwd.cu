@@ -152,3 +152,31 @@ extern "C" int acsr_attn_calib_fwd(const float* mq, const float* mk, const float
   }
   return ACSR_ERR_UNSUPPORTED;
 }
+
+/* ACTiSASRec: acsr_attn_calib_fwd with an additive raw-score bias (q.posK + q.timeK[t_ij], acsr_pair_score) and the attacked /
+ * final calibrated attention matrices written out [B,H,L,L] (the time-aware context terms are formed from them by
+ * acsr_pair_context).  Plain (transformer_layers.py) variant, L <= 64: every entry of both matrices is written. */
+extern "C" int acsr_attn_calib_ti_fwd(const float* s_bias, const float* mq, const float* mk, const float* mv, const float* aq,
+                                      const float* ak, const float* gate_logit, const int64_t* item_seq, const float* order_w,
+                                      const float* order_b, const float* dist_w, const float* dist_b, const float* scalar, int B,
+                                      int L, int H, int dh, int two_level, int combine_option, float comb_scalar, int rich_mode,
+                                      const float* rich_ratio, float p_attn, const float* D1, const float* D2, const float* D3,
+                                      const float* noise, const void* rng, uint32_t rng_stream, float* ctx_att, float* ctx_cal,
+                                      double* pen_sq, float* prob_att, float* prob_cal, void* stream) {
+  AttnParams p = {};
+  attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
+                   combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, nullptr, nullptr);
+  p.ctx_att = ctx_att; p.ctx_cal = ctx_cal; p.pen_sq = pen_sq; p.probs = nullptr;
+  p.s_bias = s_bias; p.prob_att_out = prob_att; p.prob_cal_out = prob_cal;
+  int rc = attn_validate(p, "attn_calib_ti_fwd");
+  if (rc) return rc;
+  ACSR_REQUIRE(ctx_cal != nullptr && prob_cal != nullptr, "attn_calib_ti_fwd: ctx_cal / prob_cal is NULL");
+  ACSR_REQUIRE(p.plain && L <= 64, "attn_calib_ti_fwd: the time-aware terms need ACSR_ATTN_PLAIN and L <= 64");
+  switch (dh) {
+    case 8: return launch_fwd<8>(p, (cudaStream_t)stream);
+    case 16: return launch_fwd<16>(p, (cudaStream_t)stream);
+    case 32: return launch_fwd<32>(p, (cudaStream_t)stream);
+    case 64: return launch_fwd<64>(p, (cudaStream_t)stream);
+  }
+  return ACSR_ERR_UNSUPPORTED;
+}

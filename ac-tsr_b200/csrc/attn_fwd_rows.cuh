@@ -33,6 +33,11 @@ __device__ __forceinline__ void fwd_row_iter(const AttnParams& p, const AttnSmem
       bufA[j] = a ? r.A[jj] : 0.f;
     }
     if (a && rowok) { const float om = 1.0f - Mj; cx.pen = fmaf(om, om, cx.pen); }
+    if (p.prob_cal_out != nullptr && a && rowok) {
+      const long long e = (((long long)b * p.H + h) * L + i) * L + j;
+      p.prob_cal_out[e] = Rf;
+      if (p.prob_att_out != nullptr && need_att) p.prob_att_out[e] = r.A[jj];
+    }
     if (p.probs && a && rowok) {
       const long long e = (((long long)b * p.H + h) * L + i) * L + j;
       const long long plane = (long long)p.B * p.H * L * L;

@@ -36,6 +36,11 @@ class SyntheticSequentialDataset(object):
         seq, ln, tgt = synth_sequences(n_rows, L, n_items, seed, full_len)
         feat = {self.iid_field + config['LIST_SUFFIX']: seq, config['ITEM_LIST_LENGTH_FIELD']: ln, self.iid_field: tgt,
                 self.uid_field: torch.arange(n_rows, dtype=torch.int64) % max(n_rows - 1, 1) + 1}
+        if str(config.get('model', '')) == 'ACTiSASRec':    # increasing time stamps, 0 on the padding (sequential_dataset.py:128-132)
+            g = torch.Generator().manual_seed(seed + 7)
+            ts = (torch.cumsum(torch.randint(0, 40, (n_rows, L), generator=g), 1) + 1000).float()
+            ts[seq == 0] = 0.0
+            feat[config['TIME_FIELD'] + config['LIST_SUFFIX']] = ts
         if pin and torch.cuda.is_available():
             feat = {k: v.pin_memory() for k, v in feat.items()}
         self.inter_feat = Interaction(feat)
@@ -54,6 +59,8 @@ def _model_fields(config):
     f = [iid + config['LIST_SUFFIX'], config['ITEM_LIST_LENGTH_FIELD'], iid]
     if str(config.get('model', '')) == 'ACSSEPT':          # the one model that reads the user id (acssept.py:177)
         f.append(config['USER_ID_FIELD'])
+    if str(config.get('model', '')) == 'ACTiSASRec':       # ... and the one that reads the time stamps (actisasrec.py:177)
+        f.append(config['TIME_FIELD'] + config['LIST_SUFFIX'])
     return f
 
 
@@ -67,7 +74,7 @@ class _PackedBatches(object):
     def fill(self, inter_feat):
         n = len(inter_feat)
         nb = n // self.bs
-        if nb == 0 or any(f not in inter_feat for f in self.fields):
+        if nb == 0 or any(f not in inter_feat or inter_feat[f].dtype != torch.int64 for f in self.fields):    # int64 fields only
             self.nb = 0
             return
         per = [int(np.prod(inter_feat[f].shape[1:])) for f in self.fields]

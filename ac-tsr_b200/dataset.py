@@ -219,13 +219,17 @@ class SequentialDataset(object):
         gather = seq_start[:, None] + cols[None, :]
         valid = cols[None, :] < length[:, None]
         item_list = np.where(valid, iid[np.minimum(gather, n - 1)], 0)
-        self.inter_feat = Interaction({
+        feat = {
             self.uid_field: torch.from_numpy(uid[tgt].copy()),
             self.iid_field: torch.from_numpy(iid[tgt].copy()),
             self.time_field: torch.from_numpy(t[tgt].copy()),
             self.item_list_length_field: torch.from_numpy(length.astype(np.int64)),
             self.item_id_list_field: torch.from_numpy(item_list.astype(np.int64)),
-        })
+        }
+        if str(self.config.get('model', '')) == 'ACTiSASRec':       # the one model that reads timestamp_list (actisasrec.py:35, 177)
+            time_list = np.where(valid, t[np.minimum(gather, n - 1)], 0).astype(np.float32)
+            feat[self.time_field + self.config['LIST_SUFFIX']] = torch.from_numpy(time_list)
+        self.inter_feat = Interaction(feat)
 
     # -- API the model / trainer / loaders use ---------------------------------------------------------
     def num(self, field):

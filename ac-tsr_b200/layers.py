@@ -152,7 +152,7 @@ class AttackRTransformerLayer(nn.Module):
         self.anneal_step = 0
 
     def forward(self, hidden_states, attention_mask, return_attention_prob=False, return_all_attention_prob=False,
-                rt=None, layer_idx=0, need_attacked=True):
+                rt=None, layer_idx=0, need_attacked=True, time_terms=None):
         rt = rt or default_runtime(hidden_states.device)
         if self.combine_option not in ops.COMBINE_IDS:
             raise KeyError(self.combine_option)
@@ -187,13 +187,26 @@ class AttackRTransformerLayer(nn.Module):
         opts = ops.AttnOpts(aa.num_attention_heads, self.two_level, self.combine_option,
                             self.rich_calibrated_combine if not self.two_level else 'none', p_attn,
                             bidirectional=bool(getattr(rt, 'bidirectional', False)), plain=self.plain_variant)
-        ctx_att, ctx_cal, pen_sq, probs = ops.AttnCalibFn.apply(
+        calib_args = (
             mq, mk, mv, aq, ak, gate_logit, key_ids,
             aa.order_affine.weight if aa.use_order else None, aa.order_affine.bias if aa.use_order else None,
             aa.distance_affine.weight if aa.use_distance else None, aa.distance_affine.bias if aa.use_distance else None,
             aa.scalar if aa.use_distance else None,
             getattr(self, 'rich_calibrated_combine_ratio', None) if not self.two_level else None,
-            opts, comb_scalar, p_attn, rand, rt.rng, base, need_attacked, want_probs)
+            opts, comb_scalar, p_attn, rand, rt.rng, base, need_attacked)
+        if time_terms is None:
+            ctx_att, ctx_cal, pen_sq, probs = ops.AttnCalibFn.apply(*calib_args, want_probs)
+        else:
+            # ACTiSASRec (transformer_layers.py:1116-1134, 1085-1091): q.posK + q.timeK[t_ij] join the raw scores, and
+            # probs.posV + probs.timeV[t_ij] the context of both streams
+            if want_probs:
+                raise NotImplementedError('attention probabilities of the time-aware layer are not exported')
+            s_bias = time_terms.score_bias(mq)
+            ctx_att, ctx_cal, pen_sq, prob_att, prob_cal = ops.AttnCalibTiFn.apply(s_bias, *calib_args)
+            ctx_cal = ctx_cal + time_terms.context(prob_cal)
+            if need_attacked:
+                ctx_att = ctx_att + time_terms.context(prob_att)
+            probs = None
         cal_att_out = aa.cal_adjusted_outputs(ctx_cal, x, rt, (layer_idx, 'D5'), base + 3)
         cal_out = self.feed_forward(cal_att_out, rt, (layer_idx, 'D7'), base + 5)
         att_out = None

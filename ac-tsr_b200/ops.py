@@ -249,6 +249,157 @@ class AttnCalibFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------
+# ACTiSASRec: time-interval aware keys / values (timeaware.cu) around the fused attention
+# ------------------------------------------------------------------------------------------
+def time_matrix(time_seq, time_span):
+    """actisasrec.py:146-155: [B, L] time stamps -> int32 [B, L, L] clipped intervals"""
+    ts = time_seq.to(torch.float32).contiguous()
+    B, L = ts.shape
+    out = torch.empty((B, L, L), dtype=torch.int32, device=ts.device)
+    LIB.call('acsr_time_matrix', _p(ts), B, L, int(time_span), _p(out, torch.int32), _stream())
+    return out
+
+
+class PairSpec:
+    """everything of the pair embedding E[b,i,j,c] = P[j,c]*Dp[b,j,c] + T[t[b,i,j],c]*Dt[b,i,j,c] except the two tables"""
+
+    def __init__(self, tmat, n_heads, p, Dp=None, Dt=None, rng=None, stream_p=0, stream_t=0):
+        self.tmat, self.H, self.p = tmat.contiguous(), int(n_heads), float(p)
+        self.Dp, self.Dt = _c(Dp), _c(Dt)
+        self.rng, self.stream_p, self.stream_t = rng, int(stream_p), int(stream_t)
+
+    def args(self, B, L, d, span1):
+        return (_p(self.tmat, torch.int32), B, L, self.H, d // self.H, span1, self.p, _p(self.Dp), _p(self.Dt),
+                self.rng.ptr if (self.rng is not None and self.p > 0) else None, self.stream_p, self.stream_t)
+
+
+def _pair_score(x, P, T, spec, causal):
+    B, L, d = x.shape
+    out = torch.empty((B, spec.H, L, L), dtype=torch.float32, device=x.device)
+    a = spec.args(B, L, d, T.shape[0])
+    LIB.call('acsr_pair_score', _p(x), _p(P), _p(T), *a, int(causal), _p(out), _stream())
+    return out
+
+
+def _pair_context(prob, P, T, spec, d):
+    B, H, L, _ = prob.shape
+    y = torch.empty((B, L, d), dtype=torch.float32, device=prob.device)
+    a = spec.args(B, L, d, T.shape[0])
+    LIB.call('acsr_pair_context', _p(prob), _p(P), _p(T), *a, 0, _p(y), _stream())
+    return y
+
+
+def _pair_wgrad(a_mat, v, P, T, spec):
+    B, L, d = v.shape
+    dP, dT = torch.zeros_like(P), torch.zeros_like(T)
+    a = spec.args(B, L, d, T.shape[0])
+    LIB.call('acsr_pair_wgrad', _p(a_mat), _p(v), a[0], *a[1:], _p(dP), _p(dT), _stream())
+    return dP, dT
+
+
+class PairScoreFn(torch.autograd.Function):
+    """s[b,h,i,j] = q_i . (posK_j + timeK[t_ij]) per head, with the reference's element-wise dropout of both embeddings
+    (actisasrec.py:120-123, transformer_layers.py:1128-1134); the [B,L,L,d] gather never exists."""
+
+    @staticmethod
+    def forward(ctx, x, P, T, spec, causal):
+        x, P, T = x.contiguous(), P.contiguous(), T.contiguous()
+        ctx.save_for_backward(x, P, T)
+        ctx.spec, ctx.causal = spec, bool(causal)
+        return _pair_score(x, P, T, spec, causal)
+
+    @staticmethod
+    def backward(ctx, ds):
+        x, P, T = ctx.saved_tensors
+        ds = (torch.tril(ds) if ctx.causal else ds).contiguous()       # pairs j > i were not computed: they carry no gradient
+        dx = _pair_context(ds, P, T, ctx.spec, x.shape[-1]) if ctx.needs_input_grad[0] else None
+        dP = dT = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dP, dT = _pair_wgrad(ds, x, P, T, ctx.spec)
+        return dx, dP, dT, None, None
+
+
+class PairContextFn(torch.autograd.Function):
+    """y[b,i,:] = sum_j prob[b,h,i,j] (posV_j + timeV[t_ij]) (transformer_layers.py:1088-1091)"""
+
+    @staticmethod
+    def forward(ctx, prob, P, T, spec):
+        prob, P, T = prob.contiguous(), P.contiguous(), T.contiguous()
+        ctx.save_for_backward(prob, P, T)
+        ctx.spec = spec
+        return _pair_context(prob, P, T, spec, P.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        prob, P, T = ctx.saved_tensors
+        dy = dy.contiguous()
+        dprob = _pair_score(dy, P, T, ctx.spec, 0) if ctx.needs_input_grad[0] else None
+        dP = dT = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dP, dT = _pair_wgrad(prob, dy, P, T, ctx.spec)
+        return dprob, dP, dT, None
+
+
+class AttnCalibTiFn(torch.autograd.Function):
+    """AttnCalibFn with an additive raw-score bias and the attacked / final calibrated attention matrices as differentiable
+    outputs -> (ctx_att|None, ctx_cal, pen_sq, prob_att|None, prob_cal).  transformer_layers.py variant, L <= 64."""
+
+    @staticmethod
+    def forward(ctx, s_bias, mq, mk, mv, aq, ak, gate_logit, key_ids, order_w, order_b, dist_w, dist_b, scalar, rich_ratio,
+                opts, comb_scalar, p_attn, rand, rng, rng_stream, need_att):
+        B, L, d = mq.shape
+        H = opts.n_heads
+        dh = d // H
+        ctx.set_materialize_grads(False)
+        s_bias, mq, mk, mv, aq, ak = (t.contiguous() for t in (s_bias, mq, mk, mv, aq, ak))
+        gate_logit = _c(gate_logit)
+        key_ids = key_ids.contiguous()
+        D1, D2, D3, noise = (_c(rand.get(k)) if rand else None for k in ('D1', 'D2', 'D3', 'noise'))
+        dev = mq.device
+        ctx_cal = torch.empty((B, L, d), dtype=torch.float32, device=dev)
+        ctx_att = torch.empty_like(ctx_cal) if need_att else None
+        prob_cal = torch.empty((B, H, L, L), dtype=torch.float32, device=dev)
+        prob_att = torch.empty_like(prob_cal) if need_att else None
+        pen = torch.zeros(1, dtype=torch.float64, device=dev)
+        LIB.call('acsr_attn_calib_ti_fwd', _p(s_bias), _p(mq), _p(mk), _p(mv), _p(aq), _p(ak), _p(gate_logit),
+                 _p(key_ids, torch.int64), _p(order_w), _p(order_b), _p(dist_w), _p(dist_b), _p(scalar), B, L, H, dh,
+                 opts.two_level, opts.combine, float(comb_scalar), opts.rich, _p(rich_ratio),
+                 p_attn, _p(D1), _p(D2), _p(D3), _p(noise), rng.ptr if rng is not None else None, rng_stream,
+                 _p(ctx_att), _p(ctx_cal), pen.data_ptr(), _p(prob_att), _p(prob_cal), _stream())
+        ctx.save_for_backward(s_bias, mq, mk, mv, aq, ak, gate_logit, key_ids, order_w, order_b, dist_w, dist_b, scalar,
+                              rich_ratio, D1, D2, D3, noise)
+        ctx.meta = (B, L, H, dh, opts, float(comb_scalar), p_attn, rng, rng_stream, need_att)
+        return ctx_att, ctx_cal, pen.to(torch.float32), prob_att, prob_cal
+
+    @staticmethod
+    def backward(ctx, d_att, d_cal, d_pen, d_pa, d_pc):
+        (s_bias, mq, mk, mv, aq, ak, gate_logit, key_ids, order_w, order_b, dist_w, dist_b, scalar, rich_ratio,
+         D1, D2, D3, noise) = ctx.saved_tensors
+        B, L, H, dh, opts, comb_scalar, p_attn, rng, rng_stream, need_att = ctx.meta
+        d_att = _c(d_att) if need_att else None
+        d_pa = _c(d_pa) if need_att else None
+        d_cal, d_pen, d_pc = _c(d_cal), _c(d_pen), _c(d_pc)
+        z = torch.zeros_like
+        d_mq, d_mk, d_mv, d_aq, d_ak = (torch.empty_like(mq) for _ in range(5))
+        d_gate = z(gate_logit) if gate_logit is not None else None
+        d_ow = z(order_w) if order_w is not None else None
+        d_ob = z(order_b) if order_b is not None else None
+        d_dw = z(dist_w) if dist_w is not None else None
+        d_db = z(dist_b) if dist_b is not None else None
+        d_sc = z(scalar) if scalar is not None else None
+        d_rr = z(rich_ratio) if rich_ratio is not None else None
+        d_sb = z(s_bias)
+        LIB.call('acsr_attn_calib_ti_bwd', _p(d_att), _p(d_cal), _p(d_pen), _p(d_pa), _p(d_pc), _p(s_bias), _p(mq), _p(mk),
+                 _p(mv), _p(aq), _p(ak), _p(gate_logit), _p(key_ids, torch.int64), _p(order_w), _p(order_b), _p(dist_w),
+                 _p(dist_b), _p(scalar), B, L, H, dh, opts.two_level, opts.combine, comb_scalar, opts.rich, _p(rich_ratio),
+                 p_attn, _p(D1), _p(D2), _p(D3), _p(noise), rng.ptr if rng is not None else None, rng_stream,
+                 _p(d_mq), _p(d_mk), _p(d_mv), _p(d_aq), _p(d_ak), _p(d_gate), _p(d_ow), _p(d_ob), _p(d_dw), _p(d_db),
+                 _p(d_sc), _p(d_rr), _p(d_sb), _stream())
+        return (d_sb, d_mq, d_mk, d_mv, d_aq, d_ak, d_gate, None, d_ow, d_ob, d_dw, d_db, d_sc, d_rr,
+                None, None, None, None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------
 # full-catalogue logits on tcgen05
 # ------------------------------------------------------------------------------------------
 def logits_num_chunks(M, V, d=64):

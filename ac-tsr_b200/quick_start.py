@@ -11,12 +11,13 @@ import torch
 from .acsasrec import ACSASRec
 from .acbert4rec import AcBERT4Rec
 from .acssept import ACSSEPT
+from .actisasrec import ACTiSASRec
 from .compat import Config
 from .dataset import create_dataset, data_preparation
-from .trainer import ACSASRecTrainer, AcBERT4RecTrainer, ACSSEPTTrainer
+from .trainer import ACSASRecTrainer, AcBERT4RecTrainer, ACSSEPTTrainer, ACTiSASRecTrainer
 
 _MODELS = {'ACSASRec': (ACSASRec, ACSASRecTrainer), 'AcBERT4Rec': (AcBERT4Rec, AcBERT4RecTrainer),
-           'ACSSEPT': (ACSSEPT, ACSSEPTTrainer)}
+           'ACSSEPT': (ACSSEPT, ACSSEPTTrainer), 'ACTiSASRec': (ACTiSASRec, ACTiSASRecTrainer)}
 
 
 def init_seed(seed, reproducibility):

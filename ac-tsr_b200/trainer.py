@@ -610,8 +610,12 @@ class ACSASRecTrainer(object):
         if g is None:
             dev = self.device
             # static inputs (sequence, length, held-out item) as views of one flat buffer: a packed batch is ONE copy
-            lay, total = PackedInteraction.layout_of({**{k: interaction[k] for k in fields}, m.POS_ITEM_ID: positive_i})
-            inter = PackedInteraction(torch.empty(total, dtype=torch.int64, device=dev), lay)
+            if all(interaction[k].dtype == torch.int64 for k in fields):
+                lay, total = PackedInteraction.layout_of({**{k: interaction[k] for k in fields}, m.POS_ITEM_ID: positive_i})
+                inter = PackedInteraction(torch.empty(total, dtype=torch.int64, device=dev), lay)
+            else:                             # a float field (ACTiSASRec's time stamps): one static tensor per field
+                inter = Interaction({**{k: torch.empty_like(interaction[k], device=dev) for k in fields},
+                                     m.POS_ITEM_ID: torch.empty_like(positive_i, device=dev)})
             static = {k: inter[k] for k in fields}
             for k in fields:
                 static[k].copy_(interaction[k])
@@ -628,7 +632,7 @@ class ACSASRecTrainer(object):
                 _, _, rec = m.full_sort_topk(inter, kmax, pos)
             g = dict(graph=graph, static=static, pos=pos, rec=rec, inter=inter)
             self._eval_graphs[key] = g
-        if getattr(interaction, 'layout', None) == g['inter'].layout and positive_i is interaction.interaction.get(m.POS_ITEM_ID):
+        if getattr(interaction, 'layout', None) == getattr(g['inter'], 'layout', ()) and positive_i is interaction.interaction.get(m.POS_ITEM_ID):
             g['inter'].packed.copy_(interaction.packed, non_blocking=True)
         else:
             for k in fields:
@@ -669,4 +673,9 @@ class ACSSEPTTrainer(ACSASRecTrainer):
     (trainer.py:1038-1048), so get_trainer (utils.py:89-100) hands its ACSSEPT the stock Trainer, which sums the two losses and
     cannot evaluate the tuple full_sort_predict returns; this class is the trainer the model's (attacked, calibrated) API is
     written for, on the autograd Functions over the same kernels."""
+    pass
+
+
+class ACTiSASRecTrainer(ACSASRecTrainer):
+    """ACTiSASRec (actisasrec.py) under the AC training step; like ACSSEPT the reference registers no trainer of this name."""
     pass

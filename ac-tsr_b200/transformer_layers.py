@@ -32,3 +32,61 @@ class AttackRTransformerEncoder(_layers.AttackRTransformerEncoder):
         super().__init__(n_layers, n_heads, hidden_size, inner_size, hidden_dropout_prob, attn_dropout_prob, hidden_act,
                          layer_norm_eps, combine_option, use_order=use_order, use_distance=use_distance, two_level=two_level,
                          rich_calibrated_combine=rich_calibrated_combine, seq_length=50)
+
+
+class TimeTerms:
+    """The time-interval aware key / value embeddings of one ACTiSASRec forward (actisasrec.py:104-124), as the layers use them:
+    tables + interval matrix + dropout streams instead of the reference's gathered and dropped [B,L,L,d] tensors.  One instance
+    is shared by all layers (the reference draws the four dropout masks once per forward)."""
+
+    def __init__(self, pos_k, pos_v, time_k, time_v, tmat, n_heads, p, rt):
+        from . import ops
+        self.ops = ops
+        self.pos_k, self.pos_v, self.time_k, self.time_v = pos_k, pos_v, time_k, time_v
+        m = (lambda k: rt.mask(k)) if p > 0 else (lambda k: None)
+        self.spec_k = ops.PairSpec(tmat, n_heads, p, m('posK'), m('timeK'), rt.rng, 2, 4)
+        self.spec_v = ops.PairSpec(tmat, n_heads, p, m('posV'), m('timeV'), rt.rng, 3, 5)
+
+    def score_bias(self, mq):
+        return self.ops.PairScoreFn.apply(mq, self.pos_k, self.time_k, self.spec_k, 1)
+
+    def context(self, prob):
+        return self.ops.PairContextFn.apply(prob, self.pos_v, self.time_v, self.spec_v)
+
+
+class ACTimeAwareMultiHeadAttention(AttackRMultiHeadAttention):
+    """transformer_layers.py:1010-1177: the parameter set is that of AttackRMultiHeadAttention"""
+
+
+class ACTimeAwareTransformerLayer(AttackRTransformerLayer):
+    """transformer_layers.py:1232-1327.  forward takes a TimeTerms object where the reference takes the four gathered tensors
+    (absolute_pos_K, absolute_pos_V, time_matrix_emb_K, time_matrix_emb_V)."""
+
+    def forward(self, hidden_states, attention_mask, time_terms, return_attention_prob=False, rt=None, layer_idx=0,
+                need_attacked=True):
+        return super().forward(hidden_states, attention_mask, return_attention_prob, False, rt=rt, layer_idx=layer_idx,
+                               need_attacked=need_attacked, time_terms=time_terms)
+
+
+class ACTimeAwareTransformerEncoder(AttackRTransformerEncoder):
+    """transformer_layers.py:1330-1448."""
+
+    layer_class = ACTimeAwareTransformerLayer
+
+    def forward(self, hidden_states, attention_mask, time_terms, output_all_encoded_layers=True, rt=None):
+        from .layers import default_runtime
+        rt = rt or default_runtime(hidden_states.device)
+        all_encoder_layers, all_attack_masks = [], []
+        att = cal = None
+        n = len(self.layer)
+        for layer_idx, layer_module in enumerate(self.layer):
+            need_att = (layer_idx == n - 1) or not rt.attacked_last_only
+            att, cal, attack_mask, _ = layer_module(hidden_states, attention_mask, time_terms, rt=rt, layer_idx=layer_idx,
+                                                    need_attacked=need_att)
+            hidden_states = cal
+            all_attack_masks.append(attack_mask)
+            if output_all_encoded_layers:
+                all_encoder_layers.append((att, cal))
+        if not output_all_encoded_layers:
+            all_encoder_layers.append((att, cal))
+        return all_encoder_layers, all_attack_masks

@@ -463,6 +463,52 @@ int acsr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    float lr, float beta1, float beta2, float eps, float weight_decay,
                    int64_t* step_count, void* stream);
 
+/* ---- ACTiSASRec: time-interval aware keys / values ----------------------------------------------
+ * replaces model/sequential_recommender/actisasrec.py:104-124, 146-155 and the time-aware terms of
+ * model/transformer_layers.py:1085-1091 (context) and 1116-1134 (scores).  The reference gathers two [B,L,L,d] tensors
+ * (time_matrix_emb_K/V[t_ij]) and drops them out element-wise; here they never exist.  With the pair embedding
+ *     E[b,i,j,c] = P[j,c]*Dp[b,j,c] + T[tmat[b,i,j],c]*Dt[b,i,j,c]
+ * (P [L,d] absolute-position table, T [span1,d] interval table, span1 = time_span + 1, Dp / Dt inverted-dropout multipliers:
+ * explicit tensors [B,L,d] / [B,L,L,d], or Philox streams stream_p / stream_t of `rng`, or none when p == 0):
+ *   acsr_time_matrix   tmat[b,i,j] = (int) min(|ts[b,i] - ts[b,j]|, time_span)        (actisasrec.py:146-155, fp32 like the field)
+ *   acsr_pair_score    s[b,h,i,j]  = sum_{c in head h} x[b,i,c] * E[b,i,j,c]          (x = mixed query: the score bias;
+ *                                                                                      x = d context: d of the attention matrix)
+ *   acsr_pair_context  y[b,i,c] (+)= sum_j prob[b,h(c),i,j] * E[b,i,j,c]              (prob = attention: the context term;
+ *                                                                                      prob = d bias: d of the mixed query)
+ *   acsr_pair_wgrad    dP[j,c] += sum_{b,i} a[b,h,i,j]*v[b,i,c]*Dp[b,j,c];  dT[t,c] += sum_{tmat=t} a*v*Dt     (row 0 of both
+ *                      tables is nn.Embedding's padding_idx, actisasrec.py:55-58: no gradient)
+ * causal != 0: pairs j > i are written as 0 without being computed.  L <= 64, head size a multiple of 4. */
+int acsr_time_matrix(const float* time_seq, int B, int L, int time_span, int32_t* tmat, void* stream);
+int acsr_pair_score(const float* x, const float* P, const float* T, const int32_t* tmat, int B, int L, int H, int dh, int span1,
+                    float p, const float* Dp, const float* Dt, const void* rng, uint32_t stream_p, uint32_t stream_t, int causal,
+                    float* s_out, void* stream);
+int acsr_pair_context(const float* prob, const float* P, const float* T, const int32_t* tmat, int B, int L, int H, int dh, int span1,
+                      float p, const float* Dp, const float* Dt, const void* rng, uint32_t stream_p, uint32_t stream_t,
+                      int accumulate, float* y, void* stream);
+int acsr_pair_wgrad(const float* a, const float* v, const int32_t* tmat, int B, int L, int H, int dh, int span1,
+                    float p, const float* Dp, const float* Dt, const void* rng, uint32_t stream_p, uint32_t stream_t,
+                    float* dP, float* dT, void* stream);
+/* the fused attention of acsr_attn_calib_fwd / _bwd (ACSR_ATTN_PLAIN, L <= 64) around those terms: s_bias [B,H,L,L] is added to
+ * the raw scores q_i.k_j before the calibrators (transformer_layers.py:1134); prob_att / prob_cal [B,H,L,L] receive the attacked
+ * and the final calibrated attention (every entry written).  Backward: d_prob_att / d_prob_cal are the cotangents of those two
+ * matrices (NULL == zero), d_s_bias [B,H,L,L] receives the gradient of the bias where a row's chain runs (caller zero-fills). */
+int acsr_attn_calib_ti_fwd(const float* s_bias, const float* mq, const float* mk, const float* mv, const float* aq,
+                           const float* ak, const float* gate_logit, const int64_t* item_seq, const float* order_w,
+                           const float* order_b, const float* dist_w, const float* dist_b, const float* scalar, int B,
+                           int L, int H, int dh, int two_level, int combine_option, float comb_scalar, int rich_mode,
+                           const float* rich_ratio, float p_attn, const float* D1, const float* D2, const float* D3,
+                           const float* noise, const void* rng, uint32_t rng_stream, float* ctx_att, float* ctx_cal,
+                           double* pen_sq, float* prob_att, float* prob_cal, void* stream);
+int acsr_attn_calib_ti_bwd(const float* d_ctx_att, const float* d_ctx_cal, const float* d_pen_sq, const float* d_prob_att,
+                           const float* d_prob_cal, const float* s_bias, const float* mq, const float* mk,
+                           const float* mv, const float* aq, const float* ak, const float* gate_logit, const int64_t* item_seq,
+                           const float* order_w, const float* order_b, const float* dist_w, const float* dist_b, const float* scalar,
+                           int B, int L, int H, int dh, int two_level, int combine_option, float comb_scalar, int rich_mode,
+                           const float* rich_ratio, float p_attn, const float* D1, const float* D2, const float* D3,
+                           const float* noise, const void* rng, uint32_t rng_stream, float* d_mq, float* d_mk, float* d_mv,
+                           float* d_aq, float* d_ak, float* d_gate_logit, float* d_order_w, float* d_order_b, float* d_dist_w,
+                           float* d_dist_b, float* d_scalar, float* d_rich_ratio, float* d_s_bias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

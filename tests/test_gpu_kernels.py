@@ -1050,6 +1050,81 @@ def test_attn_calib_transformer_layers_variant(A, case):
     close(ctx_cal2, r['ctx_cal'].detach(), 3e-5, 'ctx_cal (calibrated only)')
 
 
+# ---- ACTiSASRec: time-interval aware terms (timeaware.cu) ----
+def _pair_ref(P, T, tmat, Dp, Dt):
+    """E[b,i,j,c] = P[j,c]*Dp[b,j,c] + T[t[b,i,j],c]*Dt[b,i,j,c] in double"""
+    return (P.double().unsqueeze(0) * Dp.double()).unsqueeze(1) + T.double()[tmat.long()] * Dt.double()
+
+
+@pytest.mark.parametrize('shape', [(3, 50, 2, 32, 17, 0.5), (2, 23, 4, 8, 256, 0.0), (5, 64, 1, 64, 40, 0.3), (2, 50, 2, 128, 256, 0.5)])
+def test_time_aware_pair_kernels(A, shape):
+    """pair_score / pair_context / pair_wgrad and the interval matrix against a dense double-precision restatement of
+    actisasrec.py:110-124, 146-155 and transformer_layers.py:1085-1091, 1128-1134 (explicit dropout multipliers)"""
+    B, L, H, dh, span, p = shape
+    d = H * dh
+    g = torch.Generator().manual_seed(B * 100 + L)
+    ts = (torch.cumsum(torch.randint(0, 2 * max(span // L, 2), (B, L), generator=g), 1) + 1000).float()
+    ts[1, L // 2:] = 0.0                                         # a padded tail
+    tmat = A.ops.time_matrix(ts.cuda(), span)
+    want_t = (ts.unsqueeze(-1) - ts.unsqueeze(1)).abs().clamp(max=span).int()
+    assert torch.equal(tmat.cpu(), want_t) and tmat.dtype == torch.int32
+    P, T = torch.randn(L, d, generator=g) * 0.5, torch.randn(span + 1, d, generator=g) * 0.5
+    Dp = drop((B, L, d), p, g) if p > 0 else torch.ones(B, L, d)
+    Dt = drop((B, L, L, d), p, g) if p > 0 else torch.ones(B, L, L, d)
+    x = torch.randn(B, L, d, generator=g)
+    prob = torch.randn(B, H, L, L, generator=g)
+    gs, gy = torch.randn(B, H, L, L, generator=g), torch.randn(B, L, d, generator=g)
+    # reference in double
+    Pd, Td, xd, pd = (t.clone().double().requires_grad_(True) for t in (P, T, x, prob))
+    E = (Pd.unsqueeze(0) * Dp.double()).unsqueeze(1) + torch.nn.functional.embedding(want_t.long(), Td, padding_idx=0) * Dt.double()
+    Eh = E.view(B, L, L, H, dh).permute(0, 3, 1, 2, 4)           # [B,H,L,L,dh]
+    s_ref = (Eh @ xd.view(B, L, H, dh).permute(0, 2, 1, 3).unsqueeze(-1)).squeeze(-1)
+    y_ref = (pd.unsqueeze(-2) @ Eh).squeeze(-2).permute(0, 2, 1, 3).reshape(B, L, d)
+    causal = torch.tril(torch.ones(L, L)).bool()
+    ((s_ref * gs.double() * causal).sum() + (y_ref * gy.double()).sum()).backward()
+    spec = A.ops.PairSpec(tmat, H, p, Dp.cuda() if p > 0 else None, Dt.cuda() if p > 0 else None)
+    Pc, Tc, xc, pc = (t.clone().cuda().requires_grad_(True) for t in (P, T, x, prob))
+    s = A.ops.PairScoreFn.apply(xc, Pc, Tc, spec, 1)
+    y = A.ops.PairContextFn.apply(pc, Pc, Tc, spec)
+    close(s, (s_ref * causal).detach(), 2e-5, 'pair score')
+    assert float(s.cpu()[:, :, ~causal].abs().max()) == 0.0
+    close(y, y_ref.detach(), 2e-5, 'pair context')
+    ((s * gs.cuda()).sum() + (y * gy.cuda()).sum()).backward()
+    close(xc.grad, xd.grad, 3e-5, 'd x')
+    close(pc.grad, pd.grad, 3e-5, 'd prob')
+    want_dP = Pd.grad.clone()
+    want_dP[0] = 0                                               # nn.Embedding(padding_idx=0) on the position ids (actisasrec.py:55-56)
+    close(Pc.grad, want_dP, 5e-5, 'd position table')
+    close(Tc.grad, Td.grad, 5e-5, 'd interval table')
+    assert float(Tc.grad[0].abs().max()) == 0.0
+
+
+def test_time_aware_philox_dropout_is_consistent(A):
+    """with Philox multipliers forward and backward must draw the same masks: the kernels are linear in x / prob, so the
+    gradient against a fixed cotangent equals the finite response of the forward"""
+    B, L, H, dh, span, p = 2, 50, 2, 32, 30, 0.5
+    d = H * dh
+    g = torch.Generator().manual_seed(5)
+    ts = (torch.cumsum(torch.randint(0, 5, (B, L), generator=g), 1) + 10).float().cuda()
+    tmat = A.ops.time_matrix(ts, span)
+    rng = A.ops.DeviceRng(123, torch.device('cuda'))
+    rng.advance()
+    spec = A.ops.PairSpec(tmat, H, p, None, None, rng, 2, 4)
+    P, T = (torch.randn(L, d, generator=g) * 0.5).cuda(), (torch.randn(span + 1, d, generator=g) * 0.5).cuda()
+    x = torch.randn(B, L, d, generator=g).cuda().requires_grad_(True)
+    gs = torch.randn(B, H, L, L, generator=g).cuda()
+    s1 = A.ops.PairScoreFn.apply(x, P, T, spec, 0)
+    s2 = A.ops.PairScoreFn.apply(x, P, T, spec, 0)
+    assert torch.equal(s1, s2)
+    keep = float((A.ops.PairScoreFn.apply(torch.ones_like(x), torch.zeros_like(P), torch.ones_like(T), spec, 0)).mean()) / dh
+    assert abs(keep - 1.0) < 0.05                               # E[multiplier] == 1 (inverted dropout)
+    (s1 * gs).sum().backward()
+    x2 = torch.randn(B, L, d, generator=g).cuda()
+    lhs = float((A.ops.PairScoreFn.apply(x2, P, T, spec, 0) * gs).sum())
+    rhs = float((x.grad * x2).sum())
+    assert abs(lhs - rhs) <= 2e-4 * max(abs(lhs), 1.0)
+
+
 def test_gather_rows_and_weighted_ce(A):
     """the two pieces AcBERT4Rec adds around the encoder (acbert4rec.py:198-222): row gather (+ scatter-add backward) and the
     masked-item cross entropy with per-row weights."""

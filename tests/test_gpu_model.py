@@ -15,6 +15,7 @@ from golden_util import GOLDEN_DIR, load_case
 
 EVERY = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
 ALL = [n for n in EVERY if not n.startswith(('bert_', 'ssept_', 'ti_'))]
+TI = [n for n in EVERY if n.startswith('ti_')]              # ACTiSASRec cases (actisasrec.py on transformer_layers.py)
 SSEPT = [n for n in EVERY if n.startswith('ssept_')]        # ACSSEPT cases (acssept.py on transformer_layers.py)
 BERT = [n for n in EVERY if n.startswith('bert_')]          # AcBERT4Rec cases (acbert4rec.py)
 TRAIN = [n for n in ALL if '_train' in n]
@@ -748,6 +749,96 @@ def test_ssept_trainer_epoch_and_eval(A, tmp_path):
     assert float((model.user_embedding.weight.detach() - before_u).abs().max()) > 0       # trained through the input concat
     assert all(np.isfinite(v) for v in result.values()) and 'hit@10' in result
     # the graphed evaluation and the eager one agree
+    model.eval()
+    batch = next(iter(A.data.FullSortEvalDataLoader(config, valid_ds)))
+    rec_g = trainer.eval_batch(batch).cpu()
+    trainer.use_graph = False
+    rec_e = trainer.eval_batch(batch).cpu()
+    assert torch.equal(rec_g, rec_e)
+
+
+# ---- ACTiSASRec: goldens from the real reference (tests/golden/make_golden.py: make_ti_case) ----
+def build_ti(A, c, **extra):
+    config = make_config(A, dict(c['cfg']), TIME_FIELD='timestamp', **extra)
+    config['model'] = 'ACTiSASRec'
+    model = A.ACTiSASRec(config, DS(c['V'])).to('cuda')
+    model.load_state_dict({k: v.cuda() for k, v in c['params'].items()}, strict=True)      # reference state_dict loads unchanged
+    model._debug_rand = {k: v.cuda() for k, v in c['rand'].d.items()}
+    return config, model
+
+
+def ti_inter(A, c):
+    inter = inter_of(A, c)
+    inter.interaction['timestamp_list'] = c['batch']['time'].cuda()
+    return inter
+
+
+@pytest.mark.parametrize('name', [n for n in TI if '_train' in n])
+def test_ti_golden_train_losses_and_routed_grads(A, name):
+    c = load_case(name)
+    z = c['z']
+    config, model = build_ti(A, c)
+    model.train()
+    l_att, l_cal = model.calculate_loss(ti_inter(A, c))
+    assert abs(float(l_att) - float(z['loss_att'])) < 1e-4 * abs(float(z['loss_att']))
+    assert abs(float(l_cal) - float(z['loss_cal'])) < 1e-4 * abs(float(z['loss_cal']))
+    for n, p in model.named_parameters():
+        p.requires_grad = not ('attack_key_transform' in n or 'attack_query_transform' in n)
+    l_cal.backward(retain_graph=True)
+    for n, p in model.named_parameters():
+        p.requires_grad = ('attack_key_transform' in n or 'attack_query_transform' in n)
+    l_att.backward()
+    assert set(n for n, _ in model.named_parameters()) == set(c['grads'])
+    for n, p in model.named_parameters():
+        ref = c['grads'][n]
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(ref)
+        scale = float(ref.abs().max())
+        err = float((got - ref).abs().max())
+        assert err <= 1e-3 * scale + 1e-8, (n, err, scale)
+
+
+@pytest.mark.parametrize('name', [n for n in TI if '_eval' in n])
+def test_ti_golden_eval(A, name):
+    c = load_case(name)
+    z = c['z']
+    config, model = build_ti(A, c)
+    model.eval()
+    inter = ti_inter(A, c)
+    with torch.no_grad():
+        tm = model.get_time_matrix(inter['timestamp_list'])
+        att, cal, masks = model.forward(inter['item_id_list'], inter['item_length'], tm)
+        assert rel(att, z['out_att']) < 1e-4 and rel(cal, z['out_cal']) < 1e-4
+        for l, m in enumerate(masks):
+            assert rel(m.pen_sq, z['pen_sq.%d' % l]) < 1e-5
+        sa, sc = model.full_sort_predict(inter)
+        assert rel(sc, z['scores']) < 1e-4 and rel(sa, z['scores_att']) < 1e-4
+        val, idx, rec = model.full_sort_topk(inter, c['k'], inter['item_id'])
+        ok, nbad = O.topk_equal_modulo_ties(idx.cpu(), torch.from_numpy(z['topk_idx']), torch.from_numpy(z['scores']))
+        assert ok, nbad
+        pa, pc = model.predict(inter)
+        assert rel(pa, z['predict_att']) < 1e-4 and rel(pc, z['predict_cal']) < 1e-4
+
+
+def test_ti_trainer_epoch_and_eval(A, tmp_path):
+    """ACTiSASRecTrainer: Philox dropout of the time-aware terms, routed double backward, graphed full-sort evaluation"""
+    cfg = O.default_cfg(n_layers=2)
+    cfg.update(time_span=64, TIME_FIELD='timestamp')
+    V = 200
+    config = make_config(A, cfg, checkpoint_dir=str(tmp_path), epochs=1, train_batch_size=32, eval_batch_size=32, cuda_graph=True)
+    config['model'] = 'ACTiSASRec'
+    torch.manual_seed(0)
+    train_ds = A.data.SyntheticSequentialDataset(config, 32 * 3, V, seed=1)
+    valid_ds = A.data.SyntheticSequentialDataset(config, 64, V, seed=2)
+    model = A.ACTiSASRec(config, train_ds).to('cuda')
+    trainer = A.ACTiSASRecTrainer(config, model)
+    assert trainer.fused is None
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    score, result = trainer.fit(A.data.TrainDataLoader(config, train_ds, shuffle=True), A.data.FullSortEvalDataLoader(config, valid_ds),
+                                verbose=False, saved=True)
+    for n in ('item_embedding.weight', 'time_matrix_emb_K_embedding.weight', 'time_matrix_emb_V_embedding.weight',
+              'absolute_pos_K_embedding.weight', 'absolute_pos_V_embedding.weight'):
+        assert float((dict(model.named_parameters())[n].detach() - before[n]).abs().max()) > 0, n
+    assert all(np.isfinite(v) for v in result.values()) and 'hit@10' in result
     model.eval()
     batch = next(iter(A.data.FullSortEvalDataLoader(config, valid_ds)))
     rec_g = trainer.eval_batch(batch).cpu()
