@@ -61,6 +61,8 @@ class ACSSEPT(SequentialRecommender):
         self.use_distance = config['use_distance']
         self.trainable_mask_loss_weight = config['trainable_mask_loss_weight']
         self.n_users = dataset.num(self.USER_ID)
+        self.EXTRA_FIELDS = [self.USER_ID]                 # read by the training step besides sequence / length / target
+        self.GRAPH_SAFE_STEP = True                      # no host-side work in the step: the trainer may capture it in a CUDA graph
         self.EVAL_FIELDS = [self.ITEM_SEQ, self.ITEM_SEQ_LEN, self.USER_ID]      # what an evaluation batch must carry
 
         self.user_embedding = nn.Embedding(self.n_users, self.user_hidden_size, padding_idx=0)         # concatenated to item_seq

@@ -41,6 +41,8 @@ class ACTiSASRec(SequentialRecommender):
         self.use_order = config['use_order']
         self.use_distance = config['use_distance']
         self.trainable_mask_loss_weight = config['trainable_mask_loss_weight']
+        self.EXTRA_FIELDS = [self.timestamp]                 # read by the training step besides sequence / length / target
+        self.GRAPH_SAFE_STEP = True                      # no host-side work in the step: the trainer may capture it in a CUDA graph
         self.EVAL_FIELDS = [self.ITEM_SEQ, self.ITEM_SEQ_LEN, self.timestamp]   # what an evaluation batch must carry
 
         self.item_embedding = nn.Embedding(self.n_items, self.hidden_size, padding_idx=0)

@@ -330,7 +330,7 @@ class ACSASRecTrainer(object):
         f = [m.ITEM_SEQ, m.ITEM_SEQ_LEN, m.POS_ITEM_ID]
         if m.loss_type == 'BPR':
             f.append(m.NEG_ITEM_ID)
-        return f
+        return f + [k for k in getattr(m, 'EXTRA_FIELDS', []) if k not in f]      # ACSSEPT: user id; ACTiSASRec: time stamps
 
     def _capture(self, interaction=None, loader=None):
         """capture the whole step as one CUDA graph.  interaction: the batch arrives by a copy into the static input buffers
@@ -341,8 +341,13 @@ class ACSASRecTrainer(object):
         if loader is not None:
             lay, total = loader.layout()
         else:
-            lay, total = PackedInteraction.layout_of({k: interaction[k] for k in self._fields()})
-        static_inter = PackedInteraction(torch.empty(total, dtype=torch.int64, device=dev), lay)
+            lay, total = None, 0
+            if all(interaction[k].dtype == torch.int64 for k in self._fields()):
+                lay, total = PackedInteraction.layout_of({k: interaction[k] for k in self._fields()})
+        if loader is None and lay is None:        # a float field (ACTiSASRec's time stamps): one static tensor per field
+            static_inter = Interaction({k: torch.empty_like(interaction[k], device=dev) for k in self._fields()})
+        else:
+            static_inter = PackedInteraction(torch.empty(total, dtype=torch.int64, device=dev), lay)
         static = {k: static_inter[k] for k in self._fields()}
         if loader is None:
             for k in static:
@@ -390,7 +395,7 @@ class ACSASRecTrainer(object):
     def _host_schedule(self):
         """combine_option 'annealing' (layers.py:889-891): the mixing rate exp(-anneal_step / 1e5) is a host float that changes
         with EVERY forward, train or eval.  A captured graph would freeze it, so such models always launch eagerly."""
-        enc = getattr(self.model, 'trm_encoder', None)
+        enc = getattr(self.model, 'trm_encoder', None) or getattr(self.model, 'ti_trm_encoder', None)
         return enc is not None and any(getattr(l, 'combine_option', None) == 'annealing' for l in enc.layer)
 
     def graphed_step(self, interaction):
@@ -404,7 +409,7 @@ class ACSASRecTrainer(object):
                 return self._step_body(interaction.to(self.device))      # ragged last batch: eager launch
             self._capture(interaction)
         si = self._graph['static_inter']
-        if getattr(interaction, 'layout', None) == si.layout:
+        if getattr(interaction, 'layout', None) == getattr(si, 'layout', ()):
             si.packed.copy_(interaction.packed, non_blocking=True)          # packed batch: one copy
         else:
             st = self._graph['static']
@@ -423,8 +428,11 @@ class ACSASRecTrainer(object):
         self.model.train()
         tot_a = torch.zeros((), dtype=torch.float64, device=self.device)
         tot_c = torch.zeros((), dtype=torch.float64, device=self.device)
-        graph_ok = self.use_graph and self.fused is not None and isinstance(self.optimizer, FlatAdam) and not self.clip_grad_norm
-        if (getattr(train_data, 'device_resident', False) and graph_ok and not self._host_schedule()
+        # the captured step: AC-SASRec's fused one-pass step, or -- for sibling models whose step has no host-side work
+        # (GRAPH_SAFE_STEP) -- the autograd Functions' forward + routed double backward + Adam as they launch
+        graph_ok = (self.use_graph and (self.fused is not None or getattr(self.model, 'GRAPH_SAFE_STEP', False))
+                    and isinstance(self.optimizer, FlatAdam) and not self.clip_grad_norm)
+        if (getattr(train_data, 'device_resident', False) and graph_ok and self.fused is not None and not self._host_schedule()
                 and train_data.L <= 64 and train_data.full_batches > 0):
             # HBM-resident data (f-2): the epoch is graph replays + one eager step for the ragged tail
             train_data.new_epoch()

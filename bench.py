@@ -558,6 +558,9 @@ def run_ours(args):
     large = None
     if world == 1 and not args.no_large_batch and args.workload == 'c2' and args.batch == 0:
         large = large_batch_record(A, dev, cfg, 2048, L, V, max(10, K // 4), flush)
+    siblings = None
+    if world == 1 and not args.no_siblings and args.workload == 'c2' and args.batch == 0:
+        siblings = sibling_models_record(A, dev, B, L, V, max(10, K // 5))
     cpu = eager = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(cfg, B if args.workload == 'c2' else min(B, 32), L, V, budget_s=20.0)
@@ -598,6 +601,8 @@ def run_ours(args):
         line['parity'] = parity
     if large is not None:
         line['large_batch'] = large
+    if siblings is not None:
+        line['sibling_models'] = siblings
     if sharded is not None:
         line['vocab_sharded'] = sharded
     if longseq is not None:
@@ -843,6 +848,111 @@ def _timed_cpu(step, budget_s, max_n):
     return n, time.time() - t0
 
 
+def sibling_models_record(A, dev, B, L, V, K):
+    """the sibling AC models on the same kernels, at the headline shape (C2: V, B, L of the workload, d = 64,
+    2 layers, 2 heads).  Train step = calculate_loss + the two routed backward passes + fused Adam through the autograd Functions
+    (eager launches; the fused one-pass step is AC-SASRec's), eval = the trainer's graphed full-sort batch.  Device-timed.  Next
+    to each: the oracle port of the reference's CPU step on a bounded batch, all host threads."""
+    from oracle import acsr_oracle as O
+    out = {}
+    base = model_cfg()
+    base.update(n_layers=2, n_heads=2, hidden_size=64, inner_size=256, MAX_ITEM_LIST_LENGTH=L)
+    common = dict(USER_ID_FIELD='user_id', ITEM_ID_FIELD='item_id', LIST_SUFFIX='_list', ITEM_LIST_LENGTH_FIELD='item_length',
+                  NEG_PREFIX='neg_', TIME_FIELD='timestamp', device=dev, seed=42, learning_rate=1e-4, epochs=1, train_batch_size=B,
+                  eval_batch_size=B, topk=[1, 3, 5, 10, 20, 50], metrics=['Hit', 'MRR', 'NDCG'], valid_metric='Hit@10',
+                  checkpoint_dir='/tmp/acsr_bench_ckpt', cuda_graph=True, logits_passes=3)
+    specs = [
+        ('AcBERT4Rec', dict(combine_option='fixed', mask_ratio=0.2, MAX_ITEM_LIST_LENGTH=L - 1), A.AcBERT4Rec, A.AcBERT4RecTrainer),
+        ('ACSSEPT', dict(user_hidden_size=32, item_hidden_size=32), A.ACSSEPT, A.ACSSEPTTrainer),
+        ('ACTiSASRec', dict(time_span=256), A.ACTiSASRec, A.ACTiSASRecTrainer),
+    ]
+    Bc = 32                                    # rows of the CPU sample
+    for name, extra, Model, Trainer in specs:
+        try:
+            d = dict(base)
+            d.update(common)
+            d.update(extra)
+            config = A.Config(model=name, config_dict=d)
+            config['model'] = name
+            Lm = d['MAX_ITEM_LIST_LENGTH']
+            ds = A.data.SyntheticSequentialDataset(config, 2 * B, V, seed=77, pin=False)
+            torch.manual_seed(42)
+            model = Model(config, ds).to(dev)
+            trainer = Trainer(config, model)
+            feat = ds.inter_feat
+            batches = [A.Interaction({k: v[i * B:(i + 1) * B].to(dev) for k, v in feat.interaction.items()}) for i in range(2)]
+            it = [0]
+
+            graphed = bool(getattr(model, 'GRAPH_SAFE_STEP', False))
+
+            def eager_step():
+                trainer.train_step(batches[it[0] % 2])
+                it[0] += 1
+
+            def step():
+                if graphed:
+                    trainer.graphed_step(batches[it[0] % 2])      # the captured step: batch copied into the static buffers + replay
+                    it[0] += 1
+                else:
+                    eager_step()
+
+            def ev():
+                b = batches[it[0] % 2]
+                with torch.no_grad():
+                    trainer.eval_batch((b, None, None, b['item_id']))
+                it[0] += 1
+
+            def timed(fn, n):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / n
+            model.train()
+            for _ in range(3):
+                step()
+            ms = timed(step, K)
+            ms_eager = timed(eager_step, K) if graphed else ms
+            model.eval()
+            for _ in range(3):
+                ev()
+            ms_eval = timed(ev, K)
+            # CPU: the oracle restatement of this model's reference step on Bc rows
+            torch.set_num_threads(os.cpu_count() or 1)
+            cfg = {k: d[k] for k in base}
+            cfg.update({k: v for k, v in extra.items()})
+            params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+            seq, ln, tgt = (feat[k][:Bc] for k in ('item_id_list', 'item_length', 'item_id'))
+            rnd = O.draw_rand(dict(cfg, hidden_size=model.hidden_size), Bc, Lm, 5)
+            if name == 'AcBERT4Rec':
+                import random
+                random.seed(1)
+                ms_, pi_, _, mi_ = model.reconstruct_train_data(seq)
+                cpu_fn = lambda: O.bert_train_grads(params, cfg, ms_, pi_, mi_, rnd)
+            elif name == 'ACSSEPT':
+                cpu_fn = lambda: O.ssept_train_grads(params, cfg, seq, ln, feat['user_id'][:Bc], tgt, rnd)
+            else:
+                cpu_fn = lambda: O.ti_train_grads(params, cfg, seq, ln, feat['timestamp_list'][:Bc], tgt, rnd)
+            cpu_fn()
+            n, dt = _timed_cpu(cpu_fn, 4.0, 3)
+            out[name] = {'train': {'value': round(B / (ms / 1e3), 1), 'unit': 'seq/s', 'ms_per_step': round(ms, 3),
+                                   'eager_ms_per_step': round(ms_eager, 3),
+                                   'launch': 'CUDA graph replay of the autograd step' if graphed else 'eager launches (host-side masking, acbert4rec.py:86-150, is part of the step)'},
+                         'eval': {'value': round(B / (ms_eval / 1e3), 1), 'unit': 'users/s', 'ms_per_batch': round(ms_eval, 3)},
+                         'cpu_baseline': {'value': round(Bc * n / dt, 2), 'unit': 'seq/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                          'sample': '%d oracle training steps (gradients, no optimizer) of B=%d' % (n, Bc)},
+                         'config': 'V=%d B=%d L=%d hidden=%d layers=2 heads=2 %s' % (V, B, Lm, model.hidden_size, extra)}
+            del trainer, model
+            torch.cuda.empty_cache()
+        except Exception as e:                                          # a sub-record must never sink the bench line
+            out[name] = {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+    out['launch'] = 'train: the autograd Functions (routed double backward) + fused Adam; eval: CUDA graph replay'
+    return out
+
+
 def cpu_baseline(cfg, B, L, V, budget_s=20.0):
     torch.set_num_threads(os.cpu_count() or 1)
     n, dt = _timed_cpu(oracle_step_fn(cfg, B, L, V), budget_s, 10)
@@ -907,6 +1017,7 @@ def main():
     ap.add_argument('--no-parity', action='store_true', help='skip the in-run parity check against the CPU oracle')
     ap.add_argument('--no-large-batch', action='store_true', help='skip the B=2048 sub-record')
     ap.add_argument('--no-vocab-sharded', action='store_true', help='skip the 1M-item vocab-sharded sub-record')
+    ap.add_argument('--no-siblings', action='store_true', help='skip the sibling-model (AcBERT4Rec / ACSSEPT / ACTiSASRec) sub-record')
     ap.add_argument('--no-long-seq', action='store_true', help='skip the long-sequence (config #5) sub-record')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS), help='c2 = the headline configuration (default)')
     ap.add_argument('--full-len', action='store_true', help='every sequence has the maximum length (worst case) instead of LogNormal lengths')
