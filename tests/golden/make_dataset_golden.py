@@ -50,7 +50,7 @@ def main():
         train, valid, test = dataset.build()
         rec = {'user_num': int(dataset.user_num), 'item_num': int(dataset.item_num), 'config': extra}
         for part, ds in (('train', train), ('valid', valid), ('test', test)):
-            for f in ('user_id', 'item_id', 'item_length', 'item_id_list'):
+            for f in ('user_id', 'item_id', 'item_length', 'item_id_list', 'timestamp_list'):     # timestamp_list: read by ACTiSASRec only
                 rec['%s.%s' % (part, f)] = digest(ds.inter_feat[f])
         rec['item_token_sha256'] = hashlib.sha256('\n'.join(dataset.field2id_token['item_id']).encode()).hexdigest()
         out[name] = rec

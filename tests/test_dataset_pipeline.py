@@ -28,6 +28,20 @@ def digest(t):
 
 
 @pytest.mark.parametrize('name', sorted(REF))
+def test_timestamp_list_matches_reference_pipeline(name):
+    """ACTiSASRec reads `timestamp_list` (actisasrec.py:35, 177): emitted for that model only, bit-identical to the reference's
+    augmentation (sequential_dataset.py:112-135)"""
+    ref = REF[name]
+    config = make_config(ref['config'])
+    assert 'timestamp_list' not in A.create_dataset(config).build()[0].inter_feat
+    config['model'] = 'ACTiSASRec'
+    parts = dict(zip(('train', 'valid', 'test'), A.create_dataset(config).build()))
+    for part, d in parts.items():
+        assert digest(d.inter_feat['timestamp_list']) == ref['%s.timestamp_list' % part], part
+        assert digest(d.inter_feat['item_id_list']) == ref['%s.item_id_list' % part], part
+
+
+@pytest.mark.parametrize('name', sorted(REF))
 def test_dataset_matches_reference_pipeline(name):
     ref = REF[name]
     config = make_config(ref['config'])

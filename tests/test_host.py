@@ -286,3 +286,42 @@ def test_bert_masking_follows_the_reference_procedure():
     assert seq.shape[1] == b['item_seq'].shape[1] + 1
     assert torch.equal(seq, O.bert_test_sequence(b['item_seq'], b['item_len'], c['V']))
     assert set(model.state_dict()) == set(c['params'])
+
+
+def test_sibling_models_keep_reference_state_dicts_and_have_no_cpu_path():
+    """ACSSEPT / ACTiSASRec: parameter names and shapes are those of the reference's checkpoints (goldens made by
+    the real reference), get_model / get_trainer style lookup by name works, and CPU tensors raise instead of falling back"""
+    from ac_tsr_b200.quick_start import _MODELS
+
+    class DSU:
+        def __init__(self, n_items, n_users):
+            self.n_items, self.n_users = n_items, n_users
+
+        def num(self, field):
+            return self.n_users if field == 'user_id' else self.n_items
+    for name in sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))):
+        if not name.startswith(('ssept_', 'ti_')):
+            continue
+        c = load_case(name)
+        cls_name = 'ACSSEPT' if c['ssept'] else 'ACTiSASRec'
+        Model, Trainer = _MODELS[cls_name]
+        assert Model.__name__ == cls_name and Trainer.__name__ == cls_name + 'Trainer'
+        cfg = cfg_for(**{k: c['cfg'][k] for k in c['cfg']})
+        cfg['TIME_FIELD'] = 'timestamp'
+        model = Model(cfg, DSU(c['V'], int(c['z']['U']) if c['ssept'] else 0))
+        own = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        ref = {k: tuple(v.shape) for k, v in c['params'].items()}
+        assert own == ref, name
+        model.load_state_dict(c['params'], strict=True)
+        b = c['batch']
+        f = {'item_id_list': b['item_seq'], 'item_length': b['item_len'], 'item_id': b['pos']}
+        if c['ssept']:
+            f['user_id'] = b['user']
+        else:
+            f['timestamp_list'] = b['time']
+        with pytest.raises(A.AcsrError, match='CUDA'):
+            model.full_sort_predict(A.Interaction(f))
+    # the gate of the transformer_layers.py encoder is 50 wide whatever the sequence length (transformer_layers.py:891)
+    enc = A.transformer_layers.AttackRTransformerEncoder(n_layers=1, hidden_size=32, inner_size=32, combine_option='gate')
+    assert enc.layer[0].gate.out_features == 50 and enc.layer[0].plain_variant
+    assert not A.layers.AttackRTransformerEncoder(n_layers=1, hidden_size=32, inner_size=32).layer[0].plain_variant
