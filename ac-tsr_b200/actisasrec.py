@@ -108,7 +108,10 @@ class ACTiSASRec(SequentialRecommender):
         p = self.dropout.p if self.training else 0.0
         x = ops.EmbedLnDropoutFn.apply(item_seq, self.item_embedding.weight, None, self.LayerNorm.weight, self.LayerNorm.bias,
                                        self.LayerNorm.eps, p, rt.mask('emb') if p > 0 else None, rt.rng, 1)
-        tt = TimeTerms(self.absolute_pos_K_embedding.weight[:L], self.absolute_pos_V_embedding.weight[:L],
+        pk, pv = self.absolute_pos_K_embedding.weight, self.absolute_pos_V_embedding.weight
+        if L != pk.size(0):                # (the reference only runs L == MAX_ITEM_LIST_LENGTH, actisasrec.py:149-150)
+            pk, pv = pk[:L], pv[:L]
+        tt = TimeTerms(pk, pv,
                        self.time_matrix_emb_K_embedding.weight, self.time_matrix_emb_V_embedding.weight,
                        time_matrix.to(torch.int32), self.n_heads, p, rt)
         masks, att, cal = [], None, None

@@ -34,6 +34,14 @@ def _c(t):
     return None if t is None else t.contiguous()
 
 
+def _wants_grad(t):
+    """False only for a LEAF tensor whose requires_grad is off right now.  The reference trainer routes its two backward passes by
+    toggling requires_grad on the parameters between them (trainer.py:672-686): the graph was built with every parameter
+    trainable, so ctx.needs_input_grad still says True, but autograd drops a gradient that arrives at a leaf with
+    requires_grad False -- computing it would be wasted work (half of all weight-gradient launches of a step)."""
+    return t is not None and (t.requires_grad or not t.is_leaf)
+
+
 class DeviceRng:
     """{seed, step} in device memory; kernels read it so CUDA-graph replays draw fresh masks."""
 
@@ -69,6 +77,8 @@ class EmbedLnDropoutFn(torch.autograd.Function):
     def backward(ctx, d_out):
         item_seq, table, pos_emb, ln_w, stats, mask = ctx.saved_tensors
         B, L, d, V, p, rng, rng_stream = ctx.meta
+        if not (_wants_grad(table) or _wants_grad(pos_emb) or _wants_grad(ln_w)):      # the attacked-loss pass of the routed backward
+            return None, None, None, None, None, None, None, None, None, None
         d_out = d_out.contiguous()
         d_table = torch.zeros_like(table)
         d_pos = torch.zeros_like(pos_emb) if pos_emb is not None else None
@@ -314,7 +324,7 @@ class PairScoreFn(torch.autograd.Function):
         ds = (torch.tril(ds) if ctx.causal else ds).contiguous()       # pairs j > i were not computed: they carry no gradient
         dx = _pair_context(ds, P, T, ctx.spec, x.shape[-1]) if ctx.needs_input_grad[0] else None
         dP = dT = None
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+        if (ctx.needs_input_grad[1] and _wants_grad(P)) or (ctx.needs_input_grad[2] and _wants_grad(T)):
             dP, dT = _pair_wgrad(ds, x, P, T, ctx.spec)
         return dx, dP, dT, None, None
 
@@ -335,7 +345,7 @@ class PairContextFn(torch.autograd.Function):
         dy = dy.contiguous()
         dprob = _pair_score(dy, P, T, ctx.spec, 0) if ctx.needs_input_grad[0] else None
         dP = dT = None
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+        if (ctx.needs_input_grad[1] and _wants_grad(P)) or (ctx.needs_input_grad[2] and _wants_grad(T)):
             dP, dT = _pair_wgrad(prob, dy, P, T, ctx.spec)
         return dprob, dP, dT, None
 
@@ -516,6 +526,7 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias
         N, K = weight.shape
         x2 = x.reshape(-1, K)
         if not x2.is_contiguous():
@@ -539,7 +550,7 @@ class LinearFn(torch.autograd.Function):
             dx = torch.empty((rows, K), dtype=torch.float32, device=dy.device)
             gemm_batch([gemm_problem(dy2, w, dx, rows, K, N, b_strides=(1, K, 0, N))])      # dx = dy.W: weight read transposed
             dx = dx.view_as(x)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        if (ctx.needs_input_grad[1] and _wants_grad(weight)) or (ctx.has_bias and ctx.needs_input_grad[2] and _wants_grad(ctx.bias_ref)):
             x2 = x.reshape(-1, K)
             if not x2.is_contiguous():
                 x2 = x2.contiguous()
@@ -615,7 +626,7 @@ class LogitsCEFn(torch.autograd.Function):
         if d == 64:
             if ctx.needs_input_grad[0]:
                 d_out = ce_bwd_dout(out, table, lse, target, row_scale, torch.zeros((M, d), dtype=torch.float32, device=out.device), passes)
-            if ctx.needs_input_grad[1]:
+            if ctx.needs_input_grad[1] and _wants_grad(table):
                 d_table = ce_bwd_dtable(out, table, lse, target, row_scale, torch.zeros((V, d), dtype=torch.float32, device=out.device), passes)
             return d_out, d_table, None, None, None, None
         Gt = ce_grad_matrix_t(out, table, lse, target, row_scale, passes)
@@ -623,7 +634,7 @@ class LogitsCEFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:            # d_out [M,d] = Gt^T . E : contraction over the catalogue, split over the CTAs
             d_out = torch.zeros((M, d), dtype=torch.float32, device=out.device)
             pr.append(wgrad_problem(Gt, table, V, M, d, d_out))
-        if ctx.needs_input_grad[1]:            # d_E [V,d] = Gt . out
+        if ctx.needs_input_grad[1] and _wants_grad(table):            # d_E [V,d] = Gt . out
             d_table = torch.empty((V, d), dtype=torch.float32, device=out.device)
             pr.append(gemm_problem(Gt, out, d_table, V, d, M, b_strides=(1, d, 0, M)))
         if pr:
