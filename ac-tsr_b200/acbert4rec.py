@@ -70,6 +70,10 @@ class AcBERT4Rec(SequentialRecommender):
         self._rng = None
         self._debug_rand = None            # explicit dropout masks / noise (parity tests)
         self._debug_masked = None          # explicit (masked_item_seq, pos_items, neg_items, masked_index) (parity tests)
+        # the training step split for the trainer's CUDA graph: prepare_batch (host: the reference's python masking) fills these
+        # fields, the rest of the step (calculate_loss on them + routed backward + Adam) has no host-side work
+        self.EXTRA_FIELDS = ['bert_masked_seq', 'bert_pos_items', 'bert_neg_items', 'bert_masked_index']
+        self.GRAPH_SAFE_STEP = True
         self.apply(self._init_weights)
 
     def _init_weights(self, module):
@@ -116,6 +120,15 @@ class AcBERT4Rec(SequentialRecommender):
         def t(x):
             return torch.tensor(x, dtype=torch.long, device=device).view(batch_size, -1)
         return t(masked_item_sequence), t(pos_items), t(neg_items), t(masked_index)
+
+    def prepare_batch(self, interaction):
+        """host half of the training step: reconstruct_train_data (acbert4rec.py:86-150, python `random`, one call per step as in the
+        reference) -> the interaction plus the four masked tensors, which calculate_loss then takes as given"""
+        from .compat import Interaction
+        masked = self.reconstruct_train_data(interaction[self.ITEM_SEQ])
+        fields = {k: interaction[k] for k in (self.ITEM_SEQ, self.ITEM_SEQ_LEN, self.POS_ITEM_ID)}
+        fields.update(zip(self.EXTRA_FIELDS, masked))
+        return Interaction(fields)
 
     def reconstruct_test_data(self, item_seq, item_seq_len):
         """mask token appended at position item_seq_len of a sequence one longer (acbert4rec.py:152-160), vectorised"""
@@ -170,6 +183,8 @@ class AcBERT4Rec(SequentialRecommender):
         item_seq = interaction[self.ITEM_SEQ]
         if self._debug_masked is not None:
             masked_item_seq, pos_items, neg_items, masked_index = self._debug_masked
+        elif self.EXTRA_FIELDS[0] in interaction:          # prepared on the host by prepare_batch (the trainer's graphed step)
+            masked_item_seq, pos_items, neg_items, masked_index = (interaction[k] for k in self.EXTRA_FIELDS)
         else:
             masked_item_seq, pos_items, neg_items, masked_index = self.reconstruct_train_data(item_seq)
         attacked_output, calibrated_output, all_attack_masks = self.forward(masked_item_seq)

@@ -54,6 +54,9 @@ __device__ __forceinline__ void stage_pos(const PairSpec& s, int b, float* Ps, f
   }
 }
 
+// thread per (i, j) pair.  (A variant with d/4 lanes per pair -- coalesced reads of the interval-table row, shuffle reductions per
+// head -- measured 2x SLOWER on B200, 156 vs 79 us at B=256, L=50, d=64: with one pair in flight per lane the dependent chain
+// t_ij -> table row -> FMA is exposed, while here a thread has the 16 row loads of its pair in flight at once.)
 __global__ void __launch_bounds__(kPairThreads) pair_score_kernel(const PairSpec s, const float* __restrict__ x, float* __restrict__ out, int causal) {
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x, L = s.L, d = s.d, dp = d + 4;

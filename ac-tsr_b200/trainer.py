@@ -404,6 +404,10 @@ class ACSASRecTrainer(object):
         if self._host_schedule() or int(interaction[self.model.ITEM_SEQ].shape[1]) > 64:
             # annealing: see _host_schedule; sequences longer than 64: the attention backward's workspace may have to grow
             return self._step_body(interaction.to(self.device))
+        if self.fused is None and hasattr(self.model, 'prepare_batch'):
+            if self._graph is not None and self._graph['key'][0][1] != tuple(interaction[self.model.ITEM_SEQ].shape):
+                return self._step_body(interaction.to(self.device))      # ragged last batch: eager launch (masks itself)
+            interaction = self.model.prepare_batch(interaction)          # host half of the step (AcBERT4Rec's python masking)
         if self._graph is None or self._graph['key'] != self._graph_key(interaction):
             if self._graph is not None:
                 return self._step_body(interaction.to(self.device))      # ragged last batch: eager launch

@@ -847,15 +847,17 @@ def test_ti_trainer_epoch_and_eval(A, tmp_path):
     assert torch.equal(rec_g, rec_e)
 
 
-@pytest.mark.parametrize('name', ['ACSSEPT', 'ACTiSASRec'])
+@pytest.mark.parametrize('name', ['ACSSEPT', 'ACTiSASRec', 'AcBERT4Rec'])
 def test_sibling_graphed_step_matches_eager(A, tmp_path, name):
     """sibling models with no host-side work in the step are captured in a CUDA graph by the trainer (forward + routed double
     backward + Adam through the autograd Functions); three graphed steps leave the same parameters as three eager ones"""
     cfg = O.default_cfg(n_layers=2)
-    cfg.update(time_span=64, TIME_FIELD='timestamp', user_hidden_size=32, item_hidden_size=32)
+    cfg.update(time_span=64, TIME_FIELD='timestamp', user_hidden_size=32, item_hidden_size=32, mask_ratio=0.2)
     V, B = 300, 32
     finals = []
     for use_graph in (True, False):
+        import random
+        random.seed(11)                        # AcBERT4Rec: the host-side masking stream (one reconstruct_train_data per step either way)
         config = make_config(A, cfg, checkpoint_dir=str(tmp_path), train_batch_size=B, eval_batch_size=B, cuda_graph=use_graph)
         config['model'] = name
         ds = A.data.SyntheticSequentialDataset(config, 3 * B, V, seed=4)
