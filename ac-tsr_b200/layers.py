@@ -151,6 +151,28 @@ class AttackRTransformerLayer(nn.Module):
         self.feed_forward = FeedForward(hidden_size, intermediate_size, hidden_dropout_prob, hidden_act, layer_norm_eps)
         self.anneal_step = 0
 
+    def _dense_pair(self, ctx_cal, ctx_att, x, rt, layer_idx, base):
+        """cal_adjusted_outputs + feed_forward (layers.py:676-684, 790-798) of the calibrated and the attacked stream, the two
+        streams sharing each GEMM launch; same dropout keys / Philox streams as the one-stream methods -> (cal_out, att_out)"""
+        aa, ff = self.attack_attention, self.feed_forward
+        training = self.training
+        p_out = aa.out_dropout.p if training else 0.0
+        p_ff = ff.dropout.p if training else 0.0
+        act = ops.ACT_IDS[ff.hidden_act]
+
+        def bdrl(h, bias, res, ln, p, key, stream):
+            return ops.BiasDropoutResLnFn.apply(h, bias, res, ln.weight, ln.bias, ln.eps, p, rt.mask((layer_idx, key)) if p > 0 else None,
+                                                rt.rng, stream)
+        h_cal, h_att = ops.multi_linear([ctx_cal, ctx_att], [aa.dense.weight, aa.dense.weight])
+        a_cal = bdrl(h_cal, aa.dense.bias, x, aa.LayerNorm, p_out, 'D5', base + 3)
+        a_att = bdrl(h_att, aa.dense.bias, x, aa.LayerNorm, p_out, 'D4', base + 2)
+        z_cal, z_att = ops.multi_linear([a_cal, a_att], [ff.dense_1.weight, ff.dense_1.weight])
+        z_cal = ops.BiasActFn.apply(z_cal, ff.dense_1.bias, act)
+        z_att = ops.BiasActFn.apply(z_att, ff.dense_1.bias, act)
+        o_cal, o_att = ops.multi_linear([z_cal, z_att], [ff.dense_2.weight, ff.dense_2.weight])
+        return (bdrl(o_cal, ff.dense_2.bias, a_cal, ff.LayerNorm, p_ff, 'D7', base + 5),
+                bdrl(o_att, ff.dense_2.bias, a_att, ff.LayerNorm, p_ff, 'D6', base + 4))
+
     def forward(self, hidden_states, attention_mask, return_attention_prob=False, return_all_attention_prob=False,
                 rt=None, layer_idx=0, need_attacked=True, time_terms=None):
         rt = rt or default_runtime(hidden_states.device)
@@ -162,17 +184,20 @@ class AttackRTransformerLayer(nn.Module):
         x = hidden_states
         B, L, d = x.shape
         key_ids = key_ids_from_mask(attention_mask)
-        mq = ops.linear(x, aa.query.weight, aa.query.bias)
-        mk = ops.linear(x, aa.key.weight, aa.key.bias)
-        mv = ops.linear(x, aa.value.weight, aa.value.bias)
-        aq = ops.linear(mq, aa.attack_query_transform.weight, aa.attack_query_transform.bias)
-        ak = ops.linear(mk, aa.attack_key_transform.weight, aa.attack_key_transform.bias)
+        # the three projections of x are one launch, the attack pair (+ the gate) of mixed_q / mixed_k another (ops.MultiLinearFn)
+        mq, mk, mv = ops.multi_linear([x, x, x], [aa.query.weight, aa.key.weight, aa.value.weight],
+                                      [aa.query.bias, aa.key.bias, aa.value.bias])
         gate_logit, comb_scalar = None, 0.0
         if self.combine_option == 'gate':
             if self.gate.out_features != L:
                 raise ValueError('gate width %d != sequence length %d (layers.py:878/887)' % (self.gate.out_features, L))
-            gate_logit = ops.linear(mq, self.gate.weight, self.gate.bias)
-        elif self.combine_option == 'annealing':
+            aq, ak, gate_logit = ops.multi_linear(
+                [mq, mk, mq], [aa.attack_query_transform.weight, aa.attack_key_transform.weight, self.gate.weight],
+                [aa.attack_query_transform.bias, aa.attack_key_transform.bias, self.gate.bias])
+        else:
+            aq, ak = ops.multi_linear([mq, mk], [aa.attack_query_transform.weight, aa.attack_key_transform.weight],
+                                      [aa.attack_query_transform.bias, aa.attack_key_transform.bias])
+        if self.combine_option == 'annealing':
             comb_scalar = math.exp(-self.anneal_step / 100000)      # layers.py:889-891
             self.anneal_step += 1
         base = _stream_base(layer_idx)
@@ -207,12 +232,13 @@ class AttackRTransformerLayer(nn.Module):
             if need_attacked:
                 ctx_att = ctx_att + time_terms.context(prob_att)
             probs = None
-        cal_att_out = aa.cal_adjusted_outputs(ctx_cal, x, rt, (layer_idx, 'D5'), base + 3)
-        cal_out = self.feed_forward(cal_att_out, rt, (layer_idx, 'D7'), base + 5)
         att_out = None
         if need_attacked:
-            att_att_out = aa.cal_adjusted_outputs(ctx_att, x, rt, (layer_idx, 'D4'), base + 2)
-            att_out = self.feed_forward(att_att_out, rt, (layer_idx, 'D6'), base + 4)
+            # both streams go through the same out-projection / feed-forward weights: one launch per GEMM for the pair
+            cal_out, att_out = self._dense_pair(ctx_cal, ctx_att, x, rt, layer_idx, base)
+        else:
+            cal_att_out = aa.cal_adjusted_outputs(ctx_cal, x, rt, (layer_idx, 'D5'), base + 3)
+            cal_out = self.feed_forward(cal_att_out, rt, (layer_idx, 'D7'), base + 5)
         attack_mask = AttackMask(pen_sq, probs[2] if probs is not None else None)
         combined = probs[5] if probs is not None else None
         if return_all_attention_prob:

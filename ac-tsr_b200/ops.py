@@ -564,6 +564,69 @@ def linear(x, weight, bias=None):
     return LinearFn.apply(x, weight, bias)
 
 
+class MultiLinearFn(torch.autograd.Function):
+    """n independent y_i = x_i.W_i^T (+ b_i) as ONE launch of the K-streamed tcgen05 GEMM (a problem list), and in the backward one
+    launch for all input gradients and one for all weight / bias gradients -- the Q/K/V projections, the attack pair + gate,
+    and the attacked / calibrated streams through the same dense or feed-forward weight (layers.py:658-659, 680, 687-689,
+    791-794, 887).  Inputs / weights may repeat; autograd sums the returned gradients."""
+
+    @staticmethod
+    def forward(ctx, n, *args):
+        xs, ws, bs = args[:n], args[n:2 * n], args[2 * n:3 * n]
+        ctx.set_materialize_grads(False)
+        x2s, ys, pr = [], [], []
+        for x, w, b in zip(xs, ws, bs):
+            N, K = w.shape
+            x2 = x.reshape(-1, K)
+            x2 = x2 if x2.is_contiguous() else x2.contiguous()
+            w = w if w.is_contiguous() else w.contiguous()
+            y = torch.empty((x2.shape[0], N), dtype=torch.float32, device=x.device)
+            pr.append(gemm_problem(x2, w, y, x2.shape[0], N, K, bias=b))
+            x2s.append(x2)
+            ys.append(y.view(*x.shape[:-1], N))
+        gemm_batch(pr)
+        ctx.save_for_backward(*x2s, *ws)
+        ctx.n, ctx.bias_refs, ctx.x_shapes = n, bs, [x.shape for x in xs]
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        x2s, ws = saved[:n], saved[n:]
+        dxs, dWs, dbs = [None] * n, [None] * n, [None] * n
+        pr_x, pr_w = [], []
+        for i, dy in enumerate(dys):
+            if dy is None:
+                continue
+            w, b = ws[i], ctx.bias_refs[i]
+            N, K = w.shape
+            dy2 = dy.reshape(-1, N)
+            dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
+            rows = dy2.shape[0]
+            if ctx.needs_input_grad[1 + i]:
+                wc = w if w.is_contiguous() else w.contiguous()
+                dx = torch.empty((rows, K), dtype=torch.float32, device=dy.device)
+                pr_x.append(gemm_problem(dy2, wc, dx, rows, K, N, b_strides=(1, K, 0, N)))
+                dxs[i] = dx.view(ctx.x_shapes[i])
+            if (ctx.needs_input_grad[1 + n + i] and _wants_grad(w)) or (b is not None and ctx.needs_input_grad[1 + 2 * n + i] and _wants_grad(b)):
+                dWs[i] = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
+                dbs[i] = torch.zeros(N, dtype=torch.float32, device=dy.device) if b is not None else None
+                pr_w.append(wgrad_problem(dy2, x2s[i], rows, N, K, dWs[i], dbs[i]))
+        if pr_x:
+            gemm_batch(pr_x)
+        if pr_w:
+            gemm_batch(pr_w)
+        return (None, *dxs, *dWs, *dbs)
+
+
+def multi_linear(xs, weights, biases=None):
+    """[x_i.W_i^T + b_i] as one launch (MultiLinearFn)"""
+    n = len(xs)
+    biases = list(biases) if biases is not None else [None] * n
+    return MultiLinearFn.apply(n, *xs, *weights, *biases)
+
+
 class GatherRowsFn(torch.autograd.Function):
     """rows x[idx] of a [T, d] matrix (AcBERT4Rec: the hidden states of the masked positions, acbert4rec.py:214-222 does it with a
     one-hot bmm); backward: scatter-add of the gradient rows."""
