@@ -42,6 +42,53 @@ def _wants_grad(t):
     return t is not None and (t.requires_grad or not t.is_leaf)
 
 
+_DIRECT_GRAD = [False]
+
+
+class direct_param_grads:
+    """Inside this context the backward kernels accumulate parameter gradients STRAIGHT into `param.grad` when the parameter is a
+    leaf that owns a gradient buffer (the trainer's flat gradient) and return None for it: the kernels add with atomics anyway,
+    so the zero-filled temporary and autograd's `grad += temporary` -- two more launches per parameter and pass -- disappear.
+    The trainer's step uses it; everywhere else (tests, torch.autograd.grad) gradients are returned the usual way."""
+
+    def __enter__(self):
+        self.prev = _DIRECT_GRAD[0]
+        _DIRECT_GRAD[0] = True
+
+    def __exit__(self, *a):
+        _DIRECT_GRAD[0] = self.prev
+
+
+def _grad_sink(t):
+    """the buffer a backward kernel may accumulate t's gradient into directly, or None"""
+    if _DIRECT_GRAD[0] and t is not None and t.is_leaf and t.requires_grad and t.grad is not None and t.grad.is_contiguous():
+        return t.grad
+    return None
+
+
+def _param_grad_buffers(params):
+    """gradient destinations of a backward kernel for the given parameter tensors (None entries allowed) ->
+    (buffers handed to the kernel, gradients returned to autograd).  A parameter whose gradient autograd would drop gets no
+    buffer (the kernels skip NULL destinations); one with a sink accumulates in place; the rest share ONE zero-filled block."""
+    bufs, rets, need = [None] * len(params), [None] * len(params), []
+    for i, t in enumerate(params):
+        if t is None or not _wants_grad(t):
+            continue
+        sink = _grad_sink(t)
+        if sink is not None:
+            bufs[i] = sink
+        else:
+            need.append(i)
+    if need:
+        sizes = [(params[i].numel() + 3) // 4 * 4 for i in need]
+        block = torch.zeros(sum(sizes), dtype=torch.float32, device=params[need[0]].device)
+        off = 0
+        for i, n in zip(need, sizes):
+            bufs[i] = rets[i] = block[off:off + params[i].numel()].view(params[i].shape)
+            off += n
+    return bufs, rets
+
+
 class DeviceRng:
     """{seed, step} in device memory; kernels read it so CUDA-graph replays draw fresh masks."""
 
@@ -104,6 +151,7 @@ class BiasDropoutResLnFn(torch.autograd.Function):
                  rng.ptr if rng is not None else None, rng_stream, _p(out), _p(stats), _stream())
         ctx.save_for_backward(h, bias, res, ln_w, stats, mask)
         ctx.meta = (T, d, p, rng, rng_stream)
+        ctx.ln_b_ref = ln_b
         return out
 
     @staticmethod
@@ -113,12 +161,10 @@ class BiasDropoutResLnFn(torch.autograd.Function):
         d_out = d_out.contiguous()
         d_h = torch.empty_like(h)
         d_res = torch.empty_like(h)
-        d_bias = torch.zeros_like(bias) if bias is not None else None
-        d_w = torch.zeros_like(ln_w)
-        d_b = torch.zeros_like(ln_w)
+        (b_bias, b_w, b_b), (d_bias, d_w, d_b) = _param_grad_buffers([bias, ln_w, ctx.ln_b_ref])
         LIB.call('acsr_bias_dropout_res_ln_bwd', _p(d_out), _p(h), _p(bias), _p(res), _p(ln_w), _p(stats), T, d, T, T, T, p,
-                 _p(mask), rng.ptr if rng is not None else None, rng_stream, _p(d_h), _p(d_res), _p(d_bias), _p(d_w),
-                 _p(d_b), _stream())
+                 _p(mask), rng.ptr if rng is not None else None, rng_stream, _p(d_h), _p(d_res), _p(b_bias), _p(b_w),
+                 _p(b_b), _stream())
         return d_h, d_bias, d_res, d_w, d_b, None, None, None, None, None
 
 
@@ -142,8 +188,8 @@ class BiasActFn(torch.autograd.Function):
         T, n, act = ctx.meta
         d_out = d_out.contiguous()
         d_h = torch.empty_like(h)
-        d_bias = torch.zeros_like(bias) if bias is not None else None
-        LIB.call('acsr_bias_act_bwd', _p(d_out), _p(h), _p(bias), T, n, act, T, T, _p(d_h), _p(d_bias), _stream())
+        (b_bias,), (d_bias,) = _param_grad_buffers([bias])
+        LIB.call('acsr_bias_act_bwd', _p(d_out), _p(h), _p(bias), T, n, act, T, T, _p(d_h), _p(b_bias), _stream())
         return d_h, d_bias, None
 
 
@@ -241,19 +287,17 @@ class AttnCalibFn(torch.autograd.Function):
         z = torch.zeros_like
         d_mq, d_mk, d_mv, d_aq, d_ak = (torch.empty_like(mq) for _ in range(5))
         d_gate = z(gate_logit) if gate_logit is not None else None
-        d_ow = z(order_w) if order_w is not None else None
-        d_ob = z(order_b) if order_b is not None else None
-        d_dw = z(dist_w) if dist_w is not None else None
-        d_db = z(dist_b) if dist_b is not None else None
-        d_sc = z(scalar) if scalar is not None else None
-        d_rr = z(rich_ratio) if rich_ratio is not None else None
+        # the calibrator parameters: straight into their .grad when the trainer asks for it, dropped (NULL) when the routed backward
+        # would discard them, else one shared zero-filled block
+        (b_ow, b_ob, b_dw, b_db, b_sc, b_rr), (d_ow, d_ob, d_dw, d_db, d_sc, d_rr) = _param_grad_buffers(
+            [order_w, order_b, dist_w, dist_b, scalar, rich_ratio])
         attn_workspace(B, L, H, 1, mq.device)
         LIB.call('acsr_attn_calib_bwd', _p(d_att), _p(d_cal), _p(d_pen), _p(mq), _p(mk), _p(mv), _p(aq), _p(ak),
                  _p(gate_logit), _p(key_ids, torch.int64), _p(order_w), _p(order_b), _p(dist_w), _p(dist_b), _p(scalar),
                  B, L, H, dh, opts.two_level, opts.combine, comb_scalar, opts.rich, _p(rich_ratio),
                  p_attn, _p(D1), _p(D2), _p(D3), _p(noise), rng.ptr if rng is not None else None, rng_stream,
-                 _p(d_mq), _p(d_mk), _p(d_mv), _p(d_aq), _p(d_ak), _p(d_gate), _p(d_ow), _p(d_ob), _p(d_dw), _p(d_db),
-                 _p(d_sc), _p(d_rr), None, None, _stream())
+                 _p(d_mq), _p(d_mk), _p(d_mv), _p(d_aq), _p(d_ak), _p(d_gate), _p(b_ow), _p(b_ob), _p(b_dw), _p(b_db),
+                 _p(b_sc), _p(b_rr), None, None, _stream())
         return (d_mq, d_mk, d_mv, d_aq, d_ak, d_gate, None, d_ow, d_ob, d_dw, d_db, d_sc, d_rr,
                 None, None, None, None, None, None, None, None)
 
@@ -392,19 +436,15 @@ class AttnCalibTiFn(torch.autograd.Function):
         z = torch.zeros_like
         d_mq, d_mk, d_mv, d_aq, d_ak = (torch.empty_like(mq) for _ in range(5))
         d_gate = z(gate_logit) if gate_logit is not None else None
-        d_ow = z(order_w) if order_w is not None else None
-        d_ob = z(order_b) if order_b is not None else None
-        d_dw = z(dist_w) if dist_w is not None else None
-        d_db = z(dist_b) if dist_b is not None else None
-        d_sc = z(scalar) if scalar is not None else None
-        d_rr = z(rich_ratio) if rich_ratio is not None else None
+        (b_ow, b_ob, b_dw, b_db, b_sc, b_rr), (d_ow, d_ob, d_dw, d_db, d_sc, d_rr) = _param_grad_buffers(
+            [order_w, order_b, dist_w, dist_b, scalar, rich_ratio])
         d_sb = z(s_bias)
         LIB.call('acsr_attn_calib_ti_bwd', _p(d_att), _p(d_cal), _p(d_pen), _p(d_pa), _p(d_pc), _p(s_bias), _p(mq), _p(mk),
                  _p(mv), _p(aq), _p(ak), _p(gate_logit), _p(key_ids, torch.int64), _p(order_w), _p(order_b), _p(dist_w),
                  _p(dist_b), _p(scalar), B, L, H, dh, opts.two_level, opts.combine, comb_scalar, opts.rich, _p(rich_ratio),
                  p_attn, _p(D1), _p(D2), _p(D3), _p(noise), rng.ptr if rng is not None else None, rng_stream,
-                 _p(d_mq), _p(d_mk), _p(d_mv), _p(d_aq), _p(d_ak), _p(d_gate), _p(d_ow), _p(d_ob), _p(d_dw), _p(d_db),
-                 _p(d_sc), _p(d_rr), _p(d_sb), _stream())
+                 _p(d_mq), _p(d_mk), _p(d_mv), _p(d_aq), _p(d_ak), _p(d_gate), _p(b_ow), _p(b_ob), _p(b_dw), _p(b_db),
+                 _p(b_sc), _p(b_rr), _p(d_sb), _stream())
         return (d_sb, d_mq, d_mk, d_mv, d_aq, d_ak, d_gate, None, d_ow, d_ob, d_dw, d_db, d_sc, d_rr,
                 None, None, None, None, None, None, None)
 
@@ -518,6 +558,16 @@ def linear_tok_bdrl(X, rows, K, W, bias, res, res_rows, ln_w, ln_b, eps, p, mask
              float(eps), float(p), _p(mask), rngp, int(rng_stream), _p(HZ), _p(out), _p(stats), passes, _stream())
 
 
+def _linear_grad_buffers(weight, bias):
+    """(dW, db) destinations of a weight-gradient problem: both always exist (the kernel writes both), in place when possible"""
+    sw, sb = _grad_sink(weight), (_grad_sink(bias) if bias is not None else None)
+    if sw is not None and (bias is None or sb is not None):
+        return (sw, sb), (None, None)
+    dW = torch.zeros(weight.shape, dtype=torch.float32, device=weight.device)
+    db = torch.zeros(bias.shape, dtype=torch.float32, device=weight.device) if bias is not None else None
+    return (dW, db), (dW, db)
+
+
 class LinearFn(torch.autograd.Function):
     """y = x.W^T (+ b) -- every nn.Linear of the API-compatible (autograd) path.  Forward, dX and dW/db all run on the
     K-streamed tcgen05 kernel (acsr_gemm_batch, 3xTF32): no library GEMM."""
@@ -554,9 +604,8 @@ class LinearFn(torch.autograd.Function):
             x2 = x.reshape(-1, K)
             if not x2.is_contiguous():
                 x2 = x2.contiguous()
-            dW = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
-            db = torch.zeros(N, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
-            gemm_batch([wgrad_problem(dy2, x2, rows, N, K, dW, db)])
+            (bW, bb), (dW, db) = _linear_grad_buffers(weight, ctx.bias_ref)
+            gemm_batch([wgrad_problem(dy2, x2, rows, N, K, bW, bb)])
         return dx, dW, db
 
 
@@ -574,12 +623,13 @@ class MultiLinearFn(torch.autograd.Function):
     def forward(ctx, n, *args):
         xs, ws, bs = args[:n], args[n:2 * n], args[2 * n:3 * n]
         ctx.set_materialize_grads(False)
-        x2s, ys, pr = [], [], []
+        x2s, ys, pr, keep = [], [], [], []
         for x, w, b in zip(xs, ws, bs):
             N, K = w.shape
             x2 = x.reshape(-1, K)
             x2 = x2 if x2.is_contiguous() else x2.contiguous()
             w = w if w.is_contiguous() else w.contiguous()
+            keep.append(w)
             y = torch.empty((x2.shape[0], N), dtype=torch.float32, device=x.device)
             pr.append(gemm_problem(x2, w, y, x2.shape[0], N, K, bias=b))
             x2s.append(x2)
@@ -596,6 +646,7 @@ class MultiLinearFn(torch.autograd.Function):
         x2s, ws = saved[:n], saved[n:]
         dxs, dWs, dbs = [None] * n, [None] * n, [None] * n
         pr_x, pr_w = [], []
+        keep = []          # every operand of a problem stays referenced until its launch (a freed temporary could be handed out again)
         for i, dy in enumerate(dys):
             if dy is None:
                 continue
@@ -603,20 +654,23 @@ class MultiLinearFn(torch.autograd.Function):
             N, K = w.shape
             dy2 = dy.reshape(-1, N)
             dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
+            keep.append(dy2)
             rows = dy2.shape[0]
             if ctx.needs_input_grad[1 + i]:
                 wc = w if w.is_contiguous() else w.contiguous()
+                keep.append(wc)
                 dx = torch.empty((rows, K), dtype=torch.float32, device=dy.device)
                 pr_x.append(gemm_problem(dy2, wc, dx, rows, K, N, b_strides=(1, K, 0, N)))
                 dxs[i] = dx.view(ctx.x_shapes[i])
             if (ctx.needs_input_grad[1 + n + i] and _wants_grad(w)) or (b is not None and ctx.needs_input_grad[1 + 2 * n + i] and _wants_grad(b)):
-                dWs[i] = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
-                dbs[i] = torch.zeros(N, dtype=torch.float32, device=dy.device) if b is not None else None
-                pr_w.append(wgrad_problem(dy2, x2s[i], rows, N, K, dWs[i], dbs[i]))
+                (bW, bb), (dWs[i], dbs[i]) = _linear_grad_buffers(w, b)
+                keep += [bW, bb]
+                pr_w.append(wgrad_problem(dy2, x2s[i], rows, N, K, bW, bb))
         if pr_x:
             gemm_batch(pr_x)
         if pr_w:
             gemm_batch(pr_w)
+        del keep
         return (None, *dxs, *dWs, *dbs)
 
 

@@ -9,6 +9,7 @@ both routed backward passes -> Adam) is captured once in a CUDA graph and replay
 noise streams advanced on the device; evaluation uses the fused logits+top-k kernel, so neither
 the [B,V] scores nor the [B,V] int pos_matrix of the reference exist.
 """
+import contextlib
 import os
 import time
 from logging import getLogger
@@ -245,11 +246,13 @@ class ACSASRecTrainer(object):
             return attacked_loss.detach(), calibrated_loss.detach()
         self.optimizer.zero_grad()
         attacked_loss, calibrated_loss = self.model.calculate_loss(interaction)
-        self._route(attack=False)
-        calibrated_loss.backward(retain_graph=True)
-        if attacked_loss is not None:
-            self._route(attack=True)
-            attacked_loss.backward()
+        # parameter gradients go straight into the optimizer's gradient buffer (ops.direct_param_grads)
+        with (ops.direct_param_grads() if isinstance(self.optimizer, FlatAdam) else contextlib.nullcontext()):
+            self._route(attack=False)
+            calibrated_loss.backward(retain_graph=True)
+            if attacked_loss is not None:
+                self._route(attack=True)
+                attacked_loss.backward()
         for p in self.model.parameters():
             p.requires_grad = True
         if self.dp_world > 1:               # batch data-parallel: average the flat gradient over ranks (NCCL / NVLink)

@@ -874,3 +874,35 @@ def test_sibling_graphed_step_matches_eager(A, tmp_path, name):
     assert abs(la_g - la_e) < 1e-4 * abs(la_e) and abs(lc_g - lc_e) < 1e-4 * abs(lc_e)
     for n in pe:
         assert float((pg[n] - pe[n]).abs().max()) < 2e-5, n
+
+
+@pytest.mark.parametrize('name', ['ACSSEPT', 'ACTiSASRec', 'ACSASRec'])
+def test_direct_param_grads_equal_autograd_accumulation(A, tmp_path, name, monkeypatch):
+    """the trainer's autograd step lets the backward kernels accumulate parameter gradients straight into the flat gradient buffer
+    (ops.direct_param_grads) and skips gradients the routed double backward would drop; the flat gradient and the parameters after
+    two steps equal those of plain autograd accumulation"""
+    import contextlib
+    cfg = O.default_cfg(n_layers=2)
+    cfg.update(time_span=64, TIME_FIELD='timestamp', user_hidden_size=32, item_hidden_size=32)
+    V, B = 300, 32
+    finals = []
+    for direct in (True, False):
+        if not direct:
+            monkeypatch.setattr(A.ops, 'direct_param_grads', contextlib.nullcontext)
+            monkeypatch.setattr(A.ops, '_wants_grad', lambda t: t is not None)
+        config = make_config(A, cfg, checkpoint_dir=str(tmp_path), train_batch_size=B, eval_batch_size=B, cuda_graph=False, fused_step=False)
+        config['model'] = name
+        ds = A.data.SyntheticSequentialDataset(config, B, V, seed=4)
+        torch.manual_seed(3)
+        model = getattr(A, name)(config, ds).to('cuda')
+        trainer = getattr(A, name + 'Trainer')(config, model)
+        assert trainer.fused is None
+        model.train()
+        batch = A.Interaction({k: v.cuda() for k, v in ds.inter_feat.interaction.items()})
+        for _ in range(2):
+            la, lc = trainer.train_step(batch)
+        finals.append((float(la), float(lc), trainer.optimizer.flat_grad.clone(), trainer.optimizer.flat_param.clone()))
+    (la1, lc1, g1, p1), (la0, lc0, g0, p0) = finals
+    assert abs(la1 - la0) < 1e-5 * abs(la0) and abs(lc1 - lc0) < 1e-5 * abs(lc0)
+    assert float((g1 - g0).abs().max()) <= 2e-5 * float(g0.abs().max())
+    assert float((p1 - p0).abs().max()) < 5e-6
