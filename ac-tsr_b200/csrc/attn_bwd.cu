@@ -288,6 +288,7 @@ int acsr_attn_calib_bwd(const float* d_ctx_att, const float* d_ctx_cal, const fl
   p.t0 = d_ctx_cal; p.t1 = d_ctx_att; p.t1_is_att = 1; p.d_pen0 = d_pen_sq;
   p.d_mq = d_mq; p.d_mk = d_mk; p.d_mv = d_mv; p.d_aq = d_aq; p.d_ak = d_ak; p.d_gate = d_gate_logit;
   p.d_ow = d_order_w; p.d_ob = d_order_b; p.d_dw = d_dist_w; p.d_db = d_dist_b; p.d_scalar = d_scalar; p.d_ratio = d_rich_ratio;
+  plain_range(p, d_ctx_att != nullptr);
   int rc = attn_validate(p, "attn_calib_bwd");
   if (rc) return rc;
   ACSR_REQUIRE(d_mq && d_mk && d_mv && d_aq && d_ak, "attn_calib_bwd: NULL output");
@@ -315,6 +316,7 @@ int acsr_attn_calib_ti_bwd(const float* d_ctx_att, const float* d_ctx_cal, const
   p.s_bias = s_bias; p.dprob_att = d_prob_att; p.dprob_cal = d_prob_cal; p.d_s_bias = d_s_bias;
   p.d_mq = d_mq; p.d_mk = d_mk; p.d_mv = d_mv; p.d_aq = d_aq; p.d_ak = d_ak; p.d_gate = d_gate_logit;
   p.d_ow = d_order_w; p.d_ob = d_order_b; p.d_dw = d_dist_w; p.d_db = d_dist_b; p.d_scalar = d_scalar; p.d_ratio = d_rich_ratio;
+  plain_range(p, d_ctx_att != nullptr || d_prob_att != nullptr);
   int rc = attn_validate(p, "attn_calib_ti_bwd");
   if (rc) return rc;
   ACSR_REQUIRE(d_mq && d_mk && d_mv && d_aq && d_ak, "attn_calib_ti_bwd: NULL output");
@@ -341,6 +343,7 @@ int acsr_attn_calib_bwd2(const float* d_ctx_cal0, const float* d_pen_sq0, const 
   p.s1_td = (long long)B * L * H * dh; p.s1_ll = (long long)B * L * L;
   p.d_mq = d_mq; p.d_mk = d_mk; p.d_mv = d_mv; p.d_aq = d_aq; p.d_ak = d_ak; p.d_gate = d_gate_logit;
   p.d_ow = d_order_w; p.d_ob = d_order_b; p.d_dw = d_dist_w; p.d_db = d_dist_b; p.d_scalar = d_scalar; p.d_ratio = d_rich_ratio;
+  plain_range(p, d_ctx_att1 != nullptr);
   int rc = attn_validate(p, "attn_calib_bwd2");
   if (rc) return rc;
   ACSR_REQUIRE(d_mq && d_mk && d_mv && d_aq && d_ak, "attn_calib_bwd2: NULL output");

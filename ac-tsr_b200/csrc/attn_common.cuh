@@ -271,7 +271,7 @@ __device__ __forceinline__ int stage_common(const AttnParams& p, const AttnSmem&
   const unsigned m0 = (unsigned)sm.misc[0], m1 = (unsigned)sm.misc[1];
   int nkey = m1 ? 64 - __clz(m1) : (m0 ? 32 - __clz(m0) : 0);
   nkey = max(nkey, 1);
-  if (p.plain) nkey = L;       // masked keys keep a weight (the attack noise): every key row is staged
+  if (p.plain && p.full) nkey = L;       // masked keys keep a weight (the attack noise): every key row is staged
   const int nkp = (nkey + 3) & ~3;
   stage_tile<DH>(sm.K, p.mk, b, h, L, p.d, nkey, nkp);
   stage_tile<DH>(sm.V, p.mv, b, h, L, p.d, nkey, nkp);
@@ -624,7 +624,7 @@ static inline int attn_validate(const AttnParams& p, const char* who) {
   ACSR_REQUIRE(p.mq && p.mk && p.mv && p.aq && p.ak && p.item_seq, "%s: NULL input", who);
   ACSR_REQUIRE(p.B > 0 && p.H > 0, "%s: bad B/H", who);
   if (p.L < 1 || p.L > 256) { set_error("%s: L=%d unsupported (1..256)", who, p.L); return ACSR_ERR_UNSUPPORTED; }
-  if (p.full && p.L > 64) { set_error("%s: the bidirectional mask / the transformer_layers variant are implemented for L <= 64 (L=%d)", who, p.L); return ACSR_ERR_UNSUPPORTED; }
+  if ((p.full || p.plain) && p.L > 64) { set_error("%s: the bidirectional mask / the transformer_layers variant are implemented for L <= 64 (L=%d)", who, p.L); return ACSR_ERR_UNSUPPORTED; }
   if (!(p.dh == 8 || p.dh == 16 || p.dh == 32 || p.dh == 64)) {
     set_error("%s: head size %d unsupported (8/16/32/64)", who, p.dh);
     return ACSR_ERR_UNSUPPORTED;
@@ -639,6 +639,14 @@ static inline int attn_validate(const AttnParams& p, const char* who) {
   ACSR_REQUIRE(!(p.p > 0.f && p.D1 == nullptr && p.rng == nullptr), "%s: p>0 needs explicit masks or rng", who);
   ACSR_REQUIRE((p.D1 == nullptr) == (p.D3 == nullptr), "%s: D1/D3 must be given together", who);
   return ACSR_OK;
+}
+
+// The plain variant needs every key of a row only because of the ATTACKED weights (bare noise on masked keys) and of the
+// unmasked softmax of combine_option fixed.  A call without the attacked stream (evaluation, non-final layers, the calibrated
+// pass of the routed backward) and with gate / annealing has origin = calibrated = combined = 0 on every masked key, so the
+// exact causal work skipping of the layers.py kernels applies to it as well.
+static inline void plain_range(AttnParams& p, bool attacked_stream) {
+  if (p.plain && !p.bidir && !attacked_stream && p.combine != ACSR_ATTN_COMBINE_FIXED) p.full = 0;
 }
 
 // attn_long.cu: 64 < L <= 256 (key-side tiles resident, query rows streamed, backward matrices in a global workspace)

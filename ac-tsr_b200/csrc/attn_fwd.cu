@@ -140,6 +140,7 @@ extern "C" int acsr_attn_calib_fwd(const float* mq, const float* mk, const float
   attn_fill_common(p, mq, mk, mv, aq, ak, gate_logit, item_seq, order_w, order_b, dist_w, dist_b, scalar, B, L, H, dh, two_level,
                    combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, order, ctx_rows);
   p.ctx_att = ctx_att; p.ctx_cal = ctx_cal; p.pen_sq = pen_sq; p.probs = probs_out;
+  plain_range(p, ctx_att != nullptr || probs_out != nullptr);
   int rc = attn_validate(p, "attn_calib_fwd");
   if (rc) return rc;
   ACSR_REQUIRE(ctx_cal != nullptr, "attn_calib_fwd: ctx_cal is NULL");
@@ -168,6 +169,7 @@ extern "C" int acsr_attn_calib_ti_fwd(const float* s_bias, const float* mq, cons
                    combine_option, comb_scalar, rich_mode, rich_ratio, p_attn, D1, D2, D3, noise, rng, rng_stream, nullptr, nullptr);
   p.ctx_att = ctx_att; p.ctx_cal = ctx_cal; p.pen_sq = pen_sq; p.probs = nullptr;
   p.s_bias = s_bias; p.prob_att_out = prob_att; p.prob_cal_out = prob_cal;
+  plain_range(p, ctx_att != nullptr);       // without the attacked stream only the keys in play are written to prob_cal (caller zero-fills)
   int rc = attn_validate(p, "attn_calib_ti_fwd");
   if (rc) return rc;
   ACSR_REQUIRE(ctx_cal != nullptr && prob_cal != nullptr, "attn_calib_ti_fwd: ctx_cal / prob_cal is NULL");

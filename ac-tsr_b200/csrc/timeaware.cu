@@ -13,7 +13,7 @@
 //     pair_wgrad    dP[j,c] += sum_{b,i} a[b,h,i,j] * v[b,i,c] * Dp[b,j,c] ;  dT[t,c] += sum_{t_ij = t} a_ij * v[b,i,c] * Dt[b,i,j,c]
 // (row 0 of both tables is nn.Embedding's padding_idx and gets no gradient, actisasrec.py:55-58).  One CTA works on one
 // sequence; x / P.Dp / p / t tiles sit in shared memory, T rows (<= 257 x d floats) are read through L1/L2, and pair_wgrad
-// accumulates the table gradients in shared memory when they fit and flushes them once per CTA.
+// accumulates the interval-table gradient in shared memory when it fits and flushes it once per CTA.
 #include "acsr_common.cuh"
 #include "../../include/acsr.h"
 
@@ -138,12 +138,10 @@ __global__ void __launch_bounds__(kPairThreads) pair_wgrad_kernel(const PairSpec
   float* Vs = sm;                                        // [L][d+4]
   float* As = Vs + L * dp;                               // [H][L][L]
   int* Ts = reinterpret_cast<int*>(As + H * L * L);      // [L][L]
-  float* accP = reinterpret_cast<float*>(Ts + L * L);    // [L][d]
-  float* accT = acc_in_smem ? accP + L * d : dT;         // [span1][d]
+  float* accT = acc_in_smem ? reinterpret_cast<float*>(Ts + L * L) : dT;      // [span1][d]
   const float inv_keep = s.p > 0.f ? 1.0f / (1.0f - s.p) : 1.0f;
   unsigned long long seed = 0, step = 0;
   if (s.rng != nullptr) { seed = s.rng->seed; step = s.rng->step; }
-  for (int e = threadIdx.x; e < L * d; e += blockDim.x) accP[e] = 0.f;
   if (acc_in_smem) for (int e = threadIdx.x; e < s.span1 * d; e += blockDim.x) accT[e] = 0.f;
   for (int b = blockIdx.x; b < s.B; b += gridDim.x) {
     __syncthreads();
@@ -174,13 +172,15 @@ __global__ void __launch_bounds__(kPairThreads) pair_wgrad_kernel(const PairSpec
       }
       if (j != 0) {                                      // position 0 is the padding_idx row of the position tables
         const float4 m = mult4(s, s.Dp, s.stream_p, (long long)b * L + j, c, inv_keep, seed, step);
-        float* dst = accP + j * d + c;                   // this thread owns (j, c..c+3) of accP
-        dst[0] += sp.x * m.x; dst[1] += sp.y * m.y; dst[2] += sp.z * m.z; dst[3] += sp.w * m.w;
+        float* dst = dP + j * d + c;                     // L*d reductions per sequence: straight to global
+        if (sp.x * m.x != 0.f) atomicAdd(dst + 0, sp.x * m.x);
+        if (sp.y * m.y != 0.f) atomicAdd(dst + 1, sp.y * m.y);
+        if (sp.z * m.z != 0.f) atomicAdd(dst + 2, sp.z * m.z);
+        if (sp.w * m.w != 0.f) atomicAdd(dst + 3, sp.w * m.w);
       }
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < L * d; e += blockDim.x) if (accP[e] != 0.f) atomicAdd(dP + e, accP[e]);
   if (acc_in_smem) for (int e = threadIdx.x; e < s.span1 * d; e += blockDim.x) if (accT[e] != 0.f) atomicAdd(dT + e, accT[e]);
 }
 
@@ -208,6 +208,7 @@ template <typename K>
 static int pair_prep(K kernel, size_t smem, const char* who) {
   if (smem > 227 * 1024) { set_error("%s: needs %zu bytes of shared memory (> 227 KB)", who, smem); return ACSR_ERR_UNSUPPORTED; }
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) { set_error("%s: smem %zu: %s", who, smem, cudaGetErrorString(e)); return ACSR_ERR_CUDA; }
   return ACSR_OK;
 }
@@ -268,13 +269,13 @@ int acsr_pair_wgrad(const float* a, const float* v, const int32_t* tmat, int B, 
   int rc = pair_validate(s, "pair_wgrad");
   if (rc) return rc;
   ACSR_REQUIRE(a && v && dP && dT, "pair_wgrad: NULL pointer");
-  const size_t base = ((size_t)L * (s.d + 4) + (size_t)H * L * L + (size_t)L * L + (size_t)L * s.d) * sizeof(float);
+  const size_t base = ((size_t)L * (s.d + 4) + (size_t)H * L * L + (size_t)L * L) * sizeof(float);
   const size_t with_t = base + (size_t)span1 * s.d * sizeof(float);
-  const int in_smem = with_t <= 200 * 1024;
+  const int in_smem = with_t <= 200 * 1024;        // (<= 112 KB, the C2 shape: two CTAs share an SM)
   const size_t smem = in_smem ? with_t : base;
   rc = pair_prep(pair_wgrad_kernel, smem, "pair_wgrad");
   if (rc) return rc;
-  pair_wgrad_kernel<<<std::min(B, 2 * 148), kPairThreads, smem, (cudaStream_t)stream>>>(s, a, v, dP, dT, in_smem);
+  pair_wgrad_kernel<<<std::min(B, 4 * 148), kPairThreads, smem, (cudaStream_t)stream>>>(s, a, v, dP, dT, in_smem);
   return check_launch("pair_wgrad");
 }
 

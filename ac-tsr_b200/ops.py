@@ -412,7 +412,8 @@ class AttnCalibTiFn(torch.autograd.Function):
         dev = mq.device
         ctx_cal = torch.empty((B, L, d), dtype=torch.float32, device=dev)
         ctx_att = torch.empty_like(ctx_cal) if need_att else None
-        prob_cal = torch.empty((B, H, L, L), dtype=torch.float32, device=dev)
+        # without the attacked stream (gate / annealing) the kernel only visits the keys in play: the rest of prob_cal is zero
+        prob_cal = (torch.empty if need_att else torch.zeros)((B, H, L, L), dtype=torch.float32, device=dev)
         prob_att = torch.empty_like(prob_cal) if need_att else None
         pen = torch.zeros(1, dtype=torch.float64, device=dev)
         LIB.call('acsr_attn_calib_ti_fwd', _p(s_bias), _p(mq), _p(mk), _p(mv), _p(aq), _p(ak), _p(gate_logit),
