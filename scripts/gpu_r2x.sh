@@ -1,4 +1,4 @@
-N=4
+N=${1:-4}
 mkdir -p gpurun_out
 S=$(date +%s)
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 100 --warmup 10 > gpurun_out/bench_r02_n${N}_full.json 2> gpurun_out/bench_r02_n${N}_full.err; echo "bench rc=$? wall=$(( $(date +%s) - S ))s"
