@@ -325,3 +325,68 @@ def test_sibling_models_keep_reference_state_dicts_and_have_no_cpu_path():
     enc = A.transformer_layers.AttackRTransformerEncoder(n_layers=1, hidden_size=32, inner_size=32, combine_option='gate')
     assert enc.layer[0].gate.out_features == 50 and enc.layer[0].plain_variant
     assert not A.layers.AttackRTransformerEncoder(n_layers=1, hidden_size=32, inner_size=32).layer[0].plain_variant
+
+
+def test_backward_gradient_routing_helpers():
+    """ops._wants_grad / _param_grad_buffers / direct_param_grads (host logic of the autograd path): a leaf whose requires_grad is
+    off at backward time gets no buffer (the reference's routed double backward would drop that gradient, trainer.py:672-686);
+    inside direct_param_grads a leaf that owns a .grad accumulates in place and nothing is returned to autograd; everything else
+    shares one zero-filled block"""
+    ops = A.ops
+    a = torch.nn.Parameter(torch.ones(3, 5))
+    b = torch.nn.Parameter(torch.ones(7))
+    c = torch.ones(4, requires_grad=True) * 2.0            # non-leaf: always wanted
+    a.grad, b.grad = torch.zeros_like(a), torch.zeros_like(b)
+    assert ops._wants_grad(a) and ops._wants_grad(c) and not ops._wants_grad(None)
+    b.requires_grad = False
+    assert not ops._wants_grad(b)
+    bufs, rets = ops._param_grad_buffers([a, b, None, c])
+    assert bufs[1] is None and rets[1] is None and bufs[2] is None
+    assert bufs[0] is rets[0] and bufs[3] is rets[3] and bufs[0].shape == a.shape and bufs[3].shape == c.shape
+    assert float(bufs[0].abs().sum()) == 0.0 and bufs[0].data_ptr() != a.grad.data_ptr()
+    assert bufs[0].untyped_storage().data_ptr() == bufs[3].untyped_storage().data_ptr()       # one shared block
+    assert bufs[3].data_ptr() % 16 == 0                                                        # 4-float aligned slots
+    with ops.direct_param_grads():
+        bufs, rets = ops._param_grad_buffers([a, b, None, c])
+        assert bufs[0] is a.grad and rets[0] is None           # in place, nothing for autograd to add
+        assert bufs[1] is None and bufs[3] is rets[3]
+        (bW, bb), (dW, db) = ops._linear_grad_buffers(a, None)
+        assert bW is a.grad and dW is None and bb is None
+        b.requires_grad = True
+        (bW, bb), (dW, db) = ops._linear_grad_buffers(a, b)
+        assert bW is a.grad and bb is b.grad and dW is None and db is None
+    assert ops._grad_sink(a) is None                           # outside the context gradients go back to autograd
+    (bW, bb), (dW, db) = ops._linear_grad_buffers(a, b)
+    assert bW is dW and bb is db and float(dW.abs().sum()) == 0.0
+
+
+def test_model_fields_and_bert_prepare_batch():
+    """the fields a loader ships per model, and AcBERT4Rec.prepare_batch (the host half of its graphed step) == one
+    reconstruct_train_data call on the same python `random` stream"""
+    import random
+    from ac_tsr_b200.data import _model_fields
+    cfg = cfg_for()
+    assert _model_fields(cfg) == ['item_id_list', 'item_length', 'item_id']
+    cfg['model'] = 'ACSSEPT'
+    assert _model_fields(cfg)[-1] == 'user_id'
+    cfg['model'] = 'ACTiSASRec'
+    cfg['TIME_FIELD'] = 'timestamp'
+    assert _model_fields(cfg)[-1] == 'timestamp_list'
+    ds = A.data.SyntheticSequentialDataset(cfg, 16, 50, seed=3, pin=False)
+    ts = ds.inter_feat['timestamp_list']
+    assert ts.dtype == torch.float32 and bool((ts[ds.inter_feat['item_id_list'] == 0] == 0).all())
+    loader = A.data.TrainDataLoader(cfg, ds, shuffle=False, batch_size=8)
+    batch = next(iter(loader))                                  # a float field: the batch is not packed into the int64 buffer
+    assert batch['timestamp_list'].dtype == torch.float32 and batch['item_id_list'].shape == (8, 50)
+    c = load_case('bert_fixed_train')
+    bcfg = cfg_for(**{k: c['cfg'][k] for k in c['cfg']})
+    model = A.AcBERT4Rec(bcfg, DS(c['V']))
+    b = c['batch']
+    inter = A.Interaction({'item_id_list': b['item_seq'], 'item_length': b['item_len'], 'item_id': b['pos']})
+    random.seed(5)
+    want = model.reconstruct_train_data(b['item_seq'])
+    random.seed(5)
+    prepared = model.prepare_batch(inter)
+    for k, w in zip(model.EXTRA_FIELDS, want):
+        assert torch.equal(prepared[k], w), k
+    assert model.GRAPH_SAFE_STEP and all(k in prepared for k in ('item_id_list', 'item_length', 'item_id'))
