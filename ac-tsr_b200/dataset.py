@@ -298,6 +298,15 @@ def create_dataset(config):
     return SequentialDataset(config)
 
 
+def device_resident_training(config):
+    """HBM-resident training data (data.DeviceTrainDataLoader) is AC-SASRec's: its fused step gathers the batch inside the captured
+    graph.  The sibling models read more fields (user id, time stamps) or prepare the batch on the host (AcBERT4Rec's python
+    masking) and take pinned host batches from TrainDataLoader."""
+    dev = config['device']
+    return (getattr(dev, 'type', str(dev)) == 'cuda' and bool(config.get('device_resident_data', True))
+            and str(config.get('model', 'ACSASRec')) == 'ACSASRec')
+
+
 def data_preparation(config, dataset):
     """data/utils.py:96-150 -> (train_data, valid_data, test_data)"""
     from .data import TrainDataLoader, DeviceTrainDataLoader, FullSortEvalDataLoader
@@ -305,7 +314,5 @@ def data_preparation(config, dataset):
     if (config['eval_args'] or {}).get('mode', 'full') != 'full':
         raise NotImplementedError('eval_args.mode: only full-sort evaluation is on the hot path')
     # training data resident in HBM with the epoch shuffle on the device (f-2) unless `device_resident_data: False`
-    dev = config['device']
-    on_gpu = getattr(dev, 'type', str(dev)) == 'cuda' and config.get('device_resident_data', True)
-    train_loader = DeviceTrainDataLoader(config, train, shuffle=True) if on_gpu else TrainDataLoader(config, train, shuffle=True)
+    train_loader = (DeviceTrainDataLoader if device_resident_training(config) else TrainDataLoader)(config, train, shuffle=True)
     return (train_loader, FullSortEvalDataLoader(config, valid), FullSortEvalDataLoader(config, test))

@@ -390,3 +390,43 @@ def test_model_fields_and_bert_prepare_batch():
     for k, w in zip(model.EXTRA_FIELDS, want):
         assert torch.equal(prepared[k], w), k
     assert model.GRAPH_SAFE_STEP and all(k in prepared for k in ('item_id_list', 'item_length', 'item_id'))
+
+
+@pytest.mark.parametrize('name,yaml_file,fields', [
+    ('ACSSEPT', 'ml-100k-acssept.yaml', ['item_id_list', 'item_length', 'item_id', 'user_id']),
+    ('ACTiSASRec', 'ml-100k-actisasrec.yaml', ['item_id_list', 'item_length', 'item_id', 'timestamp_list']),
+    ('AcBERT4Rec', 'ml-100k-acbert4rec.yaml', ['item_id_list', 'item_length', 'item_id']),
+])
+def test_sibling_run_recbole_pipeline_up_to_the_first_batch(name, yaml_file, fields):
+    """run_recbole.py --model=<sibling> --config_files=config/<yaml>: Config -> dataset -> loaders -> model, everything short of the
+    first kernel (no GPU here): the batches carry the fields the model reads, the models take their sizes from the dataset, and
+    only AC-SASRec trains from the HBM-resident loader"""
+    from ac_tsr_b200.dataset import device_resident_training
+    from ac_tsr_b200.quick_start import get_model, get_trainer
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    config = A.Config(model=name, dataset='ml-100k', config_file_list=[os.path.join(root, 'config', yaml_file)],
+                      config_dict={'data_path': os.path.join(root, 'tests', 'golden') + '/', 'device': torch.device('cpu')})
+    assert config['model'] == name
+    ds = A.create_dataset(config)
+    train, valid, test = A.data_preparation(config, ds)
+    assert type(train).__name__ == 'TrainDataLoader'
+    batch = next(iter(train))
+    for f in fields:
+        assert f in batch and len(batch[f]) == config['train_batch_size'], f
+    ev, hist, pu, pi = next(iter(valid))
+    for f in fields:
+        assert f in ev, f
+    model = get_model(name)(config, train.dataset)
+    assert get_trainer(None, name).__name__ == name + 'Trainer'
+    assert model.n_items == ds.item_num
+    if name == 'ACSSEPT':
+        assert model.n_users == ds.user_num and model.hidden_size == 64
+    if name == 'ACTiSASRec':
+        assert batch['timestamp_list'].dtype == torch.float32 and model.time_matrix_emb_K_embedding.num_embeddings == 257
+    # loader choice on a GPU box
+    config['device'] = torch.device('cuda')
+    assert not device_resident_training(config)
+    config['model'] = 'ACSASRec'
+    assert device_resident_training(config)
+    config['device_resident_data'] = False
+    assert not device_resident_training(config)
