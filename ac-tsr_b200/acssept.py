@@ -10,6 +10,9 @@ term is the fused tcgen05 logits kernel over the item table, the second one numb
 logits of a row alike, so it cancels in the cross entropy, in the BPR difference and in the top-k order; it is added where the
 reference returns raw scores (predict, full_sort_predict).
 
+(The reference only runs with user_hidden_size == item_hidden_size: acssept.py:127 expands the user vector "as" the item
+embeddings.  Any pair of widths works here.)
+
 Trainer: the reference registers no ACSSEPTTrainer (recbole/trainer/trainer.py:1038-1048 lists AttackRSASRec, ACSASRec and
 AcBERT4Rec; utils.py:89-100 then falls back to the stock Trainer, whose evaluation cannot take the tuple full_sort_predict
 returns, trainer.py:397).  ACSSEPTTrainer here is the AC step the model's tuple API is written for (trainer.py:505-1036).

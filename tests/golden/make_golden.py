@@ -478,6 +478,23 @@ TI_CASES = [
     ('ti_gate_eval', 131, 3, 53, False, dict(n_layers=2, hidden_size=32, inner_size=64)),
 ]
 
+# (the reference's ACSSEPT only runs with user_hidden_size == item_hidden_size: acssept.py:127 expands the user vector "as" the item
+# embeddings; the implementation here takes any pair of widths)
+# more configuration branches of the two transformer_layers.py models, used by tests/test_oracle_golden.py ONLY (they pin the
+# oracle restatement; the CUDA path's own branch coverage is the kernel test matrix): file names start with `oracleonly_`
+ORACLE_ONLY_TI = [
+    ('oracleonly_ti_bpr_noorder_train', 101, 3, 61, True, dict(n_layers=1, hidden_size=32, inner_size=64, loss_type='BPR', use_order=False,
+                                                              trainable_mask_loss_weight=True)),
+    ('oracleonly_ti_nodist_onelevel_train', 101, 3, 62, True, dict(n_layers=2, hidden_size=32, inner_size=64, use_distance=False, two_level=False,
+                                                                  rich_calibrated_combine='trainable', time_span=8)),
+]
+ORACLE_ONLY_SSEPT = [
+    ('oracleonly_ssept_noorder_tw_train', 101, 13, 3, 63, True, dict(n_layers=2, n_heads=4, use_order=False, trainable_mask_loss_weight=True,
+                                                                    item_hidden_size=16, user_hidden_size=16)),
+    ('oracleonly_ssept_relu_eval', 101, 13, 3, 64, False, dict(n_layers=1, hidden_act='relu', combine_option='fixed', item_hidden_size=24,
+                                                              user_hidden_size=24)),
+]
+
 SSEPT_CASES = [
     # ACSSEPT.  hidden = item_hidden_size + user_hidden_size
     ('ssept_gate_train', 151, 23, 3, 41, True, dict(n_layers=2)),
@@ -532,11 +549,11 @@ if __name__ == '__main__':
         if only and name not in only:
             continue
         make_bert_case(name, V, B, seed, train, **kw)
-    for name, V, B, seed, train, kw in TI_CASES:
+    for name, V, B, seed, train, kw in TI_CASES + ORACLE_ONLY_TI:
         if only and name not in only:
             continue
         make_ti_case(name, V, B, seed, train, **kw)
-    for name, V, U, B, seed, train, kw in SSEPT_CASES:
+    for name, V, U, B, seed, train, kw in SSEPT_CASES + ORACLE_ONLY_SSEPT:
         if only and name not in only:
             continue
         make_ssept_case(name, V, U, B, seed, train, **kw)

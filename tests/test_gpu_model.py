@@ -14,7 +14,7 @@ from oracle import acsr_oracle as O
 from golden_util import GOLDEN_DIR, load_case
 
 EVERY = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
-ALL = [n for n in EVERY if not n.startswith(('bert_', 'ssept_', 'ti_'))]
+ALL = [n for n in EVERY if not n.startswith(('bert_', 'ssept_', 'ti_', 'oracleonly_'))]      # oracleonly_*: tests/test_oracle_golden.py only
 TI = [n for n in EVERY if n.startswith('ti_')]              # ACTiSASRec cases (actisasrec.py on transformer_layers.py)
 SSEPT = [n for n in EVERY if n.startswith('ssept_')]        # ACSSEPT cases (acssept.py on transformer_layers.py)
 BERT = [n for n in EVERY if n.startswith('bert_')]          # AcBERT4Rec cases (acbert4rec.py)

@@ -10,9 +10,9 @@ from oracle import acsr_oracle as O
 from golden_util import GOLDEN_DIR, load_case
 
 EVERY = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
-ALL = [n for n in EVERY if not n.startswith(('bert_', 'ssept_', 'ti_'))]
-TI = [n for n in EVERY if n.startswith('ti_')]              # ACTiSASRec cases (actisasrec.py on transformer_layers.py)
-SSEPT = [n for n in EVERY if n.startswith('ssept_')]        # ACSSEPT cases (acssept.py on transformer_layers.py)
+ALL = [n for n in EVERY if not n.startswith(('bert_', 'ssept_', 'ti_', 'oracleonly_'))]
+TI = [n for n in EVERY if n.startswith(('ti_', 'oracleonly_ti_'))]              # ACTiSASRec cases (actisasrec.py on transformer_layers.py)
+SSEPT = [n for n in EVERY if n.startswith(('ssept_', 'oracleonly_ssept_'))]      # oracleonly_*: more config branches, pin the oracle only        # ACSSEPT cases (acssept.py on transformer_layers.py)
 BERT = [n for n in EVERY if n.startswith('bert_')]          # AcBERT4Rec cases (acbert4rec.py)
 TRAIN = [n for n in ALL if '_train' in n]
 EVAL = [n for n in ALL if '_eval' in n]
